@@ -1,0 +1,284 @@
+/*
+ * lldba.h — C-ABI of the B200-native point+line bundle-adjustment and descriptor-matching core.
+ *
+ * This is the drop-in boundary for the hot path of LLD-SLAM (reference tree paths below are relative
+ * to the reference repository root).  The reference has no FFI layer: its callers invoke C++ members
+ * directly.  Each entry point here replaces the *body* of one of those members; the thin C++ shim in
+ * lld_slam_b200/host/ keeps the reference's class / method names and flattens the caller's objects
+ * into the plain arrays declared here.
+ *
+ *   lld_ba_local           <- Optimizer::LocalBundleAdjustment      include/Optimizer.h:49,  src/Optimizer.cc:936-1388
+ *                             + LineOptimizer::{AddLineMinimal,DisableOutliers,GetLineData}  include/LineOptimizer.h:13-20
+ *   lld_ba_global          <- Optimizer::BundleAdjustment / GlobalBundleAdjustment           include/Optimizer.h:43-47, src/Optimizer.cc:312-559
+ *   lld_pose_opt           <- Optimizer::PoseOptimization            include/Optimizer.h:50,  src/Optimizer.cc:653-932
+ *   lld_descriptor_distance<- ORBmatcher::DescriptorDistance         include/ORBmatcher.h:51, src/ORBmatcher.cc:1647-1663
+ *   lld_sbp_frame          <- ORBmatcher::SearchByProjection(Frame&,const Frame&,th,bMono)   include/ORBmatcher.h:52, src/ORBmatcher.cc:1328-1470
+ *   lld_sbp_mappoints      <- ORBmatcher::SearchByProjection(Frame&,vector<MapPoint*>&,th)   include/ORBmatcher.h:47, src/ORBmatcher.cc:45-129
+ *   lld_line_match         <- TwoFrameLineMatcher::MatchLines        include/TwoFrameLineMatcher.h:39, src/TwoFrameLineMatcher.cc:26-124
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  All arrays are caller-owned HOST memory, contiguous, little endian.
+ *   - Every problem struct is *batched*: entity arrays of all independent units (BA windows, frames,
+ *     frame pairs) are concatenated and addressed through CSR offset arrays.  A single reference call is
+ *     the batch-of-one case.
+ *   - Return value: 0 = ok; <0 = error (LLD_ERR_*).  Nothing throws.  On error the outputs are undefined.
+ *   - A context owns one CUDA stream plus its device workspace.  Contexts are not shared between threads;
+ *     the reference enters this path from three threads concurrently (Tracking, LocalMapping, GBA), so a
+ *     caller creates one context per calling thread.
+ *   - There is no CPU fallback: every compute entry point fails with LLD_ERR_CUDA when no device is usable.
+ *   - Precision contract of the reference (src/Converter.cc:37-47,110-116): map state arrives float-valued,
+ *     is widened to double, optimised in double and narrowed by the caller.  Arrays typed `double` below
+ *     carry such widened values; arrays typed `float` are values the reference itself keeps as float.
+ */
+#ifndef LLDBA_H
+#define LLDBA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLD_OK 0
+#define LLD_ERR_CUDA (-1)
+#define LLD_ERR_ARG (-2)
+#define LLD_ERR_NCCL (-3)
+#define LLD_ERR_UNSUPPORTED (-4)
+
+/* ------------------------------------------------------------------------------------------------
+ * Bundle adjustment (local windows and global map)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* One batch of independent BA problems ("windows").  Entities of window w live at
+ * [kf_off[w], kf_off[w+1]) etc.; KF indices stored in observations are window-local.
+ * Observations are grouped by landmark in the reference's insertion order
+ * (src/Optimizer.cc:1093-1178 for points, :1182-1218 / src/LineOptimizer.cc:59-125 for lines). */
+typedef struct lld_ba_problem {
+  int32_t n_win;
+  const int32_t* kf_off; /* [n_win+1] */
+  const int32_t* pt_off; /* [n_win+1] */
+  const int32_t* ln_off; /* [n_win+1] */
+
+  /* keyframes */
+  const double* kf_Tcw;     /* [n_kf][12]  R row-major (9) then t (3): world->camera, as Converter::toSE3Quat receives it */
+  const uint8_t* kf_fixed;  /* [n_kf]      vSE3->setFixed(...)  src/Optimizer.cc:1043,1057 */
+  const double* kf_intr;    /* [n_kf][5]   fx fy cx cy bf used by point edges */
+  const double* kf_line_cam;/* [n_kf][4]   f cx cy baseline used by line edges observed from this KF.
+                               LocalBA: the *current* KF's values for every KF (src/Optimizer.cc:1211-1215);
+                               GBA: each KF's own (src/Optimizer.cc:200-210). */
+
+  /* map points */
+  const double* pt_xyz;       /* [n_pt][3] */
+  const int32_t* pt_obs_off;  /* [n_pt+1]  CSR into the point observation arrays */
+  const int32_t* pt_obs_kf;   /* [n_pt_obs] window-local KF index */
+  const float* pt_obs_uvr;    /* [n_pt_obs][3] u v uR ; uR<0 => monocular edge (src/Optimizer.cc:1119) */
+  const float* pt_obs_info;   /* [n_pt_obs]  invSigma2 (float in the reference, src/Optimizer.cc:1129) */
+
+  /* map lines, minimal (X0, dir) parametrisation of MapLine::GetMinimalPos */
+  const double* ln_x0_dir;    /* [n_ln][6]  X0 (closest point to origin), unit direction */
+  const int32_t* ln_obs_off;  /* [n_ln+1]   CSR; one entry per (line, KF) = one proj_map element */
+  const int32_t* ln_obs_kf;   /* [n_ln_obs] */
+  const float* ln_obs_left;   /* [n_ln_obs][4] xs ys xe ye of the left KeyLine (pixels) */
+  const float* ln_obs_right;  /* [n_ln_obs][4] right KeyLine, xs<0 => no right edge (src/LineOptimizer.cc:65-68) */
+  const double* ln_obs_info;  /* [n_ln_obs][2] information of the left / right edge (gamma^2 / 1.44^(2*octave); 1 in GBA) */
+  const uint8_t* ln_obs_stereo;/* [n_ln_obs] 1: Huber delta / chi2 gate = stereo value, 0: mono value (src/LineOptimizer.cc:83-88) */
+
+  /* constants of the entry point */
+  int32_t robust_points;      /* Huber on point edges (LocalBA: 1; GBA: bRobust) */
+  double delta_pt_mono;       /* (double)(float)sqrt(5.991) */
+  double delta_pt_stereo;     /* (double)(float)sqrt(7.815) */
+  double delta_ln_mono;       /* gamma-scaled, src/LineOptimizer.cc:33-36 */
+  double delta_ln_stereo;
+  double chi2_pt_mono;        /* 5.991 outlier gate, src/Optimizer.cc:1246 */
+  double chi2_pt_stereo;      /* 7.815 */
+  int32_t ln_endpoints_normalized; /* 0: pixel endpoints used as homogeneous (x,y,1) (LocalBA, src/LineOptimizer.cc:106-113);
+                                      1: K^-1 * (x,y,1) with the KF's fx fy cx cy (GBA, src/Optimizer.cc:234-235) */
+  int32_t ln_filter;          /* 4: line dropped after round 1 when 2*(#inlier edges) <= ln_filter (include/LineOptimizer.h:23) */
+} lld_ba_problem;
+
+typedef struct lld_ba_result {
+  double* kf_Tcw;        /* [n_kf][12]   optimised poses (fixed KFs: re-orthonormalised input, as toCvMat(SE3Quat) gives) */
+  double* pt_xyz;        /* [n_pt][3] */
+  double* ln_x0_dir;     /* [n_ln][6]    GetLineData / GBA read-back: X0 = alpha*R[:,1], dir = R[:,0] */
+  uint8_t* pt_obs_bad;   /* [n_pt_obs]   1 => (KF,point) goes to vToErase (src/Optimizer.cc:1281-1311); zero in GBA */
+  uint8_t* ln_obs_bad;   /* [n_ln_obs][2] 1 => GetLineData lists this edge's KF as outlier projection */
+  uint8_t* ln_removed;   /* [n_ln]       1 => line vertex removed by DisableOutliers, GetLineData returns false */
+  /* LM trace, [n_win][log_stride]: entry 0 = initial robust chi2, entry k = chi2 after outer iteration k.
+   * Round 2 of LocalBA is appended after round 1.  n_iter_done[w][r] = outer iterations executed in round r. */
+  int32_t log_stride;
+  double* chi2_log;      /* may be NULL */
+  double* lambda_log;    /* may be NULL */
+  int32_t* trials_log;   /* may be NULL */
+  int32_t* n_iter_done;  /* [n_win][2], may be NULL */
+} lld_ba_result;
+
+int lld_ctx_create(int device, void** ctx);
+void lld_ctx_destroy(void* ctx);
+/* last CUDA / NCCL error text of this context (static storage inside ctx) */
+const char* lld_ctx_last_error(void* ctx);
+
+/* Multi-GPU: join an NCCL communicator created from `unique_id` (128 bytes from lld_comm_unique_id on rank 0,
+ * distributed by the caller, e.g. torch.distributed broadcast).  Needed only by lld_ba_global with n_ranks>1. */
+int lld_comm_unique_id(uint8_t id_out[128]);
+int lld_comm_init(void* ctx, int n_ranks, int rank, const uint8_t unique_id[128]);
+
+/* LocalBundleAdjustment: its_round1 (5) LM iterations with Huber, outlier gating, its_round2 (15) without.
+ * stop_flag mirrors pbStopFlag (src/Optimizer.cc:1220-1236): polled on the host between LM steps. */
+int lld_ba_local(void* ctx, const lld_ba_problem* p, int its_round1, int its_round2,
+                 const volatile uint8_t* stop_flag, lld_ba_result* out);
+
+/* BundleAdjustment: one optimize(n_iter) pass, no outlier round.
+ * With a communicator of n_ranks>1 each rank passes its own landmark shard (all KFs replicated,
+ * identical order); the reduced camera system and chi2 are all-reduced over NCCL. */
+int lld_ba_global(void* ctx, const lld_ba_problem* p, int n_iter, const volatile uint8_t* stop_flag,
+                  lld_ba_result* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Motion-only pose optimisation (batched frames)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct lld_pose_problem {
+  int32_t n_frames;
+  const double* Tcw;        /* [n_frames][12] initial pose (pFrame->mTcw widened) */
+  const double* intr;       /* [n_frames][5]  fx fy cx cy bf */
+  const double* line_cam;   /* [n_frames][4]  f(=fx) cx cy baseline(=mbf/fx as float)  src/Optimizer.cc:600-631 */
+  const int32_t* pt_off;    /* [n_frames+1] */
+  const float* pt_xw;       /* [n_pt][3]  MapPoint world position (float, src/Optimizer.cc:745-748) */
+  const float* pt_uvr;      /* [n_pt][3]  uR<0 => mono */
+  const float* pt_info;     /* [n_pt] */
+  const int32_t* ln_off;    /* [n_frames+1] one entry per frame line with a MapLine */
+  const double* ln_x0_dir;  /* [n_ln][6] */
+  const float* ln_left;     /* [n_ln][4] */
+  const float* ln_right;    /* [n_ln][4] xs<0 => no right edge */
+  const double* ln_info;    /* [n_ln][2] */
+  const uint8_t* ln_stereo; /* [n_ln]    Huber delta selector (line_matches[i]>=0) */
+  const uint8_t* ln_gate_stereo; /* [n_ln][2] chi2-gate selector per edge: the reference indexes vnStereoLines by the
+                                    frame line id, not the edge id (src/Optimizer.cc:894-898); the shim reproduces that */
+  double delta_mono, delta_stereo;        /* (double)(float)sqrt(5.991|7.815) */
+  double delta_ln_mono, delta_ln_stereo;  /* (double)(float)(delta*gamma) */
+  float chi2_mono, chi2_stereo;           /* 5.991f 7.815f */
+  double gate_ln_mono, gate_ln_stereo;    /* (double)(deltaLines*deltaLines as float) */
+  int32_t n_rounds;  /* 4 */
+  int32_t its;       /* 10 */
+} lld_pose_problem;
+
+typedef struct lld_pose_result {
+  double* Tcw;           /* [n_frames][12] */
+  uint8_t* pt_outlier;   /* [n_pt]  pFrame->mvbOutlier */
+  uint8_t* ln_outlier;   /* [n_ln]  pFrame->mvbOutlierLines (last edge of the line wins, as in the reference) */
+  int32_t* n_inliers;    /* [n_frames] return value nInitialCorrespondences - nBad (0 when <3 correspondences) */
+  double* chi2_final;    /* [n_frames] robust chi2 after the last LM iteration of the last round; may be NULL */
+} lld_pose_result;
+
+int lld_pose_opt(void* ctx, const lld_pose_problem* p, lld_pose_result* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * ORB descriptor matching
+ * ---------------------------------------------------------------------------------------------- */
+/* host inline popcount distance, identical to ORBmatcher::DescriptorDistance */
+int lld_descriptor_distance(const uint8_t a[32], const uint8_t b[32]);
+
+/* Frame grid parameters shared by both SearchByProjection variants (src/Frame.cc:391-456, include/Frame.h:43-44) */
+typedef struct lld_frame_geom {
+  float fx, fy, cx, cy, bf, b; /* b = mb, stereo baseline in metres (forward/backward test) */
+  float min_x, max_x, min_y, max_y; /* mnMinX ... image bounds after undistortion */
+  int32_t n_levels;
+  const float* scale_factors; /* [n_levels] mvScaleFactors */
+} lld_frame_geom;
+
+/* SearchByProjection(CurrentFrame, LastFrame, th, bMono), batched over frame pairs. */
+typedef struct lld_sbp_frame_problem {
+  int32_t n_pairs;
+  lld_frame_geom geom;
+  float th;
+  int32_t mono;              /* bMono */
+  int32_t check_orientation; /* mbCheckOrientation */
+  /* current frames */
+  const int32_t* cur_off;    /* [n_pairs+1] */
+  const float* cur_xy;       /* [n_cur][2] mvKeysUn[i].pt */
+  const uint8_t* cur_octave; /* [n_cur] */
+  const float* cur_angle;    /* [n_cur] */
+  const float* cur_uright;   /* [n_cur] */
+  const uint8_t* cur_desc;   /* [n_cur][32] */
+  const uint8_t* cur_claimed;/* [n_cur] mvpMapPoints[i] && Observations()>0 on entry */
+  const float* cur_Tcw;      /* [n_pairs][12] float */
+  const float* last_Tcw;     /* [n_pairs][12] float */
+  /* last frames */
+  const int32_t* last_off;   /* [n_pairs+1] */
+  const uint8_t* last_valid; /* [n_last] mvpMapPoints[i] && !mvbOutlier[i] */
+  const float* last_xw;      /* [n_last][3] pMP->GetWorldPos() */
+  const uint8_t* last_octave;/* [n_last] mvKeys[i].octave */
+  const float* last_angle;   /* [n_last] mvKeysUn[i].angle */
+  const uint8_t* last_desc;  /* [n_last][32] pMP->GetDescriptor() */
+  const uint8_t* last_has_obs;/* [n_last] pMP->Observations()>0 : a kp claimed by this point blocks later points */
+} lld_sbp_frame_problem;
+
+typedef struct lld_sbp_result {
+  int32_t* match;      /* [n_cur]  index (pair-local) of the matched last/map point, -1 = none; = CurrentFrame.mvpMapPoints after the call */
+  int32_t* n_matches;  /* [n_pairs] return value */
+  int32_t* best_idx;   /* [n_last] best current kp found for each query before the orientation filter, -1 = none; may be NULL */
+  int32_t* best_dist;  /* [n_last] its Hamming distance (256 when none); may be NULL */
+} lld_sbp_result;
+
+int lld_sbp_frame(void* ctx, const lld_sbp_frame_problem* p, lld_sbp_result* out);
+
+/* SearchByProjection(Frame& F, const vector<MapPoint*>&, th), batched over (frame, local-map) pairs. */
+typedef struct lld_sbp_mp_problem {
+  int32_t n_pairs;
+  lld_frame_geom geom;
+  float th;
+  float nn_ratio;            /* mfNNratio */
+  const int32_t* cur_off;    /* frame keypoints, as above */
+  const float* cur_xy;
+  const uint8_t* cur_octave;
+  const float* cur_uright;
+  const uint8_t* cur_desc;
+  const uint8_t* cur_claimed;
+  const int32_t* mp_off;     /* [n_pairs+1] */
+  const uint8_t* mp_valid;   /* [n_mp] mbTrackInView && !isBad() */
+  const float* mp_proj;      /* [n_mp][3] mTrackProjX, mTrackProjY, mTrackProjXR */
+  const int32_t* mp_level;   /* [n_mp] mnTrackScaleLevel */
+  const float* mp_viewcos;   /* [n_mp] mTrackViewCos */
+  const uint8_t* mp_desc;    /* [n_mp][32] */
+  const uint8_t* mp_has_obs; /* [n_mp] */
+} lld_sbp_mp_problem;
+
+int lld_sbp_mappoints(void* ctx, const lld_sbp_mp_problem* p, lld_sbp_result* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stereo line matching (float line descriptors)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct lld_line_match_problem {
+  int32_t n_pairs;
+  int32_t desc_dim;         /* D floats per descriptor row */
+  const int32_t* left_off;  /* [n_pairs+1] */
+  const int32_t* right_off; /* [n_pairs+1] */
+  const float* left_seg;    /* [n_left][4] startPointX startPointY endPointX endPointY */
+  const int32_t* left_octave;
+  const float* right_seg;
+  const int32_t* right_octave;
+  const float* left_desc;   /* [n_left][D] */
+  const float* right_desc;  /* [n_right][D] */
+  double K[9];              /* row-major */
+  double baseline;          /* b of TwoFrameLineMatcher(K,b,tau,minLineLength,matcher) */
+  double tau;
+  int32_t min_line_length;
+} lld_line_match_problem;
+
+typedef struct lld_line_match_result {
+  int32_t* match;  /* [n_left] pair-local right index or -1 */
+  float* dist;     /* [n_left] descriptor distance of the match (inf when none); may be NULL */
+} lld_line_match_result;
+
+int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_line_match_result* out);
+
+/* Library self-description (for tests and the bench): version string, number of kernels launched by the
+ * last call on this context, device-side duration of the last call measured with CUDA events on the
+ * context's stream (milliseconds; h2d/compute/d2h). */
+const char* lld_version(void);
+int64_t lld_ctx_launch_count(void* ctx);
+void lld_ctx_last_timing(void* ctx, float* ms_h2d, float* ms_compute, float* ms_d2h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLDBA_H */
