@@ -136,6 +136,9 @@ def fill_struct(struct_cls, fields: Dict[str, Any]):
         v = fields[name]
         if v is None:
             continue  # NULL pointer
+        if isinstance(ctype, type) and issubclass(ctype, C.Array):
+            setattr(s, name, ctype(*[float(x) for x in np.asarray(v).ravel()]))
+            continue
         if isinstance(v, np.ndarray):
             want = _NP2C.get(v.dtype)
             if want is not ctype:
@@ -146,9 +149,6 @@ def fill_struct(struct_cls, fields: Dict[str, Any]):
             setattr(s, name, v.ctypes.data_as(ctype))
         elif isinstance(v, C.Structure):
             setattr(s, name, v)
-        elif isinstance(ctype, type) and issubclass(ctype, C.Array):
-            arr = ctype(*[float(x) for x in np.asarray(v).ravel()])
-            setattr(s, name, arr)
         else:
             setattr(s, name, v)
     return s, keep

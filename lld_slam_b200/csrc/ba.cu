@@ -1,0 +1,610 @@
+// ba.cu — host driver of the batched point+line bundle adjustment and the lld_ba_* C-ABI entry points.
+//
+// Replaces the bodies of Optimizer::LocalBundleAdjustment (src/Optimizer.cc:1019-1386) and
+// Optimizer::BundleAdjustment (src/Optimizer.cc:321-559): the g2o graph + BlockSolver + Levenberg loop become
+// the kernel sequence of ba_kernels.cuh; LM control runs on the device, the host only enqueues steps and polls
+// one counter.  No CPU fallback: every path below ends in kernel launches on the context's stream.
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "ba_kernels.cuh"
+#include "lld_ctx.h"
+
+#ifdef LLD_WITH_NCCL
+#include <nccl.h>
+#endif
+
+using namespace lld;
+
+static const int CHUNK = 256;          // edge-list entries per chunk (k_lin_poses / k_schur_rows CTA)
+static const int SMEM_SOLVE_MAX_N = 162;  // dense LDL^T in shared memory up to this dimension (27 free KFs)
+
+struct BaState {
+  BaView v{};
+  // host copies needed after upload
+  int n_win = 0;
+  int max_n = 0;       // largest reduced system dimension over the windows
+  int max_nnb = 0;
+  size_t n_nb_total = 0;
+  bool global_mode = false;
+  const double* d_kf_Tcw_in = nullptr;
+  const double* d_pt_in = nullptr;
+  const double* d_ln_in = nullptr;
+  size_t h2d_bytes = 0;
+  // output staging on device
+  double* d_out_kf = nullptr;
+  double* d_out_pt = nullptr;
+  double* d_out_ln = nullptr;
+  uint8_t* d_pt_bad = nullptr;
+  uint8_t* d_ln_bad = nullptr;
+};
+
+namespace {
+
+template <typename T>
+int up(LldCtx* c, T** dst, const T* src, size_t n, size_t* bytes) {
+  cudaError_t e = cudaSuccess;
+  T* d = c->alloc<T>(n ? n : 1, &e);
+  if (e != cudaSuccess) {
+    snprintf(c->err, sizeof(c->err), "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+    return LLD_ERR_CUDA;
+  }
+  if (n && src) {
+    e = cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) {
+      snprintf(c->err, sizeof(c->err), "cudaMemcpyAsync H2D: %s", cudaGetErrorString(e));
+      return LLD_ERR_CUDA;
+    }
+    if (bytes) *bytes += n * sizeof(T);
+  }
+  *dst = d;
+  return LLD_OK;
+}
+#define UP(dst, src, n)                                                     \
+  do {                                                                      \
+    int _r = up(c, &(dst), (src), (size_t)(n), &S->h2d_bytes);              \
+    if (_r != LLD_OK) return _r;                                            \
+  } while (0)
+#define DEV(dst, T, n)                                                      \
+  do {                                                                      \
+    T* _p = nullptr;                                                        \
+    int _r = up<T>(c, &_p, nullptr, (size_t)(n), nullptr);                  \
+    if (_r != LLD_OK) return _r;                                            \
+    (dst) = _p;                                                             \
+  } while (0)
+
+}  // namespace
+
+// Flatten + index the problem on the host, upload, initialise device state.
+static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int log_stride) {
+  if (!c->ba) c->ba = new BaState();
+  BaState* S = c->ba;
+  *S = BaState();
+  S->global_mode = global_mode;
+  c->pool_reset();
+  BaView& v = S->v;
+  const int nw = p->n_win;
+  LLD_ARG(c, nw >= 1);
+  const int n_kf = p->kf_off[nw], n_pt = p->pt_off[nw], n_ln = p->ln_off[nw];
+  const int n_pe = p->pt_obs_off[n_pt], n_lc = p->ln_obs_off[n_ln];
+  v.n_win = nw; v.n_kf = n_kf; v.n_pt = n_pt; v.n_ln = n_ln; v.n_pe = n_pe; v.n_lc = n_lc;
+  S->n_win = nw;
+
+  // ---- host indexing ----
+  std::vector<int> kf_win(n_kf), pt_win(n_pt), ln_win(n_ln), kf_g(n_kf, -1), w_g0(nw + 1, 0);
+  std::vector<int> g_kf;
+  for (int w = 0; w < nw; w++) {
+    w_g0[w] = (int)g_kf.size();
+    for (int k = p->kf_off[w]; k < p->kf_off[w + 1]; k++) {
+      kf_win[k] = w;
+      if (!p->kf_fixed[k]) {
+        kf_g[k] = (int)g_kf.size();
+        g_kf.push_back(k);
+      }
+    }
+    for (int i = p->pt_off[w]; i < p->pt_off[w + 1]; i++) pt_win[i] = w;
+    for (int i = p->ln_off[w]; i < p->ln_off[w + 1]; i++) ln_win[i] = w;
+    S->max_n = std::max(S->max_n, 6 * ((int)g_kf.size() - w_g0[w]));
+  }
+  w_g0[nw] = (int)g_kf.size();
+  const int nG = (int)g_kf.size();
+  v.n_free_total = nG;
+
+  std::vector<int> pe_kf(n_pe), pe_pt(n_pe), lc_kf(n_lc), lc_ln(n_lc);
+  for (int i = 0; i < n_pt; i++) {
+    const int w = pt_win[i], k0 = p->kf_off[w], nk = p->kf_off[w + 1] - k0;
+    LLD_ARG(c, p->pt_obs_off[i + 1] - p->pt_obs_off[i] <= 254);
+    for (int e = p->pt_obs_off[i]; e < p->pt_obs_off[i + 1]; e++) {
+      LLD_ARG(c, p->pt_obs_kf[e] >= 0 && p->pt_obs_kf[e] < nk);
+      pe_kf[e] = k0 + p->pt_obs_kf[e];
+      pe_pt[e] = i;
+    }
+  }
+  for (int i = 0; i < n_ln; i++) {
+    const int w = ln_win[i], k0 = p->kf_off[w], nk = p->kf_off[w + 1] - k0;
+    LLD_ARG(c, p->ln_obs_off[i + 1] - p->ln_obs_off[i] <= 254);
+    for (int e = p->ln_obs_off[i]; e < p->ln_obs_off[i + 1]; e++) {
+      LLD_ARG(c, p->ln_obs_kf[e] >= 0 && p->ln_obs_kf[e] < nk);
+      lc_kf[e] = k0 + p->ln_obs_kf[e];
+      lc_ln[e] = i;
+    }
+  }
+  // per-free-keyframe edge lists (counting sort; points in edge order, then line cells in cell order)
+  std::vector<int> kfl_off(nG + 1, 0);
+  for (int e = 0; e < n_pe; e++)
+    if (kf_g[pe_kf[e]] >= 0) kfl_off[kf_g[pe_kf[e]] + 1]++;
+  for (int e = 0; e < n_lc; e++)
+    if (kf_g[lc_kf[e]] >= 0) kfl_off[kf_g[lc_kf[e]] + 1]++;
+  for (int g = 0; g < nG; g++) kfl_off[g + 1] += kfl_off[g];
+  const int n_list = kfl_off[nG];
+  std::vector<int> kfl_ref(std::max(n_list, 1)), cur(kfl_off.begin(), kfl_off.end() - 1);
+  for (int e = 0; e < n_pe; e++) {
+    const int g = kf_g[pe_kf[e]];
+    if (g >= 0) kfl_ref[cur[g]++] = e;
+  }
+  for (int e = 0; e < n_lc; e++) {
+    const int g = kf_g[lc_kf[e]];
+    if (g >= 0) kfl_ref[cur[g]++] = ~e;
+  }
+  // chunks
+  std::vector<int> ch_g, ch_begin, ch_end, g_ch0(nG + 1, 0);
+  for (int g = 0; g < nG; g++) {
+    g_ch0[g] = (int)ch_g.size();
+    for (int b = kfl_off[g]; b < kfl_off[g + 1]; b += CHUNK) {
+      ch_g.push_back(g);
+      ch_begin.push_back(b);
+      ch_end.push_back(std::min(b + CHUNK, kfl_off[g + 1]));
+    }
+  }
+  g_ch0[nG] = (int)ch_g.size();
+  const int n_ch = (int)ch_g.size();
+  v.n_chunks = n_ch;
+  // neighbour lists (block columns >= own row)
+  std::vector<int> nb_off(nG + 1, 0), nb_g;
+  if (!global_mode) {
+    for (int w = 0; w < nw; w++)
+      for (int g = w_g0[w]; g < w_g0[w + 1]; g++) {
+        nb_off[g] = (int)nb_g.size();
+        for (int b = g; b < w_g0[w + 1]; b++) nb_g.push_back(b);
+      }
+    nb_off[nG] = (int)nb_g.size();
+  } else {
+    // covisibility: blocks sharing at least one landmark
+    std::vector<std::vector<int>> nbs(nG);
+    std::vector<int> gs;
+    auto add = [&](std::vector<int>& gl) {
+      std::sort(gl.begin(), gl.end());
+      gl.erase(std::unique(gl.begin(), gl.end()), gl.end());
+      for (size_t a = 0; a < gl.size(); a++)
+        for (size_t b = a; b < gl.size(); b++) nbs[gl[a]].push_back(gl[b]);
+    };
+    for (int i = 0; i < n_pt; i++) {
+      gs.clear();
+      for (int e = p->pt_obs_off[i]; e < p->pt_obs_off[i + 1]; e++)
+        if (kf_g[pe_kf[e]] >= 0) gs.push_back(kf_g[pe_kf[e]]);
+      add(gs);
+    }
+    for (int i = 0; i < n_ln; i++) {
+      gs.clear();
+      for (int e = p->ln_obs_off[i]; e < p->ln_obs_off[i + 1]; e++)
+        if (kf_g[lc_kf[e]] >= 0) gs.push_back(kf_g[lc_kf[e]]);
+      add(gs);
+    }
+    for (int g = 0; g < nG; g++) {
+      auto& l = nbs[g];
+      l.push_back(g);
+      std::sort(l.begin(), l.end());
+      l.erase(std::unique(l.begin(), l.end()), l.end());
+      nb_off[g] = (int)nb_g.size();
+      nb_g.insert(nb_g.end(), l.begin(), l.end());
+    }
+    nb_off[nG] = (int)nb_g.size();
+  }
+  for (int g = 0; g < nG; g++) S->max_nnb = std::max(S->max_nnb, nb_off[g + 1] - nb_off[g]);
+  S->n_nb_total = nb_g.size();
+  LLD_ARG(c, 6 * S->max_nnb <= 1024);
+  // rowslot table + partial-row offsets
+  std::vector<long long> rs_off(std::max(nG, 1), 0), ch_S_off(std::max(n_ch, 1), 0);
+  long long rs_total = 0, chS_total = 0;
+  for (int g = 0; g < nG; g++) {
+    rs_off[g] = rs_total;
+    rs_total += (long long)(kfl_off[g + 1] - kfl_off[g]) * (nb_off[g + 1] - nb_off[g]);
+  }
+  for (int ch = 0; ch < n_ch; ch++) {
+    ch_S_off[ch] = chS_total;
+    const int nnb = nb_off[ch_g[ch] + 1] - nb_off[ch_g[ch]];
+    chS_total += 36LL * nnb + 6;
+  }
+  std::vector<uint8_t> rowslot((size_t)std::max(rs_total, 1LL), 0xFF);
+  for (int g = 0; g < nG; g++) {
+    const int nnb = nb_off[g + 1] - nb_off[g];
+    const int* nbl = nb_g.data() + nb_off[g];
+    for (int i = kfl_off[g]; i < kfl_off[g + 1]; i++) {
+      uint8_t* row = rowslot.data() + rs_off[g] + (long long)(i - kfl_off[g]) * nnb;
+      const int ref = kfl_ref[i];
+      int b0, b1;
+      const int* kfs;
+      if (ref >= 0) { b0 = p->pt_obs_off[pe_pt[ref]]; b1 = p->pt_obs_off[pe_pt[ref] + 1]; kfs = pe_kf.data(); }
+      else { b0 = p->ln_obs_off[lc_ln[~ref]]; b1 = p->ln_obs_off[lc_ln[~ref] + 1]; kfs = lc_kf.data(); }
+      for (int e2 = b0; e2 < b1; e2++) {
+        const int b = kf_g[kfs[e2]];
+        if (b < g) continue;
+        int j;
+        if (!global_mode) j = b - g;
+        else j = (int)(std::lower_bound(nbl, nbl + nnb, b) - nbl);
+        row[j] = (uint8_t)(e2 - b0);
+      }
+    }
+  }
+  // global-memory solve scratch for windows too large for shared memory
+  std::vector<long long> w_scr(nw, 0);
+  long long scr_total = 0;
+  for (int w = 0; w < nw; w++) {
+    const long long n = 6LL * (w_g0[w + 1] - w_g0[w]);
+    w_scr[w] = scr_total;
+    if (S->max_n > SMEM_SOLVE_MAX_N) scr_total += n * n + 2 * n;
+  }
+
+  // ---- upload (timed as h2d) ----
+  int* tmp_i;
+  UP(tmp_i, p->kf_off, nw + 1); v.kf_off = tmp_i;
+  UP(tmp_i, p->pt_off, nw + 1); v.pt_off = tmp_i;
+  UP(tmp_i, p->ln_off, nw + 1); v.ln_off = tmp_i;
+  UP(tmp_i, kf_win.data(), n_kf); v.kf_win = tmp_i;
+  UP(tmp_i, pt_win.data(), n_pt); v.pt_win = tmp_i;
+  UP(tmp_i, ln_win.data(), n_ln); v.ln_win = tmp_i;
+  UP(tmp_i, kf_g.data(), n_kf); v.kf_g = tmp_i;
+  UP(tmp_i, g_kf.data(), nG); v.g_kf = tmp_i;
+  UP(tmp_i, w_g0.data(), nw + 1); v.w_g0 = tmp_i;
+  double* tmp_d;
+  UP(tmp_d, p->kf_intr, 5 * (size_t)n_kf); v.kf_intr = tmp_d;
+  UP(tmp_d, p->kf_line_cam, 4 * (size_t)n_kf); v.kf_lcam = tmp_d;
+  UP(tmp_i, p->pt_obs_off, n_pt + 1); v.pt_obs_off = tmp_i;
+  UP(tmp_i, pe_kf.data(), n_pe); v.pe_kf = tmp_i;
+  UP(tmp_i, pe_pt.data(), n_pe); v.pe_pt = tmp_i;
+  float* tmp_f;
+  UP(tmp_f, p->pt_obs_uvr, 3 * (size_t)n_pe); v.pe_uvr = tmp_f;
+  UP(tmp_f, p->pt_obs_info, n_pe); v.pe_info = tmp_f;
+  UP(tmp_i, p->ln_obs_off, n_ln + 1); v.ln_obs_off = tmp_i;
+  UP(tmp_i, lc_kf.data(), n_lc); v.lc_kf = tmp_i;
+  UP(tmp_i, lc_ln.data(), n_lc); v.lc_ln = tmp_i;
+  UP(tmp_f, p->ln_obs_left, 4 * (size_t)n_lc); v.lc_left = tmp_f;
+  UP(tmp_f, p->ln_obs_right, 4 * (size_t)n_lc); v.lc_right = tmp_f;
+  UP(tmp_d, p->ln_obs_info, 2 * (size_t)n_lc); v.lc_info = tmp_d;
+  uint8_t* tmp_u;
+  UP(tmp_u, p->ln_obs_stereo, n_lc); v.lc_stereo = tmp_u;
+  UP(tmp_i, kfl_off.data(), nG + 1); v.kfl_off = tmp_i;
+  UP(tmp_i, kfl_ref.data(), n_list); v.kfl_ref = tmp_i;
+  UP(tmp_i, ch_g.data(), n_ch); v.ch_g = tmp_i;
+  UP(tmp_i, ch_begin.data(), n_ch); v.ch_begin = tmp_i;
+  UP(tmp_i, ch_end.data(), n_ch); v.ch_end = tmp_i;
+  UP(tmp_i, g_ch0.data(), nG + 1); v.g_ch0 = tmp_i;
+  UP(tmp_i, nb_off.data(), nG + 1); v.nb_off = tmp_i;
+  UP(tmp_i, nb_g.data(), nb_g.size()); v.nb_g = tmp_i;
+  UP(tmp_u, rowslot.data(), (size_t)rs_total); v.rowslot = tmp_u;
+  long long* tmp_l;
+  UP(tmp_l, rs_off.data(), nG); v.rs_off = tmp_l;
+  UP(tmp_l, ch_S_off.data(), n_ch); v.ch_S_off = tmp_l;
+  UP(tmp_l, w_scr.data(), nw); v.w_scratch_off = tmp_l;
+  double *d_T, *d_P, *d_L;
+  UP(d_T, p->kf_Tcw, 12 * (size_t)n_kf);
+  UP(d_P, p->pt_xyz, 3 * (size_t)n_pt);
+  UP(d_L, p->ln_x0_dir, 6 * (size_t)n_ln);
+  S->d_kf_Tcw_in = d_T; S->d_pt_in = d_P; S->d_ln_in = d_L;
+
+  // ---- device-only buffers ----
+  for (int b = 0; b < 2; b++) {
+    DEV(v.pose_qt[b], double, 7 * (size_t)n_kf);
+    DEV(v.pose_Rt[b], double, 12 * (size_t)n_kf);
+    DEV(v.pt_xyz[b], double, 3 * (size_t)n_pt);
+    DEV(v.ln_st[b], double, 5 * (size_t)n_ln);
+  }
+  DEV(v.pe_level, uint8_t, n_pe); DEV(v.lc_level, uint8_t, 2 * (size_t)n_lc); DEV(v.ln_removed, uint8_t, n_ln);
+  DEV(v.pe_chi2, double, n_pe); DEV(v.lc_chi2, double, 2 * (size_t)n_lc);
+  DEV(v.pt_H, double, 9 * (size_t)n_pt); DEV(v.ln_H, double, 14 * (size_t)n_ln);
+  DEV(v.pe_W, double, 18 * (size_t)n_pe); DEV(v.lc_W, double, 24 * (size_t)n_lc);
+  DEV(v.ch_pose, double, 28 * (size_t)n_ch);
+  DEV(v.g_Hpp, double, 21 * (size_t)nG); DEV(v.g_bp, double, 6 * (size_t)nG); DEV(v.g_nact, int, nG);
+  DEV(v.lm_chi2lin, double, n_pt + n_ln); DEV(v.lm_maxdiag, double, n_pt + n_ln); DEV(v.lm_active, uint8_t, n_pt + n_ln);
+  DEV(v.pe_Y, double, 18 * (size_t)n_pe); DEV(v.lc_Y, double, 24 * (size_t)n_lc);
+  DEV(v.ch_S, double, (size_t)chS_total);
+  DEV(v.S_blk, double, 36 * nb_g.size());
+  DEV(v.g_bs, double, 6 * (size_t)nG); DEV(v.g_x, double, 6 * (size_t)nG);
+  DEV(v.pt_c, double, 3 * (size_t)n_pt); DEV(v.ln_c, double, 4 * (size_t)n_ln);
+  DEV(v.lm_chi2, double, n_pt + n_ln); DEV(v.lm_scale, double, n_pt + n_ln);
+  DEV(v.w_phase, int, nw); DEV(v.w_sel, int, nw); DEV(v.w_iter, int, nw); DEV(v.w_trials, int, nw);
+  DEV(v.w_maxit, int, nw); DEV(v.w_nbad, int, nw); DEV(v.w_ok, int, nw); DEV(v.w_nlog, int, nw);
+  DEV(v.w_lambda, double, nw); DEV(v.w_ni, double, nw); DEV(v.w_curchi, double, nw); DEV(v.w_inichi, double, nw);
+  DEV(v.w_scale_p, double, nw); DEV(v.w_red_sum, double, 4 * (size_t)nw); DEV(v.w_red_max, double, nw);
+  DEV(v.n_active_win, int, 1);
+  v.log_stride = log_stride;
+  DEV(v.chi2_log, double, (size_t)nw * log_stride); DEV(v.lambda_log, double, (size_t)nw * log_stride);
+  DEV(v.trials_log, int, (size_t)nw * log_stride); DEV(v.iter_done, int, 2 * (size_t)nw);
+  DEV(v.solve_scratch, double, (size_t)scr_total);
+  DEV(S->d_out_kf, double, 12 * (size_t)n_kf); DEV(S->d_out_pt, double, 3 * (size_t)n_pt);
+  DEV(S->d_out_ln, double, 6 * (size_t)n_ln);
+  DEV(S->d_pt_bad, uint8_t, n_pe); DEV(S->d_ln_bad, uint8_t, 2 * (size_t)n_lc);
+  LLD_CUDA(c, cudaMemsetAsync(v.chi2_log, 0, sizeof(double) * (size_t)nw * log_stride, c->stream));
+  LLD_CUDA(c, cudaMemsetAsync(v.lambda_log, 0, sizeof(double) * (size_t)nw * log_stride, c->stream));
+  LLD_CUDA(c, cudaMemsetAsync(v.trials_log, 0, sizeof(int) * (size_t)nw * log_stride, c->stream));
+  LLD_CUDA(c, cudaMemsetAsync(S->d_pt_bad, 0, n_pe ? n_pe : 1, c->stream));
+  LLD_CUDA(c, cudaMemsetAsync(S->d_ln_bad, 0, n_lc ? 2 * (size_t)n_lc : 1, c->stream));
+
+  v.prm.robust_pt = p->robust_points;
+  v.prm.robust_ln = 1;
+  v.prm.delta_pt_mono = p->delta_pt_mono; v.prm.delta_pt_stereo = p->delta_pt_stereo;
+  v.prm.delta_ln_mono = p->delta_ln_mono; v.prm.delta_ln_stereo = p->delta_ln_stereo;
+  v.prm.chi2_pt_mono = p->chi2_pt_mono; v.prm.chi2_pt_stereo = p->chi2_pt_stereo;
+  v.prm.ln_norm = p->ln_endpoints_normalized;
+  v.prm.ln_filter = p->ln_filter;
+  return LLD_OK;
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+static int ba_init_state(LldCtx* c) {
+  BaState* S = c->ba;
+  BaView& v = S->v;
+  const int n = std::max({v.n_kf, v.n_pt, v.n_ln, v.n_pe, v.n_lc, v.n_free_total, 1});
+  LLD_LAUNCH(c, k_init_state, cdiv(n, 256), 256, 0, v, S->d_kf_Tcw_in, S->d_pt_in, S->d_ln_in, v.lc_right);
+  LLD_CUDA(c, cudaGetLastError());
+  return LLD_OK;
+}
+
+#ifdef LLD_WITH_NCCL
+#define LLD_NCCL(ctx, call)                                                                              \
+  do {                                                                                                   \
+    ncclResult_t _r = (call);                                                                            \
+    if (_r != ncclSuccess) {                                                                             \
+      snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, ncclGetErrorString(_r)); \
+      return LLD_ERR_NCCL;                                                                               \
+    }                                                                                                    \
+  } while (0)
+#endif
+
+// all-reduce hooks of the global BA (no-ops on one rank)
+static int ba_allreduce_lin(LldCtx* c) {
+#ifdef LLD_WITH_NCCL
+  if (c->n_ranks > 1) {
+    BaView& v = c->ba->v;
+    ncclComm_t comm = reinterpret_cast<ncclComm_t>(c->comm);
+    LLD_NCCL(c, ncclAllReduce(v.w_red_sum, v.w_red_sum, 4 * (size_t)v.n_win, ncclDouble, ncclSum, comm, c->stream));
+    LLD_NCCL(c, ncclAllReduce(v.w_red_max, v.w_red_max, (size_t)v.n_win, ncclDouble, ncclMax, comm, c->stream));
+    LLD_NCCL(c, ncclAllReduce(v.g_Hpp, v.g_Hpp, 21 * (size_t)v.n_free_total, ncclDouble, ncclSum, comm, c->stream));
+    LLD_NCCL(c, ncclAllReduce(v.g_bp, v.g_bp, 6 * (size_t)v.n_free_total, ncclDouble, ncclSum, comm, c->stream));
+    LLD_NCCL(c, ncclAllReduce(v.g_nact, v.g_nact, (size_t)v.n_free_total, ncclInt, ncclSum, comm, c->stream));
+  }
+#endif
+  return LLD_OK;
+}
+static int ba_allreduce_trial(LldCtx* c) {
+#ifdef LLD_WITH_NCCL
+  if (c->n_ranks > 1) {
+    BaView& v = c->ba->v;
+    ncclComm_t comm = reinterpret_cast<ncclComm_t>(c->comm);
+    LLD_NCCL(c, ncclAllReduce(v.w_red_sum, v.w_red_sum, 4 * (size_t)v.n_win, ncclDouble, ncclSum, comm, c->stream));
+  }
+#endif
+  return LLD_OK;
+}
+
+// multi-GPU: every rank holds the Schur contributions of its own landmarks; rank 0 alone carries Hpp + lambda I and bp
+static int ba_allreduce_rows(LldCtx* c) {
+#ifdef LLD_WITH_NCCL
+  if (c->n_ranks > 1) {
+    BaState* S = c->ba;
+    BaView& v = S->v;
+    ncclComm_t comm = reinterpret_cast<ncclComm_t>(c->comm);
+    LLD_NCCL(c, ncclAllReduce(v.S_blk, v.S_blk, 36 * S->n_nb_total, ncclDouble, ncclSum, comm, c->stream));
+    LLD_NCCL(c, ncclAllReduce(v.g_bs, v.g_bs, 6 * (size_t)v.n_free_total, ncclDouble, ncclSum, comm, c->stream));
+  }
+#endif
+  return LLD_OK;
+}
+
+template <bool SMEM>
+static int launch_solve(LldCtx* c, BaView& v, int max_n) {
+  size_t smem = SMEM ? sizeof(double) * ((size_t)max_n * max_n + 2 * (size_t)max_n) : 0;
+  if (SMEM) LLD_CUDA(c, cudaFuncSetAttribute(k_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LLD_LAUNCH(c, k_solve<SMEM>, v.n_win, 256, smem, v);
+  return LLD_OK;
+}
+
+// one LM step of every window still running
+static int ba_step(LldCtx* c, int round, int stop_now) {
+  BaState* S = c->ba;
+  BaView& v = S->v;
+  const int gp = cdiv(std::max(v.n_pt, 1), LM_TPB), gl = cdiv(std::max(v.n_ln, 1), LM_TPB);
+  if (v.n_pt) LLD_LAUNCH(c, k_lin_points, gp, LM_TPB, 0, v);
+  if (v.n_ln) LLD_LAUNCH(c, k_lin_lines, gl, LM_TPB, 0, v);
+  if (v.n_chunks) LLD_LAUNCH(c, k_lin_poses, v.n_chunks, LM_TPB, 0, v);
+  if (v.n_free_total) LLD_LAUNCH(c, k_reduce_pose, cdiv(v.n_free_total * 28, 128), 128, 0, v);
+  LLD_LAUNCH(c, k_reduce_lin, v.n_win, 256, 0, v);
+  if (S->global_mode) { int r = ba_allreduce_lin(c); if (r) return r; }
+  LLD_LAUNCH(c, k_begin, cdiv(v.n_win, 64), 64, 0, v);
+  if (v.n_pt) LLD_LAUNCH(c, k_schur_points, gp, LM_TPB, 0, v);
+  if (v.n_ln) LLD_LAUNCH(c, k_schur_lines, gl, LM_TPB, 0, v);
+  if (v.n_chunks) {
+    const int tpb = 32 * cdiv(6 * S->max_nnb, 32);
+    LLD_LAUNCH(c, k_schur_rows, v.n_chunks, tpb, 0, v);
+  }
+  if (v.n_free_total) {
+    const int tpb = std::min(256, 32 * cdiv(6 * S->max_nnb, 32));
+    LLD_LAUNCH(c, k_reduce_rows, v.n_free_total, tpb, 0, v, (S->global_mode && c->n_ranks > 1 && c->rank != 0) ? 0 : 1);
+  }
+  if (S->global_mode) { int r = ba_allreduce_rows(c); if (r) return r; }
+  if (S->max_n <= SMEM_SOLVE_MAX_N) { int r = launch_solve<true>(c, v, S->max_n); if (r) return r; }
+  else { int r = launch_solve<false>(c, v, S->max_n); if (r) return r; }
+  if (v.n_pt) LLD_LAUNCH(c, k_backsub_points, gp, LM_TPB, 0, v);
+  if (v.n_ln) LLD_LAUNCH(c, k_backsub_lines, gl, LM_TPB, 0, v);
+  LLD_LAUNCH(c, k_reduce_trial, v.n_win, 256, 0, v);
+  if (S->global_mode) { int r = ba_allreduce_trial(c); if (r) return r; }
+  LLD_LAUNCH(c, k_decide, cdiv(v.n_win, 64), 64, 0, v, round, stop_now);
+  LLD_CUDA(c, cudaGetLastError());
+  return LLD_OK;
+}
+
+// optimize(maxit) for the whole batch (SparseOptimizer::optimize, sparse_optimizer.cpp:354-419)
+static int ba_run_round(LldCtx* c, int maxit, int round, const volatile uint8_t* stop) {
+  BaState* S = c->ba;
+  BaView& v = S->v;
+  LLD_LAUNCH(c, k_round_init, cdiv(v.n_win, 64), 64, 0, v, maxit, round);
+  if (maxit <= 0) return LLD_OK;
+  int* h_active = reinterpret_cast<int*>(c->pinned);
+  int launched = 0;
+  const int hard_cap = maxit * 10 + 4;
+  bool first = true;
+  while (true) {
+    const int n = first ? maxit : 2;
+    first = false;
+    for (int s = 0; s < n; s++) {
+      const int stop_now = (stop && *stop) ? 1 : 0;
+      int r = ba_step(c, round, stop_now);
+      if (r) return r;
+      launched++;
+      if (stop_now) break;
+    }
+    LLD_CUDA(c, cudaMemcpyAsync(h_active, v.n_active_win, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LLD_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (*h_active <= 0) break;
+    if (launched >= hard_cap) {
+      snprintf(c->err, sizeof(c->err), "LM step budget exhausted (%d steps, %d windows still active)", launched, *h_active);
+      return LLD_ERR_CUDA;
+    }
+  }
+  return LLD_OK;
+}
+
+static int ba_download(LldCtx* c, const lld_ba_problem* p, lld_ba_result* out, bool local) {
+  BaState* S = c->ba;
+  BaView& v = S->v;
+  const int n = std::max({v.n_kf, v.n_pt, v.n_ln, 1});
+  if (local) {
+    if (v.n_pe) LLD_LAUNCH(c, k_flag_points, cdiv(v.n_pe, 256), 256, 0, v, S->d_pt_bad);
+    if (v.n_ln) LLD_LAUNCH(c, k_final_lines, cdiv(v.n_ln, 128), 128, 0, v, S->d_ln_bad);
+  }
+  LLD_LAUNCH(c, k_export, cdiv(n, 256), 256, 0, v, S->d_out_kf, S->d_out_pt, S->d_out_ln, S->d_ln_in);
+  LLD_CUDA(c, cudaGetLastError());
+  LLD_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  auto D2H = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+    if (!dst || !bytes) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream);
+  };
+  LLD_CUDA(c, D2H(out->kf_Tcw, S->d_out_kf, sizeof(double) * 12 * (size_t)v.n_kf));
+  LLD_CUDA(c, D2H(out->pt_xyz, S->d_out_pt, sizeof(double) * 3 * (size_t)v.n_pt));
+  LLD_CUDA(c, D2H(out->ln_x0_dir, S->d_out_ln, sizeof(double) * 6 * (size_t)v.n_ln));
+  LLD_CUDA(c, D2H(out->pt_obs_bad, S->d_pt_bad, (size_t)v.n_pe));
+  LLD_CUDA(c, D2H(out->ln_obs_bad, S->d_ln_bad, 2 * (size_t)v.n_lc));
+  LLD_CUDA(c, D2H(out->ln_removed, v.ln_removed, (size_t)v.n_ln));
+  const int ls = std::min(out->log_stride, v.log_stride);
+  if (out->log_stride == v.log_stride) {
+    LLD_CUDA(c, D2H(out->chi2_log, v.chi2_log, sizeof(double) * (size_t)v.n_win * ls));
+    LLD_CUDA(c, D2H(out->lambda_log, v.lambda_log, sizeof(double) * (size_t)v.n_win * ls));
+    LLD_CUDA(c, D2H(out->trials_log, v.trials_log, sizeof(int) * (size_t)v.n_win * ls));
+  }
+  LLD_CUDA(c, D2H(out->n_iter_done, v.iter_done, sizeof(int) * 2 * (size_t)v.n_win));
+  LLD_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+  LLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]);
+  cudaEventElapsedTime(&c->ms_compute, c->ev[1], c->ev[2]);
+  cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]);
+  (void)p;
+  return LLD_OK;
+}
+
+// ---- resident-mode entry points (bench: inputs already in HBM) ---------------------------------------------
+extern "C" int lld_ba_upload(void* ctx, const lld_ba_problem* p, int global_mode, int log_stride) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (!c || !p) return LLD_ERR_ARG;
+  LLD_CUDA(c, cudaSetDevice(c->device));
+  LLD_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+  int r = ba_upload(c, p, global_mode != 0, log_stride);
+  if (r) return r;
+  LLD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  LLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LLD_OK;
+}
+
+// (re)initialise the device state from the uploaded inputs and run; round-2 parameters as in lld_ba_local.
+extern "C" int lld_ba_run_local(void* ctx, int its1, int its2, const volatile uint8_t* stop) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (!c || !c->ba) return LLD_ERR_ARG;
+  LLD_CUDA(c, cudaSetDevice(c->device));
+  BaState* S = c->ba;
+  BaView& v = S->v;
+  int r = ba_init_state(c);
+  if (r) return r;
+  if (stop && *stop) {  // src/Optimizer.cc:1220-1222
+    LLD_LAUNCH(c, k_round_init, cdiv(v.n_win, 64), 64, 0, v, 0, 0);
+    return LLD_OK;
+  }
+  const int rp = v.prm.robust_pt;
+  v.prm.robust_ln = 1;
+  r = ba_run_round(c, its1, 0, stop);
+  if (r) return r;
+  if (!(stop && *stop)) {  // bDoMore, src/Optimizer.cc:1230-1236
+    if (v.n_pe) LLD_LAUNCH(c, k_flag_points, cdiv(v.n_pe, 256), 256, 0, v, (uint8_t*)nullptr);
+    if (v.n_ln) LLD_LAUNCH(c, k_flag_lines, cdiv(v.n_ln, 128), 128, 0, v);
+    v.prm.robust_pt = 0;
+    v.prm.robust_ln = 0;
+    r = ba_run_round(c, its2, 1, stop);
+    v.prm.robust_pt = rp;
+    v.prm.robust_ln = 1;
+    if (r) return r;
+  }
+  return LLD_OK;
+}
+
+extern "C" int lld_ba_run_global(void* ctx, int n_iter, const volatile uint8_t* stop) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (!c || !c->ba) return LLD_ERR_ARG;
+  LLD_CUDA(c, cudaSetDevice(c->device));
+  int r = ba_init_state(c);
+  if (r) return r;
+  c->ba->v.prm.robust_ln = 1;
+  return ba_run_round(c, n_iter, 0, stop);
+}
+
+extern "C" int lld_ba_sync(void* ctx) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (!c) return LLD_ERR_ARG;
+  LLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LLD_OK;
+}
+
+extern "C" int lld_ba_download(void* ctx, const lld_ba_problem* p, lld_ba_result* out, int local) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (!c || !c->ba || !out) return LLD_ERR_ARG;
+  return ba_download(c, p, out, local != 0);
+}
+
+// ---- reference-shaped entry points -------------------------------------------------------------------------
+extern "C" int lld_ba_local(void* ctx, const lld_ba_problem* p, int its1, int its2, const volatile uint8_t* stop,
+                            lld_ba_result* out) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (!c || !p || !out) return LLD_ERR_ARG;
+  c->launches = 0;
+  int r = lld_ba_upload(ctx, p, 0, its1 + its2 + 2);
+  if (r) return r;
+  LLD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  r = lld_ba_run_local(ctx, its1, its2, stop);
+  if (r) return r;
+  return ba_download(c, p, out, true);
+}
+
+extern "C" int lld_ba_global(void* ctx, const lld_ba_problem* p, int n_iter, const volatile uint8_t* stop,
+                             lld_ba_result* out) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (!c || !p || !out) return LLD_ERR_ARG;
+  LLD_ARG(c, p->n_win == 1);
+  c->launches = 0;
+  int r = lld_ba_upload(ctx, p, 1, n_iter + 2);
+  if (r) return r;
+  LLD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  r = lld_ba_run_global(ctx, n_iter, stop);
+  if (r) return r;
+  return ba_download(c, p, out, false);
+}
+
+void lld_ba_state_free(BaState* s) { delete s; }

@@ -1,0 +1,125 @@
+// ba.cuh — device-side view of one batched bundle-adjustment problem and the per-window LM state.
+//
+// Data layout in HBM (all SoA, one contiguous array per field over the whole batch):
+//   keyframes   : pose_qt[2][n_kf][7]  (double buffer selected per window by w_sel), pose_Rt[2][n_kf][12] derived,
+//                 kf_intr[n_kf][5], kf_lcam[n_kf][4], kf_g[n_kf] (global free-pose block index or -1)
+//   map points  : pt_xyz[2][n_pt][3]; CSR pt_obs_off; per edge pe_kf (global kf id), pe_uvr (3 x f32), pe_info (f32)
+//   map lines   : ln_st[2][n_ln][5] (q, alpha); CSR ln_obs_off over cells; per cell lc_kf, lc_left/right (4 x f32),
+//                 lc_info (2 x f64), lc_stereo
+//   edges are grouped by landmark (the reference's insertion order), so one thread owns one landmark's edges;
+//   a second index (kfl_*) lists, per free keyframe, the edges that touch it, cut into fixed-size chunks.
+#pragma once
+#include <stdint.h>
+
+namespace lld {
+
+enum : int { PH_LIN = 0, PH_RETRY = 1, PH_DONE = 2 };
+
+struct BaParams {
+  int robust_pt, robust_ln;
+  double delta_pt_mono, delta_pt_stereo, delta_ln_mono, delta_ln_stereo;
+  double chi2_pt_mono, chi2_pt_stereo;
+  int ln_norm;  // endpoints K^-1-normalised
+  int ln_filter;
+};
+
+struct BaView {
+  int n_win, n_kf, n_pt, n_ln, n_pe, n_lc;
+  int n_free_total;  // sum of free poses over the batch
+  int n_chunks;
+  // static topology
+  const int *kf_off, *pt_off, *ln_off;
+  const int *kf_win, *pt_win, *ln_win;
+  const int* kf_g;       // [n_kf] global free block index or -1
+  const int* g_kf;       // [n_free_total] inverse map
+  const int* w_g0;       // [n_win+1] first global free block of window
+  const double* kf_intr;
+  const double* kf_lcam;
+  const int* pt_obs_off;
+  const int* pe_kf;
+  const int* pe_pt;
+  const float* pe_uvr;
+  const float* pe_info;
+  const int* ln_obs_off;
+  const int* lc_kf;
+  const int* lc_ln;
+  const float* lc_left;
+  const float* lc_right;
+  const double* lc_info;
+  const uint8_t* lc_stereo;
+  // per-free-KF edge lists, chunked
+  const int* kfl_off;    // [n_free_total+1]
+  const int* kfl_ref;    // >=0 point edge id ; <0 : ~cell id
+  const int* ch_g;       // [n_chunks] free block of the chunk
+  const int* ch_begin;   // [n_chunks]
+  const int* ch_end;
+  const int* g_ch0;      // [n_free_total+1] first chunk of each free block
+  // Schur row structure
+  const int* nb_off;     // [n_free_total+1] neighbour list (block columns >= own) per free block, in blocks
+  const int* nb_g;       // neighbour global block ids, ascending, first = self
+  const uint8_t* rowslot;     // per list entry: nnb(a) bytes, offset of the co-edge in the landmark's range or 0xFF
+  const long long* rs_off;    // [n_free_total] byte offset of block a's first entry row in rowslot
+  // dynamic state
+  double* pose_qt[2];
+  double* pose_Rt[2];
+  double* pt_xyz[2];
+  double* ln_st[2];
+  uint8_t* pe_level;
+  uint8_t* lc_level;   // [n_lc][2]
+  uint8_t* ln_removed;
+  double* pe_chi2;
+  double* lc_chi2;     // [n_lc][2]
+  // linearisation
+  double* pt_H;   // [n_pt][9]  Hll (00 01 02 11 12 22) + bl (3)
+  double* ln_H;   // [n_ln][14] Hll upper (10) + bl (4)
+  double* pe_W;   // [n_pe][18]
+  double* lc_W;   // [n_lc][24]
+  double* ch_pose;  // [n_chunks][28] partial Hpp (21 upper) + bp (6) + n_active
+  double* g_Hpp;    // [n_free_total][21]
+  double* g_bp;     // [n_free_total][6]
+  int* g_nact;      // [n_free_total]
+  double* lm_chi2lin;  // [n_pt+n_ln]
+  double* lm_maxdiag;  // [n_pt+n_ln]
+  uint8_t* lm_active;  // [n_pt+n_ln]
+  // trial
+  double* pe_Y;   // [n_pe][18]
+  double* lc_Y;   // [n_lc][24]
+  double* ch_S;   // chunk partial rows: at ch_S_off[chunk], 6 x (6*nnb) doubles + 6 (b part)
+  const long long* ch_S_off;
+  double* S_blk;  // [n_nb_total][36]
+  double* g_bs;   // [n_free_total][6] bschur
+  double* g_x;    // [n_free_total][6] pose solution (kept on failure)
+  double* pt_c;   // [n_pt][3]  Dinv * bl
+  double* ln_c;   // [n_ln][4]
+  double* lm_chi2;
+  double* lm_scale;
+  // per-window LM state
+  int* w_phase;
+  int* w_sel;
+  int* w_iter;
+  int* w_trials;
+  int* w_maxit;
+  int* w_nbad;
+  int* w_ok;
+  int* w_nlog;
+  double* w_lambda;
+  double* w_ni;
+  double* w_curchi;
+  double* w_inichi;
+  double* w_scale_p;
+  double* w_red_sum;  // [n_win][4] reduced scalars (chi2, scale_l, n_active_landmarks, spare) — NCCL sum in multi-GPU
+  double* w_red_max;  // [n_win]    max |diag Hll| — NCCL max in multi-GPU
+  int* n_active_win;  // [1]
+  // logs
+  int log_stride;
+  double* chi2_log;
+  double* lambda_log;
+  int* trials_log;
+  int* iter_done;  // [n_win][2]
+  // dense solve scratch (global-memory path) per window
+  double* solve_scratch;
+  const long long* w_scratch_off;
+  BaParams prm;
+};
+
+}  // namespace lld

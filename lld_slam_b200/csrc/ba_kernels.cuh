@@ -1,0 +1,1106 @@
+// ba_kernels.cuh — sm_100a kernels of the batched point+line bundle adjustment.
+//
+// One LM "step" of every window in the batch is the fixed kernel sequence
+//   [k_lin_points, k_lin_lines, k_lin_poses, k_reduce_pose, k_reduce_lin, k_begin]   (windows in PH_LIN only)
+//   k_schur_points, k_schur_lines, k_schur_rows, k_reduce_rows, k_solve,
+//   k_backsub_points, k_backsub_lines, k_reduce_trial, k_decide
+// Each kernel looks at the per-window phase and returns early for windows that do not need it, so the
+// whole batch advances in lock step while every window follows its own Levenberg-Marquardt trajectory
+// (Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-164).
+// Reductions are fixed-order (no floating-point atomics): results are run-to-run reproducible.
+#pragma once
+#include <cfloat>
+
+#include "ba.cuh"
+#include "lld_math.cuh"
+
+namespace lld {
+
+#define LM_TPB 128
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  return v;
+}
+// fixed-order block sum (blockDim.x multiple of 32, <= 1024); result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double* sm /*>=32*/) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sm[wid] = v;
+  __syncthreads();
+  double r = 0;
+  if (wid == 0) {
+    r = (lane < (int)(blockDim.x >> 5)) ? sm[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+__device__ __forceinline__ double block_max(double v, double* sm) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sm[wid] = v;
+  __syncthreads();
+  double r = 0;
+  if (wid == 0) {
+    r = (lane < (int)(blockDim.x >> 5)) ? sm[lane] : 0.0;
+    r = warp_max(r);
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// state initialisation
+// ------------------------------------------------------------------------------------------------
+__global__ void k_init_state(BaView v, const double* __restrict__ kf_Tcw, const double* __restrict__ pt_xyz,
+                             const double* __restrict__ ln_x0_dir, const float* __restrict__ lc_right) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < v.n_kf) {
+    double qt[7], Rt[12];
+    pose_from_Rt(kf_Tcw + 12 * (size_t)i, qt);
+    pose_to_Rt(qt, Rt);
+    for (int b = 0; b < 2; b++) {
+      for (int k = 0; k < 7; k++) v.pose_qt[b][7 * (size_t)i + k] = qt[k];
+      for (int k = 0; k < 12; k++) v.pose_Rt[b][12 * (size_t)i + k] = Rt[k];
+    }
+  }
+  if (i < v.n_pt)
+    for (int k = 0; k < 3; k++) {
+      const double x = pt_xyz[3 * (size_t)i + k];
+      v.pt_xyz[0][3 * (size_t)i + k] = x;
+      v.pt_xyz[1][3 * (size_t)i + k] = x;
+    }
+  if (i < v.n_ln) {
+    double st[5];
+    line_from_x0_dir(ln_x0_dir + 6 * (size_t)i, ln_x0_dir + 6 * (size_t)i + 3, st);
+    for (int k = 0; k < 5; k++) {
+      v.ln_st[0][5 * (size_t)i + k] = st[k];
+      v.ln_st[1][5 * (size_t)i + k] = st[k];
+    }
+    v.ln_removed[i] = 0;
+  }
+  if (i < v.n_pe) {
+    v.pe_level[i] = 0;
+    v.pe_chi2[i] = 0.0;
+  }
+  if (i < v.n_lc) {
+    v.lc_level[2 * i] = 0;
+    v.lc_level[2 * i + 1] = (lc_right[4 * (size_t)i] < 0.f) ? 2 : 0;  // src/LineOptimizer.cc:65-68
+    v.lc_chi2[2 * i] = 0.0;
+    v.lc_chi2[2 * i + 1] = 0.0;
+  }
+  if (i < v.n_free_total)
+    for (int k = 0; k < 6; k++) v.g_x[6 * (size_t)i + k] = 0.0;
+}
+
+__global__ void k_round_init(BaView v, int maxit, int round) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= v.n_win) return;
+  v.w_phase[w] = (maxit > 0) ? PH_LIN : PH_DONE;
+  v.w_iter[w] = 0;
+  v.w_trials[w] = 0;
+  v.w_maxit[w] = maxit;
+  v.w_nbad[w] = 0;
+  v.w_ok[w] = 1;
+  v.w_lambda[w] = -1.0;
+  v.w_ni[w] = 2.0;
+  if (round == 0) {
+    v.w_sel[w] = 0;
+    v.w_nlog[w] = 0;
+    v.iter_done[2 * w] = 0;
+    v.iter_done[2 * w + 1] = 0;
+  }
+  if (w == 0) *v.n_active_win = (maxit > 0) ? v.n_win : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// linearisation: one thread per landmark
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void make_line_obs(const BaView& v, int kf, const float* seg, LineObs& o) {
+  if (v.prm.ln_norm) {  // K^-1 (x,y,1)  src/Optimizer.cc:234-235
+    const double* in = v.kf_intr + 5 * (size_t)kf;
+    o.x1[0] = ((double)seg[0] - in[2]) / in[0]; o.x1[1] = ((double)seg[1] - in[3]) / in[1];
+    o.x2[0] = ((double)seg[2] - in[2]) / in[0]; o.x2[1] = ((double)seg[3] - in[3]) / in[1];
+  } else {
+    o.x1[0] = seg[0]; o.x1[1] = seg[1];
+    o.x2[0] = seg[2]; o.x2[1] = seg[3];
+  }
+  o.x1[2] = 1.0;
+  o.x2[2] = 1.0;
+}
+
+__global__ void __launch_bounds__(LM_TPB) k_lin_points(BaView v) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= v.n_pt) return;
+  const int w = v.pt_win[p];
+  if (v.w_phase[w] != PH_LIN) return;
+  const int sel = v.w_sel[w];
+  const double* Xp = v.pt_xyz[sel] + 3 * (size_t)p;
+  const double X[3] = {Xp[0], Xp[1], Xp[2]};
+  double H[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+  double chi = 0;
+  int nact = 0;
+  const int e0 = v.pt_obs_off[p], e1 = v.pt_obs_off[p + 1];
+  for (int e = e0; e < e1; e++) {
+    const int kf = v.pe_kf[e];
+    const int g = v.kf_g[kf];
+    double* W = v.pe_W + 18 * (size_t)e;
+    if (v.pe_level[e] != 0) {
+      if (g >= 0)
+#pragma unroll
+        for (int k = 0; k < 18; k++) W[k] = 0.0;
+      continue;
+    }
+    nact++;
+    const double* Rt = v.pose_Rt[sel] + 12 * (size_t)kf;
+    const double* intr = v.kf_intr + 5 * (size_t)kf;
+    const float* obs = v.pe_uvr + 3 * (size_t)e;
+    const bool stereo = !(obs[2] < 0.f);
+    double xc[3], err[3], Jl[9];
+    map_Rt(Rt, X, xc);
+    pt_residual<true>(xc, intr, obs, stereo, err);
+    const double info = (double)v.pe_info[e];
+    const double c2 = err[0] * (info * err[0]) + err[1] * (info * err[1]) + err[2] * (info * err[2]);
+    double wgt = 1.0, rho = c2;
+    if (v.prm.robust_pt) rho = huber(c2, stereo ? v.prm.delta_pt_stereo : v.prm.delta_pt_mono, &wgt);
+    chi += rho;
+    const double wo = wgt * info;
+    pt_jac_point(xc, Rt, intr, stereo, Jl);
+    // Hll += Jl^T wo Jl ; bl -= Jl^T wo err
+    double JW[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) JW[k] = wo * Jl[k];
+    H[0] += JW[0] * Jl[0] + JW[3] * Jl[3] + JW[6] * Jl[6];
+    H[1] += JW[0] * Jl[1] + JW[3] * Jl[4] + JW[6] * Jl[7];
+    H[2] += JW[0] * Jl[2] + JW[3] * Jl[5] + JW[6] * Jl[8];
+    H[3] += JW[1] * Jl[1] + JW[4] * Jl[4] + JW[7] * Jl[7];
+    H[4] += JW[1] * Jl[2] + JW[4] * Jl[5] + JW[7] * Jl[8];
+    H[5] += JW[2] * Jl[2] + JW[5] * Jl[5] + JW[8] * Jl[8];
+#pragma unroll
+    for (int c = 0; c < 3; c++) bl[c] -= JW[c] * err[0] + JW[3 + c] * err[1] + JW[6 + c] * err[2];
+    if (g >= 0) {
+      double Jp[18];
+      pt_jac_pose(xc, intr, stereo, Jp);
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) W[r * 3 + c] = Jp[r] * JW[c] + Jp[6 + r] * JW[3 + c] + Jp[12 + r] * JW[6 + c];
+    }
+  }
+  double* Ho = v.pt_H + 9 * (size_t)p;
+#pragma unroll
+  for (int k = 0; k < 6; k++) Ho[k] = H[k];
+  Ho[6] = bl[0]; Ho[7] = bl[1]; Ho[8] = bl[2];
+  v.lm_chi2lin[p] = chi;
+  v.lm_maxdiag[p] = nact ? fmax(fabs(H[0]), fmax(fabs(H[3]), fabs(H[5]))) : 0.0;
+  v.lm_active[p] = nact > 0;
+}
+
+// index of (r,c), r<=c, in the packed upper triangle of a 4x4
+__device__ __forceinline__ constexpr int u4(int r, int c) { return r * 4 - (r * (r - 1)) / 2 + (c - r); }
+
+__global__ void __launch_bounds__(LM_TPB) k_lin_lines(BaView v) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= v.n_ln) return;
+  const int w = v.ln_win[l];
+  if (v.w_phase[w] != PH_LIN) return;
+  const int sel = v.w_sel[w];
+  const double* stp = v.ln_st[sel] + 5 * (size_t)l;
+  const double st[5] = {stp[0], stp[1], stp[2], stp[3], stp[4]};
+  double r1[3], r2[3], X1[3], X2[3];
+  line_axes(st, r1, r2);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    X1[i] = st[4] * r2[i];
+    X2[i] = X1[i] + r1[i];
+  }
+  double H[10], bl[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 10; k++) H[k] = 0;
+  double chi = 0;
+  int nact = 0;
+  const bool removed = v.ln_removed[l] != 0;
+  const int c0 = v.ln_obs_off[l], c1 = v.ln_obs_off[l + 1];
+  for (int c = c0; c < c1; c++) {
+    const int kf = v.lc_kf[c];
+    const int g = v.kf_g[kf];
+    double W[24];
+#pragma unroll
+    for (int k = 0; k < 24; k++) W[k] = 0.0;
+    const uint8_t lv0 = v.lc_level[2 * c], lv1 = v.lc_level[2 * c + 1];
+    if (!removed && (lv0 == 0 || lv1 == 0)) {
+      const double* Rt = v.pose_Rt[sel] + 12 * (size_t)kf;
+      const double* cam = v.kf_lcam + 4 * (size_t)kf;
+      double P1[3], P2[3];
+      map_Rt(Rt, X1, P1);
+      map_Rt(Rt, X2, P2);
+      const double delta = v.lc_stereo[c] ? v.prm.delta_ln_stereo : v.prm.delta_ln_mono;
+#pragma unroll 1
+      for (int side = 0; side < 2; side++) {
+        if ((side == 0 ? lv0 : lv1) != 0) continue;
+        nact++;
+        LineObs o;
+        make_line_obs(v, kf, (side == 0 ? v.lc_left : v.lc_right) + 4 * (size_t)c, o);
+        double err[2], Jp[12], Jl[8];
+        line_linearize<true>(P1, P2, cam[0], cam[1], cam[2], side ? -cam[3] : 0.0, o, Rt, X1, X2, r2, err, Jp, Jl);
+        const double info = v.lc_info[2 * (size_t)c + side];
+        const double c2 = err[0] * (info * err[0]) + err[1] * (info * err[1]);
+        double wgt = 1.0, rho = c2;
+        if (v.prm.robust_ln) rho = huber(c2, delta, &wgt);
+        chi += rho;
+        const double wo = wgt * info;
+        double JW[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) JW[k] = wo * Jl[k];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+          for (int cc = r; cc < 4; cc++) H[u4(r, cc)] += JW[r] * Jl[cc] + JW[4 + r] * Jl[4 + cc];
+          bl[r] -= JW[r] * err[0] + JW[4 + r] * err[1];
+        }
+        if (g >= 0) {
+#pragma unroll
+          for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) W[r * 4 + cc] += Jp[r] * JW[cc] + Jp[6 + r] * JW[4 + cc];
+        }
+      }
+    }
+    if (g >= 0) {
+      double* Wo = v.lc_W + 24 * (size_t)c;
+#pragma unroll
+      for (int k = 0; k < 24; k++) Wo[k] = W[k];
+    }
+  }
+  double* Ho = v.ln_H + 14 * (size_t)l;
+#pragma unroll
+  for (int k = 0; k < 10; k++) Ho[k] = H[k];
+#pragma unroll
+  for (int k = 0; k < 4; k++) Ho[10 + k] = bl[k];
+  const int li = v.n_pt + l;
+  v.lm_chi2lin[li] = chi;
+  v.lm_maxdiag[li] = nact ? fmax(fmax(fabs(H[u4(0, 0)]), fabs(H[u4(1, 1)])), fmax(fabs(H[u4(2, 2)]), fabs(H[u4(3, 3)]))) : 0.0;
+  v.lm_active[li] = nact > 0;
+}
+
+// pose pass: one CTA per chunk of a free keyframe's edge list; recomputes residual, weight and the pose Jacobian
+// and reduces Jp^T (w Omega) Jp and -Jp^T (w Omega) r in fixed order.
+__global__ void __launch_bounds__(LM_TPB) k_lin_poses(BaView v) {
+  const int ch = blockIdx.x;
+  const int g = v.ch_g[ch];
+  const int kf = v.g_kf[g];
+  const int w = v.kf_win[kf];
+  if (v.w_phase[w] != PH_LIN) return;
+  const int sel = v.w_sel[w];
+  __shared__ double sm[32];
+  const double* Rt = v.pose_Rt[sel] + 12 * (size_t)kf;
+  const double* intr = v.kf_intr + 5 * (size_t)kf;
+  const double* cam = v.kf_lcam + 4 * (size_t)kf;
+  double acc[28];
+#pragma unroll
+  for (int k = 0; k < 28; k++) acc[k] = 0.0;
+  for (int i = v.ch_begin[ch] + threadIdx.x; i < v.ch_end[ch]; i += blockDim.x) {
+    const int ref = v.kfl_ref[i];
+    if (ref >= 0) {
+      const int e = ref;
+      if (v.pe_level[e] != 0) continue;
+      const double* X = v.pt_xyz[sel] + 3 * (size_t)v.pe_pt[e];
+      const float* obs = v.pe_uvr + 3 * (size_t)e;
+      const bool stereo = !(obs[2] < 0.f);
+      double xc[3], err[3], Jp[18];
+      map_Rt(Rt, X, xc);
+      pt_residual<true>(xc, intr, obs, stereo, err);
+      const double info = (double)v.pe_info[e];
+      const double c2 = err[0] * (info * err[0]) + err[1] * (info * err[1]) + err[2] * (info * err[2]);
+      double wgt = 1.0;
+      if (v.prm.robust_pt) huber(c2, stereo ? v.prm.delta_pt_stereo : v.prm.delta_pt_mono, &wgt);
+      const double wo = wgt * info;
+      pt_jac_pose(xc, intr, stereo, Jp);
+      int k = 0;
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+#pragma unroll
+        for (int c = r; c < 6; c++, k++) acc[k] += wo * (Jp[r] * Jp[c] + Jp[6 + r] * Jp[6 + c] + Jp[12 + r] * Jp[12 + c]);
+        acc[21 + r] -= wo * (Jp[r] * err[0] + Jp[6 + r] * err[1] + Jp[12 + r] * err[2]);
+      }
+      acc[27] += 1.0;
+    } else {
+      const int c = ~ref;
+      const int l = v.lc_ln[c];
+      if (v.ln_removed[l]) continue;
+      const uint8_t lv0 = v.lc_level[2 * c], lv1 = v.lc_level[2 * c + 1];
+      if (lv0 != 0 && lv1 != 0) continue;
+      const double* stp = v.ln_st[sel] + 5 * (size_t)l;
+      const double st[5] = {stp[0], stp[1], stp[2], stp[3], stp[4]};
+      double r1[3], r2[3], X1[3], X2[3], P1[3], P2[3];
+      line_axes(st, r1, r2);
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        X1[q] = st[4] * r2[q];
+        X2[q] = X1[q] + r1[q];
+      }
+      map_Rt(Rt, X1, P1);
+      map_Rt(Rt, X2, P2);
+      const double delta = v.lc_stereo[c] ? v.prm.delta_ln_stereo : v.prm.delta_ln_mono;
+#pragma unroll 1
+      for (int side = 0; side < 2; side++) {
+        if ((side == 0 ? lv0 : lv1) != 0) continue;
+        LineObs o;
+        make_line_obs(v, kf, (side == 0 ? v.lc_left : v.lc_right) + 4 * (size_t)c, o);
+        double err[2], Jp[12];
+        line_linearize<false>(P1, P2, cam[0], cam[1], cam[2], side ? -cam[3] : 0.0, o, Rt, X1, X2, r2, err, Jp, nullptr);
+        const double info = v.lc_info[2 * (size_t)c + side];
+        const double c2 = err[0] * (info * err[0]) + err[1] * (info * err[1]);
+        double wgt = 1.0;
+        if (v.prm.robust_ln) huber(c2, delta, &wgt);
+        const double wo = wgt * info;
+        int k = 0;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+#pragma unroll
+          for (int cc = r; cc < 6; cc++, k++) acc[k] += wo * (Jp[r] * Jp[cc] + Jp[6 + r] * Jp[6 + cc]);
+          acc[21 + r] -= wo * (Jp[r] * err[0] + Jp[6 + r] * err[1]);
+        }
+        acc[27] += 1.0;
+      }
+    }
+  }
+#pragma unroll 1
+  for (int k = 0; k < 28; k++) {
+    const double s = block_sum(acc[k], sm);
+    if (threadIdx.x == 0) v.ch_pose[28 * (size_t)ch + k] = s;
+  }
+}
+
+// sum the chunk partials of each free keyframe (fixed order)
+__global__ void k_reduce_pose(BaView v) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = t / 28, k = t % 28;
+  if (g >= v.n_free_total) return;
+  const int w = v.kf_win[v.g_kf[g]];
+  if (v.w_phase[w] != PH_LIN) return;
+  double s = 0;
+  for (int ch = v.g_ch0[g]; ch < v.g_ch0[g + 1]; ch++) s += v.ch_pose[28 * (size_t)ch + k];
+  if (k < 21) v.g_Hpp[21 * (size_t)g + k] = s;
+  else if (k < 27) v.g_bp[6 * (size_t)g + (k - 21)] = s;
+  else v.g_nact[g] = (int)(s + 0.5);
+}
+
+// per-window reduction of the landmark scalars written by the linearisation (chi2, max diag, #active)
+__global__ void __launch_bounds__(256) k_reduce_lin(BaView v) {
+  const int w = blockIdx.x;
+  if (v.w_phase[w] != PH_LIN) return;
+  __shared__ double sm[32];
+  double chi = 0, mx = 0, na = 0;
+  for (int p = v.pt_off[w] + threadIdx.x; p < v.pt_off[w + 1]; p += blockDim.x) {
+    chi += v.lm_chi2lin[p];
+    mx = fmax(mx, v.lm_maxdiag[p]);
+    na += v.lm_active[p] ? 1.0 : 0.0;
+  }
+  for (int l = v.ln_off[w] + threadIdx.x; l < v.ln_off[w + 1]; l += blockDim.x) {
+    chi += v.lm_chi2lin[v.n_pt + l];
+    mx = fmax(mx, v.lm_maxdiag[v.n_pt + l]);
+    na += v.lm_active[v.n_pt + l] ? 1.0 : 0.0;
+  }
+  chi = block_sum(chi, sm);
+  na = block_sum(na, sm);
+  mx = block_max(mx, sm);
+  if (threadIdx.x == 0) {
+    v.w_red_sum[4 * w + 0] = chi;
+    v.w_red_sum[4 * w + 1] = 0.0;
+    v.w_red_sum[4 * w + 2] = na;
+    v.w_red_max[w] = mx;
+  }
+}
+
+// iteration start: currentChi, iniChi, lambda init at iteration 0 (optimization_algorithm_levenberg.cpp:75-97,166-180)
+__global__ void k_begin(BaView v) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= v.n_win) return;
+  if (v.w_phase[w] != PH_LIN) return;
+  const double chi = v.w_red_sum[4 * w + 0];
+  const int nact = (int)(v.w_red_sum[4 * w + 2] + 0.5);
+  if (nact == 0 && v.w_iter[w] == 0) {  // empty index mapping: optimize() returns without iterating
+    v.w_phase[w] = PH_DONE;
+    atomicSub(v.n_active_win, 1);
+    return;
+  }
+  v.w_curchi[w] = chi;
+  v.w_inichi[w] = chi;
+  v.w_trials[w] = 0;
+  if (v.w_iter[w] == 0) {
+    double mx = v.w_red_max[w];
+    for (int g = v.w_g0[w]; g < v.w_g0[w + 1]; g++) {
+      if (v.g_nact[g] == 0) continue;
+      const double* H = v.g_Hpp + 21 * (size_t)g;
+      int k = 0;
+      for (int r = 0; r < 6; r++) {
+        mx = fmax(mx, fabs(H[k]));
+        k += 6 - r;
+      }
+    }
+    v.w_lambda[w] = 1e-5 * mx;
+    v.w_ni[w] = 2.0;
+    v.w_nbad[w] = 0;
+    const int n = v.w_nlog[w];
+    if (n < v.log_stride) v.chi2_log[(size_t)w * v.log_stride + n] = chi;
+    v.w_nlog[w] = n + 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// trial: Schur complement pieces per landmark (lambda dependent)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LM_TPB) k_schur_points(BaView v) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= v.n_pt) return;
+  const int w = v.pt_win[p];
+  if (v.w_phase[w] == PH_DONE) return;
+  const double lam = v.w_lambda[w];
+  const double* Hi = v.pt_H + 9 * (size_t)p;
+  const bool act = v.lm_active[p];
+  double Di[9];
+  {
+    const double A[9] = {Hi[0] + lam, Hi[1], Hi[2], Hi[1], Hi[3] + lam, Hi[4], Hi[2], Hi[4], Hi[5] + lam};
+    inv3_sym(A, Di);
+  }
+  if (act) {
+    double* c = v.pt_c + 3 * (size_t)p;
+#pragma unroll
+    for (int i = 0; i < 3; i++) c[i] = Di[3 * i] * Hi[6] + Di[3 * i + 1] * Hi[7] + Di[3 * i + 2] * Hi[8];
+  }
+  for (int e = v.pt_obs_off[p]; e < v.pt_obs_off[p + 1]; e++) {
+    if (v.kf_g[v.pe_kf[e]] < 0) continue;
+    const double* W = v.pe_W + 18 * (size_t)e;
+    double* Y = v.pe_Y + 18 * (size_t)e;
+    if (!act || v.pe_level[e] != 0) {
+#pragma unroll
+      for (int k = 0; k < 18; k++) Y[k] = 0.0;
+      continue;
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      const double w0 = W[3 * r], w1 = W[3 * r + 1], w2 = W[3 * r + 2];
+#pragma unroll
+      for (int c = 0; c < 3; c++) Y[3 * r + c] = w0 * Di[c] + w1 * Di[3 + c] + w2 * Di[6 + c];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(LM_TPB) k_schur_lines(BaView v) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= v.n_ln) return;
+  const int w = v.ln_win[l];
+  if (v.w_phase[w] == PH_DONE) return;
+  const double lam = v.w_lambda[w];
+  const double* Hi = v.ln_H + 14 * (size_t)l;
+  const bool act = v.lm_active[v.n_pt + l];
+  double Di[16];
+  {
+    double A[16];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) A[4 * r + c] = Hi[r <= c ? u4(r, c) : u4(c, r)] + (r == c ? lam : 0.0);
+    inv4(A, Di);
+  }
+  if (act) {
+    double* c = v.ln_c + 4 * (size_t)l;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      c[i] = Di[4 * i] * Hi[10] + Di[4 * i + 1] * Hi[11] + Di[4 * i + 2] * Hi[12] + Di[4 * i + 3] * Hi[13];
+  }
+  for (int cc = v.ln_obs_off[l]; cc < v.ln_obs_off[l + 1]; cc++) {
+    if (v.kf_g[v.lc_kf[cc]] < 0) continue;
+    const double* W = v.lc_W + 24 * (size_t)cc;
+    double* Y = v.lc_Y + 24 * (size_t)cc;
+    if (!act) {
+#pragma unroll
+      for (int k = 0; k < 24; k++) Y[k] = 0.0;
+      continue;
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      const double w0 = W[4 * r], w1 = W[4 * r + 1], w2 = W[4 * r + 2], w3 = W[4 * r + 3];
+#pragma unroll
+      for (int c = 0; c < 4; c++) Y[4 * r + c] = w0 * Di[c] + w1 * Di[4 + c] + w2 * Di[8 + c] + w3 * Di[12 + c];
+    }
+  }
+}
+
+// Schur rows: CTA = one chunk of free keyframe a's edge list; thread t = (neighbour j, column c) owns the 6
+// accumulators S[a, nb_j][0..5][c] in registers.  Per list entry (landmark l seen by a):
+//   S[a,b] -= Y_(l,a) W_(l,b)^T  for every free b >= a that also sees l;   bschur[a] -= Y_(l,a) bl
+// (block_solver.hpp:381-440).  The co-edge of (l,b) is found through the rowslot byte table.
+__global__ void __launch_bounds__(1024) k_schur_rows(BaView v) {
+  const int ch = blockIdx.x;
+  const int g = v.ch_g[ch];
+  const int kf = v.g_kf[g];
+  const int w = v.kf_win[kf];
+  if (v.w_phase[w] == PH_DONE) return;
+  const int nnb = v.nb_off[g + 1] - v.nb_off[g];
+  const int t = threadIdx.x;
+  const bool live = t < 6 * nnb;
+  const int j = t / 6, c = t - 6 * j;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  double bacc = 0;
+  const int i0 = v.ch_begin[ch], i1 = v.ch_end[ch];
+  const uint8_t* slot_base = v.rowslot + v.rs_off[g] + (long long)(i0 - v.kfl_off[g]) * nnb + j;
+  if (live) {
+    for (int i = i0; i < i1; i++, slot_base += nnb) {
+      const int ref = v.kfl_ref[i];
+      const uint8_t slot = *slot_base;
+      if (ref >= 0) {
+        const int e = ref;
+        const double* Y = v.pe_Y + 18 * (size_t)e;
+        if (j == 0) {
+          const double* bl = v.pt_H + 9 * (size_t)v.pe_pt[e] + 6;
+          bacc += Y[3 * c] * bl[0] + Y[3 * c + 1] * bl[1] + Y[3 * c + 2] * bl[2];
+        }
+        if (slot != 0xFF) {
+          const int e2 = v.pt_obs_off[v.pe_pt[e]] + slot;
+          const double* Wr = v.pe_W + 18 * (size_t)e2 + 3 * c;
+          const double w0 = Wr[0], w1 = Wr[1], w2 = Wr[2];
+#pragma unroll
+          for (int r = 0; r < 6; r++) acc[r] += Y[3 * r] * w0 + Y[3 * r + 1] * w1 + Y[3 * r + 2] * w2;
+        }
+      } else {
+        const int cc = ~ref;
+        const double* Y = v.lc_Y + 24 * (size_t)cc;
+        if (j == 0) {
+          const double* bl = v.ln_H + 14 * (size_t)v.lc_ln[cc] + 10;
+          bacc += Y[4 * c] * bl[0] + Y[4 * c + 1] * bl[1] + Y[4 * c + 2] * bl[2] + Y[4 * c + 3] * bl[3];
+        }
+        if (slot != 0xFF) {
+          const int c2 = v.ln_obs_off[v.lc_ln[cc]] + slot;
+          const double* Wr = v.lc_W + 24 * (size_t)c2 + 4 * c;
+          const double w0 = Wr[0], w1 = Wr[1], w2 = Wr[2], w3 = Wr[3];
+#pragma unroll
+          for (int r = 0; r < 6; r++) acc[r] += Y[4 * r] * w0 + Y[4 * r + 1] * w1 + Y[4 * r + 2] * w2 + Y[4 * r + 3] * w3;
+        }
+      }
+    }
+    double* out = v.ch_S + v.ch_S_off[ch];
+    const int ld = 6 * nnb;
+#pragma unroll
+    for (int r = 0; r < 6; r++) out[(size_t)r * ld + t] = acc[r];
+    if (j == 0) out[(size_t)6 * ld + c] = bacc;
+  }
+}
+
+// S(a, nb_j) = [j==0] (Hpp_a + lambda I) - sum_chunks partial ; bschur_a = bp_a - sum_chunks partial_b
+__global__ void k_reduce_rows(BaView v, int with_diag) {
+  const int g = blockIdx.x;
+  const int w = v.kf_win[v.g_kf[g]];
+  if (v.w_phase[w] == PH_DONE) return;
+  const int nnb = v.nb_off[g + 1] - v.nb_off[g];
+  const int ld = 6 * nnb;
+  const double lam = v.w_lambda[w];
+  for (int t = threadIdx.x; t < ld; t += blockDim.x) {
+    const int j = t / 6, c = t - 6 * j;
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    for (int ch = v.g_ch0[g]; ch < v.g_ch0[g + 1]; ch++) {
+      const double* part = v.ch_S + v.ch_S_off[ch];
+#pragma unroll
+      for (int r = 0; r < 6; r++) s[r] += part[(size_t)r * ld + t];
+    }
+    double* S = v.S_blk + 36 * (size_t)(v.nb_off[g] + j);
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      double d = 0.0;
+      if (j == 0 && with_diag) {
+        const int rr = r < c ? r : c, cc = r < c ? c : r;
+        d = v.g_Hpp[21 * (size_t)g + (rr * 6 - (rr * (rr - 1)) / 2 + (cc - rr))];
+        if (r == c) d += lam;
+      }
+      S[6 * r + c] = d - s[r];
+    }
+    if (j == 0) {
+      double sb = 0;
+      for (int ch = v.g_ch0[g]; ch < v.g_ch0[g + 1]; ch++) sb += (v.ch_S + v.ch_S_off[ch])[(size_t)6 * ld + c];
+      v.g_bs[6 * (size_t)g + c] = (with_diag ? v.g_bp[6 * (size_t)g + c] : 0.0) - sb;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reduced camera system: dense LDL^T of one window by one CTA (lower triangle, row-major, leading dim ld)
+// stands in for LinearSolverEigen / LinearSolverDense (Thirdparty/g2o/g2o/solvers/*.h); failure = zero or
+// non-finite pivot.
+// ------------------------------------------------------------------------------------------------
+__device__ bool ldlt_solve_cta(double* A, int n, int ld, double* b /*in: rhs, out: x*/, double* tmp, int* flag) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) *flag = 1;
+  __syncthreads();
+  for (int j = 0; j < n; j++) {
+    const double d = A[(size_t)j * ld + j];
+    if (!(d != 0.0) || !isfinite(d)) {
+      if (tid == 0) *flag = 0;
+      __syncthreads();
+      return false;
+    }
+    const double id = 1.0 / d;
+    for (int i = j + 1 + tid; i < n; i += nt) {
+      const double a = A[(size_t)i * ld + j];
+      tmp[i] = a;
+      A[(size_t)i * ld + j] = a * id;
+    }
+    __syncthreads();
+    const int m = n - j - 1;
+    // trailing update on the lower triangle: A[i][k] -= L[i][j] * tmp[k], j < k <= i
+    for (int idx = tid; idx < m * m; idx += nt) {
+      const int ii = idx / m, kk = idx - ii * m;
+      if (kk <= ii) {
+        const int i = j + 1 + ii, k = j + 1 + kk;
+        A[(size_t)i * ld + k] -= A[(size_t)i * ld + j] * tmp[k];
+      }
+    }
+    __syncthreads();
+  }
+  // forward: L z = b
+  for (int j = 0; j < n; j++) {
+    const double bj = b[j];
+    for (int i = j + 1 + tid; i < n; i += nt) b[i] -= A[(size_t)i * ld + j] * bj;
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += nt) b[i] /= A[(size_t)i * ld + i];
+  __syncthreads();
+  // backward: L^T x = z
+  for (int j = n - 1; j >= 0; j--) {
+    const double xj = b[j];
+    for (int i = tid; i < j; i += nt) b[i] -= A[(size_t)j * ld + i] * xj;
+    __syncthreads();
+  }
+  return true;
+}
+
+// one CTA per window: assemble the dense reduced camera system from the block rows, factor, solve, apply the
+// pose update T <- exp(x) T into the trial buffer and accumulate the pose part of computeScale().
+template <bool SMEM>
+__global__ void __launch_bounds__(256) k_solve(BaView v) {
+  extern __shared__ double smem[];
+  const int w = blockIdx.x;
+  if (v.w_phase[w] == PH_DONE) return;
+  const int g0 = v.w_g0[w], nf = v.w_g0[w + 1] - g0;
+  const int n = 6 * nf;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ int flag;
+  __shared__ double red[32];
+  double* A = SMEM ? smem : (v.solve_scratch + v.w_scratch_off[w]);
+  double* rhs = SMEM ? (smem + (size_t)n * n) : (A + (size_t)n * n);
+  double* tmp = rhs + n;
+  const int sel = v.w_sel[w];
+  bool ok = true;
+  if (n > 0) {
+    for (int idx = tid; idx < n * n; idx += nt) A[idx] = 0.0;
+    __syncthreads();
+    for (int a = 0; a < nf; a++) {
+      const int g = g0 + a;
+      const int nb0 = v.nb_off[g], nnb = v.nb_off[g + 1] - nb0;
+      for (int idx = tid; idx < nnb * 36; idx += nt) {
+        const int j = idx / 36, rc = idx - 36 * j, r = rc / 6, c = rc - 6 * r;
+        const int b = v.nb_g[nb0 + j] - g0;
+        if (j == 0 && c < r) continue;  // diagonal block: keep one triangle
+        A[(size_t)(6 * b + c) * n + (6 * a + r)] = v.S_blk[36 * (size_t)(nb0 + j) + rc];
+      }
+    }
+    for (int i = tid; i < n; i += nt) rhs[i] = v.g_bs[6 * (size_t)g0 + i];
+    __syncthreads();
+    ok = ldlt_solve_cta(A, n, n, rhs, tmp, &flag);
+    __syncthreads();
+    if (ok)
+      for (int i = tid; i < n; i += nt) v.g_x[6 * (size_t)g0 + i] = rhs[i];
+    __syncthreads();
+  }
+  // pose update into the trial buffer; fixed / inactive keyframes are carried over unchanged
+  for (int k = v.kf_off[w] + tid; k < v.kf_off[w + 1]; k += nt) {
+    const int g = v.kf_g[k];
+    double qt[7];
+    const double* src = v.pose_qt[sel] + 7 * (size_t)k;
+    if (g >= 0 && v.g_nact[g] > 0) {
+      pose_oplus(src, v.g_x + 6 * (size_t)g, qt);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 7; q++) qt[q] = src[q];
+    }
+    double Rt[12];
+    pose_to_Rt(qt, Rt);
+    double* dq = v.pose_qt[sel ^ 1] + 7 * (size_t)k;
+    double* dr = v.pose_Rt[sel ^ 1] + 12 * (size_t)k;
+#pragma unroll
+    for (int q = 0; q < 7; q++) dq[q] = qt[q];
+#pragma unroll
+    for (int q = 0; q < 12; q++) dr[q] = Rt[q];
+  }
+  // scale contribution of the poses: sum x (lambda x + b)   (computeScale, levenberg.cpp:182-189)
+  const double lam = v.w_lambda[w];
+  double sc = 0;
+  for (int i = tid; i < n; i += nt) {
+    const int g = g0 + i / 6;
+    if (v.g_nact[g] == 0) continue;
+    const double x = v.g_x[6 * (size_t)g0 + i];
+    sc += x * (lam * x + v.g_bp[6 * (size_t)g0 + i]);
+  }
+  sc = block_sum(sc, red);
+  if (tid == 0) {
+    v.w_scale_p[w] = sc;
+    v.w_ok[w] = ok ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// back-substitution + update + error at the trial state (one thread per landmark)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LM_TPB) k_backsub_points(BaView v) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= v.n_pt) return;
+  const int w = v.pt_win[p];
+  if (v.w_phase[w] == PH_DONE) return;
+  const int sel = v.w_sel[w];
+  const double* Xo = v.pt_xyz[sel] + 3 * (size_t)p;
+  double* Xn = v.pt_xyz[sel ^ 1] + 3 * (size_t)p;
+  if (!v.lm_active[p]) {
+    Xn[0] = Xo[0]; Xn[1] = Xo[1]; Xn[2] = Xo[2];
+    v.lm_chi2[p] = 0.0;
+    v.lm_scale[p] = 0.0;
+    return;
+  }
+  const double* cp = v.pt_c + 3 * (size_t)p;
+  double xl[3] = {cp[0], cp[1], cp[2]};
+  const int e0 = v.pt_obs_off[p], e1 = v.pt_obs_off[p + 1];
+  for (int e = e0; e < e1; e++) {
+    if (v.pe_level[e] != 0) continue;
+    const int g = v.kf_g[v.pe_kf[e]];
+    if (g < 0) continue;
+    const double* Y = v.pe_Y + 18 * (size_t)e;
+    const double* xp = v.g_x + 6 * (size_t)g;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      const double x = xp[r];
+      xl[0] -= Y[3 * r] * x; xl[1] -= Y[3 * r + 1] * x; xl[2] -= Y[3 * r + 2] * x;
+    }
+  }
+  const double X[3] = {Xo[0] + xl[0], Xo[1] + xl[1], Xo[2] + xl[2]};
+  Xn[0] = X[0]; Xn[1] = X[1]; Xn[2] = X[2];
+  const double lam = v.w_lambda[w];
+  const double* bl = v.pt_H + 9 * (size_t)p + 6;
+  v.lm_scale[p] = xl[0] * (lam * xl[0] + bl[0]) + xl[1] * (lam * xl[1] + bl[1]) + xl[2] * (lam * xl[2] + bl[2]);
+  double chi = 0;
+  for (int e = e0; e < e1; e++) {
+    if (v.pe_level[e] != 0) continue;
+    const int kf = v.pe_kf[e];
+    const double* Rt = v.pose_Rt[sel ^ 1] + 12 * (size_t)kf;
+    const float* obs = v.pe_uvr + 3 * (size_t)e;
+    const bool stereo = !(obs[2] < 0.f);
+    double xc[3], err[3];
+    map_Rt(Rt, X, xc);
+    pt_residual<true>(xc, v.kf_intr + 5 * (size_t)kf, obs, stereo, err);
+    const double info = (double)v.pe_info[e];
+    const double c2 = err[0] * (info * err[0]) + err[1] * (info * err[1]) + err[2] * (info * err[2]);
+    v.pe_chi2[e] = c2;
+    double wgt;
+    chi += v.prm.robust_pt ? huber(c2, stereo ? v.prm.delta_pt_stereo : v.prm.delta_pt_mono, &wgt) : c2;
+  }
+  v.lm_chi2[p] = chi;
+}
+
+__global__ void __launch_bounds__(LM_TPB) k_backsub_lines(BaView v) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= v.n_ln) return;
+  const int w = v.ln_win[l];
+  if (v.w_phase[w] == PH_DONE) return;
+  const int sel = v.w_sel[w];
+  const int li = v.n_pt + l;
+  const double* so = v.ln_st[sel] + 5 * (size_t)l;
+  double* sn = v.ln_st[sel ^ 1] + 5 * (size_t)l;
+  if (!v.lm_active[li]) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) sn[k] = so[k];
+    v.lm_chi2[li] = 0.0;
+    v.lm_scale[li] = 0.0;
+    return;
+  }
+  const double* cp = v.ln_c + 4 * (size_t)l;
+  double xl[4] = {cp[0], cp[1], cp[2], cp[3]};
+  const int c0 = v.ln_obs_off[l], c1 = v.ln_obs_off[l + 1];
+  for (int c = c0; c < c1; c++) {
+    const int g = v.kf_g[v.lc_kf[c]];
+    if (g < 0) continue;
+    const double* Y = v.lc_Y + 24 * (size_t)c;
+    const double* xp = v.g_x + 6 * (size_t)g;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      const double x = xp[r];
+      xl[0] -= Y[4 * r] * x; xl[1] -= Y[4 * r + 1] * x; xl[2] -= Y[4 * r + 2] * x; xl[3] -= Y[4 * r + 3] * x;
+    }
+  }
+  const double st0[5] = {so[0], so[1], so[2], so[3], so[4]};
+  double st[5];
+  line_oplus(st0, xl, st);
+#pragma unroll
+  for (int k = 0; k < 5; k++) sn[k] = st[k];
+  const double lam = v.w_lambda[w];
+  const double* bl = v.ln_H + 14 * (size_t)l + 10;
+  v.lm_scale[li] = xl[0] * (lam * xl[0] + bl[0]) + xl[1] * (lam * xl[1] + bl[1]) + xl[2] * (lam * xl[2] + bl[2]) +
+                   xl[3] * (lam * xl[3] + bl[3]);
+  double r1[3], r2[3], X1[3], X2[3];
+  line_axes(st, r1, r2);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    X1[i] = st[4] * r2[i];
+    X2[i] = X1[i] + r1[i];
+  }
+  double chi = 0;
+  for (int c = c0; c < c1; c++) {
+    const uint8_t lv0 = v.lc_level[2 * c], lv1 = v.lc_level[2 * c + 1];
+    if (lv0 != 0 && lv1 != 0) continue;
+    const int kf = v.lc_kf[c];
+    const double* Rt = v.pose_Rt[sel ^ 1] + 12 * (size_t)kf;
+    const double* cam = v.kf_lcam + 4 * (size_t)kf;
+    double P1[3], P2[3];
+    map_Rt(Rt, X1, P1);
+    map_Rt(Rt, X2, P2);
+    const double delta = v.lc_stereo[c] ? v.prm.delta_ln_stereo : v.prm.delta_ln_mono;
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+      if ((side == 0 ? lv0 : lv1) != 0) continue;
+      LineObs o;
+      make_line_obs(v, kf, (side == 0 ? v.lc_left : v.lc_right) + 4 * (size_t)c, o);
+      double err[2];
+      line_residual(P1, P2, cam[0], cam[1], cam[2], side ? -cam[3] : 0.0, o, err);
+      const double info = v.lc_info[2 * (size_t)c + side];
+      const double c2 = err[0] * (info * err[0]) + err[1] * (info * err[1]);
+      v.lc_chi2[2 * (size_t)c + side] = c2;
+      double wgt;
+      chi += v.prm.robust_ln ? huber(c2, delta, &wgt) : c2;
+    }
+  }
+  v.lm_chi2[li] = chi;
+}
+
+__global__ void __launch_bounds__(256) k_reduce_trial(BaView v) {
+  const int w = blockIdx.x;
+  if (v.w_phase[w] == PH_DONE) return;
+  __shared__ double sm[32];
+  double chi = 0, sc = 0;
+  for (int p = v.pt_off[w] + threadIdx.x; p < v.pt_off[w + 1]; p += blockDim.x) {
+    chi += v.lm_chi2[p];
+    sc += v.lm_scale[p];
+  }
+  for (int l = v.ln_off[w] + threadIdx.x; l < v.ln_off[w + 1]; l += blockDim.x) {
+    chi += v.lm_chi2[v.n_pt + l];
+    sc += v.lm_scale[v.n_pt + l];
+  }
+  chi = block_sum(chi, sm);
+  sc = block_sum(sc, sm);
+  if (threadIdx.x == 0) {
+    v.w_red_sum[4 * w + 0] = chi;
+    v.w_red_sum[4 * w + 1] = sc;
+  }
+}
+
+// accept / reject and the outer-iteration bookkeeping (optimization_algorithm_levenberg.cpp:99-164,
+// sparse_optimizer.cpp:376-418)
+__global__ void k_decide(BaView v, int round, int stop_now) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= v.n_win) return;
+  if (v.w_phase[w] == PH_DONE) return;
+  double tempChi = v.w_red_sum[4 * w + 0];
+  if (!v.w_ok[w]) tempChi = DBL_MAX;
+  const double cur = v.w_curchi[w];
+  double rho = cur - tempChi;
+  double scale = v.w_scale_p[w] + v.w_red_sum[4 * w + 1];
+  scale += 1e-3;
+  rho /= scale;
+  double lam = v.w_lambda[w], ni = v.w_ni[w];
+  double newcur = cur;
+  if (rho > 0 && isfinite(tempChi)) {
+    double alpha = 1. - pow((2 * rho - 1), 3);
+    alpha = fmin(alpha, 2. / 3.);
+    const double sf = fmax(1. / 3., alpha);
+    lam *= sf;
+    ni = 2;
+    newcur = tempChi;
+    v.w_sel[w] ^= 1;  // the trial buffer becomes the estimate (discardTop)
+  } else {
+    lam *= ni;
+    ni *= 2;  // pop(): the estimate buffer is untouched
+  }
+  v.w_lambda[w] = lam;
+  v.w_ni[w] = ni;
+  v.w_curchi[w] = newcur;
+  const int q = v.w_trials[w] + 1;
+  v.w_trials[w] = q;
+  if (rho < 0 && q < 10 && !stop_now) {
+    v.w_phase[w] = PH_RETRY;
+    return;
+  }
+  // end of this outer iteration
+  const int n = v.w_nlog[w];
+  if (n < v.log_stride) {
+    v.chi2_log[(size_t)w * v.log_stride + n] = newcur;
+    v.lambda_log[(size_t)w * v.log_stride + n - 1 - round] = lam;
+    v.trials_log[(size_t)w * v.log_stride + n - 1 - round] = q;
+  }
+  v.w_nlog[w] = n + 1;
+  const int it = v.w_iter[w] + 1;
+  v.w_iter[w] = it;
+  v.iter_done[2 * w + round] = it;
+  bool term = (q == 10 || rho == 0);
+  if (!term) {
+    const double ini = v.w_inichi[w];
+    int nb = v.w_nbad[w];
+    if ((ini - newcur) * 1e3 < ini) nb++;
+    else nb = 0;
+    v.w_nbad[w] = nb;
+    if (nb >= 3) term = true;
+  }
+  if (term || it >= v.w_maxit[w] || stop_now) {
+    v.w_phase[w] = PH_DONE;
+    atomicSub(v.n_active_win, 1);
+  } else {
+    v.w_phase[w] = PH_LIN;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// outlier gating between the two rounds of LocalBundleAdjustment and final classification
+// ------------------------------------------------------------------------------------------------
+// src/Optimizer.cc:1239-1267 : chi2 of the LAST computed error (stale semantics) and depth at the current estimate
+__global__ void k_flag_points(BaView v, uint8_t* bad_out /*nullptr: gate (set level); else: final flags*/) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= v.n_pe) return;
+  const int p = v.pe_pt[e];
+  const int w = v.pt_win[p];
+  const int sel = v.w_sel[w];
+  const float* obs = v.pe_uvr + 3 * (size_t)e;
+  const bool stereo = !(obs[2] < 0.f);
+  const double th = stereo ? v.prm.chi2_pt_stereo : v.prm.chi2_pt_mono;
+  double xc[3];
+  map_Rt(v.pose_Rt[sel] + 12 * (size_t)v.pe_kf[e], v.pt_xyz[sel] + 3 * (size_t)p, xc);
+  const bool bad = (v.pe_chi2[e] > th) || !(xc[2] > 0.0);
+  if (bad_out) bad_out[e] = bad ? 1 : 0;
+  else if (bad) v.pe_level[e] = 1;
+}
+
+__device__ __forceinline__ bool line_edge_depth_ok(const BaView& v, int sel, int kf, const double* X1, const double* X2,
+                                                   int side, const LineObs& o) {
+  const double* Rt = v.pose_Rt[sel] + 12 * (size_t)kf;
+  const double* cam = v.kf_lcam + 4 * (size_t)kf;
+  double P1[3], P2[3];
+  map_Rt(Rt, X1, P1);
+  map_Rt(Rt, X2, P2);
+  const double bx = side ? -cam[3] : 0.0;
+  const double X0c[3] = {P1[0] + bx, P1[1], P1[2]};
+  const double ldc[3] = {P2[0] - P1[0], P2[1] - P1[1], P2[2] - P1[2]};
+  return line_depth_positive(X0c, ldc, cam[0], cam[1], cam[2], o.x1, o.x2);
+}
+
+// LineOptimizer::DisableOutliers  src/LineOptimizer.cc:129-170 (one thread per line)
+__global__ void k_flag_lines(BaView v) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= v.n_ln) return;
+  const int w = v.ln_win[l];
+  const int sel = v.w_sel[w];
+  const double* stp = v.ln_st[sel] + 5 * (size_t)l;
+  const double st[5] = {stp[0], stp[1], stp[2], stp[3], stp[4]};
+  double r1[3], r2[3], X1[3], X2[3];
+  line_axes(st, r1, r2);
+  for (int i = 0; i < 3; i++) {
+    X1[i] = st[4] * r2[i];
+    X2[i] = X1[i] + r1[i];
+  }
+  int cnt = 0, nedge = 0;
+  for (int c = v.ln_obs_off[l]; c < v.ln_obs_off[l + 1]; c++) {
+    const int kf = v.lc_kf[c];
+    const double d = v.lc_stereo[c] ? v.prm.delta_ln_stereo : v.prm.delta_ln_mono;
+    const double thr = d * d;
+    for (int side = 0; side < 2; side++) {
+      if (v.lc_level[2 * c + side] == 2) continue;
+      nedge++;
+      LineObs o;
+      make_line_obs(v, kf, (side == 0 ? v.lc_left : v.lc_right) + 4 * (size_t)c, o);
+      const bool dp = line_edge_depth_ok(v, sel, kf, X1, X2, side, o);
+      if (v.lc_chi2[2 * (size_t)c + side] > thr || !dp) v.lc_level[2 * c + side] = 1;
+      else cnt += 2;
+    }
+  }
+  if (nedge > 0 && cnt <= v.prm.ln_filter) v.ln_removed[l] = 1;
+}
+
+// LineOptimizer::GetLineData  src/LineOptimizer.cc:172-201 : depth first, then the error recomputed at the final state
+__global__ void k_final_lines(BaView v, uint8_t* bad_out /*[n_lc][2]*/) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= v.n_ln) return;
+  const int w = v.ln_win[l];
+  const int sel = v.w_sel[w];
+  const bool removed = v.ln_removed[l] != 0;
+  const double* stp = v.ln_st[sel] + 5 * (size_t)l;
+  const double st[5] = {stp[0], stp[1], stp[2], stp[3], stp[4]};
+  double r1[3], r2[3], X1[3], X2[3];
+  line_axes(st, r1, r2);
+  for (int i = 0; i < 3; i++) {
+    X1[i] = st[4] * r2[i];
+    X2[i] = X1[i] + r1[i];
+  }
+  for (int c = v.ln_obs_off[l]; c < v.ln_obs_off[l + 1]; c++) {
+    const int kf = v.lc_kf[c];
+    const double d = v.lc_stereo[c] ? v.prm.delta_ln_stereo : v.prm.delta_ln_mono;
+    const double thr = d * d;
+    for (int side = 0; side < 2; side++) {
+      uint8_t bad = 0;
+      if (!removed && v.lc_level[2 * c + side] != 2) {
+        LineObs o;
+        make_line_obs(v, kf, (side == 0 ? v.lc_left : v.lc_right) + 4 * (size_t)c, o);
+        const bool dp = line_edge_depth_ok(v, sel, kf, X1, X2, side, o);
+        const double* Rt = v.pose_Rt[sel] + 12 * (size_t)kf;
+        const double* cam = v.kf_lcam + 4 * (size_t)kf;
+        double P1[3], P2[3], err[2];
+        map_Rt(Rt, X1, P1);
+        map_Rt(Rt, X2, P2);
+        line_residual(P1, P2, cam[0], cam[1], cam[2], side ? -cam[3] : 0.0, o, err);
+        const double info = v.lc_info[2 * (size_t)c + side];
+        const double c2 = err[0] * (info * err[0]) + err[1] * (info * err[1]);
+        bad = (c2 > thr || !dp) ? 1 : 0;
+      }
+      bad_out[2 * (size_t)c + side] = bad;
+    }
+  }
+}
+
+// gather the selected state buffers into the output layout
+__global__ void k_export(BaView v, double* kf_Tcw, double* pt_xyz, double* ln_x0_dir, const double* ln_x0_dir_in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < v.n_kf) {
+    const int sel = v.w_sel[v.kf_win[i]];
+    for (int k = 0; k < 12; k++) kf_Tcw[12 * (size_t)i + k] = v.pose_Rt[sel][12 * (size_t)i + k];
+  }
+  if (i < v.n_pt) {
+    const int sel = v.w_sel[v.pt_win[i]];
+    for (int k = 0; k < 3; k++) pt_xyz[3 * (size_t)i + k] = v.pt_xyz[sel][3 * (size_t)i + k];
+  }
+  if (i < v.n_ln) {
+    const int sel = v.w_sel[v.ln_win[i]];
+    if (v.ln_removed[i]) {
+      for (int k = 0; k < 6; k++) ln_x0_dir[6 * (size_t)i + k] = ln_x0_dir_in[6 * (size_t)i + k];
+    } else {
+      const double* stp = v.ln_st[sel] + 5 * (size_t)i;
+      const double st[5] = {stp[0], stp[1], stp[2], stp[3], stp[4]};
+      double r1[3], r2[3];
+      line_axes(st, r1, r2);
+      for (int k = 0; k < 3; k++) {
+        ln_x0_dir[6 * (size_t)i + k] = st[4] * r2[k];
+        ln_x0_dir[6 * (size_t)i + 3 + k] = r1[k];
+      }
+    }
+  }
+}
+
+}  // namespace lld

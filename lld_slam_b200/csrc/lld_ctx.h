@@ -1,0 +1,93 @@
+// lld_ctx.h — per-thread context (stream, workspace, timing) shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/lldba.h"
+
+struct BaState;      // ba.cu
+struct ncclComm;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  // grow-only device allocation; contents are NOT preserved on growth
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct LldCtx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  char err[512] = {0};
+  int64_t launches = 0;
+  float ms_h2d = 0, ms_compute = 0, ms_d2h = 0;
+  int sm_count = 148;
+  // NCCL (global BA)
+  ncclComm* comm = nullptr;
+  int n_ranks = 1, rank = 0;
+  // pooled device buffers, reused across calls (index = allocation order inside one call)
+  std::vector<DevBuf> pool;
+  size_t pool_next = 0;
+  // pinned host scratch for small read-backs
+  void* pinned = nullptr;
+  size_t pinned_cap = 0;
+  BaState* ba = nullptr;
+
+  void pool_reset() { pool_next = 0; }
+  template <typename T>
+  T* alloc(size_t n, cudaError_t* e) {
+    if (pool_next >= pool.size()) pool.emplace_back();
+    DevBuf& b = pool[pool_next++];
+    cudaError_t r = b.reserve(n * sizeof(T) + 16);
+    if (r != cudaSuccess) {
+      *e = r;
+      return nullptr;
+    }
+    return reinterpret_cast<T*>(b.p);
+  }
+};
+
+#define LLD_CUDA(ctx, call)                                                                            \
+  do {                                                                                                 \
+    cudaError_t _e = (call);                                                                           \
+    if (_e != cudaSuccess) {                                                                           \
+      snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      return LLD_ERR_CUDA;                                                                             \
+    }                                                                                                  \
+  } while (0)
+
+#define LLD_ARG(ctx, cond)                                                                     \
+  do {                                                                                         \
+    if (!(cond)) {                                                                             \
+      snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d bad argument: %s", __FILE__, __LINE__, #cond); \
+      return LLD_ERR_ARG;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+// kernel launch with bookkeeping (the launch count feeds bench.py's gpu_launches)
+#define LLD_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
+  do {                                                                          \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);            \
+    (ctx)->launches++;                                                          \
+  } while (0)
+
+static inline LldCtx* lld_ctx_cast(void* p) { return reinterpret_cast<LldCtx*>(p); }

@@ -1,0 +1,212 @@
+"""GPU parity tests: the CUDA library (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances are the ones BASELINE.json's north_star states: per-iteration chi2 within 1e-6 relative, final poses within
+1e-5 m / 1e-6 rad, identical inlier / outlier flags; Hamming matches and distances bit-exact; float line-descriptor
+distances within 1e-5 * max(1, d).
+"""
+import numpy as np
+import pytest
+
+from lld_slam_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+CHI2_RTOL = 1e-6
+POS_TOL = 1e-5
+ROT_TOL = 1e-6
+
+
+def rot_angle(Ta, Tb):
+    Ra = Ta[:, :9].reshape(-1, 3, 3)
+    Rb = Tb[:, :9].reshape(-1, 3, 3)
+    d = np.einsum("nij,nik->njk", Ra, Rb) - np.eye(3)
+    return np.linalg.norm(d.reshape(-1, 9), axis=1) / np.sqrt(2.0)
+
+
+def check_ba(g, o, what=""):
+    assert np.array_equal(g["n_iter_done"], o["n_iter_done"]), f"{what} iterations {g['n_iter_done']} vs {o['n_iter_done']}"
+    assert np.array_equal(g["trials_log"], o["trials_log"]), f"{what} LM trials differ"
+    den = np.maximum(np.abs(o["chi2_log"]), 1e-9)
+    rel = np.abs(g["chi2_log"] - o["chi2_log"]) / den
+    assert rel.max() <= CHI2_RTOL, f"{what} chi2 rel err {rel.max():.3e}\n gpu {g['chi2_log']}\n ora {o['chi2_log']}"
+    lrel = np.abs(g["lambda_log"] - o["lambda_log"]) / np.maximum(np.abs(o["lambda_log"]), 1e-30)
+    assert lrel.max() <= 1e-5, f"{what} lambda rel err {lrel.max():.3e}"
+    assert np.array_equal(g["pt_obs_bad"], o["pt_obs_bad"]), f"{what} point flags differ at {np.nonzero(g['pt_obs_bad'] != o['pt_obs_bad'])[0][:10]}"
+    assert np.array_equal(g["ln_obs_bad"], o["ln_obs_bad"]), f"{what} line flags differ"
+    assert np.array_equal(g["ln_removed"], o["ln_removed"]), f"{what} removed lines differ"
+    dt = np.abs(g["kf_Tcw"][:, 9:] - o["kf_Tcw"][:, 9:]).max()
+    assert dt <= POS_TOL, f"{what} pose translation diff {dt:.3e} m"
+    dr = rot_angle(g["kf_Tcw"], o["kf_Tcw"]).max()
+    assert dr <= ROT_TOL, f"{what} pose rotation diff {dr:.3e} rad"
+    if g["pt_xyz"].size:
+        dp = np.abs(g["pt_xyz"] - o["pt_xyz"]).max()
+        assert dp <= 1e-4, f"{what} point diff {dp:.3e} m"
+    if g["ln_x0_dir"].size:
+        dl = np.abs(g["ln_x0_dir"] - o["ln_x0_dir"]).max()
+        assert dl <= 1e-4, f"{what} line diff {dl:.3e}"
+
+
+def test_local_ba_cfg1(gpu_ctx):
+    """BASELINE config 1: 10 KF / 2k points / 400 lines, reference schedule 5 + 15."""
+    p = synth.make_local_ba_batch(1, 10, 2000, 400, synth.seed_for(1))
+    g = api.ba_local(p, 5, 15, impl="gpu", ctx=gpu_ctx)
+    o = api.ba_local(p, 5, 15, impl="oracle")
+    assert gpu_ctx.launch_count() > 0
+    check_ba(g, o, "cfg1")
+
+
+def test_local_ba_flat10(gpu_ctx):
+    """config 1 with 10 LM iterations flat (no second round)."""
+    p = synth.make_local_ba_batch(1, 10, 2000, 400, synth.seed_for(1) + 7)
+    g = api.ba_local(p, 10, 0, impl="gpu", ctx=gpu_ctx)
+    o = api.ba_local(p, 10, 0, impl="oracle")
+    check_ba(g, o, "flat10")
+
+
+def test_local_ba_batch_ragged(gpu_ctx):
+    """several independent windows of different shapes in one batch, incl. extra fixed cameras."""
+    rng = np.random.default_rng(5)
+    wins = [synth.make_ba_window(8, 500, 100, rng, n_fixed_extra=2),
+            synth.make_ba_window(5, 300, 0, rng),
+            synth.make_ba_window(12, 50, 200, rng),
+            synth.make_ba_window(20, 800, 150, rng, n_fixed_extra=1),
+            synth.make_ba_window(3, 40, 10, rng)]
+    p = synth.batch_ba(wins, "local")
+    g = api.ba_local(p, 5, 15, impl="gpu", ctx=gpu_ctx)
+    o = api.ba_local(p, 5, 15, impl="oracle")
+    check_ba(g, o, "ragged")
+
+
+def test_local_ba_target_shape(gpu_ctx):
+    """north_star target shape 10 KF / 5k points / 1k lines."""
+    p = synth.make_local_ba_batch(1, 10, 5000, 1000, 77)
+    g = api.ba_local(p, 5, 15, impl="gpu", ctx=gpu_ctx)
+    o = api.ba_local(p, 5, 15, impl="oracle")
+    check_ba(g, o, "target")
+
+
+def test_local_ba_large_window_global_solve(gpu_ctx):
+    """a window whose reduced camera system does not fit shared memory (30 KFs -> 174 unknowns)."""
+    p = synth.make_local_ba_batch(1, 30, 1500, 300, 31)
+    g = api.ba_local(p, 5, 10, impl="gpu", ctx=gpu_ctx)
+    o = api.ba_local(p, 5, 10, impl="oracle")
+    check_ba(g, o, "large")
+
+
+def test_local_ba_stop_flag(gpu_ctx):
+    """pbStopFlag already set on entry: nothing is optimised (src/Optimizer.cc:1220-1222)."""
+    p = synth.make_local_ba_batch(1, 6, 200, 40, 3)
+    stop = np.ones(1, np.uint8)
+    g = api.ba_local(p, 5, 15, impl="gpu", ctx=gpu_ctx, stop=stop)
+    o = api.ba_local(p, 5, 15, impl="oracle", stop=stop)
+    assert np.array_equal(g["n_iter_done"], o["n_iter_done"])
+    assert np.abs(g["kf_Tcw"] - o["kf_Tcw"]).max() < 1e-12
+    assert np.abs(g["pt_xyz"] - p["pt_xyz"]).max() == 0
+
+
+@pytest.mark.parametrize("robust", [False, True])
+def test_global_ba_small(gpu_ctx, robust):
+    p = synth.make_global_ba(40, 4000, 800, 11, robust_points=robust)
+    g = api.ba_global(p, 10, impl="gpu", ctx=gpu_ctx)
+    o = api.ba_global(p, 10, impl="oracle")
+    check_ba(g, o, f"gba robust={robust}")
+
+
+def test_local_ba_reproducible(gpu_ctx):
+    """fixed-order reductions: two runs give bit-identical results."""
+    p = synth.make_local_ba_batch(3, 10, 800, 160, 21)
+    a = api.ba_local(p, 5, 15, impl="gpu", ctx=gpu_ctx)
+    b = api.ba_local(p, 5, 15, impl="gpu", ctx=gpu_ctx)
+    for k in ("kf_Tcw", "pt_xyz", "ln_x0_dir", "chi2_log"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def check_pose(g, o):
+    assert np.array_equal(g["n_inliers"], o["n_inliers"]), np.nonzero(g["n_inliers"] != o["n_inliers"])
+    assert np.array_equal(g["pt_outlier"], o["pt_outlier"])
+    assert np.array_equal(g["ln_outlier"], o["ln_outlier"])
+    rel = np.abs(g["chi2_final"] - o["chi2_final"]) / np.maximum(np.abs(o["chi2_final"]), 1e-9)
+    assert rel.max() <= CHI2_RTOL, rel.max()
+    assert np.abs(g["Tcw"][:, 9:] - o["Tcw"][:, 9:]).max() <= POS_TOL
+    assert rot_angle(g["Tcw"], o["Tcw"]).max() <= ROT_TOL
+
+
+def test_pose_opt_batch(gpu_ctx):
+    p = synth.make_pose_batch(96, 300, 60, synth.seed_for(3))
+    check_pose(api.pose_opt(p, impl="gpu", ctx=gpu_ctx), api.pose_opt(p, impl="oracle"))
+
+
+def test_pose_opt_full_frame_shape(gpu_ctx):
+    """BASELINE config 3 frame shape: 1.5k points + 300 lines."""
+    p = synth.make_pose_batch(8, 1500, 300, synth.seed_for(3) + 1)
+    check_pose(api.pose_opt(p, impl="gpu", ctx=gpu_ctx), api.pose_opt(p, impl="oracle"))
+
+
+def test_pose_opt_degenerate(gpu_ctx):
+    """frames with < 3 correspondences return 0; frames with < 10 edges stop after the first round."""
+    a = synth.make_pose_batch(1, 2, 1, 5)
+    b = synth.make_pose_batch(1, 6, 1, 6)
+    for p in (a, b):
+        check_pose(api.pose_opt(p, impl="gpu", ctx=gpu_ctx), api.pose_opt(p, impl="oracle"))
+
+
+def test_sbp_frame(gpu_ctx):
+    """SearchByProjection(Current, Last): bit-exact matches, best indices and Hamming distances."""
+    p = synth.make_sbp_frame_batch(12, 2000, synth.seed_for(2))
+    g = api.sbp_frame(p, impl="gpu", ctx=gpu_ctx)
+    o = api.sbp_frame(p, impl="oracle")
+    assert o["n_matches"].sum() > 1000
+    for k in ("match", "n_matches", "best_idx", "best_dist"):
+        assert np.array_equal(g[k], o[k]), f"{k}: {np.nonzero(g[k] != o[k])[0][:10]}"
+
+
+def test_sbp_frame_small_and_mono(gpu_ctx):
+    p = synth.make_sbp_frame_batch(3, 64, 4)
+    p["mono"] = 1
+    p["check_orientation"] = 0
+    g = api.sbp_frame(p, impl="gpu", ctx=gpu_ctx)
+    o = api.sbp_frame(p, impl="oracle")
+    for k in ("match", "n_matches", "best_idx", "best_dist"):
+        assert np.array_equal(g[k], o[k]), k
+
+
+def test_sbp_mappoints(gpu_ctx):
+    """SearchByProjection(Frame, local map points): ratio test, claimed keypoints."""
+    p = synth.make_sbp_mp_batch(6, 2000, 1500, 17)
+    g = api.sbp_mappoints(p, impl="gpu", ctx=gpu_ctx)
+    o = api.sbp_mappoints(p, impl="oracle")
+    assert o["n_matches"].sum() > 500
+    for k in ("match", "n_matches", "best_idx", "best_dist"):
+        assert np.array_equal(g[k], o[k]), f"{k}: {np.nonzero(g[k] != o[k])[0][:10]}"
+
+
+def check_line_match(g, o):
+    same = g["match"] == o["match"]
+    fin = np.isfinite(o["dist"]) & same
+    assert np.abs(g["dist"][fin] - o["dist"][fin]).max(initial=0) <= 1e-5 * max(1.0, float(o["dist"][fin].max(initial=1.0)))
+    # a differing match is only tolerated when the competing distances are within the stated tolerance
+    bad = np.nonzero(~same)[0]
+    for i in bad:
+        assert np.isfinite(g["dist"][i]) and np.isfinite(o["dist"][i]) and abs(g["dist"][i] - o["dist"][i]) <= 1e-5 * max(1, o["dist"][i]), i
+    assert len(bad) <= max(1, len(same) // 1000)
+
+
+@pytest.mark.parametrize("D", [64, 72])
+def test_line_match(gpu_ctx, D):
+    p = synth.make_line_match_batch(6, 500, D, 9 + D)
+    g = api.line_match(p, impl="gpu", ctx=gpu_ctx)
+    o = api.line_match(p, impl="oracle")
+    assert (o["match"] >= 0).sum() > 100
+    check_line_match(g, o)
+
+
+def test_line_match_ragged(gpu_ctx):
+    p = synth.make_line_match_batch(5, 60, 64, 2, ragged=True)
+    check_line_match(api.line_match(p, impl="gpu", ctx=gpu_ctx), api.line_match(p, impl="oracle"))
+
+
+def test_no_cpu_fallback():
+    """a bad device index must fail loudly, not fall back."""
+    from lld_slam_b200 import capi
+    with pytest.raises(RuntimeError):
+        capi.Context(12345)
