@@ -1,0 +1,468 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native point+line BA / descriptor-matching core.
+
+A "step" is one full pass of the hot path over one batch of synthetic input:
+  workload "batched_local_ba" (BASELINE.json configs[3] shape, weak scaling): per GPU `--windows` independent local-BA
+  windows of 20 keyframes / 5 000 points / 1 000 lines, the reference schedule 5 + 15 LM iterations with the outlier
+  round in between (Optimizer::LocalBundleAdjustment).  metric = LM outer iterations per second over all windows.
+Secondary workloads of BASELINE.json's metric (descriptor matches/s, pose-only frames/s, single-window local BA at the
+north_star target shape 10 / 5k / 1k) are measured in the same run and reported under "extra".
+
+`value`   : inputs resident in HBM, device-timed with CUDA events on the library's stream.
+`e2e`     : the same step through the reference-shaped C-ABI call (lld_ba_local) with pinned HOST buffers: host indexing,
+            H2D, compute, D2H all inside the timed region.
+`roofline`: dominant kernel of the step from per-launch CUDA events (lld_ctx_profile), against MEASURED_PEAKS.json.
+`cpu_baseline`: the CPU oracle (a restatement of the reference's g2o path; the reference itself cannot be built here)
+            on one host core per problem, on a bounded sample of the same workload.
+--impl reference : the CPU oracle on all host cores (rank 0 only).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from lld_slam_b200 import api, capi, synth  # noqa: E402
+
+WIN_KF, WIN_PT, WIN_LN = 20, 5000, 1000
+ITS1, ITS2 = 5, 15
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, val in zip(names, f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def bind_resident(lib):
+    d = lib.dll
+    vp = C.c_void_p
+    d.lld_ba_upload.argtypes = [vp, C.POINTER(capi.BaProblem), C.c_int, C.c_int]; d.lld_ba_upload.restype = C.c_int
+    d.lld_ba_run_local.argtypes = [vp, C.c_int, C.c_int, capi.c_u8p]; d.lld_ba_run_local.restype = C.c_int
+    d.lld_ba_sync.argtypes = [vp]; d.lld_ba_sync.restype = C.c_int
+    d.lld_ba_download.argtypes = [vp, C.POINTER(capi.BaProblem), C.POINTER(capi.BaResult), C.c_int]; d.lld_ba_download.restype = C.c_int
+    d.lld_ctx_profile.argtypes = [vp, C.c_int]; d.lld_ctx_profile.restype = None
+    d.lld_ctx_profile_report.argtypes = [vp, C.c_char_p, C.c_int]; d.lld_ctx_profile_report.restype = C.c_int
+    d.lld_ctx_last_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]; d.lld_ctx_last_bytes.restype = None
+    d.lld_ctx_event_record.argtypes = [vp, C.c_int]; d.lld_ctx_event_record.restype = C.c_int
+    d.lld_ctx_event_elapsed_ms.argtypes = [vp]; d.lld_ctx_event_elapsed_ms.restype = C.c_float
+    d.lld_sbp_frame_upload.argtypes = [vp, C.POINTER(capi.SbpFrameProblem)]; d.lld_sbp_frame_upload.restype = C.c_int
+    d.lld_sbp_run.argtypes = [vp, C.POINTER(C.c_int)]; d.lld_sbp_run.restype = C.c_int
+    d.lld_pose_upload.argtypes = [vp, C.POINTER(capi.PoseProblem)]; d.lld_pose_upload.restype = C.c_int
+    d.lld_pose_run.argtypes = [vp]; d.lld_pose_run.restype = C.c_int
+    return d
+
+
+def profile_report(d, ctx):
+    buf = C.create_string_buffer(1 << 16)
+    ctx.check(d.lld_ctx_profile_report(ctx.handle, buf, len(buf)), "profile_report")
+    return json.loads(buf.value.decode())
+
+
+def pin(arr):
+    """copy a numpy array into pinned host memory (torch-owned) and return the numpy view + keepalive"""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+    return t.numpy(), t
+
+
+def pinned_problem(p):
+    keep, out = [], {}
+    for k, v in p.items():
+        if isinstance(v, np.ndarray):
+            a, t = pin(v)
+            out[k] = a
+            keep.append(t)
+        else:
+            out[k] = v
+    return out, keep
+
+
+def edge_counts(p):
+    n_pe = int(p["pt_obs_off"][-1])
+    n_le = int(p["ln_obs_off"][-1]) + int((p["ln_obs_right"][:, 0] >= 0).sum())
+    return n_pe, n_le
+
+
+def algorithmic_bytes_per_iter(p, trials=1):
+    """(1+t)(24 Ep + 36 El) + 2(1+t)(24 P + 40 L) + 96 Nkf + 8 (6 Nkf)^2 per window."""
+    n_pe, n_le = edge_counts(p)
+    P, L, K = int(p["pt_off"][-1]), int(p["ln_off"][-1]), int(p["kf_off"][-1])
+    nw = int(p["n_win"])
+    nk = K / nw
+    return (1 + trials) * (24 * n_pe + 36 * n_le) + 2 * (1 + trials) * (24 * P + 40 * L) + 96 * K + nw * 8 * (6 * nk) ** 2
+
+
+# per-kernel algorithmic bytes of OUR decomposition: what each launch must read + write once
+def kernel_bytes(name, p):
+    n_pe, n_le = edge_counts(p)
+    n_lc = int(p["ln_obs_off"][-1])
+    P, L, K = int(p["pt_off"][-1]), int(p["ln_off"][-1]), int(p["kf_off"][-1])
+    nw = int(p["n_win"])
+    nf = K / nw - 1
+    tbl = {
+        "k_lin_points": n_pe * (24 + 144) + P * (24 + 72),
+        "k_lin_lines": n_lc * (56 + 192) + L * (40 + 112),
+        "k_lin_poses": n_pe * 24 + n_lc * 56 + (n_pe + n_lc) * 24,
+        "k_schur_points": n_pe * (144 + 144) + P * (72 + 24),
+        "k_schur_lines": n_lc * (192 + 192) + L * (112 + 32),
+        "k_schur_rows": n_pe * (144 + 144) + n_lc * (192 + 192) + nw * 8 * 36 * nf * (nf + 1) / 2,
+        "k_backsub_points": n_pe * (144 + 24 + 8) + P * (24 + 24 + 24),
+        "k_backsub_lines": n_lc * (192 + 56 + 16) + L * (40 + 40 + 32),
+    }
+    return tbl.get(name)
+
+
+def make_batch(n_win, seed):
+    return synth.make_local_ba_batch(n_win, WIN_KF, WIN_PT, WIN_LN, seed)
+
+
+def run_reference_arm(args):
+    """CPU oracle on all host cores: one window per worker thread (ctypes releases the GIL)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_win = max(cores, 1)
+    wins = [make_batch(1, synth.seed_for(4) + 1000 + i) for i in range(n_win)]
+    api.ba_local(wins[0], ITS1, ITS2, impl="oracle")  # load + warm
+
+    def one(p):
+        o = api.ba_local(p, ITS1, ITS2, impl="oracle")
+        return int(o["n_iter_done"].sum())
+
+    with ThreadPoolExecutor(cores) as ex:
+        for _ in range(args.warmup):
+            list(ex.map(one, wins[:cores]))
+        t0 = time.perf_counter()
+        iters = 0
+        for _ in range(args.steps):
+            iters += sum(ex.map(one, wins))
+        dt = time.perf_counter() - t0
+    val = iters / dt
+    line = {
+        "impl": "reference", "metric": "local_ba_lm_iters_per_sec", "value": val, "unit": "LM iterations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"batched_local_ba: windows of {WIN_KF} KF / {WIN_PT} points / {WIN_LN} lines, schedule {ITS1}+{ITS2}",
+                   "note": "CPU oracle (restatement of the reference g2o path; the reference needs Eigen/OpenCV/LBDMOD, absent here)"},
+        "cpu_baseline": {"value": val, "unit": "LM iterations/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_win} windows per step, one per host thread"},
+        "e2e": {"value": val, "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--windows", type=int, default=64, help="local-BA windows per GPU")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    hbm_peak, peak_src = load_peaks()
+
+    lib = capi.load_library()
+    d = bind_resident(lib)
+    ctx = capi.Context(local_rank)
+    p = make_batch(args.windows, synth.seed_for(4) + rank)
+    prob, keep = capi.fill_struct(capi.BaProblem, p)
+    log_stride = ITS1 + ITS2 + 2
+    out = api._ba_outputs(p, log_stride)
+    res, keep2 = capi.fill_struct(capi.BaResult, out)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---------------- resident (value) ----------------
+    ctx.check(d.lld_ba_upload(ctx.handle, C.byref(prob), 0, log_stride), "upload")
+
+    def step():
+        ctx.check(d.lld_ba_run_local(ctx.handle, ITS1, ITS2, None), "run_local")
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ctx.check(d.lld_ba_sync(ctx.handle), "sync")
+    l0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ctx.check(d.lld_ba_sync(ctx.handle), "sync")
+    d.lld_ctx_event_record(ctx.handle, 0)
+    for _ in range(args.steps):
+        step()
+    d.lld_ctx_event_record(ctx.handle, 1)
+    ctx.check(d.lld_ba_sync(ctx.handle), "sync")
+    ms = float(d.lld_ctx_event_elapsed_ms(ctx.handle))
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - l0
+    ctx.check(d.lld_ba_download(ctx.handle, C.byref(prob), C.byref(res), 1), "download")
+    iters_per_step = int(out["n_iter_done"].sum())
+    trials_per_step = int(out["trials_log"].sum())
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, float(iters_per_step), float(launches)], device=f"cuda:{local_rank}", dtype=torch.float64)
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone()
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        ms = float(tm[0]); iters_total = float(ts[1]); launches = int(ts[2])
+    else:
+        iters_total = float(iters_per_step)
+    value = iters_total * args.steps / (ms * 1e-3)
+
+    # ---------------- per-kernel profile (roofline) ----------------
+    d.lld_ctx_profile(ctx.handle, 1)
+    step()
+    prof = profile_report(d, ctx)
+    d.lld_ctx_profile(ctx.handle, 0)
+    tot_ms = sum(v["ms"] for v in prof.values())
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    top_name, top_ms, top_n = top[0], top[1]["ms"], top[1]["n"]
+    kb = kernel_bytes(top_name.split("<")[0], p)
+    roofline = {"bound": "hbm", "kernel": top_name, "share_of_step": top_ms / tot_ms if tot_ms else None,
+                "avg_launch_us": 1e3 * top_ms / max(top_n, 1), "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
+                "traffic": None}
+    if kb:
+        ach = kb / (1e-3 * top_ms / max(top_n, 1)) / 1e9
+        roofline.update({"achieved": ach, "frac": ach / hbm_peak, "algorithmic_bytes_per_launch": kb})
+    else:
+        roofline.update({"achieved": None, "frac": None})
+    step_bytes = algorithmic_bytes_per_iter(p) * iters_per_step  # t = 1 trials: lower bound
+    roofline_step = {"bound": "hbm", "what": "whole LM iteration vs SURVEY §8(d) algorithmic bytes (t=1)",
+                     "achieved": step_bytes / (ms * 1e-3 / args.steps) / 1e9, "peak": hbm_peak, "unit": "GB/s"}
+    roofline_step["frac"] = roofline_step["achieved"] / hbm_peak
+    kernel_table = {k: {"ms": round(v["ms"], 4), "n": v["n"], "share": round(v["ms"] / tot_ms, 4)} for k, v in
+                    sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+
+    # ---------------- end to end through the reference-shaped call, pinned host buffers ----------------
+    pp, keep3 = pinned_problem(p)
+    prob_h, keep4 = capi.fill_struct(capi.BaProblem, pp)
+    outp, keep5 = pinned_problem(out)
+    res_h, keep6 = capi.fill_struct(capi.BaResult, outp)
+    for _ in range(2):
+        ctx.check(lib.ba_local(ctx.handle, C.byref(prob_h), ITS1, ITS2, None, C.byref(res_h)), "ba_local")
+    barrier()
+    t0 = time.perf_counter()
+    e_iters = 0
+    for _ in range(args.steps):
+        ctx.check(lib.ba_local(ctx.handle, C.byref(prob_h), ITS1, ITS2, None, C.byref(res_h)), "ba_local")
+        e_iters += int(outp["n_iter_done"].sum())
+    e_dt = time.perf_counter() - t0
+    h2d, d2h = C.c_int64(), C.c_int64()
+    d.lld_ctx_last_bytes(ctx.handle, C.byref(h2d), C.byref(d2h))
+    if dist is not None:
+        import torch
+        t = torch.tensor([e_dt, float(e_iters)], device=f"cuda:{local_rank}", dtype=torch.float64)
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        e_dt = float(tm[0]); e_iters = float(ts[1])
+    e2e = {"value": e_iters / e_dt, "unit": "LM iterations/s", "h2d_bytes_per_step": int(h2d.value),
+           "d2h_bytes_per_step": int(d2h.value), "ms_per_step": 1e3 * e_dt / args.steps}
+
+    extra = {}
+    cpu_baseline = None
+    if rank == 0:
+        # ---------------- CPU baseline: oracle, one core, bounded sample ----------------
+        if world == 1:
+            sample = make_batch(1, synth.seed_for(4) + 999)
+            t0 = time.perf_counter()
+            o1 = api.ba_local(sample, ITS1, ITS2, impl="oracle")
+            t1 = time.perf_counter() - t0
+            n_s = int(max(2, min(16, 12.0 / max(t1, 1e-3))))
+            sample = make_batch(n_s, synth.seed_for(4) + 998)
+            t0 = time.perf_counter()
+            o = api.ba_local(sample, ITS1, ITS2, impl="oracle")
+            tc = time.perf_counter() - t0
+            cpu_baseline = {"value": int(o["n_iter_done"].sum()) / tc, "unit": "LM iterations/s", "cores": 1, "kind": "port",
+                            "sample": f"{n_s} windows of {WIN_KF}/{WIN_PT}/{WIN_LN}, schedule {ITS1}+{ITS2}, sequential on one core"}
+        if not args.no_extra and world == 1:
+            extra = run_extra(lib, d, ctx, hbm_peak)
+    line = {
+        "metric": "local_ba_lm_iters_per_sec", "value": value, "unit": "LM iterations/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"batched_local_ba: {args.windows} windows/GPU of {WIN_KF} KF / {WIN_PT} points / {WIN_LN} lines, "
+                               f"schedule {ITS1}+{ITS2} (BASELINE configs[3] shape, weak scaling)",
+                   "windows_per_gpu": args.windows, "iters_per_step": iters_total, "lm_trials_per_step_rank0": trials_per_step,
+                   "l2": "inputs larger than L2 (per-GPU working set > 500 MB)", "parallelism": f"windows sharded over {world} GPU(s), no collective"},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step,
+        "kernels": kernel_table, "cpu_baseline": cpu_baseline, "extra": extra,
+    }
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def run_extra(lib, d, ctx, hbm_peak):
+    """secondary workloads of the BASELINE metric (single GPU): Hamming matching, pose-only LM, single-window BA."""
+    ex = {}
+    # --- Hamming SearchByProjection, BASELINE configs[1]: 2k ORB / frame, batch of 1024 pairs
+    try:
+        P, N = 1024, 2000
+        m = synth.make_sbp_frame_batch(P, N, synth.seed_for(2))
+        geom, gk = capi.make_geom(m["geom"])
+        f = dict(m); f["geom"] = geom
+        prob, keep = capi.fill_struct(capi.SbpFrameProblem, f)
+        ctx.check(d.lld_sbp_frame_upload(ctx.handle, C.byref(prob)), "sbp upload")
+        passes = C.c_int()
+        for _ in range(3):
+            ctx.check(d.lld_sbp_run(ctx.handle, C.byref(passes)), "sbp run")
+        d.lld_ba_sync(ctx.handle)
+        d.lld_ctx_event_record(ctx.handle, 0)
+        K = 10
+        for _ in range(K):
+            ctx.check(d.lld_sbp_run(ctx.handle, C.byref(passes)), "sbp run")
+        d.lld_ctx_event_record(ctx.handle, 1)
+        d.lld_ba_sync(ctx.handle)
+        ms = float(d.lld_ctx_event_elapsed_ms(ctx.handle)) / K
+        alg = P * (2 * N * 32 + 2 * N * 16 + N * 8)  # 208 KB / pair
+        d.lld_ctx_profile(ctx.handle, 1)
+        ctx.check(d.lld_sbp_run(ctx.handle, C.byref(passes)), "sbp run")
+        prof = profile_report(d, ctx)
+        d.lld_ctx_profile(ctx.handle, 0)
+        # one-core oracle on a bounded sample
+        ms_ = synth.make_sbp_frame_batch(32, N, synth.seed_for(2) + 1)
+        t0 = time.perf_counter(); api.sbp_frame(ms_, impl="oracle"); tc = time.perf_counter() - t0
+        ex["hamming_search_by_projection"] = {
+            "metric": "descriptor_matches_per_sec", "value": P * N / (ms * 1e-3), "unit": "queries resolved/s",
+            "config": f"{P} frame pairs x {N} ORB keypoints, th=7, claim passes={passes.value}", "ms_per_batch": ms,
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak, "what": "whole matcher (grid build + all claim passes) vs 208 KB/pair"},
+            "kernels": {k: {"ms": round(v["ms"], 4), "n": v["n"]} for k, v in prof.items()},
+            "cpu_baseline": {"value": 32 * N / tc, "unit": "queries resolved/s", "cores": 1, "kind": "port", "sample": "32 pairs"},
+        }
+    except Exception as e:  # noqa: BLE001
+        ex["hamming_search_by_projection"] = {"error": str(e)}
+    # --- pose-only LM, BASELINE configs[2] shape: frames x (1.5k points + 300 lines), 4 x 10 schedule
+    try:
+        F = 1024
+        pz = synth.make_pose_batch(F, 1500, 300, synth.seed_for(3))
+        prob, keep = capi.fill_struct(capi.PoseProblem, pz)
+        ctx.check(d.lld_pose_upload(ctx.handle, C.byref(prob)), "pose upload")
+        for _ in range(2):
+            ctx.check(d.lld_pose_run(ctx.handle), "pose run")
+        d.lld_ba_sync(ctx.handle)
+        d.lld_ctx_event_record(ctx.handle, 0)
+        K = 3
+        for _ in range(K):
+            ctx.check(d.lld_pose_run(ctx.handle), "pose run")
+        d.lld_ctx_event_record(ctx.handle, 1)
+        d.lld_ba_sync(ctx.handle)
+        ms = float(d.lld_ctx_event_elapsed_ms(ctx.handle)) / K
+        ps = synth.make_pose_batch(16, 1500, 300, synth.seed_for(3) + 1)
+        t0 = time.perf_counter(); api.pose_opt(ps, impl="oracle"); tc = time.perf_counter() - t0
+        ex["pose_optimization"] = {"metric": "frames_per_sec", "value": F / (ms * 1e-3), "unit": "frames/s",
+                                   "config": f"{F} frames x (1500 points + 300 lines), 4x10 LM", "ms_per_batch": ms,
+                                   "cpu_baseline": {"value": 16 / tc, "unit": "frames/s", "cores": 1, "kind": "port", "sample": "16 frames"}}
+    except Exception as e:  # noqa: BLE001
+        ex["pose_optimization"] = {"error": str(e)}
+    # --- single local-BA window at the north_star target shape 10 KF / 5k points / 1k lines
+    try:
+        p1 = synth.make_local_ba_batch(1, 10, 5000, 1000, synth.seed_for(1) + 5)
+        prob, keep = capi.fill_struct(capi.BaProblem, p1)
+        out = api._ba_outputs(p1, ITS1 + ITS2 + 2)
+        res, keep2 = capi.fill_struct(capi.BaResult, out)
+        ctx.check(d.lld_ba_upload(ctx.handle, C.byref(prob), 0, ITS1 + ITS2 + 2), "upload")
+        for _ in range(3):
+            ctx.check(d.lld_ba_run_local(ctx.handle, ITS1, ITS2, None), "run")
+        d.lld_ba_sync(ctx.handle)
+        d.lld_ctx_event_record(ctx.handle, 0)
+        K = 10
+        for _ in range(K):
+            ctx.check(d.lld_ba_run_local(ctx.handle, ITS1, ITS2, None), "run")
+        d.lld_ctx_event_record(ctx.handle, 1)
+        d.lld_ba_sync(ctx.handle)
+        ms = float(d.lld_ctx_event_elapsed_ms(ctx.handle)) / K
+        ctx.check(d.lld_ba_download(ctx.handle, C.byref(prob), C.byref(res), 1), "download")
+        its = int(out["n_iter_done"].sum())
+        t0 = time.perf_counter(); o = api.ba_local(p1, ITS1, ITS2, impl="oracle"); tc = time.perf_counter() - t0
+        ex["single_window_local_ba"] = {"metric": "lm_iters_per_sec", "value": its / (ms * 1e-3), "unit": "LM iterations/s",
+                                        "config": "1 window 10 KF / 5000 points / 1000 lines, schedule 5+15 (latency bound)",
+                                        "ms_per_call": ms, "iters": its,
+                                        "cpu_baseline": {"value": int(o["n_iter_done"].sum()) / tc, "unit": "LM iterations/s", "cores": 1,
+                                                         "kind": "port", "sample": "the same window"}}
+        ex["single_window_local_ba"]["speedup_vs_cpu_1core"] = ex["single_window_local_ba"]["value"] / ex["single_window_local_ba"]["cpu_baseline"]["value"]
+    except Exception as e:  # noqa: BLE001
+        ex["single_window_local_ba"] = {"error": str(e)}
+    return ex
+
+
+if __name__ == "__main__":
+    main()

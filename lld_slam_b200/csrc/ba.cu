@@ -338,6 +338,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   v.prm.chi2_pt_mono = p->chi2_pt_mono; v.prm.chi2_pt_stereo = p->chi2_pt_stereo;
   v.prm.ln_norm = p->ln_endpoints_normalized;
   v.prm.ln_filter = p->ln_filter;
+  c->last_h2d_bytes = S->h2d_bytes;
   return LLD_OK;
 }
 
@@ -509,6 +510,9 @@ static int ba_download(LldCtx* c, const lld_ba_problem* p, lld_ba_result* out, b
   cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->ms_compute, c->ev[1], c->ev[2]);
   cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]);
+  c->last_d2h_bytes = sizeof(double) * (12 * (size_t)v.n_kf + 3 * (size_t)v.n_pt + 6 * (size_t)v.n_ln) + (size_t)v.n_pe +
+                      2 * (size_t)v.n_lc + (size_t)v.n_ln + (sizeof(double) * 2 + sizeof(int)) * (size_t)v.n_win * ls +
+                      sizeof(int) * 2 * (size_t)v.n_win;
   (void)p;
   return LLD_OK;
 }

@@ -21,6 +21,8 @@ extern "C" int lld_ctx_create(int device, void** out) {
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return LLD_ERR_CUDA; }
   for (int i = 0; i < 4; i++)
     if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return LLD_ERR_CUDA; }
+  for (int i = 0; i < 2; i++)
+    if (cudaEventCreate(&c->ev_user[i]) != cudaSuccess) { delete c; return LLD_ERR_CUDA; }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   c->pinned_cap = 1 << 16;
   if (cudaMallocHost(&c->pinned, c->pinned_cap) != cudaSuccess) { delete c; return LLD_ERR_CUDA; }
@@ -37,6 +39,7 @@ extern "C" void lld_ctx_destroy(void* ctx) {
   if (c->comm) ncclCommDestroy(reinterpret_cast<ncclComm_t>(c->comm));
 #endif
   for (auto& b : c->pool) b.release();
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->pinned) cudaFreeHost(c->pinned);
   for (int i = 0; i < 4; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -60,6 +63,59 @@ extern "C" void lld_ctx_last_timing(void* ctx, float* a, float* b, float* d) {
   if (b) *b = c->ms_compute;
   if (d) *d = c->ms_d2h;
 }
+// per-kernel CUDA-event profile: enable, run, then read a JSON report {"kernel": {"ms": total, "n": launches}, ...}
+extern "C" void lld_ctx_profile(void* ctx, int on) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (!c) return;
+  c->prof_on = on != 0;
+  c->prof.clear();
+  c->ev_next = 0;
+}
+extern "C" int lld_ctx_profile_report(void* ctx, char* buf, int cap) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (!c || !buf || cap < 8) return LLD_ERR_ARG;
+  cudaStreamSynchronize(c->stream);
+  struct Acc { const char* name; double ms; long n; };
+  std::vector<Acc> acc;
+  for (auto& r : c->prof) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    Acc* f = nullptr;
+    for (auto& a : acc)
+      if (a.name == r.name || !strcmp(a.name, r.name)) { f = &a; break; }
+    if (!f) { acc.push_back({r.name, 0.0, 0}); f = &acc.back(); }
+    f->ms += ms;
+    f->n++;
+  }
+  int off = snprintf(buf, cap, "{");
+  for (size_t i = 0; i < acc.size() && off < cap - 96; i++)
+    off += snprintf(buf + off, cap - off, "%s\"%s\": {\"ms\": %.6f, \"n\": %ld}", i ? ", " : "", acc[i].name, acc[i].ms, acc[i].n);
+  snprintf(buf + off, cap - off, "}");
+  return LLD_OK;
+}
+extern "C" void lld_ctx_last_bytes(void* ctx, int64_t* h2d, int64_t* d2h) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (!c) return;
+  if (h2d) *h2d = (int64_t)c->last_h2d_bytes;
+  if (d2h) *d2h = (int64_t)c->last_d2h_bytes;
+}
+
+// CUDA-event timing on the context's stream (torch.cuda.Event only sees torch's stream)
+extern "C" int lld_ctx_event_record(void* ctx, int which) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (!c || which < 0 || which > 1) return LLD_ERR_ARG;
+  LLD_CUDA(c, cudaEventRecord(c->ev_user[which], c->stream));
+  return LLD_OK;
+}
+extern "C" float lld_ctx_event_elapsed_ms(void* ctx) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (!c) return -1.f;
+  cudaEventSynchronize(c->ev_user[1]);
+  float ms = -1.f;
+  cudaEventElapsedTime(&ms, c->ev_user[0], c->ev_user[1]);
+  return ms;
+}
+
 extern "C" void* lld_ctx_stream(void* ctx) {
   LldCtx* c = lld_ctx_cast(ctx);
   return c ? (void*)c->stream : nullptr;

@@ -37,6 +37,7 @@ struct LldCtx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_user[2] = {nullptr, nullptr};  // bench.py timing on this context's stream
   char err[512] = {0};
   int64_t launches = 0;
   float ms_h2d = 0, ms_compute = 0, ms_d2h = 0;
@@ -51,6 +52,21 @@ struct LldCtx {
   void* pinned = nullptr;
   size_t pinned_cap = 0;
   BaState* ba = nullptr;
+  size_t last_h2d_bytes = 0, last_d2h_bytes = 0;
+  // optional per-launch CUDA-event profiling (bench.py roofline): one event pair around every kernel launch
+  struct ProfRec { const char* name; cudaEvent_t a, b; };
+  bool prof_on = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_next = 0;
+  cudaEvent_t prof_event() {
+    if (ev_next >= ev_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev_pool.push_back(e);
+    }
+    return ev_pool[ev_next++];
+  }
 
   void pool_reset() { pool_next = 0; }
   template <typename T>
@@ -86,7 +102,17 @@ struct LldCtx {
 // kernel launch with bookkeeping (the launch count feeds bench.py's gpu_launches)
 #define LLD_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
   do {                                                                          \
+    cudaEvent_t _pa = nullptr, _pb = nullptr;                                   \
+    if ((ctx)->prof_on) {                                                       \
+      _pa = (ctx)->prof_event();                                                \
+      cudaEventRecord(_pa, (ctx)->stream);                                      \
+    }                                                                           \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);            \
+    if ((ctx)->prof_on) {                                                       \
+      _pb = (ctx)->prof_event();                                                \
+      cudaEventRecord(_pb, (ctx)->stream);                                      \
+      (ctx)->prof.push_back({#kernel, _pa, _pb});                               \
+    }                                                                           \
     (ctx)->launches++;                                                          \
   } while (0)
 

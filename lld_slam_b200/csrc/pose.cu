@@ -155,9 +155,6 @@ __global__ void __launch_bounds__(PTPB) k_pose_opt(PoseView v, int stage_smem) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ double part[NW][28];
   __shared__ double red[28];
-  __shared__ double s_Rt[12];      // pose under evaluation
-  __shared__ double s_qt[7];       // current estimate
-  __shared__ int s_ctl[4];         // [0] continue trial loop, [1] continue iterations, [2] robust on
   const int f = blockIdx.x;
   const int tid = threadIdx.x;
   const int p0 = v.pt_off[f], np = v.pt_off[f + 1] - p0;
@@ -191,6 +188,7 @@ __global__ void __launch_bounds__(PTPB) k_pose_opt(PoseView v, int stage_smem) {
     for (int i = tid; i < nl; i += PTPB) s_st[i] = F.lstereo[i];
     F.x0d = s_x0d; F.linfo = s_linfo; F.xw = s_xw; F.uvr = s_uvr; F.info = s_info;
     F.left = s_left; F.right = s_right; F.lstereo = s_st;
+    __syncthreads();
   }
   double* pchi = v.pt_chi2 + p0;
   double* lchi = v.ln_chi2 + 2 * (size_t)l0;
