@@ -3,7 +3,7 @@
 // Reference: src/TwoFrameLineMatcher.cc:26-124 with vgl::TriangulateLine (src/vgl.cc:78-108),
 // ReprojectKeyLineTo3D (src/LineMatching.cc:277-291), NormalizedLineEquation (src/vgl.cc:578-585).
 // The descriptor distance LineMatcher::MatchLineDescriptors lives in the un-vendored LBDMOD library
-// (parity unpinned, see oracle/lldo_match.cpp): defined here as the L2 norm of the float rows.
+// (un-vendored and unpinned, so parity is unpinned): defined here as the L2 norm of the float rows.
 //
 // Device plan per stereo pair:
 //   k_line_prep   : per line, K^T-normalised image line equation and pixel length

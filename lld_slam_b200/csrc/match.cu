@@ -166,7 +166,7 @@ __device__ __forceinline__ void top2_insert(Top2& t, int d, int k, int idx, int 
   }
 }
 
-// cv::Mat (CV_32F) row of R*x + t : double accumulation, one rounding (see oracle/lldo_match.cpp gemm_row)
+// cv::Mat (CV_32F) row of R*x + t : double accumulation, one rounding
 __device__ __forceinline__ float gemm_row(const float* R, const float* x, float t) {
   const double s = __dadd_rn(__dadd_rn(__dmul_rn((double)R[0], (double)x[0]), __dmul_rn((double)R[1], (double)x[1])),
                              __dmul_rn((double)R[2], (double)x[2]));

@@ -1,0 +1,263 @@
+"""CPU tests (-m "not gpu"): the oracle against independent checks and the committed golden vectors, the
+host-compiled device math against the oracle, and the C-ABI library's exported symbols (no compute without a GPU)."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from lld_slam_b200 import api, capi, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+dp = C.POINTER(C.c_double)
+fp = C.POINTER(C.c_float)
+P = lambda a: a.ctypes.data_as(dp)  # noqa: E731
+PF = lambda a: a.ctypes.data_as(fp)  # noqa: E731
+INTR = np.array([707.0912, 707.0912, 601.8873, 183.1104, 379.8145]).astype(np.float32).astype(np.float64)
+
+
+def rand_pose(rng):
+    w = rng.normal(0, 0.3, 3)
+    return np.concatenate([synth._rodrigues(w[None])[0].reshape(-1), rng.normal(0, 1, 3)]).astype(np.float32).astype(np.float64)
+
+
+def oracle_edge(ol, kind, T, lm, lcam, obs, want_jl=True):
+    err = np.zeros(3); Jl = np.zeros(12); Jp = np.zeros(18)
+    d = ol.lldo_edge_eval(kind, P(T), P(lm), P(INTR), P(lcam), P(obs), P(err), P(Jl) if want_jl else None, P(Jp))
+    nl = 4 if kind == 2 else 3
+    return err[:d].copy(), Jl[:d * nl].reshape(d, nl).copy(), Jp[:d * 6].reshape(d, 6).copy()
+
+
+def test_oracle_jacobians_numeric(built):
+    """analytic Jacobians of the oracle's edges against central differences through the vertex oplus."""
+    ol = capi.load_oracle().dll
+    rng = np.random.default_rng(0)
+    lcam = np.array([INTR[0], INTR[2], INTR[3], -0.5371])
+
+    def oplus_pose(T, u):
+        o = np.zeros(12); ol.lldo_pose_oplus(P(T), P(np.asarray(u, float)), P(o)); return o
+
+    def oplus_line(l, u):
+        o = np.zeros(6); ol.lldo_line_oplus(P(l), P(np.asarray(u, float)), P(o)); return o
+
+    for _ in range(20):
+        T = rand_pose(rng)
+        R = T[:9].reshape(3, 3)
+        Xc = np.array([rng.uniform(-8, 8), rng.uniform(-2, 3), rng.uniform(3, 40)])
+        X = R.T @ (Xc - T[9:])
+        obs = np.array([rng.uniform(0, 1241), rng.uniform(0, 376), rng.uniform(0, 1241)])
+        # mono: tight; stereo: the residual rounds 1/z to float32, so use a larger step and tolerance
+        for kind, h, tol in ((0, 1e-6, 1e-5), (1, 1e-3, 2e-2)):
+            e, Jl, Jp = oracle_edge(ol, kind, T, X, lcam, obs)
+            nJl = np.zeros_like(Jl); nJp = np.zeros_like(Jp)
+            for i in range(3):
+                dd = np.zeros(3); dd[i] = h
+                nJl[:, i] = (oracle_edge(ol, kind, T, X + dd, lcam, obs)[0] - oracle_edge(ol, kind, T, X - dd, lcam, obs)[0]) / (2 * h)
+            for i in range(6):
+                dd = np.zeros(6); dd[i] = h
+                nJp[:, i] = (oracle_edge(ol, kind, oplus_pose(T, dd), X, lcam, obs)[0] - oracle_edge(ol, kind, oplus_pose(T, -dd), X, lcam, obs)[0]) / (2 * h)
+            assert np.abs(Jl - nJl).max() <= tol * max(1.0, np.abs(Jl).max())
+            assert np.abs(Jp - nJp).max() <= tol * max(1.0, np.abs(Jp).max())
+        d = rng.normal(0, 1, 3); d /= np.linalg.norm(d)
+        Pw = R.T @ (np.array([rng.uniform(-8, 8), rng.uniform(-2, 3), rng.uniform(4, 30)]) - T[9:])
+        ln = np.concatenate([Pw - (Pw @ d) * d, d])
+        ob = np.array([rng.uniform(0, 1241), rng.uniform(0, 376), 1.0, rng.uniform(0, 1241), rng.uniform(0, 376), 1.0])
+        e, Jl, Jp = oracle_edge(ol, 2, T, ln, lcam, ob)
+        h = 1e-6
+        nJl = np.zeros_like(Jl); nJp = np.zeros_like(Jp)
+        for i in range(4):
+            dd = np.zeros(4); dd[i] = h
+            nJl[:, i] = (oracle_edge(ol, 2, T, oplus_line(ln, dd), lcam, ob)[0] - oracle_edge(ol, 2, T, oplus_line(ln, -dd), lcam, ob)[0]) / (2 * h)
+        for i in range(6):
+            dd = np.zeros(6); dd[i] = h
+            nJp[:, i] = (oracle_edge(ol, 2, oplus_pose(T, dd), ln, lcam, ob)[0] - oracle_edge(ol, 2, oplus_pose(T, -dd), ln, lcam, ob)[0]) / (2 * h)
+        assert np.abs(Jl - nJl).max() <= 1e-4 * max(1.0, np.abs(Jl).max())
+        assert np.abs(Jp - nJp).max() <= 1e-4 * max(1.0, np.abs(Jp).max())
+
+
+def test_device_math_matches_oracle(built):
+    """lld_slam_b200/csrc/lld_math.cuh compiled for the host (tests/hostcheck) against the oracle, edge by edge."""
+    ol = capi.load_oracle().dll
+    dm = C.CDLL(os.path.join(ROOT, "tests", "hostcheck", "libdevmath_host.so"))
+    rng = np.random.default_rng(1)
+    for it in range(500):
+        T = rand_pose(rng)
+        R = T[:9].reshape(3, 3)
+        Xc = np.array([rng.uniform(-10, 10), rng.uniform(-2, 3), rng.uniform(2, 60)])
+        X = R.T @ (Xc - T[9:])
+        obs = np.array([rng.uniform(0, 1241), rng.uniform(0, 376), rng.uniform(0, 1241)], np.float32)
+        for kind in (0, 1, 3):
+            e1, Jl1, Jp1 = oracle_edge(ol, kind, T, X, np.zeros(4), obs.astype(np.float64), want_jl=kind != 3)
+            e2 = np.zeros(3); Jl2 = np.zeros(9); Jp2 = np.zeros(18)
+            d = dm.dm_point(kind, P(T), P(X), P(INTR), PF(obs), P(e2), P(Jl2), P(Jp2))
+            assert np.abs(e1 - e2[:d]).max() <= 1e-10
+            if kind != 3:
+                assert np.abs(Jl1 - Jl2[:d * 3].reshape(d, 3)).max() <= 1e-12 * np.abs(Jl1).max()
+            assert np.abs(Jp1 - Jp2[:d * 6].reshape(d, 6)).max() <= 1e-12 * np.abs(Jp1).max()
+        dd = rng.normal(0, 1, 3); dd /= np.linalg.norm(dd)
+        Pw = R.T @ (np.array([rng.uniform(-10, 10), rng.uniform(-2, 3), rng.uniform(4, 40)]) - T[9:])
+        ln = np.concatenate([Pw - (Pw @ dd) * dd, dd])
+        lcam = np.array([INTR[0], INTR[2], INTR[3], rng.choice([0.0, -0.5371])])
+        ob = np.array([rng.uniform(0, 1241), rng.uniform(0, 376), 1.0, rng.uniform(0, 1241), rng.uniform(0, 376), 1.0])
+        e1, Jl1, Jp1 = oracle_edge(ol, 2, T, ln, lcam, ob)
+        e2 = np.zeros(2); Jl2 = np.zeros(8); Jp2 = np.zeros(12); e3 = np.zeros(2); dpz = C.c_int()
+        dm.dm_line(P(T), P(ln), P(lcam), P(ob), P(e2), P(Jl2), P(Jp2), P(e3), C.byref(dpz))
+        assert np.abs(e1 - e2).max() <= 1e-9 * max(1.0, np.abs(e1).max())
+        assert np.array_equal(e2, e3)
+        assert np.abs(Jl1 - Jl2.reshape(2, 4)).max() <= 1e-9 * np.abs(Jl1).max()
+        assert np.abs(Jp1 - Jp2.reshape(2, 6)).max() <= 1e-9 * np.abs(Jp1).max()
+        assert ol.lldo_line_depth_positive(P(T), P(ln), P(lcam), P(ob)) == dpz.value
+        u = rng.normal(0, 0.05, 6) if it % 10 else rng.normal(0, 1e-7, 6)
+        o1 = np.zeros(12); o2 = np.zeros(12)
+        ol.lldo_pose_oplus(P(T), P(u), P(o1)); dm.dm_pose_oplus(P(T), P(u), P(o2))
+        assert np.abs(o1 - o2).max() <= 1e-14
+        u4 = rng.normal(0, 0.05, 4)
+        o1 = np.zeros(6); o2 = np.zeros(6)
+        ol.lldo_line_oplus(P(ln), P(u4), P(o1)); dm.dm_line_oplus(P(ln), P(u4), P(o2))
+        assert np.abs(o1 - o2).max() <= 1e-12
+    for d in (3, 4):
+        A = rng.normal(0, 1, (d, d)); A = A @ A.T + np.eye(d)
+        I = np.zeros((d, d))
+        dm.dm_inv(d, P(np.ascontiguousarray(A)), P(I))
+        assert np.abs(I - np.linalg.inv(A)).max() <= 1e-12
+
+
+def test_descriptor_distance_vs_cv2_and_numpy(built):
+    """ORBmatcher::DescriptorDistance == popcount == cv2.NORM_HAMMING, for the oracle and the library's host inline."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(2)
+    for _ in range(200):
+        a = rng.integers(0, 256, 32, dtype=np.uint8); b = rng.integers(0, 256, 32, dtype=np.uint8)
+        ref = int(np.unpackbits(a ^ b).sum())
+        assert ref == int(cv2.norm(a, b, cv2.NORM_HAMMING))
+        assert api.descriptor_distance(a, b, impl="oracle") == ref
+        assert api.descriptor_distance(a, b, impl="gpu") == ref  # host inline of the product library, no device needed
+
+
+def test_oracle_lm_step_against_numpy_dense(built):
+    """one Gauss-Newton/LM iteration of the oracle reproduces a dense numpy normal-equation solve of the same problem."""
+    p = synth.make_local_ba_batch(1, 4, 30, 8, 3, outlier_frac=0.0)
+    p["robust_points"] = 0
+    p["delta_ln_mono"] = p["delta_ln_stereo"] = 1e9   # Huber never active -> plain least squares
+    o = api.ba_local(p, 1, 0, impl="oracle")
+    ol = capi.load_oracle().dll
+    nk, npnt, nl = 4, 30, 8
+    free = [k for k in range(nk) if not p["kf_fixed"][k]]
+    n = 6 * len(free) + 3 * npnt + 4 * nl
+    H = np.zeros((n, n)); b = np.zeros(n)
+    col_p = {k: 6 * i for i, k in enumerate(free)}
+    off_pt, off_ln = 6 * len(free), 6 * len(free) + 3 * npnt
+    chi0 = 0.0
+
+    def add(Jl, Jp, e, info, lc, pc):
+        nonlocal chi0
+        chi0 += info * float(e @ e)
+        J = np.zeros((len(e), n))
+        J[:, lc:lc + Jl.shape[1]] = Jl
+        if pc is not None:
+            J[:, pc:pc + 6] = Jp
+        H[:] += info * J.T @ J
+        b[:] += -info * J.T @ e
+
+    for i in range(npnt):
+        for e in range(p["pt_obs_off"][i], p["pt_obs_off"][i + 1]):
+            kf = p["pt_obs_kf"][e]; obs = p["pt_obs_uvr"][e].astype(np.float64)
+            kind = 0 if obs[2] < 0 else 1
+            er, Jl, Jp = oracle_edge(ol, kind, p["kf_Tcw"][kf], p["pt_xyz"][i], np.zeros(4), obs)
+            add(Jl, Jp, er, float(p["pt_obs_info"][e]), off_pt + 3 * i, col_p.get(kf))
+    for i in range(nl):
+        for c in range(p["ln_obs_off"][i], p["ln_obs_off"][i + 1]):
+            kf = p["ln_obs_kf"][c]; cam = p["kf_line_cam"][kf]
+            for side, seg in ((0, p["ln_obs_left"][c]), (1, p["ln_obs_right"][c])):
+                if side == 1 and seg[0] < 0:
+                    continue
+                lcam = np.array([cam[0], cam[1], cam[2], -cam[3] if side else 0.0])
+                ob = np.array([seg[0], seg[1], 1.0, seg[2], seg[3], 1.0], np.float64)
+                er, Jl, Jp = oracle_edge(ol, 2, p["kf_Tcw"][kf], p["ln_x0_dir"][i], lcam, ob)
+                add(Jl, Jp, er, float(p["ln_obs_info"][c, side]), off_ln + 4 * i, col_p.get(kf))
+    assert abs(chi0 - o["chi2_log"][0, 0]) <= 1e-9 * chi0
+    lam = 1e-5 * np.abs(np.diag(H)).max()
+    x = np.linalg.solve(H + lam * np.eye(n), b)
+    # apply to the first free pose and compare with the oracle's result after its single iteration
+    k = free[0]
+    Tn = np.zeros(12)
+    ol.lldo_pose_oplus(P(p["kf_Tcw"][k]), P(np.ascontiguousarray(x[col_p[k]:col_p[k] + 6])), P(Tn))
+    if o["trials_log"][0, 0] == 1 and o["chi2_log"][0, 1] < o["chi2_log"][0, 0]:
+        assert np.abs(Tn - o["kf_Tcw"][k]).max() <= 1e-7
+        Xn = p["pt_xyz"][0] + x[off_pt:off_pt + 3]
+        assert np.abs(Xn - o["pt_xyz"][0]).max() <= 1e-6
+
+
+GOLDEN = os.path.join(ROOT, "tests", "golden", "oracle_golden.json")
+
+
+def test_oracle_golden_vectors(built):
+    """committed fixtures (tests/golden/make_golden.py): the oracle must keep reproducing them bit-for-bit / to 1e-12."""
+    g = json.load(open(GOLDEN))
+    p = synth.make_local_ba_batch(1, 5, 120, 30, g["ba_local"]["seed"])
+    o = api.ba_local(p, 5, 15, impl="oracle")
+    assert o["n_iter_done"].tolist() == g["ba_local"]["n_iter_done"]
+    assert np.allclose(o["chi2_log"][0], g["ba_local"]["chi2_log"], rtol=1e-10, atol=0)
+    assert int(o["pt_obs_bad"].sum()) == g["ba_local"]["n_pt_bad"] and int(o["ln_obs_bad"].sum()) == g["ba_local"]["n_ln_bad"]
+    assert np.allclose(o["kf_Tcw"], np.array(g["ba_local"]["kf_Tcw"]), rtol=0, atol=1e-10)
+    q = synth.make_pose_batch(3, 80, 20, g["pose"]["seed"])
+    r = api.pose_opt(q, impl="oracle")
+    assert r["n_inliers"].tolist() == g["pose"]["n_inliers"]
+    assert np.allclose(r["Tcw"], np.array(g["pose"]["Tcw"]), rtol=0, atol=1e-10)
+    m = synth.make_sbp_frame_batch(2, 300, g["sbp"]["seed"])
+    s = api.sbp_frame(m, impl="oracle")
+    assert s["n_matches"].tolist() == g["sbp"]["n_matches"]
+    assert int(s["best_dist"][s["best_idx"] >= 0].sum()) == g["sbp"]["dist_sum"]
+    assert s["match"].tolist() == g["sbp"]["match"]
+    lm = synth.make_line_match_batch(2, 60, 64, g["lines"]["seed"])
+    t = api.line_match(lm, impl="oracle")
+    assert t["match"].tolist() == g["lines"]["match"]
+
+
+def test_matching_oracle_properties(built):
+    """domain properties of the matcher: every match within TH_HIGH, claimed keypoints never matched, matches are a
+    partial injection when every query has observations."""
+    m = synth.make_sbp_frame_batch(4, 800, 5)
+    m["last_has_obs"][:] = 1
+    m["check_orientation"] = 0
+    s = api.sbp_frame(m, impl="oracle")
+    assert (s["best_dist"][s["best_idx"] >= 0] <= 100).all()
+    for pr in range(4):
+        q0, q1 = m["last_off"][pr], m["last_off"][pr + 1]
+        bi = s["best_idx"][q0:q1]
+        bi = bi[bi >= 0]
+        assert len(np.unique(bi)) == len(bi)
+        c0 = m["cur_off"][pr]
+        assert not m["cur_claimed"][c0 + bi].any()
+    lm = synth.make_line_match_batch(3, 100, 64, 8)
+    t = api.line_match(lm, impl="oracle")
+    for pr in range(3):
+        a0, a1 = lm["left_off"][pr], lm["left_off"][pr + 1]
+        mm = t["match"][a0:a1]; mm = mm[mm >= 0]
+        assert len(np.unique(mm)) == len(mm)
+        assert (t["dist"][a0:a1][t["match"][a0:a1] >= 0] < lm["tau"]).all()
+
+
+def test_library_exports_every_declared_symbol(built):
+    """the C-ABI shared library loads and exports every function include/lldba.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "lldba.h")).read()
+    names = set(re.findall(r"\b(lld_[a-z0-9_]+)\s*\(", hdr))
+    assert {"lld_ba_local", "lld_ba_global", "lld_pose_opt", "lld_sbp_frame", "lld_sbp_mappoints", "lld_line_match",
+            "lld_descriptor_distance", "lld_ctx_create", "lld_ctx_destroy", "lld_comm_init"} <= names
+    dll = capi.load_library().dll
+    for n in sorted(names):
+        assert hasattr(dll, n), f"liblldba.so does not export {n}"
+    assert dll.lld_version().startswith(b"lldba")
+
+
+def test_product_never_routes_through_the_oracle():
+    """the product sources must not reference the oracle (no CPU fallback)."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "lld_slam_b200", "csrc")):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "lldo_" not in txt and "liblld_oracle" not in txt, f
+    with pytest.raises(RuntimeError):
+        capi.Context(0 if not os.path.exists("/dev/nvidia0") else 9999)
