@@ -261,3 +261,14 @@ def test_product_never_routes_through_the_oracle():
                 assert "lldo_" not in txt and "liblld_oracle" not in txt, f
     with pytest.raises(RuntimeError):
         capi.Context(0 if not os.path.exists("/dev/nvidia0") else 9999)
+
+
+def test_cpp_shim_compiles_and_links(built, tmp_path):
+    """lld_slam_b200/host/lld_shim.h (reference class names over the C-ABI) compiles as C++14 and links to liblldba.so."""
+    import subprocess
+    exe = str(tmp_path / "shim_test")
+    csrc = os.path.join(ROOT, "lld_slam_b200", "csrc")
+    r = subprocess.run(["g++", "-std=c++14", "-Wall", os.path.join(ROOT, "tests", "hostcheck", "shim_compile.cpp"), "-o", exe,
+                        "-L" + csrc, "-llldba", "-Wl,-rpath," + csrc], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert subprocess.run([exe]).returncode == 0
