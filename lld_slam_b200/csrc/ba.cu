@@ -130,36 +130,67 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
       lc_ln[e] = i;
     }
   }
-  // per-free-keyframe edge lists (counting sort; points in edge order, then line cells in cell order)
-  std::vector<int> kfl_off(nG + 1, 0);
-  for (int e = 0; e < n_pe; e++)
-    if (kf_g[pe_kf[e]] >= 0) kfl_off[kf_g[pe_kf[e]] + 1]++;
-  for (int e = 0; e < n_lc; e++)
-    if (kf_g[lc_kf[e]] >= 0) kfl_off[kf_g[lc_kf[e]] + 1]++;
-  for (int g = 0; g < nG; g++) kfl_off[g + 1] += kfl_off[g];
-  const int n_list = kfl_off[nG];
-  std::vector<int> kfl_ref(std::max(n_list, 1)), cur(kfl_off.begin(), kfl_off.end() - 1);
-  for (int e = 0; e < n_pe; e++) {
-    const int g = kf_g[pe_kf[e]];
-    if (g >= 0) kfl_ref[cur[g]++] = e;
-  }
-  for (int e = 0; e < n_lc; e++) {
-    const int g = kf_g[lc_kf[e]];
-    if (g >= 0) kfl_ref[cur[g]++] = ~e;
-  }
-  // chunks
-  std::vector<int> ch_g, ch_begin, ch_end, g_ch0(nG + 1, 0);
-  for (int g = 0; g < nG; g++) {
-    g_ch0[g] = (int)ch_g.size();
-    for (int b = kfl_off[g]; b < kfl_off[g + 1]; b += CHUNK) {
-      ch_g.push_back(g);
-      ch_begin.push_back(b);
-      ch_end.push_back(std::min(b + CHUNK, kfl_off[g + 1]));
+  // ---- co-visibility signature of every landmark (set of free blocks observing it) ----
+  // Landmarks with the same signature are made adjacent in every keyframe's list, so k_schur_rows can test
+  // "does neighbour j see these landmarks" once per segment instead of once per entry.
+  auto signature = [&](const int* off, const std::vector<int>& ekf, int i, int g0, int nf) -> uint64_t {
+    uint64_t key = 0;
+    if (nf <= 64) {
+      for (int e = off[i]; e < off[i + 1]; e++) {
+        const int g = kf_g[ekf[e]];
+        if (g >= 0) key |= 1ull << (g - g0);
+      }
+    } else {  // FNV-1a over the sorted block list; segments are verified exactly below, the key only orders
+      std::vector<int> gs;
+      for (int e = off[i]; e < off[i + 1]; e++)
+        if (kf_g[ekf[e]] >= 0) gs.push_back(kf_g[ekf[e]]);
+      std::sort(gs.begin(), gs.end());
+      key = 1469598103934665603ull;
+      for (int g : gs) { key ^= (uint64_t)(g + 1); key *= 1099511628211ull; }
+    }
+    return key;
+  };
+  std::vector<int> pt_order(n_pt), ln_order(n_ln);
+  {
+    std::vector<uint64_t> key(std::max(n_pt, n_ln));
+    for (int w = 0; w < nw; w++) {
+      const int g0 = w_g0[w], nf = w_g0[w + 1] - g0;
+      for (int i = p->pt_off[w]; i < p->pt_off[w + 1]; i++) { key[i] = signature(p->pt_obs_off, pe_kf, i, g0, nf); pt_order[i] = i; }
+      std::stable_sort(pt_order.begin() + p->pt_off[w], pt_order.begin() + p->pt_off[w + 1],
+                       [&](int a, int b) { return key[a] < key[b]; });
+    }
+    for (int w = 0; w < nw; w++) {
+      const int g0 = w_g0[w], nf = w_g0[w + 1] - g0;
+      for (int i = p->ln_off[w]; i < p->ln_off[w + 1]; i++) { key[i] = signature(p->ln_obs_off, lc_kf, i, g0, nf); ln_order[i] = i; }
+      std::stable_sort(ln_order.begin() + p->ln_off[w], ln_order.begin() + p->ln_off[w + 1],
+                       [&](int a, int b) { return key[a] < key[b]; });
     }
   }
-  g_ch0[nG] = (int)ch_g.size();
-  const int n_ch = (int)ch_g.size();
-  v.n_chunks = n_ch;
+  // per-free-keyframe lists (counting sort in signature order), separately for point edges and line cells
+  auto build_lists = [&](int n_lm, const int* off, const std::vector<int>& ekf, const std::vector<int>& order,
+                         std::vector<int>& l_off, std::vector<int>& l_ref, std::vector<int>& e_pos) {
+    l_off.assign(nG + 1, 0);
+    const int n_e = n_lm ? off[n_lm] : 0;
+    for (int e = 0; e < n_e; e++)
+      if (kf_g[ekf[e]] >= 0) l_off[kf_g[ekf[e]] + 1]++;
+    for (int g = 0; g < nG; g++) l_off[g + 1] += l_off[g];
+    l_ref.assign(std::max(l_off[nG], 1), 0);
+    e_pos.assign(std::max(n_e, 1), -1);
+    std::vector<int> cur(l_off.begin(), l_off.end() - 1);
+    for (int oi = 0; oi < n_lm; oi++) {
+      const int i = order[oi];
+      for (int e = off[i]; e < off[i + 1]; e++) {
+        const int g = kf_g[ekf[e]];
+        if (g < 0) continue;
+        e_pos[e] = cur[g];
+        l_ref[cur[g]++] = e;
+      }
+    }
+  };
+  std::vector<int> pl_off, pl_edge, pe_pos, ll_off, ll_cell, lc_pos;
+  build_lists(n_pt, p->pt_obs_off, pe_kf, pt_order, pl_off, pl_edge, pe_pos);
+  build_lists(n_ln, p->ln_obs_off, lc_kf, ln_order, ll_off, ll_cell, lc_pos);
+  const int n_plist = pl_off[nG], n_llist = ll_off[nG];
   // neighbour lists (block columns >= own row)
   std::vector<int> nb_off(nG + 1, 0), nb_g;
   if (!global_mode) {
@@ -204,38 +235,76 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   for (int g = 0; g < nG; g++) S->max_nnb = std::max(S->max_nnb, nb_off[g + 1] - nb_off[g]);
   S->n_nb_total = nb_g.size();
   LLD_ARG(c, 6 * S->max_nnb <= 1024);
-  // rowslot table + partial-row offsets
-  std::vector<long long> rs_off(std::max(nG, 1), 0), ch_S_off(std::max(n_ch, 1), 0);
-  long long rs_total = 0, chS_total = 0;
-  for (int g = 0; g < nG; g++) {
-    rs_off[g] = rs_total;
-    rs_total += (long long)(kfl_off[g + 1] - kfl_off[g]) * (nb_off[g + 1] - nb_off[g]);
-  }
+  // position tables: per list entry and neighbour, the list position of the co-edge (or -1)
+  auto build_tab = [&](const std::vector<int>& l_off, const std::vector<int>& l_ref, const int* off, const std::vector<int>& e_lm,
+                       const std::vector<int>& ekf, const std::vector<int>& e_pos, std::vector<long long>& t_off, std::vector<int>& tab) {
+    t_off.assign(std::max(nG, 1), 0);
+    long long tot = 0;
+    for (int g = 0; g < nG; g++) {
+      t_off[g] = tot;
+      tot += (long long)(l_off[g + 1] - l_off[g]) * (nb_off[g + 1] - nb_off[g]);
+    }
+    tab.assign((size_t)std::max(tot, 1LL), -1);
+    for (int g = 0; g < nG; g++) {
+      const int nnb = nb_off[g + 1] - nb_off[g];
+      const int* nbl = nb_g.data() + nb_off[g];
+      for (int i = l_off[g]; i < l_off[g + 1]; i++) {
+        int* row = tab.data() + t_off[g] + (long long)(i - l_off[g]) * nnb;
+        const int lm = e_lm[l_ref[i]];
+        for (int e2 = off[lm]; e2 < off[lm + 1]; e2++) {
+          const int b = kf_g[ekf[e2]];
+          if (b < g) continue;
+          const int j = global_mode ? (int)(std::lower_bound(nbl, nbl + nnb, b) - nbl) : b - g;
+          row[j] = e_pos[e2];
+        }
+      }
+    }
+  };
+  std::vector<long long> pl_tab_off, ll_tab_off;
+  std::vector<int> pl_tab, ll_tab;
+  build_tab(pl_off, pl_edge, p->pt_obs_off, pe_pt, pe_kf, pe_pos, pl_tab_off, pl_tab);
+  build_tab(ll_off, ll_cell, p->ln_obs_off, lc_ln, lc_kf, lc_pos, ll_tab_off, ll_tab);
+  // chunks + segments (runs of entries whose table rows have the same -1 pattern)
+  const long long n_list_total = (long long)n_plist + n_llist;
+  int CH = CHUNK;
+  while (CH > 32 && n_list_total / CH < 3 * (long long)c->sm_count) CH >>= 1;
+  std::vector<int> ch_g, ch_begin, ch_end, ch_seg0, seg_begin, seg_end, g_chp0(nG + 1, 0), g_chl0(nG + 1, 0);
+  auto build_chunks = [&](const std::vector<int>& l_off, const std::vector<long long>& t_off, const std::vector<int>& tab,
+                          std::vector<int>& g_c0) {
+    for (int g = 0; g < nG; g++) {
+      g_c0[g] = (int)ch_g.size();
+      const int nnb = nb_off[g + 1] - nb_off[g];
+      auto same = [&](int a, int b) {
+        const int* ra = tab.data() + t_off[g] + (long long)(a - l_off[g]) * nnb;
+        const int* rb = tab.data() + t_off[g] + (long long)(b - l_off[g]) * nnb;
+        for (int j = 0; j < nnb; j++)
+          if ((ra[j] < 0) != (rb[j] < 0)) return false;
+        return true;
+      };
+      for (int b = l_off[g]; b < l_off[g + 1]; b += CH) {
+        const int e = std::min(b + CH, l_off[g + 1]);
+        ch_g.push_back(g); ch_begin.push_back(b); ch_end.push_back(e);
+        ch_seg0.push_back((int)seg_begin.size());
+        int s0 = b;
+        for (int i = b + 1; i <= e; i++)
+          if (i == e || !same(i - 1, i)) { seg_begin.push_back(s0); seg_end.push_back(i); s0 = i; }
+      }
+    }
+    g_c0[nG] = (int)ch_g.size();
+  };
+  build_chunks(pl_off, pl_tab_off, pl_tab, g_chp0);
+  const int n_chp = (int)ch_g.size();
+  build_chunks(ll_off, ll_tab_off, ll_tab, g_chl0);
+  const int n_ch = (int)ch_g.size();
+  ch_seg0.push_back((int)seg_begin.size());
+  v.n_chunks = n_ch;
+  v.n_chunks_pt = n_chp;
+  std::vector<long long> ch_S_off(std::max(n_ch, 1), 0);
+  long long chS_total = 0;
   for (int ch = 0; ch < n_ch; ch++) {
     ch_S_off[ch] = chS_total;
     const int nnb = nb_off[ch_g[ch] + 1] - nb_off[ch_g[ch]];
     chS_total += 36LL * nnb + 6;
-  }
-  std::vector<uint8_t> rowslot((size_t)std::max(rs_total, 1LL), 0xFF);
-  for (int g = 0; g < nG; g++) {
-    const int nnb = nb_off[g + 1] - nb_off[g];
-    const int* nbl = nb_g.data() + nb_off[g];
-    for (int i = kfl_off[g]; i < kfl_off[g + 1]; i++) {
-      uint8_t* row = rowslot.data() + rs_off[g] + (long long)(i - kfl_off[g]) * nnb;
-      const int ref = kfl_ref[i];
-      int b0, b1;
-      const int* kfs;
-      if (ref >= 0) { b0 = p->pt_obs_off[pe_pt[ref]]; b1 = p->pt_obs_off[pe_pt[ref] + 1]; kfs = pe_kf.data(); }
-      else { b0 = p->ln_obs_off[lc_ln[~ref]]; b1 = p->ln_obs_off[lc_ln[~ref] + 1]; kfs = lc_kf.data(); }
-      for (int e2 = b0; e2 < b1; e2++) {
-        const int b = kf_g[kfs[e2]];
-        if (b < g) continue;
-        int j;
-        if (!global_mode) j = b - g;
-        else j = (int)(std::lower_bound(nbl, nbl + nnb, b) - nbl);
-        row[j] = (uint8_t)(e2 - b0);
-      }
-    }
   }
   // global-memory solve scratch for windows too large for shared memory
   std::vector<long long> w_scr(nw, 0);
@@ -274,17 +343,27 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   UP(tmp_d, p->ln_obs_info, 2 * (size_t)n_lc); v.lc_info = tmp_d;
   uint8_t* tmp_u;
   UP(tmp_u, p->ln_obs_stereo, n_lc); v.lc_stereo = tmp_u;
-  UP(tmp_i, kfl_off.data(), nG + 1); v.kfl_off = tmp_i;
-  UP(tmp_i, kfl_ref.data(), n_list); v.kfl_ref = tmp_i;
+  UP(tmp_i, pl_off.data(), nG + 1); v.pl_off = tmp_i;
+  UP(tmp_i, pl_edge.data(), n_plist); v.pl_edge = tmp_i;
+  UP(tmp_i, pe_pos.data(), n_pe); v.pe_pos = tmp_i;
+  UP(tmp_i, ll_off.data(), nG + 1); v.ll_off = tmp_i;
+  UP(tmp_i, ll_cell.data(), n_llist); v.ll_cell = tmp_i;
+  UP(tmp_i, lc_pos.data(), n_lc); v.lc_pos = tmp_i;
   UP(tmp_i, ch_g.data(), n_ch); v.ch_g = tmp_i;
   UP(tmp_i, ch_begin.data(), n_ch); v.ch_begin = tmp_i;
   UP(tmp_i, ch_end.data(), n_ch); v.ch_end = tmp_i;
-  UP(tmp_i, g_ch0.data(), nG + 1); v.g_ch0 = tmp_i;
+  UP(tmp_i, ch_seg0.data(), ch_seg0.size()); v.ch_seg0 = tmp_i;
+  UP(tmp_i, seg_begin.data(), seg_begin.size()); v.seg_begin = tmp_i;
+  UP(tmp_i, seg_end.data(), seg_end.size()); v.seg_end = tmp_i;
+  UP(tmp_i, g_chp0.data(), nG + 1); v.g_chp0 = tmp_i;
+  UP(tmp_i, g_chl0.data(), nG + 1); v.g_chl0 = tmp_i;
   UP(tmp_i, nb_off.data(), nG + 1); v.nb_off = tmp_i;
   UP(tmp_i, nb_g.data(), nb_g.size()); v.nb_g = tmp_i;
-  UP(tmp_u, rowslot.data(), (size_t)rs_total); v.rowslot = tmp_u;
+  UP(tmp_i, pl_tab.data(), pl_tab.size()); v.pl_tab = tmp_i;
+  UP(tmp_i, ll_tab.data(), ll_tab.size()); v.ll_tab = tmp_i;
   long long* tmp_l;
-  UP(tmp_l, rs_off.data(), nG); v.rs_off = tmp_l;
+  UP(tmp_l, pl_tab_off.data(), nG); v.pl_tab_off = tmp_l;
+  UP(tmp_l, ll_tab_off.data(), nG); v.ll_tab_off = tmp_l;
   UP(tmp_l, ch_S_off.data(), n_ch); v.ch_S_off = tmp_l;
   UP(tmp_l, w_scr.data(), nw); v.w_scratch_off = tmp_l;
   double *d_T, *d_P, *d_L;
@@ -303,15 +382,14 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   DEV(v.pe_level, uint8_t, n_pe); DEV(v.lc_level, uint8_t, 2 * (size_t)n_lc); DEV(v.ln_removed, uint8_t, n_ln);
   DEV(v.pe_chi2, double, n_pe); DEV(v.lc_chi2, double, 2 * (size_t)n_lc);
   DEV(v.pt_H, double, 9 * (size_t)n_pt); DEV(v.ln_H, double, 14 * (size_t)n_ln);
-  DEV(v.pe_W, double, 18 * (size_t)n_pe); DEV(v.lc_W, double, 24 * (size_t)n_lc);
+  DEV(v.P_rec, double, 27 * (size_t)n_plist); DEV(v.L_rec, double, 38 * (size_t)n_llist);
   DEV(v.ch_pose, double, 28 * (size_t)n_ch);
   DEV(v.g_Hpp, double, 21 * (size_t)nG); DEV(v.g_bp, double, 6 * (size_t)nG); DEV(v.g_nact, int, nG);
   DEV(v.lm_chi2lin, double, n_pt + n_ln); DEV(v.lm_maxdiag, double, n_pt + n_ln); DEV(v.lm_active, uint8_t, n_pt + n_ln);
-  DEV(v.pe_Y, double, 18 * (size_t)n_pe); DEV(v.lc_Y, double, 24 * (size_t)n_lc);
   DEV(v.ch_S, double, (size_t)chS_total);
   DEV(v.S_blk, double, 36 * nb_g.size());
   DEV(v.g_bs, double, 6 * (size_t)nG); DEV(v.g_x, double, 6 * (size_t)nG);
-  DEV(v.pt_c, double, 3 * (size_t)n_pt); DEV(v.ln_c, double, 4 * (size_t)n_ln);
+  DEV(v.pt_D, double, 9 * (size_t)n_pt); DEV(v.ln_D, double, 14 * (size_t)n_ln);
   DEV(v.lm_chi2, double, n_pt + n_ln); DEV(v.lm_scale, double, n_pt + n_ln);
   DEV(v.w_phase, int, nw); DEV(v.w_sel, int, nw); DEV(v.w_iter, int, nw); DEV(v.w_trials, int, nw);
   DEV(v.w_maxit, int, nw); DEV(v.w_nbad, int, nw); DEV(v.w_ok, int, nw); DEV(v.w_nlog, int, nw);
@@ -408,7 +486,7 @@ template <bool SMEM>
 static int launch_solve(LldCtx* c, BaView& v, int max_n) {
   size_t smem = SMEM ? sizeof(double) * ((size_t)max_n * max_n + 2 * (size_t)max_n) : 0;
   if (SMEM) LLD_CUDA(c, cudaFuncSetAttribute(k_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  LLD_LAUNCH(c, k_solve<SMEM>, v.n_win, 256, smem, v);
+  LLD_LAUNCH(c, k_solve<SMEM>, v.n_win, 512, smem, v);
   return LLD_OK;
 }
 
@@ -426,9 +504,16 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   LLD_LAUNCH(c, k_begin, cdiv(v.n_win, 64), 64, 0, v);
   if (v.n_pt) LLD_LAUNCH(c, k_schur_points, gp, LM_TPB, 0, v);
   if (v.n_ln) LLD_LAUNCH(c, k_schur_lines, gl, LM_TPB, 0, v);
-  if (v.n_chunks) {
+  {
     const int tpb = 32 * cdiv(6 * S->max_nnb, 32);
-    LLD_LAUNCH(c, k_schur_rows, v.n_chunks, tpb, 0, v);
+    const int nl = v.n_chunks - v.n_chunks_pt;
+    if (tpb <= 256) {
+      if (v.n_chunks_pt) LLD_LAUNCH(c, (k_schur_rows<3, 256>), v.n_chunks_pt, tpb, 0, v, 0);
+      if (nl) LLD_LAUNCH(c, (k_schur_rows<4, 256>), nl, tpb, 0, v, v.n_chunks_pt);
+    } else {
+      if (v.n_chunks_pt) LLD_LAUNCH(c, (k_schur_rows<3, 1024>), v.n_chunks_pt, tpb, 0, v, 0);
+      if (nl) LLD_LAUNCH(c, (k_schur_rows<4, 1024>), nl, tpb, 0, v, v.n_chunks_pt);
+    }
   }
   if (v.n_free_total) {
     const int tpb = std::min(256, 32 * cdiv(6 * S->max_nnb, 32));

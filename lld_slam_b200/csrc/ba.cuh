@@ -47,18 +47,30 @@ struct BaView {
   const float* lc_right;
   const double* lc_info;
   const uint8_t* lc_stereo;
-  // per-free-KF edge lists, chunked
-  const int* kfl_off;    // [n_free_total+1]
-  const int* kfl_ref;    // >=0 point edge id ; <0 : ~cell id
+  // per-free-KF edge lists ("rows"): points and line cells separately, entries grouped by co-visibility signature,
+  // cut into chunks; chunk ids [0, n_chunks_pt) are point chunks, [n_chunks_pt, n_chunks) line chunks
+  int n_chunks_pt;
+  const int* pl_off;     // [n_free_total+1] point-list offsets
+  const int* pl_edge;    // [n_plist] point edge id of the list entry
+  const int* pe_pos;     // [n_pe] list position of the edge or -1 (fixed keyframe)
+  const int* ll_off;     // [n_free_total+1] line-list offsets
+  const int* ll_cell;    // [n_llist] line cell id
+  const int* lc_pos;     // [n_lc]
   const int* ch_g;       // [n_chunks] free block of the chunk
-  const int* ch_begin;   // [n_chunks]
+  const int* ch_begin;   // [n_chunks] list range of the chunk
   const int* ch_end;
-  const int* g_ch0;      // [n_free_total+1] first chunk of each free block
+  const int* ch_seg0;    // [n_chunks+1] first segment of the chunk
+  const int* seg_begin;  // segments: runs of list entries with the same set of co-observing keyframes
+  const int* seg_end;
+  const int* g_chp0;     // [n_free_total+1] first point chunk of each free block
+  const int* g_chl0;     // [n_free_total+1] first line chunk (absolute chunk id)
   // Schur row structure
   const int* nb_off;     // [n_free_total+1] neighbour list (block columns >= own) per free block, in blocks
   const int* nb_g;       // neighbour global block ids, ascending, first = self
-  const uint8_t* rowslot;     // per list entry: nnb(a) bytes, offset of the co-edge in the landmark's range or 0xFF
-  const long long* rs_off;    // [n_free_total] byte offset of block a's first entry row in rowslot
+  const int* pl_tab;     // per point-list entry: nnb(a) ints, list position of the co-edge on neighbour j or -1
+  const long long* pl_tab_off;  // [n_free_total] offset of block a's first entry row
+  const int* ll_tab;
+  const long long* ll_tab_off;
   // dynamic state
   double* pose_qt[2];
   double* pose_Rt[2];
@@ -72,8 +84,8 @@ struct BaView {
   // linearisation
   double* pt_H;   // [n_pt][9]  Hll (00 01 02 11 12 22) + bl (3)
   double* ln_H;   // [n_ln][14] Hll upper (10) + bl (4)
-  double* pe_W;   // [n_pe][18]
-  double* lc_W;   // [n_lc][24]
+  double* P_rec;  // [n_plist][27] per point-list entry: W (6x3), (Hll+lambda I)^-1 packed (6), D^-1 b_l (3)
+  double* L_rec;  // [n_llist][38] per line-list entry:  W (6x4), inverse packed (10), D^-1 b_l (4)
   double* ch_pose;  // [n_chunks][28] partial Hpp (21 upper) + bp (6) + n_active
   double* g_Hpp;    // [n_free_total][21]
   double* g_bp;     // [n_free_total][6]
@@ -82,15 +94,13 @@ struct BaView {
   double* lm_maxdiag;  // [n_pt+n_ln]
   uint8_t* lm_active;  // [n_pt+n_ln]
   // trial
-  double* pe_Y;   // [n_pe][18]
-  double* lc_Y;   // [n_lc][24]
   double* ch_S;   // chunk partial rows: at ch_S_off[chunk], 6 x (6*nnb) doubles + 6 (b part)
   const long long* ch_S_off;
   double* S_blk;  // [n_nb_total][36]
   double* g_bs;   // [n_free_total][6] bschur
   double* g_x;    // [n_free_total][6] pose solution (kept on failure)
-  double* pt_c;   // [n_pt][3]  Dinv * bl
-  double* ln_c;   // [n_ln][4]
+  double* pt_D;   // [n_pt][9]  (Hll+lambda I)^-1 packed (6) + D^-1 b_l (3)
+  double* ln_D;   // [n_ln][14] inverse packed (10) + D^-1 b_l (4)
   double* lm_chi2;
   double* lm_scale;
   // per-window LM state

@@ -150,10 +150,10 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_points(BaView v) {
   const int e0 = v.pt_obs_off[p], e1 = v.pt_obs_off[p + 1];
   for (int e = e0; e < e1; e++) {
     const int kf = v.pe_kf[e];
-    const int g = v.kf_g[kf];
-    double* W = v.pe_W + 18 * (size_t)e;
+    const int pos = v.pe_pos[e];
+    double* W = v.P_rec + 27 * (size_t)(pos < 0 ? 0 : pos);
     if (v.pe_level[e] != 0) {
-      if (g >= 0)
+      if (pos >= 0)
 #pragma unroll
         for (int k = 0; k < 18; k++) W[k] = 0.0;
       continue;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_points(BaView v) {
     H[5] += JW[2] * Jl[2] + JW[5] * Jl[5] + JW[8] * Jl[8];
 #pragma unroll
     for (int c = 0; c < 3; c++) bl[c] -= JW[c] * err[0] + JW[3 + c] * err[1] + JW[6 + c] * err[2];
-    if (g >= 0) {
+    if (pos >= 0) {
       double Jp[18];
       pt_jac_pose(xc, intr, stereo, Jp);
 #pragma unroll
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_lines(BaView v) {
   const int c0 = v.ln_obs_off[l], c1 = v.ln_obs_off[l + 1];
   for (int c = c0; c < c1; c++) {
     const int kf = v.lc_kf[c];
-    const int g = v.kf_g[kf];
+    const int pos = v.lc_pos[c];
     double W[24];
 #pragma unroll
     for (int k = 0; k < 24; k++) W[k] = 0.0;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_lines(BaView v) {
           for (int cc = r; cc < 4; cc++) H[u4(r, cc)] += JW[r] * Jl[cc] + JW[4 + r] * Jl[4 + cc];
           bl[r] -= JW[r] * err[0] + JW[4 + r] * err[1];
         }
-        if (g >= 0) {
+        if (pos >= 0) {
 #pragma unroll
           for (int r = 0; r < 6; r++)
 #pragma unroll
@@ -273,8 +273,8 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_lines(BaView v) {
         }
       }
     }
-    if (g >= 0) {
-      double* Wo = v.lc_W + 24 * (size_t)c;
+    if (pos >= 0) {
+      double* Wo = v.L_rec + 38 * (size_t)pos;
 #pragma unroll
       for (int k = 0; k < 24; k++) Wo[k] = W[k];
     }
@@ -290,6 +290,26 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_lines(BaView v) {
   v.lm_active[li] = nact > 0;
 }
 
+// fixed-order reduction of NV per-thread values over the CTA (LM_TPB threads); result in out[0..NV) for all threads
+template <int NV>
+__device__ __forceinline__ void block_reduce_nv(const double* acc, double (*part)[NV], double* out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    double x = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) part[wid][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s2 = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s2 += part[w][threadIdx.x];
+    out[threadIdx.x] = s2;
+  }
+  __syncthreads();
+}
+
 // pose pass: one CTA per chunk of a free keyframe's edge list; recomputes residual, weight and the pose Jacobian
 // and reduces Jp^T (w Omega) Jp and -Jp^T (w Omega) r in fixed order.
 __global__ void __launch_bounds__(LM_TPB) k_lin_poses(BaView v) {
@@ -299,17 +319,18 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_poses(BaView v) {
   const int w = v.kf_win[kf];
   if (v.w_phase[w] != PH_LIN) return;
   const int sel = v.w_sel[w];
-  __shared__ double sm[32];
+  __shared__ double part[LM_TPB / 32][28];
+  __shared__ double red[28];
   const double* Rt = v.pose_Rt[sel] + 12 * (size_t)kf;
   const double* intr = v.kf_intr + 5 * (size_t)kf;
   const double* cam = v.kf_lcam + 4 * (size_t)kf;
+  const bool is_pt = ch < v.n_chunks_pt;
   double acc[28];
 #pragma unroll
   for (int k = 0; k < 28; k++) acc[k] = 0.0;
   for (int i = v.ch_begin[ch] + threadIdx.x; i < v.ch_end[ch]; i += blockDim.x) {
-    const int ref = v.kfl_ref[i];
-    if (ref >= 0) {
-      const int e = ref;
+    if (is_pt) {
+      const int e = v.pl_edge[i];
       if (v.pe_level[e] != 0) continue;
       const double* X = v.pt_xyz[sel] + 3 * (size_t)v.pe_pt[e];
       const float* obs = v.pe_uvr + 3 * (size_t)e;
@@ -332,7 +353,7 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_poses(BaView v) {
       }
       acc[27] += 1.0;
     } else {
-      const int c = ~ref;
+      const int c = v.ll_cell[i];
       const int l = v.lc_ln[c];
       if (v.ln_removed[l]) continue;
       const uint8_t lv0 = v.lc_level[2 * c], lv1 = v.lc_level[2 * c + 1];
@@ -372,11 +393,8 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_poses(BaView v) {
       }
     }
   }
-#pragma unroll 1
-  for (int k = 0; k < 28; k++) {
-    const double s = block_sum(acc[k], sm);
-    if (threadIdx.x == 0) v.ch_pose[28 * (size_t)ch + k] = s;
-  }
+  block_reduce_nv<28>(acc, part, red);
+  if (threadIdx.x < 28) v.ch_pose[28 * (size_t)ch + threadIdx.x] = red[threadIdx.x];
 }
 
 // sum the chunk partials of each free keyframe (fixed order)
@@ -387,7 +405,8 @@ __global__ void k_reduce_pose(BaView v) {
   const int w = v.kf_win[v.g_kf[g]];
   if (v.w_phase[w] != PH_LIN) return;
   double s = 0;
-  for (int ch = v.g_ch0[g]; ch < v.g_ch0[g + 1]; ch++) s += v.ch_pose[28 * (size_t)ch + k];
+  for (int ch = v.g_chp0[g]; ch < v.g_chp0[g + 1]; ch++) s += v.ch_pose[28 * (size_t)ch + k];
+  for (int ch = v.g_chl0[g]; ch < v.g_chl0[g + 1]; ch++) s += v.ch_pose[28 * (size_t)ch + k];
   if (k < 21) v.g_Hpp[21 * (size_t)g + k] = s;
   else if (k < 27) v.g_bp[6 * (size_t)g + (k - 21)] = s;
   else v.g_nact[g] = (int)(s + 0.5);
@@ -458,6 +477,8 @@ __global__ void k_begin(BaView v) {
 // ------------------------------------------------------------------------------------------------
 // trial: Schur complement pieces per landmark (lambda dependent)
 // ------------------------------------------------------------------------------------------------
+// per landmark: Dinv = (Hll + lambda I)^-1 (general inverse, block_solver.hpp:389), c = Dinv b_l; both are also
+// scattered into the list-order records so that k_schur_rows reads one contiguous record per entry.
 __global__ void __launch_bounds__(LM_TPB) k_schur_points(BaView v) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= v.n_pt) return;
@@ -465,32 +486,23 @@ __global__ void __launch_bounds__(LM_TPB) k_schur_points(BaView v) {
   if (v.w_phase[w] == PH_DONE) return;
   const double lam = v.w_lambda[w];
   const double* Hi = v.pt_H + 9 * (size_t)p;
-  const bool act = v.lm_active[p];
   double Di[9];
   {
     const double A[9] = {Hi[0] + lam, Hi[1], Hi[2], Hi[1], Hi[3] + lam, Hi[4], Hi[2], Hi[4], Hi[5] + lam};
     inv3_sym(A, Di);
   }
-  if (act) {
-    double* c = v.pt_c + 3 * (size_t)p;
+  double rec[9] = {Di[0], Di[1], Di[2], Di[4], Di[5], Di[8], 0, 0, 0};
 #pragma unroll
-    for (int i = 0; i < 3; i++) c[i] = Di[3 * i] * Hi[6] + Di[3 * i + 1] * Hi[7] + Di[3 * i + 2] * Hi[8];
-  }
+  for (int i = 0; i < 3; i++) rec[6 + i] = Di[3 * i] * Hi[6] + Di[3 * i + 1] * Hi[7] + Di[3 * i + 2] * Hi[8];
+  double* Do = v.pt_D + 9 * (size_t)p;
+#pragma unroll
+  for (int k = 0; k < 9; k++) Do[k] = rec[k];
   for (int e = v.pt_obs_off[p]; e < v.pt_obs_off[p + 1]; e++) {
-    if (v.kf_g[v.pe_kf[e]] < 0) continue;
-    const double* W = v.pe_W + 18 * (size_t)e;
-    double* Y = v.pe_Y + 18 * (size_t)e;
-    if (!act || v.pe_level[e] != 0) {
+    const int pos = v.pe_pos[e];
+    if (pos < 0) continue;
+    double* R = v.P_rec + 27 * (size_t)pos + 18;
 #pragma unroll
-      for (int k = 0; k < 18; k++) Y[k] = 0.0;
-      continue;
-    }
-#pragma unroll
-    for (int r = 0; r < 6; r++) {
-      const double w0 = W[3 * r], w1 = W[3 * r + 1], w2 = W[3 * r + 2];
-#pragma unroll
-      for (int c = 0; c < 3; c++) Y[3 * r + c] = w0 * Di[c] + w1 * Di[3 + c] + w2 * Di[6 + c];
-    }
+    for (int k = 0; k < 9; k++) R[k] = rec[k];
   }
 }
 
@@ -501,7 +513,6 @@ __global__ void __launch_bounds__(LM_TPB) k_schur_lines(BaView v) {
   if (v.w_phase[w] == PH_DONE) return;
   const double lam = v.w_lambda[w];
   const double* Hi = v.ln_H + 14 * (size_t)l;
-  const bool act = v.lm_active[v.n_pt + l];
   double Di[16];
   {
     double A[16];
@@ -511,82 +522,107 @@ __global__ void __launch_bounds__(LM_TPB) k_schur_lines(BaView v) {
       for (int c = 0; c < 4; c++) A[4 * r + c] = Hi[r <= c ? u4(r, c) : u4(c, r)] + (r == c ? lam : 0.0);
     inv4(A, Di);
   }
-  if (act) {
-    double* c = v.ln_c + 4 * (size_t)l;
+  double rec[14];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-      c[i] = Di[4 * i] * Hi[10] + Di[4 * i + 1] * Hi[11] + Di[4 * i + 2] * Hi[12] + Di[4 * i + 3] * Hi[13];
-  }
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int c = r; c < 4; c++) rec[u4(r, c)] = Di[4 * r + c];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    rec[10 + i] = Di[4 * i] * Hi[10] + Di[4 * i + 1] * Hi[11] + Di[4 * i + 2] * Hi[12] + Di[4 * i + 3] * Hi[13];
+  double* Do = v.ln_D + 14 * (size_t)l;
+#pragma unroll
+  for (int k = 0; k < 14; k++) Do[k] = rec[k];
   for (int cc = v.ln_obs_off[l]; cc < v.ln_obs_off[l + 1]; cc++) {
-    if (v.kf_g[v.lc_kf[cc]] < 0) continue;
-    const double* W = v.lc_W + 24 * (size_t)cc;
-    double* Y = v.lc_Y + 24 * (size_t)cc;
-    if (!act) {
+    const int pos = v.lc_pos[cc];
+    if (pos < 0) continue;
+    double* R = v.L_rec + 38 * (size_t)pos + 24;
 #pragma unroll
-      for (int k = 0; k < 24; k++) Y[k] = 0.0;
-      continue;
-    }
-#pragma unroll
-    for (int r = 0; r < 6; r++) {
-      const double w0 = W[4 * r], w1 = W[4 * r + 1], w2 = W[4 * r + 2], w3 = W[4 * r + 3];
-#pragma unroll
-      for (int c = 0; c < 4; c++) Y[4 * r + c] = w0 * Di[c] + w1 * Di[4 + c] + w2 * Di[8 + c] + w3 * Di[12 + c];
-    }
+    for (int k = 0; k < 14; k++) R[k] = rec[k];
   }
 }
 
-// Schur rows: CTA = one chunk of free keyframe a's edge list; thread t = (neighbour j, column c) owns the 6
-// accumulators S[a, nb_j][0..5][c] in registers.  Per list entry (landmark l seen by a):
-//   S[a,b] -= Y_(l,a) W_(l,b)^T  for every free b >= a that also sees l;   bschur[a] -= Y_(l,a) bl
-// (block_solver.hpp:381-440).  The co-edge of (l,b) is found through the rowslot byte table.
-__global__ void __launch_bounds__(1024) k_schur_rows(BaView v) {
-  const int ch = blockIdx.x;
+// Schur rows: CTA = one chunk of free keyframe a's list; thread t = (neighbour j, column c) owns the 6 accumulators
+// S[a, nb_j][0..5][c] in registers.  Per list entry (landmark l seen by a) and every free b >= a that also sees l:
+//   S[a,b] -= W_(l,a) Dinv_l W_(l,b)^T ;   bschur[a] -= W_(l,a) (Dinv_l b_l)          (block_solver.hpp:381-440)
+// Entries are grouped into segments that share one set of co-observing keyframes, so a thread tests "does my
+// neighbour see these landmarks" once per segment; own records (W_a, Dinv, c) are staged through shared memory in
+// coalesced blocks; the co-edge row W_b[c][:] is a gather through the int position table.
+constexpr int ROW_SB = 32;  // entries staged per block
+template <int D, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_schur_rows(BaView v, int chunk_base) {
+  constexpr int REC = 6 * D + D * (D + 1) / 2 + D;
+  constexpr int OFF_D = 6 * D, OFF_C = 6 * D + D * (D + 1) / 2;
+  const int ch = chunk_base + blockIdx.x;
   const int g = v.ch_g[ch];
   const int kf = v.g_kf[g];
   const int w = v.kf_win[kf];
   if (v.w_phase[w] == PH_DONE) return;
+  __shared__ double srec[ROW_SB * REC];
   const int nnb = v.nb_off[g + 1] - v.nb_off[g];
   const int t = threadIdx.x;
   const bool live = t < 6 * nnb;
-  const int j = t / 6, c = t - 6 * j;
+  const int j = live ? t / 6 : 0, c = t - 6 * (t / 6);
   double acc[6] = {0, 0, 0, 0, 0, 0};
   double bacc = 0;
   const int i0 = v.ch_begin[ch], i1 = v.ch_end[ch];
-  const uint8_t* slot_base = v.rowslot + v.rs_off[g] + (long long)(i0 - v.kfl_off[g]) * nnb + j;
-  if (live) {
-    for (int i = i0; i < i1; i++, slot_base += nnb) {
-      const int ref = v.kfl_ref[i];
-      const uint8_t slot = *slot_base;
-      if (ref >= 0) {
-        const int e = ref;
-        const double* Y = v.pe_Y + 18 * (size_t)e;
-        if (j == 0) {
-          const double* bl = v.pt_H + 9 * (size_t)v.pe_pt[e] + 6;
-          bacc += Y[3 * c] * bl[0] + Y[3 * c + 1] * bl[1] + Y[3 * c + 2] * bl[2];
-        }
-        if (slot != 0xFF) {
-          const int e2 = v.pt_obs_off[v.pe_pt[e]] + slot;
-          const double* Wr = v.pe_W + 18 * (size_t)e2 + 3 * c;
-          const double w0 = Wr[0], w1 = Wr[1], w2 = Wr[2];
+  const double* rec_g = D == 3 ? v.P_rec : v.L_rec;
+  const int l_off = (D == 3 ? v.pl_off : v.ll_off)[g];
+  const int* tab = (D == 3 ? v.pl_tab : v.ll_tab) + (D == 3 ? v.pl_tab_off : v.ll_tab_off)[g] + (long long)(i0 - l_off) * nnb + j;
+  int seg = v.ch_seg0[ch];
+  const int seg_end_idx = v.ch_seg0[ch + 1];
+  for (int blk = i0; blk < i1; blk += ROW_SB) {
+    const int nb = min(ROW_SB, i1 - blk);
+    __syncthreads();
+    for (int q = t; q < nb * REC; q += blockDim.x) srec[q] = rec_g[(size_t)blk * REC + q];
+    __syncthreads();
+    // segments intersecting [blk, blk+nb)
+    while (seg < seg_end_idx && v.seg_end[seg] <= blk) seg++;
+    for (int s2 = seg; s2 < seg_end_idx && v.seg_begin[s2] < blk + nb; s2++) {
+      const int a = max(v.seg_begin[s2], blk), b = min(v.seg_end[s2], blk + nb);
+      if (!live) continue;
+      if (j == 0) {  // b_schur part (every entry)
+        for (int i = a; i < b; i++) {
+          const double* R = srec + (i - blk) * REC;
+          double sb = 0;
 #pragma unroll
-          for (int r = 0; r < 6; r++) acc[r] += Y[3 * r] * w0 + Y[3 * r + 1] * w1 + Y[3 * r + 2] * w2;
+          for (int k = 0; k < D; k++) sb += R[D * c + k] * R[OFF_C + k];
+          bacc += sb;
         }
-      } else {
-        const int cc = ~ref;
-        const double* Y = v.lc_Y + 24 * (size_t)cc;
-        if (j == 0) {
-          const double* bl = v.ln_H + 14 * (size_t)v.lc_ln[cc] + 10;
-          bacc += Y[4 * c] * bl[0] + Y[4 * c + 1] * bl[1] + Y[4 * c + 2] * bl[2] + Y[4 * c + 3] * bl[3];
-        }
-        if (slot != 0xFF) {
-          const int c2 = v.ln_obs_off[v.lc_ln[cc]] + slot;
-          const double* Wr = v.lc_W + 24 * (size_t)c2 + 4 * c;
-          const double w0 = Wr[0], w1 = Wr[1], w2 = Wr[2], w3 = Wr[3];
+      }
+      if (tab[(long long)(a - i0) * nnb] < 0) continue;  // the whole segment misses this neighbour
+#pragma unroll 4
+      for (int i = a; i < b; i++) {
+        const int pos2 = tab[(long long)(i - i0) * nnb];
+        const double* Wb = rec_g + (size_t)pos2 * REC + D * c;
+        const double* R = srec + (i - blk) * REC;
+        double wb[D], z[D];
 #pragma unroll
-          for (int r = 0; r < 6; r++) acc[r] += Y[4 * r] * w0 + Y[4 * r + 1] * w1 + Y[4 * r + 2] * w2 + Y[4 * r + 3] * w3;
+        for (int k = 0; k < D; k++) wb[k] = Wb[k];
+        if (D == 3) {
+          z[0] = R[OFF_D + 0] * wb[0] + R[OFF_D + 1] * wb[1] + R[OFF_D + 2] * wb[2];
+          z[1] = R[OFF_D + 1] * wb[0] + R[OFF_D + 3] * wb[1] + R[OFF_D + 4] * wb[2];
+          z[2] = R[OFF_D + 2] * wb[0] + R[OFF_D + 4] * wb[1] + R[OFF_D + 5] * wb[2];
+        } else {
+#pragma unroll
+          for (int r = 0; r < D; r++) {
+            double zz = 0;
+#pragma unroll
+            for (int k = 0; k < D; k++) zz += R[OFF_D + (r <= k ? u4(r, k) : u4(k, r))] * wb[k];
+            z[r] = zz;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+          double a2 = 0;
+#pragma unroll
+          for (int k = 0; k < D; k++) a2 += R[D * r + k] * z[k];
+          acc[r] += a2;
         }
       }
     }
+  }
+  if (live) {
     double* out = v.ch_S + v.ch_S_off[ch];
     const int ld = 6 * nnb;
 #pragma unroll
@@ -606,10 +642,15 @@ __global__ void k_reduce_rows(BaView v, int with_diag) {
   for (int t = threadIdx.x; t < ld; t += blockDim.x) {
     const int j = t / 6, c = t - 6 * j;
     double s[6] = {0, 0, 0, 0, 0, 0};
-    for (int ch = v.g_ch0[g]; ch < v.g_ch0[g + 1]; ch++) {
-      const double* part = v.ch_S + v.ch_S_off[ch];
+    double sb = 0;
+    for (int rng = 0; rng < 2; rng++) {
+      const int c0 = rng == 0 ? v.g_chp0[g] : v.g_chl0[g], c1 = rng == 0 ? v.g_chp0[g + 1] : v.g_chl0[g + 1];
+      for (int ch = c0; ch < c1; ch++) {
+        const double* part = v.ch_S + v.ch_S_off[ch];
 #pragma unroll
-      for (int r = 0; r < 6; r++) s[r] += part[(size_t)r * ld + t];
+        for (int r = 0; r < 6; r++) s[r] += part[(size_t)r * ld + t];
+        if (j == 0) sb += part[(size_t)6 * ld + c];
+      }
     }
     double* S = v.S_blk + 36 * (size_t)(v.nb_off[g] + j);
 #pragma unroll
@@ -622,11 +663,7 @@ __global__ void k_reduce_rows(BaView v, int with_diag) {
       }
       S[6 * r + c] = d - s[r];
     }
-    if (j == 0) {
-      double sb = 0;
-      for (int ch = v.g_ch0[g]; ch < v.g_ch0[g + 1]; ch++) sb += (v.ch_S + v.ch_S_off[ch])[(size_t)6 * ld + c];
-      v.g_bs[6 * (size_t)g + c] = (with_diag ? v.g_bp[6 * (size_t)g + c] : 0.0) - sb;
-    }
+    if (j == 0) v.g_bs[6 * (size_t)g + c] = (with_diag ? v.g_bp[6 * (size_t)g + c] : 0.0) - sb;
   }
 }
 
@@ -637,6 +674,7 @@ __global__ void k_reduce_rows(BaView v, int with_diag) {
 // ------------------------------------------------------------------------------------------------
 __device__ bool ldlt_solve_cta(double* A, int n, int ld, double* b /*in: rhs, out: x*/, double* tmp, int* flag) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
   if (tid == 0) *flag = 1;
   __syncthreads();
   for (int j = 0; j < n; j++) {
@@ -647,44 +685,39 @@ __device__ bool ldlt_solve_cta(double* A, int n, int ld, double* b /*in: rhs, ou
       return false;
     }
     const double id = 1.0 / d;
-    for (int i = j + 1 + tid; i < n; i += nt) {
-      const double a = A[(size_t)i * ld + j];
-      tmp[i] = a;
-      A[(size_t)i * ld + j] = a * id;
-    }
+    for (int i = j + 1 + tid; i < n; i += nt) tmp[i] = A[(size_t)i * ld + j];
     __syncthreads();
-    const int m = n - j - 1;
-    // trailing update on the lower triangle: A[i][k] -= L[i][j] * tmp[k], j < k <= i
-    for (int idx = tid; idx < m * m; idx += nt) {
-      const int ii = idx / m, kk = idx - ii * m;
-      if (kk <= ii) {
-        const int i = j + 1 + ii, k = j + 1 + kk;
-        A[(size_t)i * ld + k] -= A[(size_t)i * ld + j] * tmp[k];
+    const double bj = b[j];
+    // one warp per row: A[i][k] -= L[i][j] * tmp[k] for j < k <= i ; forward substitution fused (b[i] -= L[i][j] b[j])
+    for (int i = j + 1 + wid; i < n; i += nw) {
+      const double lij = tmp[i] * id;
+      double* row = A + (size_t)i * ld;
+      for (int k = j + 1 + lane; k <= i; k += 32) row[k] -= lij * tmp[k];
+      if (lane == 0) {
+        row[j] = lij;
+        b[i] -= lij * bj;
       }
     }
     __syncthreads();
   }
-  // forward: L z = b
-  for (int j = 0; j < n; j++) {
-    const double bj = b[j];
-    for (int i = j + 1 + tid; i < n; i += nt) b[i] -= A[(size_t)i * ld + j] * bj;
-    __syncthreads();
-  }
   for (int i = tid; i < n; i += nt) b[i] /= A[(size_t)i * ld + i];
   __syncthreads();
-  // backward: L^T x = z
-  for (int j = n - 1; j >= 0; j--) {
-    const double xj = b[j];
-    for (int i = tid; i < j; i += nt) b[i] -= A[(size_t)j * ld + i] * xj;
-    __syncthreads();
+  // backward: L^T x = z, one warp
+  if (wid == 0) {
+    for (int j = n - 1; j >= 0; j--) {
+      const double xj = b[j];
+      for (int i = lane; i < j; i += 32) b[i] -= A[(size_t)j * ld + i] * xj;
+      __syncwarp();
+    }
   }
+  __syncthreads();
   return true;
 }
 
 // one CTA per window: assemble the dense reduced camera system from the block rows, factor, solve, apply the
 // pose update T <- exp(x) T into the trial buffer and accumulate the pose part of computeScale().
 template <bool SMEM>
-__global__ void __launch_bounds__(256) k_solve(BaView v) {
+__global__ void __launch_bounds__(512) k_solve(BaView v) {
   extern __shared__ double smem[];
   const int w = blockIdx.x;
   if (v.w_phase[w] == PH_DONE) return;
@@ -772,21 +805,26 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_points(BaView v) {
     v.lm_scale[p] = 0.0;
     return;
   }
-  const double* cp = v.pt_c + 3 * (size_t)p;
-  double xl[3] = {cp[0], cp[1], cp[2]};
+  const double* Dp = v.pt_D + 9 * (size_t)p;
+  double s3[3] = {0, 0, 0};
   const int e0 = v.pt_obs_off[p], e1 = v.pt_obs_off[p + 1];
   for (int e = e0; e < e1; e++) {
     if (v.pe_level[e] != 0) continue;
-    const int g = v.kf_g[v.pe_kf[e]];
-    if (g < 0) continue;
-    const double* Y = v.pe_Y + 18 * (size_t)e;
-    const double* xp = v.g_x + 6 * (size_t)g;
+    const int pos = v.pe_pos[e];
+    if (pos < 0) continue;
+    const double* W = v.P_rec + 27 * (size_t)pos;
+    const double* xp = v.g_x + 6 * (size_t)v.kf_g[v.pe_kf[e]];
 #pragma unroll
     for (int r = 0; r < 6; r++) {
       const double x = xp[r];
-      xl[0] -= Y[3 * r] * x; xl[1] -= Y[3 * r + 1] * x; xl[2] -= Y[3 * r + 2] * x;
+      s3[0] += W[3 * r] * x; s3[1] += W[3 * r + 1] * x; s3[2] += W[3 * r + 2] * x;
     }
   }
+  // xl = Dinv (bl - W^T xp) = c - Dinv (W^T xp)
+  double xl[3];
+  xl[0] = Dp[6] - (Dp[0] * s3[0] + Dp[1] * s3[1] + Dp[2] * s3[2]);
+  xl[1] = Dp[7] - (Dp[1] * s3[0] + Dp[3] * s3[1] + Dp[4] * s3[2]);
+  xl[2] = Dp[8] - (Dp[2] * s3[0] + Dp[4] * s3[1] + Dp[5] * s3[2]);
   const double X[3] = {Xo[0] + xl[0], Xo[1] + xl[1], Xo[2] + xl[2]};
   Xn[0] = X[0]; Xn[1] = X[1]; Xn[2] = X[2];
   const double lam = v.w_lambda[w];
@@ -827,19 +865,27 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_lines(BaView v) {
     v.lm_scale[li] = 0.0;
     return;
   }
-  const double* cp = v.ln_c + 4 * (size_t)l;
-  double xl[4] = {cp[0], cp[1], cp[2], cp[3]};
+  const double* Dp = v.ln_D + 14 * (size_t)l;
+  double s4[4] = {0, 0, 0, 0};
   const int c0 = v.ln_obs_off[l], c1 = v.ln_obs_off[l + 1];
   for (int c = c0; c < c1; c++) {
-    const int g = v.kf_g[v.lc_kf[c]];
-    if (g < 0) continue;
-    const double* Y = v.lc_Y + 24 * (size_t)c;
-    const double* xp = v.g_x + 6 * (size_t)g;
+    const int pos = v.lc_pos[c];
+    if (pos < 0) continue;
+    const double* W = v.L_rec + 38 * (size_t)pos;
+    const double* xp = v.g_x + 6 * (size_t)v.kf_g[v.lc_kf[c]];
 #pragma unroll
     for (int r = 0; r < 6; r++) {
       const double x = xp[r];
-      xl[0] -= Y[4 * r] * x; xl[1] -= Y[4 * r + 1] * x; xl[2] -= Y[4 * r + 2] * x; xl[3] -= Y[4 * r + 3] * x;
+      s4[0] += W[4 * r] * x; s4[1] += W[4 * r + 1] * x; s4[2] += W[4 * r + 2] * x; s4[3] += W[4 * r + 3] * x;
     }
+  }
+  double xl[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    double zz = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) zz += Dp[r <= k ? u4(r, k) : u4(k, r)] * s4[k];
+    xl[r] = Dp[10 + r] - zz;
   }
   const double st0[5] = {so[0], so[1], so[2], so[3], so[4]};
   double st[5];
