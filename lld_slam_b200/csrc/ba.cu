@@ -27,6 +27,7 @@ struct BaState {
   int max_n = 0;       // largest reduced system dimension over the windows
   int max_nnb = 0;
   size_t n_nb_total = 0;
+  int umax = 5;
   bool global_mode = false;
   const double* d_kf_Tcw_in = nullptr;
   const double* d_pt_in = nullptr;
@@ -151,21 +152,30 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     return key;
   };
   std::vector<int> pt_order(n_pt), ln_order(n_ln);
-  {
-    std::vector<uint64_t> key(std::max(n_pt, n_ln));
-    for (int w = 0; w < nw; w++) {
-      const int g0 = w_g0[w], nf = w_g0[w + 1] - g0;
-      for (int i = p->pt_off[w]; i < p->pt_off[w + 1]; i++) { key[i] = signature(p->pt_obs_off, pe_kf, i, g0, nf); pt_order[i] = i; }
-      std::stable_sort(pt_order.begin() + p->pt_off[w], pt_order.begin() + p->pt_off[w + 1],
-                       [&](int a, int b) { return key[a] < key[b]; });
-    }
-    for (int w = 0; w < nw; w++) {
-      const int g0 = w_g0[w], nf = w_g0[w + 1] - g0;
-      for (int i = p->ln_off[w]; i < p->ln_off[w + 1]; i++) { key[i] = signature(p->ln_obs_off, lc_kf, i, g0, nf); ln_order[i] = i; }
-      std::stable_sort(ln_order.begin() + p->ln_off[w], ln_order.begin() + p->ln_off[w + 1],
-                       [&](int a, int b) { return key[a] < key[b]; });
-    }
+  std::vector<uint64_t> pt_key(n_pt), ln_key(n_ln);
+  for (int w = 0; w < nw; w++) {
+    const int g0 = w_g0[w], nf = w_g0[w + 1] - g0;
+    for (int i = p->pt_off[w]; i < p->pt_off[w + 1]; i++) { pt_key[i] = signature(p->pt_obs_off, pe_kf, i, g0, nf); pt_order[i] = i; }
+    std::stable_sort(pt_order.begin() + p->pt_off[w], pt_order.begin() + p->pt_off[w + 1],
+                     [&](int a, int b) { return pt_key[a] < pt_key[b]; });
+    for (int i = p->ln_off[w]; i < p->ln_off[w + 1]; i++) { ln_key[i] = signature(p->ln_obs_off, lc_kf, i, g0, nf); ln_order[i] = i; }
+    std::stable_sort(ln_order.begin() + p->ln_off[w], ln_order.begin() + p->ln_off[w + 1],
+                     [&](int a, int b) { return ln_key[a] < ln_key[b]; });
   }
+  // dense mode: every window small enough to keep its whole S in one CTA's registers, one edge per (landmark, KF)
+  bool dense = !global_mode && S->max_n <= 6 * 32;
+  auto has_dup = [&](int n_lm, const int* off, const std::vector<int>& ekf) {
+    std::vector<int> seen;
+    for (int i = 0; i < n_lm; i++) {
+      seen.clear();
+      for (int e = off[i]; e < off[i + 1]; e++) seen.push_back(ekf[e]);
+      std::sort(seen.begin(), seen.end());
+      if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) return true;
+    }
+    return false;
+  };
+  if (dense && (has_dup(n_pt, p->pt_obs_off, pe_kf) || has_dup(n_ln, p->ln_obs_off, lc_kf))) dense = false;
+  v.dense_mode = dense ? 1 : 0;
   // per-free-keyframe lists (counting sort in signature order), separately for point edges and line cells
   auto build_lists = [&](int n_lm, const int* off, const std::vector<int>& ekf, const std::vector<int>& order,
                          std::vector<int>& l_off, std::vector<int>& l_ref, std::vector<int>& e_pos) {
@@ -260,10 +270,73 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
       }
     }
   };
-  std::vector<long long> pl_tab_off, ll_tab_off;
-  std::vector<int> pl_tab, ll_tab;
-  build_tab(pl_off, pl_edge, p->pt_obs_off, pe_pt, pe_kf, pe_pos, pl_tab_off, pl_tab);
-  build_tab(ll_off, ll_cell, p->ln_obs_off, lc_ln, lc_kf, lc_pos, ll_tab_off, ll_tab);
+  std::vector<long long> pl_tab_off(std::max(nG, 1), 0), ll_tab_off(std::max(nG, 1), 0);
+  std::vector<int> pl_tab(1, -1), ll_tab(1, -1);
+  if (!dense) {
+    build_tab(pl_off, pl_edge, p->pt_obs_off, pe_pt, pe_kf, pe_pos, pl_tab_off, pl_tab);
+    build_tab(ll_off, ll_cell, p->ln_obs_off, lc_ln, lc_kf, lc_pos, ll_tab_off, ll_tab);
+  }
+  // dense-mode structures
+  std::vector<int> pt_spos(std::max(n_pt, 1), 0), ln_spos(std::max(n_ln, 1), 0), pts_w0(n_pt + 1, 0), lns_w0(n_ln + 1, 0);
+  std::vector<uint32_t> pts_mask(std::max(n_pt, 1), 0), lns_mask(std::max(n_ln, 1), 0);
+  std::vector<int> pe_wpos(std::max(n_pe, 1), -1), lc_wpos(std::max(n_lc, 1), -1);
+  std::vector<int> dt_begin, dt_end, dsp_tile0;
+  std::vector<long long> dpart_off;
+  long long dpart_total = 0;
+  int n_splits = 1, umax = 5;
+  size_t n_pw = 0, n_lw = 0;
+  if (dense) {
+    auto slots = [&](int n_lm, const int* off, const std::vector<int>& ekf, const std::vector<int>& order,
+                     const std::vector<uint64_t>& key, std::vector<int>& spos, std::vector<uint32_t>& mask,
+                     std::vector<int>& w0, std::vector<int>& wpos) {
+      std::vector<std::pair<int, int>> ge;
+      for (int oi = 0; oi < n_lm; oi++) {
+        const int i = order[oi];
+        spos[i] = oi;
+        mask[oi] = (uint32_t)key[i];
+        ge.clear();
+        for (int e = off[i]; e < off[i + 1]; e++)
+          if (kf_g[ekf[e]] >= 0) ge.push_back({kf_g[ekf[e]], e});
+        std::sort(ge.begin(), ge.end());
+        for (size_t k = 0; k < ge.size(); k++) wpos[ge[k].second] = w0[oi] + (int)k;
+        w0[oi + 1] = w0[oi] + (int)ge.size();
+      }
+    };
+    slots(n_pt, p->pt_obs_off, pe_kf, pt_order, pt_key, pt_spos, pts_mask, pts_w0, pe_wpos);
+    slots(n_ln, p->ln_obs_off, lc_kf, ln_order, ln_key, ln_spos, lns_mask, lns_w0, lc_wpos);
+    n_pw = (size_t)pts_w0[n_pt]; n_lw = (size_t)lns_w0[n_ln];
+    n_splits = std::max(1, std::min(32, (3 * c->sm_count + nw - 1) / nw));
+    for (int w = 0; w < nw; w++) {
+      const int nf = w_g0[w + 1] - w_g0[w];
+      umax = std::max(umax, (nf * (nf + 1) / 2 * 6 + 255) / 256);
+    }
+    const int DT_LM_H = 64, DT_EDGES_H = 256;
+    for (int kind = 0; kind < 2; kind++) {
+      const int* loff = kind == 0 ? p->pt_off : p->ln_off;
+      const std::vector<int>& w0 = kind == 0 ? pts_w0 : lns_w0;
+      for (int w = 0; w < nw; w++) {
+        const int t0 = (int)dt_begin.size();
+        int b = loff[w];
+        while (b < loff[w + 1]) {
+          int e = b;
+          while (e < loff[w + 1] && e - b < DT_LM_H && w0[e + 1] - w0[b] <= DT_EDGES_H) e++;
+          if (e == b) e = b + 1;  // a single landmark never exceeds the slot cap (<= 32 free keyframes)
+          dt_begin.push_back(b); dt_end.push_back(e);
+          b = e;
+        }
+        const int nt = (int)dt_begin.size() - t0;
+        for (int sp = 0; sp < n_splits; sp++) dsp_tile0.push_back(t0 + (int)((long long)nt * sp / n_splits));
+      }
+      dsp_tile0.push_back((int)dt_begin.size());
+    }
+    for (int kind = 0; kind < 2; kind++)
+      for (int w = 0; w < nw; w++) {
+        const int nf = w_g0[w + 1] - w_g0[w];
+        for (int sp = 0; sp < n_splits; sp++) { dpart_off.push_back(dpart_total); dpart_total += 36LL * (nf * (nf + 1) / 2) + 6 * nf; }
+      }
+  }
+  v.n_splits = n_splits;
+  S->umax = umax;
   // chunks + segments (runs of entries whose table rows have the same -1 pattern)
   const long long n_list_total = (long long)n_plist + n_llist;
   int CH = CHUNK;
@@ -286,8 +359,10 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         ch_g.push_back(g); ch_begin.push_back(b); ch_end.push_back(e);
         ch_seg0.push_back((int)seg_begin.size());
         int s0 = b;
-        for (int i = b + 1; i <= e; i++)
-          if (i == e || !same(i - 1, i)) { seg_begin.push_back(s0); seg_end.push_back(i); s0 = i; }
+        if (dense) { seg_begin.push_back(b); seg_end.push_back(e); }
+        else
+          for (int i = b + 1; i <= e; i++)
+            if (i == e || !same(i - 1, i)) { seg_begin.push_back(s0); seg_end.push_back(i); s0 = i; }
       }
     }
     g_c0[nG] = (int)ch_g.size();
@@ -365,6 +440,21 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   UP(tmp_l, pl_tab_off.data(), nG); v.pl_tab_off = tmp_l;
   UP(tmp_l, ll_tab_off.data(), nG); v.ll_tab_off = tmp_l;
   UP(tmp_l, ch_S_off.data(), n_ch); v.ch_S_off = tmp_l;
+  UP(tmp_i, pt_spos.data(), n_pt); v.pt_spos = tmp_i;
+  UP(tmp_i, ln_spos.data(), n_ln); v.ln_spos = tmp_i;
+  UP(tmp_i, pts_w0.data(), n_pt + 1); v.pts_w0 = tmp_i;
+  UP(tmp_i, lns_w0.data(), n_ln + 1); v.lns_w0 = tmp_i;
+  UP(tmp_i, pe_wpos.data(), n_pe); v.pe_wpos = tmp_i;
+  UP(tmp_i, lc_wpos.data(), n_lc); v.lc_wpos = tmp_i;
+  UP(tmp_i, dt_begin.data(), dt_begin.size()); v.dt_begin = tmp_i;
+  UP(tmp_i, dt_end.data(), dt_end.size()); v.dt_end = tmp_i;
+  UP(tmp_i, dsp_tile0.data(), dsp_tile0.size()); v.dsp_tile0 = tmp_i;
+  UP(tmp_l, dpart_off.data(), dpart_off.size()); v.dpart_off = tmp_l;
+  {
+    uint32_t* tmp_m;
+    UP(tmp_m, pts_mask.data(), n_pt); v.pts_mask = tmp_m;
+    UP(tmp_m, lns_mask.data(), n_ln); v.lns_mask = tmp_m;
+  }
   UP(tmp_l, w_scr.data(), nw); v.w_scratch_off = tmp_l;
   double *d_T, *d_P, *d_L;
   UP(d_T, p->kf_Tcw, 12 * (size_t)n_kf);
@@ -382,7 +472,10 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   DEV(v.pe_level, uint8_t, n_pe); DEV(v.lc_level, uint8_t, 2 * (size_t)n_lc); DEV(v.ln_removed, uint8_t, n_ln);
   DEV(v.pe_chi2, double, n_pe); DEV(v.lc_chi2, double, 2 * (size_t)n_lc);
   DEV(v.pt_H, double, 9 * (size_t)n_pt); DEV(v.ln_H, double, 14 * (size_t)n_ln);
-  DEV(v.P_rec, double, 27 * (size_t)n_plist); DEV(v.L_rec, double, 38 * (size_t)n_llist);
+  DEV(v.P_rec, double, dense ? 1 : 27 * (size_t)n_plist); DEV(v.L_rec, double, dense ? 1 : 38 * (size_t)n_llist);
+  DEV(v.pe_Wl, double, 18 * n_pw); DEV(v.lc_Wl, double, 24 * n_lw);
+  DEV(v.pts_D, double, dense ? 9 * (size_t)n_pt : 1); DEV(v.lns_D, double, dense ? 14 * (size_t)n_ln : 1);
+  DEV(v.dpart, double, (size_t)dpart_total);
   DEV(v.ch_pose, double, 28 * (size_t)n_ch);
   DEV(v.g_Hpp, double, 21 * (size_t)nG); DEV(v.g_bp, double, 6 * (size_t)nG); DEV(v.g_nact, int, nG);
   DEV(v.lm_chi2lin, double, n_pt + n_ln); DEV(v.lm_maxdiag, double, n_pt + n_ln); DEV(v.lm_active, uint8_t, n_pt + n_ln);
@@ -504,7 +597,20 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   LLD_LAUNCH(c, k_begin, cdiv(v.n_win, 64), 64, 0, v);
   if (v.n_pt) LLD_LAUNCH(c, k_schur_points, gp, LM_TPB, 0, v);
   if (v.n_ln) LLD_LAUNCH(c, k_schur_lines, gl, LM_TPB, 0, v);
-  {
+  if (v.dense_mode) {
+    const dim3 grid(v.n_splits, v.n_win);
+    const size_t sm3 = sizeof(double) * (DT_EDGES * 18 + DT_LM * 9), sm4 = sizeof(double) * (DT_EDGES * 24 + DT_LM * 14);
+    if (S->umax <= 5) {
+      LLD_LAUNCH(c, (k_schur_dense<3, 5>), grid, 256, sm3, v);
+      { LLD_CUDA(c, cudaFuncSetAttribute(k_schur_dense<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
+                    LLD_LAUNCH(c, (k_schur_dense<4, 5>), grid, 256, sm4, v); }
+    } else {
+      LLD_LAUNCH(c, (k_schur_dense<3, 13>), grid, 256, sm3, v);
+      { LLD_CUDA(c, cudaFuncSetAttribute(k_schur_dense<4, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
+                    LLD_LAUNCH(c, (k_schur_dense<4, 13>), grid, 256, sm4, v); }
+    }
+    LLD_LAUNCH(c, k_reduce_dense, v.n_win, 256, 0, v);
+  } else {
     const int tpb = 32 * cdiv(6 * S->max_nnb, 32);
     const int nl = v.n_chunks - v.n_chunks_pt;
     if (tpb <= 256) {
@@ -514,10 +620,10 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
       if (v.n_chunks_pt) LLD_LAUNCH(c, (k_schur_rows<3, 1024>), v.n_chunks_pt, tpb, 0, v, 0);
       if (nl) LLD_LAUNCH(c, (k_schur_rows<4, 1024>), nl, tpb, 0, v, v.n_chunks_pt);
     }
-  }
-  if (v.n_free_total) {
-    const int tpb = std::min(256, 32 * cdiv(6 * S->max_nnb, 32));
-    LLD_LAUNCH(c, k_reduce_rows, v.n_free_total, tpb, 0, v, (S->global_mode && c->n_ranks > 1 && c->rank != 0) ? 0 : 1);
+    if (v.n_free_total) {
+      const int tpb2 = std::min(256, 32 * cdiv(6 * S->max_nnb, 32));
+      LLD_LAUNCH(c, k_reduce_rows, v.n_free_total, tpb2, 0, v, (S->global_mode && c->n_ranks > 1 && c->rank != 0) ? 0 : 1);
+    }
   }
   if (S->global_mode) { int r = ba_allreduce_rows(c); if (r) return r; }
   if (S->max_n <= SMEM_SOLVE_MAX_N) { int r = launch_solve<true>(c, v, S->max_n); if (r) return r; }

@@ -71,6 +71,27 @@ struct BaView {
   const long long* pl_tab_off;  // [n_free_total] offset of block a's first entry row
   const int* ll_tab;
   const long long* ll_tab_off;
+  // dense mode (every window has <= 32 free keyframes): landmarks in co-visibility-signature order, W stored per
+  // landmark with its free edges sorted by keyframe; k_schur_dense keeps a window's whole S in registers
+  int dense_mode;
+  int n_splits;            // CTAs per window in k_schur_dense
+  const int* pt_spos;      // [n_pt] position of the point in signature order (window-contiguous)
+  const int* ln_spos;      // [n_ln]
+  const uint32_t* pts_mask;  // [n_pt] by sorted position: bit h set when free keyframe h (window-local) observes it
+  const uint32_t* lns_mask;  // [n_ln]
+  const int* pts_w0;       // [n_pt+1] by sorted position: first W slot of the landmark (free edges, ascending keyframe)
+  const int* lns_w0;       // [n_ln+1]
+  const int* pe_wpos;      // [n_pe] W slot of the edge or -1
+  const int* lc_wpos;      // [n_lc]
+  const int* dt_begin;     // dense tiles: ranges of sorted positions (points first, then lines)
+  const int* dt_end;
+  const int* dsp_tile0;    // [(n_win*n_splits)+1] x 2 kinds: first tile of each (window, split)
+  double* pe_Wl;           // [n_pwslots][18]
+  double* lc_Wl;           // [n_lwslots][24]
+  double* pts_D;           // [n_pt][9]  by sorted position: inverse packed (6) + D^-1 b_l (3)
+  double* lns_D;           // [n_ln][14]
+  double* dpart;           // dense partial sums: per (kind, window, split): 36*NB + 6*nf doubles
+  const long long* dpart_off;  // [2*n_win*n_splits]
   // dynamic state
   double* pose_qt[2];
   double* pose_Rt[2];

@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_points(BaView v) {
   const int e0 = v.pt_obs_off[p], e1 = v.pt_obs_off[p + 1];
   for (int e = e0; e < e1; e++) {
     const int kf = v.pe_kf[e];
-    const int pos = v.pe_pos[e];
-    double* W = v.P_rec + 27 * (size_t)(pos < 0 ? 0 : pos);
+    const int pos = v.dense_mode ? v.pe_wpos[e] : v.pe_pos[e];
+    double* W = v.dense_mode ? v.pe_Wl + 18 * (size_t)(pos < 0 ? 0 : pos) : v.P_rec + 27 * (size_t)(pos < 0 ? 0 : pos);
     if (v.pe_level[e] != 0) {
       if (pos >= 0)
 #pragma unroll
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_lines(BaView v) {
   const int c0 = v.ln_obs_off[l], c1 = v.ln_obs_off[l + 1];
   for (int c = c0; c < c1; c++) {
     const int kf = v.lc_kf[c];
-    const int pos = v.lc_pos[c];
+    const int pos = v.dense_mode ? v.lc_wpos[c] : v.lc_pos[c];
     double W[24];
 #pragma unroll
     for (int k = 0; k < 24; k++) W[k] = 0.0;
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_lines(BaView v) {
       }
     }
     if (pos >= 0) {
-      double* Wo = v.L_rec + 38 * (size_t)pos;
+      double* Wo = v.dense_mode ? v.lc_Wl + 24 * (size_t)pos : v.L_rec + 38 * (size_t)pos;
 #pragma unroll
       for (int k = 0; k < 24; k++) Wo[k] = W[k];
     }
@@ -494,9 +494,10 @@ __global__ void __launch_bounds__(LM_TPB) k_schur_points(BaView v) {
   double rec[9] = {Di[0], Di[1], Di[2], Di[4], Di[5], Di[8], 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < 3; i++) rec[6 + i] = Di[3 * i] * Hi[6] + Di[3 * i + 1] * Hi[7] + Di[3 * i + 2] * Hi[8];
-  double* Do = v.pt_D + 9 * (size_t)p;
+  double* Do = v.dense_mode ? v.pts_D + 9 * (size_t)v.pt_spos[p] : v.pt_D + 9 * (size_t)p;
 #pragma unroll
   for (int k = 0; k < 9; k++) Do[k] = rec[k];
+  if (v.dense_mode) return;
   for (int e = v.pt_obs_off[p]; e < v.pt_obs_off[p + 1]; e++) {
     const int pos = v.pe_pos[e];
     if (pos < 0) continue;
@@ -530,9 +531,10 @@ __global__ void __launch_bounds__(LM_TPB) k_schur_lines(BaView v) {
 #pragma unroll
   for (int i = 0; i < 4; i++)
     rec[10 + i] = Di[4 * i] * Hi[10] + Di[4 * i + 1] * Hi[11] + Di[4 * i + 2] * Hi[12] + Di[4 * i + 3] * Hi[13];
-  double* Do = v.ln_D + 14 * (size_t)l;
+  double* Do = v.dense_mode ? v.lns_D + 14 * (size_t)v.ln_spos[l] : v.ln_D + 14 * (size_t)l;
 #pragma unroll
   for (int k = 0; k < 14; k++) Do[k] = rec[k];
+  if (v.dense_mode) return;
   for (int cc = v.ln_obs_off[l]; cc < v.ln_obs_off[l + 1]; cc++) {
     const int pos = v.lc_pos[cc];
     if (pos < 0) continue;
@@ -664,6 +666,169 @@ __global__ void k_reduce_rows(BaView v, int with_diag) {
       S[6 * r + c] = d - s[r];
     }
     if (j == 0) v.g_bs[6 * (size_t)g + c] = (with_diag ? v.g_bp[6 * (size_t)g + c] : 0.0) - sb;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense mode: window-stationary Schur complement.  One CTA owns (a share of) one window and keeps the whole upper
+// triangle of S in registers: unit u = (block (a,b), column c) -> 6 accumulators, UMAX units per thread.  Landmarks
+// stream through shared memory in co-visibility-signature order (W of a tile is one contiguous range); all landmarks
+// of a segment share the mask, so "is my block hit" and the W slots (popcount of the mask below a / b) are decided
+// once per segment; the inner loop reads only shared memory.  No atomics: partial sums per (window, split) are
+// reduced in fixed order by k_reduce_dense.
+// ------------------------------------------------------------------------------------------------
+constexpr int DT_LM = 64;     // landmarks per tile (cap)
+constexpr int DT_EDGES = 256; // W slots per tile (cap)
+template <int D, int UMAX>
+__global__ void __launch_bounds__(256) k_schur_dense(BaView v) {
+  constexpr int ND = D * (D + 1) / 2 + D;
+  const int w = blockIdx.y, split = blockIdx.x;
+  if (v.w_phase[w] == PH_DONE) return;
+  extern __shared__ double dsm[];
+  double* s_W = dsm;                         // [DT_EDGES][6D]
+  double* s_D = dsm + DT_EDGES * 6 * D;      // [DT_LM][ND]
+  __shared__ uint32_t s_mask[DT_LM];
+  __shared__ int s_w0[DT_LM + 1];
+  const int t = threadIdx.x;
+  const int nf = v.w_g0[w + 1] - v.w_g0[w];
+  const int NU = nf * (nf + 1) / 2 * 6;
+  // decode my units: block index -> (a, b), a <= b, row-major over the upper triangle
+  int ua[UMAX], ub[UMAX], uc[UMAX];
+#pragma unroll
+  for (int q = 0; q < UMAX; q++) {
+    const int u = t + q * 256;
+    ua[q] = -1; ub[q] = 0; uc[q] = 0;
+    if (u < NU) {
+      int blk = u / 6, a = 0;
+      uc[q] = u - 6 * blk;
+      while (blk >= nf - a) { blk -= nf - a; a++; }
+      ua[q] = a; ub[q] = a + blk;
+    }
+  }
+  const bool bthread = t < 6 * nf;   // b_schur part: thread (a = t/6, r = t%6)
+  const int ba = t / 6, br = t - 6 * (t / 6);
+  double acc[UMAX][6];
+#pragma unroll
+  for (int q = 0; q < UMAX; q++)
+#pragma unroll
+    for (int r = 0; r < 6; r++) acc[q][r] = 0.0;
+  double bacc = 0.0;
+  const int kind = D == 3 ? 0 : 1;
+  const int* tile0 = v.dsp_tile0 + (size_t)kind * ((size_t)v.n_win * v.n_splits + 1);
+  const int tb = tile0[w * v.n_splits + split], te = tile0[w * v.n_splits + split + 1];
+  const uint32_t* masks = D == 3 ? v.pts_mask : v.lns_mask;
+  const int* w0s = D == 3 ? v.pts_w0 : v.lns_w0;
+  const double* Wg = D == 3 ? v.pe_Wl : v.lc_Wl;
+  const double* Dg = D == 3 ? v.pts_D : v.lns_D;
+  for (int tile = tb; tile < te; tile++) {
+    const int l0 = v.dt_begin[tile], l1 = v.dt_end[tile];
+    const int nl = l1 - l0;
+    const int e0 = w0s[l0], ne = w0s[l1] - e0;
+    __syncthreads();
+    for (int i = t; i < nl; i += 256) s_mask[i] = masks[l0 + i];
+    for (int i = t; i <= nl; i += 256) s_w0[i] = w0s[l0 + i] - e0;
+    for (int i = t; i < ne * 6 * D; i += 256) s_W[i] = Wg[(size_t)e0 * 6 * D + i];
+    for (int i = t; i < nl * ND; i += 256) s_D[i] = Dg[(size_t)l0 * ND + i];
+    __syncthreads();
+    uint32_t pm = 0;          // mask of the running segment
+    uint32_t hit = 0;         // bit q: unit q is hit by this segment
+    int sa[UMAX], sb[UMAX];   // W slots of a and b inside the landmark
+    int bslot = -1;
+#pragma unroll
+    for (int q = 0; q < UMAX; q++) { sa[q] = 0; sb[q] = 0; }
+    for (int i = 0; i < nl; i++) {
+      const uint32_t m = s_mask[i];
+      if (m != pm) {
+        pm = m;
+        hit = 0;
+#pragma unroll
+        for (int q = 0; q < UMAX; q++) {
+          if (ua[q] >= 0 && ((m >> ua[q]) & 1u) && ((m >> ub[q]) & 1u)) {
+            hit |= 1u << q;
+            sa[q] = __popc(m & ((1u << ua[q]) - 1u));
+            sb[q] = __popc(m & ((1u << ub[q]) - 1u));
+          }
+        }
+        bslot = (bthread && ((m >> ba) & 1u)) ? __popc(m & ((1u << ba) - 1u)) : -1;
+      }
+      if (!hit && bslot < 0) continue;
+      const double* Dv = s_D + i * ND;
+      const double* Wl = s_W + (size_t)s_w0[i] * 6 * D;
+      if (bslot >= 0) {
+        const double* Wa = Wl + bslot * 6 * D + D * br;
+        double sbv = 0;
+#pragma unroll
+        for (int k = 0; k < D; k++) sbv += Wa[k] * Dv[D * (D + 1) / 2 + k];
+        bacc += sbv;
+      }
+#pragma unroll
+      for (int q = 0; q < UMAX; q++) {
+        if (!((hit >> q) & 1u)) continue;
+        const double* Wa = Wl + sa[q] * 6 * D;
+        const double* Wb = Wl + sb[q] * 6 * D + D * uc[q];
+        double z[D];
+        if (D == 3) {
+          z[0] = Dv[0] * Wb[0] + Dv[1] * Wb[1] + Dv[2] * Wb[2];
+          z[1] = Dv[1] * Wb[0] + Dv[3] * Wb[1] + Dv[4] * Wb[2];
+          z[2] = Dv[2] * Wb[0] + Dv[4] * Wb[1] + Dv[5] * Wb[2];
+        } else {
+#pragma unroll
+          for (int r = 0; r < D; r++) {
+            double zz = 0;
+#pragma unroll
+            for (int k = 0; k < D; k++) zz += Dv[r <= k ? u4(r, k) : u4(k, r)] * Wb[k];
+            z[r] = zz;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+          double a2 = 0;
+#pragma unroll
+          for (int k = 0; k < D; k++) a2 += Wa[D * r + k] * z[k];
+          acc[q][r] += a2;
+        }
+      }
+    }
+  }
+  double* out = v.dpart + v.dpart_off[((size_t)kind * v.n_win + w) * v.n_splits + split];
+#pragma unroll
+  for (int q = 0; q < UMAX; q++) {
+    const int u = t + q * 256;
+    if (u < NU)
+#pragma unroll
+      for (int r = 0; r < 6; r++) out[(size_t)u * 6 + r] = acc[q][r];
+  }
+  if (bthread) out[(size_t)NU * 6 + t] = bacc;
+}
+
+// S(a,b) = [a==b] (Hpp_a + lambda I) - sum over (kind, split) partials ; bschur_a = bp_a - sum partial_b
+__global__ void k_reduce_dense(BaView v) {
+  const int w = blockIdx.x;
+  if (v.w_phase[w] == PH_DONE) return;
+  const int g0 = v.w_g0[w], nf = v.w_g0[w + 1] - g0;
+  const int NU = nf * (nf + 1) / 2 * 6;
+  const double lam = v.w_lambda[w];
+  for (int x = threadIdx.x; x < NU * 6 + 6 * nf; x += blockDim.x) {
+    double s = 0;
+    for (int kind = 0; kind < 2; kind++)
+      for (int sp = 0; sp < v.n_splits; sp++) s += (v.dpart + v.dpart_off[((size_t)kind * v.n_win + w) * v.n_splits + sp])[x];
+    if (x < NU * 6) {
+      const int u = x / 6, r = x - 6 * u;
+      int blk = u / 6, a = 0;
+      const int c = u - 6 * blk;
+      while (blk >= nf - a) { blk -= nf - a; a++; }
+      const int g = g0 + a, j = blk;
+      double d = 0.0;
+      if (j == 0) {
+        const int rr = r < c ? r : c, cc = r < c ? c : r;
+        d = v.g_Hpp[21 * (size_t)g + (rr * 6 - (rr * (rr - 1)) / 2 + (cc - rr))];
+        if (r == c) d += lam;
+      }
+      v.S_blk[36 * (size_t)(v.nb_off[g] + j) + 6 * r + c] = d - s;
+    } else {
+      const int i = x - NU * 6;
+      v.g_bs[6 * (size_t)g0 + i] = v.g_bp[6 * (size_t)g0 + i] - s;
+    }
   }
 }
 
@@ -805,14 +970,14 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_points(BaView v) {
     v.lm_scale[p] = 0.0;
     return;
   }
-  const double* Dp = v.pt_D + 9 * (size_t)p;
+  const double* Dp = v.dense_mode ? v.pts_D + 9 * (size_t)v.pt_spos[p] : v.pt_D + 9 * (size_t)p;
   double s3[3] = {0, 0, 0};
   const int e0 = v.pt_obs_off[p], e1 = v.pt_obs_off[p + 1];
   for (int e = e0; e < e1; e++) {
     if (v.pe_level[e] != 0) continue;
-    const int pos = v.pe_pos[e];
+    const int pos = v.dense_mode ? v.pe_wpos[e] : v.pe_pos[e];
     if (pos < 0) continue;
-    const double* W = v.P_rec + 27 * (size_t)pos;
+    const double* W = v.dense_mode ? v.pe_Wl + 18 * (size_t)pos : v.P_rec + 27 * (size_t)pos;
     const double* xp = v.g_x + 6 * (size_t)v.kf_g[v.pe_kf[e]];
 #pragma unroll
     for (int r = 0; r < 6; r++) {
@@ -865,13 +1030,13 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_lines(BaView v) {
     v.lm_scale[li] = 0.0;
     return;
   }
-  const double* Dp = v.ln_D + 14 * (size_t)l;
+  const double* Dp = v.dense_mode ? v.lns_D + 14 * (size_t)v.ln_spos[l] : v.ln_D + 14 * (size_t)l;
   double s4[4] = {0, 0, 0, 0};
   const int c0 = v.ln_obs_off[l], c1 = v.ln_obs_off[l + 1];
   for (int c = c0; c < c1; c++) {
-    const int pos = v.lc_pos[c];
+    const int pos = v.dense_mode ? v.lc_wpos[c] : v.lc_pos[c];
     if (pos < 0) continue;
-    const double* W = v.L_rec + 38 * (size_t)pos;
+    const double* W = v.dense_mode ? v.lc_Wl + 24 * (size_t)pos : v.L_rec + 38 * (size_t)pos;
     const double* xp = v.g_x + 6 * (size_t)v.kf_g[v.lc_kf[c]];
 #pragma unroll
     for (int r = 0; r < 6; r++) {
