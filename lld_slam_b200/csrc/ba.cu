@@ -27,7 +27,6 @@ struct BaState {
   int max_n = 0;       // largest reduced system dimension over the windows
   int max_nnb = 0;
   size_t n_nb_total = 0;
-  int umax = 5;
   bool global_mode = false;
   const double* d_kf_Tcw_in = nullptr;
   const double* d_pt_in = nullptr;
@@ -280,10 +279,11 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   std::vector<int> pt_spos(std::max(n_pt, 1), 0), ln_spos(std::max(n_ln, 1), 0), pts_w0(n_pt + 1, 0), lns_w0(n_ln + 1, 0);
   std::vector<uint32_t> pts_mask(std::max(n_pt, 1), 0), lns_mask(std::max(n_ln, 1), 0);
   std::vector<int> pe_wpos(std::max(n_pe, 1), -1), lc_wpos(std::max(n_lc, 1), -1);
-  std::vector<int> dt_begin, dt_end, dsp_tile0;
-  std::vector<long long> dpart_off;
+  std::vector<int> it_piece, it_task0, pc_begin, pc_end, pc_n, gb_off(1, 0), gv_off(1, 0);
+  std::vector<long long> pc_out, gb_src(1, 0), gv_src(1, 0);
+  std::vector<std::pair<int, long long>> gb_tmp, gv_tmp;
   long long dpart_total = 0;
-  int n_splits = 1, umax = 5;
+  int n_items_pt = 0;
   size_t n_pw = 0, n_lw = 0;
   if (dense) {
     auto slots = [&](int n_lm, const int* off, const std::vector<int>& ekf, const std::vector<int>& order,
@@ -305,38 +305,59 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     slots(n_pt, p->pt_obs_off, pe_kf, pt_order, pt_key, pt_spos, pts_mask, pts_w0, pe_wpos);
     slots(n_ln, p->ln_obs_off, lc_kf, ln_order, ln_key, ln_spos, lns_mask, lns_w0, lc_wpos);
     n_pw = (size_t)pts_w0[n_pt]; n_lw = (size_t)lns_w0[n_ln];
-    n_splits = std::max(1, std::min(32, (3 * c->sm_count + nw - 1) / nw));
-    for (int w = 0; w < nw; w++) {
-      const int nf = w_g0[w + 1] - w_g0[w];
-      umax = std::max(umax, (nf * (nf + 1) / 2 * 6 + 255) / 256);
-    }
-    const int DT_LM_H = 64, DT_EDGES_H = 256;
+    const int PIECE_CAP = 128;
     for (int kind = 0; kind < 2; kind++) {
       const int* loff = kind == 0 ? p->pt_off : p->ln_off;
-      const std::vector<int>& w0 = kind == 0 ? pts_w0 : lns_w0;
+      const std::vector<uint32_t>& mask = kind == 0 ? pts_mask : lns_mask;
+      if (kind == 1) n_items_pt = (int)it_piece.size();
       for (int w = 0; w < nw; w++) {
-        const int t0 = (int)dt_begin.size();
+        const int g0 = w_g0[w];
         int b = loff[w];
         while (b < loff[w + 1]) {
-          int e = b;
-          while (e < loff[w + 1] && e - b < DT_LM_H && w0[e + 1] - w0[b] <= DT_EDGES_H) e++;
-          if (e == b) e = b + 1;  // a single landmark never exceeds the slot cap (<= 32 free keyframes)
-          dt_begin.push_back(b); dt_end.push_back(e);
+          int e = b + 1;
+          while (e < loff[w + 1] && mask[e] == mask[b] && e - b < PIECE_CAP) e++;
+          const uint32_t m = mask[b];
+          const int n = __builtin_popcount(m);
+          if (n > 0) {
+            const int pc = (int)pc_begin.size();
+            pc_begin.push_back(b); pc_end.push_back(e); pc_n.push_back(n); pc_out.push_back(dpart_total);
+            const int npair = n * (n + 1) / 2, ntask = 6 * npair + n;
+            int hl[32], k = 0;
+            for (int h = 0; h < 32; h++)
+              if ((m >> h) & 1u) hl[k++] = h;
+            int pr = 0;
+            for (int ia = 0; ia < n; ia++)
+              for (int ib = ia; ib < n; ib++, pr++)
+                gb_tmp.push_back({nb_off[g0 + hl[ia]] + (hl[ib] - hl[ia]), dpart_total + 36LL * pr});
+            for (int ia = 0; ia < n; ia++) gv_tmp.push_back({g0 + hl[ia], dpart_total + 6LL * (6 * npair + ia)});
+            for (int t0 = 0; t0 < ntask; t0 += 32) { it_piece.push_back(pc); it_task0.push_back(t0); }
+            dpart_total += 6LL * ntask;
+          }
           b = e;
         }
-        const int nt = (int)dt_begin.size() - t0;
-        for (int sp = 0; sp < n_splits; sp++) dsp_tile0.push_back(t0 + (int)((long long)nt * sp / n_splits));
       }
-      dsp_tile0.push_back((int)dt_begin.size());
     }
-    for (int kind = 0; kind < 2; kind++)
-      for (int w = 0; w < nw; w++) {
-        const int nf = w_g0[w + 1] - w_g0[w];
-        for (int sp = 0; sp < n_splits; sp++) { dpart_off.push_back(dpart_total); dpart_total += 36LL * (nf * (nf + 1) / 2) + 6 * nf; }
-      }
+    // CSR of the gather lists (stable: piece order)
+    gb_off.assign(nb_g.size() + 1, 0);
+    for (auto& x : gb_tmp) gb_off[x.first + 1]++;
+    for (size_t i = 0; i < nb_g.size(); i++) gb_off[i + 1] += gb_off[i];
+    gb_src.assign(std::max<size_t>(gb_tmp.size(), 1), 0);
+    {
+      std::vector<int> cur(gb_off.begin(), gb_off.end() - 1);
+      for (auto& x : gb_tmp) gb_src[cur[x.first]++] = x.second;
+    }
+    gv_off.assign(nG + 1, 0);
+    for (auto& x : gv_tmp) gv_off[x.first + 1]++;
+    for (int i = 0; i < nG; i++) gv_off[i + 1] += gv_off[i];
+    gv_src.assign(std::max<size_t>(gv_tmp.size(), 1), 0);
+    {
+      std::vector<int> cur(gv_off.begin(), gv_off.end() - 1);
+      for (auto& x : gv_tmp) gv_src[cur[x.first]++] = x.second;
+    }
   }
-  v.n_splits = n_splits;
-  S->umax = umax;
+  v.n_items = (int)it_piece.size();
+  v.n_items_pt = dense ? n_items_pt : 0;
+
   // chunks + segments (runs of entries whose table rows have the same -1 pattern)
   const long long n_list_total = (long long)n_plist + n_llist;
   int CH = CHUNK;
@@ -446,10 +467,18 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   UP(tmp_i, lns_w0.data(), n_ln + 1); v.lns_w0 = tmp_i;
   UP(tmp_i, pe_wpos.data(), n_pe); v.pe_wpos = tmp_i;
   UP(tmp_i, lc_wpos.data(), n_lc); v.lc_wpos = tmp_i;
-  UP(tmp_i, dt_begin.data(), dt_begin.size()); v.dt_begin = tmp_i;
-  UP(tmp_i, dt_end.data(), dt_end.size()); v.dt_end = tmp_i;
-  UP(tmp_i, dsp_tile0.data(), dsp_tile0.size()); v.dsp_tile0 = tmp_i;
-  UP(tmp_l, dpart_off.data(), dpart_off.size()); v.dpart_off = tmp_l;
+  UP(tmp_i, pt_order.data(), n_pt); v.pt_sorted = tmp_i;
+  UP(tmp_i, ln_order.data(), n_ln); v.ln_sorted = tmp_i;
+  UP(tmp_i, it_piece.data(), it_piece.size()); v.it_piece = tmp_i;
+  UP(tmp_i, it_task0.data(), it_task0.size()); v.it_task0 = tmp_i;
+  UP(tmp_i, pc_begin.data(), pc_begin.size()); v.pc_begin = tmp_i;
+  UP(tmp_i, pc_end.data(), pc_end.size()); v.pc_end = tmp_i;
+  UP(tmp_i, pc_n.data(), pc_n.size()); v.pc_n = tmp_i;
+  UP(tmp_l, pc_out.data(), pc_out.size()); v.pc_out = tmp_l;
+  UP(tmp_i, gb_off.data(), gb_off.size()); v.gb_off = tmp_i;
+  UP(tmp_l, gb_src.data(), gb_src.size()); v.gb_src = tmp_l;
+  UP(tmp_i, gv_off.data(), gv_off.size()); v.gv_off = tmp_i;
+  UP(tmp_l, gv_src.data(), gv_src.size()); v.gv_src = tmp_l;
   {
     uint32_t* tmp_m;
     UP(tmp_m, pts_mask.data(), n_pt); v.pts_mask = tmp_m;
@@ -474,7 +503,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   DEV(v.pt_H, double, 9 * (size_t)n_pt); DEV(v.ln_H, double, 14 * (size_t)n_ln);
   DEV(v.P_rec, double, dense ? 1 : 27 * (size_t)n_plist); DEV(v.L_rec, double, dense ? 1 : 38 * (size_t)n_llist);
   DEV(v.pe_Wl, double, 18 * n_pw); DEV(v.lc_Wl, double, 24 * n_lw);
-  DEV(v.pts_D, double, dense ? 9 * (size_t)n_pt : 1); DEV(v.lns_D, double, dense ? 14 * (size_t)n_ln : 1);
+  DEV(v.pts_D, double, dense ? 10 * (size_t)n_pt : 1); DEV(v.lns_D, double, dense ? 14 * (size_t)n_ln : 1);
   DEV(v.dpart, double, (size_t)dpart_total);
   DEV(v.ch_pose, double, 28 * (size_t)n_ch);
   DEV(v.g_Hpp, double, 21 * (size_t)nG); DEV(v.g_bp, double, 6 * (size_t)nG); DEV(v.g_nact, int, nG);
@@ -598,18 +627,11 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   if (v.n_pt) LLD_LAUNCH(c, k_schur_points, gp, LM_TPB, 0, v);
   if (v.n_ln) LLD_LAUNCH(c, k_schur_lines, gl, LM_TPB, 0, v);
   if (v.dense_mode) {
-    const dim3 grid(v.n_splits, v.n_win);
-    const size_t sm3 = sizeof(double) * (DT_EDGES * 18 + DT_LM * 9), sm4 = sizeof(double) * (DT_EDGES * 24 + DT_LM * 14);
-    if (S->umax <= 5) {
-      LLD_LAUNCH(c, (k_schur_dense<3, 5>), grid, 256, sm3, v);
-      { LLD_CUDA(c, cudaFuncSetAttribute(k_schur_dense<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
-                    LLD_LAUNCH(c, (k_schur_dense<4, 5>), grid, 256, sm4, v); }
-    } else {
-      LLD_LAUNCH(c, (k_schur_dense<3, 13>), grid, 256, sm3, v);
-      { LLD_CUDA(c, cudaFuncSetAttribute(k_schur_dense<4, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
-                    LLD_LAUNCH(c, (k_schur_dense<4, 13>), grid, 256, sm4, v); }
-    }
-    LLD_LAUNCH(c, k_reduce_dense, v.n_win, 256, 0, v);
+    const int nip = v.n_items_pt, nil = v.n_items - v.n_items_pt;
+    if (nip) LLD_LAUNCH(c, k_schur_piece<3>, cdiv(nip, 8), 256, 0, v, 0, nip);
+    if (nil) LLD_LAUNCH(c, k_schur_piece<4>, cdiv(nil, 8), 256, 0, v, nip, nil);
+    const int nblk = (int)S->n_nb_total;
+    LLD_LAUNCH(c, k_reduce_piece, cdiv(nblk * 6 + v.n_free_total * 6, 256), 256, 0, v, nblk);
   } else {
     const int tpb = 32 * cdiv(6 * S->max_nnb, 32);
     const int nl = v.n_chunks - v.n_chunks_pt;

@@ -74,7 +74,8 @@ struct BaView {
   // dense mode (every window has <= 32 free keyframes): landmarks in co-visibility-signature order, W stored per
   // landmark with its free edges sorted by keyframe; k_schur_dense keeps a window's whole S in registers
   int dense_mode;
-  int n_splits;            // CTAs per window in k_schur_dense
+  const int* pt_sorted;    // [n_pt] landmark at each sorted position
+  const int* ln_sorted;
   const int* pt_spos;      // [n_pt] position of the point in signature order (window-contiguous)
   const int* ln_spos;      // [n_ln]
   const uint32_t* pts_mask;  // [n_pt] by sorted position: bit h set when free keyframe h (window-local) observes it
@@ -83,15 +84,26 @@ struct BaView {
   const int* lns_w0;       // [n_ln+1]
   const int* pe_wpos;      // [n_pe] W slot of the edge or -1
   const int* lc_wpos;      // [n_lc]
-  const int* dt_begin;     // dense tiles: ranges of sorted positions (points first, then lines)
-  const int* dt_end;
-  const int* dsp_tile0;    // [(n_win*n_splits)+1] x 2 kinds: first tile of each (window, split)
+  // dense-mode work decomposition: a "piece" is a run of <= 128 landmarks (sorted positions) with the same mask;
+  // its tasks are (pair of its keyframes, column c) plus one b_schur task per keyframe; 32 tasks = one warp item
+  int n_items;             // warp work items (points first, then lines)
+  int n_items_pt;
+  const int* it_piece;     // [n_items] piece of the item
+  const int* it_task0;     // [n_items] first task of the item
+  const int* pc_begin;     // [n_pieces] first landmark (sorted position)
+  const int* pc_end;
+  const int* pc_n;         // [n_pieces] free keyframes per landmark (popcount of the mask)
+  const long long* pc_out; // [n_pieces] offset of the piece's task outputs in dpart (6 doubles per task)
+  // gather lists for the reduction: per unit (window, block (a,b)) the contributing (piece, pair) outputs
+  const int* gb_off;       // [n_blocks_total+1]   blocks in nb order (same indexing as S_blk)
+  const long long* gb_src; // dpart offsets of the pair's first task (6 columns x 6 doubles contiguous)
+  const int* gv_off;       // [n_free_total+1]     per free keyframe: b_schur task outputs
+  const long long* gv_src;
   double* pe_Wl;           // [n_pwslots][18]
   double* lc_Wl;           // [n_lwslots][24]
-  double* pts_D;           // [n_pt][9]  by sorted position: inverse packed (6) + D^-1 b_l (3)
+  double* pts_D;           // [n_pt][10] by sorted position: inverse packed (6) + D^-1 b_l (3) + pad
   double* lns_D;           // [n_ln][14]
-  double* dpart;           // dense partial sums: per (kind, window, split): 36*NB + 6*nf doubles
-  const long long* dpart_off;  // [2*n_win*n_splits]
+  double* dpart;           // per-task partial sums (6 doubles per task)
   // dynamic state
   double* pose_qt[2];
   double* pose_Rt[2];

@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(LM_TPB) k_schur_points(BaView v) {
   double rec[9] = {Di[0], Di[1], Di[2], Di[4], Di[5], Di[8], 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < 3; i++) rec[6 + i] = Di[3 * i] * Hi[6] + Di[3 * i + 1] * Hi[7] + Di[3 * i + 2] * Hi[8];
-  double* Do = v.dense_mode ? v.pts_D + 9 * (size_t)v.pt_spos[p] : v.pt_D + 9 * (size_t)p;
+  double* Do = v.dense_mode ? v.pts_D + 10 * (size_t)v.pt_spos[p] : v.pt_D + 9 * (size_t)p;
 #pragma unroll
   for (int k = 0; k < 9; k++) Do[k] = rec[k];
   if (v.dense_mode) return;
@@ -670,165 +670,139 @@ __global__ void k_reduce_rows(BaView v, int with_diag) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// dense mode: window-stationary Schur complement.  One CTA owns (a share of) one window and keeps the whole upper
-// triangle of S in registers: unit u = (block (a,b), column c) -> 6 accumulators, UMAX units per thread.  Landmarks
-// stream through shared memory in co-visibility-signature order (W of a tile is one contiguous range); all landmarks
-// of a segment share the mask, so "is my block hit" and the W slots (popcount of the mask below a / b) are decided
-// once per segment; the inner loop reads only shared memory.  No atomics: partial sums per (window, split) are
-// reduced in fixed order by k_reduce_dense.
+// dense mode Schur complement by co-visibility classes.
+// Landmarks are stored in signature order; a "piece" is a run of landmarks seen by exactly the same n free keyframes,
+// with their W blocks contiguous and sorted by keyframe, so every address in the inner loop is affine in the landmark
+// index (no gathers, no tests).  One warp = 32 tasks of one piece; task = (pair (ia, ib) of the piece's keyframes,
+// column c) accumulating  sum_l W_(l,ia) Dinv_l W_(l,ib)[c,:]^T  (6 values) in registers, or one b_schur task per
+// keyframe accumulating  sum_l W_(l,ia) (Dinv_l b_l).  Outputs go to a scratch slot per task; k_reduce_piece sums
+// them per S block in fixed order (block_solver.hpp:381-440 without atomics).
 // ------------------------------------------------------------------------------------------------
-constexpr int DT_LM = 64;     // landmarks per tile (cap)
-constexpr int DT_EDGES = 256; // W slots per tile (cap)
-template <int D, int UMAX>
-__global__ void __launch_bounds__(256) k_schur_dense(BaView v) {
-  constexpr int ND = D * (D + 1) / 2 + D;
-  const int w = blockIdx.y, split = blockIdx.x;
+template <int D>
+__global__ void __launch_bounds__(256) k_schur_piece(BaView v, int item_base, int n_items) {
+  constexpr int WS = 6 * D;                       // doubles per W block
+  constexpr int DS = D == 3 ? 10 : 14;            // doubles per landmark inverse record
+  constexpr int OFF_C = D * (D + 1) / 2;
+  const int item = item_base + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= item_base + n_items) return;
+  const int lane = threadIdx.x & 31;
+  const int pc = v.it_piece[item];
+  const int l0 = v.pc_begin[pc], l1 = v.pc_end[pc];
+  const int w = (D == 3 ? v.pt_win : v.ln_win)[(D == 3 ? v.pt_sorted : v.ln_sorted)[l0]];
   if (v.w_phase[w] == PH_DONE) return;
-  extern __shared__ double dsm[];
-  double* s_W = dsm;                         // [DT_EDGES][6D]
-  double* s_D = dsm + DT_EDGES * 6 * D;      // [DT_LM][ND]
-  __shared__ uint32_t s_mask[DT_LM];
-  __shared__ int s_w0[DT_LM + 1];
-  const int t = threadIdx.x;
-  const int nf = v.w_g0[w + 1] - v.w_g0[w];
-  const int NU = nf * (nf + 1) / 2 * 6;
-  // decode my units: block index -> (a, b), a <= b, row-major over the upper triangle
-  int ua[UMAX], ub[UMAX], uc[UMAX];
+  const int n = v.pc_n[pc];
+  const int npair = n * (n + 1) / 2;
+  const int ntask = 6 * npair + n;
+  const int task = v.it_task0[item] + lane;
+  if (task >= ntask) return;
+  const double* Wg = (D == 3 ? v.pe_Wl : v.lc_Wl) + (size_t)(D == 3 ? v.pts_w0 : v.lns_w0)[l0] * WS;
+  const double* Dg = (D == 3 ? v.pts_D : v.lns_D) + (size_t)l0 * DS;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  const int nl = l1 - l0;
+  const size_t lstride = (size_t)n * WS;
+  if (task < 6 * npair) {
+    int pr = task / 6, ia = 0;
+    const int c = task - 6 * pr;
+    while (pr >= n - ia) { pr -= n - ia; ia++; }
+    const int ib = ia + pr;
+    const double* Wa = Wg + ia * WS;
+    const double* Wb = Wg + ib * WS + D * c;
+#pragma unroll 2
+    for (int l = 0; l < nl; l++, Wa += lstride, Wb += lstride) {
+      const double* Dv = Dg + (size_t)l * DS;
+      double wb[D], z[D];
 #pragma unroll
-  for (int q = 0; q < UMAX; q++) {
-    const int u = t + q * 256;
-    ua[q] = -1; ub[q] = 0; uc[q] = 0;
-    if (u < NU) {
-      int blk = u / 6, a = 0;
-      uc[q] = u - 6 * blk;
-      while (blk >= nf - a) { blk -= nf - a; a++; }
-      ua[q] = a; ub[q] = a + blk;
+      for (int k = 0; k < D; k++) wb[k] = Wb[k];
+      if (D == 3) {
+        const double2 d01 = *reinterpret_cast<const double2*>(Dv), d23 = *reinterpret_cast<const double2*>(Dv + 2),
+                      d45 = *reinterpret_cast<const double2*>(Dv + 4);
+        z[0] = d01.x * wb[0] + d01.y * wb[1] + d23.x * wb[2];
+        z[1] = d01.y * wb[0] + d23.y * wb[1] + d45.x * wb[2];
+        z[2] = d23.x * wb[0] + d45.x * wb[1] + d45.y * wb[2];
+      } else {
+#pragma unroll
+        for (int r = 0; r < D; r++) {
+          double zz = 0;
+#pragma unroll
+          for (int k = 0; k < D; k++) zz += Dv[r <= k ? u4(r, k) : u4(k, r)] * wb[k];
+          z[r] = zz;
+        }
+      }
+      double wa[WS];
+#pragma unroll
+      for (int k = 0; k < WS; k += 2) {
+        const double2 t2 = *reinterpret_cast<const double2*>(Wa + k);
+        wa[k] = t2.x; wa[k + 1] = t2.y;
+      }
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        double a2 = 0;
+#pragma unroll
+        for (int k = 0; k < D; k++) a2 += wa[D * r + k] * z[k];
+        acc[r] += a2;
+      }
     }
-  }
-  const bool bthread = t < 6 * nf;   // b_schur part: thread (a = t/6, r = t%6)
-  const int ba = t / 6, br = t - 6 * (t / 6);
-  double acc[UMAX][6];
+  } else {
+    const int ia = task - 6 * npair;
+    const double* Wa = Wg + ia * WS;
+    for (int l = 0; l < nl; l++, Wa += lstride) {
+      const double* cv = Dg + (size_t)l * DS + OFF_C;
 #pragma unroll
-  for (int q = 0; q < UMAX; q++)
+      for (int r = 0; r < 6; r++) {
+        double a2 = 0;
 #pragma unroll
-    for (int r = 0; r < 6; r++) acc[q][r] = 0.0;
-  double bacc = 0.0;
-  const int kind = D == 3 ? 0 : 1;
-  const int* tile0 = v.dsp_tile0 + (size_t)kind * ((size_t)v.n_win * v.n_splits + 1);
-  const int tb = tile0[w * v.n_splits + split], te = tile0[w * v.n_splits + split + 1];
-  const uint32_t* masks = D == 3 ? v.pts_mask : v.lns_mask;
-  const int* w0s = D == 3 ? v.pts_w0 : v.lns_w0;
-  const double* Wg = D == 3 ? v.pe_Wl : v.lc_Wl;
-  const double* Dg = D == 3 ? v.pts_D : v.lns_D;
-  for (int tile = tb; tile < te; tile++) {
-    const int l0 = v.dt_begin[tile], l1 = v.dt_end[tile];
-    const int nl = l1 - l0;
-    const int e0 = w0s[l0], ne = w0s[l1] - e0;
-    __syncthreads();
-    for (int i = t; i < nl; i += 256) s_mask[i] = masks[l0 + i];
-    for (int i = t; i <= nl; i += 256) s_w0[i] = w0s[l0 + i] - e0;
-    for (int i = t; i < ne * 6 * D; i += 256) s_W[i] = Wg[(size_t)e0 * 6 * D + i];
-    for (int i = t; i < nl * ND; i += 256) s_D[i] = Dg[(size_t)l0 * ND + i];
-    __syncthreads();
-    uint32_t pm = 0;          // mask of the running segment
-    uint32_t hit = 0;         // bit q: unit q is hit by this segment
-    int sa[UMAX], sb[UMAX];   // W slots of a and b inside the landmark
-    int bslot = -1;
-#pragma unroll
-    for (int q = 0; q < UMAX; q++) { sa[q] = 0; sb[q] = 0; }
-    for (int i = 0; i < nl; i++) {
-      const uint32_t m = s_mask[i];
-      if (m != pm) {
-        pm = m;
-        hit = 0;
-#pragma unroll
-        for (int q = 0; q < UMAX; q++) {
-          if (ua[q] >= 0 && ((m >> ua[q]) & 1u) && ((m >> ub[q]) & 1u)) {
-            hit |= 1u << q;
-            sa[q] = __popc(m & ((1u << ua[q]) - 1u));
-            sb[q] = __popc(m & ((1u << ub[q]) - 1u));
-          }
-        }
-        bslot = (bthread && ((m >> ba) & 1u)) ? __popc(m & ((1u << ba) - 1u)) : -1;
-      }
-      if (!hit && bslot < 0) continue;
-      const double* Dv = s_D + i * ND;
-      const double* Wl = s_W + (size_t)s_w0[i] * 6 * D;
-      if (bslot >= 0) {
-        const double* Wa = Wl + bslot * 6 * D + D * br;
-        double sbv = 0;
-#pragma unroll
-        for (int k = 0; k < D; k++) sbv += Wa[k] * Dv[D * (D + 1) / 2 + k];
-        bacc += sbv;
-      }
-#pragma unroll
-      for (int q = 0; q < UMAX; q++) {
-        if (!((hit >> q) & 1u)) continue;
-        const double* Wa = Wl + sa[q] * 6 * D;
-        const double* Wb = Wl + sb[q] * 6 * D + D * uc[q];
-        double z[D];
-        if (D == 3) {
-          z[0] = Dv[0] * Wb[0] + Dv[1] * Wb[1] + Dv[2] * Wb[2];
-          z[1] = Dv[1] * Wb[0] + Dv[3] * Wb[1] + Dv[4] * Wb[2];
-          z[2] = Dv[2] * Wb[0] + Dv[4] * Wb[1] + Dv[5] * Wb[2];
-        } else {
-#pragma unroll
-          for (int r = 0; r < D; r++) {
-            double zz = 0;
-#pragma unroll
-            for (int k = 0; k < D; k++) zz += Dv[r <= k ? u4(r, k) : u4(k, r)] * Wb[k];
-            z[r] = zz;
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < 6; r++) {
-          double a2 = 0;
-#pragma unroll
-          for (int k = 0; k < D; k++) a2 += Wa[D * r + k] * z[k];
-          acc[q][r] += a2;
-        }
+        for (int k = 0; k < D; k++) a2 += Wa[D * r + k] * cv[k];
+        acc[r] += a2;
       }
     }
   }
-  double* out = v.dpart + v.dpart_off[((size_t)kind * v.n_win + w) * v.n_splits + split];
+  double* out = v.dpart + v.pc_out[pc] + (size_t)task * 6;
 #pragma unroll
-  for (int q = 0; q < UMAX; q++) {
-    const int u = t + q * 256;
-    if (u < NU)
-#pragma unroll
-      for (int r = 0; r < 6; r++) out[(size_t)u * 6 + r] = acc[q][r];
-  }
-  if (bthread) out[(size_t)NU * 6 + t] = bacc;
+  for (int r = 0; r < 6; r++) out[r] = acc[r];
 }
 
-// S(a,b) = [a==b] (Hpp_a + lambda I) - sum over (kind, split) partials ; bschur_a = bp_a - sum partial_b
-__global__ void k_reduce_dense(BaView v) {
-  const int w = blockIdx.x;
-  if (v.w_phase[w] == PH_DONE) return;
-  const int g0 = v.w_g0[w], nf = v.w_g0[w + 1] - g0;
-  const int NU = nf * (nf + 1) / 2 * 6;
-  const double lam = v.w_lambda[w];
-  for (int x = threadIdx.x; x < NU * 6 + 6 * nf; x += blockDim.x) {
-    double s = 0;
-    for (int kind = 0; kind < 2; kind++)
-      for (int sp = 0; sp < v.n_splits; sp++) s += (v.dpart + v.dpart_off[((size_t)kind * v.n_win + w) * v.n_splits + sp])[x];
-    if (x < NU * 6) {
-      const int u = x / 6, r = x - 6 * u;
-      int blk = u / 6, a = 0;
-      const int c = u - 6 * blk;
-      while (blk >= nf - a) { blk -= nf - a; a++; }
-      const int g = g0 + a, j = blk;
+// S(a,b) = [a==b] (Hpp_a + lambda I) - sum over contributing (piece, pair) ; bschur_a = bp_a - sum b tasks
+// one thread per (block, column c) and per (keyframe, row r)
+__global__ void k_reduce_piece(BaView v, int n_blocks) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < n_blocks * 6) {
+    const int blk = x / 6, c = x - 6 * blk;
+    // owning free block row g: largest g with nb_off[g] <= blk
+    int lo = 0, hi = v.n_free_total;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (v.nb_off[mid] <= blk) lo = mid;
+      else hi = mid;
+    }
+    const int g = lo, j = blk - v.nb_off[g];
+    const int w = v.kf_win[v.g_kf[g]];
+    if (v.w_phase[w] == PH_DONE) return;
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    for (int q = v.gb_off[blk]; q < v.gb_off[blk + 1]; q++) {
+      const double* src = v.dpart + v.gb_src[q] + 6 * c;
+#pragma unroll
+      for (int r = 0; r < 6; r++) s[r] += src[r];
+    }
+    const double lam = v.w_lambda[w];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
       double d = 0.0;
       if (j == 0) {
         const int rr = r < c ? r : c, cc = r < c ? c : r;
         d = v.g_Hpp[21 * (size_t)g + (rr * 6 - (rr * (rr - 1)) / 2 + (cc - rr))];
         if (r == c) d += lam;
       }
-      v.S_blk[36 * (size_t)(v.nb_off[g] + j) + 6 * r + c] = d - s;
-    } else {
-      const int i = x - NU * 6;
-      v.g_bs[6 * (size_t)g0 + i] = v.g_bp[6 * (size_t)g0 + i] - s;
+      v.S_blk[36 * (size_t)blk + 6 * r + c] = d - s[r];
     }
+  } else {
+    const int y = x - n_blocks * 6;
+    if (y >= v.n_free_total * 6) return;
+    const int g = y / 6, r = y - 6 * g;
+    const int w = v.kf_win[v.g_kf[g]];
+    if (v.w_phase[w] == PH_DONE) return;
+    double s = 0;
+    for (int q = v.gv_off[g]; q < v.gv_off[g + 1]; q++) s += v.dpart[v.gv_src[q] + r];
+    v.g_bs[6 * (size_t)g + r] = v.g_bp[6 * (size_t)g + r] - s;
   }
 }
 
@@ -970,7 +944,7 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_points(BaView v) {
     v.lm_scale[p] = 0.0;
     return;
   }
-  const double* Dp = v.dense_mode ? v.pts_D + 9 * (size_t)v.pt_spos[p] : v.pt_D + 9 * (size_t)p;
+  const double* Dp = v.dense_mode ? v.pts_D + 10 * (size_t)v.pt_spos[p] : v.pt_D + 9 * (size_t)p;
   double s3[3] = {0, 0, 0};
   const int e0 = v.pt_obs_off[p], e1 = v.pt_obs_off[p + 1];
   for (int e = e0; e < e1; e++) {
