@@ -452,12 +452,18 @@ def run_extra(lib, d, ctx, hbm_peak):
         ms = float(d.lld_ctx_event_elapsed_ms(ctx.handle)) / K
         ctx.check(d.lld_ba_download(ctx.handle, C.byref(prob), C.byref(res), 1), "download")
         its = int(out["n_iter_done"].sum())
+        d.lld_ctx_profile(ctx.handle, 1)
+        ctx.check(d.lld_ba_run_local(ctx.handle, ITS1, ITS2, None), "run")
+        prof1 = profile_report(d, ctx)
+        d.lld_ctx_profile(ctx.handle, 0)
         t0 = time.perf_counter(); o = api.ba_local(p1, ITS1, ITS2, impl="oracle"); tc = time.perf_counter() - t0
         ex["single_window_local_ba"] = {"metric": "lm_iters_per_sec", "value": its / (ms * 1e-3), "unit": "LM iterations/s",
                                         "config": "1 window 10 KF / 5000 points / 1000 lines, schedule 5+15 (latency bound)",
                                         "ms_per_call": ms, "iters": its,
                                         "cpu_baseline": {"value": int(o["n_iter_done"].sum()) / tc, "unit": "LM iterations/s", "cores": 1,
                                                          "kind": "port", "sample": "the same window"}}
+        ex["single_window_local_ba"]["kernels_us_per_launch"] = {k: round(1e3 * v["ms"] / max(v["n"], 1), 2) for k, v in
+                                                                 sorted(prof1.items(), key=lambda kv: -kv[1]["ms"])}
         ex["single_window_local_ba"]["speedup_vs_cpu_1core"] = ex["single_window_local_ba"]["value"] / ex["single_window_local_ba"]["cpu_baseline"]["value"]
     except Exception as e:  # noqa: BLE001
         ex["single_window_local_ba"] = {"error": str(e)}

@@ -18,7 +18,7 @@
 using namespace lld;
 
 static const int CHUNK = 256;          // edge-list entries per chunk (k_lin_poses / k_schur_rows CTA)
-static const int SMEM_SOLVE_MAX_N = 162;  // dense LDL^T in shared memory up to this dimension (27 free KFs)
+static const int SMEM_SOLVE_MAX_N = 156;  // dense LDL^T in shared memory up to this dimension (26 free KFs)
 
 struct BaState {
   BaView v{};
@@ -305,7 +305,8 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     slots(n_pt, p->pt_obs_off, pe_kf, pt_order, pt_key, pt_spos, pts_mask, pts_w0, pe_wpos);
     slots(n_ln, p->ln_obs_off, lc_kf, ln_order, ln_key, ln_spos, lns_mask, lns_w0, lc_wpos);
     n_pw = (size_t)pts_w0[n_pt]; n_lw = (size_t)lns_w0[n_ln];
-    const int PIECE_CAP = 128;
+    int PIECE_CAP = 128;  // shorter pieces when the batch is small, so that every SM gets warps
+    while (PIECE_CAP > 8 && (long long)(n_pt + n_ln) * 5 / (2 * PIECE_CAP) < 16LL * c->sm_count) PIECE_CAP >>= 1;
     for (int kind = 0; kind < 2; kind++) {
       const int* loff = kind == 0 ? p->pt_off : p->ln_off;
       const std::vector<uint32_t>& mask = kind == 0 ? pts_mask : lns_mask;
@@ -361,7 +362,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   // chunks + segments (runs of entries whose table rows have the same -1 pattern)
   const long long n_list_total = (long long)n_plist + n_llist;
   int CH = CHUNK;
-  while (CH > 32 && n_list_total / CH < 3 * (long long)c->sm_count) CH >>= 1;
+  while (CH > 32 && n_list_total / CH < 2 * (long long)c->sm_count) CH >>= 1;
   std::vector<int> ch_g, ch_begin, ch_end, ch_seg0, seg_begin, seg_end, g_chp0(nG + 1, 0), g_chl0(nG + 1, 0);
   auto build_chunks = [&](const std::vector<int>& l_off, const std::vector<long long>& t_off, const std::vector<int>& tab,
                           std::vector<int>& g_c0) {
@@ -408,7 +409,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   for (int w = 0; w < nw; w++) {
     const long long n = 6LL * (w_g0[w + 1] - w_g0[w]);
     w_scr[w] = scr_total;
-    if (S->max_n > SMEM_SOLVE_MAX_N) scr_total += n * n + 2 * n;
+    if (S->max_n > SMEM_SOLVE_MAX_N) scr_total += n * n + 8 * n + 8;
   }
 
   // ---- upload (timed as h2d) ----
@@ -606,7 +607,7 @@ static int ba_allreduce_rows(LldCtx* c) {
 
 template <bool SMEM>
 static int launch_solve(LldCtx* c, BaView& v, int max_n) {
-  size_t smem = SMEM ? sizeof(double) * ((size_t)max_n * max_n + 2 * (size_t)max_n) : 0;
+  size_t smem = SMEM ? sizeof(double) * ((size_t)max_n * max_n + 8 * (size_t)max_n + 8) : 0;
   if (SMEM) LLD_CUDA(c, cudaFuncSetAttribute(k_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LLD_LAUNCH(c, k_solve<SMEM>, v.n_win, 512, smem, v);
   return LLD_OK;
@@ -620,10 +621,15 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   if (v.n_pt) LLD_LAUNCH(c, k_lin_points, gp, LM_TPB, 0, v);
   if (v.n_ln) LLD_LAUNCH(c, k_lin_lines, gl, LM_TPB, 0, v);
   if (v.n_chunks) LLD_LAUNCH(c, k_lin_poses, v.n_chunks, LM_TPB, 0, v);
-  if (v.n_free_total) LLD_LAUNCH(c, k_reduce_pose, cdiv(v.n_free_total * 28, 128), 128, 0, v);
-  LLD_LAUNCH(c, k_reduce_lin, v.n_win, 256, 0, v);
-  if (S->global_mode) { int r = ba_allreduce_lin(c); if (r) return r; }
-  LLD_LAUNCH(c, k_begin, cdiv(v.n_win, 64), 64, 0, v);
+  const bool multi = S->global_mode && c->n_ranks > 1;
+  if (!multi) {
+    LLD_LAUNCH(c, k_begin_fused, v.n_win, 256, 0, v);
+  } else {
+    if (v.n_free_total) LLD_LAUNCH(c, k_reduce_pose, cdiv(v.n_free_total * 28, 128), 128, 0, v);
+    LLD_LAUNCH(c, k_reduce_lin, v.n_win, 256, 0, v);
+    { int r = ba_allreduce_lin(c); if (r) return r; }
+    LLD_LAUNCH(c, k_begin, cdiv(v.n_win, 64), 64, 0, v);
+  }
   if (v.n_pt) LLD_LAUNCH(c, k_schur_points, gp, LM_TPB, 0, v);
   if (v.n_ln) LLD_LAUNCH(c, k_schur_lines, gl, LM_TPB, 0, v);
   if (v.dense_mode) {
@@ -652,9 +658,13 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   else { int r = launch_solve<false>(c, v, S->max_n); if (r) return r; }
   if (v.n_pt) LLD_LAUNCH(c, k_backsub_points, gp, LM_TPB, 0, v);
   if (v.n_ln) LLD_LAUNCH(c, k_backsub_lines, gl, LM_TPB, 0, v);
-  LLD_LAUNCH(c, k_reduce_trial, v.n_win, 256, 0, v);
-  if (S->global_mode) { int r = ba_allreduce_trial(c); if (r) return r; }
-  LLD_LAUNCH(c, k_decide, cdiv(v.n_win, 64), 64, 0, v, round, stop_now);
+  if (!multi) {
+    LLD_LAUNCH(c, k_decide_fused, v.n_win, 256, 0, v, round, stop_now);
+  } else {
+    LLD_LAUNCH(c, k_reduce_trial, v.n_win, 256, 0, v);
+    { int r = ba_allreduce_trial(c); if (r) return r; }
+    LLD_LAUNCH(c, k_decide, cdiv(v.n_win, 64), 64, 0, v, round, stop_now);
+  }
   LLD_CUDA(c, cudaGetLastError());
   return LLD_OK;
 }

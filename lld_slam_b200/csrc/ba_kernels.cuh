@@ -440,10 +440,7 @@ __global__ void __launch_bounds__(256) k_reduce_lin(BaView v) {
 }
 
 // iteration start: currentChi, iniChi, lambda init at iteration 0 (optimization_algorithm_levenberg.cpp:75-97,166-180)
-__global__ void k_begin(BaView v) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= v.n_win) return;
-  if (v.w_phase[w] != PH_LIN) return;
+__device__ __forceinline__ void begin_window(const BaView& v, int w) {
   const double chi = v.w_red_sum[4 * w + 0];
   const int nact = (int)(v.w_red_sum[4 * w + 2] + 0.5);
   if (nact == 0 && v.w_iter[w] == 0) {  // empty index mapping: optimize() returns without iterating
@@ -472,6 +469,53 @@ __global__ void k_begin(BaView v) {
     if (n < v.log_stride) v.chi2_log[(size_t)w * v.log_stride + n] = chi;
     v.w_nlog[w] = n + 1;
   }
+}
+
+__global__ void k_begin(BaView v) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= v.n_win) return;
+  if (v.w_phase[w] != PH_LIN) return;
+  begin_window(v, w);
+}
+
+// single-rank fast path: chunk partial sums of the window's keyframes, landmark scalars and the iteration-start
+// bookkeeping in one CTA per window (saves two launches and their dependent-load latency per LM step)
+__global__ void __launch_bounds__(256) k_begin_fused(BaView v) {
+  const int w = blockIdx.x;
+  if (v.w_phase[w] != PH_LIN) return;
+  __shared__ double sm[32];
+  const int g0 = v.w_g0[w], nf = v.w_g0[w + 1] - g0;
+  for (int x = threadIdx.x; x < nf * 28; x += blockDim.x) {
+    const int g = g0 + x / 28, k = x % 28;
+    double s2 = 0;
+    for (int ch = v.g_chp0[g]; ch < v.g_chp0[g + 1]; ch++) s2 += v.ch_pose[28 * (size_t)ch + k];
+    for (int ch = v.g_chl0[g]; ch < v.g_chl0[g + 1]; ch++) s2 += v.ch_pose[28 * (size_t)ch + k];
+    if (k < 21) v.g_Hpp[21 * (size_t)g + k] = s2;
+    else if (k < 27) v.g_bp[6 * (size_t)g + (k - 21)] = s2;
+    else v.g_nact[g] = (int)(s2 + 0.5);
+  }
+  double chi = 0, mx = 0, na = 0;
+  for (int p = v.pt_off[w] + threadIdx.x; p < v.pt_off[w + 1]; p += blockDim.x) {
+    chi += v.lm_chi2lin[p];
+    mx = fmax(mx, v.lm_maxdiag[p]);
+    na += v.lm_active[p] ? 1.0 : 0.0;
+  }
+  for (int l = v.ln_off[w] + threadIdx.x; l < v.ln_off[w + 1]; l += blockDim.x) {
+    chi += v.lm_chi2lin[v.n_pt + l];
+    mx = fmax(mx, v.lm_maxdiag[v.n_pt + l]);
+    na += v.lm_active[v.n_pt + l] ? 1.0 : 0.0;
+  }
+  chi = block_sum(chi, sm);
+  na = block_sum(na, sm);
+  mx = block_max(mx, sm);
+  if (threadIdx.x == 0) {
+    v.w_red_sum[4 * w + 0] = chi;
+    v.w_red_sum[4 * w + 1] = 0.0;
+    v.w_red_sum[4 * w + 2] = na;
+    v.w_red_max[w] = mx;
+  }
+  __syncthreads();   // g_Hpp / g_nact written above are read by begin_window (same CTA, global memory)
+  if (threadIdx.x == 0) begin_window(v, w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -811,31 +855,76 @@ __global__ void k_reduce_piece(BaView v, int n_blocks) {
 // stands in for LinearSolverEigen / LinearSolverDense (Thirdparty/g2o/g2o/solvers/*.h); failure = zero or
 // non-finite pivot.
 // ------------------------------------------------------------------------------------------------
+// Blocked (6-column supernode) LDL^T of the reduced camera system by one CTA: per block column
+//   (1) thread 0 factors the 6x6 diagonal block and forward-solves the rhs block,
+//   (2) one thread per row below solves its 1x6 panel row  T = A_ik L_kk^-T  and  L = T D^-1,
+//   (3) one warp per row applies the rank-6 update  A_ij -= sum_c L_ic T_jc  and  b_i -= sum_c L_ic z_c.
+// n is a multiple of 6.  tmp: >= 7n doubles (T transposed [6][n] + z[6]).
 __device__ bool ldlt_solve_cta(double* A, int n, int ld, double* b /*in: rhs, out: x*/, double* tmp, int* flag) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  double* Tt = tmp;          // [6][n]
+  double* zb = tmp + 6 * n;  // [6]
   if (tid == 0) *flag = 1;
   __syncthreads();
-  for (int j = 0; j < n; j++) {
-    const double d = A[(size_t)j * ld + j];
-    if (!(d != 0.0) || !isfinite(d)) {
-      if (tid == 0) *flag = 0;
-      __syncthreads();
-      return false;
-    }
-    const double id = 1.0 / d;
-    for (int i = j + 1 + tid; i < n; i += nt) tmp[i] = A[(size_t)i * ld + j];
-    __syncthreads();
-    const double bj = b[j];
-    // one warp per row: A[i][k] -= L[i][j] * tmp[k] for j < k <= i ; forward substitution fused (b[i] -= L[i][j] b[j])
-    for (int i = j + 1 + wid; i < n; i += nw) {
-      const double lij = tmp[i] * id;
-      double* row = A + (size_t)i * ld;
-      for (int k = j + 1 + lane; k <= i; k += 32) row[k] -= lij * tmp[k];
-      if (lane == 0) {
-        row[j] = lij;
-        b[i] -= lij * bj;
+  for (int k0 = 0; k0 < n; k0 += 6) {
+    if (tid == 0) {
+      // unblocked LDL^T of the 6x6 diagonal block (lower part), in place: strict lower -> L, diagonal -> D
+      bool ok = true;
+      for (int j = 0; j < 6 && ok; j++) {
+        double d = A[(size_t)(k0 + j) * ld + k0 + j];
+        for (int q = 0; q < j; q++) {
+          const double l = A[(size_t)(k0 + j) * ld + k0 + q];
+          d -= l * l * A[(size_t)(k0 + q) * ld + k0 + q];
+        }
+        if (!(d != 0.0) || !isfinite(d)) { ok = false; break; }
+        A[(size_t)(k0 + j) * ld + k0 + j] = d;
+        for (int i = j + 1; i < 6; i++) {
+          double s2 = A[(size_t)(k0 + i) * ld + k0 + j];
+          for (int q = 0; q < j; q++)
+            s2 -= A[(size_t)(k0 + i) * ld + k0 + q] * A[(size_t)(k0 + j) * ld + k0 + q] * A[(size_t)(k0 + q) * ld + k0 + q];
+          A[(size_t)(k0 + i) * ld + k0 + j] = s2 / d;
+        }
       }
+      if (!ok) *flag = 0;
+      else {
+        // z = L_kk^-1 b_k
+        for (int i = 0; i < 6; i++) {
+          double s2 = b[k0 + i];
+          for (int q = 0; q < i; q++) s2 -= A[(size_t)(k0 + i) * ld + k0 + q] * zb[q];
+          zb[i] = s2;
+          b[k0 + i] = s2;
+        }
+      }
+    }
+    __syncthreads();
+    if (!*flag) return false;
+    // panel rows: T_i = A_i,k L_kk^-T  (forward substitution along the row), L_i = T_i / D
+    for (int i = k0 + 6 + tid; i < n; i += nt) {
+      double* row = A + (size_t)i * ld + k0;
+      double t6[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        double s2 = row[c];
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+          if (q < c) s2 -= t6[q] * A[(size_t)(k0 + c) * ld + k0 + q];
+        t6[c] = s2;
+      }
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        Tt[(size_t)c * n + i] = t6[c];
+        row[c] = t6[c] / A[(size_t)(k0 + c) * ld + k0 + c];
+      }
+    }
+    __syncthreads();
+    // rank-6 trailing update, one warp per row
+    for (int i = k0 + 6 + wid; i < n; i += nw) {
+      double* row = A + (size_t)i * ld;
+      const double l0 = row[k0], l1 = row[k0 + 1], l2 = row[k0 + 2], l3 = row[k0 + 3], l4 = row[k0 + 4], l5 = row[k0 + 5];
+      for (int j = k0 + 6 + lane; j <= i; j += 32)
+        row[j] -= l0 * Tt[j] + l1 * Tt[n + j] + l2 * Tt[2 * n + j] + l3 * Tt[3 * n + j] + l4 * Tt[4 * n + j] + l5 * Tt[5 * n + j];
+      if (lane == 0) b[i] -= l0 * zb[0] + l1 * zb[1] + l2 * zb[2] + l3 * zb[3] + l4 * zb[4] + l5 * zb[5];
     }
     __syncthreads();
   }
@@ -867,7 +956,7 @@ __global__ void __launch_bounds__(512) k_solve(BaView v) {
   __shared__ double red[32];
   double* A = SMEM ? smem : (v.solve_scratch + v.w_scratch_off[w]);
   double* rhs = SMEM ? (smem + (size_t)n * n) : (A + (size_t)n * n);
-  double* tmp = rhs + n;
+  double* tmp = rhs + n;  // 6n + 6 doubles
   const int sel = v.w_sel[w];
   bool ok = true;
   if (n > 0) {
@@ -1093,10 +1182,7 @@ __global__ void __launch_bounds__(256) k_reduce_trial(BaView v) {
 
 // accept / reject and the outer-iteration bookkeeping (optimization_algorithm_levenberg.cpp:99-164,
 // sparse_optimizer.cpp:376-418)
-__global__ void k_decide(BaView v, int round, int stop_now) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= v.n_win) return;
-  if (v.w_phase[w] == PH_DONE) return;
+__device__ __forceinline__ void decide_window(const BaView& v, int w, int round, int stop_now) {
   double tempChi = v.w_red_sum[4 * w + 0];
   if (!v.w_ok[w]) tempChi = DBL_MAX;
   const double cur = v.w_curchi[w];
@@ -1152,6 +1238,36 @@ __global__ void k_decide(BaView v, int round, int stop_now) {
     atomicSub(v.n_active_win, 1);
   } else {
     v.w_phase[w] = PH_LIN;
+  }
+}
+
+__global__ void k_decide(BaView v, int round, int stop_now) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= v.n_win) return;
+  if (v.w_phase[w] == PH_DONE) return;
+  decide_window(v, w, round, stop_now);
+}
+
+// single-rank fast path: trial reduction + decision in one CTA per window
+__global__ void __launch_bounds__(256) k_decide_fused(BaView v, int round, int stop_now) {
+  const int w = blockIdx.x;
+  if (v.w_phase[w] == PH_DONE) return;
+  __shared__ double sm[32];
+  double chi = 0, sc = 0;
+  for (int p = v.pt_off[w] + threadIdx.x; p < v.pt_off[w + 1]; p += blockDim.x) {
+    chi += v.lm_chi2[p];
+    sc += v.lm_scale[p];
+  }
+  for (int l = v.ln_off[w] + threadIdx.x; l < v.ln_off[w + 1]; l += blockDim.x) {
+    chi += v.lm_chi2[v.n_pt + l];
+    sc += v.lm_scale[v.n_pt + l];
+  }
+  chi = block_sum(chi, sm);
+  sc = block_sum(sc, sm);
+  if (threadIdx.x == 0) {
+    v.w_red_sum[4 * w + 0] = chi;
+    v.w_red_sum[4 * w + 1] = sc;
+    decide_window(v, w, round, stop_now);
   }
 }
 
