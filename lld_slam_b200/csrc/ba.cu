@@ -5,6 +5,10 @@
 // the kernel sequence of ba_kernels.cuh; LM control runs on the device, the host only enqueues steps and polls
 // one counter.  No CPU fallback: every path below ends in kernel launches on the context's stream.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
+#include <cstdlib>
 #include <numeric>
 #include <vector>
 
@@ -74,6 +78,27 @@ int up(LldCtx* c, T** dst, const T* src, size_t n, size_t* bytes) {
     (dst) = _p;                                                             \
   } while (0)
 
+// host-side parallel loop over independent windows (the indexing of a 64-window batch is ~60 ms on one core)
+template <class F>
+void par_for(int n, F f) {
+  unsigned nt = std::min<unsigned>(std::min<unsigned>(std::thread::hardware_concurrency(), 16u), (unsigned)std::max(n, 1));
+  if (nt <= 1 || n < 4) {
+    for (int i = 0; i < n; i++) f(i);
+    return;
+  }
+  std::atomic<int> next{0};
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++)
+    th.emplace_back([&] {
+      for (;;) {
+        const int i = next.fetch_add(1);
+        if (i >= n) break;
+        f(i);
+      }
+    });
+  for (auto& t : th) t.join();
+}
+
 }  // namespace
 
 // Flatten + index the problem on the host, upload, initialise device state.
@@ -92,6 +117,14 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   S->n_win = nw;
 
   // ---- host indexing ----
+  const bool timing = getenv("LLD_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto stage = [&](const char* name) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[lld_ba_upload] %-28s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   std::vector<int> kf_win(n_kf), pt_win(n_pt), ln_win(n_ln), kf_g(n_kf, -1), w_g0(nw + 1, 0);
   std::vector<int> g_kf;
   for (int w = 0; w < nw; w++) {
@@ -112,39 +145,48 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   v.n_free_total = nG;
 
   std::vector<int> pe_kf(n_pe), pe_pt(n_pe), lc_kf(n_lc), lc_ln(n_lc);
-  for (int i = 0; i < n_pt; i++) {
-    const int w = pt_win[i], k0 = p->kf_off[w], nk = p->kf_off[w + 1] - k0;
-    LLD_ARG(c, p->pt_obs_off[i + 1] - p->pt_obs_off[i] <= 254);
-    for (int e = p->pt_obs_off[i]; e < p->pt_obs_off[i + 1]; e++) {
-      LLD_ARG(c, p->pt_obs_kf[e] >= 0 && p->pt_obs_kf[e] < nk);
-      pe_kf[e] = k0 + p->pt_obs_kf[e];
-      pe_pt[e] = i;
+  std::atomic<int> bad_arg{0};
+  par_for(nw, [&](int w) {
+    const int k0 = p->kf_off[w], nk = p->kf_off[w + 1] - k0;
+    for (int i = p->pt_off[w]; i < p->pt_off[w + 1]; i++) {
+      if (p->pt_obs_off[i + 1] - p->pt_obs_off[i] > 254) bad_arg = 1;
+      for (int e = p->pt_obs_off[i]; e < p->pt_obs_off[i + 1]; e++) {
+        if (p->pt_obs_kf[e] < 0 || p->pt_obs_kf[e] >= nk) { bad_arg = 1; continue; }
+        pe_kf[e] = k0 + p->pt_obs_kf[e];
+        pe_pt[e] = i;
+      }
     }
-  }
-  for (int i = 0; i < n_ln; i++) {
-    const int w = ln_win[i], k0 = p->kf_off[w], nk = p->kf_off[w + 1] - k0;
-    LLD_ARG(c, p->ln_obs_off[i + 1] - p->ln_obs_off[i] <= 254);
-    for (int e = p->ln_obs_off[i]; e < p->ln_obs_off[i + 1]; e++) {
-      LLD_ARG(c, p->ln_obs_kf[e] >= 0 && p->ln_obs_kf[e] < nk);
-      lc_kf[e] = k0 + p->ln_obs_kf[e];
-      lc_ln[e] = i;
+    for (int i = p->ln_off[w]; i < p->ln_off[w + 1]; i++) {
+      if (p->ln_obs_off[i + 1] - p->ln_obs_off[i] > 254) bad_arg = 1;
+      for (int e = p->ln_obs_off[i]; e < p->ln_obs_off[i + 1]; e++) {
+        if (p->ln_obs_kf[e] < 0 || p->ln_obs_kf[e] >= nk) { bad_arg = 1; continue; }
+        lc_kf[e] = k0 + p->ln_obs_kf[e];
+        lc_ln[e] = i;
+      }
     }
-  }
+  });
+  LLD_ARG(c, bad_arg.load() == 0);
+  stage("ids");
   // ---- co-visibility signature of every landmark (set of free blocks observing it) ----
   // Landmarks with the same signature are made adjacent in every keyframe's list, so k_schur_rows can test
   // "does neighbour j see these landmarks" once per segment instead of once per entry.
+  std::atomic<int> dup_free{0};   // a landmark observed twice by the same free keyframe (never happens in the reference)
   auto signature = [&](const int* off, const std::vector<int>& ekf, int i, int g0, int nf) -> uint64_t {
     uint64_t key = 0;
     if (nf <= 64) {
       for (int e = off[i]; e < off[i + 1]; e++) {
         const int g = kf_g[ekf[e]];
-        if (g >= 0) key |= 1ull << (g - g0);
+        if (g >= 0) {
+          if (key & (1ull << (g - g0))) dup_free = 1;
+          key |= 1ull << (g - g0);
+        }
       }
     } else {  // FNV-1a over the sorted block list; segments are verified exactly below, the key only orders
       std::vector<int> gs;
       for (int e = off[i]; e < off[i + 1]; e++)
         if (kf_g[ekf[e]] >= 0) gs.push_back(kf_g[ekf[e]]);
       std::sort(gs.begin(), gs.end());
+      if (std::adjacent_find(gs.begin(), gs.end()) != gs.end()) dup_free = 1;
       key = 1469598103934665603ull;
       for (int g : gs) { key ^= (uint64_t)(g + 1); key *= 1099511628211ull; }
     }
@@ -152,7 +194,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   };
   std::vector<int> pt_order(n_pt), ln_order(n_ln);
   std::vector<uint64_t> pt_key(n_pt), ln_key(n_ln);
-  for (int w = 0; w < nw; w++) {
+  par_for(nw, [&](int w) {
     const int g0 = w_g0[w], nf = w_g0[w + 1] - g0;
     for (int i = p->pt_off[w]; i < p->pt_off[w + 1]; i++) { pt_key[i] = signature(p->pt_obs_off, pe_kf, i, g0, nf); pt_order[i] = i; }
     std::stable_sort(pt_order.begin() + p->pt_off[w], pt_order.begin() + p->pt_off[w + 1],
@@ -160,46 +202,42 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     for (int i = p->ln_off[w]; i < p->ln_off[w + 1]; i++) { ln_key[i] = signature(p->ln_obs_off, lc_kf, i, g0, nf); ln_order[i] = i; }
     std::stable_sort(ln_order.begin() + p->ln_off[w], ln_order.begin() + p->ln_off[w + 1],
                      [&](int a, int b) { return ln_key[a] < ln_key[b]; });
-  }
-  // dense mode: every window small enough to keep its whole S in one CTA's registers, one edge per (landmark, KF)
-  bool dense = !global_mode && S->max_n <= 6 * 32;
-  auto has_dup = [&](int n_lm, const int* off, const std::vector<int>& ekf) {
-    std::vector<int> seen;
-    for (int i = 0; i < n_lm; i++) {
-      seen.clear();
-      for (int e = off[i]; e < off[i + 1]; e++) seen.push_back(ekf[e]);
-      std::sort(seen.begin(), seen.end());
-      if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) return true;
-    }
-    return false;
-  };
-  if (dense && (has_dup(n_pt, p->pt_obs_off, pe_kf) || has_dup(n_ln, p->ln_obs_off, lc_kf))) dense = false;
+  });
+  stage("signature sort");
+  // dense mode: every window small enough to keep its whole S in registers / one edge per (landmark, free KF)
+  const bool dense = !global_mode && S->max_n <= 6 * 32 && dup_free.load() == 0;
+  LLD_ARG(c, dup_free.load() == 0 || !global_mode);
   v.dense_mode = dense ? 1 : 0;
   // per-free-keyframe lists (counting sort in signature order), separately for point edges and line cells
-  auto build_lists = [&](int n_lm, const int* off, const std::vector<int>& ekf, const std::vector<int>& order,
+  auto build_lists = [&](int n_lm, const int* lm_off, const int* off, const std::vector<int>& ekf, const std::vector<int>& order,
                          std::vector<int>& l_off, std::vector<int>& l_ref, std::vector<int>& e_pos) {
     l_off.assign(nG + 1, 0);
     const int n_e = n_lm ? off[n_lm] : 0;
-    for (int e = 0; e < n_e; e++)
-      if (kf_g[ekf[e]] >= 0) l_off[kf_g[ekf[e]] + 1]++;
+    par_for(nw, [&](int w) {   // a window's edges only touch the window's own free blocks
+      for (int e = off[lm_off[w]]; e < off[lm_off[w + 1]]; e++)
+        if (kf_g[ekf[e]] >= 0) l_off[kf_g[ekf[e]] + 1]++;
+    });
     for (int g = 0; g < nG; g++) l_off[g + 1] += l_off[g];
     l_ref.assign(std::max(l_off[nG], 1), 0);
     e_pos.assign(std::max(n_e, 1), -1);
     std::vector<int> cur(l_off.begin(), l_off.end() - 1);
-    for (int oi = 0; oi < n_lm; oi++) {
-      const int i = order[oi];
-      for (int e = off[i]; e < off[i + 1]; e++) {
-        const int g = kf_g[ekf[e]];
-        if (g < 0) continue;
-        e_pos[e] = cur[g];
-        l_ref[cur[g]++] = e;
+    par_for(nw, [&](int w) {
+      for (int oi = lm_off[w]; oi < lm_off[w + 1]; oi++) {
+        const int i = order[oi];
+        for (int e = off[i]; e < off[i + 1]; e++) {
+          const int g = kf_g[ekf[e]];
+          if (g < 0) continue;
+          e_pos[e] = cur[g];
+          l_ref[cur[g]++] = e;
+        }
       }
-    }
+    });
   };
   std::vector<int> pl_off, pl_edge, pe_pos, ll_off, ll_cell, lc_pos;
-  build_lists(n_pt, p->pt_obs_off, pe_kf, pt_order, pl_off, pl_edge, pe_pos);
-  build_lists(n_ln, p->ln_obs_off, lc_kf, ln_order, ll_off, ll_cell, lc_pos);
+  build_lists(n_pt, p->pt_off, p->pt_obs_off, pe_kf, pt_order, pl_off, pl_edge, pe_pos);
+  build_lists(n_ln, p->ln_off, p->ln_obs_off, lc_kf, ln_order, ll_off, ll_cell, lc_pos);
   const int n_plist = pl_off[nG], n_llist = ll_off[nG];
+  stage("kf lists");
   // neighbour lists (block columns >= own row)
   std::vector<int> nb_off(nG + 1, 0), nb_g;
   if (!global_mode) {
@@ -275,90 +313,118 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     build_tab(pl_off, pl_edge, p->pt_obs_off, pe_pt, pe_kf, pe_pos, pl_tab_off, pl_tab);
     build_tab(ll_off, ll_cell, p->ln_obs_off, lc_ln, lc_kf, lc_pos, ll_tab_off, ll_tab);
   }
+  stage("neighbours + tabs");
   // dense-mode structures
   std::vector<int> pt_spos(std::max(n_pt, 1), 0), ln_spos(std::max(n_ln, 1), 0), pts_w0(n_pt + 1, 0), lns_w0(n_ln + 1, 0);
   std::vector<uint32_t> pts_mask(std::max(n_pt, 1), 0), lns_mask(std::max(n_ln, 1), 0);
   std::vector<int> pe_wpos(std::max(n_pe, 1), -1), lc_wpos(std::max(n_lc, 1), -1);
   std::vector<int> it_piece, it_task0, pc_begin, pc_end, pc_n, gb_off(1, 0), gv_off(1, 0);
   std::vector<long long> pc_out, gb_src(1, 0), gv_src(1, 0);
-  std::vector<std::pair<int, long long>> gb_tmp, gv_tmp;
   long long dpart_total = 0;
   int n_items_pt = 0;
   size_t n_pw = 0, n_lw = 0;
   if (dense) {
-    auto slots = [&](int n_lm, const int* off, const std::vector<int>& ekf, const std::vector<int>& order,
+    // W slots: landmarks in signature order, each landmark's free edges sorted by keyframe
+    auto slots = [&](int n_lm, const int* lm_off, const int* off, const std::vector<int>& ekf, const std::vector<int>& order,
                      const std::vector<uint64_t>& key, std::vector<int>& spos, std::vector<uint32_t>& mask,
                      std::vector<int>& w0, std::vector<int>& wpos) {
-      std::vector<std::pair<int, int>> ge;
-      for (int oi = 0; oi < n_lm; oi++) {
-        const int i = order[oi];
-        spos[i] = oi;
-        mask[oi] = (uint32_t)key[i];
-        ge.clear();
-        for (int e = off[i]; e < off[i + 1]; e++)
-          if (kf_g[ekf[e]] >= 0) ge.push_back({kf_g[ekf[e]], e});
-        std::sort(ge.begin(), ge.end());
-        for (size_t k = 0; k < ge.size(); k++) wpos[ge[k].second] = w0[oi] + (int)k;
-        w0[oi + 1] = w0[oi] + (int)ge.size();
-      }
+      par_for(nw, [&](int w) {
+        for (int oi = lm_off[w]; oi < lm_off[w + 1]; oi++) {
+          const int i = order[oi];
+          spos[i] = oi;
+          mask[oi] = (uint32_t)key[i];
+          w0[oi + 1] = __builtin_popcountll(key[i]);
+        }
+      });
+      for (int oi = 0; oi < n_lm; oi++) w0[oi + 1] += w0[oi];
+      par_for(nw, [&](int w) {
+        std::pair<int, int> ge[32];
+        for (int oi = lm_off[w]; oi < lm_off[w + 1]; oi++) {
+          const int i = order[oi];
+          int n = 0;
+          for (int e = off[i]; e < off[i + 1]; e++)
+            if (kf_g[ekf[e]] >= 0) ge[n++] = {kf_g[ekf[e]], e};
+          std::sort(ge, ge + n);
+          for (int k = 0; k < n; k++) wpos[ge[k].second] = w0[oi] + k;
+        }
+      });
     };
-    slots(n_pt, p->pt_obs_off, pe_kf, pt_order, pt_key, pt_spos, pts_mask, pts_w0, pe_wpos);
-    slots(n_ln, p->ln_obs_off, lc_kf, ln_order, ln_key, ln_spos, lns_mask, lns_w0, lc_wpos);
+    slots(n_pt, p->pt_off, p->pt_obs_off, pe_kf, pt_order, pt_key, pt_spos, pts_mask, pts_w0, pe_wpos);
+    slots(n_ln, p->ln_off, p->ln_obs_off, lc_kf, ln_order, ln_key, ln_spos, lns_mask, lns_w0, lc_wpos);
     n_pw = (size_t)pts_w0[n_pt]; n_lw = (size_t)lns_w0[n_ln];
     int PIECE_CAP = 128;  // shorter pieces when the batch is small, so that every SM gets warps
     while (PIECE_CAP > 8 && (long long)(n_pt + n_ln) * 5 / (2 * PIECE_CAP) < 16LL * c->sm_count) PIECE_CAP >>= 1;
-    for (int kind = 0; kind < 2; kind++) {
+    // pieces / items / gather entries: built per (kind, window) with local offsets, merged in order afterwards
+    struct Job {
+      std::vector<int> pb, pe, pn, itp, itt;
+      std::vector<long long> pout;
+      std::vector<std::pair<int, long long>> gb, gv;
+      long long dsize = 0;
+    };
+    std::vector<Job> jobs(2 * (size_t)nw);
+    par_for(2 * nw, [&](int jid) {
+      const int kind = jid / nw, w = jid % nw;
+      Job& J = jobs[jid];
       const int* loff = kind == 0 ? p->pt_off : p->ln_off;
       const std::vector<uint32_t>& mask = kind == 0 ? pts_mask : lns_mask;
-      if (kind == 1) n_items_pt = (int)it_piece.size();
-      for (int w = 0; w < nw; w++) {
-        const int g0 = w_g0[w];
-        int b = loff[w];
-        while (b < loff[w + 1]) {
-          int e = b + 1;
-          while (e < loff[w + 1] && mask[e] == mask[b] && e - b < PIECE_CAP) e++;
-          const uint32_t m = mask[b];
-          const int n = __builtin_popcount(m);
-          if (n > 0) {
-            const int pc = (int)pc_begin.size();
-            pc_begin.push_back(b); pc_end.push_back(e); pc_n.push_back(n); pc_out.push_back(dpart_total);
-            const int npair = n * (n + 1) / 2, ntask = 6 * npair + n;
-            int hl[32], k = 0;
-            for (int h = 0; h < 32; h++)
-              if ((m >> h) & 1u) hl[k++] = h;
-            int pr = 0;
-            for (int ia = 0; ia < n; ia++)
-              for (int ib = ia; ib < n; ib++, pr++)
-                gb_tmp.push_back({nb_off[g0 + hl[ia]] + (hl[ib] - hl[ia]), dpart_total + 36LL * pr});
-            for (int ia = 0; ia < n; ia++) gv_tmp.push_back({g0 + hl[ia], dpart_total + 6LL * (6 * npair + ia)});
-            for (int t0 = 0; t0 < ntask; t0 += 32) { it_piece.push_back(pc); it_task0.push_back(t0); }
-            dpart_total += 6LL * ntask;
-          }
-          b = e;
+      const int g0 = w_g0[w];
+      int b = loff[w];
+      while (b < loff[w + 1]) {
+        int e = b + 1;
+        while (e < loff[w + 1] && mask[e] == mask[b] && e - b < PIECE_CAP) e++;
+        const uint32_t m = mask[b];
+        const int n = __builtin_popcount(m);
+        if (n > 0) {
+          const int pc = (int)J.pb.size();
+          J.pb.push_back(b); J.pe.push_back(e); J.pn.push_back(n); J.pout.push_back(J.dsize);
+          const int npair = n * (n + 1) / 2, ntask = 6 * npair + n;
+          int hl[32], k = 0;
+          for (int h = 0; h < 32; h++)
+            if ((m >> h) & 1u) hl[k++] = h;
+          int pr = 0;
+          for (int ia = 0; ia < n; ia++)
+            for (int ib = ia; ib < n; ib++, pr++) J.gb.push_back({nb_off[g0 + hl[ia]] + (hl[ib] - hl[ia]), J.dsize + 36LL * pr});
+          for (int ia = 0; ia < n; ia++) J.gv.push_back({g0 + hl[ia], J.dsize + 6LL * (6 * npair + ia)});
+          for (int t0 = 0; t0 < ntask; t0 += 32) { J.itp.push_back(pc); J.itt.push_back(t0); }
+          J.dsize += 6LL * ntask;
         }
+        b = e;
       }
-    }
-    // CSR of the gather lists (stable: piece order)
+    });
     gb_off.assign(nb_g.size() + 1, 0);
-    for (auto& x : gb_tmp) gb_off[x.first + 1]++;
-    for (size_t i = 0; i < nb_g.size(); i++) gb_off[i + 1] += gb_off[i];
-    gb_src.assign(std::max<size_t>(gb_tmp.size(), 1), 0);
-    {
-      std::vector<int> cur(gb_off.begin(), gb_off.end() - 1);
-      for (auto& x : gb_tmp) gb_src[cur[x.first]++] = x.second;
-    }
     gv_off.assign(nG + 1, 0);
-    for (auto& x : gv_tmp) gv_off[x.first + 1]++;
+    for (size_t jid = 0; jid < jobs.size(); jid++) {
+      Job& J = jobs[jid];
+      if (jid == (size_t)nw) n_items_pt = (int)it_piece.size();
+      const int pbase = (int)pc_begin.size();
+      pc_begin.insert(pc_begin.end(), J.pb.begin(), J.pb.end());
+      pc_end.insert(pc_end.end(), J.pe.begin(), J.pe.end());
+      pc_n.insert(pc_n.end(), J.pn.begin(), J.pn.end());
+      for (long long o : J.pout) pc_out.push_back(o + dpart_total);
+      for (int x : J.itp) it_piece.push_back(x + pbase);
+      it_task0.insert(it_task0.end(), J.itt.begin(), J.itt.end());
+      for (auto& x : J.gb) { gb_off[x.first + 1]++; x.second += dpart_total; }
+      for (auto& x : J.gv) { gv_off[x.first + 1]++; x.second += dpart_total; }
+      dpart_total += J.dsize;
+    }
+    if (nw == 0 || jobs.size() <= (size_t)nw) n_items_pt = (int)it_piece.size();
+    for (size_t i = 0; i < nb_g.size(); i++) gb_off[i + 1] += gb_off[i];
     for (int i = 0; i < nG; i++) gv_off[i + 1] += gv_off[i];
-    gv_src.assign(std::max<size_t>(gv_tmp.size(), 1), 0);
+    gb_src.assign(std::max<size_t>((size_t)gb_off[nb_g.size()], 1), 0);
+    gv_src.assign(std::max<size_t>((size_t)gv_off[nG], 1), 0);
     {
-      std::vector<int> cur(gv_off.begin(), gv_off.end() - 1);
-      for (auto& x : gv_tmp) gv_src[cur[x.first]++] = x.second;
+      // stable fill in job order (points of window 0.., then lines): a block's contributions keep a fixed order
+      std::vector<int> curb(gb_off.begin(), gb_off.end() - 1), curv(gv_off.begin(), gv_off.end() - 1);
+      for (auto& J : jobs) {
+        for (auto& x : J.gb) gb_src[curb[x.first]++] = x.second;
+        for (auto& x : J.gv) gv_src[curv[x.first]++] = x.second;
+      }
     }
   }
   v.n_items = (int)it_piece.size();
   v.n_items_pt = dense ? n_items_pt : 0;
 
+  stage("dense slots/pieces/gather");
   // chunks + segments (runs of entries whose table rows have the same -1 pattern)
   const long long n_list_total = (long long)n_plist + n_llist;
   int CH = CHUNK;
@@ -412,6 +478,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     if (S->max_n > SMEM_SOLVE_MAX_N) scr_total += n * n + 8 * n + 8;
   }
 
+  stage("chunks");
   // ---- upload (timed as h2d) ----
   int* tmp_i;
   UP(tmp_i, p->kf_off, nw + 1); v.kf_off = tmp_i;
@@ -492,6 +559,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   UP(d_L, p->ln_x0_dir, 6 * (size_t)n_ln);
   S->d_kf_Tcw_in = d_T; S->d_pt_in = d_P; S->d_ln_in = d_L;
 
+  stage("H2D enqueue");
   // ---- device-only buffers ----
   for (int b = 0; b < 2; b++) {
     DEV(v.pose_qt[b], double, 7 * (size_t)n_kf);
@@ -539,6 +607,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   v.prm.chi2_pt_mono = p->chi2_pt_mono; v.prm.chi2_pt_stereo = p->chi2_pt_stereo;
   v.prm.ln_norm = p->ln_endpoints_normalized;
   v.prm.ln_filter = p->ln_filter;
+  stage("device buffers");
   c->last_h2d_bytes = S->h2d_bytes;
   return LLD_OK;
 }
@@ -637,7 +706,7 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
     if (nip) LLD_LAUNCH(c, k_schur_piece<3>, cdiv(nip, 8), 256, 0, v, 0, nip);
     if (nil) LLD_LAUNCH(c, k_schur_piece<4>, cdiv(nil, 8), 256, 0, v, nip, nil);
     const int nblk = (int)S->n_nb_total;
-    LLD_LAUNCH(c, k_reduce_piece, cdiv(nblk * 6 + v.n_free_total * 6, 256), 256, 0, v, nblk);
+    LLD_LAUNCH(c, k_reduce_piece, cdiv(nblk * 6 + v.n_free_total, 8), 256, 0, v, nblk);
   } else {
     const int tpb = 32 * cdiv(6 * S->max_nnb, 32);
     const int nl = v.n_chunks - v.n_chunks_pt;

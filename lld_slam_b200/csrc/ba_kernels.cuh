@@ -806,13 +806,13 @@ __global__ void __launch_bounds__(256) k_schur_piece(BaView v, int item_base, in
 }
 
 // S(a,b) = [a==b] (Hpp_a + lambda I) - sum over contributing (piece, pair) ; bschur_a = bp_a - sum b tasks
-// one thread per (block, column c) and per (keyframe, row r)
-__global__ void k_reduce_piece(BaView v, int n_blocks) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x < n_blocks * 6) {
-    const int blk = x / 6, c = x - 6 * blk;
-    // owning free block row g: largest g with nb_off[g] <= blk
-    int lo = 0, hi = v.n_free_total;
+// one warp per (block, column c) and per free keyframe: lanes stride over the gather list, fixed-order shuffle tree
+__global__ void __launch_bounds__(256) k_reduce_piece(BaView v, int n_blocks) {
+  const int wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wi < n_blocks * 6) {
+    const int blk = wi / 6, c = wi - 6 * blk;
+    int lo = 0, hi = v.n_free_total;   // owning free block row g: largest g with nb_off[g] <= blk
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
       if (v.nb_off[mid] <= blk) lo = mid;
@@ -822,31 +822,42 @@ __global__ void k_reduce_piece(BaView v, int n_blocks) {
     const int w = v.kf_win[v.g_kf[g]];
     if (v.w_phase[w] == PH_DONE) return;
     double s[6] = {0, 0, 0, 0, 0, 0};
-    for (int q = v.gb_off[blk]; q < v.gb_off[blk + 1]; q++) {
+    for (int q = v.gb_off[blk] + lane; q < v.gb_off[blk + 1]; q += 32) {
       const double* src = v.dpart + v.gb_src[q] + 6 * c;
 #pragma unroll
       for (int r = 0; r < 6; r++) s[r] += src[r];
     }
-    const double lam = v.w_lambda[w];
 #pragma unroll
-    for (int r = 0; r < 6; r++) {
-      double d = 0.0;
-      if (j == 0) {
-        const int rr = r < c ? r : c, cc = r < c ? c : r;
-        d = v.g_Hpp[21 * (size_t)g + (rr * 6 - (rr * (rr - 1)) / 2 + (cc - rr))];
-        if (r == c) d += lam;
+    for (int r = 0; r < 6; r++) s[r] = warp_sum(s[r]);
+    if (lane == 0) {
+      const double lam = v.w_lambda[w];
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        double d = 0.0;
+        if (j == 0) {
+          const int rr = r < c ? r : c, cc = r < c ? c : r;
+          d = v.g_Hpp[21 * (size_t)g + (rr * 6 - (rr * (rr - 1)) / 2 + (cc - rr))];
+          if (r == c) d += lam;
+        }
+        v.S_blk[36 * (size_t)blk + 6 * r + c] = d - s[r];
       }
-      v.S_blk[36 * (size_t)blk + 6 * r + c] = d - s[r];
     }
   } else {
-    const int y = x - n_blocks * 6;
-    if (y >= v.n_free_total * 6) return;
-    const int g = y / 6, r = y - 6 * g;
+    const int g = wi - n_blocks * 6;
+    if (g >= v.n_free_total) return;
     const int w = v.kf_win[v.g_kf[g]];
     if (v.w_phase[w] == PH_DONE) return;
-    double s = 0;
-    for (int q = v.gv_off[g]; q < v.gv_off[g + 1]; q++) s += v.dpart[v.gv_src[q] + r];
-    v.g_bs[6 * (size_t)g + r] = v.g_bp[6 * (size_t)g + r] - s;
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    for (int q = v.gv_off[g] + lane; q < v.gv_off[g + 1]; q += 32) {
+      const double* src = v.dpart + v.gv_src[q];
+#pragma unroll
+      for (int r = 0; r < 6; r++) s[r] += src[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) s[r] = warp_sum(s[r]);
+    if (lane == 0)
+#pragma unroll
+      for (int r = 0; r < 6; r++) v.g_bs[6 * (size_t)g + r] = v.g_bp[6 * (size_t)g + r] - s[r];
   }
 }
 
@@ -869,31 +880,49 @@ __device__ bool ldlt_solve_cta(double* A, int n, int ld, double* b /*in: rhs, ou
   __syncthreads();
   for (int k0 = 0; k0 < n; k0 += 6) {
     if (tid == 0) {
-      // unblocked LDL^T of the 6x6 diagonal block (lower part), in place: strict lower -> L, diagonal -> D
+      // unblocked LDL^T of the 6x6 diagonal block in registers (independent loads first), then written back
+      double M[6][6], zz[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        zz[i] = b[k0 + i];
+#pragma unroll
+        for (int j = 0; j < 6; j++) M[i][j] = (j <= i) ? A[(size_t)(k0 + i) * ld + k0 + j] : 0.0;
+      }
       bool ok = true;
-      for (int j = 0; j < 6 && ok; j++) {
-        double d = A[(size_t)(k0 + j) * ld + k0 + j];
-        for (int q = 0; q < j; q++) {
-          const double l = A[(size_t)(k0 + j) * ld + k0 + q];
-          d -= l * l * A[(size_t)(k0 + q) * ld + k0 + q];
-        }
-        if (!(d != 0.0) || !isfinite(d)) { ok = false; break; }
-        A[(size_t)(k0 + j) * ld + k0 + j] = d;
-        for (int i = j + 1; i < 6; i++) {
-          double s2 = A[(size_t)(k0 + i) * ld + k0 + j];
-          for (int q = 0; q < j; q++)
-            s2 -= A[(size_t)(k0 + i) * ld + k0 + q] * A[(size_t)(k0 + j) * ld + k0 + q] * A[(size_t)(k0 + q) * ld + k0 + q];
-          A[(size_t)(k0 + i) * ld + k0 + j] = s2 / d;
-        }
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        double d = M[j][j];
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+          if (q < j) d -= M[j][q] * M[j][q] * M[q][q];
+        if (!(d != 0.0) || !isfinite(d)) ok = false;
+        M[j][j] = d;
+        const double id = 1.0 / d;
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+          if (i > j) {
+            double s2 = M[i][j];
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+              if (q < j) s2 -= M[i][q] * M[j][q] * M[q][q];
+            M[i][j] = s2 * id;
+          }
       }
       if (!ok) *flag = 0;
       else {
-        // z = L_kk^-1 b_k
+#pragma unroll
         for (int i = 0; i < 6; i++) {
-          double s2 = b[k0 + i];
-          for (int q = 0; q < i; q++) s2 -= A[(size_t)(k0 + i) * ld + k0 + q] * zb[q];
-          zb[i] = s2;
-          b[k0 + i] = s2;
+#pragma unroll
+          for (int q = 0; q < 6; q++)
+            if (q < i) zz[i] -= M[i][q] * zz[q];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          zb[i] = zz[i];
+          b[k0 + i] = zz[i];
+#pragma unroll
+          for (int j = 0; j < 6; j++)
+            if (j <= i) A[(size_t)(k0 + i) * ld + k0 + j] = M[i][j];
         }
       }
     }
