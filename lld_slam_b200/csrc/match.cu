@@ -25,7 +25,6 @@ namespace {
 
 constexpr int GRID_COLS = 64, GRID_ROWS = 48, N_CELLS = GRID_COLS * GRID_ROWS;
 constexpr int TH_HIGH = 100, HISTO_LENGTH = 30;
-constexpr int QL = 8;  // lanes per query
 
 struct MatchView {
   int n_pairs, n_cur, n_q;
@@ -68,11 +67,13 @@ struct MatchView {
   const float* last_Tcw;
   // results / iteration state
   int* owner;      // [n_cur] smallest accepted query (with observations) that matched the keypoint; -1 = claimed on entry
-  int* owner_prev;
   int* q_best;     // [n_q] matched keypoint (pair-local, original index) or -1
   int* q_dist;
-  int* q_prev;
   int* changed;    // [1]
+  int* q_pair;     // [n_q] pair of the query
+  int* pair_mode;  // [n_pairs] v0: 0 = levels [oct-1, oct+1], 1 = forward, 2 = backward
+  unsigned long long* q_top;  // [n_q][4] four best candidates, packed (dist | cell | idx | octave), ascending
+  int* q_ncand;    // [n_q] number of admissible candidates seen by the scan
   int* match;      // [n_cur]
   int* n_matches;  // [n_pairs]
 };
@@ -152,19 +153,15 @@ __global__ void k_cell_fill(MatchView v) {
   v.s_desc[2 * d + 1] = src[1];
 }
 
-struct Top2 {
-  int d1, k1, i1, l1;  // best: distance, order key, keypoint index, level
-  int d2, k2, l2;      // second best
-};
-__device__ __forceinline__ bool lex_less(int da, int ka, int db, int kb) { return da < db || (da == db && ka < kb); }
-__device__ __forceinline__ void top2_insert(Top2& t, int d, int k, int idx, int lvl) {
-  if (lex_less(d, k, t.d1, t.k1)) {
-    t.d2 = t.d1; t.k2 = t.k1; t.l2 = t.l1;
-    t.d1 = d; t.k1 = k; t.i1 = idx; t.l1 = lvl;
-  } else if (lex_less(d, k, t.d2, t.k2)) {
-    t.d2 = d; t.k2 = k; t.l2 = lvl;
-  }
+// packed candidate key: lexicographic (distance, grid traversal order) == integer order
+//   [dist:9 | cell:12 | idx:16 | octave:3]   (cell = ix*48+iy : x outer, y inner; idx = insertion order inside a cell)
+constexpr unsigned long long EMPTY_KEY = ~0ull;
+__device__ __forceinline__ unsigned long long pack_key(int d, int cell, int idx, int oct) {
+  return ((unsigned long long)d << 31) | ((unsigned long long)cell << 19) | ((unsigned long long)idx << 3) | (unsigned long long)oct;
 }
+__device__ __forceinline__ int key_dist(unsigned long long k) { return (int)(k >> 31); }
+__device__ __forceinline__ int key_idx(unsigned long long k) { return (int)((k >> 3) & 0xFFFFull); }
+__device__ __forceinline__ int key_oct(unsigned long long k) { return (int)(k & 7ull); }
 
 // cv::Mat (CV_32F) row of R*x + t : double accumulation, one rounding
 __device__ __forceinline__ float gemm_row(const float* R, const float* x, float t) {
@@ -173,130 +170,186 @@ __device__ __forceinline__ float gemm_row(const float* R, const float* x, float 
   return (float)__dadd_rn(s, (double)t);
 }
 
-// One query per QL lanes.
-__global__ void __launch_bounds__(256) k_match(MatchView v, int pass) {
-  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-  const int q = gt / QL, lane = gt % QL;
-  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) / QL * QL);
-  if (q >= v.n_q) return;  // whole group exits together (QL divides the block size)
-  const int p = find_pair(v.q_off, v.n_pairs, q);
-  const int qi = q - v.q_off[p];  // pair-local query index
+// per pair: forward / backward decision of the frame-to-frame variant (src/ORBmatcher.cc:1340-1350)
+__global__ void k_pair_prep(MatchView v) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= v.n_pairs) return;
+  int mode = 0;
+  if (v.variant == 0) {
+    const float* Tc = v.cur_Tcw + 12 * (size_t)p;
+    const float* Tl = v.last_Tcw + 12 * (size_t)p;
+    float twc[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const double s = __dadd_rn(__dadd_rn(__dmul_rn((double)Tc[i], (double)Tc[9]), __dmul_rn((double)Tc[3 + i], (double)Tc[10])),
+                                 __dmul_rn((double)Tc[6 + i], (double)Tc[11]));
+      twc[i] = (float)(-s);
+    }
+    const float tlc2 = gemm_row(Tl + 6, twc, Tl[11]);
+    const bool fwd = tlc2 > v.b && !v.mono;
+    const bool bwd = -tlc2 > v.b && !v.mono;
+    mode = fwd ? 1 : (bwd ? 2 : 0);
+  }
+  v.pair_mode[p] = mode;
+}
+__global__ void k_query_pair(MatchView v) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= v.n_q) return;
+  v.q_pair[q] = find_pair(v.q_off, v.n_pairs, q);
+}
+
+struct QueryWin {
+  bool valid;
+  float x, y, r, urq;
+  int minLevel, maxLevel;
+};
+__device__ __forceinline__ QueryWin query_window(const MatchView& v, int q, int p) {
+  QueryWin w;
+  w.valid = v.q_valid[q] != 0;
+  w.x = w.y = w.r = w.urq = 0.f;
+  w.minLevel = w.maxLevel = -1;
+  if (!w.valid) return w;
+  if (v.variant == 0) {
+    const float* Tc = v.cur_Tcw + 12 * (size_t)p;
+    const float* Xw = v.q_xw + 3 * (size_t)q;
+    const float xc = gemm_row(Tc, Xw, Tc[9]);
+    const float yc = gemm_row(Tc + 3, Xw, Tc[10]);
+    const float zc = gemm_row(Tc + 6, Xw, Tc[11]);
+    const float invzc = (float)(1.0 / (double)zc);
+    if (invzc < 0) w.valid = false;
+    w.x = __fadd_rn(__fmul_rn(__fmul_rn(v.fx, xc), invzc), v.cx);
+    w.y = __fadd_rn(__fmul_rn(__fmul_rn(v.fy, yc), invzc), v.cy);
+    if (w.x < v.min_x || w.x > v.max_x) w.valid = false;
+    if (w.y < v.min_y || w.y > v.max_y) w.valid = false;
+    const int oct = v.q_octave[q];
+    w.r = __fmul_rn(v.th, v.scale[oct]);
+    w.urq = __fsub_rn(w.x, __fmul_rn(v.bf, invzc));
+    const int mode = v.pair_mode[p];
+    if (mode == 1) { w.minLevel = oct; w.maxLevel = -1; }
+    else if (mode == 2) { w.minLevel = 0; w.maxLevel = oct; }
+    else { w.minLevel = oct - 1; w.maxLevel = oct + 1; }
+  } else {
+    const float* pj = v.q_xw + 3 * (size_t)q;
+    w.x = pj[0]; w.y = pj[1]; w.urq = pj[2];
+    const int lvl = v.q_level[q];
+    float rr = ((double)v.q_viewcos[q] > 0.998) ? 2.5f : 4.0f;  // RadiusByViewingCos :131-137
+    if (v.th != 1.0f) rr = __fmul_rn(rr, v.th);
+    w.r = __fmul_rn(rr, v.scale[lvl]);
+    w.minLevel = lvl - 1; w.maxLevel = lvl;
+  }
+  return w;
+}
+
+// Scan the window of one query (one thread).  excl_below >= 0: skip keypoints owned by a query < excl_below.
+// Keeps the four smallest keys in t[0..3]; returns the number of admissible candidates.
+__device__ __forceinline__ int scan_window(const MatchView& v, int q, int p, const QueryWin& w, int excl_below,
+                                           unsigned long long* t) {
+  t[0] = t[1] = t[2] = t[3] = EMPTY_KEY;
+  if (!w.valid) return 0;
+  // Frame::GetFeaturesInArea window  src/Frame.cc:396-410
+  const int x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(w.x, v.min_x), w.r), v.winv)));
+  const int x1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(w.x, v.min_x), w.r), v.winv)));
+  const int y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(w.y, v.min_y), w.r), v.hinv)));
+  const int y1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(w.y, v.min_y), w.r), v.hinv)));
+  if (!(x0 < GRID_COLS && x1 >= 0 && y0 < GRID_ROWS && y1 >= 0)) return 0;
+  const bool check_levels = (w.minLevel > 0) || (w.maxLevel >= 0);
+  const uint4* qd = reinterpret_cast<const uint4*>(v.q_desc + 32 * (size_t)q);
+  const uint4 a0 = qd[0], a1 = qd[1];
+  const int* cstart = v.cell_count + (size_t)p * (N_CELLS + 1);
+  const size_t base = (size_t)v.cur_off[p];
+  const int* own = v.owner + base;
+  int ncand = 0;
+  for (int ix = x0; ix <= x1; ix++) {
+    const int s0 = cstart[ix * GRID_ROWS + y0], s1 = cstart[ix * GRID_ROWS + y1 + 1];
+    for (int s = s0; s < s1; s++) {
+      const int meta = v.s_meta[base + s];
+      const int oct = meta & 0xFF;
+      if (check_levels) {
+        if (oct < w.minLevel) continue;
+        if (w.maxLevel >= 0 && oct > w.maxLevel) continue;
+      }
+      const float2 xy = v.s_xy[base + s];
+      const float dx = __fsub_rn(xy.x, w.x), dy = __fsub_rn(xy.y, w.y);
+      if (!(fabsf(dx) < w.r && fabsf(dy) < w.r)) continue;
+      const int idx = v.s_idx[base + s];
+      const int ow = own[idx];
+      if (ow < 0 || (excl_below >= 0 && ow < excl_below)) continue;  // claimed on entry / by an earlier accepted query
+      const float ur = v.s_ur[base + s];
+      if (ur > 0) {
+        const float er = fabsf(__fsub_rn(w.urq, ur));
+        if (er > w.r) continue;
+      }
+      const uint4 b0 = v.s_desc[2 * (base + s)], b1 = v.s_desc[2 * (base + s) + 1];
+      const int d = popc256(a0, a1, b0, b1);
+      ncand++;
+      unsigned long long k = pack_key(d, meta >> 8, idx, oct);
+      if (k < t[3]) {
+        t[3] = k;
+        if (t[3] < t[2]) { const unsigned long long u = t[2]; t[2] = t[3]; t[3] = u; }
+        if (t[2] < t[1]) { const unsigned long long u = t[1]; t[1] = t[2]; t[2] = u; }
+        if (t[1] < t[0]) { const unsigned long long u = t[0]; t[0] = t[1]; t[1] = u; }
+      }
+    }
+  }
+  return ncand;
+}
+
+// pass 0: one thread per query scans its window once and caches the four best candidates
+__global__ void __launch_bounds__(128) k_match_scan(MatchView v) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= v.n_q) return;
+  const int p = v.q_pair[q];
+  const QueryWin w = query_window(v, q, p);
+  unsigned long long t[4];
+  const int n = scan_window(v, q, p, w, -1, t);
+  ulonglong2* dst = reinterpret_cast<ulonglong2*>(v.q_top + 4 * (size_t)q);
+  dst[0] = make_ulonglong2(t[0], t[1]);
+  dst[1] = make_ulonglong2(t[2], t[3]);
+  v.q_ncand[q] = n;
+}
+
+// resolution pass: best (and second best) candidate not owned by an earlier accepted query, from the cached top-4;
+// a rescan is only needed when the cache is exhausted although more candidates exist
+__global__ void __launch_bounds__(128) k_match_resolve(MatchView v, int pass) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= v.n_q) return;
+  const int p = v.q_pair[q];
+  const int qi = q - v.q_off[p];
+  const int* own = v.owner + (size_t)v.cur_off[p];
+  const ulonglong2* src = reinterpret_cast<const ulonglong2*>(v.q_top + 4 * (size_t)q);
+  const ulonglong2 ta = src[0], tb = src[1];
+  unsigned long long t[4] = {ta.x, ta.y, tb.x, tb.y};
+  const int need = v.variant == 1 ? 2 : 1;
+  unsigned long long k1 = EMPTY_KEY, k2 = EMPTY_KEY;
+  int found = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (t[j] == EMPTY_KEY || found >= need) continue;
+    if (own[key_idx(t[j])] < qi) continue;
+    if (found == 0) k1 = t[j];
+    else k2 = t[j];
+    found++;
+  }
+  if (found < need && v.q_ncand[q] > 4) {  // cache exhausted: scan again with the exclusion applied
+    const QueryWin w = query_window(v, q, p);
+    scan_window(v, q, p, w, qi, t);
+    k1 = t[0];
+    k2 = t[1];
+  }
   int best = -1, bdist = 256;
-  bool valid = v.q_valid[q] != 0;
-  float x = 0, y = 0, r = 0, urq = 0, er_lim = 0;
-  int minLevel = -1, maxLevel = -1;
-  if (valid) {
-    if (v.variant == 0) {
-      const float* Tc = v.cur_Tcw + 12 * (size_t)p;
-      const float* Xw = v.q_xw + 3 * (size_t)q;
-      const float xc = gemm_row(Tc, Xw, Tc[9]);
-      const float yc = gemm_row(Tc + 3, Xw, Tc[10]);
-      const float zc = gemm_row(Tc + 6, Xw, Tc[11]);
-      const float invzc = (float)(1.0 / (double)zc);
-      if (invzc < 0) valid = false;
-      x = __fadd_rn(__fmul_rn(__fmul_rn(v.fx, xc), invzc), v.cx);
-      y = __fadd_rn(__fmul_rn(__fmul_rn(v.fy, yc), invzc), v.cy);
-      if (x < v.min_x || x > v.max_x) valid = false;
-      if (y < v.min_y || y > v.max_y) valid = false;
-      const int oct = v.q_octave[q];
-      r = __fmul_rn(v.th, v.scale[oct]);
-      er_lim = r;
-      urq = __fsub_rn(x, __fmul_rn(v.bf, invzc));
-      // forward / backward: tlc = Rlw * twc + tlw  with twc = -Rcw^T tcw   (src/ORBmatcher.cc:1340-1350)
-      const float* Tl = v.last_Tcw + 12 * (size_t)p;
-      float twc[3];
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        const double s = __dadd_rn(__dadd_rn(__dmul_rn((double)Tc[i], (double)Tc[9]), __dmul_rn((double)Tc[3 + i], (double)Tc[10])),
-                                   __dmul_rn((double)Tc[6 + i], (double)Tc[11]));
-        twc[i] = (float)(-s);
-      }
-      const float tlc2 = gemm_row(Tl + 6, twc, Tl[11]);
-      const bool fwd = tlc2 > v.b && !v.mono;
-      const bool bwd = -tlc2 > v.b && !v.mono;
-      if (fwd) { minLevel = oct; maxLevel = -1; }
-      else if (bwd) { minLevel = 0; maxLevel = oct; }
-      else { minLevel = oct - 1; maxLevel = oct + 1; }
-    } else {
-      const float* pj = v.q_xw + 3 * (size_t)q;
-      x = pj[0]; y = pj[1]; urq = pj[2];
-      const int lvl = v.q_level[q];
-      float rr = ((double)v.q_viewcos[q] > 0.998) ? 2.5f : 4.0f;  // RadiusByViewingCos :131-137
-      if (v.th != 1.0f) rr = __fmul_rn(rr, v.th);
-      r = __fmul_rn(rr, v.scale[lvl]);
-      er_lim = r;
-      minLevel = lvl - 1; maxLevel = lvl;
+  if (k1 != EMPTY_KEY && key_dist(k1) <= TH_HIGH) {
+    bool ok = true;
+    if (v.variant == 1) {
+      // ratio test only when best and second best share the level  (src/ORBmatcher.cc:118-121)
+      const int d2 = k2 != EMPTY_KEY ? key_dist(k2) : 256;
+      const int l2 = k2 != EMPTY_KEY ? key_oct(k2) : -1;
+      if (key_oct(k1) == l2 && (float)key_dist(k1) > __fmul_rn(v.nn_ratio, (float)d2)) ok = false;
     }
+    if (ok) { best = key_idx(k1); bdist = key_dist(k1); }
   }
-  Top2 t;
-  t.d1 = 256; t.k1 = INT_MAX; t.i1 = -1; t.l1 = -1;
-  t.d2 = 256; t.k2 = INT_MAX; t.l2 = -1;
-  if (valid) {
-    // Frame::GetFeaturesInArea window  src/Frame.cc:396-410
-    const int x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, v.min_x), r), v.winv)));
-    const int x1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, v.min_x), r), v.winv)));
-    const int y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, v.min_y), r), v.hinv)));
-    const int y1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, v.min_y), r), v.hinv)));
-    if (x0 < GRID_COLS && x1 >= 0 && y0 < GRID_ROWS && y1 >= 0) {
-      const bool check_levels = (minLevel > 0) || (maxLevel >= 0);
-      const uint4* qd = reinterpret_cast<const uint4*>(v.q_desc + 32 * (size_t)q);
-      const uint4 a0 = qd[0], a1 = qd[1];
-      const int* cstart = v.cell_count + (size_t)p * (N_CELLS + 1);
-      const size_t base = (size_t)v.cur_off[p];
-      const int* own = v.owner + base;
-      for (int ix = x0; ix <= x1; ix++) {
-        const int s0 = cstart[ix * GRID_ROWS + y0], s1 = cstart[ix * GRID_ROWS + y1 + 1];
-        for (int s = s0 + lane; s < s1; s += QL) {
-          const int meta = v.s_meta[base + s];
-          const int oct = meta & 0xFF;
-          if (check_levels) {
-            if (oct < minLevel) continue;
-            if (maxLevel >= 0 && oct > maxLevel) continue;
-          }
-          const float2 xy = v.s_xy[base + s];
-          const float dx = __fsub_rn(xy.x, x), dy = __fsub_rn(xy.y, y);
-          if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
-          const int idx = v.s_idx[base + s];
-          const int ow = own[idx];
-          if (ow < qi) continue;  // claimed on entry (-1) or by an earlier accepted query
-          const float ur = v.s_ur[base + s];
-          if (ur > 0) {
-            const float er = fabsf(__fsub_rn(urq, ur));
-            if (er > er_lim) continue;
-          }
-          const uint4 b0 = v.s_desc[2 * (base + s)], b1 = v.s_desc[2 * (base + s) + 1];
-          const int d = popc256(a0, a1, b0, b1);
-          // grid traversal order: cell (x outer, y inner), then insertion (= keypoint index) order
-          const int key = ((meta >> 8) << 16) | idx;
-          top2_insert(t, d, key, idx, oct);
-        }
-      }
-    }
-  }
-  // merge the QL lanes' top-2 lists
-#pragma unroll
-  for (int o = QL / 2; o > 0; o >>= 1) {
-    Top2 u;
-    u.d1 = __shfl_xor_sync(gmask, t.d1, o); u.k1 = __shfl_xor_sync(gmask, t.k1, o);
-    u.i1 = __shfl_xor_sync(gmask, t.i1, o); u.l1 = __shfl_xor_sync(gmask, t.l1, o);
-    u.d2 = __shfl_xor_sync(gmask, t.d2, o); u.k2 = __shfl_xor_sync(gmask, t.k2, o);
-    u.l2 = __shfl_xor_sync(gmask, t.l2, o);
-    if (u.i1 >= 0) top2_insert(t, u.d1, u.k1, u.i1, u.l1);
-    if (u.k2 != INT_MAX) top2_insert(t, u.d2, u.k2, -2, u.l2);
-  }
-  if (lane == 0) {
-    if (valid && t.i1 >= 0 && t.d1 <= TH_HIGH) {
-      bool ok = true;
-      if (v.variant == 1) {
-        // ratio test only when best and second best share the level  (src/ORBmatcher.cc:118-121)
-        if (t.l1 == t.l2 && (float)t.d1 > __fmul_rn(v.nn_ratio, (float)t.d2)) ok = false;
-      }
-      if (ok) { best = t.i1; bdist = t.d1; }
-    }
-    if (pass > 0 && v.q_best[q] != best) atomicOr(v.changed, 1);
-    v.q_best[q] = best;
-    v.q_dist[q] = bdist;
-  }
+  if (pass > 0 && v.q_best[q] != best) atomicOr(v.changed, 1);
+  v.q_best[q] = best;
+  v.q_dist[q] = bdist;
 }
 
 __global__ void k_owner_reset(MatchView v) {
@@ -310,7 +363,7 @@ __global__ void k_claim(MatchView v) {
   if (q >= v.n_q) return;
   const int b = v.q_best[q];
   if (b < 0 || !v.q_has_obs[q]) return;
-  const int p = find_pair(v.q_off, v.n_pairs, q);
+  const int p = v.q_pair[q];
   atomicMin(&v.owner[(size_t)v.cur_off[p] + b], q - v.q_off[p]);
 }
 
@@ -416,8 +469,11 @@ static int match_run(LldCtx* c, MatchView& v, int* passes_out) {
   int pass = 0;
   const int max_pass = 64;
   if (v.n_q) {
+    LLD_LAUNCH(c, k_pair_prep, cdiv(v.n_pairs, 128), 128, 0, v);
+    LLD_LAUNCH(c, k_query_pair, cdiv(v.n_q, 256), 256, 0, v);
+    LLD_LAUNCH(c, k_match_scan, cdiv(v.n_q, 128), 128, 0, v);
     while (true) {
-      LLD_LAUNCH(c, k_match, cdiv(v.n_q * QL, 256), 256, 0, v, pass);
+      LLD_LAUNCH(c, k_match_resolve, cdiv(v.n_q, 128), 128, 0, v, pass);
       if (pass > 0) {
         LLD_CUDA(c, cudaMemcpyAsync(h_changed, v.changed, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         LLD_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -451,6 +507,10 @@ static int match_alloc_common(LldCtx* c, MatchView& v) {
   UPC(v.q_best, int, nullptr, v.n_q);
   UPC(v.q_dist, int, nullptr, v.n_q);
   UPC(v.changed, int, nullptr, 1);
+  UPC(v.q_pair, int, nullptr, v.n_q);
+  UPC(v.pair_mode, int, nullptr, v.n_pairs);
+  UPC(v.q_top, unsigned long long, nullptr, 4 * (size_t)v.n_q);
+  UPC(v.q_ncand, int, nullptr, v.n_q);
   UPC(v.match, int, nullptr, v.n_cur);
   UPC(v.n_matches, int, nullptr, v.n_pairs);
   LLD_CUDA(c, cudaMemsetAsync(v.changed, 0, sizeof(int), c->stream));
@@ -489,6 +549,8 @@ static int sbp_frame_upload(LldCtx* c, const lld_sbp_frame_problem* p, MatchView
   LLD_ARG(c, p->n_pairs >= 1);
   v.n_cur = p->cur_off[p->n_pairs];
   v.n_q = p->last_off[p->n_pairs];
+  LLD_ARG(c, p->geom.n_levels >= 1 && p->geom.n_levels <= 8);  // octave is packed into 3 bits of the candidate key
+  for (int i = 0; i < p->n_pairs; i++) LLD_ARG(c, p->cur_off[i + 1] - p->cur_off[i] <= 65535);
   v.variant = 0;
   set_geom(v, p->geom);
   v.th = p->th; v.nn_ratio = 0; v.mono = p->mono; v.check_ori = p->check_orientation;
@@ -519,6 +581,8 @@ static int sbp_mp_upload(LldCtx* c, const lld_sbp_mp_problem* p, MatchView& v) {
   LLD_ARG(c, p->n_pairs >= 1);
   v.n_cur = p->cur_off[p->n_pairs];
   v.n_q = p->mp_off[p->n_pairs];
+  LLD_ARG(c, p->geom.n_levels >= 1 && p->geom.n_levels <= 8);
+  for (int i = 0; i < p->n_pairs; i++) LLD_ARG(c, p->cur_off[i + 1] - p->cur_off[i] <= 65535);
   v.variant = 1;
   set_geom(v, p->geom);
   v.th = p->th; v.nn_ratio = p->nn_ratio; v.mono = 0; v.check_ori = 0;
