@@ -48,11 +48,8 @@ struct MatchView {
   int* cell_count;  // [n_pairs][N_CELLS+1] -> start offsets after the scan
   int* cell_fill;   // [n_pairs][N_CELLS]
   int* kp_cell;     // [n_cur] cell of each keypoint or -1
-  float2* s_xy;
-  float* s_ur;
-  int* s_meta;      // octave | cell << 8
-  int* s_idx;       // original (pair-local) index
-  uint4* s_desc;    // 2 x uint4 per keypoint
+  uint4* s_rec;     // packed by cell, 48 B per keypoint: {x, y, uRight, meta} + 32 B descriptor, 16-byte aligned
+                    // meta = idx (16) | cell (12) << 16 | octave (3) << 28 | claimed-on-entry << 31
   // queries
   const int* q_off;
   const uint8_t* q_valid;
@@ -144,13 +141,17 @@ __global__ void k_cell_fill(MatchView v) {
   const int p = find_pair(v.cur_off, v.n_pairs, i);
   const int slot = atomicAdd(&v.cell_fill[(size_t)p * N_CELLS + cell], 1);
   const size_t d = (size_t)v.cur_off[p] + v.cell_count[(size_t)p * (N_CELLS + 1) + cell] + slot;
-  v.s_xy[d] = make_float2(v.cur_xy[2 * (size_t)i], v.cur_xy[2 * (size_t)i + 1]);
-  v.s_ur[d] = v.cur_uright[i];
-  v.s_meta[d] = (int)v.cur_octave[i] | (cell << 8);
-  v.s_idx[d] = i - v.cur_off[p];
+  const unsigned meta = (unsigned)(i - v.cur_off[p]) | ((unsigned)cell << 16) | ((unsigned)(v.cur_octave[i] & 7) << 28) |
+                        (v.cur_claimed[i] ? 0x80000000u : 0u);
+  uint4 h;
+  h.x = __float_as_uint(v.cur_xy[2 * (size_t)i]);
+  h.y = __float_as_uint(v.cur_xy[2 * (size_t)i + 1]);
+  h.z = __float_as_uint(v.cur_uright[i]);
+  h.w = meta;
   const uint4* src = reinterpret_cast<const uint4*>(v.cur_desc + 32 * (size_t)i);
-  v.s_desc[2 * d] = src[0];
-  v.s_desc[2 * d + 1] = src[1];
+  v.s_rec[3 * d] = h;
+  v.s_rec[3 * d + 1] = src[0];
+  v.s_rec[3 * d + 2] = src[1];
 }
 
 // packed candidate key: lexicographic (distance, grid traversal order) == integer order
@@ -259,30 +260,32 @@ __device__ __forceinline__ int scan_window(const MatchView& v, int q, int p, con
   const size_t base = (size_t)v.cur_off[p];
   const int* own = v.owner + base;
   int ncand = 0;
+  const uint4* rec = v.s_rec + 3 * base;
   for (int ix = x0; ix <= x1; ix++) {
     const int s0 = cstart[ix * GRID_ROWS + y0], s1 = cstart[ix * GRID_ROWS + y1 + 1];
+#pragma unroll 2
     for (int s = s0; s < s1; s++) {
-      const int meta = v.s_meta[base + s];
-      const int oct = meta & 0xFF;
+      const uint4 h = rec[3 * (size_t)s];
+      const uint4 b0 = rec[3 * (size_t)s + 1], b1 = rec[3 * (size_t)s + 2];
+      const unsigned meta = h.w;
+      if (meta & 0x80000000u) continue;  // claimed on entry
+      const int oct = (meta >> 28) & 7;
       if (check_levels) {
         if (oct < w.minLevel) continue;
         if (w.maxLevel >= 0 && oct > w.maxLevel) continue;
       }
-      const float2 xy = v.s_xy[base + s];
-      const float dx = __fsub_rn(xy.x, w.x), dy = __fsub_rn(xy.y, w.y);
+      const float dx = __fsub_rn(__uint_as_float(h.x), w.x), dy = __fsub_rn(__uint_as_float(h.y), w.y);
       if (!(fabsf(dx) < w.r && fabsf(dy) < w.r)) continue;
-      const int idx = v.s_idx[base + s];
-      const int ow = own[idx];
-      if (ow < 0 || (excl_below >= 0 && ow < excl_below)) continue;  // claimed on entry / by an earlier accepted query
-      const float ur = v.s_ur[base + s];
+      const int idx = meta & 0xFFFF;
+      if (excl_below >= 0 && own[idx] < excl_below) continue;  // owned by an earlier accepted query
+      const float ur = __uint_as_float(h.z);
       if (ur > 0) {
         const float er = fabsf(__fsub_rn(w.urq, ur));
         if (er > w.r) continue;
       }
-      const uint4 b0 = v.s_desc[2 * (base + s)], b1 = v.s_desc[2 * (base + s) + 1];
       const int d = popc256(a0, a1, b0, b1);
       ncand++;
-      unsigned long long k = pack_key(d, meta >> 8, idx, oct);
+      unsigned long long k = pack_key(d, (meta >> 16) & 0xFFF, idx, oct);
       if (k < t[3]) {
         t[3] = k;
         if (t[3] < t[2]) { const unsigned long long u = t[2]; t[2] = t[3]; t[3] = u; }
@@ -498,11 +501,7 @@ static int match_alloc_common(LldCtx* c, MatchView& v) {
   UPC(v.cell_count, int, nullptr, (size_t)v.n_pairs * (N_CELLS + 1));
   UPC(v.cell_fill, int, nullptr, (size_t)v.n_pairs * N_CELLS);
   UPC(v.kp_cell, int, nullptr, v.n_cur);
-  UPC(v.s_xy, float2, nullptr, v.n_cur);
-  UPC(v.s_ur, float, nullptr, v.n_cur);
-  UPC(v.s_meta, int, nullptr, v.n_cur);
-  UPC(v.s_idx, int, nullptr, v.n_cur);
-  UPC(v.s_desc, uint4, nullptr, 2 * (size_t)v.n_cur);
+  UPC(v.s_rec, uint4, nullptr, 3 * (size_t)v.n_cur);
   UPC(v.owner, int, nullptr, v.n_cur);
   UPC(v.q_best, int, nullptr, v.n_q);
   UPC(v.q_dist, int, nullptr, v.n_q);
