@@ -31,6 +31,7 @@ struct BaState {
   int max_n = 0;       // largest reduced system dimension over the windows
   int max_nnb = 0;
   size_t n_nb_total = 0;
+  size_t env_smem = 0;
   bool global_mode = false;
   const double* d_kf_Tcw_in = nullptr;
   const double* d_pt_in = nullptr;
@@ -102,7 +103,8 @@ void par_for(int n, F f) {
 }  // namespace
 
 // Flatten + index the problem on the host, upload, initialise device state.
-static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int log_stride) {
+static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int log_stride,
+                     const lld_ba_problem* full = nullptr /* multi-rank: whole problem, for the rank-invariant structure */) {
   if (!c->ba) c->ba = new BaState();
   BaState* S = c->ba;
   *S = BaState();
@@ -257,16 +259,19 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
       for (size_t a = 0; a < gl.size(); a++)
         for (size_t b = a; b < gl.size(); b++) nbs[gl[a]].push_back(gl[b]);
     };
-    for (int i = 0; i < n_pt; i++) {
+    // every rank derives the block pattern from the WHOLE problem (single window: kf index == local index)
+    const lld_ba_problem* sp = full ? full : p;
+    const int sn_pt = sp->pt_off[1], sn_ln = sp->ln_off[1];
+    for (int i = 0; i < sn_pt; i++) {
       gs.clear();
-      for (int e = p->pt_obs_off[i]; e < p->pt_obs_off[i + 1]; e++)
-        if (kf_g[pe_kf[e]] >= 0) gs.push_back(kf_g[pe_kf[e]]);
+      for (int e = sp->pt_obs_off[i]; e < sp->pt_obs_off[i + 1]; e++)
+        if (kf_g[sp->pt_obs_kf[e]] >= 0) gs.push_back(kf_g[sp->pt_obs_kf[e]]);
       add(gs);
     }
-    for (int i = 0; i < n_ln; i++) {
+    for (int i = 0; i < sn_ln; i++) {
       gs.clear();
-      for (int e = p->ln_obs_off[i]; e < p->ln_obs_off[i + 1]; e++)
-        if (kf_g[lc_kf[e]] >= 0) gs.push_back(kf_g[lc_kf[e]]);
+      for (int e = sp->ln_obs_off[i]; e < sp->ln_obs_off[i + 1]; e++)
+        if (kf_g[sp->ln_obs_kf[e]] >= 0) gs.push_back(kf_g[sp->ln_obs_kf[e]]);
       add(gs);
     }
     for (int g = 0; g < nG; g++) {
@@ -469,13 +474,41 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     const int nnb = nb_off[ch_g[ch] + 1] - nb_off[ch_g[ch]];
     chS_total += 36LL * nnb + 6;
   }
+  // envelope of the reduced camera system (global BA with a system too large for the dense solvers)
+  std::vector<int> env_first(1, 0), env_blk_last(1, 0);
+  std::vector<long long> env_rowptr(2, 0);
+  v.env_mode = 0;
+  if (global_mode && S->max_n > SMEM_SOLVE_MAX_N) {
+    std::vector<int> fb(nG);
+    for (int g = 0; g < nG; g++) fb[g] = g;
+    for (int a = 0; a < nG; a++)
+      for (int q = nb_off[a]; q < nb_off[a + 1]; q++) fb[nb_g[q]] = std::min(fb[nb_g[q]], a);
+    const int n = 6 * nG;
+    env_first.assign(n, 0); env_rowptr.assign(n + 1, 0); env_blk_last.assign(nG, 0);
+    int maxlen = 1, ph = 6;
+    for (int i = 0; i < n; i++) {
+      env_first[i] = 6 * fb[i / 6];
+      env_rowptr[i + 1] = env_rowptr[i] + (i - env_first[i] + 1);
+      maxlen = std::max(maxlen, i - env_first[i] + 1);
+    }
+    for (int g = 0; g < nG; g++) env_blk_last[g] = g;
+    for (int b = 0; b < nG; b++)
+      for (int k = fb[b]; k <= b; k++) env_blk_last[k] = std::max(env_blk_last[k], b);
+    for (int k = 0; k < nG; k++) ph = std::max(ph, 6 * (env_blk_last[k] - k));
+    v.env_mode = 1; v.env_panel_h = ph; v.env_maxlen = maxlen;
+    S->env_smem = sizeof(double) * (6 * (size_t)ph + 8 + 32 * (size_t)maxlen + (size_t)n) + 64;
+    if (S->env_smem > 220 * 1024) {
+      snprintf(c->err, sizeof(c->err), "global BA: envelope of the reduced system too wide for the on-chip solver (panel %d rows, row %d, n %d)", ph, maxlen, n);
+      return LLD_ERR_UNSUPPORTED;
+    }
+  }
   // global-memory solve scratch for windows too large for shared memory
   std::vector<long long> w_scr(nw, 0);
   long long scr_total = 0;
   for (int w = 0; w < nw; w++) {
     const long long n = 6LL * (w_g0[w + 1] - w_g0[w]);
     w_scr[w] = scr_total;
-    if (S->max_n > SMEM_SOLVE_MAX_N) scr_total += n * n + 8 * n + 8;
+    if (S->max_n > SMEM_SOLVE_MAX_N && !v.env_mode) scr_total += n * n + 8 * n + 8;
   }
 
   stage("chunks");
@@ -553,6 +586,9 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     UP(tmp_m, lns_mask.data(), n_ln); v.lns_mask = tmp_m;
   }
   UP(tmp_l, w_scr.data(), nw); v.w_scratch_off = tmp_l;
+  UP(tmp_i, env_first.data(), env_first.size()); v.env_first = tmp_i;
+  UP(tmp_i, env_blk_last.data(), env_blk_last.size()); v.env_blk_last = tmp_i;
+  UP(tmp_l, env_rowptr.data(), env_rowptr.size()); v.env_rowptr = tmp_l;
   double *d_T, *d_P, *d_L;
   UP(d_T, p->kf_Tcw, 12 * (size_t)n_kf);
   UP(d_P, p->pt_xyz, 3 * (size_t)n_pt);
@@ -591,6 +627,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   DEV(v.chi2_log, double, (size_t)nw * log_stride); DEV(v.lambda_log, double, (size_t)nw * log_stride);
   DEV(v.trials_log, int, (size_t)nw * log_stride); DEV(v.iter_done, int, 2 * (size_t)nw);
   DEV(v.solve_scratch, double, (size_t)scr_total);
+  DEV(v.env_A, double, (size_t)env_rowptr.back());
   DEV(S->d_out_kf, double, 12 * (size_t)n_kf); DEV(S->d_out_pt, double, 3 * (size_t)n_pt);
   DEV(S->d_out_ln, double, 6 * (size_t)n_ln);
   DEV(S->d_pt_bad, uint8_t, n_pe); DEV(S->d_ln_bad, uint8_t, 2 * (size_t)n_lc);
@@ -723,7 +760,10 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
     }
   }
   if (S->global_mode) { int r = ba_allreduce_rows(c); if (r) return r; }
-  if (S->max_n <= SMEM_SOLVE_MAX_N) { int r = launch_solve<true>(c, v, S->max_n); if (r) return r; }
+  if (v.env_mode) {
+    LLD_CUDA(c, cudaFuncSetAttribute(k_solve_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->env_smem));
+    LLD_LAUNCH(c, k_solve_env, 1, 1024, S->env_smem, v);
+  } else if (S->max_n <= SMEM_SOLVE_MAX_N) { int r = launch_solve<true>(c, v, S->max_n); if (r) return r; }
   else { int r = launch_solve<false>(c, v, S->max_n); if (r) return r; }
   if (v.n_pt) LLD_LAUNCH(c, k_backsub_points, gp, LM_TPB, 0, v);
   if (v.n_ln) LLD_LAUNCH(c, k_backsub_lines, gl, LM_TPB, 0, v);
@@ -894,13 +934,45 @@ extern "C" int lld_ba_global(void* ctx, const lld_ba_problem* p, int n_iter, con
   LldCtx* c = lld_ctx_cast(ctx);
   if (!c || !p || !out) return LLD_ERR_ARG;
   LLD_ARG(c, p->n_win == 1);
+  LLD_CUDA(c, cudaSetDevice(c->device));
   c->launches = 0;
-  int r = lld_ba_upload(ctx, p, 1, n_iter + 2);
+  const int R = c->n_ranks, rk = c->rank;
+  if (R <= 1) {
+    LLD_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    int r = ba_upload(c, p, true, n_iter + 2);
+    if (r) return r;
+    LLD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    r = lld_ba_run_global(ctx, n_iter, stop);
+    if (r) return r;
+    return ba_download(c, p, out, false);
+  }
+  // multi-rank: every rank receives the whole problem and keeps a contiguous block of the landmarks; keyframes are
+  // replicated.  The shard is a view on the caller's arrays with re-based CSR offsets.
+  const int n_pt = p->pt_off[1], n_ln = p->ln_off[1];
+  const int plo = (int)((long long)n_pt * rk / R), phi = (int)((long long)n_pt * (rk + 1) / R);
+  const int llo = (int)((long long)n_ln * rk / R), lhi = (int)((long long)n_ln * (rk + 1) / R);
+  const int pe0 = p->pt_obs_off[plo], lc0 = p->ln_obs_off[llo];
+  std::vector<int32_t> poff(phi - plo + 1), loff(lhi - llo + 1);
+  for (int i = 0; i <= phi - plo; i++) poff[i] = p->pt_obs_off[plo + i] - pe0;
+  for (int i = 0; i <= lhi - llo; i++) loff[i] = p->ln_obs_off[llo + i] - lc0;
+  const int32_t pto[2] = {0, phi - plo}, lno[2] = {0, lhi - llo};
+  lld_ba_problem sh = *p;
+  sh.pt_off = pto; sh.ln_off = lno;
+  sh.pt_xyz = p->pt_xyz + 3 * (size_t)plo; sh.pt_obs_off = poff.data();
+  sh.pt_obs_kf = p->pt_obs_kf + pe0; sh.pt_obs_uvr = p->pt_obs_uvr + 3 * (size_t)pe0; sh.pt_obs_info = p->pt_obs_info + pe0;
+  sh.ln_x0_dir = p->ln_x0_dir + 6 * (size_t)llo; sh.ln_obs_off = loff.data();
+  sh.ln_obs_kf = p->ln_obs_kf + lc0; sh.ln_obs_left = p->ln_obs_left + 4 * (size_t)lc0; sh.ln_obs_right = p->ln_obs_right + 4 * (size_t)lc0;
+  sh.ln_obs_info = p->ln_obs_info + 2 * (size_t)lc0; sh.ln_obs_stereo = p->ln_obs_stereo + lc0;
+  lld_ba_result so = *out;
+  so.pt_xyz = out->pt_xyz + 3 * (size_t)plo; so.ln_x0_dir = out->ln_x0_dir + 6 * (size_t)llo;
+  so.pt_obs_bad = out->pt_obs_bad + pe0; so.ln_obs_bad = out->ln_obs_bad + 2 * (size_t)lc0; so.ln_removed = out->ln_removed + llo;
+  LLD_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+  int r = ba_upload(c, &sh, true, n_iter + 2, p);
   if (r) return r;
   LLD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   r = lld_ba_run_global(ctx, n_iter, stop);
   if (r) return r;
-  return ba_download(c, p, out, false);
+  return ba_download(c, &sh, &so, false);
 }
 
 void lld_ba_state_free(BaState* s) { delete s; }

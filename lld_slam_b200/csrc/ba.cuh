@@ -162,6 +162,15 @@ struct BaView {
   // dense solve scratch (global-memory path) per window
   double* solve_scratch;
   const long long* w_scratch_off;
+  // envelope (profile) storage of the reduced camera system for large single problems (global BA):
+  // scalar row i holds columns [env_first[i], i] at env_A + env_rowptr[i]
+  int env_mode;
+  int env_panel_h;            // max number of scalar rows below a pivot block that touch it
+  int env_maxlen;             // longest row
+  const int* env_first;       // [n]
+  const long long* env_rowptr;// [n+1]
+  const int* env_blk_last;    // [n/6] last block row whose envelope reaches block column k
+  double* env_A;
   BaParams prm;
 };
 

@@ -971,6 +971,195 @@ __device__ bool ldlt_solve_cta(double* A, int n, int ld, double* b /*in: rhs, ou
   return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// envelope (skyline) LDL^T for the global-BA reduced camera system: same 6-column supernode algorithm as
+// ldlt_solve_cta, restricted to the profile  first[i] <= j <= i  (no fill outside the envelope).  One CTA, matrix in
+// global memory (L2 resident), panel / rhs scratch in shared memory.  Stands in for Eigen::SimplicialLDLT
+// (Thirdparty/g2o/g2o/solvers/linear_solver_eigen.h:94-124).
+// ------------------------------------------------------------------------------------------------
+#define ENV_A(i, j) A[rowptr[i] + ((j) - first[i])]
+constexpr int ENV_BS_ROWS = 32;  // rows staged per chunk in the backward substitution
+__global__ void __launch_bounds__(1024) k_solve_env(BaView v) {
+  extern __shared__ double esm[];
+  const int w = 0;
+  if (v.w_phase[w] == PH_DONE) return;
+  const int g0 = v.w_g0[w], nf = v.w_g0[w + 1] - g0;
+  const int n = 6 * nf;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  const int ph = v.env_panel_h;
+  double* Tt = esm;                    // [6][ph]
+  double* zb = esm + 6 * (size_t)ph;   // [6]
+  double* stage = zb + 8;              // [ENV_BS_ROWS][maxlen]
+  double* b = stage + (size_t)ENV_BS_ROWS * v.env_maxlen;  // rhs / solution in shared memory, n doubles
+  __shared__ int flag;
+  __shared__ double red[32];
+  double* A = v.env_A;
+  const long long* rowptr = v.env_rowptr;
+  const int* first = v.env_first;
+  const int sel = v.w_sel[w];
+  // assemble: zero the envelope, scatter the block rows (upper blocks (a,b) -> lower entries), rhs
+  const long long nnz = rowptr[n];
+  for (long long i = tid; i < nnz; i += nt) A[i] = 0.0;
+  if (tid == 0) flag = 1;
+  __syncthreads();
+  for (int a = 0; a < nf; a++) {
+    const int g = g0 + a;
+    const int nb0 = v.nb_off[g], nnb = v.nb_off[g + 1] - nb0;
+    for (int idx = tid; idx < nnb * 36; idx += nt) {
+      const int j = idx / 36, rc = idx - 36 * j, r = rc / 6, c = rc - 6 * r;
+      const int bb = v.nb_g[nb0 + j] - g0;
+      if (j == 0 && c < r) continue;
+      ENV_A(6 * bb + c, 6 * a + r) = v.S_blk[36 * (size_t)(nb0 + j) + rc];
+    }
+  }
+  for (int i = tid; i < n; i += nt) b[i] = v.g_bs[6 * (size_t)g0 + i];
+  __syncthreads();
+  bool ok = true;
+  for (int k0 = 0; k0 < n && ok; k0 += 6) {
+    const int kb = k0 / 6;
+    const int i_end = 6 * (v.env_blk_last[kb] + 1);
+    if (tid == 0) {
+      double M[6][6], zz[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        zz[i] = b[k0 + i];
+#pragma unroll
+        for (int j = 0; j < 6; j++) M[i][j] = (j <= i) ? ENV_A(k0 + i, k0 + j) : 0.0;
+      }
+      bool okk = true;
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        double d = M[j][j];
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+          if (q < j) d -= M[j][q] * M[j][q] * M[q][q];
+        if (!(d != 0.0) || !isfinite(d)) okk = false;
+        M[j][j] = d;
+        const double id = 1.0 / d;
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+          if (i > j) {
+            double s2 = M[i][j];
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+              if (q < j) s2 -= M[i][q] * M[j][q] * M[q][q];
+            M[i][j] = s2 * id;
+          }
+      }
+      if (!okk) flag = 0;
+      else {
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+          for (int q = 0; q < 6; q++)
+            if (q < i) zz[i] -= M[i][q] * zz[q];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          zb[i] = zz[i];
+          b[k0 + i] = zz[i];
+#pragma unroll
+          for (int j = 0; j < 6; j++)
+            if (j <= i) ENV_A(k0 + i, k0 + j) = M[i][j];
+        }
+      }
+    }
+    __syncthreads();
+    if (!flag) { ok = false; break; }
+    // panel rows
+    for (int i = k0 + 6 + tid; i < i_end; i += nt) {
+      double t6[6] = {0, 0, 0, 0, 0, 0};
+      if (first[i] <= k0) {
+        double* row = &ENV_A(i, k0);
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          double s2 = row[c];
+#pragma unroll
+          for (int q = 0; q < 6; q++)
+            if (q < c) s2 -= t6[q] * ENV_A(k0 + c, k0 + q);
+          t6[c] = s2;
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) row[c] = t6[c] / ENV_A(k0 + c, k0 + c);
+      }
+#pragma unroll
+      for (int c = 0; c < 6; c++) Tt[(size_t)c * ph + (i - k0 - 6)] = t6[c];
+    }
+    __syncthreads();
+    for (int i = k0 + 6 + wid; i < i_end; i += nw) {
+      if (first[i] > k0) continue;
+      double* row = A + rowptr[i] - first[i];
+      const double l0 = row[k0], l1 = row[k0 + 1], l2 = row[k0 + 2], l3 = row[k0 + 3], l4 = row[k0 + 4], l5 = row[k0 + 5];
+      const int jb = max(k0 + 6, first[i]);
+      for (int j = jb + lane; j <= i; j += 32) {
+        const int q = j - k0 - 6;
+        row[j] -= l0 * Tt[q] + l1 * Tt[ph + q] + l2 * Tt[2 * (size_t)ph + q] + l3 * Tt[3 * (size_t)ph + q] + l4 * Tt[4 * (size_t)ph + q] +
+                  l5 * Tt[5 * (size_t)ph + q];
+      }
+      if (lane == 0) b[i] -= l0 * zb[0] + l1 * zb[1] + l2 * zb[2] + l3 * zb[3] + l4 * zb[4] + l5 * zb[5];
+    }
+    __syncthreads();
+  }
+  if (ok) {
+    for (int i = tid; i < n; i += nt) b[i] /= ENV_A(i, i);
+    __syncthreads();
+    // backward substitution, rows staged through shared memory in chunks (one warp does the dependent chain)
+    const int ml = v.env_maxlen;
+    for (int j1 = n; j1 > 0; j1 -= ENV_BS_ROWS) {
+      const int j0 = max(0, j1 - ENV_BS_ROWS);
+      for (int r = j0 + wid; r < j1; r += nw) {
+        const int len = r - first[r];
+        for (int q = lane; q < len; q += 32) stage[(size_t)(r - j0) * ml + q] = A[rowptr[r] + q];
+      }
+      __syncthreads();
+      if (wid == 0) {
+        for (int j = j1 - 1; j >= j0; j--) {
+          const double xj = b[j];
+          const int f = first[j], len = j - f;
+          for (int q = lane; q < len; q += 32) b[f + q] -= stage[(size_t)(j - j0) * ml + q] * xj;
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < n; i += nt) v.g_x[6 * (size_t)g0 + i] = b[i];
+  }
+  __syncthreads();
+  for (int k = v.kf_off[w] + tid; k < v.kf_off[w + 1]; k += nt) {
+    const int g = v.kf_g[k];
+    double qt[7];
+    const double* src = v.pose_qt[sel] + 7 * (size_t)k;
+    if (g >= 0 && v.g_nact[g] > 0) {
+      pose_oplus(src, v.g_x + 6 * (size_t)g, qt);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 7; q++) qt[q] = src[q];
+    }
+    double Rt[12];
+    pose_to_Rt(qt, Rt);
+    double* dq = v.pose_qt[sel ^ 1] + 7 * (size_t)k;
+    double* dr = v.pose_Rt[sel ^ 1] + 12 * (size_t)k;
+#pragma unroll
+    for (int q = 0; q < 7; q++) dq[q] = qt[q];
+#pragma unroll
+    for (int q = 0; q < 12; q++) dr[q] = Rt[q];
+  }
+  const double lam = v.w_lambda[w];
+  double sc = 0;
+  for (int i = tid; i < n; i += nt) {
+    const int g = g0 + i / 6;
+    if (v.g_nact[g] == 0) continue;
+    const double x = v.g_x[6 * (size_t)g0 + i];
+    sc += x * (lam * x + v.g_bp[6 * (size_t)g0 + i]);
+  }
+  sc = block_sum(sc, red);
+  if (tid == 0) {
+    v.w_scale_p[w] = sc;
+    v.w_ok[w] = ok ? 1 : 0;
+  }
+}
+#undef ENV_A
+
 // one CTA per window: assemble the dense reduced camera system from the block rows, factor, solve, apply the
 // pose update T <- exp(x) T into the trial buffer and accumulate the pose part of computeScale().
 template <bool SMEM>

@@ -210,3 +210,11 @@ def test_no_cpu_fallback():
     from lld_slam_b200 import capi
     with pytest.raises(RuntimeError):
         capi.Context(12345)
+
+
+def test_global_ba_banded_envelope(gpu_ctx):
+    """a chain of 200 keyframes: reduced system 1194 x 1194 with a band envelope, on-device skyline LDL^T."""
+    p = synth.make_global_ba(200, 20000, 4000, 19)
+    g = api.ba_global(p, 6, impl="gpu", ctx=gpu_ctx)
+    o = api.ba_global(p, 6, impl="oracle")
+    check_ba(g, o, "gba banded")
