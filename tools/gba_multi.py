@@ -21,6 +21,7 @@ ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--robust", action="store_true")
+ap.add_argument("--profile", action="store_true")
 a = ap.parse_args()
 
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); lr = int(os.environ.get("LOCAL_RANK", "0"))
@@ -54,6 +55,14 @@ for rep in range(a.reps):
         dist.barrier()
     times.append(time.perf_counter() - t0)
 h2d, comp, d2h = ctx.last_timing()
+prof = None
+if a.profile:
+    import bench
+    d = bench.bind_resident(lib)
+    d.lld_ctx_profile(ctx.handle, 1)
+    api.ba_global(p, a.iters, impl="gpu", ctx=ctx)
+    prof = bench.profile_report(d, ctx)
+    d.lld_ctx_profile(ctx.handle, 0)
 res = {"n_gpus": world, "kf": a.kf, "pts": a.pts, "lines": a.lines, "point_edges": n_pe, "line_cells": n_lc,
        "iters_done": int(g["n_iter_done"][0, 0]), "trials": int(g["trials_log"].sum()),
        "wall_s_best": min(times), "device_compute_ms": comp, "chi2_first": float(g["chi2_log"][0, 0]),
@@ -78,6 +87,8 @@ if a.check and rank == 0:
                     "pose_t_max": float(np.abs(g["kf_Tcw"][:, 9:] - o["kf_Tcw"][:, 9:]).max()),
                     "pose_R_max": float(np.abs(g["kf_Tcw"][:, :9] - o["kf_Tcw"][:, :9]).max()),
                     "pt_max": float(np.abs(g["pt_xyz"] - o["pt_xyz"]).max())}
+if prof is not None:
+    res["kernels_us_per_launch"] = {k: round(1e3 * v["ms"] / max(v["n"], 1), 1) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
 if rank == 0:
     print(json.dumps(res))
 if dist is not None:
