@@ -31,7 +31,8 @@ struct BaState {
   int max_n = 0;       // largest reduced system dimension over the windows
   int max_nnb = 0;
   size_t n_nb_total = 0;
-  size_t env_smem = 0;
+  size_t env_smem = 0, band_smem = 0;
+  bool use_band = false;
   bool global_mode = false;
   const double* d_kf_Tcw_in = nullptr;
   const double* d_pt_in = nullptr;
@@ -475,7 +476,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     chS_total += 36LL * nnb + 6;
   }
   // envelope of the reduced camera system (global BA with a system too large for the dense solvers)
-  std::vector<int> env_first(1, 0), env_blk_last(1, 0);
+  std::vector<int> env_first(1, 0), env_blk_last(1, 0), lo_off(2, 0), lo_col(1, 0), lo_src(1, 0);
   std::vector<long long> env_rowptr(2, 0);
   v.env_mode = 0;
   if (global_mode && S->max_n > SMEM_SOLVE_MAX_N) {
@@ -496,8 +497,24 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
       for (int k = fb[b]; k <= b; k++) env_blk_last[k] = std::max(env_blk_last[k], b);
     for (int k = 0; k < nG; k++) ph = std::max(ph, 6 * (env_blk_last[k] - k));
     v.env_mode = 1; v.env_panel_h = ph; v.env_maxlen = maxlen;
+    // banded sliding-window variant: block half-bandwidth and lower-block gather lists
+    int B = 1;
+    for (int g = 0; g < nG; g++) B = std::max(B, g - fb[g]);
+    v.band_B = B;
+    S->band_smem = sizeof(double) * ((size_t)(6 * (B + 2)) * (6 * (B + 2)) + 36 * (size_t)B + 8 + 6 * (B + 2) + 36 * (size_t)(B + 1) + 6) + 64;
+    S->use_band = S->band_smem <= 220 * 1024 && (B + 1) * 36 + 6 <= 2048;
+    lo_off.assign(nG + 1, 0);
+    for (int a = 0; a < nG; a++)
+      for (int q = nb_off[a]; q < nb_off[a + 1]; q++) lo_off[nb_g[q] + 1]++;
+    for (int g = 0; g < nG; g++) lo_off[g + 1] += lo_off[g];
+    lo_col.assign(std::max(lo_off[nG], 1), 0); lo_src.assign(std::max(lo_off[nG], 1), 0);
+    {
+      std::vector<int> cur(lo_off.begin(), lo_off.end() - 1);
+      for (int a = 0; a < nG; a++)
+        for (int q = nb_off[a]; q < nb_off[a + 1]; q++) { const int r = nb_g[q]; lo_col[cur[r]] = a; lo_src[cur[r]++] = q; }
+    }
     S->env_smem = sizeof(double) * (6 * (size_t)ph + 8 + 32 * (size_t)maxlen + (size_t)n) + 64;
-    if (S->env_smem > 220 * 1024) {
+    if (!S->use_band && S->env_smem > 220 * 1024) {
       snprintf(c->err, sizeof(c->err), "global BA: envelope of the reduced system too wide for the on-chip solver (panel %d rows, row %d, n %d)", ph, maxlen, n);
       return LLD_ERR_UNSUPPORTED;
     }
@@ -589,6 +606,9 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   UP(tmp_i, env_first.data(), env_first.size()); v.env_first = tmp_i;
   UP(tmp_i, env_blk_last.data(), env_blk_last.size()); v.env_blk_last = tmp_i;
   UP(tmp_l, env_rowptr.data(), env_rowptr.size()); v.env_rowptr = tmp_l;
+  UP(tmp_i, lo_off.data(), lo_off.size()); v.lo_off = tmp_i;
+  UP(tmp_i, lo_col.data(), lo_col.size()); v.lo_col = tmp_i;
+  UP(tmp_i, lo_src.data(), lo_src.size()); v.lo_src = tmp_i;
   double *d_T, *d_P, *d_L;
   UP(d_T, p->kf_Tcw, 12 * (size_t)n_kf);
   UP(d_P, p->pt_xyz, 3 * (size_t)n_pt);
@@ -622,12 +642,20 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   DEV(v.w_maxit, int, nw); DEV(v.w_nbad, int, nw); DEV(v.w_ok, int, nw); DEV(v.w_nlog, int, nw);
   DEV(v.w_lambda, double, nw); DEV(v.w_ni, double, nw); DEV(v.w_curchi, double, nw); DEV(v.w_inichi, double, nw);
   DEV(v.w_scale_p, double, nw); DEV(v.w_red_sum, double, 4 * (size_t)nw); DEV(v.w_red_max, double, nw);
+  {
+    int max_lm = 0;
+    for (int w = 0; w < nw; w++) max_lm = std::max(max_lm, (p->pt_off[w + 1] - p->pt_off[w]) + (p->ln_off[w + 1] - p->ln_off[w]));
+    v.n_slices = std::max(1, std::min(128, max_lm / 16384));
+  }
+  DEV(v.w_part, double, 4 * (size_t)nw * v.n_slices);
   DEV(v.n_active_win, int, 1);
   v.log_stride = log_stride;
   DEV(v.chi2_log, double, (size_t)nw * log_stride); DEV(v.lambda_log, double, (size_t)nw * log_stride);
   DEV(v.trials_log, int, (size_t)nw * log_stride); DEV(v.iter_done, int, 2 * (size_t)nw);
   DEV(v.solve_scratch, double, (size_t)scr_total);
-  DEV(v.env_A, double, (size_t)env_rowptr.back());
+  DEV(v.env_A, double, S->use_band ? 1 : (size_t)env_rowptr.back());
+  DEV(v.band_L, double, S->use_band ? (size_t)nG * (v.band_B + 1) * 36 : 1);
+  DEV(v.band_z, double, S->use_band ? 6 * (size_t)nG : 1);
   DEV(S->d_out_kf, double, 12 * (size_t)n_kf); DEV(S->d_out_pt, double, 3 * (size_t)n_pt);
   DEV(S->d_out_ln, double, 6 * (size_t)n_ln);
   DEV(S->d_pt_bad, uint8_t, n_pe); DEV(S->d_ln_bad, uint8_t, 2 * (size_t)n_lc);
@@ -728,12 +756,14 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   if (v.n_ln) LLD_LAUNCH(c, k_lin_lines, gl, LM_TPB, 0, v);
   if (v.n_chunks) LLD_LAUNCH(c, k_lin_poses, v.n_chunks, LM_TPB, 0, v);
   const bool multi = S->global_mode && c->n_ranks > 1;
-  if (!multi) {
+  const bool fused = !multi && v.n_slices == 1;
+  if (fused) {
     LLD_LAUNCH(c, k_begin_fused, v.n_win, 256, 0, v);
   } else {
     if (v.n_free_total) LLD_LAUNCH(c, k_reduce_pose, cdiv(v.n_free_total * 28, 128), 128, 0, v);
-    LLD_LAUNCH(c, k_reduce_lin, v.n_win, 256, 0, v);
-    { int r = ba_allreduce_lin(c); if (r) return r; }
+    LLD_LAUNCH(c, k_reduce_lin, v.n_win * v.n_slices, 256, 0, v);
+    LLD_LAUNCH(c, k_sum_lin, cdiv(v.n_win, 64), 64, 0, v);
+    if (multi) { int r = ba_allreduce_lin(c); if (r) return r; }
     LLD_LAUNCH(c, k_begin, cdiv(v.n_win, 64), 64, 0, v);
   }
   if (v.n_pt) LLD_LAUNCH(c, k_schur_points, gp, LM_TPB, 0, v);
@@ -760,18 +790,22 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
     }
   }
   if (S->global_mode) { int r = ba_allreduce_rows(c); if (r) return r; }
-  if (v.env_mode) {
+  if (v.env_mode && S->use_band) {
+    LLD_CUDA(c, cudaFuncSetAttribute(k_solve_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->band_smem));
+    LLD_LAUNCH(c, k_solve_band, 1, 1024, S->band_smem, v);
+  } else if (v.env_mode) {
     LLD_CUDA(c, cudaFuncSetAttribute(k_solve_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->env_smem));
     LLD_LAUNCH(c, k_solve_env, 1, 1024, S->env_smem, v);
   } else if (S->max_n <= SMEM_SOLVE_MAX_N) { int r = launch_solve<true>(c, v, S->max_n); if (r) return r; }
   else { int r = launch_solve<false>(c, v, S->max_n); if (r) return r; }
   if (v.n_pt) LLD_LAUNCH(c, k_backsub_points, gp, LM_TPB, 0, v);
   if (v.n_ln) LLD_LAUNCH(c, k_backsub_lines, gl, LM_TPB, 0, v);
-  if (!multi) {
+  if (fused) {
     LLD_LAUNCH(c, k_decide_fused, v.n_win, 256, 0, v, round, stop_now);
   } else {
-    LLD_LAUNCH(c, k_reduce_trial, v.n_win, 256, 0, v);
-    { int r = ba_allreduce_trial(c); if (r) return r; }
+    LLD_LAUNCH(c, k_reduce_trial, v.n_win * v.n_slices, 256, 0, v);
+    LLD_LAUNCH(c, k_sum_trial, cdiv(v.n_win, 64), 64, 0, v);
+    if (multi) { int r = ba_allreduce_trial(c); if (r) return r; }
     LLD_LAUNCH(c, k_decide, cdiv(v.n_win, 64), 64, 0, v, round, stop_now);
   }
   LLD_CUDA(c, cudaGetLastError());

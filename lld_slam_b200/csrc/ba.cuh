@@ -152,6 +152,8 @@ struct BaView {
   double* w_scale_p;
   double* w_red_sum;  // [n_win][4] reduced scalars (chi2, scale_l, n_active_landmarks, spare) — NCCL sum in multi-GPU
   double* w_red_max;  // [n_win]    max |diag Hll| — NCCL max in multi-GPU
+  int n_slices;       // CTAs per window in the two-level landmark reductions (large problems / multi-rank)
+  double* w_part;     // [n_win][n_slices][4]
   int* n_active_win;  // [1]
   // logs
   int log_stride;
@@ -171,6 +173,13 @@ struct BaView {
   const long long* env_rowptr;// [n+1]
   const int* env_blk_last;    // [n/6] last block row whose envelope reaches block column k
   double* env_A;
+  // banded sliding-window solver (global BA): block half-bandwidth, lower-block gather lists, column panels of L
+  int band_B;                 // max over block rows of (row - first block column)
+  const int* lo_off;          // [n_free_total+1] lower blocks (row r, col c <= r) of the reduced system
+  const int* lo_col;          // column block c
+  const int* lo_src;          // index of block (c, r) in S_blk (to be read transposed)
+  double* band_L;             // [n_free_total][(band_B+1)][36] column panels: block 0 = L_kk (strict lower) + D (diagonal)
+  double* band_z;             // [6 * n_free_total] forward-substituted rhs
   BaParams prm;
 };
 

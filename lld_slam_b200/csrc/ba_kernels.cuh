@@ -412,18 +412,22 @@ __global__ void k_reduce_pose(BaView v) {
   else v.g_nact[g] = (int)(s + 0.5);
 }
 
-// per-window reduction of the landmark scalars written by the linearisation (chi2, max diag, #active)
+// two-level per-window reduction of the landmark scalars written by the linearisation (chi2, max diag, #active):
+// n_slices CTAs per window write partials, k_sum_lin adds them in fixed order
 __global__ void __launch_bounds__(256) k_reduce_lin(BaView v) {
-  const int w = blockIdx.x;
+  const int w = blockIdx.x / v.n_slices, sl = blockIdx.x % v.n_slices;
   if (v.w_phase[w] != PH_LIN) return;
   __shared__ double sm[32];
   double chi = 0, mx = 0, na = 0;
-  for (int p = v.pt_off[w] + threadIdx.x; p < v.pt_off[w + 1]; p += blockDim.x) {
+  const int np = v.pt_off[w + 1] - v.pt_off[w], nl = v.ln_off[w + 1] - v.ln_off[w];
+  const int p0 = v.pt_off[w] + (int)((long long)np * sl / v.n_slices), p1 = v.pt_off[w] + (int)((long long)np * (sl + 1) / v.n_slices);
+  const int l0 = v.ln_off[w] + (int)((long long)nl * sl / v.n_slices), l1 = v.ln_off[w] + (int)((long long)nl * (sl + 1) / v.n_slices);
+  for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
     chi += v.lm_chi2lin[p];
     mx = fmax(mx, v.lm_maxdiag[p]);
     na += v.lm_active[p] ? 1.0 : 0.0;
   }
-  for (int l = v.ln_off[w] + threadIdx.x; l < v.ln_off[w + 1]; l += blockDim.x) {
+  for (int l = l0 + threadIdx.x; l < l1; l += blockDim.x) {
     chi += v.lm_chi2lin[v.n_pt + l];
     mx = fmax(mx, v.lm_maxdiag[v.n_pt + l]);
     na += v.lm_active[v.n_pt + l] ? 1.0 : 0.0;
@@ -432,11 +436,22 @@ __global__ void __launch_bounds__(256) k_reduce_lin(BaView v) {
   na = block_sum(na, sm);
   mx = block_max(mx, sm);
   if (threadIdx.x == 0) {
-    v.w_red_sum[4 * w + 0] = chi;
-    v.w_red_sum[4 * w + 1] = 0.0;
-    v.w_red_sum[4 * w + 2] = na;
-    v.w_red_max[w] = mx;
+    double* o = v.w_part + 4 * (size_t)blockIdx.x;
+    o[0] = chi; o[1] = mx; o[2] = na;
   }
+}
+__global__ void k_sum_lin(BaView v) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= v.n_win || v.w_phase[w] != PH_LIN) return;
+  double chi = 0, mx = 0, na = 0;
+  for (int s2 = 0; s2 < v.n_slices; s2++) {
+    const double* o = v.w_part + 4 * ((size_t)w * v.n_slices + s2);
+    chi += o[0]; mx = fmax(mx, o[1]); na += o[2];
+  }
+  v.w_red_sum[4 * w + 0] = chi;
+  v.w_red_sum[4 * w + 1] = 0.0;
+  v.w_red_sum[4 * w + 2] = na;
+  v.w_red_max[w] = mx;
 }
 
 // iteration start: currentChi, iniChi, lambda init at iteration 0 (optimization_algorithm_levenberg.cpp:75-97,166-180)
@@ -1160,6 +1175,242 @@ __global__ void __launch_bounds__(1024) k_solve_env(BaView v) {
 }
 #undef ENV_A
 
+// ------------------------------------------------------------------------------------------------
+// Banded LDL^T with a sliding shared-memory window (global BA).  The reduced camera system of a long trajectory is
+// block-banded (half bandwidth B blocks = longest track); only block rows / columns [k, k+B] are touched while pivot
+// block k is eliminated, so the CTA keeps a circular (B+2)^2-block window in shared memory: per pivot
+//   A: thread 0 factors the 6x6 diagonal block (registers) and forward-solves its rhs,
+//   B: one thread per scalar row of the panel computes T = A_ik L_kk^-T, L = T D^-1; the spare row slot is zeroed,
+//   C: one warp per row applies the rank-6 update; column panel k of L is streamed to HBM; block row k+B+1 is
+//      gathered (transposed upper blocks) into the spare slot.
+// Three barriers per pivot, no global-memory latency on the critical path.  The backward substitution walks the stored
+// column panels with register prefetch of the next panel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_solve_band(BaView v) {
+  extern __shared__ double bsm[];
+  const int w = 0;
+  if (v.w_phase[w] == PH_DONE) return;
+  const int g0 = v.w_g0[w], nf = v.w_g0[w + 1] - g0;
+  const int B = v.band_B, WB = B + 2, LDW = 6 * WB, PB = B + 1;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  double* Wm = bsm;                          // [LDW][LDW]
+  double* Tt = Wm + (size_t)LDW * LDW;       // [6][6B]
+  double* zb = Tt + 36 * (size_t)B;          // [8]
+  double* rw = zb + 8;                       // [LDW] rhs window
+  double* pan = rw + LDW;                    // [PB*36 + 6] panel buffer for the backward pass
+  __shared__ int flag;
+  __shared__ double red[32];
+  const int sel = v.w_sel[w];
+  auto zero_row = [&](int r) {
+    const int s = r % WB;
+    for (int i = tid; i < 6 * LDW; i += nt) Wm[(size_t)(6 * s) * LDW + i] = 0.0;
+  };
+  auto scatter_row = [&](int r) {
+    const int s = r % WB;
+    const int q0 = v.lo_off[g0 + r], q1 = v.lo_off[g0 + r + 1];
+    for (int i = tid; i < (q1 - q0) * 36; i += nt) {
+      const int q = q0 + i / 36, e = i % 36, rr = e / 6, cc = e - 6 * rr;
+      const int c = v.lo_col[q];
+      if (c == r && cc < rr) continue;
+      Wm[(size_t)(6 * s + cc) * LDW + 6 * (c % WB) + rr] = v.S_blk[36 * (size_t)v.lo_src[q] + e];
+    }
+    if (tid < 6) rw[6 * s + tid] = v.g_bs[6 * (size_t)(g0 + r) + tid];
+  };
+  if (tid == 0) flag = 1;
+  for (int i = tid; i < LDW * LDW; i += nt) Wm[i] = 0.0;
+  __syncthreads();
+  for (int r = 0; r < nf && r <= B; r++) scatter_row(r);
+  __syncthreads();
+  bool ok = true;
+  for (int k = 0; k < nf; k++) {
+    const int sk = k % WB;
+    const int kend = min(k + B, nf - 1);
+    // ---- A
+    if (tid == 0) {
+      double M[6][6], zz[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        zz[i] = rw[6 * sk + i];
+#pragma unroll
+        for (int j = 0; j < 6; j++) M[i][j] = (j <= i) ? Wm[(size_t)(6 * sk + i) * LDW + 6 * sk + j] : 0.0;
+      }
+      bool okk = true;
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        double d = M[j][j];
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+          if (q < j) d -= M[j][q] * M[j][q] * M[q][q];
+        if (!(d != 0.0) || !isfinite(d)) okk = false;
+        M[j][j] = d;
+        const double id = 1.0 / d;
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+          if (i > j) {
+            double s2 = M[i][j];
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+              if (q < j) s2 -= M[i][q] * M[j][q] * M[q][q];
+            M[i][j] = s2 * id;
+          }
+      }
+      if (!okk) flag = 0;
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+          if (q < i) zz[i] -= M[i][q] * zz[q];
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        zb[i] = zz[i];
+        v.band_z[6 * (size_t)k + i] = zz[i];
+#pragma unroll
+        for (int j = 0; j < 6; j++)
+          if (j <= i) Wm[(size_t)(6 * sk + i) * LDW + 6 * sk + j] = M[i][j];
+      }
+    }
+    __syncthreads();
+    if (!flag) { ok = false; break; }
+    // ---- B: panel rows + zero the spare slot
+    const int npr = 6 * (kend - k);
+    for (int x = tid; x < npr; x += nt) {
+      const int ib = k + 1 + x / 6, ri = x % 6;
+      double* row = Wm + (size_t)(6 * (ib % WB) + ri) * LDW + 6 * sk;
+      double t6[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        double s2 = row[c];
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+          if (q < c) s2 -= t6[q] * Wm[(size_t)(6 * sk + c) * LDW + 6 * sk + q];
+        t6[c] = s2;
+      }
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        row[c] = t6[c] / Wm[(size_t)(6 * sk + c) * LDW + 6 * sk + c];
+        Tt[(size_t)c * 6 * B + x] = t6[c];
+      }
+    }
+    if (k + B + 1 < nf) zero_row(k + B + 1);
+    __syncthreads();
+    // ---- C: trailing update (one warp per row), column panel to HBM, gather of the incoming block row
+    for (int x = wid; x < npr; x += nw) {
+      const int ib = k + 1 + x / 6, ri = x % 6;
+      double* row = Wm + (size_t)(6 * (ib % WB) + ri) * LDW;
+      const double* lp = row + 6 * sk;
+      const double l0 = lp[0], l1 = lp[1], l2 = lp[2], l3 = lp[3], l4 = lp[4], l5 = lp[5];
+      for (int jj = lane; jj <= x; jj += 32) {
+        const int jb = k + 1 + jj / 6, jc = jj % 6;
+        row[6 * (jb % WB) + jc] -= l0 * Tt[jj] + l1 * Tt[6 * B + jj] + l2 * Tt[12 * B + jj] + l3 * Tt[18 * B + jj] +
+                                   l4 * Tt[24 * B + jj] + l5 * Tt[30 * B + jj];
+      }
+      if (lane == 0) rw[6 * (ib % WB) + ri] -= l0 * zb[0] + l1 * zb[1] + l2 * zb[2] + l3 * zb[3] + l4 * zb[4] + l5 * zb[5];
+    }
+    {
+      double* Lk = v.band_L + (size_t)k * PB * 36;
+      for (int i = tid; i < (kend - k + 1) * 36; i += nt) {
+        const int ib = k + i / 36, e = i % 36, rr = e / 6, cc = e - 6 * rr;
+        Lk[i] = Wm[(size_t)(6 * (ib % WB) + rr) * LDW + 6 * sk + cc];
+      }
+    }
+    if (k + B + 1 < nf) scatter_row(k + B + 1);
+    __syncthreads();
+  }
+  if (ok) {
+    // backward substitution over the stored column panels; x window kept in rw (circular), panel k-1 prefetched
+    double pre[2] = {0, 0};
+    const int plen = PB * 36 + 6;   // panel + z_k
+    auto fetch = [&](int k, double* r2) {
+      // each thread prefetches up to 2 entries of panel k (plen <= 2 * blockDim for B <= 55)
+      for (int u = 0; u < 2; u++) {
+        const int i = tid + u * nt;
+        if (i < PB * 36) r2[u] = v.band_L[(size_t)k * PB * 36 + i];
+        else if (i < plen) r2[u] = v.band_z[6 * (size_t)k + (i - PB * 36)];
+      }
+    };
+    auto commit = [&](const double* r2) {
+      for (int u = 0; u < 2; u++) {
+        const int i = tid + u * nt;
+        if (i < plen) pan[i] = r2[u];
+      }
+    };
+    fetch(nf - 1, pre);
+    commit(pre);
+    __syncthreads();
+    for (int k = nf - 1; k >= 0; k--) {
+      const int kend = min(k + B, nf - 1);
+      if (k > 0) fetch(k - 1, pre);
+      // y_c = z_c / D_c - sum_{ib>k} sum_r L(ib,k)[r][c] x_ib[r]  : 6 warps, one per c
+      if (wid < 6) {
+        const int c = wid;
+        double acc = 0;
+        const int nterm = 6 * (kend - k);
+        for (int q = lane; q < nterm; q += 32) {
+          const int ib = k + 1 + q / 6, r = q % 6;
+          acc += pan[(size_t)(ib - k) * 36 + 6 * r + c] * rw[6 * (ib % WB) + r];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) zb[c] = pan[PB * 36 + c] / pan[6 * c + c] - acc;
+      }
+      __syncthreads();
+      if (tid == 0) {   // x_k = L_kk^-T y   (unit lower 6x6)
+        double x6[6];
+#pragma unroll
+        for (int i = 5; i >= 0; i--) {
+          double s2 = zb[i];
+#pragma unroll
+          for (int q = 0; q < 6; q++)
+            if (q > i) s2 -= pan[6 * q + i] * x6[q];
+          x6[i] = s2;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          rw[6 * (k % WB) + i] = x6[i];
+          v.g_x[6 * (size_t)(g0 + k) + i] = x6[i];
+        }
+      }
+      __syncthreads();
+      if (k > 0) commit(pre);
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  for (int k = v.kf_off[w] + tid; k < v.kf_off[w + 1]; k += nt) {
+    const int g = v.kf_g[k];
+    double qt[7];
+    const double* src = v.pose_qt[sel] + 7 * (size_t)k;
+    if (g >= 0 && v.g_nact[g] > 0) {
+      pose_oplus(src, v.g_x + 6 * (size_t)g, qt);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 7; q++) qt[q] = src[q];
+    }
+    double Rt[12];
+    pose_to_Rt(qt, Rt);
+    double* dq = v.pose_qt[sel ^ 1] + 7 * (size_t)k;
+    double* dr = v.pose_Rt[sel ^ 1] + 12 * (size_t)k;
+#pragma unroll
+    for (int q = 0; q < 7; q++) dq[q] = qt[q];
+#pragma unroll
+    for (int q = 0; q < 12; q++) dr[q] = Rt[q];
+  }
+  const double lam = v.w_lambda[w];
+  const int n = 6 * nf;
+  double sc = 0;
+  for (int i = tid; i < n; i += nt) {
+    const int g = g0 + i / 6;
+    if (v.g_nact[g] == 0) continue;
+    const double x = v.g_x[6 * (size_t)g0 + i];
+    sc += x * (lam * x + v.g_bp[6 * (size_t)g0 + i]);
+  }
+  sc = block_sum(sc, red);
+  if (tid == 0) {
+    v.w_scale_p[w] = sc;
+    v.w_ok[w] = ok ? 1 : 0;
+  }
+}
+
 // one CTA per window: assemble the dense reduced camera system from the block rows, factor, solve, apply the
 // pose update T <- exp(x) T into the trial buffer and accumulate the pose part of computeScale().
 template <bool SMEM>
@@ -1378,24 +1629,38 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_lines(BaView v) {
 }
 
 __global__ void __launch_bounds__(256) k_reduce_trial(BaView v) {
-  const int w = blockIdx.x;
+  const int w = blockIdx.x / v.n_slices, sl = blockIdx.x % v.n_slices;
   if (v.w_phase[w] == PH_DONE) return;
   __shared__ double sm[32];
   double chi = 0, sc = 0;
-  for (int p = v.pt_off[w] + threadIdx.x; p < v.pt_off[w + 1]; p += blockDim.x) {
+  const int np = v.pt_off[w + 1] - v.pt_off[w], nl = v.ln_off[w + 1] - v.ln_off[w];
+  const int p0 = v.pt_off[w] + (int)((long long)np * sl / v.n_slices), p1 = v.pt_off[w] + (int)((long long)np * (sl + 1) / v.n_slices);
+  const int l0 = v.ln_off[w] + (int)((long long)nl * sl / v.n_slices), l1 = v.ln_off[w] + (int)((long long)nl * (sl + 1) / v.n_slices);
+  for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
     chi += v.lm_chi2[p];
     sc += v.lm_scale[p];
   }
-  for (int l = v.ln_off[w] + threadIdx.x; l < v.ln_off[w + 1]; l += blockDim.x) {
+  for (int l = l0 + threadIdx.x; l < l1; l += blockDim.x) {
     chi += v.lm_chi2[v.n_pt + l];
     sc += v.lm_scale[v.n_pt + l];
   }
   chi = block_sum(chi, sm);
   sc = block_sum(sc, sm);
   if (threadIdx.x == 0) {
-    v.w_red_sum[4 * w + 0] = chi;
-    v.w_red_sum[4 * w + 1] = sc;
+    double* o = v.w_part + 4 * (size_t)blockIdx.x;
+    o[0] = chi; o[1] = sc;
   }
+}
+__global__ void k_sum_trial(BaView v) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= v.n_win || v.w_phase[w] == PH_DONE) return;
+  double chi = 0, sc = 0;
+  for (int s2 = 0; s2 < v.n_slices; s2++) {
+    const double* o = v.w_part + 4 * ((size_t)w * v.n_slices + s2);
+    chi += o[0]; sc += o[1];
+  }
+  v.w_red_sum[4 * w + 0] = chi;
+  v.w_red_sum[4 * w + 1] = sc;
 }
 
 // accept / reject and the outer-iteration bookkeeping (optimization_algorithm_levenberg.cpp:99-164,
