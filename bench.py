@@ -140,31 +140,54 @@ def edge_counts(p):
     return n_pe, n_le
 
 
-def algorithmic_bytes_per_iter(p, trials=1):
-    """(1+t)(24 Ep + 36 El) + 2(1+t)(24 P + 40 L) + 96 Nkf + 8 (6 Nkf)^2 per window."""
+def free_edge_counts(p):
+    """point edges / line cells whose keyframe is free (only those carry a W block into the Schur complement)"""
+    fixed = p["kf_fixed"].astype(bool)
+    kf_off = p["kf_off"]
+
+    def count(lm_off, obs_off, obs_kf):
+        n = 0
+        for w in range(int(p["n_win"])):
+            e0, e1 = int(obs_off[lm_off[w]]), int(obs_off[lm_off[w + 1]])
+            n += int((~fixed[kf_off[w] + obs_kf[e0:e1]]).sum())
+        return n
+    return count(p["pt_off"], p["pt_obs_off"], p["pt_obs_kf"]), count(p["ln_off"], p["ln_obs_off"], p["ln_obs_kf"])
+
+
+def algorithmic_bytes_step(p, iters_total, trials_total):
+    """SURVEY.md §8(d), summed over the LM iterations actually executed in one step:
+    per window and iteration with t trials  (1+t)(24 Ep + 36 El) + 2(1+t)(24 P + 40 L) + 96 Nkf + 8 (6 Nkf)^2.
+    Every window has the same shape, so the batch total is the per-window figure times the iterations (and trials)
+    summed over the windows."""
     n_pe, n_le = edge_counts(p)
     P, L, K = int(p["pt_off"][-1]), int(p["ln_off"][-1]), int(p["kf_off"][-1])
     nw = int(p["n_win"])
-    nk = K / nw
-    return (1 + trials) * (24 * n_pe + 36 * n_le) + 2 * (1 + trials) * (24 * P + 40 * L) + 96 * K + nw * 8 * (6 * nk) ** 2
+    edge = (24 * n_pe + 36 * n_le) / nw
+    lm = 2 * (24 * P + 40 * L) / nw
+    cam = 96 * K / nw + 8 * (6 * K / nw) ** 2
+    return (iters_total + trials_total) * (edge + lm) + iters_total * cam
 
 
 # per-kernel algorithmic bytes of OUR decomposition (DESIGN.md §kernels): what each launch must read + write once
 def kernel_bytes(name, p):
     n_pe, n_le = edge_counts(p)
     n_lc = int(p["ln_obs_off"][-1])
+    n_pw, n_lw = free_edge_counts(p)
     P, L, K = int(p["pt_off"][-1]), int(p["ln_off"][-1]), int(p["kf_off"][-1])
     nw = int(p["n_win"])
     nf = K / nw - 1
     tbl = {
-        "k_lin_points": n_pe * (24 + 144) + P * (24 + 72),
-        "k_lin_lines": n_lc * (56 + 192) + L * (40 + 112),
+        "k_lin_points": n_pe * 24 + n_pw * 144 + P * (24 + 72),
+        "k_lin_lines": n_lc * 56 + n_lw * 192 + L * (40 + 112),
         "k_lin_poses": n_pe * 24 + n_lc * 56 + (n_pe + n_lc) * 24,
-        "k_schur_points": n_pe * (144 + 144) + P * (72 + 24),
-        "k_schur_lines": n_lc * (192 + 192) + L * (112 + 32),
+        "k_schur_points": P * (72 + 80),
+        "k_schur_lines": L * (112 + 112),
+        # dense-mode Schur complement by co-visibility class: every W block and every landmark inverse record once
+        "k_schur_piece<3>": n_pw * 144 + P * 80,
+        "k_schur_piece<4>": n_lw * 192 + L * 112,
         "k_schur_rows": n_pe * (144 + 144) + n_lc * (192 + 192) + nw * 8 * 36 * nf * (nf + 1) / 2,
-        "k_backsub_points": n_pe * (144 + 24 + 8) + P * (24 + 24 + 24),
-        "k_backsub_lines": n_lc * (192 + 56 + 16) + L * (40 + 40 + 32),
+        "k_backsub_points": n_pw * 144 + n_pe * (24 + 8) + P * (24 + 24 + 80),
+        "k_backsub_lines": n_lw * 192 + n_lc * (56 + 16) + L * (40 + 40 + 112),
     }
     return tbl.get(name)
 
@@ -292,7 +315,8 @@ def main():
     tot_ms = sum(v["ms"] for v in prof.values())
     top = max(prof.items(), key=lambda kv: kv[1]["ms"])
     top_name, top_ms, top_n = top[0], top[1]["ms"], top[1]["n"]
-    kb = kernel_bytes(top_name.split("<")[0], p)
+    key = top_name.strip("()")
+    kb = kernel_bytes(key, p) or kernel_bytes(key.split("<")[0], p)
     roofline = {"bound": "hbm", "kernel": top_name, "share_of_step": top_ms / tot_ms if tot_ms else None,
                 "avg_launch_us": 1e3 * top_ms / max(top_n, 1), "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
                 "traffic": None}
@@ -301,8 +325,8 @@ def main():
         roofline.update({"achieved": ach, "frac": ach / hbm_peak, "algorithmic_bytes_per_launch": kb})
     else:
         roofline.update({"achieved": None, "frac": None})
-    step_bytes = algorithmic_bytes_per_iter(p) * iters_per_step  # t = 1 trials: lower bound
-    roofline_step = {"bound": "hbm", "what": "whole LM iteration vs SURVEY §8(d) algorithmic bytes (t=1)",
+    step_bytes = algorithmic_bytes_step(p, iters_per_step, trials_per_step)
+    roofline_step = {"bound": "hbm", "what": "whole step vs SURVEY §8(d) algorithmic bytes summed over the executed LM iterations and trials",
                      "achieved": step_bytes / (ms * 1e-3 / args.steps) / 1e9, "peak": hbm_peak, "unit": "GB/s"}
     roofline_step["frac"] = roofline_step["achieved"] / hbm_peak
     kernel_table = {k: {"ms": round(v["ms"], 4), "n": v["n"], "share": round(v["ms"] / tot_ms, 4)} for k, v in

@@ -133,6 +133,12 @@ int lld_ba_local(void* ctx, const lld_ba_problem* p, int its_round1, int its_rou
 int lld_ba_global(void* ctx, const lld_ba_problem* p, int n_iter, const volatile uint8_t* stop_flag,
                   lld_ba_result* out);
 
+/* Landmark partition used by lld_ba_global on n_ranks>1: rank r owns points [out[0], out[1]) and lines
+ * [out[2], out[3]) (contiguous blocks; keyframes are replicated).  Host arithmetic only, no device needed.
+ * There is no reference counterpart (the reference is single-process); the partitioned loop is the independent
+ * per-landmark Schur loop of Thirdparty/g2o/g2o/core/block_solver.hpp:381-432. */
+void lld_ba_shard_bounds(int32_t n_pt, int32_t n_ln, int32_t rank, int32_t n_ranks, int32_t out[4]);
+
 /* ------------------------------------------------------------------------------------------------
  * Motion-only pose optimisation (batched frames)
  * ---------------------------------------------------------------------------------------------- */

@@ -198,6 +198,8 @@ class _Lib:
             d.lld_comm_unique_id.restype = C.c_int
             d.lld_comm_init.argtypes = [vp, C.c_int, C.c_int, c_u8p]
             d.lld_comm_init.restype = C.c_int
+            d.lld_ba_shard_bounds.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i32p]
+            d.lld_ba_shard_bounds.restype = None
 
     def _sig(self, name, argtypes):
         f = getattr(self.dll, self.prefix + name)

@@ -963,6 +963,14 @@ extern "C" int lld_ba_local(void* ctx, const lld_ba_problem* p, int its1, int it
   return ba_download(c, p, out, true);
 }
 
+// landmark block partition of the multi-rank global BA (host arithmetic only; also used by the CPU-side tests)
+extern "C" void lld_ba_shard_bounds(int32_t n_pt, int32_t n_ln, int32_t rank, int32_t n_ranks, int32_t out[4]) {
+  out[0] = (int32_t)((long long)n_pt * rank / n_ranks);
+  out[1] = (int32_t)((long long)n_pt * (rank + 1) / n_ranks);
+  out[2] = (int32_t)((long long)n_ln * rank / n_ranks);
+  out[3] = (int32_t)((long long)n_ln * (rank + 1) / n_ranks);
+}
+
 extern "C" int lld_ba_global(void* ctx, const lld_ba_problem* p, int n_iter, const volatile uint8_t* stop,
                              lld_ba_result* out) {
   LldCtx* c = lld_ctx_cast(ctx);
@@ -982,9 +990,9 @@ extern "C" int lld_ba_global(void* ctx, const lld_ba_problem* p, int n_iter, con
   }
   // multi-rank: every rank receives the whole problem and keeps a contiguous block of the landmarks; keyframes are
   // replicated.  The shard is a view on the caller's arrays with re-based CSR offsets.
-  const int n_pt = p->pt_off[1], n_ln = p->ln_off[1];
-  const int plo = (int)((long long)n_pt * rk / R), phi = (int)((long long)n_pt * (rk + 1) / R);
-  const int llo = (int)((long long)n_ln * rk / R), lhi = (int)((long long)n_ln * (rk + 1) / R);
+  int32_t sb[4];
+  lld_ba_shard_bounds(p->pt_off[1], p->ln_off[1], rk, R, sb);
+  const int plo = sb[0], phi = sb[1], llo = sb[2], lhi = sb[3];
   const int pe0 = p->pt_obs_off[plo], lc0 = p->ln_obs_off[llo];
   std::vector<int32_t> poff(phi - plo + 1), loff(lhi - llo + 1);
   for (int i = 0; i <= phi - plo; i++) poff[i] = p->pt_obs_off[plo + i] - pe0;
