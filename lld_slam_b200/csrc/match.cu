@@ -18,6 +18,7 @@
 // reference computes in float; compile this unit with --fmad=false.
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 
 #include "lld_ctx.h"
 
@@ -73,6 +74,8 @@ struct MatchView {
   int* q_ncand;    // [n_q] number of admissible candidates seen by the scan
   int* match;      // [n_cur]
   int* n_matches;  // [n_pairs]
+  int max_cur, max_q;  // largest pair (host side dispatch)
+  int fused_ok;
 };
 
 __device__ __forceinline__ int popc256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
@@ -172,11 +175,9 @@ __device__ __forceinline__ float gemm_row(const float* R, const float* x, float 
 }
 
 // per pair: forward / backward decision of the frame-to-frame variant (src/ORBmatcher.cc:1340-1350)
-__global__ void k_pair_prep(MatchView v) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= v.n_pairs) return;
+__device__ __forceinline__ int pair_mode_of(const MatchView& v, int p) {
   int mode = 0;
-  if (v.variant == 0) {
+  {
     const float* Tc = v.cur_Tcw + 12 * (size_t)p;
     const float* Tl = v.last_Tcw + 12 * (size_t)p;
     float twc[3];
@@ -191,7 +192,12 @@ __global__ void k_pair_prep(MatchView v) {
     const bool bwd = -tlc2 > v.b && !v.mono;
     mode = fwd ? 1 : (bwd ? 2 : 0);
   }
-  v.pair_mode[p] = mode;
+  return mode;
+}
+__global__ void k_pair_prep(MatchView v) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= v.n_pairs) return;
+  v.pair_mode[p] = v.variant == 0 ? pair_mode_of(v, p) : 0;
 }
 __global__ void k_query_pair(MatchView v) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -204,7 +210,7 @@ struct QueryWin {
   float x, y, r, urq;
   int minLevel, maxLevel;
 };
-__device__ __forceinline__ QueryWin query_window(const MatchView& v, int q, int p) {
+__device__ __forceinline__ QueryWin query_window(const MatchView& v, int q, int p, int mode) {
   QueryWin w;
   w.valid = v.q_valid[q] != 0;
   w.x = w.y = w.r = w.urq = 0.f;
@@ -225,7 +231,6 @@ __device__ __forceinline__ QueryWin query_window(const MatchView& v, int q, int 
     const int oct = v.q_octave[q];
     w.r = __fmul_rn(v.th, v.scale[oct]);
     w.urq = __fsub_rn(w.x, __fmul_rn(v.bf, invzc));
-    const int mode = v.pair_mode[p];
     if (mode == 1) { w.minLevel = oct; w.maxLevel = -1; }
     else if (mode == 2) { w.minLevel = 0; w.maxLevel = oct; }
     else { w.minLevel = oct - 1; w.maxLevel = oct + 1; }
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(128) k_match_scan(MatchView v) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= v.n_q) return;
   const int p = v.q_pair[q];
-  const QueryWin w = query_window(v, q, p);
+  const QueryWin w = query_window(v, q, p, v.variant == 0 ? v.pair_mode[p] : 0);
   unsigned long long t[4];
   const int n = scan_window(v, q, p, w, -1, t);
   ulonglong2* dst = reinterpret_cast<ulonglong2*>(v.q_top + 4 * (size_t)q);
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(128) k_match_resolve(MatchView v, int pass) {
     found++;
   }
   if (found < need && v.q_ncand[q] > 4) {  // cache exhausted: scan again with the exclusion applied
-    const QueryWin w = query_window(v, q, p);
+    const QueryWin w = query_window(v, q, p, v.variant == 0 ? v.pair_mode[p] : 0);
     scan_window(v, q, p, w, qi, t);
     k1 = t[0];
     k2 = t[1];
@@ -428,6 +433,466 @@ __global__ void __launch_bounds__(256) k_finalize(MatchView v) {
   if (threadIdx.x == 0) v.n_matches[p] = cnt_acc - cnt_rej;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused matcher: ONE CTA per frame pair, the whole pair resident in shared memory.
+//   build : PosInGrid counting sort of the current keypoints (smem integer atomics), slots inside a cell ordered by
+//           keypoint index, so "slot order" == the reference's candidate traversal order (cell x outer, y inner,
+//           insertion order); 16 B headers {x, y, uRight, owner:16 | octave | claimed} + 32 B descriptors in smem
+//   scan  : one thread per query (<= FUSED_QPT queries per thread), candidates read from shared memory; the four best
+//           candidates are kept in registers as 32-bit keys (distance << 16 | slot)
+//   claim : the sequential "claimed keypoint" rule (src/ORBmatcher.cc:87-89,1403-1405) as a fixed point iterated inside
+//           the CTA (owner = 16 high bits of the header word, smem atomicMin), no host round trips
+//   final : rotation histogram + ComputeThreeMaxima, match table, counts
+// HBM traffic = the pair's inputs once + the outputs: the SURVEY §8(d) algorithmic bytes.  Used when every pair fits
+// (keypoints <= smem capacity, queries <= FUSED_QPT * FUSED_NT); larger frames take the multi-kernel path above.
+// ------------------------------------------------------------------------------------------------
+constexpr int FUSED_NT = 512, FUSED_QPT = 4, FUSED_KPT = 4;  // <= 2048 queries and 2048 keypoints per pair
+constexpr unsigned EMPTY32 = 0xFFFFFFFFu;
+
+struct FusedLayout {
+  int ncap;        // keypoint capacity (multiple of 8)
+  int off_desc;    // byte offsets into dynamic shared memory
+  int off_cstart;
+  int off_sidx;
+  int off_perm;
+  int total;
+};
+static FusedLayout fused_layout(int max_cur) {
+  FusedLayout L;
+  L.ncap = std::max(8, (max_cur + 7) & ~7);
+  L.off_desc = 16 * L.ncap;
+  const int desc_bytes = std::max(32 * L.ncap, 4 * N_CELLS);   // the cell counters alias the descriptor area during the build
+  L.off_cstart = L.off_desc + desc_bytes;
+  L.off_sidx = L.off_cstart + ((2 * (N_CELLS + 2) + 15) & ~15);
+  L.off_perm = L.off_sidx + ((2 * L.ncap + 15) & ~15);
+  L.total = L.off_perm + 2 * FUSED_QPT * FUSED_NT;   // query permutation (sorted by octave), 16-bit
+  return L;
+}
+
+// Scan the window of one query against the smem-resident pair; top-4 32-bit keys in t, #admissible candidates returned.
+// The walk covers the cells of Frame::GetFeaturesInArea (src/Frame.cc:396-410) that can hold an admissible keypoint:
+// PosInGrid (:446-456) is monotone in the coordinate, so the cells of (x -+ (r + margin)) bound every keypoint passing
+// |dx| < r; this drops the outermost column / row that floor / ceil add (none of their keypoints can pass the test).
+// The admission test is branch-free on one 16 B header; admitted slots go to a 4-deep pending list that is drained
+// through the 256-bit popcount + top-4 insertion when full and once after the walk, where the lanes have reconverged.
+__device__ __forceinline__ int fused_scan(const MatchView& v, const QueryWin& w, const uint4& a0, const uint4& a1,
+                                          const uint4* __restrict__ hdr, const uint4* __restrict__ dsc,
+                                          const unsigned short* __restrict__ cstart, int excl_below, unsigned* t) {
+  t[0] = t[1] = t[2] = t[3] = EMPTY32;
+  if (!w.valid) return 0;
+  int x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(w.x, v.min_x), w.r), v.winv)));
+  int x1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(w.x, v.min_x), w.r), v.winv)));
+  int y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(w.y, v.min_y), w.r), v.hinv)));
+  int y1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(w.y, v.min_y), w.r), v.hinv)));
+  if (!(x0 < GRID_COLS && x1 >= 0 && y0 < GRID_ROWS && y1 >= 0)) return 0;
+  {
+    const float m = w.r + 0.0625f;  // far above the rounding of the float subtraction in the admission test
+    x0 = max(x0, (int)roundf(__fmul_rn(__fsub_rn(w.x - m, v.min_x), v.winv)));
+    x1 = min(x1, (int)roundf(__fmul_rn(__fsub_rn(w.x + m, v.min_x), v.winv)));
+    y0 = max(y0, (int)roundf(__fmul_rn(__fsub_rn(w.y - m, v.min_y), v.hinv)));
+    y1 = min(y1, (int)roundf(__fmul_rn(__fsub_rn(w.y + m, v.min_y), v.hinv)));
+  }
+  const bool check_levels = (w.minLevel > 0) || (w.maxLevel >= 0);
+  const int lvl_lo = check_levels ? w.minLevel : -1;
+  const int lvl_hi = (check_levels && w.maxLevel >= 0) ? w.maxLevel : 8;
+  const int excl = excl_below >= 0 ? excl_below : 0;  // owners are >= 0, so 0 excludes nothing
+  unsigned long long pend = 0;
+  int np = 0, ncand = 0;
+  auto drain = [&]() {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (j < np) {
+        const int sl = (int)((pend >> (16 * j)) & 0xFFFFull);
+        const int d = popc256(a0, a1, dsc[2 * sl], dsc[2 * sl + 1]);
+        const unsigned k = ((unsigned)d << 16) | (unsigned)sl;
+        if (k < t[3]) {
+          t[3] = k;
+          if (t[3] < t[2]) { const unsigned u = t[2]; t[2] = t[3]; t[3] = u; }
+          if (t[2] < t[1]) { const unsigned u = t[1]; t[1] = t[2]; t[2] = u; }
+          if (t[1] < t[0]) { const unsigned u = t[0]; t[0] = t[1]; t[1] = u; }
+        }
+      }
+    }
+    ncand += np;
+    np = 0;
+  };
+  for (int ix = x0; ix <= x1; ix++) {
+    const int s0 = cstart[ix * GRID_ROWS + y0], s1 = y1 >= y0 ? cstart[ix * GRID_ROWS + y1 + 1] : s0;
+    for (int s = s0; s < s1; s++) {
+      const uint4 h = hdr[s];
+      const unsigned meta = h.w;
+      const int oct = (meta >> 1) & 7;
+      const float dx = __fsub_rn(__uint_as_float(h.x), w.x), dy = __fsub_rn(__uint_as_float(h.y), w.y);
+      const float ur = __uint_as_float(h.z);
+      const float er = fabsf(__fsub_rn(w.urq, ur));
+      bool ok = !(meta & 1u);                          // not claimed on entry
+      ok = ok && oct >= lvl_lo && oct <= lvl_hi;       // level range (Frame::GetFeaturesInArea)
+      ok = ok && fabsf(dx) < w.r && fabsf(dy) < w.r;
+      ok = ok && (int)(meta >> 16) >= excl;            // not owned by an earlier accepted query
+      ok = ok && !(ur > 0 && er > w.r);                // stereo consistency
+      if (ok) {
+        if (np == 4) drain();
+        pend = (pend << 16) | (unsigned long long)s;
+        np++;
+      }
+    }
+  }
+  drain();
+  return ncand;
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(FUSED_NT, 2) k_match_fused(MatchView v, FusedLayout L) {
+  extern __shared__ uint4 fsm[];
+  __shared__ int s_warp[FUSED_NT / 32];
+  __shared__ int s_hist[HISTO_LENGTH];
+  __shared__ int s_keep[3];
+  __shared__ int s_acc, s_rej, s_mode;
+  const int p = blockIdx.x, tid = threadIdx.x;
+  const int c0 = v.cur_off[p], nc = v.cur_off[p + 1] - c0;
+  const int q0 = v.q_off[p], nq = v.q_off[p + 1] - q0;
+  uint4* hdr = fsm;
+  uint4* dsc = reinterpret_cast<uint4*>(reinterpret_cast<char*>(fsm) + L.off_desc);
+  int* cnt = reinterpret_cast<int*>(dsc);  // aliases the descriptor area until the records are loaded
+  unsigned short* cstart = reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(fsm) + L.off_cstart);
+  unsigned short* sidx = reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(fsm) + L.off_sidx);
+  unsigned short* perm = reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(fsm) + L.off_perm);
+  unsigned* hdr_w = reinterpret_cast<unsigned*>(hdr);  // word 4*s+3 = meta of slot s
+  const int lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = FUSED_NT / 32;
+
+  // ---- issue the global loads of this CTA's keypoints (thread tid owns keypoints tid + u * FUSED_NT) and of the query
+  // sort keys up front, so that their latency overlaps the ballot sort below
+  float kx[FUSED_KPT], ky[FUSED_KPT], kur[FUSED_KPT];
+  unsigned kmeta[FUSED_KPT];
+#pragma unroll
+  for (int u = 0; u < FUSED_KPT; u++) {
+    const int i = tid + u * FUSED_NT;
+    kx[u] = ky[u] = kur[u] = 0.f;
+    kmeta[u] = 0;
+    if (i < nc) {
+      const size_t gi = (size_t)c0 + i;
+      const float2 xy = reinterpret_cast<const float2*>(v.cur_xy)[gi];
+      kx[u] = xy.x;
+      ky[u] = xy.y;
+      kur[u] = v.cur_uright[gi];
+      kmeta[u] = 0xFFFF0000u | ((unsigned)(v.cur_octave[gi] & 7) << 1) | (v.cur_claimed[gi] ? 1u : 0u);
+    }
+  }
+  int key[FUSED_QPT];
+#pragma unroll
+  for (int u = 0; u < FUSED_QPT; u++) {
+    const int qi = tid + u * FUSED_NT;
+    key[u] = 9;
+    if (qi < nq) {
+      const int q = q0 + qi;
+      const int lv = VARIANT == 0 ? min((int)v.q_octave[q], 7) : min(max(v.q_level[q], 0), 7);
+      key[u] = v.q_valid[q] ? lv : 8;
+    }
+  }
+  if (tid < HISTO_LENGTH) s_hist[tid] = 0;
+  if (tid == 0) {
+    s_acc = 0; s_rej = 0;
+    s_keep[0] = s_keep[1] = s_keep[2] = -1;
+    s_mode = VARIANT == 0 ? pair_mode_of(v, p) : 0;
+  }
+
+  // ---- queries sorted by octave: the window radius is th * scale[octave], so the lanes of a warp then walk windows of
+  // similar size (the claim order still uses the original query index).  Ballot counting sort, 9 buckets (8 = invalid).
+  {
+    int* wcnt = cnt;  // [9][FUSED_QPT * NW], scratch in the (still unused) descriptor area
+    int rnk[FUSED_QPT];
+#pragma unroll
+    for (int u = 0; u < FUSED_QPT; u++) {
+      rnk[u] = 0;
+#pragma unroll
+      for (int b = 0; b < 9; b++) {
+        const unsigned m = __ballot_sync(0xffffffffu, key[u] == b);
+        if (key[u] == b) rnk[u] = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) wcnt[b * (FUSED_QPT * NW) + u * NW + wid] = __popc(m);
+      }
+    }
+    __syncthreads();
+    if (wid == 0) {  // exclusive prefix over the 9 * 64 (bucket-major) group counts
+      constexpr int TOT = 9 * FUSED_QPT * NW, PER = TOT / 32;
+      static_assert(PER * 32 == TOT, "group counts must divide over one warp");
+      int loc[PER], sum = 0;
+#pragma unroll
+      for (int k = 0; k < PER; k++) { loc[k] = wcnt[PER * lane + k]; sum += loc[k]; }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int x = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += x;
+      }
+      int base = incl - sum;
+#pragma unroll
+      for (int k = 0; k < PER; k++) { wcnt[PER * lane + k] = base; base += loc[k]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < FUSED_QPT; u++)
+      if (key[u] <= 8) perm[wcnt[key[u] * (FUSED_QPT * NW) + u * NW + wid] + rnk[u]] = (unsigned short)(tid + u * FUSED_NT);
+    __syncthreads();
+  }
+
+  // ---- build: count -> scan -> fill -> order inside cells -> inverse -> records written by the owning threads
+  for (int i = tid; i < N_CELLS; i += FUSED_NT) cnt[i] = 0;
+  __syncthreads();
+  int kcell[FUSED_KPT];
+#pragma unroll
+  for (int u = 0; u < FUSED_KPT; u++) {
+    const int i = tid + u * FUSED_NT;
+    kcell[u] = -1;
+    if (i < nc) {  // Frame::PosInGrid  src/Frame.cc:446-456
+      const int px = (int)roundf(__fmul_rn(__fsub_rn(kx[u], v.min_x), v.winv));
+      const int py = (int)roundf(__fmul_rn(__fsub_rn(ky[u], v.min_y), v.hinv));
+      if (!(px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS)) kcell[u] = px * GRID_ROWS + py;
+      if (kcell[u] >= 0) atomicAdd(&cnt[kcell[u]], 1);
+      v.match[(size_t)c0 + i] = -1;
+    }
+  }
+  __syncthreads();
+  {
+    constexpr int PER = N_CELLS / FUSED_NT;  // 6 consecutive cells per thread
+    static_assert(PER * FUSED_NT == N_CELLS, "cells must divide over the CTA");
+    int loc[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { loc[k] = cnt[PER * tid + k]; sum += loc[k]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int x = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += x;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int x = lane < FUSED_NT / 32 ? s_warp[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane < FUSED_NT / 32) s_warp[lane] = x;  // inclusive over warps
+    }
+    __syncthreads();
+    int base = incl - sum + (wid ? s_warp[wid - 1] : 0);
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      cstart[PER * tid + k] = (unsigned short)base;
+      cnt[PER * tid + k] = base;  // fill cursor
+      base += loc[k];
+    }
+    if (tid == FUSED_NT - 1) cstart[N_CELLS] = (unsigned short)base;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < FUSED_KPT; u++)
+    if (kcell[u] >= 0) sidx[atomicAdd(&cnt[kcell[u]], 1)] = (unsigned short)(tid + u * FUSED_NT);
+  __syncthreads();
+  for (int c = tid; c < N_CELLS; c += FUSED_NT) {  // insertion order inside a cell (cells hold ~1 keypoint)
+    const int b = cstart[c], e = cstart[c + 1];
+    for (int i = b + 1; i < e; i++) {
+      const unsigned short x = sidx[i];
+      int j = i - 1;
+      while (j >= b && sidx[j] > x) { sidx[j + 1] = sidx[j]; j--; }
+      sidx[j + 1] = x;
+    }
+  }
+  __syncthreads();
+  const int ntot = cstart[N_CELLS];
+  {
+    unsigned short* inv = reinterpret_cast<unsigned short*>(hdr);  // keypoint -> slot, consumed before the headers land
+    for (int s2 = tid; s2 < ntot; s2 += FUSED_NT) inv[sidx[s2]] = (unsigned short)s2;
+    __syncthreads();
+    int kslot[FUSED_KPT];
+#pragma unroll
+    for (int u = 0; u < FUSED_KPT; u++) kslot[u] = kcell[u] >= 0 ? (int)inv[tid + u * FUSED_NT] : -1;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < FUSED_KPT; u++) {
+      if (kslot[u] < 0) continue;
+      const uint4* src = reinterpret_cast<const uint4*>(v.cur_desc + 32 * ((size_t)c0 + tid + u * FUSED_NT));
+      const uint4 d0 = src[0], d1 = src[1];
+      hdr[kslot[u]] = make_uint4(__float_as_uint(kx[u]), __float_as_uint(ky[u]), __float_as_uint(kur[u]), kmeta[u]);
+      dsc[2 * kslot[u]] = d0;
+      dsc[2 * kslot[u] + 1] = d1;
+    }
+  }
+  __syncthreads();
+
+  // ---- scan: top-4 per query in registers (thread tid, round u <-> sorted position tid + u * FUSED_NT)
+  unsigned t[FUSED_QPT][4];
+  unsigned many = 0, hasobs = 0;
+  const int mode = s_mode;
+#pragma unroll
+  for (int u = 0; u < FUSED_QPT; u++) {
+    const int sp = tid + u * FUSED_NT;
+    QueryWin w;
+    w.valid = false;
+    w.x = w.y = w.r = w.urq = 0.f;
+    w.minLevel = w.maxLevel = -1;
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    if (sp < nq) {
+      const int q = q0 + perm[sp];
+      w = query_window(v, q, p, mode);
+      const uint4* qd = reinterpret_cast<const uint4*>(v.q_desc + 32 * (size_t)q);
+      a0 = qd[0];
+      a1 = qd[1];
+      if (v.q_has_obs[q]) hasobs |= 1u << u;
+    }
+    const int n = fused_scan(v, w, a0, a1, hdr, dsc, cstart, -1, t[u]);
+    if (n > 4) many |= 1u << u;
+  }
+
+  // ---- claim fixed point
+  unsigned bestkey[FUSED_QPT];
+#pragma unroll
+  for (int u = 0; u < FUSED_QPT; u++) bestkey[u] = EMPTY32;
+  constexpr int need = VARIANT == 1 ? 2 : 1;
+  auto decide = [&](unsigned k1, unsigned k2) -> unsigned {
+    if (k1 == EMPTY32 || (int)(k1 >> 16) > TH_HIGH) return EMPTY32;
+    if (VARIANT == 1) {  // ratio test only when best and second best share the level  (src/ORBmatcher.cc:118-121)
+      const int d2 = k2 != EMPTY32 ? (int)(k2 >> 16) : 256;
+      const int l1 = (hdr_w[4 * (k1 & 0xFFFFu) + 3] >> 1) & 7;
+      const int l2 = k2 != EMPTY32 ? (int)((hdr_w[4 * (k2 & 0xFFFFu) + 3] >> 1) & 7) : -1;
+      if (l1 == l2 && (float)(k1 >> 16) > __fmul_rn(v.nn_ratio, (float)d2)) return EMPTY32;
+    }
+    return k1;
+  };
+  for (int pass = 0;; pass++) {
+    unsigned newkey[FUSED_QPT];
+    unsigned resc = 0;
+#pragma unroll
+    for (int u = 0; u < FUSED_QPT; u++) {
+      const int sp = tid + u * FUSED_NT;
+      const int qi = sp < nq ? (int)perm[sp] : -1;
+      unsigned k1 = EMPTY32, k2 = EMPTY32;
+      int found = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const unsigned k = t[u][j];
+        if (qi < 0 || k == EMPTY32 || found >= need) continue;
+        if ((int)(hdr_w[4 * (k & 0xFFFFu) + 3] >> 16) < qi) continue;
+        if (found == 0) k1 = k;
+        else k2 = k;
+        found++;
+      }
+      newkey[u] = EMPTY32;
+      if (qi >= 0 && found < need && ((many >> u) & 1u)) resc |= 1u << u;  // cache exhausted, more candidates exist
+      else if (qi >= 0) newkey[u] = decide(k1, k2);
+    }
+    // rescans with the exclusion applied: warp-uniform calls, every lane works on its own pending query (if any)
+    while (__any_sync(0xffffffffu, resc != 0)) {
+      const int u = resc ? __ffs(resc) - 1 : -1;
+      QueryWin w;
+      w.valid = false;
+      w.x = w.y = w.r = w.urq = 0.f;
+      w.minLevel = w.maxLevel = -1;
+      uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+      int qi = -1;
+      if (u >= 0) {
+        qi = perm[tid + u * FUSED_NT];
+        const int q = q0 + qi;
+        w = query_window(v, q, p, mode);
+        const uint4* qd = reinterpret_cast<const uint4*>(v.q_desc + 32 * (size_t)q);
+        a0 = qd[0];
+        a1 = qd[1];
+      }
+      unsigned tt[4];
+      fused_scan(v, w, a0, a1, hdr, dsc, cstart, qi, tt);
+      if (u >= 0) {
+        const unsigned acc = decide(tt[0], tt[1]);
+#pragma unroll
+        for (int uu = 0; uu < FUSED_QPT; uu++)
+          if (uu == u) newkey[uu] = acc;
+        resc &= resc - 1;
+      }
+    }
+    int changed = 0;
+#pragma unroll
+    for (int u = 0; u < FUSED_QPT; u++) {
+      if (newkey[u] != bestkey[u]) changed = 1;
+      bestkey[u] = newkey[u];
+    }
+    const int any = __syncthreads_or(changed);
+    if (pass > 0 && !any) break;
+    if (pass >= 64) {
+      if (tid == 0) atomicOr(v.changed, 2);  // did not converge: reported by the host after the run
+      break;
+    }
+    for (int s = tid; s < ntot; s += FUSED_NT) hdr_w[4 * s + 3] |= 0xFFFF0000u;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < FUSED_QPT; u++) {
+      const int sp = tid + u * FUSED_NT;
+      if (sp < nq && bestkey[u] != EMPTY32 && ((hasobs >> u) & 1u)) {
+        unsigned* wp = hdr_w + 4 * (bestkey[u] & 0xFFFFu) + 3;
+        atomicMin(wp, ((unsigned)perm[sp] << 16) | (*wp & 0xFFFFu));
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- results: per-query best, match table (last accepted query of a keypoint wins), rotation consistency
+  const bool ori = VARIANT == 0 && v.check_ori;
+  const float factor = 1.0f / HISTO_LENGTH;
+  int bins[FUSED_QPT];
+#pragma unroll
+  for (int u = 0; u < FUSED_QPT; u++) {
+    const int sp = tid + u * FUSED_NT;
+    bins[u] = -1;
+    if (sp >= nq) continue;
+    const int qi = perm[sp];
+    const int q = q0 + qi;
+    int best = -1, bd = 256;
+    if (bestkey[u] != EMPTY32) {
+      best = sidx[bestkey[u] & 0xFFFFu];
+      bd = (int)(bestkey[u] >> 16);
+      atomicAdd(&s_acc, 1);
+      atomicMax(&v.match[(size_t)c0 + best], qi);
+      if (ori) {
+        float rot = __fsub_rn(v.q_angle[q], v.cur_angle[(size_t)c0 + best]);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, factor));
+        if (bin == HISTO_LENGTH) bin = 0;
+        bins[u] = bin;
+        atomicAdd(&s_hist[bin], 1);
+      }
+    }
+    v.q_best[q] = best;
+    v.q_dist[q] = bd;
+  }
+  __syncthreads();
+  if (ori) {
+    if (tid == 0) {  // ORBmatcher::ComputeThreeMaxima
+      int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+      for (int i = 0; i < HISTO_LENGTH; i++) {
+        const int s = s_hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+      }
+      if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+      else if ((float)max3 < 0.1f * (float)max1) { ind3 = -1; }
+      s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < FUSED_QPT; u++) {
+      if (bins[u] < 0) continue;
+      if (bins[u] != s_keep[0] && bins[u] != s_keep[1] && bins[u] != s_keep[2]) {
+        v.match[(size_t)c0 + sidx[bestkey[u] & 0xFFFFu]] = -1;  // after every atomicMax (barrier): NULL wins, as in the reference
+        atomicAdd(&s_rej, 1);
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) v.n_matches[p] = s_acc - s_rej;
+}
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 template <typename T>
@@ -464,6 +929,19 @@ struct MatchState {
 
 // device pipeline shared by both variants; everything already uploaded into v
 static int match_run(LldCtx* c, MatchView& v, int* passes_out) {
+  if (v.fused_ok) {  // every pair fits one CTA's shared memory: single launch, no host round trips
+    const FusedLayout L = fused_layout(v.max_cur);
+    if (v.variant == 0) {
+      LLD_CUDA(c, cudaFuncSetAttribute(k_match_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+      LLD_LAUNCH(c, k_match_fused<0>, v.n_pairs, FUSED_NT, L.total, v, L);
+    } else {
+      LLD_CUDA(c, cudaFuncSetAttribute(k_match_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+      LLD_LAUNCH(c, k_match_fused<1>, v.n_pairs, FUSED_NT, L.total, v, L);
+    }
+    LLD_CUDA(c, cudaGetLastError());
+    if (passes_out) *passes_out = 0;
+    return LLD_OK;
+  }
   LLD_CUDA(c, cudaMemsetAsync(v.cell_count, 0, sizeof(int) * (size_t)v.n_pairs * (N_CELLS + 1), c->stream));
   if (v.n_cur) LLD_LAUNCH(c, k_cell_count, cdiv(v.n_cur, 256), 256, 0, v);
   LLD_LAUNCH(c, k_cell_scan, v.n_pairs, 1024, 0, v);
@@ -516,6 +994,18 @@ static int match_alloc_common(LldCtx* c, MatchView& v) {
   return LLD_OK;
 }
 
+// fused single-CTA path when the largest pair fits shared memory (LLD_MATCH_FUSED=0 forces the multi-kernel path)
+static void set_dispatch(MatchView& v, const int32_t* cur_off, const int32_t* q_off) {
+  v.max_cur = 0; v.max_q = 0;
+  for (int i = 0; i < v.n_pairs; i++) {
+    v.max_cur = std::max(v.max_cur, cur_off[i + 1] - cur_off[i]);
+    v.max_q = std::max(v.max_q, q_off[i + 1] - q_off[i]);
+  }
+  const char* e = getenv("LLD_MATCH_FUSED");
+  const bool allow = !(e && e[0] == '0');
+  v.fused_ok = allow && fused_layout(v.max_cur).total <= 227 * 1024 && v.max_q <= FUSED_QPT * FUSED_NT && v.max_cur <= FUSED_KPT * FUSED_NT;
+}
+
 static void set_geom(MatchView& v, const lld_frame_geom& g) {
   v.fx = g.fx; v.fy = g.fy; v.cx = g.cx; v.cy = g.cy; v.bf = g.bf; v.b = g.b;
   v.min_x = g.min_x; v.max_x = g.max_x; v.min_y = g.min_y; v.max_y = g.max_y;
@@ -526,6 +1016,8 @@ static void set_geom(MatchView& v, const lld_frame_geom& g) {
 
 static int match_download(LldCtx* c, MatchView& v, lld_sbp_result* out) {
   LLD_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  int* h_flag = reinterpret_cast<int*>(c->pinned);
+  LLD_CUDA(c, cudaMemcpyAsync(h_flag, v.changed, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   if (out->match && v.n_cur) LLD_CUDA(c, cudaMemcpyAsync(out->match, v.match, sizeof(int) * (size_t)v.n_cur, cudaMemcpyDeviceToHost, c->stream));
   if (out->n_matches) LLD_CUDA(c, cudaMemcpyAsync(out->n_matches, v.n_matches, sizeof(int) * (size_t)v.n_pairs, cudaMemcpyDeviceToHost, c->stream));
   if (out->best_idx && v.n_q) LLD_CUDA(c, cudaMemcpyAsync(out->best_idx, v.q_best, sizeof(int) * (size_t)v.n_q, cudaMemcpyDeviceToHost, c->stream));
@@ -535,6 +1027,10 @@ static int match_download(LldCtx* c, MatchView& v, lld_sbp_result* out) {
   cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->ms_compute, c->ev[1], c->ev[2]);
   cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]);
+  if (*h_flag & 2) {
+    snprintf(c->err, sizeof(c->err), "claim resolution did not converge in 64 passes");
+    return LLD_ERR_CUDA;
+  }
   return LLD_OK;
 }
 
@@ -550,6 +1046,7 @@ static int sbp_frame_upload(LldCtx* c, const lld_sbp_frame_problem* p, MatchView
   v.n_q = p->last_off[p->n_pairs];
   LLD_ARG(c, p->geom.n_levels >= 1 && p->geom.n_levels <= 8);  // octave is packed into 3 bits of the candidate key
   for (int i = 0; i < p->n_pairs; i++) LLD_ARG(c, p->cur_off[i + 1] - p->cur_off[i] <= 65535);
+  set_dispatch(v, p->cur_off, p->last_off);
   v.variant = 0;
   set_geom(v, p->geom);
   v.th = p->th; v.nn_ratio = 0; v.mono = p->mono; v.check_ori = p->check_orientation;
@@ -582,6 +1079,7 @@ static int sbp_mp_upload(LldCtx* c, const lld_sbp_mp_problem* p, MatchView& v) {
   v.n_q = p->mp_off[p->n_pairs];
   LLD_ARG(c, p->geom.n_levels >= 1 && p->geom.n_levels <= 8);
   for (int i = 0; i < p->n_pairs; i++) LLD_ARG(c, p->cur_off[i + 1] - p->cur_off[i] <= 65535);
+  set_dispatch(v, p->cur_off, p->mp_off);
   v.variant = 1;
   set_geom(v, p->geom);
   v.th = p->th; v.nn_ratio = p->nn_ratio; v.mono = 0; v.check_ori = 0;

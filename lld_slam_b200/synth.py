@@ -487,6 +487,24 @@ def make_sbp_frame_batch(n_pairs, n_kp, seed, th=7.0, unrelated_frac=0.3, flip_p
     )
 
 
+def concat_sbp_frame(parts):
+    """concatenate frame-pair batches of different sizes into one ragged batch (same geometry / thresholds)"""
+    out = dict(parts[0])
+    out["n_pairs"] = int(sum(p["n_pairs"] for p in parts))
+    for off_key, keys in (("cur_off", ("cur_xy", "cur_octave", "cur_angle", "cur_uright", "cur_desc", "cur_claimed")),
+                          ("last_off", ("last_valid", "last_xw", "last_octave", "last_angle", "last_desc", "last_has_obs"))):
+        offs, base = [np.zeros(1, np.int32)], 0
+        for p in parts:
+            offs.append((p[off_key][1:] + base).astype(np.int32))
+            base += int(p[off_key][-1])
+        out[off_key] = np.concatenate(offs)
+        for k in keys:
+            out[k] = np.ascontiguousarray(np.concatenate([p[k] for p in parts], 0))
+    for k in ("cur_Tcw", "last_Tcw"):
+        out[k] = np.ascontiguousarray(np.concatenate([p[k] for p in parts], 0))
+    return out
+
+
 def make_sbp_mp_batch(n_pairs, n_kp, n_mp, seed, th=3.0, nn_ratio=0.8):
     """SearchByProjection(F, local map points): map points pre-projected (isInFrustum fields)."""
     rng = np.random.default_rng(seed)

@@ -150,7 +150,14 @@ def test_pose_opt_degenerate(gpu_ctx):
         check_pose(api.pose_opt(p, impl="gpu", ctx=gpu_ctx), api.pose_opt(p, impl="oracle"))
 
 
-def test_sbp_frame(gpu_ctx):
+@pytest.fixture(params=["fused", "multikernel"])
+def match_path(request, monkeypatch):
+    """both device paths of the matcher: one CTA per pair in shared memory (frames that fit), and the multi-kernel path"""
+    monkeypatch.setenv("LLD_MATCH_FUSED", "1" if request.param == "fused" else "0")
+    return request.param
+
+
+def test_sbp_frame(gpu_ctx, match_path):
     """SearchByProjection(Current, Last): bit-exact matches, best indices and Hamming distances."""
     p = synth.make_sbp_frame_batch(12, 2000, synth.seed_for(2))
     g = api.sbp_frame(p, impl="gpu", ctx=gpu_ctx)
@@ -160,7 +167,7 @@ def test_sbp_frame(gpu_ctx):
         assert np.array_equal(g[k], o[k]), f"{k}: {np.nonzero(g[k] != o[k])[0][:10]}"
 
 
-def test_sbp_frame_small_and_mono(gpu_ctx):
+def test_sbp_frame_small_and_mono(gpu_ctx, match_path):
     p = synth.make_sbp_frame_batch(3, 64, 4)
     p["mono"] = 1
     p["check_orientation"] = 0
@@ -170,7 +177,7 @@ def test_sbp_frame_small_and_mono(gpu_ctx):
         assert np.array_equal(g[k], o[k]), k
 
 
-def test_sbp_mappoints(gpu_ctx):
+def test_sbp_mappoints(gpu_ctx, match_path):
     """SearchByProjection(Frame, local map points): ratio test, claimed keypoints."""
     p = synth.make_sbp_mp_batch(6, 2000, 1500, 17)
     g = api.sbp_mappoints(p, impl="gpu", ctx=gpu_ctx)
@@ -178,6 +185,25 @@ def test_sbp_mappoints(gpu_ctx):
     assert o["n_matches"].sum() > 500
     for k in ("match", "n_matches", "best_idx", "best_dist"):
         assert np.array_equal(g[k], o[k]), f"{k}: {np.nonzero(g[k] != o[k])[0][:10]}"
+
+
+def test_sbp_frame_large_frames_take_multikernel_path(gpu_ctx):
+    """frames beyond the shared-memory capacity of the fused kernel (5000 keypoints) still match bit-exactly"""
+    p = synth.make_sbp_frame_batch(2, 5000, 123)
+    g = api.sbp_frame(p, impl="gpu", ctx=gpu_ctx)
+    o = api.sbp_frame(p, impl="oracle")
+    for k in ("match", "n_matches", "best_idx", "best_dist"):
+        assert np.array_equal(g[k], o[k]), k
+
+
+def test_sbp_frame_ragged_pairs(gpu_ctx, match_path):
+    """pairs of different sizes in one batch, including an empty current frame"""
+    parts = [synth.make_sbp_frame_batch(1, n, 50 + n) for n in (1500, 37, 900)]
+    p = synth.concat_sbp_frame(parts)
+    g = api.sbp_frame(p, impl="gpu", ctx=gpu_ctx)
+    o = api.sbp_frame(p, impl="oracle")
+    for k in ("match", "n_matches", "best_idx", "best_dist"):
+        assert np.array_equal(g[k], o[k]), k
 
 
 def check_line_match(g, o):

@@ -15,6 +15,7 @@ ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--windows", type=int, default=64)
 ap.add_argument("--pairs", type=int, default=1024)
 ap.add_argument("--frames", type=int, default=512)
+ap.add_argument("--time", action="store_true", help="also print a CUDA-event timing (not under ncu)")
 a = ap.parse_args()
 lib = capi.load_library()
 d = bench.bind_resident(lib)
@@ -36,6 +37,13 @@ elif a.workload == "match":
     for _ in range(a.reps):
         ctx.check(d.lld_sbp_run(ctx.handle, C.byref(n)), "run")
     d.lld_ba_sync(ctx.handle)
+    if a.time:
+        d.lld_ctx_event_record(ctx.handle, 0)
+        for _ in range(20):
+            ctx.check(d.lld_sbp_run(ctx.handle, C.byref(n)), "run")
+        d.lld_ctx_event_record(ctx.handle, 1)
+        d.lld_ba_sync(ctx.handle)
+        print("match ms per batch:", float(d.lld_ctx_event_elapsed_ms(ctx.handle)) / 20)
 elif a.workload == "pose":
     pz = synth.make_pose_batch(a.frames, 1500, 300, 3)
     prob, keep = capi.fill_struct(capi.PoseProblem, pz)
