@@ -34,6 +34,8 @@ struct BaState {
   size_t env_smem = 0, band_smem = 0;
   bool use_band = false;
   bool global_mode = false;
+  bool forked = false;     // dense single-rank batch small enough that concurrent passes shorten the critical path
+  bool use_graph = false;  // replay one captured LM step instead of re-launching its kernels
   const double* d_kf_Tcw_in = nullptr;
   const double* d_pt_in = nullptr;
   const double* d_ln_in = nullptr;
@@ -44,6 +46,16 @@ struct BaState {
   double* d_out_ln = nullptr;
   uint8_t* d_pt_bad = nullptr;
   uint8_t* d_ln_bad = nullptr;
+  // one LM step captured as a CUDA graph per round (kernel arguments differ: round, robust flags)
+  cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
+  int step_kernels[2] = {0, 0};
+  void drop_graphs() {
+    for (int r = 0; r < 2; r++) {
+      if (step_graph[r]) cudaGraphExecDestroy(step_graph[r]);
+      step_graph[r] = nullptr;
+      step_kernels[r] = 0;
+    }
+  }
 };
 
 namespace {
@@ -108,6 +120,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
                      const lld_ba_problem* full = nullptr /* multi-rank: whole problem, for the rank-invariant structure */) {
   if (!c->ba) c->ba = new BaState();
   BaState* S = c->ba;
+  S->drop_graphs();
   *S = BaState();
   S->global_mode = global_mode;
   c->pool_reset();
@@ -674,6 +687,19 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   v.prm.ln_filter = p->ln_filter;
   stage("device buffers");
   c->last_h2d_bytes = S->h2d_bytes;
+  {
+    const char* e = getenv("LLD_BA_GRAPH");
+    const bool allow = !(e && e[0] == '0');
+    const bool dense_single = v.dense_mode && !(global_mode && c->n_ranks > 1) && v.n_slices == 1 && S->max_n <= SMEM_SOLVE_MAX_N && !v.env_mode;
+    S->forked = allow && dense_single;
+    S->use_graph = allow && dense_single;
+  }
+  // dynamic shared memory opt-in of the solvers (once per upload, outside any stream capture)
+  if (v.env_mode && S->use_band) LLD_CUDA(c, cudaFuncSetAttribute(k_solve_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->band_smem));
+  else if (v.env_mode) LLD_CUDA(c, cudaFuncSetAttribute(k_solve_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->env_smem));
+  else if (S->max_n <= SMEM_SOLVE_MAX_N)
+    LLD_CUDA(c, cudaFuncSetAttribute(k_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(double) * ((size_t)S->max_n * S->max_n + 8 * (size_t)S->max_n + 8))));
   return LLD_OK;
 }
 
@@ -742,8 +768,52 @@ static int ba_allreduce_rows(LldCtx* c) {
 template <bool SMEM>
 static int launch_solve(LldCtx* c, BaView& v, int max_n) {
   size_t smem = SMEM ? sizeof(double) * ((size_t)max_n * max_n + 8 * (size_t)max_n + 8) : 0;
-  if (SMEM) LLD_CUDA(c, cudaFuncSetAttribute(k_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LLD_LAUNCH(c, k_solve<SMEM>, v.n_win, 512, smem, v);
+  return LLD_OK;
+}
+
+// Dense single-rank path with the independent passes of one LM step on concurrent streams:
+//   [lin_points | lin_lines | lin_poses] -> begin -> [schur_points -> piece<3> | schur_lines -> piece<4>] -> reduce ->
+//   solve -> [backsub_points | backsub_lines] -> decide
+// (a small batch does not fill the GPU with any single pass; the critical path is what counts).  Works eagerly and
+// under stream capture (the side streams join the capture through the fork event).
+static int ba_step_forked(LldCtx* c, int round, int stop_now) {
+  BaState* S = c->ba;
+  BaView& v = S->v;
+  const int gp = cdiv(std::max(v.n_pt, 1), LM_TPB), gl = cdiv(std::max(v.n_ln, 1), LM_TPB);
+  cudaStream_t s0 = c->stream, s1 = c->side[0], s2 = c->side[1];
+  auto fork = [&](cudaStream_t t) -> cudaError_t { return cudaStreamWaitEvent(t, c->ev_fork, 0); };
+  auto join = [&](int i) -> cudaError_t {
+    cudaError_t e = cudaEventRecord(c->ev_join[i], c->side[i]);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(s0, c->ev_join[i], 0);
+  };
+  LLD_CUDA(c, cudaEventRecord(c->ev_fork, s0));
+  LLD_CUDA(c, fork(s1));
+  LLD_CUDA(c, fork(s2));
+  if (v.n_pt) LLD_LAUNCH_S(c, s0, k_lin_points, gp, LM_TPB, 0, v);
+  if (v.n_ln) LLD_LAUNCH_S(c, s1, k_lin_lines, gl, LM_TPB, 0, v);
+  if (v.n_chunks) LLD_LAUNCH_S(c, s2, k_lin_poses, v.n_chunks, LM_TPB, 0, v);
+  LLD_CUDA(c, join(0));
+  LLD_CUDA(c, join(1));
+  LLD_LAUNCH_S(c, s0, k_begin_fused, v.n_win, 256, 0, v);
+  const int nip = v.n_items_pt, nil = v.n_items - v.n_items_pt;
+  LLD_CUDA(c, cudaEventRecord(c->ev_fork, s0));
+  LLD_CUDA(c, fork(s1));
+  if (v.n_pt) LLD_LAUNCH_S(c, s0, k_schur_points, gp, LM_TPB, 0, v);
+  if (nip) LLD_LAUNCH_S(c, s0, k_schur_piece<3>, cdiv(nip, 8), 256, 0, v, 0, nip);
+  if (v.n_ln) LLD_LAUNCH_S(c, s1, k_schur_lines, gl, LM_TPB, 0, v);
+  if (nil) LLD_LAUNCH_S(c, s1, k_schur_piece<4>, cdiv(nil, 8), 256, 0, v, nip, nil);
+  LLD_CUDA(c, join(0));
+  const int nblk = (int)S->n_nb_total;
+  LLD_LAUNCH_S(c, s0, k_reduce_piece, cdiv(nblk * 6 + v.n_free_total, 8), 256, 0, v, nblk);
+  { int r = launch_solve<true>(c, v, S->max_n); if (r) return r; }
+  LLD_CUDA(c, cudaEventRecord(c->ev_fork, s0));
+  LLD_CUDA(c, fork(s1));
+  if (v.n_pt) LLD_LAUNCH_S(c, s0, k_backsub_points, gp, LM_TPB, 0, v);
+  if (v.n_ln) LLD_LAUNCH_S(c, s1, k_backsub_lines, gl, LM_TPB, 0, v);
+  LLD_CUDA(c, join(0));
+  LLD_LAUNCH_S(c, s0, k_decide_fused, v.n_win, 256, 0, v, round, stop_now);
+  LLD_CUDA(c, cudaGetLastError());
   return LLD_OK;
 }
 
@@ -751,6 +821,7 @@ static int launch_solve(LldCtx* c, BaView& v, int max_n) {
 static int ba_step(LldCtx* c, int round, int stop_now) {
   BaState* S = c->ba;
   BaView& v = S->v;
+  if (S->forked && !c->prof_on) return ba_step_forked(c, round, stop_now);
   const int gp = cdiv(std::max(v.n_pt, 1), LM_TPB), gl = cdiv(std::max(v.n_ln, 1), LM_TPB);
   if (v.n_pt) LLD_LAUNCH(c, k_lin_points, gp, LM_TPB, 0, v);
   if (v.n_ln) LLD_LAUNCH(c, k_lin_lines, gl, LM_TPB, 0, v);
@@ -791,10 +862,8 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   }
   if (S->global_mode) { int r = ba_allreduce_rows(c); if (r) return r; }
   if (v.env_mode && S->use_band) {
-    LLD_CUDA(c, cudaFuncSetAttribute(k_solve_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->band_smem));
     LLD_LAUNCH(c, k_solve_band, 1, 1024, S->band_smem, v);
   } else if (v.env_mode) {
-    LLD_CUDA(c, cudaFuncSetAttribute(k_solve_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->env_smem));
     LLD_LAUNCH(c, k_solve_env, 1, 1024, S->env_smem, v);
   } else if (S->max_n <= SMEM_SOLVE_MAX_N) { int r = launch_solve<true>(c, v, S->max_n); if (r) return r; }
   else { int r = launch_solve<false>(c, v, S->max_n); if (r) return r; }
@@ -827,8 +896,27 @@ static int ba_run_round(LldCtx* c, int maxit, int round, const volatile uint8_t*
     first = false;
     for (int s = 0; s < n; s++) {
       const int stop_now = (stop && *stop) ? 1 : 0;
-      int r = ba_step(c, round, stop_now);
-      if (r) return r;
+      if (S->use_graph && !c->prof_on && !stop_now && round < 2) {
+        if (!S->step_graph[round]) {  // capture one LM step (fork / join over the side streams included)
+          const int64_t l0 = c->launches;
+          cudaGraph_t g = nullptr;
+          LLD_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+          int r = ba_step(c, round, 0);
+          cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+          if (r) { if (g) cudaGraphDestroy(g); return r; }
+          LLD_CUDA(c, e);
+          e = cudaGraphInstantiate(&S->step_graph[round], g, 0);
+          cudaGraphDestroy(g);
+          LLD_CUDA(c, e);
+          S->step_kernels[round] = (int)(c->launches - l0);
+          c->launches = l0;
+        }
+        LLD_CUDA(c, cudaGraphLaunch(S->step_graph[round], c->stream));
+        c->launches += S->step_kernels[round];
+      } else {
+        int r = ba_step(c, round, stop_now);
+        if (r) return r;
+      }
       launched++;
       if (stop_now) break;
     }
@@ -1017,4 +1105,7 @@ extern "C" int lld_ba_global(void* ctx, const lld_ba_problem* p, int n_iter, con
   return ba_download(c, &sh, &so, false);
 }
 
-void lld_ba_state_free(BaState* s) { delete s; }
+void lld_ba_state_free(BaState* s) {
+  if (s) s->drop_graphs();
+  delete s;
+}

@@ -23,6 +23,11 @@ extern "C" int lld_ctx_create(int device, void** out) {
     if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return LLD_ERR_CUDA; }
   for (int i = 0; i < 2; i++)
     if (cudaEventCreate(&c->ev_user[i]) != cudaSuccess) { delete c; return LLD_ERR_CUDA; }
+  for (int i = 0; i < 2; i++) {
+    if (cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking) != cudaSuccess) { delete c; return LLD_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess) { delete c; return LLD_ERR_CUDA; }
+  }
+  if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) { delete c; return LLD_ERR_CUDA; }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   c->pinned_cap = 1 << 16;
   if (cudaMallocHost(&c->pinned, c->pinned_cap) != cudaSuccess) { delete c; return LLD_ERR_CUDA; }
@@ -43,8 +48,15 @@ extern "C" void lld_ctx_destroy(void* ctx) {
   if (c->pinned) cudaFreeHost(c->pinned);
   for (int i = 0; i < 4; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  lld_ba_state_free(c->ba);  // graphs first: they reference the streams
+  for (int i = 0; i < 2; i++) {
+    if (c->side[i]) cudaStreamDestroy(c->side[i]);
+    if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  for (int i = 0; i < 2; i++)
+    if (c->ev_user[i]) cudaEventDestroy(c->ev_user[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
-  lld_ba_state_free(c->ba);
   delete c;
 }
 

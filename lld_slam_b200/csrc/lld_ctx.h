@@ -36,6 +36,9 @@ struct DevBuf {
 struct LldCtx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // side streams + fork/join events: independent kernels of one LM step (point / line / pose passes) run concurrently
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_user[2] = {nullptr, nullptr};  // bench.py timing on this context's stream
   char err[512] = {0};
@@ -100,20 +103,21 @@ struct LldCtx {
   } while (0)
 
 // kernel launch with bookkeeping (the launch count feeds bench.py's gpu_launches)
-#define LLD_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
+#define LLD_LAUNCH_S(ctx, strm, kernel, grid, block, smem, ...)                 \
   do {                                                                          \
     cudaEvent_t _pa = nullptr, _pb = nullptr;                                   \
     if ((ctx)->prof_on) {                                                       \
       _pa = (ctx)->prof_event();                                                \
-      cudaEventRecord(_pa, (ctx)->stream);                                      \
+      cudaEventRecord(_pa, (strm));                                             \
     }                                                                           \
-    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);            \
+    kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                   \
     if ((ctx)->prof_on) {                                                       \
       _pb = (ctx)->prof_event();                                                \
-      cudaEventRecord(_pb, (ctx)->stream);                                      \
+      cudaEventRecord(_pb, (strm));                                             \
       (ctx)->prof.push_back({#kernel, _pa, _pb});                               \
     }                                                                           \
     (ctx)->launches++;                                                          \
   } while (0)
+#define LLD_LAUNCH(ctx, kernel, grid, block, smem, ...) LLD_LAUNCH_S(ctx, (ctx)->stream, kernel, grid, block, smem, __VA_ARGS__)
 
 static inline LldCtx* lld_ctx_cast(void* p) { return reinterpret_cast<LldCtx*>(p); }
