@@ -795,7 +795,7 @@ static int ba_step_forked(LldCtx* c, int round, int stop_now) {
   if (v.n_chunks) LLD_LAUNCH_S(c, s2, k_lin_poses, v.n_chunks, LM_TPB, 0, v);
   LLD_CUDA(c, join(0));
   LLD_CUDA(c, join(1));
-  LLD_LAUNCH_S(c, s0, k_begin_fused, v.n_win, 256, 0, v);
+  LLD_LAUNCH_S(c, s0, k_begin_fused, v.n_win, FUSED_RED_TPB, 0, v);
   const int nip = v.n_items_pt, nil = v.n_items - v.n_items_pt;
   LLD_CUDA(c, cudaEventRecord(c->ev_fork, s0));
   LLD_CUDA(c, fork(s1));
@@ -812,7 +812,7 @@ static int ba_step_forked(LldCtx* c, int round, int stop_now) {
   if (v.n_pt) LLD_LAUNCH_S(c, s0, k_backsub_points, gp, LM_TPB, 0, v);
   if (v.n_ln) LLD_LAUNCH_S(c, s1, k_backsub_lines, gl, LM_TPB, 0, v);
   LLD_CUDA(c, join(0));
-  LLD_LAUNCH_S(c, s0, k_decide_fused, v.n_win, 256, 0, v, round, stop_now);
+  LLD_LAUNCH_S(c, s0, k_decide_fused, v.n_win, FUSED_RED_TPB, 0, v, round, stop_now);
   LLD_CUDA(c, cudaGetLastError());
   return LLD_OK;
 }
@@ -829,7 +829,7 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   const bool multi = S->global_mode && c->n_ranks > 1;
   const bool fused = !multi && v.n_slices == 1;
   if (fused) {
-    LLD_LAUNCH(c, k_begin_fused, v.n_win, 256, 0, v);
+    LLD_LAUNCH(c, k_begin_fused, v.n_win, FUSED_RED_TPB, 0, v);
   } else {
     if (v.n_free_total) LLD_LAUNCH(c, k_reduce_pose, cdiv(v.n_free_total * 28, 128), 128, 0, v);
     LLD_LAUNCH(c, k_reduce_lin, v.n_win * v.n_slices, 256, 0, v);
@@ -870,7 +870,7 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   if (v.n_pt) LLD_LAUNCH(c, k_backsub_points, gp, LM_TPB, 0, v);
   if (v.n_ln) LLD_LAUNCH(c, k_backsub_lines, gl, LM_TPB, 0, v);
   if (fused) {
-    LLD_LAUNCH(c, k_decide_fused, v.n_win, 256, 0, v, round, stop_now);
+    LLD_LAUNCH(c, k_decide_fused, v.n_win, FUSED_RED_TPB, 0, v, round, stop_now);
   } else {
     LLD_LAUNCH(c, k_reduce_trial, v.n_win * v.n_slices, 256, 0, v);
     LLD_LAUNCH(c, k_sum_trial, cdiv(v.n_win, 64), 64, 0, v);

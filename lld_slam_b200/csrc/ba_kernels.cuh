@@ -455,7 +455,7 @@ __global__ void k_sum_lin(BaView v) {
 }
 
 // iteration start: currentChi, iniChi, lambda init at iteration 0 (optimization_algorithm_levenberg.cpp:75-97,166-180)
-__device__ __forceinline__ void begin_window(const BaView& v, int w) {
+__device__ __forceinline__ void begin_window(const BaView& v, int w, bool pose_diag_in_max = false) {
   const double chi = v.w_red_sum[4 * w + 0];
   const int nact = (int)(v.w_red_sum[4 * w + 2] + 0.5);
   if (nact == 0 && v.w_iter[w] == 0) {  // empty index mapping: optimize() returns without iterating
@@ -468,7 +468,7 @@ __device__ __forceinline__ void begin_window(const BaView& v, int w) {
   v.w_trials[w] = 0;
   if (v.w_iter[w] == 0) {
     double mx = v.w_red_max[w];
-    for (int g = v.w_g0[w]; g < v.w_g0[w + 1]; g++) {
+    for (int g = v.w_g0[w]; g < v.w_g0[w + 1] && !pose_diag_in_max; g++) {
       if (v.g_nact[g] == 0) continue;
       const double* H = v.g_Hpp + 21 * (size_t)g;
       int k = 0;
@@ -494,28 +494,85 @@ __global__ void k_begin(BaView v) {
 }
 
 // single-rank fast path: chunk partial sums of the window's keyframes, landmark scalars and the iteration-start
-// bookkeeping in one CTA per window (saves two launches and their dependent-load latency per LM step)
-__global__ void __launch_bounds__(256) k_begin_fused(BaView v) {
+// bookkeeping in one CTA per window (saves two launches and their dependent-load latency per LM step).
+// 1024 threads and 4-way unrolled independent loads: for a single window this kernel is pure memory latency.
+constexpr int FUSED_RED_TPB = 1024;
+__global__ void __launch_bounds__(FUSED_RED_TPB) k_begin_fused(BaView v) {
   const int w = blockIdx.x;
   if (v.w_phase[w] != PH_LIN) return;
   __shared__ double sm[32];
+  __shared__ double spart[4][32 * 28];  // up to 32 free keyframes (dense mode) x 28 values x 4 chunk quarters
   const int g0 = v.w_g0[w], nf = v.w_g0[w + 1] - g0;
-  for (int x = threadIdx.x; x < nf * 28; x += blockDim.x) {
-    const int g = g0 + x / 28, k = x % 28;
-    double s2 = 0;
-    for (int ch = v.g_chp0[g]; ch < v.g_chp0[g + 1]; ch++) s2 += v.ch_pose[28 * (size_t)ch + k];
-    for (int ch = v.g_chl0[g]; ch < v.g_chl0[g + 1]; ch++) s2 += v.ch_pose[28 * (size_t)ch + k];
-    if (k < 21) v.g_Hpp[21 * (size_t)g + k] = s2;
-    else if (k < 27) v.g_bp[6 * (size_t)g + (k - 21)] = s2;
-    else v.g_nact[g] = (int)(s2 + 0.5);
+  const int tid = threadIdx.x;
+  const bool small = nf >= 1 && nf <= 32;
+  const int parts = small ? min(4, FUSED_RED_TPB / (nf * 28)) : 1;   // 1..4 slices of every keyframe's chunk range
+  if (small) {  // thread = (slice of the chunk range, keyframe, value); the slices are added in fixed order
+    const int qtr = tid / (nf * 28), x = tid - qtr * (nf * 28);
+    if (qtr < parts) {
+      const int g = g0 + x / 28, k = x % 28;
+      double s2 = 0;
+      for (int rng = 0; rng < 2; rng++) {  // the quarter's share of the point chunks, then of the line chunks
+        const int c0 = rng == 0 ? v.g_chp0[g] : v.g_chl0[g], c1 = rng == 0 ? v.g_chp0[g + 1] : v.g_chl0[g + 1];
+        const int n = c1 - c0, b = c0 + (n * qtr) / parts, e = c0 + (n * (qtr + 1)) / parts;
+        int ch = b;
+        for (; ch + 4 <= e; ch += 4) {
+          const double a0 = v.ch_pose[28 * (size_t)ch + k], a1 = v.ch_pose[28 * (size_t)(ch + 1) + k],
+                       a2 = v.ch_pose[28 * (size_t)(ch + 2) + k], a3 = v.ch_pose[28 * (size_t)(ch + 3) + k];
+          s2 += a0; s2 += a1; s2 += a2; s2 += a3;
+        }
+        for (; ch < e; ch++) s2 += v.ch_pose[28 * (size_t)ch + k];
+      }
+      spart[qtr][x] = s2;
+    }
   }
+  __syncthreads();
+  if (small) {
+    for (int x = tid; x < nf * 28; x += blockDim.x) {
+      const int g = g0 + x / 28, k = x % 28;
+      double s2 = spart[0][x];
+      for (int q = 1; q < parts; q++) s2 += spart[q][x];
+      if (k < 21) v.g_Hpp[21 * (size_t)g + k] = s2;
+      else if (k < 27) v.g_bp[6 * (size_t)g + (k - 21)] = s2;
+      else v.g_nact[g] = (int)(s2 + 0.5);
+    }
+  } else {
+    for (int x = tid; x < nf * 28; x += blockDim.x) {
+      const int g = g0 + x / 28, k = x % 28;
+      double s2 = 0;
+      for (int ch = v.g_chp0[g]; ch < v.g_chp0[g + 1]; ch++) s2 += v.ch_pose[28 * (size_t)ch + k];
+      for (int ch = v.g_chl0[g]; ch < v.g_chl0[g + 1]; ch++) s2 += v.ch_pose[28 * (size_t)ch + k];
+      if (k < 21) v.g_Hpp[21 * (size_t)g + k] = s2;
+      else if (k < 27) v.g_bp[6 * (size_t)g + (k - 21)] = s2;
+      else v.g_nact[g] = (int)(s2 + 0.5);
+    }
+  }
+  __syncthreads();
   double chi = 0, mx = 0, na = 0;
-  for (int p = v.pt_off[w] + threadIdx.x; p < v.pt_off[w + 1]; p += blockDim.x) {
-    chi += v.lm_chi2lin[p];
-    mx = fmax(mx, v.lm_maxdiag[p]);
-    na += v.lm_active[p] ? 1.0 : 0.0;
+  for (int x = tid; x < nf * 6; x += blockDim.x) {  // lambda init also looks at the pose diagonal (levenberg.cpp:166-180)
+    const int g = g0 + x / 6, r = x % 6;
+    if (v.g_nact[g] != 0) mx = fmax(mx, fabs(v.g_Hpp[21 * (size_t)g + (r * 6 - (r * (r - 1)) / 2)]));
   }
-  for (int l = v.ln_off[w] + threadIdx.x; l < v.ln_off[w + 1]; l += blockDim.x) {
+  {
+    const int p0 = v.pt_off[w], p1 = v.pt_off[w + 1];
+    int p = p0 + tid;
+    for (; p + 3 * FUSED_RED_TPB < p1; p += 4 * FUSED_RED_TPB) {
+      const double c0 = v.lm_chi2lin[p], c1 = v.lm_chi2lin[p + FUSED_RED_TPB], c2 = v.lm_chi2lin[p + 2 * FUSED_RED_TPB],
+                   c3 = v.lm_chi2lin[p + 3 * FUSED_RED_TPB];
+      const double m0 = v.lm_maxdiag[p], m1 = v.lm_maxdiag[p + FUSED_RED_TPB], m2 = v.lm_maxdiag[p + 2 * FUSED_RED_TPB],
+                   m3 = v.lm_maxdiag[p + 3 * FUSED_RED_TPB];
+      const int a0 = v.lm_active[p], a1 = v.lm_active[p + FUSED_RED_TPB], a2 = v.lm_active[p + 2 * FUSED_RED_TPB],
+                a3 = v.lm_active[p + 3 * FUSED_RED_TPB];
+      chi += c0; chi += c1; chi += c2; chi += c3;
+      mx = fmax(fmax(fmax(mx, m0), fmax(m1, m2)), m3);
+      na += (a0 ? 1.0 : 0.0) + (a1 ? 1.0 : 0.0) + (a2 ? 1.0 : 0.0) + (a3 ? 1.0 : 0.0);
+    }
+    for (; p < p1; p += FUSED_RED_TPB) {
+      chi += v.lm_chi2lin[p];
+      mx = fmax(mx, v.lm_maxdiag[p]);
+      na += v.lm_active[p] ? 1.0 : 0.0;
+    }
+  }
+  for (int l = v.ln_off[w] + tid; l < v.ln_off[w + 1]; l += blockDim.x) {
     chi += v.lm_chi2lin[v.n_pt + l];
     mx = fmax(mx, v.lm_maxdiag[v.n_pt + l]);
     na += v.lm_active[v.n_pt + l] ? 1.0 : 0.0;
@@ -523,14 +580,13 @@ __global__ void __launch_bounds__(256) k_begin_fused(BaView v) {
   chi = block_sum(chi, sm);
   na = block_sum(na, sm);
   mx = block_max(mx, sm);
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     v.w_red_sum[4 * w + 0] = chi;
     v.w_red_sum[4 * w + 1] = 0.0;
     v.w_red_sum[4 * w + 2] = na;
     v.w_red_max[w] = mx;
   }
-  __syncthreads();   // g_Hpp / g_nact written above are read by begin_window (same CTA, global memory)
-  if (threadIdx.x == 0) begin_window(v, w);
+  if (tid == 0) begin_window(v, w, true);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1732,22 +1788,35 @@ __global__ void k_decide(BaView v, int round, int stop_now) {
 }
 
 // single-rank fast path: trial reduction + decision in one CTA per window
-__global__ void __launch_bounds__(256) k_decide_fused(BaView v, int round, int stop_now) {
+__global__ void __launch_bounds__(FUSED_RED_TPB) k_decide_fused(BaView v, int round, int stop_now) {
   const int w = blockIdx.x;
   if (v.w_phase[w] == PH_DONE) return;
   __shared__ double sm[32];
+  const int tid = threadIdx.x;
   double chi = 0, sc = 0;
-  for (int p = v.pt_off[w] + threadIdx.x; p < v.pt_off[w + 1]; p += blockDim.x) {
-    chi += v.lm_chi2[p];
-    sc += v.lm_scale[p];
+  {
+    const int p1 = v.pt_off[w + 1];
+    int p = v.pt_off[w] + tid;
+    for (; p + 3 * FUSED_RED_TPB < p1; p += 4 * FUSED_RED_TPB) {
+      const double c0 = v.lm_chi2[p], c1 = v.lm_chi2[p + FUSED_RED_TPB], c2 = v.lm_chi2[p + 2 * FUSED_RED_TPB],
+                   c3 = v.lm_chi2[p + 3 * FUSED_RED_TPB];
+      const double s0 = v.lm_scale[p], s1 = v.lm_scale[p + FUSED_RED_TPB], s2 = v.lm_scale[p + 2 * FUSED_RED_TPB],
+                   s3 = v.lm_scale[p + 3 * FUSED_RED_TPB];
+      chi += c0; chi += c1; chi += c2; chi += c3;
+      sc += s0; sc += s1; sc += s2; sc += s3;
+    }
+    for (; p < p1; p += FUSED_RED_TPB) {
+      chi += v.lm_chi2[p];
+      sc += v.lm_scale[p];
+    }
   }
-  for (int l = v.ln_off[w] + threadIdx.x; l < v.ln_off[w + 1]; l += blockDim.x) {
+  for (int l = v.ln_off[w] + tid; l < v.ln_off[w + 1]; l += blockDim.x) {
     chi += v.lm_chi2[v.n_pt + l];
     sc += v.lm_scale[v.n_pt + l];
   }
   chi = block_sum(chi, sm);
   sc = block_sum(sc, sm);
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     v.w_red_sum[4 * w + 0] = chi;
     v.w_red_sum[4 * w + 1] = sc;
     decide_window(v, w, round, stop_now);
