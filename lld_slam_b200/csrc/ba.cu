@@ -7,6 +7,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <cstdlib>
 #include <numeric>
@@ -23,6 +26,8 @@ using namespace lld;
 
 static const int CHUNK = 256;          // edge-list entries per chunk (k_lin_poses / k_schur_rows CTA)
 static const int SMEM_SOLVE_MAX_N = 156;  // dense LDL^T in shared memory up to this dimension (26 free KFs)
+
+void lld_ba_state_free(struct BaState* s);
 
 struct BaState {
   BaView v{};
@@ -58,10 +63,135 @@ struct BaState {
   }
 };
 
+// Host-side scratch of the flattening / indexing stage, kept in the context across calls: fresh allocations of this size
+// cost more in page faults and zero fill than the indexing itself.
+// page-locked storage for the index tables (asynchronous DMA instead of staged copies); plain malloc without a device
+template <typename T>
+struct PinnedAlloc {
+  using value_type = T;
+  PinnedAlloc() = default;
+  template <class U>
+  PinnedAlloc(const PinnedAlloc<U>&) {}
+  T* allocate(size_t n) {
+    void* p = nullptr;
+    const size_t bytes = n * sizeof(T) + 16;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) {
+      *reinterpret_cast<uint64_t*>(p) = 1;
+    } else {
+      cudaGetLastError();
+      p = malloc(bytes);
+      if (!p) throw std::bad_alloc();
+      *reinterpret_cast<uint64_t*>(p) = 0;
+    }
+    return reinterpret_cast<T*>(reinterpret_cast<char*>(p) + 16);
+  }
+  void deallocate(T* q, size_t) {
+    void* p = reinterpret_cast<char*>(q) - 16;
+    if (*reinterpret_cast<uint64_t*>(p)) cudaFreeHost(p);
+    else free(p);
+  }
+  template <class U>
+  bool operator==(const PinnedAlloc<U>&) const { return true; }
+  template <class U>
+  bool operator!=(const PinnedAlloc<U>&) const { return false; }
+};
+template <typename T>
+using pvec = std::vector<T, PinnedAlloc<T>>;
+
+struct BaDenseJob {
+  std::vector<int> pb, pe, pn, itp, itt;
+  std::vector<long long> pout;
+  std::vector<std::pair<int, long long>> gb, gv;
+  long long dsize = 0;
+  void clear() { pb.clear(); pe.clear(); pn.clear(); itp.clear(); itt.clear(); pout.clear(); gb.clear(); gv.clear(); dsize = 0; }
+};
+struct BaHost {
+  pvec<int> kf_win, pt_win, ln_win, kf_g, w_g0, g_kf;
+  pvec<int> pe_kf, pe_pt, lc_kf, lc_ln;
+  pvec<int> pt_order, ln_order;
+  std::vector<uint64_t> pt_key, ln_key;
+  pvec<int> pl_off, pl_edge, pe_pos, ll_off, ll_cell, lc_pos;
+  pvec<int> pt_spos, ln_spos, pts_w0, lns_w0, pe_wpos, lc_wpos;
+  pvec<uint32_t> pts_mask, lns_mask;
+  pvec<int> it_piece, it_task0, pc_begin, pc_end, pc_n, gb_off, gv_off;
+  pvec<long long> pc_out, gb_src, gv_src;
+  std::vector<BaDenseJob> jobs;
+  pvec<int> ch_g, ch_begin, ch_end, ch_seg0, seg_begin, seg_end, g_chp0, g_chl0;
+  pvec<long long> ch_S_off;
+  // persistent worker threads for the per-window loops
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  std::function<void(int)> job;
+  std::atomic<int> next{0};
+  int job_n = 0, generation = 0, running = 0;
+  bool quit = false;
+  void worker_loop() {
+    int seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_go.wait(lk, [&] { return quit || generation != seen; });
+        if (quit) return;
+        seen = generation;
+      }
+      for (;;) {
+        const int i = next.fetch_add(1);
+        if (i >= job_n) break;
+        job(i);
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (--running == 0) cv_done.notify_one();
+      }
+    }
+  }
+  template <class F>
+  void par_for(int n, F f) {
+    if (n < 4) {
+      for (int i = 0; i < n; i++) f(i);
+      return;
+    }
+    if (workers.empty()) {
+      const unsigned nt = std::min<unsigned>(std::max(2u, std::thread::hardware_concurrency()), 16u) - 1;
+      for (unsigned t = 0; t < nt; t++) workers.emplace_back([this] { worker_loop(); });
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      job = f;
+      job_n = n;
+      next.store(0);
+      running = (int)workers.size();
+      generation++;
+    }
+    cv_go.notify_all();
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n) break;
+      f(i);
+    }
+    std::unique_lock<std::mutex> lk(mu);
+    cv_done.wait(lk, [&] { return running == 0; });
+  }
+  ~BaHost() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      quit = true;
+    }
+    cv_go.notify_all();
+    for (auto& t : workers) t.join();
+  }
+};
+void lld_ba_host_free(void* h) { delete reinterpret_cast<BaHost*>(h); }
+
 namespace {
 
 template <typename T>
 int up(LldCtx* c, T** dst, const T* src, size_t n, size_t* bytes) {
+  if (c->host_only) {  // lld_ba_index_only: time / test the host stage without a device
+    *dst = nullptr;
+    return LLD_OK;
+  }
   cudaError_t e = cudaSuccess;
   T* d = c->alloc<T>(n ? n : 1, &e);
   if (e != cudaSuccess) {
@@ -92,27 +222,6 @@ int up(LldCtx* c, T** dst, const T* src, size_t n, size_t* bytes) {
     (dst) = _p;                                                             \
   } while (0)
 
-// host-side parallel loop over independent windows (the indexing of a 64-window batch is ~60 ms on one core)
-template <class F>
-void par_for(int n, F f) {
-  unsigned nt = std::min<unsigned>(std::min<unsigned>(std::thread::hardware_concurrency(), 16u), (unsigned)std::max(n, 1));
-  if (nt <= 1 || n < 4) {
-    for (int i = 0; i < n; i++) f(i);
-    return;
-  }
-  std::atomic<int> next{0};
-  std::vector<std::thread> th;
-  for (unsigned t = 0; t < nt; t++)
-    th.emplace_back([&] {
-      for (;;) {
-        const int i = next.fetch_add(1);
-        if (i >= n) break;
-        f(i);
-      }
-    });
-  for (auto& t : th) t.join();
-}
-
 }  // namespace
 
 // Flatten + index the problem on the host, upload, initialise device state.
@@ -132,6 +241,32 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   v.n_win = nw; v.n_kf = n_kf; v.n_pt = n_pt; v.n_ln = n_ln; v.n_pe = n_pe; v.n_lc = n_lc;
   S->n_win = nw;
 
+  // ---- caller-owned arrays first: with pinned host memory these DMA transfers run while the host builds the index tables ----
+  int* tmp_i;
+  double* tmp_d;
+  float* tmp_f;
+  uint8_t* tmp_u;
+  UP(tmp_i, p->kf_off, nw + 1); v.kf_off = tmp_i;
+  UP(tmp_i, p->pt_off, nw + 1); v.pt_off = tmp_i;
+  UP(tmp_i, p->ln_off, nw + 1); v.ln_off = tmp_i;
+  UP(tmp_d, p->kf_intr, 5 * (size_t)n_kf); v.kf_intr = tmp_d;
+  UP(tmp_d, p->kf_line_cam, 4 * (size_t)n_kf); v.kf_lcam = tmp_d;
+  UP(tmp_i, p->pt_obs_off, n_pt + 1); v.pt_obs_off = tmp_i;
+  UP(tmp_f, p->pt_obs_uvr, 3 * (size_t)n_pe); v.pe_uvr = tmp_f;
+  UP(tmp_f, p->pt_obs_info, n_pe); v.pe_info = tmp_f;
+  UP(tmp_i, p->ln_obs_off, n_ln + 1); v.ln_obs_off = tmp_i;
+  UP(tmp_f, p->ln_obs_left, 4 * (size_t)n_lc); v.lc_left = tmp_f;
+  UP(tmp_f, p->ln_obs_right, 4 * (size_t)n_lc); v.lc_right = tmp_f;
+  UP(tmp_d, p->ln_obs_info, 2 * (size_t)n_lc); v.lc_info = tmp_d;
+  UP(tmp_u, p->ln_obs_stereo, n_lc); v.lc_stereo = tmp_u;
+  {
+    double *d_T, *d_P, *d_L;
+    UP(d_T, p->kf_Tcw, 12 * (size_t)n_kf);
+    UP(d_P, p->pt_xyz, 3 * (size_t)n_pt);
+    UP(d_L, p->ln_x0_dir, 6 * (size_t)n_ln);
+    S->d_kf_Tcw_in = d_T; S->d_pt_in = d_P; S->d_ln_in = d_L;
+  }
+
   // ---- host indexing ----
   const bool timing = getenv("LLD_TIMING") != nullptr;
   auto t_prev = std::chrono::steady_clock::now();
@@ -141,8 +276,13 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     fprintf(stderr, "[lld_ba_upload] %-28s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(now - t_prev).count());
     t_prev = now;
   };
-  std::vector<int> kf_win(n_kf), pt_win(n_pt), ln_win(n_ln), kf_g(n_kf, -1), w_g0(nw + 1, 0);
-  std::vector<int> g_kf;
+  if (!c->ba_host) c->ba_host = new BaHost();
+  BaHost& H = *reinterpret_cast<BaHost*>(c->ba_host);
+  auto par_for = [&](int n, auto f) { H.par_for(n, f); };
+  auto& kf_win = H.kf_win; auto& pt_win = H.pt_win; auto& ln_win = H.ln_win; auto& kf_g = H.kf_g; auto& w_g0 = H.w_g0;
+  auto& g_kf = H.g_kf;
+  kf_win.resize(n_kf); pt_win.resize(n_pt); ln_win.resize(n_ln); kf_g.assign(n_kf, -1); w_g0.assign(nw + 1, 0);
+  g_kf.clear();
   for (int w = 0; w < nw; w++) {
     w_g0[w] = (int)g_kf.size();
     for (int k = p->kf_off[w]; k < p->kf_off[w + 1]; k++) {
@@ -160,7 +300,8 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   const int nG = (int)g_kf.size();
   v.n_free_total = nG;
 
-  std::vector<int> pe_kf(n_pe), pe_pt(n_pe), lc_kf(n_lc), lc_ln(n_lc);
+  auto& pe_kf = H.pe_kf; auto& pe_pt = H.pe_pt; auto& lc_kf = H.lc_kf; auto& lc_ln = H.lc_ln;
+  pe_kf.resize(n_pe); pe_pt.resize(n_pe); lc_kf.resize(n_lc); lc_ln.resize(n_lc);
   std::atomic<int> bad_arg{0};
   par_for(nw, [&](int w) {
     const int k0 = p->kf_off[w], nk = p->kf_off[w + 1] - k0;
@@ -187,7 +328,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   // Landmarks with the same signature are made adjacent in every keyframe's list, so k_schur_rows can test
   // "does neighbour j see these landmarks" once per segment instead of once per entry.
   std::atomic<int> dup_free{0};   // a landmark observed twice by the same free keyframe (never happens in the reference)
-  auto signature = [&](const int* off, const std::vector<int>& ekf, int i, int g0, int nf) -> uint64_t {
+  auto signature = [&](const int* off, const pvec<int>& ekf, int i, int g0, int nf) -> uint64_t {
     uint64_t key = 0;
     if (nf <= 64) {
       for (int e = off[i]; e < off[i + 1]; e++) {
@@ -208,16 +349,26 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     }
     return key;
   };
-  std::vector<int> pt_order(n_pt), ln_order(n_ln);
-  std::vector<uint64_t> pt_key(n_pt), ln_key(n_ln);
+  auto& pt_order = H.pt_order; auto& ln_order = H.ln_order; auto& pt_key = H.pt_key; auto& ln_key = H.ln_key;
+  pt_order.resize(n_pt); ln_order.resize(n_ln); pt_key.resize(n_pt); ln_key.resize(n_ln);
   par_for(nw, [&](int w) {
     const int g0 = w_g0[w], nf = w_g0[w + 1] - g0;
-    for (int i = p->pt_off[w]; i < p->pt_off[w + 1]; i++) { pt_key[i] = signature(p->pt_obs_off, pe_kf, i, g0, nf); pt_order[i] = i; }
-    std::stable_sort(pt_order.begin() + p->pt_off[w], pt_order.begin() + p->pt_off[w + 1],
-                     [&](int a, int b) { return pt_key[a] < pt_key[b]; });
-    for (int i = p->ln_off[w]; i < p->ln_off[w + 1]; i++) { ln_key[i] = signature(p->ln_obs_off, lc_kf, i, g0, nf); ln_order[i] = i; }
-    std::stable_sort(ln_order.begin() + p->ln_off[w], ln_order.begin() + p->ln_off[w + 1],
-                     [&](int a, int b) { return ln_key[a] < ln_key[b]; });
+    // stable order by signature; with <= 32 free keyframes the key and the landmark's window-local index fit one 64-bit word
+    auto sort_by_key = [&](const int* lm_off, const int* off, const pvec<int>& ekf, std::vector<uint64_t>& key, pvec<int>& order) {
+      const int b = lm_off[w], e = lm_off[w + 1];
+      for (int i = b; i < e; i++) key[i] = signature(off, ekf, i, g0, nf);
+      if (nf <= 32) {
+        std::vector<uint64_t> packed((size_t)(e - b));
+        for (int i = b; i < e; i++) packed[i - b] = (key[i] << 32) | (uint32_t)(i - b);
+        std::sort(packed.begin(), packed.end());
+        for (int i = b; i < e; i++) order[i] = b + (int)(packed[i - b] & 0xffffffffu);
+      } else {
+        for (int i = b; i < e; i++) order[i] = i;
+        std::stable_sort(order.begin() + b, order.begin() + e, [&](int x, int y) { return key[x] < key[y]; });
+      }
+    };
+    sort_by_key(p->pt_off, p->pt_obs_off, pe_kf, pt_key, pt_order);
+    sort_by_key(p->ln_off, p->ln_obs_off, lc_kf, ln_key, ln_order);
   });
   stage("signature sort");
   // dense mode: every window small enough to keep its whole S in registers / one edge per (landmark, free KF)
@@ -225,8 +376,8 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   LLD_ARG(c, dup_free.load() == 0 || !global_mode);
   v.dense_mode = dense ? 1 : 0;
   // per-free-keyframe lists (counting sort in signature order), separately for point edges and line cells
-  auto build_lists = [&](int n_lm, const int* lm_off, const int* off, const std::vector<int>& ekf, const std::vector<int>& order,
-                         std::vector<int>& l_off, std::vector<int>& l_ref, std::vector<int>& e_pos) {
+  auto build_lists = [&](int n_lm, const int* lm_off, const int* off, const pvec<int>& ekf, const pvec<int>& order,
+                         pvec<int>& l_off, pvec<int>& l_ref, pvec<int>& e_pos) {
     l_off.assign(nG + 1, 0);
     const int n_e = n_lm ? off[n_lm] : 0;
     par_for(nw, [&](int w) {   // a window's edges only touch the window's own free blocks
@@ -234,22 +385,23 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         if (kf_g[ekf[e]] >= 0) l_off[kf_g[ekf[e]] + 1]++;
     });
     for (int g = 0; g < nG; g++) l_off[g + 1] += l_off[g];
-    l_ref.assign(std::max(l_off[nG], 1), 0);
-    e_pos.assign(std::max(n_e, 1), -1);
+    l_ref.resize(std::max(l_off[nG], 1));
+    e_pos.resize(std::max(n_e, 1));
     std::vector<int> cur(l_off.begin(), l_off.end() - 1);
     par_for(nw, [&](int w) {
       for (int oi = lm_off[w]; oi < lm_off[w + 1]; oi++) {
         const int i = order[oi];
         for (int e = off[i]; e < off[i + 1]; e++) {
           const int g = kf_g[ekf[e]];
-          if (g < 0) continue;
+          if (g < 0) { e_pos[e] = -1; continue; }
           e_pos[e] = cur[g];
           l_ref[cur[g]++] = e;
         }
       }
     });
   };
-  std::vector<int> pl_off, pl_edge, pe_pos, ll_off, ll_cell, lc_pos;
+  auto& pl_off = H.pl_off; auto& pl_edge = H.pl_edge; auto& pe_pos = H.pe_pos;
+  auto& ll_off = H.ll_off; auto& ll_cell = H.ll_cell; auto& lc_pos = H.lc_pos;
   build_lists(n_pt, p->pt_off, p->pt_obs_off, pe_kf, pt_order, pl_off, pl_edge, pe_pos);
   build_lists(n_ln, p->ln_off, p->ln_obs_off, lc_kf, ln_order, ll_off, ll_cell, lc_pos);
   const int n_plist = pl_off[nG], n_llist = ll_off[nG];
@@ -302,8 +454,8 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   S->n_nb_total = nb_g.size();
   LLD_ARG(c, 6 * S->max_nnb <= 1024);
   // position tables: per list entry and neighbour, the list position of the co-edge (or -1)
-  auto build_tab = [&](const std::vector<int>& l_off, const std::vector<int>& l_ref, const int* off, const std::vector<int>& e_lm,
-                       const std::vector<int>& ekf, const std::vector<int>& e_pos, std::vector<long long>& t_off, std::vector<int>& tab) {
+  auto build_tab = [&](const pvec<int>& l_off, const pvec<int>& l_ref, const int* off, const pvec<int>& e_lm,
+                       const pvec<int>& ekf, const pvec<int>& e_pos, std::vector<long long>& t_off, std::vector<int>& tab) {
     t_off.assign(std::max(nG, 1), 0);
     long long tot = 0;
     for (int g = 0; g < nG; g++) {
@@ -334,19 +486,24 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   }
   stage("neighbours + tabs");
   // dense-mode structures
-  std::vector<int> pt_spos(std::max(n_pt, 1), 0), ln_spos(std::max(n_ln, 1), 0), pts_w0(n_pt + 1, 0), lns_w0(n_ln + 1, 0);
-  std::vector<uint32_t> pts_mask(std::max(n_pt, 1), 0), lns_mask(std::max(n_ln, 1), 0);
-  std::vector<int> pe_wpos(std::max(n_pe, 1), -1), lc_wpos(std::max(n_lc, 1), -1);
-  std::vector<int> it_piece, it_task0, pc_begin, pc_end, pc_n, gb_off(1, 0), gv_off(1, 0);
-  std::vector<long long> pc_out, gb_src(1, 0), gv_src(1, 0);
+  auto& pt_spos = H.pt_spos; auto& ln_spos = H.ln_spos; auto& pts_w0 = H.pts_w0; auto& lns_w0 = H.lns_w0;
+  auto& pts_mask = H.pts_mask; auto& lns_mask = H.lns_mask; auto& pe_wpos = H.pe_wpos; auto& lc_wpos = H.lc_wpos;
+  auto& it_piece = H.it_piece; auto& it_task0 = H.it_task0; auto& pc_begin = H.pc_begin; auto& pc_end = H.pc_end; auto& pc_n = H.pc_n;
+  auto& gb_off = H.gb_off; auto& gv_off = H.gv_off; auto& pc_out = H.pc_out; auto& gb_src = H.gb_src; auto& gv_src = H.gv_src;
+  pt_spos.resize(std::max(n_pt, 1)); ln_spos.resize(std::max(n_ln, 1)); pts_w0.resize(n_pt + 1); lns_w0.resize(n_ln + 1);
+  pts_w0[0] = 0; lns_w0[0] = 0;
+  pts_mask.resize(std::max(n_pt, 1)); lns_mask.resize(std::max(n_ln, 1));
+  pe_wpos.resize(std::max(n_pe, 1)); lc_wpos.resize(std::max(n_lc, 1));   // -1 for fixed-keyframe edges is written below / not read otherwise
+  it_piece.clear(); it_task0.clear(); pc_begin.clear(); pc_end.clear(); pc_n.clear(); pc_out.clear();
+  gb_off.assign(1, 0); gv_off.assign(1, 0); gb_src.assign(1, 0); gv_src.assign(1, 0);
   long long dpart_total = 0;
   int n_items_pt = 0;
   size_t n_pw = 0, n_lw = 0;
   if (dense) {
     // W slots: landmarks in signature order, each landmark's free edges sorted by keyframe
-    auto slots = [&](int n_lm, const int* lm_off, const int* off, const std::vector<int>& ekf, const std::vector<int>& order,
-                     const std::vector<uint64_t>& key, std::vector<int>& spos, std::vector<uint32_t>& mask,
-                     std::vector<int>& w0, std::vector<int>& wpos) {
+    auto slots = [&](int n_lm, const int* lm_off, const int* off, const pvec<int>& ekf, const pvec<int>& order,
+                     const std::vector<uint64_t>& key, pvec<int>& spos, pvec<uint32_t>& mask,
+                     pvec<int>& w0, pvec<int>& wpos) {
       par_for(nw, [&](int w) {
         for (int oi = lm_off[w]; oi < lm_off[w + 1]; oi++) {
           const int i = order[oi];
@@ -361,8 +518,10 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         for (int oi = lm_off[w]; oi < lm_off[w + 1]; oi++) {
           const int i = order[oi];
           int n = 0;
-          for (int e = off[i]; e < off[i + 1]; e++)
+          for (int e = off[i]; e < off[i + 1]; e++) {
             if (kf_g[ekf[e]] >= 0) ge[n++] = {kf_g[ekf[e]], e};
+            else wpos[e] = -1;
+          }
           std::sort(ge, ge + n);
           for (int k = 0; k < n; k++) wpos[ge[k].second] = w0[oi] + k;
         }
@@ -374,18 +533,16 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     int PIECE_CAP = 128;  // shorter pieces when the batch is small, so that every SM gets warps
     while (PIECE_CAP > 8 && (long long)(n_pt + n_ln) * 5 / (2 * PIECE_CAP) < 16LL * c->sm_count) PIECE_CAP >>= 1;
     // pieces / items / gather entries: built per (kind, window) with local offsets, merged in order afterwards
-    struct Job {
-      std::vector<int> pb, pe, pn, itp, itt;
-      std::vector<long long> pout;
-      std::vector<std::pair<int, long long>> gb, gv;
-      long long dsize = 0;
-    };
-    std::vector<Job> jobs(2 * (size_t)nw);
+    using Job = BaDenseJob;
+    auto& jobs = H.jobs;
+    if (jobs.size() < 2 * (size_t)nw) jobs.resize(2 * (size_t)nw);
+    for (size_t j = 0; j < 2 * (size_t)nw; j++) jobs[j].clear();
+    const size_t n_jobs = 2 * (size_t)nw;
     par_for(2 * nw, [&](int jid) {
       const int kind = jid / nw, w = jid % nw;
       Job& J = jobs[jid];
       const int* loff = kind == 0 ? p->pt_off : p->ln_off;
-      const std::vector<uint32_t>& mask = kind == 0 ? pts_mask : lns_mask;
+      const pvec<uint32_t>& mask = kind == 0 ? pts_mask : lns_mask;
       const int g0 = w_g0[w];
       int b = loff[w];
       while (b < loff[w + 1]) {
@@ -410,34 +567,50 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         b = e;
       }
     });
+    // merge the per-(kind, window) jobs: serial prefix over the job sizes, everything else per job / per window in parallel
+    std::vector<long long> jd(n_jobs + 1, 0);
+    std::vector<int> jp(n_jobs + 1, 0), ji(n_jobs + 1, 0);
+    for (size_t jid = 0; jid < n_jobs; jid++) {
+      jd[jid + 1] = jd[jid] + jobs[jid].dsize;
+      jp[jid + 1] = jp[jid] + (int)jobs[jid].pb.size();
+      ji[jid + 1] = ji[jid] + (int)jobs[jid].itp.size();
+    }
+    dpart_total = jd[n_jobs];
+    n_items_pt = ji[std::min<size_t>((size_t)nw, n_jobs)];
+    pc_begin.resize(jp[n_jobs]); pc_end.resize(jp[n_jobs]); pc_n.resize(jp[n_jobs]); pc_out.resize(jp[n_jobs]);
+    it_piece.resize(ji[n_jobs]); it_task0.resize(ji[n_jobs]);
     gb_off.assign(nb_g.size() + 1, 0);
     gv_off.assign(nG + 1, 0);
-    for (size_t jid = 0; jid < jobs.size(); jid++) {
+    par_for((int)n_jobs, [&](int jid) {
       Job& J = jobs[jid];
-      if (jid == (size_t)nw) n_items_pt = (int)it_piece.size();
-      const int pbase = (int)pc_begin.size();
-      pc_begin.insert(pc_begin.end(), J.pb.begin(), J.pb.end());
-      pc_end.insert(pc_end.end(), J.pe.begin(), J.pe.end());
-      pc_n.insert(pc_n.end(), J.pn.begin(), J.pn.end());
-      for (long long o : J.pout) pc_out.push_back(o + dpart_total);
-      for (int x : J.itp) it_piece.push_back(x + pbase);
-      it_task0.insert(it_task0.end(), J.itt.begin(), J.itt.end());
-      for (auto& x : J.gb) { gb_off[x.first + 1]++; x.second += dpart_total; }
-      for (auto& x : J.gv) { gv_off[x.first + 1]++; x.second += dpart_total; }
-      dpart_total += J.dsize;
-    }
-    if (nw == 0 || jobs.size() <= (size_t)nw) n_items_pt = (int)it_piece.size();
+      const int pbase = jp[jid], ibase = ji[jid];
+      for (size_t k = 0; k < J.pb.size(); k++) {
+        pc_begin[pbase + k] = J.pb[k]; pc_end[pbase + k] = J.pe[k]; pc_n[pbase + k] = J.pn[k]; pc_out[pbase + k] = J.pout[k] + jd[jid];
+      }
+      for (size_t k = 0; k < J.itp.size(); k++) { it_piece[ibase + k] = J.itp[k] + pbase; it_task0[ibase + k] = J.itt[k]; }
+    });
+    // a block / keyframe belongs to one window: its contributions come from that window's point job, then its line job
+    par_for(nw, [&](int w) {
+      for (int kind = 0; kind < 2; kind++) {
+        Job& J = jobs[(size_t)kind * nw + w];
+        for (auto& x : J.gb) gb_off[x.first + 1]++;
+        for (auto& x : J.gv) gv_off[x.first + 1]++;
+      }
+    });
     for (size_t i = 0; i < nb_g.size(); i++) gb_off[i + 1] += gb_off[i];
     for (int i = 0; i < nG; i++) gv_off[i + 1] += gv_off[i];
-    gb_src.assign(std::max<size_t>((size_t)gb_off[nb_g.size()], 1), 0);
-    gv_src.assign(std::max<size_t>((size_t)gv_off[nG], 1), 0);
+    gb_src.resize(std::max<size_t>((size_t)gb_off[nb_g.size()], 1));
+    gv_src.resize(std::max<size_t>((size_t)gv_off[nG], 1));
     {
-      // stable fill in job order (points of window 0.., then lines): a block's contributions keep a fixed order
       std::vector<int> curb(gb_off.begin(), gb_off.end() - 1), curv(gv_off.begin(), gv_off.end() - 1);
-      for (auto& J : jobs) {
-        for (auto& x : J.gb) gb_src[curb[x.first]++] = x.second;
-        for (auto& x : J.gv) gv_src[curv[x.first]++] = x.second;
-      }
+      par_for(nw, [&](int w) {
+        for (int kind = 0; kind < 2; kind++) {
+          const size_t jid = (size_t)kind * nw + w;
+          Job& J = jobs[jid];
+          for (auto& x : J.gb) gb_src[curb[x.first]++] = x.second + jd[jid];
+          for (auto& x : J.gv) gv_src[curv[x.first]++] = x.second + jd[jid];
+        }
+      });
     }
   }
   v.n_items = (int)it_piece.size();
@@ -448,9 +621,12 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   const long long n_list_total = (long long)n_plist + n_llist;
   int CH = CHUNK;
   while (CH > 32 && n_list_total / CH < 2 * (long long)c->sm_count) CH >>= 1;
-  std::vector<int> ch_g, ch_begin, ch_end, ch_seg0, seg_begin, seg_end, g_chp0(nG + 1, 0), g_chl0(nG + 1, 0);
-  auto build_chunks = [&](const std::vector<int>& l_off, const std::vector<long long>& t_off, const std::vector<int>& tab,
-                          std::vector<int>& g_c0) {
+  auto& ch_g = H.ch_g; auto& ch_begin = H.ch_begin; auto& ch_end = H.ch_end; auto& ch_seg0 = H.ch_seg0;
+  auto& seg_begin = H.seg_begin; auto& seg_end = H.seg_end; auto& g_chp0 = H.g_chp0; auto& g_chl0 = H.g_chl0;
+  ch_g.clear(); ch_begin.clear(); ch_end.clear(); ch_seg0.clear(); seg_begin.clear(); seg_end.clear();
+  g_chp0.assign(nG + 1, 0); g_chl0.assign(nG + 1, 0);
+  auto build_chunks = [&](const pvec<int>& l_off, const std::vector<long long>& t_off, const std::vector<int>& tab,
+                          pvec<int>& g_c0) {
     for (int g = 0; g < nG; g++) {
       g_c0[g] = (int)ch_g.size();
       const int nnb = nb_off[g + 1] - nb_off[g];
@@ -481,7 +657,8 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   ch_seg0.push_back((int)seg_begin.size());
   v.n_chunks = n_ch;
   v.n_chunks_pt = n_chp;
-  std::vector<long long> ch_S_off(std::max(n_ch, 1), 0);
+  auto& ch_S_off = H.ch_S_off;
+  ch_S_off.assign(std::max(n_ch, 1), 0);
   long long chS_total = 0;
   for (int ch = 0; ch < n_ch; ch++) {
     ch_S_off[ch] = chS_total;
@@ -543,39 +720,22 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
 
   stage("chunks");
   // ---- upload (timed as h2d) ----
-  int* tmp_i;
-  UP(tmp_i, p->kf_off, nw + 1); v.kf_off = tmp_i;
-  UP(tmp_i, p->pt_off, nw + 1); v.pt_off = tmp_i;
-  UP(tmp_i, p->ln_off, nw + 1); v.ln_off = tmp_i;
   UP(tmp_i, kf_win.data(), n_kf); v.kf_win = tmp_i;
   UP(tmp_i, pt_win.data(), n_pt); v.pt_win = tmp_i;
   UP(tmp_i, ln_win.data(), n_ln); v.ln_win = tmp_i;
   UP(tmp_i, kf_g.data(), n_kf); v.kf_g = tmp_i;
   UP(tmp_i, g_kf.data(), nG); v.g_kf = tmp_i;
   UP(tmp_i, w_g0.data(), nw + 1); v.w_g0 = tmp_i;
-  double* tmp_d;
-  UP(tmp_d, p->kf_intr, 5 * (size_t)n_kf); v.kf_intr = tmp_d;
-  UP(tmp_d, p->kf_line_cam, 4 * (size_t)n_kf); v.kf_lcam = tmp_d;
-  UP(tmp_i, p->pt_obs_off, n_pt + 1); v.pt_obs_off = tmp_i;
   UP(tmp_i, pe_kf.data(), n_pe); v.pe_kf = tmp_i;
   UP(tmp_i, pe_pt.data(), n_pe); v.pe_pt = tmp_i;
-  float* tmp_f;
-  UP(tmp_f, p->pt_obs_uvr, 3 * (size_t)n_pe); v.pe_uvr = tmp_f;
-  UP(tmp_f, p->pt_obs_info, n_pe); v.pe_info = tmp_f;
-  UP(tmp_i, p->ln_obs_off, n_ln + 1); v.ln_obs_off = tmp_i;
   UP(tmp_i, lc_kf.data(), n_lc); v.lc_kf = tmp_i;
   UP(tmp_i, lc_ln.data(), n_lc); v.lc_ln = tmp_i;
-  UP(tmp_f, p->ln_obs_left, 4 * (size_t)n_lc); v.lc_left = tmp_f;
-  UP(tmp_f, p->ln_obs_right, 4 * (size_t)n_lc); v.lc_right = tmp_f;
-  UP(tmp_d, p->ln_obs_info, 2 * (size_t)n_lc); v.lc_info = tmp_d;
-  uint8_t* tmp_u;
-  UP(tmp_u, p->ln_obs_stereo, n_lc); v.lc_stereo = tmp_u;
   UP(tmp_i, pl_off.data(), nG + 1); v.pl_off = tmp_i;
   UP(tmp_i, pl_edge.data(), n_plist); v.pl_edge = tmp_i;
-  UP(tmp_i, pe_pos.data(), n_pe); v.pe_pos = tmp_i;
+  UP(tmp_i, pe_pos.data(), dense ? 0 : n_pe); v.pe_pos = tmp_i;   // list positions are only read outside dense mode
   UP(tmp_i, ll_off.data(), nG + 1); v.ll_off = tmp_i;
   UP(tmp_i, ll_cell.data(), n_llist); v.ll_cell = tmp_i;
-  UP(tmp_i, lc_pos.data(), n_lc); v.lc_pos = tmp_i;
+  UP(tmp_i, lc_pos.data(), dense ? 0 : n_lc); v.lc_pos = tmp_i;
   UP(tmp_i, ch_g.data(), n_ch); v.ch_g = tmp_i;
   UP(tmp_i, ch_begin.data(), n_ch); v.ch_begin = tmp_i;
   UP(tmp_i, ch_end.data(), n_ch); v.ch_end = tmp_i;
@@ -622,11 +782,6 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   UP(tmp_i, lo_off.data(), lo_off.size()); v.lo_off = tmp_i;
   UP(tmp_i, lo_col.data(), lo_col.size()); v.lo_col = tmp_i;
   UP(tmp_i, lo_src.data(), lo_src.size()); v.lo_src = tmp_i;
-  double *d_T, *d_P, *d_L;
-  UP(d_T, p->kf_Tcw, 12 * (size_t)n_kf);
-  UP(d_P, p->pt_xyz, 3 * (size_t)n_pt);
-  UP(d_L, p->ln_x0_dir, 6 * (size_t)n_ln);
-  S->d_kf_Tcw_in = d_T; S->d_pt_in = d_P; S->d_ln_in = d_L;
 
   stage("H2D enqueue");
   // ---- device-only buffers ----
@@ -1038,17 +1193,107 @@ extern "C" int lld_ba_download(void* ctx, const lld_ba_problem* p, lld_ba_result
 }
 
 // ---- reference-shaped entry points -------------------------------------------------------------------------
+static int ba_local_single(LldCtx* c, const lld_ba_problem* p, int its1, int its2, const volatile uint8_t* stop, lld_ba_result* out) {
+  c->launches = 0;
+  int r = lld_ba_upload(c, p, 0, its1 + its2 + 2);
+  if (r) return r;
+  LLD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  r = lld_ba_run_local(c, its1, its2, stop);
+  if (r) return r;
+  return ba_download(c, p, out, true);
+}
+
+// Windows are independent, so a large batch is cut into sub-batches that two worker threads (each with its own child
+// context = stream + workspace) push through index -> upload -> LM -> download out of phase: while the GPU runs the LM
+// steps of one sub-batch the host builds the index tables of the next.  Results are written into disjoint slices of
+// the caller's arrays; every window computes exactly what it computes alone.
+static int ba_local_pipelined(LldCtx* c, const lld_ba_problem* p, int its1, int its2, const volatile uint8_t* stop,
+                              lld_ba_result* out, int n_sub) {
+  const int nw = p->n_win, W = 2;
+  for (int i = 0; i < W; i++)
+    if (!c->child[i]) {
+      void* h = nullptr;
+      int r = lld_ctx_create(c->device, &h);
+      if (r) { snprintf(c->err, sizeof(c->err), "pipelined local BA: child context %d failed", i); return r; }
+      c->child[i] = lld_ctx_cast(h);
+    }
+  std::atomic<int> next{0}, rc{0};
+  std::atomic<long long> launches{0}, h2d{0}, d2h{0};
+  auto t0 = std::chrono::steady_clock::now();
+  auto worker = [&](int wi) {
+    LldCtx* cc = c->child[wi];
+    cc->prof_on = false;
+    for (;;) {
+      const int k = next.fetch_add(1);
+      if (k >= n_sub || rc.load() != 0) break;
+      const int w0 = (int)((long long)nw * k / n_sub), w1 = (int)((long long)nw * (k + 1) / n_sub), m = w1 - w0;
+      if (m <= 0) continue;
+      const int k0 = p->kf_off[w0], p0 = p->pt_off[w0], l0 = p->ln_off[w0];
+      const int e0 = p->pt_obs_off[p0], c0 = p->ln_obs_off[l0];
+      const int npt = p->pt_off[w1] - p0, nln = p->ln_off[w1] - l0;
+      std::vector<int32_t> kfo(m + 1), pto(m + 1), lno(m + 1), peo(npt + 1), lco(nln + 1);
+      for (int i = 0; i <= m; i++) { kfo[i] = p->kf_off[w0 + i] - k0; pto[i] = p->pt_off[w0 + i] - p0; lno[i] = p->ln_off[w0 + i] - l0; }
+      for (int i = 0; i <= npt; i++) peo[i] = p->pt_obs_off[p0 + i] - e0;
+      for (int i = 0; i <= nln; i++) lco[i] = p->ln_obs_off[l0 + i] - c0;
+      lld_ba_problem sp = *p;
+      sp.n_win = m; sp.kf_off = kfo.data(); sp.pt_off = pto.data(); sp.ln_off = lno.data();
+      sp.kf_Tcw = p->kf_Tcw + 12 * (size_t)k0; sp.kf_fixed = p->kf_fixed + k0; sp.kf_intr = p->kf_intr + 5 * (size_t)k0;
+      sp.kf_line_cam = p->kf_line_cam + 4 * (size_t)k0;
+      sp.pt_xyz = p->pt_xyz + 3 * (size_t)p0; sp.pt_obs_off = peo.data(); sp.pt_obs_kf = p->pt_obs_kf + e0;
+      sp.pt_obs_uvr = p->pt_obs_uvr + 3 * (size_t)e0; sp.pt_obs_info = p->pt_obs_info + e0;
+      sp.ln_x0_dir = p->ln_x0_dir + 6 * (size_t)l0; sp.ln_obs_off = lco.data(); sp.ln_obs_kf = p->ln_obs_kf + c0;
+      sp.ln_obs_left = p->ln_obs_left + 4 * (size_t)c0; sp.ln_obs_right = p->ln_obs_right + 4 * (size_t)c0;
+      sp.ln_obs_info = p->ln_obs_info + 2 * (size_t)c0; sp.ln_obs_stereo = p->ln_obs_stereo + c0;
+      lld_ba_result so = *out;
+      so.kf_Tcw = out->kf_Tcw + 12 * (size_t)k0; so.pt_xyz = out->pt_xyz + 3 * (size_t)p0; so.ln_x0_dir = out->ln_x0_dir + 6 * (size_t)l0;
+      so.pt_obs_bad = out->pt_obs_bad + e0; so.ln_obs_bad = out->ln_obs_bad + 2 * (size_t)c0; so.ln_removed = out->ln_removed + l0;
+      const size_t ls = (size_t)out->log_stride;
+      so.chi2_log = out->chi2_log ? out->chi2_log + ls * w0 : nullptr;
+      so.lambda_log = out->lambda_log ? out->lambda_log + ls * w0 : nullptr;
+      so.trials_log = out->trials_log ? out->trials_log + ls * w0 : nullptr;
+      so.n_iter_done = out->n_iter_done ? out->n_iter_done + 2 * (size_t)w0 : nullptr;
+      const int r = ba_local_single(cc, &sp, its1, its2, stop, &so);
+      if (r) {
+        int z = 0;
+        if (rc.compare_exchange_strong(z, r)) snprintf(c->err, sizeof(c->err), "%s", cc->err);
+        break;
+      }
+      launches += cc->launches;
+      h2d += (long long)cc->last_h2d_bytes;
+      d2h += (long long)cc->last_d2h_bytes;
+    }
+  };
+  std::thread th(worker, 1);
+  worker(0);
+  th.join();
+  c->launches = launches.load();
+  c->last_h2d_bytes = (size_t)h2d.load();
+  c->last_d2h_bytes = (size_t)d2h.load();
+  c->ms_h2d = 0.f;
+  c->ms_compute = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();  // wall: phases overlap
+  c->ms_d2h = 0.f;
+  return rc.load();
+}
+
 extern "C" int lld_ba_local(void* ctx, const lld_ba_problem* p, int its1, int its2, const volatile uint8_t* stop,
                             lld_ba_result* out) {
   LldCtx* c = lld_ctx_cast(ctx);
   if (!c || !p || !out) return LLD_ERR_ARG;
-  c->launches = 0;
-  int r = lld_ba_upload(ctx, p, 0, its1 + its2 + 2);
-  if (r) return r;
-  LLD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-  r = lld_ba_run_local(ctx, its1, its2, stop);
-  if (r) return r;
-  return ba_download(c, p, out, true);
+  LLD_ARG(c, p->n_win >= 1);
+  // two sub-batches from 16 windows up (measured: more sub-batches lose more GPU efficiency than the overlap wins);
+  // LLD_BA_PIPE=<n> overrides, 0/1 disables
+  int n_sub = p->n_win >= 16 ? 2 : 1;
+  if (const char* e = getenv("LLD_BA_PIPE")) n_sub = std::min(atoi(e), p->n_win);
+  if (n_sub >= 2 && !c->prof_on) return ba_local_pipelined(c, p, its1, its2, stop, out, n_sub);
+  return ba_local_single(c, p, its1, its2, stop, out);
+}
+
+// host-side indexing only (no device needed): used to time / test the flattening stage on a CPU-only box.
+// Returns LLD_ERR_CUDA when it reaches the first device allocation, which is the expected outcome without a GPU.
+extern "C" int lld_ba_index_only(const lld_ba_problem* p, int global_mode) {
+  static LldCtx c;  // keeps the host scratch across calls, like a real context (single-threaded helper)
+  c.host_only = true;
+  return ba_upload(&c, p, global_mode != 0, 8);
 }
 
 // landmark block partition of the multi-rank global BA (host arithmetic only; also used by the CPU-side tests)

@@ -7,6 +7,7 @@
 
 struct BaState;
 void lld_ba_state_free(BaState*);
+void lld_ba_host_free(void*);
 
 extern "C" const char* lld_version(void) { return "lldba 0.1 (sm_100a)"; }
 
@@ -38,6 +39,8 @@ extern "C" int lld_ctx_create(int device, void** out) {
 extern "C" void lld_ctx_destroy(void* ctx) {
   LldCtx* c = lld_ctx_cast(ctx);
   if (!c) return;
+  for (int i = 0; i < 2; i++)
+    if (c->child[i]) { lld_ctx_destroy(c->child[i]); c->child[i] = nullptr; }
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
 #ifdef LLD_WITH_NCCL
@@ -49,6 +52,7 @@ extern "C" void lld_ctx_destroy(void* ctx) {
   for (int i = 0; i < 4; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   lld_ba_state_free(c->ba);  // graphs first: they reference the streams
+  lld_ba_host_free(c->ba_host);
   for (int i = 0; i < 2; i++) {
     if (c->side[i]) cudaStreamDestroy(c->side[i]);
     if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);

@@ -45,6 +45,7 @@ struct LldCtx {
   int64_t launches = 0;
   float ms_h2d = 0, ms_compute = 0, ms_d2h = 0;
   int sm_count = 148;
+  bool host_only = false;  // no device work in the upload helpers (host-stage timing hook)
   // NCCL (global BA)
   ncclComm* comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -55,6 +56,8 @@ struct LldCtx {
   void* pinned = nullptr;
   size_t pinned_cap = 0;
   BaState* ba = nullptr;
+  void* ba_host = nullptr;                // BaHost: persistent host scratch + worker threads of the indexing stage (ba.cu)
+  LldCtx* child[2] = {nullptr, nullptr};  // worker contexts of the pipelined batched local BA (ba.cu)
   size_t last_h2d_bytes = 0, last_d2h_bytes = 0;
   // optional per-launch CUDA-event profiling (bench.py roofline): one event pair around every kernel launch
   struct ProfRec { const char* name; cudaEvent_t a, b; };

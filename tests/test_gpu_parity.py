@@ -77,6 +77,19 @@ def test_local_ba_batch_ragged(gpu_ctx):
     check_ba(g, o, "ragged")
 
 
+def test_local_ba_batch_pipelined(gpu_ctx, monkeypatch):
+    """large batches are cut into sub-batches that two worker contexts pipeline (host indexing of one overlaps the LM steps
+    of the other); forced here on a ragged batch: every window must still match the oracle."""
+    monkeypatch.setenv("LLD_BA_PIPE", "3")
+    rng = np.random.default_rng(8)
+    wins = [synth.make_ba_window(int(rng.integers(4, 12)), int(rng.integers(100, 500)), int(rng.integers(0, 100)), rng)
+            for _ in range(7)]
+    p = synth.batch_ba(wins, "local")
+    g = api.ba_local(p, 5, 15, impl="gpu", ctx=gpu_ctx)
+    o = api.ba_local(p, 5, 15, impl="oracle")
+    check_ba(g, o, "pipelined")
+
+
 def test_local_ba_target_shape(gpu_ctx):
     """north_star target shape 10 KF / 5k points / 1k lines."""
     p = synth.make_local_ba_batch(1, 10, 5000, 1000, 77)
