@@ -75,6 +75,7 @@ struct PinnedAlloc {
   T* allocate(size_t n) {
     void* p = nullptr;
     const size_t bytes = n * sizeof(T) + 16;
+    std::lock_guard<std::mutex> lk(lld_capture_mutex());
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) {
       *reinterpret_cast<uint64_t*>(p) = 1;
     } else {
@@ -87,6 +88,7 @@ struct PinnedAlloc {
   }
   void deallocate(T* q, size_t) {
     void* p = reinterpret_cast<char*>(q) - 16;
+    std::lock_guard<std::mutex> lk(lld_capture_mutex());
     if (*reinterpret_cast<uint64_t*>(p)) cudaFreeHost(p);
     else free(p);
   }
@@ -850,11 +852,10 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     S->use_graph = allow && dense_single;
   }
   // dynamic shared memory opt-in of the solvers (once per upload, outside any stream capture)
-  if (v.env_mode && S->use_band) LLD_CUDA(c, cudaFuncSetAttribute(k_solve_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->band_smem));
-  else if (v.env_mode) LLD_CUDA(c, cudaFuncSetAttribute(k_solve_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->env_smem));
+  if (v.env_mode && S->use_band) LLD_CUDA(c, lld_raise_dyn_smem(k_solve_band, (size_t)(int)S->band_smem));
+  else if (v.env_mode) LLD_CUDA(c, lld_raise_dyn_smem(k_solve_env, (size_t)(int)S->env_smem));
   else if (S->max_n <= SMEM_SOLVE_MAX_N)
-    LLD_CUDA(c, cudaFuncSetAttribute(k_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(sizeof(double) * ((size_t)S->max_n * S->max_n + 8 * (size_t)S->max_n + 8))));
+    LLD_CUDA(c, lld_raise_dyn_smem(k_solve<true>, (size_t)(int)(sizeof(double) * ((size_t)S->max_n * S->max_n + 8 * (size_t)S->max_n + 8))));
   return LLD_OK;
 }
 
@@ -1055,6 +1056,7 @@ static int ba_run_round(LldCtx* c, int maxit, int round, const volatile uint8_t*
         if (!S->step_graph[round]) {  // capture one LM step (fork / join over the side streams included)
           const int64_t l0 = c->launches;
           cudaGraph_t g = nullptr;
+          std::lock_guard<std::mutex> lk(lld_capture_mutex());  // no allocation in any thread while this one captures
           LLD_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
           int r = ba_step(c, round, 0);
           cudaError_t e = cudaStreamEndCapture(c->stream, &g);

@@ -1,4 +1,6 @@
 // ctx.cu — context lifetime, NCCL communicator plumbing, library self-description.
+#include <utility>
+
 #include "lld_ctx.h"
 
 #ifdef LLD_WITH_NCCL
@@ -8,6 +10,27 @@
 struct BaState;
 void lld_ba_state_free(BaState*);
 void lld_ba_host_free(void*);
+
+std::mutex& lld_capture_mutex() {
+  static std::mutex m;
+  return m;
+}
+
+cudaError_t lld_raise_dyn_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> seen;
+  std::lock_guard<std::mutex> lk(mu);
+  for (auto& e : seen)
+    if (e.first == func) {
+      if (bytes <= e.second) return cudaSuccess;
+      cudaError_t r = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (r == cudaSuccess) e.second = bytes;
+      return r;
+    }
+  cudaError_t r = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (r == cudaSuccess) seen.push_back({func, bytes});
+  return r;
+}
 
 extern "C" const char* lld_version(void) { return "lldba 0.1 (sm_100a)"; }
 

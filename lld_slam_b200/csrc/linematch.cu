@@ -16,6 +16,7 @@
 // Tolerance (stated, because LBDMOD is unpinned): |d_gpu - d_oracle| <= 1e-5 * max(1, d); identical matches unless
 // the two best candidates of a row are closer than that.
 #include <cfloat>
+#include <cstdlib>
 #include <vector>
 #include <algorithm>
 
@@ -43,6 +44,8 @@ struct LineMatchView {
   double* right_leq;
   double* left_len;
   double* right_len;
+  double* left_un;    // [n_left][3] unit normal of the back-projection plane (leq / |leq|)
+  double* right_un;
   const long long* mat_off;  // [n_pairs] offset of the pair's nl x nr matrix
   float* dist;        // masked distance matrix, +inf where a gate fails
   int* match;
@@ -63,6 +66,9 @@ __global__ void k_line_prep(LineMatchView v, int n_left, int n_right) {
     const double n2 = sqrt(leq[0] * leq[0] + leq[1] * leq[1]);
     double* o = (side ? v.right_leq : v.left_leq) + 3 * (size_t)i;
     o[0] = leq[0] / n2; o[1] = leq[1] / n2; o[2] = leq[2] / n2;
+    const double n3 = sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]);
+    double* u = (side ? v.right_un : v.left_un) + 3 * (size_t)i;
+    u[0] = o[0] / n3; u[1] = o[1] / n3; u[2] = o[2] / n3;
     const double dx = (double)s[0] - (double)s[2], dy = (double)s[1] - (double)s[3];
     (side ? v.right_len : v.left_len)[i] = sqrt(dx * dx + dy * dy);
   }
@@ -186,6 +192,416 @@ __global__ void __launch_bounds__(32) k_line_greedy(LineMatchView v, int* taken_
   }
 }
 
+
+// ================================================================================================
+// Tensor-core path (sm_100a tcgen05): the left x right descriptor contraction of one 128-row block of a stereo pair
+// as 3xTF32 UMMAs (a = a_hi + a_lo, a.b ~ a_hi.b_hi + a_hi.b_lo + a_lo.b_hi, fp32 accumulation in TMEM), with the
+// candidate selection fused into the TMEM epilogue:
+//   k_line_tc    : CTA = (pair, 128 left lines); descriptors split into TF32 hi / lo parts while being staged into the
+//                  canonical K-major no-swizzle UMMA layout in shared memory; D[128 x 512] fp32 lives in TMEM (all 512
+//                  columns); epilogue thread = (row, column half): d^2 = |a|^2 + |b|^2 - 2 a.b, cheap gates of
+//                  CheckLinePair (octave, lengths, tau), 8 best candidates per half kept in registers -> 16 per row
+//   k_line_gate  : the geometric gates (FP64 triangulation, |X0|, endpoint depths) for the 16 candidates of every row
+//   k_line_greedy_tc : CTA per pair, candidate lists staged in shared memory, one warp replays the sequential greedy
+//                  (a list that runs dry while unseen candidates could still win falls back to an exact scan of the row);
+//                  the distance reported for a match is recomputed exactly in FP32 from the descriptors
+// The ranking uses the 3xTF32 distances (|error| ~ 1e-6 in d^2), the reported distances are exact: within the stated
+// tolerance 1e-5 * max(1, d), identical matches unless two candidates are closer than that.
+// ================================================================================================
+constexpr int TC_ROWS = 128, TC_HALF = 256, TC_COLS = 512, TC_K = 8, TC_NT = 256;
+constexpr int TC_HCAP = 128, TC_CAND = 2 * TC_HCAP;  // candidate slots per (row, column half) / per row
+constexpr int TC_AW = TC_CAND / 32;                  // admissibility mask words per row
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+// UMMA shared-memory descriptor, K-major, no swizzle: 8 x 16 B core matrices; LBO = byte distance between the two
+// 16 B K-chunks of one MMA, SBO = byte distance between 8-row groups (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+      : "memory");
+}
+// bounded wait: a tensor-core completion that never arrives is reported (err_flag) instead of hanging the device
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  for (int spin = 0; spin < (1 << 22); spin++) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+#define TMEM_LD32(r, taddr)                                                                                              \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, " \
+               "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"            \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),          \
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),    \
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),  \
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])   \
+               : "r"(taddr))
+
+struct LineTcView {
+  LineMatchView v;
+  const int* tile_pair;   // [n_tiles]
+  const int* tile_r;      // [n_tiles] 128-row block inside the pair
+  uint32_t* cand_d2;      // [n_left][TC_CAND] float bits of the 3xTF32 squared distance; slots [HCAP h, HCAP h + cnt[h]) of column half h
+  uint16_t* cand_col;     // [n_left][TC_CAND] pair-local right line
+  uint16_t* cand_cnt;     // [n_left][2] candidates per column half that pass the cheap gates and the parallax test (> HCAP: overflow)
+  uint32_t* cand_adm;     // [n_left][TC_AW] bit k: candidate slot k passes the remaining geometric gates
+  int* err_flag;          // [4] 0: a tensor-core completion barrier timed out; 1: rows that took the exact fallback scan;
+                          //     2: listed candidates; 3: listed candidates passing the geometric gates
+};
+
+// stage `rows` descriptors (global row-major fp32, D multiple of 8) as TF32 hi / lo parts into the UMMA K-major layout:
+// element (r, k) at (r/8) * sbo + (k/4) * 128 + (r%8) * 16 + (k%4) * 4 ; a warp writes 512 contiguous bytes per step
+__device__ __forceinline__ void stage_split(const float* __restrict__ g, int n_valid, int rows, int D, uint8_t* hi, uint8_t* lo) {
+  const int chunks = D >> 2, sbo = chunks * 128;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int r_in = lane & 7, c_in = lane >> 3;  // 8 rows x 4 chunks per warp step
+  const int n_groups = rows >> 3, quads = (chunks + 3) >> 2;
+  // warp w takes row groups w, w + nw, ...; inside a group it walks the quads of four 16 B chunks
+  for (int rg = wid; rg < n_groups; rg += nw) {
+    const int r = rg * 8 + r_in;
+    const float* grow = g + (size_t)r * D;
+    const bool rv = r < n_valid;
+    for (int cq = 0; cq < quads; cq += 2) {
+      const int kc0 = cq * 4 + c_in, kc1 = kc0 + 4;
+      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+      if (rv && kc0 < chunks) x0 = *reinterpret_cast<const float4*>(grow + 4 * kc0);
+      if (rv && kc1 < chunks && cq + 1 < quads) x1 = *reinterpret_cast<const float4*>(grow + 4 * kc1);
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int kc = u ? kc1 : kc0;
+        if (kc >= chunks || (u && cq + 1 >= quads)) continue;
+        const float4 x = u ? x1 : x0;
+        uint4 h, l;
+        h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
+        l.x = to_tf32(x.x - __uint_as_float(h.x)); l.y = to_tf32(x.y - __uint_as_float(h.y));
+        l.z = to_tf32(x.z - __uint_as_float(h.z)); l.w = to_tf32(x.w - __uint_as_float(h.w));
+        const int off = rg * sbo + kc * 128 + r_in * 16;
+        *reinterpret_cast<uint4*>(hi + off) = h;
+        *reinterpret_cast<uint4*>(lo + off) = l;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC_NT, 1) k_line_tc(LineTcView t) {
+  extern __shared__ __align__(1024) uint8_t tsm[];
+  const LineMatchView& v = t.v;
+  const int p = t.tile_pair[blockIdx.x];
+  const int a0 = v.left_off[p], na = v.left_off[p + 1] - a0;
+  const int b0 = v.right_off[p], nb = v.right_off[p + 1] - b0;
+  const int r0 = t.tile_r[blockIdx.x] * TC_ROWS;
+  const int D = v.D, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int a_bytes = TC_ROWS * D * 4, b_bytes = TC_HALF * D * 4;
+  uint8_t* A_hi = tsm;
+  uint8_t* A_lo = A_hi + a_bytes;
+  uint8_t* B_hi = A_lo + a_bytes;
+  uint8_t* B_lo = B_hi + b_bytes;
+  float4* colv = reinterpret_cast<float4*>(B_lo + b_bytes);   // [512] {|b|^2, unit plane normal of the right line (FP32)}
+  int8_t* colm = reinterpret_cast<int8_t*>(colv + TC_COLS);   // [512] octave of the right line, -1 = not a candidate
+  uint64_t* bar = reinterpret_cast<uint64_t*>(colm + TC_COLS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  if (wid == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::);
+  }
+  // per-column data of the cheap gates and |b|^2 (one thread per right line, two rounds)
+  for (int c = tid; c < TC_COLS; c += TC_NT) {
+    float s2 = 0.f;
+    int m = -1;
+    float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < nb) {
+      const float* g = v.right_desc + (size_t)(b0 + c) * D;
+      for (int k = 0; k < D; k += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(g + k);
+        s2 = fmaf(x.x, x.x, s2); s2 = fmaf(x.y, x.y, s2); s2 = fmaf(x.z, x.z, s2); s2 = fmaf(x.w, x.w, s2);
+      }
+      if (!(v.right_len[b0 + c] < (double)v.min_len)) m = (int8_t)min(v.right_oct[b0 + c], 127);
+      const double* un = v.right_un + 3 * (size_t)(b0 + c);
+      cv = make_float4(s2, (float)un[0], (float)un[1], (float)un[2]);
+    }
+    colv[c] = cv;
+    colm[c] = (int8_t)m;
+  }
+  stage_split(v.left_desc + (size_t)(a0 + r0) * D, na - r0, TC_ROWS, D, A_hi, A_lo);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::);
+  const uint32_t tmem = *tmem_slot;
+  // instruction descriptor: D fp32, A / B TF32, both K-major, N = 256, M = 128  (cute::UMMA::InstrDescriptor)
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_HALF >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+  const uint32_t sbo = (uint32_t)(D >> 2) * 128u;
+  for (int h = 0; h < 2; h++) {
+    if (h * TC_HALF < nb) {
+      stage_split(v.right_desc + (size_t)(b0 + h * TC_HALF) * D, nb - h * TC_HALF, TC_HALF, D, B_hi, B_lo);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::);
+        const uint32_t d_tmem = tmem + (uint32_t)(h * TC_HALF);
+        uint32_t acc = 0;
+        for (int ks = 0; ks < D / TC_K; ks++) {
+          const uint32_t koff = (uint32_t)ks * 256u;  // two 16 B chunks x 128 B per k-step
+          const uint64_t ah = umma_desc(smem_u32(A_hi) + koff, 128, sbo), al = umma_desc(smem_u32(A_lo) + koff, 128, sbo);
+          const uint64_t bh = umma_desc(smem_u32(B_hi) + koff, 128, sbo), bl = umma_desc(smem_u32(B_lo) + koff, 128, sbo);
+          umma_tf32(d_tmem, ah, bh, idesc, acc);
+          umma_tf32(d_tmem, ah, bl, idesc, 1);
+          umma_tf32(d_tmem, al, bh, idesc, 1);
+          acc = 1;
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+      }
+      // the MMAs have read B: the buffer may be refilled, D is complete
+      if (!mbar_wait(smem_u32(bar), (uint32_t)(h & 1)) && tid == 0) atomicExch(t.err_flag, 1);
+    }
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::);
+
+  // ---- epilogue: thread = (row = 32 * (warp % 4) + lane, column half = warp / 4)
+  const int q = wid & 3, ch = wid >> 2;
+  const int row = 32 * q + lane, gr = r0 + row;
+  const bool row_ok = gr < na;
+  float na2 = 0.f;
+  int octl = -2;
+  if (row_ok) {
+    const float* g = v.left_desc + (size_t)(a0 + gr) * D;
+    for (int k = 0; k < D; k += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(g + k);
+      na2 = fmaf(x.x, x.x, na2); na2 = fmaf(x.y, x.y, na2); na2 = fmaf(x.z, x.z, na2); na2 = fmaf(x.w, x.w, na2);
+    }
+    if (!(v.left_len[a0 + gr] < (double)v.min_len)) octl = min(v.left_oct[a0 + gr], 127);
+  }
+  const float tau2 = (float)(v.tau * v.tau);
+  double ul0 = 0, ul1 = 0, ul2 = 0;
+  if (row_ok) {
+    const double* u = v.left_un + 3 * (size_t)(a0 + gr);
+    ul0 = u[0]; ul1 = u[1]; ul2 = u[2];
+  }
+  const float fl0 = (float)ul0, fl1 = (float)ul1, fl2 = (float)ul2;
+  // candidates of this (row, column half): cheap gates of CheckLinePair + the parallax test of vgl::TriangulateLine
+  // (src/vgl.cc:84), appended in column order; the remaining FP64 geometry runs in k_line_gate over the lists.
+  // The parallax test is decided in FP32 from shared memory unless it is within 1e-5 of the threshold (then FP64, as the
+  // reference computes it); the per-column work is branch-free, only the append diverges.
+  int cnt = 0;
+  const size_t o = row_ok ? (size_t)(a0 + gr) * TC_CAND + (size_t)ch * TC_HCAP : 0;
+  if (ch * TC_HALF < nb) {
+    for (int cb = 0; cb < TC_HALF; cb += 32) {
+      const int c_base = ch * TC_HALF + cb;
+      if (c_base >= nb) break;  // warp-uniform
+      uint32_t r[32];
+      TMEM_LD32(r, tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c_base);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const int c = c_base + j;
+        const float4 cv = colv[c];
+        const float d2 = fmaxf(na2 + cv.x - 2.f * __uint_as_float(r[j]), 0.f);
+        const float cs = fabsf(fmaf(fl0, cv.y, fmaf(fl1, cv.z, fl2 * cv.w)));
+        bool pass = ((int)colm[c] == octl) & (d2 < tau2) & !(cs > 0.975f + 1e-5f);
+        if (pass && cs > 0.975f - 1e-5f) {  // borderline: decide in FP64
+          const double* un = v.right_un + 3 * (size_t)(b0 + c);
+          pass = !(fabs(ul0 * un[0] + ul1 * un[1] + ul2 * un[2]) > 0.975);
+        }
+        if (pass) {
+          if (cnt < TC_HCAP) {
+            t.cand_d2[o + cnt] = __float_as_uint(d2);
+            t.cand_col[o + cnt] = (uint16_t)c;
+          }
+          cnt++;
+        }
+      }
+    }
+  }
+  if (row_ok) t.cand_cnt[2 * (size_t)(a0 + gr) + ch] = (uint16_t)min(cnt, TC_HCAP + 1);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_COLS));
+}
+
+// remaining geometric gates of CheckLinePair (triangulation, |X0|, endpoint depths; FP64) over the candidate lists:
+// one warp per left line, lanes stride over the listed slots of each column half, one ballot = one word of the mask
+__global__ void __launch_bounds__(256) k_line_gate(LineTcView t, int n_left, int stats) {
+  const LineMatchView& v = t.v;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= n_left) return;
+  int lo = 0, hi = v.n_pairs;  // right lines are pair-local: the pair of left line i
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (v.left_off[mid] <= i) lo = mid;
+    else hi = mid;
+  }
+  const int b0 = v.right_off[lo];
+  int n_listed = 0, n_adm = 0;
+  // the listed slots of both column halves as one sequence (lane utilisation): entry e -> slot
+  const int cnt0 = min((int)t.cand_cnt[2 * (size_t)i], TC_HCAP), cnt1 = min((int)t.cand_cnt[2 * (size_t)i + 1], TC_HCAP);
+  const int tot = cnt0 + cnt1;
+  if (lane < TC_AW) t.cand_adm[(size_t)i * TC_AW + lane] = 0u;
+  __syncwarp();
+  for (int e0 = 0; e0 < tot; e0 += 32) {
+    const int e = e0 + lane;
+    bool adm = false;
+    int k = 0;
+    if (e < tot) {
+      k = e < cnt0 ? e : TC_HCAP + (e - cnt0);
+      const size_t slot = (size_t)i * TC_CAND + k;
+      const int c = b0 + t.cand_col[slot];
+      adm = line_pair_gate(v, v.left_seg + 4 * (size_t)i, v.left_leq + 3 * (size_t)i, v.right_leq + 3 * (size_t)c);
+      if (stats) {  // diagnostic: largest |3xTF32 - exact FP32| squared distance over the listed candidates
+        const float* da = v.left_desc + (size_t)i * v.D;
+        const float* db = v.right_desc + (size_t)c * v.D;
+        float s2 = 0.f;
+        for (int q = 0; q < v.D; q++) {
+          const float df = da[q] - db[q];
+          s2 = fmaf(df, df, s2);
+        }
+        atomicMax(reinterpret_cast<unsigned*>(t.err_flag) + 4, __float_as_uint(fabsf(s2 - __uint_as_float(t.cand_d2[slot]))));
+      }
+    }
+    if (adm) atomicOr(&t.cand_adm[(size_t)i * TC_AW + (k >> 5)], 1u << (k & 31));
+    n_adm += __popc(__ballot_sync(0xffffffffu, adm));
+  }
+  n_listed = tot;
+  if (stats && lane == 0) {
+    atomicAdd(t.err_flag + 2, n_listed);
+    atomicAdd(t.err_flag + 3, n_adm);
+  }
+}
+
+// exact squared distance of one (left, right) pair by a warp (FP32, difference form)
+__device__ __forceinline__ float warp_exact_d2(const float* a, const float* b, int D, int lane) {
+  float s2 = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float d = a[k] - b[k];
+    s2 = fmaf(d, d, s2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  return s2;
+}
+
+// One warp per pair replays the sequential greedy of MatchLines over the per-row candidate lists (admissible candidates
+// of a row = its listed slots with the gate bit set; a row whose list overflowed takes an exact scan instead).
+// The next row's list is prefetched into registers while the current row is resolved.
+__global__ void __launch_bounds__(128) k_line_greedy_tc(LineTcView t) {
+  __shared__ uint32_t s_taken[4][TC_COLS / 32];
+  const LineMatchView& v = t.v;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * 4 + wid;
+  if (p >= v.n_pairs) return;
+  const int a0 = v.left_off[p], na = v.left_off[p + 1] - a0;
+  const int b0 = v.right_off[p], nb = v.right_off[p + 1] - b0;
+  uint32_t* taken = s_taken[wid];
+  if (lane < TC_COLS / 32) taken[lane] = 0;
+  __syncwarp();
+  // lane l prefetches slot l of both column halves of the next row (most rows list < 32 candidates per half); the
+  // remaining 32-slot groups of a longer list are read on demand
+  uint32_t nd2[2] = {0, 0};
+  uint16_t ncol[2] = {0, 0};
+  uint32_t nadm = 0;
+  int ncnt0 = 0, ncnt1 = 0;
+  auto fetch = [&](int j) {
+    const size_t o = (size_t)(a0 + j) * TC_CAND;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      nd2[h] = t.cand_d2[o + (size_t)h * TC_HCAP + lane];
+      ncol[h] = t.cand_col[o + (size_t)h * TC_HCAP + lane];
+    }
+    nadm = lane < TC_AW ? t.cand_adm[(size_t)(a0 + j) * TC_AW + lane] : 0u;
+    ncnt0 = t.cand_cnt[2 * (size_t)(a0 + j)];
+    ncnt1 = t.cand_cnt[2 * (size_t)(a0 + j) + 1];
+  };
+  if (na > 0) fetch(0);
+  for (int j = 0; j < na; j++) {
+    uint32_t d2[2] = {nd2[0], nd2[1]};
+    uint16_t col[2] = {ncol[0], ncol[1]};
+    const uint32_t adm_mine = nadm;
+    const int cnt0 = ncnt0, cnt1 = ncnt1;
+    if (j + 1 < na) fetch(j + 1);
+    int bi = -1;
+    if (cnt0 <= TC_HCAP && cnt1 <= TC_HCAP) {
+      unsigned long long w = ~0ull;
+      const size_t o = (size_t)(a0 + j) * TC_CAND;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int cnt = h == 0 ? cnt0 : cnt1;
+        for (int g = 0; 32 * g < cnt; g++) {  // warp-uniform trip count
+          const uint32_t word = __shfl_sync(0xffffffffu, adm_mine, h * (TC_HCAP / 32) + g);
+          uint32_t dd = d2[h];
+          uint32_t cc = col[h];
+          if (g > 0) {
+            dd = t.cand_d2[o + (size_t)h * TC_HCAP + 32 * g + lane];
+            cc = t.cand_col[o + (size_t)h * TC_HCAP + 32 * g + lane];
+          }
+          if (32 * g + lane < cnt && ((word >> lane) & 1u) && !((taken[cc >> 5] >> (cc & 31)) & 1u)) {
+            const unsigned long long key = ((unsigned long long)dd << 16) | (unsigned long long)cc;
+            w = key < w ? key : w;
+          }
+        }
+      }
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) {
+        const unsigned long long u = __shfl_xor_sync(0xffffffffu, w, o2);
+        w = u < w ? u : w;
+      }
+      if (w != ~0ull) bi = (int)(w & 0xFFFFull);
+    } else {
+      if (lane == 0) atomicAdd(t.err_flag + 1, 1);
+      // overflowed list: exact scan of the row.  Pass A: lanes stride over the right lines and apply every gate of
+      // CheckLinePair; pass B: exact FP32 distances of the few admissible ones, computed by the whole warp per line.
+      const int gl = a0 + j;
+      const bool l_ok = !(v.left_len[gl] < (double)v.min_len);
+      const double* ul = v.left_un + 3 * (size_t)gl;
+      float best = INFINITY;
+      for (int cb = 0; cb < nb && l_ok; cb += 32) {
+        const int c = cb + lane;
+        bool ok = false;
+        if (c < nb && !((taken[c >> 5] >> (c & 31)) & 1u)) {
+          const int gc = b0 + c;
+          if (v.left_oct[gl] == v.right_oct[gc] && !(v.right_len[gc] < (double)v.min_len)) {
+            const double* un = v.right_un + 3 * (size_t)gc;
+            if (!(fabs(ul[0] * un[0] + ul[1] * un[1] + ul[2] * un[2]) > 0.975))
+              ok = line_pair_gate(v, v.left_seg + 4 * (size_t)gl, v.left_leq + 3 * (size_t)gl, v.right_leq + 3 * (size_t)gc);
+          }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        while (m) {  // ascending column order, strict <: the first minimum wins as in the reference
+          const int c2 = cb + __ffs(m) - 1;
+          m &= m - 1;
+          const float d = sqrtf(warp_exact_d2(v.left_desc + (size_t)gl * v.D, v.right_desc + (size_t)(b0 + c2) * v.D, v.D, lane));
+          if ((double)d < v.tau && d < best) { best = d; bi = c2; }
+        }
+      }
+    }
+    // exact distance of the match (FP32, difference form), as the tile path reports it
+    float d = INFINITY;
+    if (bi >= 0) d = sqrtf(warp_exact_d2(v.left_desc + (size_t)(a0 + j) * v.D, v.right_desc + (size_t)(b0 + bi) * v.D, v.D, lane));
+    if (lane == 0) {
+      v.match[a0 + j] = bi;
+      v.mdist[a0 + j] = d;
+      if (bi >= 0) taken[bi >> 5] |= 1u << (bi & 31);
+    }
+    __syncwarp();
+  }
+}
+
 template <typename T>
 int upm(LldCtx* c, T** dst, const T* src, size_t n) {
   cudaError_t e = cudaSuccess;
@@ -229,12 +645,21 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
   v.n_pairs = P; v.D = p->desc_dim;
   for (int i = 0; i < 9; i++) v.K[i] = p->K[i];
   v.baseline = p->baseline; v.tau = p->tau; v.min_len = p->min_line_length;
+  // tensor-core path: D multiple of 8 up to 72 floats, at most 512 right lines per pair (LLD_LINE_TC=0 forces the FP32 tile path)
+  int max_na = 0, max_nb = 0;
+  for (int i = 0; i < P; i++) {
+    max_na = std::max(max_na, p->left_off[i + 1] - p->left_off[i]);
+    max_nb = std::max(max_nb, p->right_off[i + 1] - p->right_off[i]);
+  }
+  const char* e_tc = getenv("LLD_LINE_TC");
+  const bool use_tc = !(e_tc && e_tc[0] == '0') && v.D % 8 == 0 && v.D >= 8 && v.D <= 72 && max_nb <= TC_COLS && max_nb >= 1 && max_na >= 1;
   // tiles + matrix offsets
   std::vector<long long> mat_off(P), taken_off(P);
   std::vector<int> tp, tr, tc;
   long long tot = 0, ttot = 0;
   for (int i = 0; i < P; i++) {
     const int na = p->left_off[i + 1] - p->left_off[i], nb = p->right_off[i + 1] - p->right_off[i];
+    if (use_tc) continue;
     mat_off[i] = tot; tot += (long long)na * nb;
     taken_off[i] = ttot; ttot += nb;
     for (int r = 0; r < cdiv(na, LT); r++)
@@ -260,6 +685,8 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
   UPM(v.right_leq, double, nullptr, 3 * (size_t)n_right);
   UPM(v.left_len, double, nullptr, n_left);
   UPM(v.right_len, double, nullptr, n_right);
+  UPM(v.left_un, double, nullptr, 3 * (size_t)n_left);
+  UPM(v.right_un, double, nullptr, 3 * (size_t)n_right);
   UPM(v.dist, float, nullptr, (size_t)tot);
   UPM(v.match, int, nullptr, n_left);
   UPM(v.mdist, float, nullptr, n_left);
@@ -267,15 +694,47 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
   UPM(d_taken, int, nullptr, (size_t)ttot);
   LLD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   const int nmax = std::max(std::max(n_left, n_right), 1);
+  int* d_tc_err = nullptr;
   LLD_LAUNCH(c, k_line_prep, cdiv(nmax, 128), 128, 0, v, n_left, n_right);
-  if (!tp.empty()) {
+  if (use_tc) {
+    std::vector<int> ttp, ttr;
+    for (int i = 0; i < P; i++) {
+      const int na = p->left_off[i + 1] - p->left_off[i];
+      if (p->right_off[i + 1] - p->right_off[i] == 0) continue;   // no right lines: every left line stays unmatched
+      for (int r = 0; r < cdiv(na, TC_ROWS); r++) { ttp.push_back(i); ttr.push_back(r); }
+    }
+    LineTcView t;
+    t.v = v;
+    int *d_ttp, *d_ttr;
+    UPM(d_ttp, int, ttp.data(), ttp.size());
+    UPM(d_ttr, int, ttr.data(), ttr.size());
+    t.tile_pair = d_ttp; t.tile_r = d_ttr;
+    UPM(t.cand_d2, uint32_t, nullptr, (size_t)n_left * TC_CAND);
+    UPM(t.cand_col, uint16_t, nullptr, (size_t)n_left * TC_CAND);
+    UPM(t.cand_cnt, uint16_t, nullptr, 2 * (size_t)n_left);
+    UPM(t.cand_adm, uint32_t, nullptr, (size_t)TC_AW * n_left);
+    UPM(t.err_flag, int, nullptr, 8);
+    LLD_CUDA(c, cudaMemsetAsync(t.err_flag, 0, 8 * sizeof(int), c->stream));
+    d_tc_err = t.err_flag;
+    LLD_CUDA(c, cudaMemsetAsync(t.cand_cnt, 0, sizeof(uint16_t) * 2 * (size_t)n_left, c->stream));
+    if (!ttp.empty()) {
+      const size_t smem = (size_t)(TC_ROWS + TC_HALF) * v.D * 8 + TC_COLS * 16 + TC_COLS + 16 + 64;
+      LLD_CUDA(c, lld_raise_dyn_smem(k_line_tc, (size_t)(int)smem));
+      LLD_LAUNCH(c, k_line_tc, (int)ttp.size(), TC_NT, smem, t);
+    }
+    LLD_LAUNCH(c, k_line_gate, cdiv(n_left, 8), 256, 0, t, n_left, getenv("LLD_LINE_STATS") ? 1 : 0);
+    LLD_LAUNCH(c, k_line_greedy_tc, cdiv(P, 4), 128, 0, t);
+  } else if (!tp.empty()) {
     const size_t smem = sizeof(float) * 2 * LT * (v.D + 1);
-    LLD_CUDA(c, cudaFuncSetAttribute(k_line_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LLD_CUDA(c, lld_raise_dyn_smem(k_line_dist, (size_t)(int)smem));
     LLD_LAUNCH(c, k_line_dist, (int)tp.size(), 256, smem, v, d_tp, d_tr, d_tc);
   }
-  LLD_LAUNCH(c, k_line_greedy, P, 32, 0, v, d_taken, d_taken_off);
+  if (!use_tc) LLD_LAUNCH(c, k_line_greedy, P, 32, 0, v, d_taken, d_taken_off);
   LLD_CUDA(c, cudaGetLastError());
   LLD_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  int* h_err = reinterpret_cast<int*>(c->pinned);
+  *h_err = 0;
+  if (d_tc_err) LLD_CUDA(c, cudaMemcpyAsync(h_err, d_tc_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   if (n_left) {
     LLD_CUDA(c, cudaMemcpyAsync(out->match, v.match, sizeof(int) * (size_t)n_left, cudaMemcpyDeviceToHost, c->stream));
     if (out->dist) LLD_CUDA(c, cudaMemcpyAsync(out->dist, v.mdist, sizeof(float) * (size_t)n_left, cudaMemcpyDeviceToHost, c->stream));
@@ -285,5 +744,12 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
   cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->ms_compute, c->ev[1], c->ev[2]);
   cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]);
+  if (getenv("LLD_LINE_STATS") && d_tc_err)
+    fprintf(stderr, "[lld_line_match] fallback rows %d, listed candidates %d, geometrically admissible %d, max |d2_tc - d2_exact| %.3e\n",
+            h_err[1], h_err[2], h_err[3], (double)*reinterpret_cast<float*>(h_err + 4));
+  if (*h_err) {
+    snprintf(c->err, sizeof(c->err), "line matcher: tensor-core completion barrier timed out");
+    return LLD_ERR_CUDA;
+  }
   return LLD_OK;
 }

@@ -5,9 +5,19 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/lldba.h"
+
+// Device / pinned allocations (implicit device-wide synchronisation) must not run while another host thread of this
+// library captures a CUDA graph: both sides take this mutex (ctx.cu).
+std::mutex& lld_capture_mutex();
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function and process-wide, while contexts of several host threads
+// launch the same kernels with different sizes: keep it monotone (never lower it under another thread's launch).
+cudaError_t lld_raise_dyn_smem(const void* func, int bytes);
+template <typename F>
+inline cudaError_t lld_raise_dyn_smem(F* func, size_t bytes) { return lld_raise_dyn_smem(reinterpret_cast<const void*>(func), (int)bytes); }
 
 struct BaState;      // ba.cu
 struct ncclComm;
@@ -18,6 +28,7 @@ struct DevBuf {
   // grow-only device allocation; contents are NOT preserved on growth
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    std::lock_guard<std::mutex> lk(lld_capture_mutex());
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;

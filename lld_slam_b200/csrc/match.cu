@@ -932,10 +932,10 @@ static int match_run(LldCtx* c, MatchView& v, int* passes_out) {
   if (v.fused_ok) {  // every pair fits one CTA's shared memory: single launch, no host round trips
     const FusedLayout L = fused_layout(v.max_cur);
     if (v.variant == 0) {
-      LLD_CUDA(c, cudaFuncSetAttribute(k_match_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+      LLD_CUDA(c, lld_raise_dyn_smem(k_match_fused<0>, (size_t)L.total));
       LLD_LAUNCH(c, k_match_fused<0>, v.n_pairs, FUSED_NT, L.total, v, L);
     } else {
-      LLD_CUDA(c, cudaFuncSetAttribute(k_match_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+      LLD_CUDA(c, lld_raise_dyn_smem(k_match_fused<1>, (size_t)L.total));
       LLD_LAUNCH(c, k_match_fused<1>, v.n_pairs, FUSED_NT, L.total, v, L);
     }
     LLD_CUDA(c, cudaGetLastError());

@@ -507,7 +507,7 @@ int pose_run(LldCtx* c, PoseView& v, size_t smem_need) {
   const size_t limit = 200 * 1024;
   const int stage = smem_need <= limit ? 1 : 0;
   const size_t smem = stage ? smem_need : 0;
-  if (stage) LLD_CUDA(c, cudaFuncSetAttribute(k_pose_opt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (stage) LLD_CUDA(c, lld_raise_dyn_smem(k_pose_opt, (size_t)(int)smem));
   LLD_LAUNCH(c, k_pose_opt, v.n_frames, PTPB, smem, v, stage);
   LLD_CUDA(c, cudaGetLastError());
   return LLD_OK;

@@ -219,6 +219,12 @@ def test_sbp_frame_ragged_pairs(gpu_ctx, match_path):
         assert np.array_equal(g[k], o[k]), k
 
 
+def test_line_match_wide_descriptor_takes_tile_path(gpu_ctx):
+    """D = 100 is not a multiple of 8: FP32 tile kernel"""
+    p = synth.make_line_match_batch(3, 200, 100, 5)
+    check_line_match(api.line_match(p, impl="gpu", ctx=gpu_ctx), api.line_match(p, impl="oracle"))
+
+
 def check_line_match(g, o):
     same = g["match"] == o["match"]
     fin = np.isfinite(o["dist"]) & same
@@ -230,8 +236,16 @@ def check_line_match(g, o):
     assert len(bad) <= max(1, len(same) // 1000)
 
 
+@pytest.fixture(params=["tcgen05", "fp32tiles"])
+def line_path(request, monkeypatch):
+    """both device paths of the line matcher: 3xTF32 tcgen05 contraction with the selection fused into the TMEM epilogue,
+    and the FP32 tile kernel (descriptor widths / pair sizes the tensor-core path does not take)"""
+    monkeypatch.setenv("LLD_LINE_TC", "1" if request.param == "tcgen05" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("D", [64, 72])
-def test_line_match(gpu_ctx, D):
+def test_line_match(gpu_ctx, D, line_path):
     p = synth.make_line_match_batch(6, 500, D, 9 + D)
     g = api.line_match(p, impl="gpu", ctx=gpu_ctx)
     o = api.line_match(p, impl="oracle")
@@ -239,7 +253,7 @@ def test_line_match(gpu_ctx, D):
     check_line_match(g, o)
 
 
-def test_line_match_ragged(gpu_ctx):
+def test_line_match_ragged(gpu_ctx, line_path):
     p = synth.make_line_match_batch(5, 60, 64, 2, ragged=True)
     check_line_match(api.line_match(p, impl="gpu", ctx=gpu_ctx), api.line_match(p, impl="oracle"))
 
