@@ -317,9 +317,13 @@ def main():
     top_name, top_ms, top_n = top[0], top[1]["ms"], top[1]["n"]
     key = top_name.strip("()")
     kb = kernel_bytes(key, p) or kernel_bytes(key.split("<")[0], p)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if args.windows == 64 and os.path.exists(tpath):  # ncu dram bytes per launch of this exact workload (committed capture)
+        traffic = json.load(open(tpath)).get("batched_local_ba_64", {}).get(top_name.strip("()"))
     roofline = {"bound": "hbm", "kernel": top_name, "share_of_step": top_ms / tot_ms if tot_ms else None,
                 "avg_launch_us": 1e3 * top_ms / max(top_n, 1), "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
-                "traffic": None}
+                "traffic": traffic, "traffic_source": "ncu --set full capture, profiles/r1j_ba_kernels_full.txt" if traffic else None}
     if kb:
         ach = kb / (1e-3 * top_ms / max(top_n, 1)) / 1e9
         roofline.update({"achieved": ach, "frac": ach / hbm_peak, "algorithmic_bytes_per_launch": kb})

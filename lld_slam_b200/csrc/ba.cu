@@ -55,6 +55,8 @@ struct BaState {
   cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
   int step_kernels[2] = {0, 0};
   void drop_graphs() {
+    if (!step_graph[0] && !step_graph[1]) return;
+    std::lock_guard<std::mutex> lk(lld_capture_mutex());
     for (int r = 0; r < 2; r++) {
       if (step_graph[r]) cudaGraphExecDestroy(step_graph[r]);
       step_graph[r] = nullptr;
@@ -1068,7 +1070,10 @@ static int ba_run_round(LldCtx* c, int maxit, int round, const volatile uint8_t*
           S->step_kernels[round] = (int)(c->launches - l0);
           c->launches = l0;
         }
-        LLD_CUDA(c, cudaGraphLaunch(S->step_graph[round], c->stream));
+        {
+          std::lock_guard<std::mutex> lk(lld_capture_mutex());  // graph launches and captures of other threads do not interleave
+          LLD_CUDA(c, cudaGraphLaunch(S->step_graph[round], c->stream));
+        }
         c->launches += S->step_kernels[round];
       } else {
         int r = ba_step(c, round, stop_now);
