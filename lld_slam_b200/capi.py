@@ -15,7 +15,7 @@ from typing import Any, Dict
 import numpy as np
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_ROOT, "lld_slam_b200", "csrc", "liblldba.so")
+LIB_PATH = os.environ.get("LLD_LIB_PATH") or os.path.join(_ROOT, "lld_slam_b200", "csrc", "liblldba.so")  # override: kernel A/B experiments
 ORACLE_PATH = os.path.join(_ROOT, "oracle", "liblld_oracle.so")
 
 c_i32p = C.POINTER(C.c_int32)

@@ -788,6 +788,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   UP(tmp_i, lo_src.data(), lo_src.size()); v.lo_src = tmp_i;
 
   stage("H2D enqueue");
+  if (c->host_only) return LLD_OK;  // lld_ba_index_only: the host stage is complete
   // ---- device-only buffers ----
   for (int b = 0; b < 2; b++) {
     DEV(v.pose_qt[b], double, 7 * (size_t)n_kf);

@@ -272,3 +272,27 @@ def test_cpp_shim_compiles_and_links(built, tmp_path):
                         "-L" + csrc, "-llldba", "-Wl,-rpath," + csrc], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     assert subprocess.run([exe]).returncode == 0
+
+
+def test_host_indexing_stage_runs_without_a_device(built):
+    """lld_ba_index_only drives the whole host stage of lld_ba_local / lld_ba_global (flattening, signature sort, keyframe lists,
+    dense pieces, gather lists, worker pool, persistent scratch) with the device calls stubbed out: it must accept
+    well-formed problems, repeatedly, and reject malformed ones — no GPU needed."""
+    import ctypes as C
+    from lld_slam_b200 import capi, synth
+    lib = capi.load_library()
+    f = lib.dll.lld_ba_index_only
+    f.argtypes = [C.POINTER(capi.BaProblem), C.c_int]
+    f.restype = C.c_int
+    p = synth.make_local_ba_batch(6, 8, 300, 60, 17)
+    prob, keep = capi.fill_struct(capi.BaProblem, p)
+    for _ in range(3):   # persistent scratch: repeated calls reuse it
+        assert f(C.byref(prob), 0) == 0
+    g = synth.make_global_ba(30, 800, 150, 5)
+    gprob, keep2 = capi.fill_struct(capi.BaProblem, g)
+    assert f(C.byref(gprob), 1) == 0
+    bad = dict(p)
+    bad["pt_obs_kf"] = p["pt_obs_kf"].copy()
+    bad["pt_obs_kf"][5] = 10 ** 6           # keyframe index outside its window
+    bprob, keep3 = capi.fill_struct(capi.BaProblem, bad)
+    assert f(C.byref(bprob), 0) == -2       # LLD_ERR_ARG
