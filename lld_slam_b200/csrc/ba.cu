@@ -695,7 +695,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     int B = 1;
     for (int g = 0; g < nG; g++) B = std::max(B, g - fb[g]);
     v.band_B = B;
-    S->band_smem = sizeof(double) * ((size_t)(6 * (B + 2)) * (6 * (B + 2)) + 36 * (size_t)B + 8 + 6 * (B + 2) + 36 * (size_t)(B + 1) + 6) + 64;
+    S->band_smem = sizeof(double) * ((size_t)(6 * (B + 2)) * (6 * (B + 2)) + 36 * (size_t)B + 32 + 6 * (B + 2) + 36 * (size_t)(B + 1) + 6) + 64;
     S->use_band = S->band_smem <= 220 * 1024 && (B + 1) * 36 + 6 <= 2048;
     lo_off.assign(nG + 1, 0);
     for (int a = 0; a < nG; a++)
@@ -827,6 +827,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   DEV(v.trials_log, int, (size_t)nw * log_stride); DEV(v.iter_done, int, 2 * (size_t)nw);
   DEV(v.solve_scratch, double, (size_t)scr_total);
   DEV(v.env_A, double, S->use_band ? 1 : (size_t)env_rowptr.back());
+  DEV(v.band_A, double, S->use_band ? (size_t)nG * ((v.band_B + 1) * 36 + 8) : 1);
   DEV(v.band_L, double, S->use_band ? (size_t)nG * (v.band_B + 1) * 36 : 1);
   DEV(v.band_z, double, S->use_band ? 6 * (size_t)nG : 1);
   DEV(S->d_out_kf, double, 12 * (size_t)n_kf); DEV(S->d_out_pt, double, 3 * (size_t)n_pt);
@@ -838,6 +839,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   LLD_CUDA(c, cudaMemsetAsync(S->d_pt_bad, 0, n_pe ? n_pe : 1, c->stream));
   LLD_CUDA(c, cudaMemsetAsync(S->d_ln_bad, 0, n_lc ? 2 * (size_t)n_lc : 1, c->stream));
 
+  v.debug = getenv("LLD_BAND_DEBUG") ? 1 : 0;
   v.prm.robust_pt = p->robust_points;
   v.prm.robust_ln = 1;
   v.prm.delta_pt_mono = p->delta_pt_mono; v.prm.delta_pt_stereo = p->delta_pt_stereo;
@@ -855,7 +857,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     S->use_graph = allow && dense_single;
   }
   // dynamic shared memory opt-in of the solvers (once per upload, outside any stream capture)
-  if (v.env_mode && S->use_band) LLD_CUDA(c, lld_raise_dyn_smem(k_solve_band, (size_t)(int)S->band_smem));
+  if (v.env_mode && S->use_band) LLD_CUDA(c, lld_raise_dyn_smem(k_solve_band<512>, (size_t)(int)S->band_smem) != cudaSuccess ? cudaErrorInvalidValue : lld_raise_dyn_smem(k_solve_band<1024>, (size_t)(int)S->band_smem));
   else if (v.env_mode) LLD_CUDA(c, lld_raise_dyn_smem(k_solve_env, (size_t)(int)S->env_smem));
   else if (S->max_n <= SMEM_SOLVE_MAX_N)
     LLD_CUDA(c, lld_raise_dyn_smem(k_solve<true>, (size_t)(int)(sizeof(double) * ((size_t)S->max_n * S->max_n + 8 * (size_t)S->max_n + 8))));
@@ -1021,7 +1023,9 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   }
   if (S->global_mode) { int r = ba_allreduce_rows(c); if (r) return r; }
   if (v.env_mode && S->use_band) {
-    LLD_LAUNCH(c, k_solve_band, 1, 1024, S->band_smem, v);
+    LLD_LAUNCH(c, k_band_assemble, v.n_free_total, 256, 0, v);
+    if ((v.band_B + 1) * 36 + 6 <= 1024) LLD_LAUNCH(c, k_solve_band<512>, 1, 512, S->band_smem, v);   // 128 registers per thread
+    else LLD_LAUNCH(c, k_solve_band<1024>, 1, 1024, S->band_smem, v);
   } else if (v.env_mode) {
     LLD_LAUNCH(c, k_solve_env, 1, 1024, S->env_smem, v);
   } else if (S->max_n <= SMEM_SOLVE_MAX_N) { int r = launch_solve<true>(c, v, S->max_n); if (r) return r; }

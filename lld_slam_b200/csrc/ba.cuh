@@ -178,8 +178,10 @@ struct BaView {
   const int* lo_off;          // [n_free_total+1] lower blocks (row r, col c <= r) of the reduced system
   const int* lo_col;          // column block c
   const int* lo_src;          // index of block (c, r) in S_blk (to be read transposed)
+  double* band_A;             // [n_free_total][(band_B+1)*36 + 8] band rows in the solver's order (k_band_assemble)
   double* band_L;             // [n_free_total][(band_B+1)][36] column panels: block 0 = L_kk (strict lower) + D (diagonal)
   double* band_z;             // [6 * n_free_total] forward-substituted rhs
+  int debug;                  // LLD_BAND_DEBUG: the band solver prints its phase cycle counts
   BaParams prm;
 };
 

@@ -10,6 +10,7 @@
 // Reductions are fixed-order (no floating-point atomics): results are run-to-run reproducible.
 #pragma once
 #include <cfloat>
+#include <cstdio>
 
 #include "ba.cuh"
 #include "lld_math.cuh"
@@ -1242,97 +1243,145 @@ __global__ void __launch_bounds__(1024) k_solve_env(BaView v) {
 // Three barriers per pivot, no global-memory latency on the critical path.  The backward substitution walks the stored
 // column panels with register prefetch of the next panel.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_solve_band(BaView v) {
+// band row r in the solver's native order: (B+1) lower blocks (column blocks r-B .. r, each [row in block][col in
+// block]) followed by the 6 rhs values; assembled in parallel from the block rows of S (stored as upper blocks)
+__global__ void __launch_bounds__(256) k_band_assemble(BaView v) {
+  const int w = 0;
+  if (v.w_phase[w] == PH_DONE) return;
+  const int g0 = v.w_g0[w];
+  const int r = blockIdx.x, B = v.band_B, RS = (B + 1) * 36 + 8;
+  double* row = v.band_A + (size_t)r * RS;
+  for (int i = threadIdx.x; i < RS; i += blockDim.x) row[i] = 0.0;
+  __syncthreads();
+  const int q0 = v.lo_off[g0 + r], q1 = v.lo_off[g0 + r + 1];
+  for (int i = threadIdx.x; i < (q1 - q0) * 36; i += blockDim.x) {
+    const int q = q0 + i / 36, e = i % 36, rr = e / 6, cc = e - 6 * rr;
+    const int c = v.lo_col[q];
+    if (c == r && cc < rr) continue;  // diagonal block: lower triangle only
+    row[(c - (r - B)) * 36 + cc * 6 + rr] = v.S_blk[36 * (size_t)v.lo_src[q] + e];
+  }
+  if (threadIdx.x < 6) row[(B + 1) * 36 + threadIdx.x] = v.g_bs[6 * (size_t)(g0 + r) + threadIdx.x];
+}
+
+// 6x6 LDL^T of the diagonal block in window slot s by one warp (right-looking over shuffles), forward solve of its rhs;
+// writes L (strict lower) and D back, z and 1/D into zq[0..5] / zq[8..13]; returns false on a zero / non-finite pivot
+__device__ __forceinline__ bool band_factor_diag(double* Wm, int LDW, int s, const double* rw, double* zq, double* band_z_k, int lane, int li, int lj) {
+  double m = lane < 21 ? Wm[(size_t)(6 * s + li) * LDW + 6 * s + lj] : 0.0;
+  double zz = lane < 6 ? rw[6 * s + lane] : 0.0;
+  bool okk = true;
+#pragma unroll
+  for (int pv = 0; pv < 6; pv++) {
+    const double d = __shfl_sync(0xffffffffu, m, pv * (pv + 1) / 2 + pv);
+    if (!(d != 0.0) || !isfinite(d)) okk = false;
+    const double id = 1.0 / d;
+    const double tip = __shfl_sync(0xffffffffu, m, li * (li + 1) / 2 + pv);   // T(i, pv), used when li > pv
+    const double tjp = __shfl_sync(0xffffffffu, m, lj * (lj + 1) / 2 + pv);   // T(j, pv), used when lj > pv
+    if (lane < 21 && lj > pv) m -= (tip * id) * tjp;
+    if (lane < 21 && lj == pv && li > pv) m *= id;
+  }
+#pragma unroll
+  for (int pv = 0; pv < 5; pv++) {   // L z = b
+    const double zp = __shfl_sync(0xffffffffu, zz, pv);
+    const double lip = __shfl_sync(0xffffffffu, m, (lane < 6 ? lane * (lane + 1) / 2 : 0) + pv);
+    if (lane < 6 && lane > pv) zz -= lip * zp;
+  }
+  if (lane < 21) Wm[(size_t)(6 * s + li) * LDW + 6 * s + lj] = m;
+  if (lane < 21 && li == lj) zq[8 + li] = 1.0 / m;
+  if (lane < 6) {
+    zq[lane] = zz;
+    band_z_k[lane] = zz;
+  }
+  return okk;
+}
+
+// Banded LDL^T, forward elimination per pivot block k in two barrier-separated phases:
+//   B: one thread per scalar row of the panel: T = A_ik L_kk^-T (kept for the update), L = T D^-1 written back
+//   C: trailing update by 3x6 half-block items (thread = one item: 18 + 36 + 18 shared-memory loads for 108 FMAs; the
+//      item -> (row block, column block) map lives in "distance from the pivot" space and is computed once), rhs update,
+//      column panel to HBM, the prefetched block row k+B+1 enters the window — and, as soon as warp 0 has updated block
+//      (k+1, k+1), it factors it (look-ahead), so the diagonal factorisation is off the critical path.
+template <int NT>
+__global__ void __launch_bounds__(NT) k_solve_band(BaView v) {
   extern __shared__ double bsm[];
   const int w = 0;
   if (v.w_phase[w] == PH_DONE) return;
   const int g0 = v.w_g0[w], nf = v.w_g0[w + 1] - g0;
-  const int B = v.band_B, WB = B + 2, LDW = 6 * WB, PB = B + 1;
+  const int B = v.band_B, WB = B + 2, LDW = 6 * WB, PB = B + 1, RS = PB * 36 + 8;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
   double* Wm = bsm;                          // [LDW][LDW]
-  double* Tt = Wm + (size_t)LDW * LDW;       // [6][6B]
-  double* zb = Tt + 36 * (size_t)B;          // [8]
-  double* rw = zb + 8;                       // [LDW] rhs window
+  double* Tt = Wm + (size_t)LDW * LDW;       // [6][6B]: T(c, x), x = panel row (consecutive lanes -> consecutive banks)
+  double* zb = Tt + 36 * (size_t)B;          // [2][16]: z block [0,6) and 1/D [8,14) of the pivot, double-buffered
+  double* rw = zb + 32;                      // [LDW] rhs window
   double* pan = rw + LDW;                    // [PB*36 + 6] panel buffer for the backward pass
   __shared__ int flag;
   __shared__ double red[32];
   const int sel = v.w_sel[w];
-  auto zero_row = [&](int r) {
-    const int s = r % WB;
-    for (int i = tid; i < 6 * LDW; i += nt) Wm[(size_t)(6 * s) * LDW + i] = 0.0;
-  };
-  auto scatter_row = [&](int r) {
-    const int s = r % WB;
-    const int q0 = v.lo_off[g0 + r], q1 = v.lo_off[g0 + r + 1];
-    for (int i = tid; i < (q1 - q0) * 36; i += nt) {
-      const int q = q0 + i / 36, e = i % 36, rr = e / 6, cc = e - 6 * rr;
-      const int c = v.lo_col[q];
-      if (c == r && cc < rr) continue;
-      Wm[(size_t)(6 * s + cc) * LDW + 6 * (c % WB) + rr] = v.S_blk[36 * (size_t)v.lo_src[q] + e];
+  auto fetch_row = [&](int r, double* r2) {
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int i = tid + u * nt;
+      r2[u] = (r < nf && i < PB * 36 + 6) ? v.band_A[(size_t)r * RS + i] : 0.0;
     }
-    if (tid < 6) rw[6 * s + tid] = v.g_bs[6 * (size_t)(g0 + r) + tid];
+  };
+  auto commit_row = [&](int r, const double* r2) {
+    if (r >= nf) return;
+    const int s = r % WB;
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int i = tid + u * nt;
+      if (i < PB * 36) {
+        const int j = i / 36, e = i - 36 * j, ri = e / 6, ci = e - 6 * ri;
+        const int c = r - B + j;
+        int sc = s + 2 + j;   // (r - B + j) mod WB with WB = B + 2
+        if (sc >= WB) sc -= WB;
+        if (c >= 0) Wm[(size_t)(6 * s + ri) * LDW + 6 * sc + ci] = r2[u];
+      } else if (i < PB * 36 + 6) {
+        rw[6 * s + (i - PB * 36)] = r2[u];
+      }
+    }
   };
   if (tid == 0) flag = 1;
   for (int i = tid; i < LDW * LDW; i += nt) Wm[i] = 0.0;
   __syncthreads();
-  for (int r = 0; r < nf && r <= B; r++) scatter_row(r);
+  for (int r = 0; r < nf && r <= B; r++) {
+    double t2[2];
+    fetch_row(r, t2);
+    commit_row(r, t2);
+  }
+  double cur[2], nxt[2] = {0, 0};
+  fetch_row(B + 1, cur);   // enters the window at the end of pivot 0
+  // lane -> (i, j) of the 6x6 lower triangle (diagonal-block factorisation by warp 0)
+  int li = 0, lj = 0;
+  {
+    int l = lane;
+    while (li < 5 && l > li) { l -= li + 1; li++; }
+    lj = l;
+    if (lane >= 21) { li = 0; lj = 0; }
+  }
   __syncthreads();
   bool ok = true;
+  if (wid == 0) {   // pivot 0 has no predecessor: factor it here
+    const bool okk = band_factor_diag(Wm, LDW, 0, rw, zb, v.band_z, lane, li, lj);
+    if (!okk && lane == 0) flag = 0;
+  }
+  __syncthreads();
+  long long tB = 0, tC1 = 0, tC2 = 0, tC3 = 0;
+  const long long t_f0 = clock64();
   for (int k = 0; k < nf; k++) {
-    const int sk = k % WB;
-    const int kend = min(k + B, nf - 1);
-    // ---- A
-    if (tid == 0) {
-      double M[6][6], zz[6];
-#pragma unroll
-      for (int i = 0; i < 6; i++) {
-        zz[i] = rw[6 * sk + i];
-#pragma unroll
-        for (int j = 0; j < 6; j++) M[i][j] = (j <= i) ? Wm[(size_t)(6 * sk + i) * LDW + 6 * sk + j] : 0.0;
-      }
-      bool okk = true;
-#pragma unroll
-      for (int j = 0; j < 6; j++) {
-        double d = M[j][j];
-#pragma unroll
-        for (int q = 0; q < 6; q++)
-          if (q < j) d -= M[j][q] * M[j][q] * M[q][q];
-        if (!(d != 0.0) || !isfinite(d)) okk = false;
-        M[j][j] = d;
-        const double id = 1.0 / d;
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-          if (i > j) {
-            double s2 = M[i][j];
-#pragma unroll
-            for (int q = 0; q < 6; q++)
-              if (q < j) s2 -= M[i][q] * M[j][q] * M[q][q];
-            M[i][j] = s2 * id;
-          }
-      }
-      if (!okk) flag = 0;
-#pragma unroll
-      for (int i = 0; i < 6; i++)
-#pragma unroll
-        for (int q = 0; q < 6; q++)
-          if (q < i) zz[i] -= M[i][q] * zz[q];
-#pragma unroll
-      for (int i = 0; i < 6; i++) {
-        zb[i] = zz[i];
-        v.band_z[6 * (size_t)k + i] = zz[i];
-#pragma unroll
-        for (int j = 0; j < 6; j++)
-          if (j <= i) Wm[(size_t)(6 * sk + i) * LDW + 6 * sk + j] = M[i][j];
-      }
-    }
-    __syncthreads();
     if (!flag) { ok = false; break; }
-    // ---- B: panel rows + zero the spare slot
-    const int npr = 6 * (kend - k);
+    const int sk = k % WB;
+    const int kend = min(k + B, nf - 1), nb_act = kend - k;
+    double* zq = zb + 16 * (k & 1);
+    const long long c0 = clock64();
+    fetch_row(k + B + 2, nxt);   // two pivots ahead of its use
+    // ---- B: panel rows
+    const int npr = 6 * nb_act;
     for (int x = tid; x < npr; x += nt) {
-      const int ib = k + 1 + x / 6, ri = x % 6;
-      double* row = Wm + (size_t)(6 * (ib % WB) + ri) * LDW + 6 * sk;
+      const int d = 1 + x / 6, ri = x - 6 * (d - 1);
+      int sl = sk + d;
+      if (sl >= WB) sl -= WB;
+      double* row = Wm + (size_t)(6 * sl + ri) * LDW + 6 * sk;
       double t6[6];
 #pragma unroll
       for (int c = 0; c < 6; c++) {
@@ -1344,35 +1393,76 @@ __global__ void __launch_bounds__(1024) k_solve_band(BaView v) {
       }
 #pragma unroll
       for (int c = 0; c < 6; c++) {
-        row[c] = t6[c] / Wm[(size_t)(6 * sk + c) * LDW + 6 * sk + c];
+        row[c] = t6[c] * zq[8 + c];
         Tt[(size_t)c * 6 * B + x] = t6[c];
       }
     }
-    if (k + B + 1 < nf) zero_row(k + B + 1);
     __syncthreads();
-    // ---- C: trailing update (one warp per row), column panel to HBM, gather of the incoming block row
-    for (int x = wid; x < npr; x += nw) {
-      const int ib = k + 1 + x / 6, ri = x % 6;
-      double* row = Wm + (size_t)(6 * (ib % WB) + ri) * LDW;
-      const double* lp = row + 6 * sk;
-      const double l0 = lp[0], l1 = lp[1], l2 = lp[2], l3 = lp[3], l4 = lp[4], l5 = lp[5];
-      for (int jj = lane; jj <= x; jj += 32) {
-        const int jb = k + 1 + jj / 6, jc = jj % 6;
-        row[6 * (jb % WB) + jc] -= l0 * Tt[jj] + l1 * Tt[6 * B + jj] + l2 * Tt[12 * B + jj] + l3 * Tt[18 * B + jj] +
-                                   l4 * Tt[24 * B + jj] + l5 * Tt[30 * B + jj];
+    const long long c1 = clock64();
+    // ---- C: trailing update, one warp per block row di (warp 0: block row 1 only, then the look-ahead): the 6x6 L block of
+    // the row lives in registers (broadcast loads), lanes walk the row's columns — T(c, column) and the six C elements
+    // of a column are consecutive over the lanes, so every shared-memory access of this phase is conflict-free
+    for (int di = (wid == 0 ? 1 : 1 + wid); di <= nb_act; di += (wid == 0 ? (1 << 20) : nw - 1)) {
+      int si = sk + di;
+      if (si >= WB) si -= WB;
+      double* rowb = Wm + (size_t)(6 * si) * LDW;
+      double L[6][6];
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) L[r][c] = rowb[(size_t)r * LDW + 6 * sk + c];
+      for (int jj = lane; jj < 6 * di; jj += 32) {
+        const int dj = 1 + jj / 6, rj = jj - 6 * (dj - 1);
+        int sj = sk + dj;
+        if (sj >= WB) sj -= WB;
+        const int col = 6 * sj + rj;
+        double tv[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) tv[c] = Tt[(size_t)c * 6 * B + jj];
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+          double a2 = 0;
+#pragma unroll
+          for (int c = 0; c < 6; c++) a2 += L[r][c] * tv[c];
+          rowb[(size_t)r * LDW + col] -= a2;
+        }
       }
-      if (lane == 0) rw[6 * (ib % WB) + ri] -= l0 * zb[0] + l1 * zb[1] + l2 * zb[2] + l3 * zb[3] + l4 * zb[4] + l5 * zb[5];
+      if (lane < 6)   // rhs rows of this block
+        rw[6 * si + lane] -= rowb[(size_t)lane * LDW + 6 * sk] * zq[0] + rowb[(size_t)lane * LDW + 6 * sk + 1] * zq[1] +
+                             rowb[(size_t)lane * LDW + 6 * sk + 2] * zq[2] + rowb[(size_t)lane * LDW + 6 * sk + 3] * zq[3] +
+                             rowb[(size_t)lane * LDW + 6 * sk + 4] * zq[4] + rowb[(size_t)lane * LDW + 6 * sk + 5] * zq[5];
     }
-    {
+    const long long c2 = clock64();
+    // look-ahead: items (1,1) live on lanes 0 and 1 of warp 0 -> block (k+1, k+1) and its rhs are final
+    if (wid == 0 && k + 1 < nf) {
+      __syncwarp();
+      int s1 = sk + 1;
+      if (s1 >= WB) s1 -= WB;
+      const bool okk = band_factor_diag(Wm, LDW, s1, rw, zb + 16 * ((k + 1) & 1), v.band_z + 6 * (size_t)(k + 1), lane, li, lj);
+      if (!okk && lane == 0) flag = 0;
+    }
+    const long long c3 = clock64();
+    // column panel k of L to HBM (backward pass) — the diagonal block of column k is no longer touched
+    if (wid != 0) {
       double* Lk = v.band_L + (size_t)k * PB * 36;
-      for (int i = tid; i < (kend - k + 1) * 36; i += nt) {
-        const int ib = k + i / 36, e = i % 36, rr = e / 6, cc = e - 6 * rr;
-        Lk[i] = Wm[(size_t)(6 * (ib % WB) + rr) * LDW + 6 * sk + cc];
+      for (int i = tid - 32; i < (nb_act + 1) * 36; i += nt - 32) {
+        const int d = i / 36, e = i - 36 * d, rr = e / 6, cc = e - 6 * rr;
+        int sl = sk + d;
+        if (sl >= WB) sl -= WB;
+        Lk[i] = Wm[(size_t)(6 * sl + rr) * LDW + 6 * sk + cc];
       }
     }
-    if (k + B + 1 < nf) scatter_row(k + B + 1);
+    // the incoming block row k + B + 1 takes the window slot of block k - 1, which no item of this phase touches
+    commit_row(k + B + 1, cur);
+    cur[0] = nxt[0];
+    cur[1] = nxt[1];
     __syncthreads();
+    tB += c1 - c0; tC1 += c2 - c1; tC2 += c3 - c2; tC3 += clock64() - c3;
   }
+  const long long t_f1 = clock64();
+  if (v.debug && tid == 0)
+    printf("[k_solve_band] nf %d B %d forward %lld cycles: panel+barrier %lld, block row 1 (warp 0) %lld, look-ahead factor %lld, tail+barrier %lld\n", nf, B,
+           t_f1 - t_f0, tB, tC1, tC2, tC3);
   if (ok) {
     // backward substitution over the stored column panels; x window kept in rw (circular), panel k-1 prefetched
     double pre[2] = {0, 0};
@@ -1432,6 +1522,7 @@ __global__ void __launch_bounds__(1024) k_solve_band(BaView v) {
     }
   }
   __syncthreads();
+  if (v.debug && tid == 0) printf("[k_solve_band] backward %lld cycles\n", clock64() - t_f1);
   for (int k = v.kf_off[w] + tid; k < v.kf_off[w + 1]; k += nt) {
     const int g = v.kf_g[k];
     double qt[7];
