@@ -1399,10 +1399,11 @@ __global__ void __launch_bounds__(NT) k_solve_band(BaView v) {
     }
     __syncthreads();
     const long long c1 = clock64();
-    // ---- C: trailing update, one warp per block row di (warp 0: block row 1 only, then the look-ahead): the 6x6 L block of
+    // ---- C: trailing update, one warp per block row di (last warp: block row 1 only, then the look-ahead): the 6x6 L block of
     // the row lives in registers (broadcast loads), lanes walk the row's columns — T(c, column) and the six C elements
     // of a column are consecutive over the lanes, so every shared-memory access of this phase is conflict-free
-    for (int di = (wid == 0 ? 1 : 1 + wid); di <= nb_act; di += (wid == 0 ? (1 << 20) : nw - 1)) {
+    // (the look-ahead warp is the LAST warp: the issue arbiter favours high warp ids, and this warp is the critical path)
+    for (int di = (wid == nw - 1 ? 1 : 2 + wid); di <= nb_act; di += (wid == nw - 1 ? (1 << 20) : nw - 1)) {
       int si = sk + di;
       if (si >= WB) si -= WB;
       double* rowb = Wm + (size_t)(6 * si) * LDW;
@@ -1434,7 +1435,7 @@ __global__ void __launch_bounds__(NT) k_solve_band(BaView v) {
     }
     const long long c2 = clock64();
     // look-ahead: items (1,1) live on lanes 0 and 1 of warp 0 -> block (k+1, k+1) and its rhs are final
-    if (wid == 0 && k + 1 < nf) {
+    if (wid == nw - 1 && k + 1 < nf) {
       __syncwarp();
       int s1 = sk + 1;
       if (s1 >= WB) s1 -= WB;
@@ -1443,9 +1444,9 @@ __global__ void __launch_bounds__(NT) k_solve_band(BaView v) {
     }
     const long long c3 = clock64();
     // column panel k of L to HBM (backward pass) — the diagonal block of column k is no longer touched
-    if (wid != 0) {
+    if (wid != nw - 1) {
       double* Lk = v.band_L + (size_t)k * PB * 36;
-      for (int i = tid - 32; i < (nb_act + 1) * 36; i += nt - 32) {
+      for (int i = tid; i < (nb_act + 1) * 36; i += nt - 32) {
         const int d = i / 36, e = i - 36 * d, rr = e / 6, cc = e - 6 * rr;
         int sl = sk + d;
         if (sl >= WB) sl -= WB;
@@ -1460,8 +1461,8 @@ __global__ void __launch_bounds__(NT) k_solve_band(BaView v) {
     tB += c1 - c0; tC1 += c2 - c1; tC2 += c3 - c2; tC3 += clock64() - c3;
   }
   const long long t_f1 = clock64();
-  if (v.debug && tid == 0)
-    printf("[k_solve_band] nf %d B %d forward %lld cycles: panel+barrier %lld, block row 1 (warp 0) %lld, look-ahead factor %lld, tail+barrier %lld\n", nf, B,
+  if (v.debug && tid == nt - 32)
+    printf("[k_solve_band] nf %d B %d forward %lld cycles: panel+barrier %lld, block row 1 (look-ahead warp, seen from thread 0: its own rows) %lld, look-ahead factor %lld, tail+barrier %lld\n", nf, B,
            t_f1 - t_f0, tB, tC1, tC2, tC3);
   if (ok) {
     // backward substitution over the stored column panels; x window kept in rw (circular), panel k-1 prefetched

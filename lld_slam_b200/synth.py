@@ -99,7 +99,7 @@ def make_ba_window(n_kf, n_pt, n_ln, rng, *, mean_track=5.0, track_mode="normal"
         L = np.clip(rng.geometric(1.0 / mean_track, n_pt), 2, 20)
     else:
         L = np.clip(np.rint(rng.normal(mean_track, 1.5, n_pt)), 2, n_all).astype(np.int64)
-    Lmax = int(L.max())
+    Lmax = int(L.max()) if n_pt else 1
     start = anchor - L + 1 + rng.integers(0, 3, n_pt)
     cand = start[:, None] + np.arange(Lmax)[None, :]
     ok = (np.arange(Lmax)[None, :] < L[:, None]) & (cand >= 0) & (cand < n_all)

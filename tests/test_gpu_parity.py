@@ -271,3 +271,55 @@ def test_global_ba_banded_envelope(gpu_ctx):
     g = api.ba_global(p, 6, impl="gpu", ctx=gpu_ctx)
     o = api.ba_global(p, 6, impl="oracle")
     check_ba(g, o, "gba banded")
+
+
+def test_sbp_frame_empty_frames(gpu_ctx, match_path):
+    """a pair whose current frame has no keypoints and a pair whose last frame has no map points, inside a batch"""
+    parts = [synth.make_sbp_frame_batch(1, 300, 71), synth.make_sbp_frame_batch(1, 200, 72), synth.make_sbp_frame_batch(1, 250, 73)]
+    p = synth.concat_sbp_frame(parts)
+    # empty the current frame of pair 1
+    c0, c1 = int(p["cur_off"][1]), int(p["cur_off"][2])
+    keep = np.ones(int(p["cur_off"][-1]), bool); keep[c0:c1] = False
+    for k in ("cur_xy", "cur_octave", "cur_angle", "cur_uright", "cur_desc", "cur_claimed"):
+        p[k] = np.ascontiguousarray(p[k][keep])
+    p["cur_off"] = np.array([0, c0, c0, c0 + int(p["cur_off"][3]) - c1], np.int32)
+    # empty the last frame of pair 2
+    q0, q1 = int(p["last_off"][2]), int(p["last_off"][3])
+    for k in ("last_valid", "last_xw", "last_octave", "last_angle", "last_desc", "last_has_obs"):
+        p[k] = np.ascontiguousarray(p[k][:q0])
+    p["last_off"] = np.array([0, int(p["last_off"][1]), q0, q0], np.int32)
+    g = api.sbp_frame(p, impl="gpu", ctx=gpu_ctx)
+    o = api.sbp_frame(p, impl="oracle")
+    assert o["n_matches"][0] > 50 and o["n_matches"][1] == 0 and o["n_matches"][2] == 0
+    for k in ("match", "n_matches", "best_idx", "best_dist"):
+        assert np.array_equal(g[k], o[k]), k
+
+
+def test_sbp_frame_capacity_boundary(gpu_ctx):
+    """2048 keypoints / queries: the largest pair the fused single-CTA kernel takes"""
+    p = synth.make_sbp_frame_batch(2, 2048, 2048)
+    g = api.sbp_frame(p, impl="gpu", ctx=gpu_ctx)
+    o = api.sbp_frame(p, impl="oracle")
+    for k in ("match", "n_matches", "best_idx", "best_dist"):
+        assert np.array_equal(g[k], o[k]), k
+
+
+def test_local_ba_points_only_and_lines_only_windows(gpu_ctx):
+    """windows without lines and without points in one batch (empty landmark classes)"""
+    rng = np.random.default_rng(91)
+    wins = [synth.make_ba_window(6, 400, 0, rng), synth.make_ba_window(6, 0, 150, rng), synth.make_ba_window(4, 120, 30, rng)]
+    p = synth.batch_ba(wins, "local")
+    g = api.ba_local(p, 5, 15, impl="gpu", ctx=gpu_ctx)
+    o = api.ba_local(p, 5, 15, impl="oracle")
+    check_ba(g, o, "points-only / lines-only")
+
+
+def test_pose_opt_without_lines(gpu_ctx):
+    p = synth.make_pose_batch(16, 400, 0, 33)
+    check_pose(api.pose_opt(p, impl="gpu", ctx=gpu_ctx), api.pose_opt(p, impl="oracle"))
+
+
+def test_line_match_single_small_pair(gpu_ctx, line_path):
+    """fewer right lines than one tensor-core column half"""
+    p = synth.make_line_match_batch(1, 40, 64, 4)
+    check_line_match(api.line_match(p, impl="gpu", ctx=gpu_ctx), api.line_match(p, impl="oracle"))
