@@ -323,3 +323,93 @@ def test_line_match_single_small_pair(gpu_ctx, line_path):
     """fewer right lines than one tensor-core column half"""
     p = synth.make_line_match_batch(1, 40, 64, 4)
     check_line_match(api.line_match(p, impl="gpu", ctx=gpu_ctx), api.line_match(p, impl="oracle"))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes.  The oracle is fast enough for a complete comparison of the matchers and of one GPU's share
+# of the batched configurations; the global BA is compared through its LM trace (chi2 per iteration, iteration and trial
+# counts): along a 1500-keyframe chain the final poses are gauge-weak and are not a stable quantity to compare.
+# ------------------------------------------------------------------------------------------------------------------
+def _point_edge_chi2(p, out, e):
+    """chi2 of point edge e at the final state (double precision restatement of the stereo / mono residual) and its gate"""
+    pt = int(np.searchsorted(p["pt_obs_off"], e, side="right") - 1)
+    w = int(np.searchsorted(p["pt_off"], pt, side="right") - 1)
+    kf = int(p["kf_off"][w] + p["pt_obs_kf"][e])
+    T = out["kf_Tcw"][kf]
+    X = T[:9].reshape(3, 3) @ out["pt_xyz"][pt] + T[9:]
+    fx, fy, cx, cy, bf = p["kf_intr"][kf]
+    u, v, ur = (float(x) for x in p["pt_obs_uvr"][e])
+    iz = 1.0 / X[2]
+    r = [u - (fx * X[0] * iz + cx), v - (fy * X[1] * iz + cy)]
+    th = float(p["chi2_pt_mono"])
+    if ur >= 0:
+        r.append(ur - (fx * X[0] * iz + cx - bf * iz))
+        th = float(p["chi2_pt_stereo"])
+    return float(p["pt_obs_info"][e]) * float(np.dot(r, r)), th
+
+
+def test_full_size_hamming_config(gpu_ctx):
+    """configs[1]: 1024 frame pairs x 2000 ORB keypoints, complete bit-exact comparison + structural properties"""
+    p = synth.make_sbp_frame_batch(1024, 2000, synth.seed_for(2))
+    g = api.sbp_frame(p, impl="gpu", ctx=gpu_ctx)
+    o = api.sbp_frame(p, impl="oracle")
+    for k in ("match", "n_matches", "best_idx", "best_dist"):
+        assert np.array_equal(g[k], o[k]), k
+    # properties: reported distances are the popcounts of the matched descriptors; counts add up
+    q = np.nonzero(g["best_idx"] >= 0)[0][:: 97]
+    pair = np.searchsorted(p["last_off"], q, side="right") - 1
+    kp = p["cur_off"][pair] + g["best_idx"][q]
+    d = np.unpackbits(p["last_desc"][q] ^ p["cur_desc"][kp], axis=1).sum(1)
+    assert np.array_equal(d, g["best_dist"][q])
+    assert 0 < int((g["match"] >= 0).sum()) <= int(g["n_matches"].sum())   # several queries may end on one keypoint
+
+
+def test_full_size_line_config(gpu_ctx):
+    """configs[1], line part: 500 x 500 lines, D = 64; 64 pairs against the oracle (the oracle needs ~0.06 s per pair)"""
+    p = synth.make_line_match_batch(64, 500, 64, synth.seed_for(2) + 7)
+    check_line_match(api.line_match(p, impl="gpu", ctx=gpu_ctx), api.line_match(p, impl="oracle"))
+
+
+def test_full_size_pose_config(gpu_ctx):
+    """configs[2] frame shape, 512 frames of 1500 points + 300 lines"""
+    p = synth.make_pose_batch(512, 1500, 300, synth.seed_for(3) + 2)
+    check_pose(api.pose_opt(p, impl="gpu", ctx=gpu_ctx), api.pose_opt(p, impl="oracle"))
+
+
+def test_full_size_batched_local_ba_config(gpu_ctx):
+    """configs[3]: one GPU's share at 8 GPUs would be 64 windows of 20 / 5000 / 1000; 16 of them against the oracle, and the
+    same 16 inside a 64-window batch must give the same results up to summation order (windows are independent; piece and
+    chunk sizes adapt to the batch, so the grouping of the fixed-order reductions differs between batch sizes)"""
+    p16 = synth.make_local_ba_batch(16, 20, 5000, 1000, synth.seed_for(4))
+    g16 = api.ba_local(p16, 5, 15, impl="gpu", ctx=gpu_ctx)
+    o16 = api.ba_local(p16, 5, 15, impl="oracle")
+    # 340k point edges: an edge whose chi2 sits on the 5.991 / 7.815 gate can flip with the 1e-6 chi2 agreement.  Such
+    # flips are accepted only when the edge's chi2 (recomputed here in numpy at the final state) is within 1e-4 of the gate.
+    flip = np.nonzero(g16["pt_obs_bad"] != o16["pt_obs_bad"])[0]
+    assert len(flip) <= 3, len(flip)
+    for e in flip:
+        c2, th = _point_edge_chi2(p16, g16, int(e))
+        assert abs(c2 - th) <= 1e-4 * th, (int(e), c2, th)
+    o16 = dict(o16)
+    o16["pt_obs_bad"] = o16["pt_obs_bad"].copy()
+    o16["pt_obs_bad"][flip] = g16["pt_obs_bad"][flip]
+    check_ba(g16, o16, "cfg4 x16")
+    p64 = synth.make_local_ba_batch(64, 20, 5000, 1000, synth.seed_for(4))
+    g64 = api.ba_local(p64, 5, 15, impl="gpu", ctx=gpu_ctx)
+    n = int(p16["kf_off"][-1])
+    assert np.array_equal(p64["kf_Tcw"][:n], p16["kf_Tcw"])          # same generator stream: the first 16 windows coincide
+    assert np.array_equal(g64["n_iter_done"][:16], g16["n_iter_done"]) and np.array_equal(g64["trials_log"][:16], g16["trials_log"])
+    # (measured: 1.5e-7 m between the two batch sizes after 20 LM iterations, the same size as the GPU-vs-oracle difference)
+    assert np.abs(g64["kf_Tcw"][:n] - g16["kf_Tcw"]).max() <= POS_TOL
+    rel = np.abs(g64["chi2_log"][:16] - g16["chi2_log"]) / np.maximum(np.abs(g16["chi2_log"]), 1e-9)
+    assert rel.max() <= CHI2_RTOL, rel.max()
+
+
+def test_full_size_global_ba_config(gpu_ctx):
+    """configs[4]: 1.5k keyframes / 300k points / 60k lines, 10 iterations: LM trace against the oracle"""
+    p = synth.make_global_ba(1500, 300000, 60000, synth.seed_for(5))
+    g = api.ba_global(p, 10, impl="gpu", ctx=gpu_ctx)
+    o = api.ba_global(p, 10, impl="oracle")
+    assert np.array_equal(g["n_iter_done"], o["n_iter_done"]) and np.array_equal(g["trials_log"], o["trials_log"])
+    rel = np.abs(g["chi2_log"] - o["chi2_log"]) / np.maximum(np.abs(o["chi2_log"]), 1e-9)
+    assert rel.max() <= CHI2_RTOL, rel.max()
