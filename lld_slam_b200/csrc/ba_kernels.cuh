@@ -1324,20 +1324,27 @@ __global__ void __launch_bounds__(NT) k_solve_band(BaView v) {
       r2[u] = (r < nf && i < PB * 36 + 6) ? v.band_A[(size_t)r * RS + i] : 0.0;
     }
   };
-  auto commit_row = [&](int r, const double* r2) {
+  // element roles of this thread inside a band row (loop invariant): kind 0 = matrix entry (block j, row ri, col ci), 1 = rhs
+  int el_kind[2], el_j[2], el_roff[2], el_ci[2];
+#pragma unroll
+  for (int u = 0; u < 2; u++) {
+    const int i = tid + u * nt;
+    el_kind[u] = i < PB * 36 ? 0 : (i < PB * 36 + 6 ? 1 : 2);
+    const int j = i / 36, e = i - 36 * j, ri = e / 6;
+    el_j[u] = j;
+    el_roff[u] = el_kind[u] == 0 ? ri * LDW : i - PB * 36;
+    el_ci[u] = e - 6 * ri;
+  }
+  auto commit_row = [&](int r, int s, const double* r2) {   // s = r mod WB
     if (r >= nf) return;
-    const int s = r % WB;
 #pragma unroll
     for (int u = 0; u < 2; u++) {
-      const int i = tid + u * nt;
-      if (i < PB * 36) {
-        const int j = i / 36, e = i - 36 * j, ri = e / 6, ci = e - 6 * ri;
-        const int c = r - B + j;
-        int sc = s + 2 + j;   // (r - B + j) mod WB with WB = B + 2
+      if (el_kind[u] == 0) {
+        int sc = s + 2 + el_j[u];   // (r - B + j) mod WB with WB = B + 2
         if (sc >= WB) sc -= WB;
-        if (c >= 0) Wm[(size_t)(6 * s + ri) * LDW + 6 * sc + ci] = r2[u];
-      } else if (i < PB * 36 + 6) {
-        rw[6 * s + (i - PB * 36)] = r2[u];
+        if (r - B + el_j[u] >= 0) Wm[6 * s * LDW + el_roff[u] + 6 * sc + el_ci[u]] = r2[u];
+      } else if (el_kind[u] == 1) {
+        rw[6 * s + el_roff[u]] = r2[u];
       }
     }
   };
@@ -1347,7 +1354,7 @@ __global__ void __launch_bounds__(NT) k_solve_band(BaView v) {
   for (int r = 0; r < nf && r <= B; r++) {
     double t2[2];
     fetch_row(r, t2);
-    commit_row(r, t2);
+    commit_row(r, r, t2);   // r <= B < WB
   }
   double cur[2], nxt[2] = {0, 0};
   fetch_row(B + 1, cur);   // enters the window at the end of pivot 0
@@ -1366,39 +1373,46 @@ __global__ void __launch_bounds__(NT) k_solve_band(BaView v) {
     if (!okk && lane == 0) flag = 0;
   }
   __syncthreads();
-  long long tB = 0, tC1 = 0, tC2 = 0, tC3 = 0;
-  const long long t_f0 = clock64();
-  for (int k = 0; k < nf; k++) {
+  // loop-invariant roles: panel row of this thread (phase B), panel-store element, update columns of this lane
+  const int pb_d = 1 + tid / 6, pb_ri = tid - 6 * (pb_d - 1);
+  int uc_d[4], uc_rj[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int jj = lane + 32 * q;
+    uc_d[q] = 1 + jj / 6;
+    uc_rj[q] = jj - 6 * (uc_d[q] - 1);
+  }
+  int sk = 0;              // k mod WB
+  int s_in = (B + 1) % WB; // (k + B + 1) mod WB: slot of the incoming row
+  for (int k = 0; k < nf; k++, sk = (sk + 1 == WB ? 0 : sk + 1), s_in = (s_in + 1 == WB ? 0 : s_in + 1)) {
     if (!flag) { ok = false; break; }
-    const int sk = k % WB;
     const int kend = min(k + B, nf - 1), nb_act = kend - k;
     double* zq = zb + 16 * (k & 1);
-    const long long c0 = clock64();
     fetch_row(k + B + 2, nxt);   // two pivots ahead of its use
     // ---- B: panel rows
     const int npr = 6 * nb_act;
     for (int x = tid; x < npr; x += nt) {
-      const int d = 1 + x / 6, ri = x - 6 * (d - 1);
+      const int d = x == tid ? pb_d : 1 + x / 6, ri = x == tid ? pb_ri : x - 6 * (1 + x / 6 - 1);
       int sl = sk + d;
       if (sl >= WB) sl -= WB;
-      double* row = Wm + (size_t)(6 * sl + ri) * LDW + 6 * sk;
+      double* row = Wm + (6 * sl + ri) * LDW + 6 * sk;
+      const double* dk = Wm + 6 * sk * LDW + 6 * sk;
       double t6[6];
 #pragma unroll
       for (int c = 0; c < 6; c++) {
         double s2 = row[c];
 #pragma unroll
         for (int q = 0; q < 6; q++)
-          if (q < c) s2 -= t6[q] * Wm[(size_t)(6 * sk + c) * LDW + 6 * sk + q];
+          if (q < c) s2 -= t6[q] * dk[c * LDW + q];
         t6[c] = s2;
       }
 #pragma unroll
       for (int c = 0; c < 6; c++) {
         row[c] = t6[c] * zq[8 + c];
-        Tt[(size_t)c * 6 * B + x] = t6[c];
+        Tt[c * 6 * B + x] = t6[c];
       }
     }
     __syncthreads();
-    const long long c1 = clock64();
     // ---- C: trailing update, one warp per block row di (last warp: block row 1 only, then the look-ahead): the 6x6 L block of
     // the row lives in registers (broadcast loads), lanes walk the row's columns — T(c, column) and the six C elements
     // of a column are consecutive over the lanes, so every shared-memory access of this phase is conflict-free
@@ -1412,20 +1426,38 @@ __global__ void __launch_bounds__(NT) k_solve_band(BaView v) {
       for (int r = 0; r < 6; r++)
 #pragma unroll
         for (int c = 0; c < 6; c++) L[r][c] = rowb[(size_t)r * LDW + 6 * sk + c];
-      for (int jj = lane; jj < 6 * di; jj += 32) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int jj = lane + 32 * q;
+        if (jj >= 6 * di) break;
+        int sj = sk + uc_d[q];
+        if (sj >= WB) sj -= WB;
+        const int col = 6 * sj + uc_rj[q];
+        double tv[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) tv[c] = Tt[c * 6 * B + jj];
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+          double a2 = 0;
+#pragma unroll
+          for (int c = 0; c < 6; c++) a2 += L[r][c] * tv[c];
+          rowb[r * LDW + col] -= a2;
+        }
+      }
+      for (int jj = lane + 128; jj < 6 * di; jj += 32) {   // block rows wider than 128 columns (B > 21)
         const int dj = 1 + jj / 6, rj = jj - 6 * (dj - 1);
         int sj = sk + dj;
         if (sj >= WB) sj -= WB;
         const int col = 6 * sj + rj;
         double tv[6];
 #pragma unroll
-        for (int c = 0; c < 6; c++) tv[c] = Tt[(size_t)c * 6 * B + jj];
+        for (int c = 0; c < 6; c++) tv[c] = Tt[c * 6 * B + jj];
 #pragma unroll
         for (int r = 0; r < 6; r++) {
           double a2 = 0;
 #pragma unroll
           for (int c = 0; c < 6; c++) a2 += L[r][c] * tv[c];
-          rowb[(size_t)r * LDW + col] -= a2;
+          rowb[r * LDW + col] -= a2;
         }
       }
       if (lane < 6)   // rhs rows of this block
@@ -1433,7 +1465,6 @@ __global__ void __launch_bounds__(NT) k_solve_band(BaView v) {
                              rowb[(size_t)lane * LDW + 6 * sk + 2] * zq[2] + rowb[(size_t)lane * LDW + 6 * sk + 3] * zq[3] +
                              rowb[(size_t)lane * LDW + 6 * sk + 4] * zq[4] + rowb[(size_t)lane * LDW + 6 * sk + 5] * zq[5];
     }
-    const long long c2 = clock64();
     // look-ahead: items (1,1) live on lanes 0 and 1 of warp 0 -> block (k+1, k+1) and its rhs are final
     if (wid == nw - 1 && k + 1 < nf) {
       __syncwarp();
@@ -1442,7 +1473,6 @@ __global__ void __launch_bounds__(NT) k_solve_band(BaView v) {
       const bool okk = band_factor_diag(Wm, LDW, s1, rw, zb + 16 * ((k + 1) & 1), v.band_z + 6 * (size_t)(k + 1), lane, li, lj);
       if (!okk && lane == 0) flag = 0;
     }
-    const long long c3 = clock64();
     // column panel k of L to HBM (backward pass) — the diagonal block of column k is no longer touched
     if (wid != nw - 1) {
       double* Lk = v.band_L + (size_t)k * PB * 36;
@@ -1454,16 +1484,11 @@ __global__ void __launch_bounds__(NT) k_solve_band(BaView v) {
       }
     }
     // the incoming block row k + B + 1 takes the window slot of block k - 1, which no item of this phase touches
-    commit_row(k + B + 1, cur);
+    commit_row(k + B + 1, s_in, cur);
     cur[0] = nxt[0];
     cur[1] = nxt[1];
     __syncthreads();
-    tB += c1 - c0; tC1 += c2 - c1; tC2 += c3 - c2; tC3 += clock64() - c3;
   }
-  const long long t_f1 = clock64();
-  if (v.debug && tid == nt - 32)
-    printf("[k_solve_band] nf %d B %d forward %lld cycles: panel+barrier %lld, block row 1 (look-ahead warp, seen from thread 0: its own rows) %lld, look-ahead factor %lld, tail+barrier %lld\n", nf, B,
-           t_f1 - t_f0, tB, tC1, tC2, tC3);
   if (ok) {
     // backward substitution over the stored column panels; x window kept in rw (circular), panel k-1 prefetched
     double pre[2] = {0, 0};
@@ -1523,7 +1548,6 @@ __global__ void __launch_bounds__(NT) k_solve_band(BaView v) {
     }
   }
   __syncthreads();
-  if (v.debug && tid == 0) printf("[k_solve_band] backward %lld cycles\n", clock64() - t_f1);
   for (int k = v.kf_off[w] + tid; k < v.kf_off[w + 1]; k += nt) {
     const int g = v.kf_g[k];
     double qt[7];

@@ -5,8 +5,9 @@
 // The descriptor distance LineMatcher::MatchLineDescriptors lives in the un-vendored LBDMOD library
 // (un-vendored and unpinned, so parity is unpinned): defined here as the L2 norm of the float rows.
 //
-// Device plan per stereo pair:
-//   k_line_prep   : per line, K^T-normalised image line equation and pixel length
+// Two device plans per stereo pair: the tensor-core path below (tcgen05, default: D multiple of 8 up to 72 floats and
+// <= 512 right lines) and the FP32 tile path for everything else:
+//   k_line_prep   : per line, K^T-normalised image line equation, unit plane normal and pixel length
 //   k_line_dist   : 32x32 tiles of the (left x right) pair matrix; descriptors staged in shared memory, dense
 //                   ||a-b||^2 contraction in FP32, fused epilogue = the geometric gates of CheckLinePair
 //                   (octave, length, triangulation angle, |X0|, endpoint depths) and the tau threshold;
@@ -227,12 +228,13 @@ __global__ void __launch_bounds__(32) k_line_greedy(LineMatchView v, int* taken_
 //   k_line_tc    : CTA = (pair, 128 left lines); descriptors split into TF32 hi / lo parts while being staged into the
 //                  canonical K-major no-swizzle UMMA layout in shared memory; D[128 x 512] fp32 lives in TMEM (all 512
 //                  columns); epilogue thread = (row, column half): d^2 = |a|^2 + |b|^2 - 2 a.b, cheap gates of
-//                  CheckLinePair (octave, lengths, tau), 8 best candidates per half kept in registers -> 16 per row
+//                  CheckLinePair (octave, lengths, tau) and the parallax test of vgl::TriangulateLine, survivors appended
+//                  to the row's candidate list (<= 128 per column half, in column order)
 //   k_line_greedy_lazy : one warp per pair replays the sequential greedy; the FP64 geometry (triangulation, |X0|,
-//                  endpoint depths) is evaluated lazily, smallest keys first, until no unexamined key can win
-//   k_line_greedy_tc : CTA per pair, candidate lists staged in shared memory, one warp replays the sequential greedy
-//                  (a list that runs dry while unseen candidates could still win falls back to an exact scan of the row);
-//                  the distance reported for a match is recomputed exactly in FP32 from the descriptors
+//                  endpoint depths) is evaluated lazily, smallest keys first, until no unexamined key can win; a row
+//                  whose list overflowed takes an exact scan of the pair
+//   k_line_exact : the distance reported for a match is recomputed exactly in FP32 from the descriptors
+//   k_line_gate  : exhaustive gate pass, statistics runs only (LLD_LINE_STATS)
 // The ranking uses the 3xTF32 distances (|error| ~ 1e-6 in d^2), the reported distances are exact: within the stated
 // tolerance 1e-5 * max(1, d), identical matches unless two candidates are closer than that.
 // ================================================================================================
