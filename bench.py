@@ -177,8 +177,10 @@ def kernel_bytes(name, p):
     nw = int(p["n_win"])
     nf = K / nw - 1
     tbl = {
-        "k_lin_points": n_pe * 24 + n_pw * 144 + P * (24 + 72),
-        "k_lin_lines": n_lc * 56 + n_lw * 192 + L * (40 + 112),
+        "k_lin_points<1>": n_pe * 24 + n_pw * 144 + P * (24 + 72),
+        "k_lin_points<4>": n_pe * 24 + n_pw * 144 + P * (24 + 72),
+        "k_lin_lines<1>": n_lc * 56 + n_lw * 192 + L * (40 + 112),
+        "k_lin_lines<8>": n_lc * 56 + n_lw * 192 + L * (40 + 112),
         "k_lin_poses": n_pe * 24 + n_lc * 56 + (n_pe + n_lc) * 24,
         "k_schur_points": P * (72 + 80),
         "k_schur_lines": L * (112 + 112),
@@ -186,8 +188,10 @@ def kernel_bytes(name, p):
         "k_schur_piece<3>": n_pw * 144 + P * 80,
         "k_schur_piece<4>": n_lw * 192 + L * 112,
         "k_schur_rows": n_pe * (144 + 144) + n_lc * (192 + 192) + nw * 8 * 36 * nf * (nf + 1) / 2,
-        "k_backsub_points": n_pw * 144 + n_pe * (24 + 8) + P * (24 + 24 + 80),
-        "k_backsub_lines": n_lw * 192 + n_lc * (56 + 16) + L * (40 + 40 + 112),
+        "k_backsub_points<1>": n_pw * 144 + n_pe * (24 + 8) + P * (24 + 24 + 80),
+        "k_backsub_points<4>": n_pw * 144 + n_pe * (24 + 8) + P * (24 + 24 + 80),
+        "k_backsub_lines<1>": n_lw * 192 + n_lc * (56 + 16) + L * (40 + 40 + 112),
+        "k_backsub_lines<8>": n_lw * 192 + n_lc * (56 + 16) + L * (40 + 40 + 112),
     }
     return tbl.get(name)
 

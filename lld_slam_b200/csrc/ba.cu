@@ -938,6 +938,11 @@ static int launch_solve(LldCtx* c, BaView& v, int max_n) {
 //   solve -> [backsub_points | backsub_lines] -> decide
 // (a small batch does not fill the GPU with any single pass; the critical path is what counts).  Works eagerly and
 // under stream capture (the side streams join the capture through the fork event).
+// up to this many map lines the line kernels run eight lanes per line (single windows); one lane per line above
+constexpr int LN_WIDE_MAX = 8192;
+// same for map points, four lanes per point
+constexpr int PT_WIDE_MAX = 32768;
+
 static int ba_step_forked(LldCtx* c, int round, int stop_now) {
   BaState* S = c->ba;
   BaView& v = S->v;
@@ -951,8 +956,10 @@ static int ba_step_forked(LldCtx* c, int round, int stop_now) {
   LLD_CUDA(c, cudaEventRecord(c->ev_fork, s0));
   LLD_CUDA(c, fork(s1));
   LLD_CUDA(c, fork(s2));
-  if (v.n_pt) LLD_LAUNCH_S(c, s0, k_lin_points, gp, LM_TPB, 0, v);
-  if (v.n_ln) LLD_LAUNCH_S(c, s1, k_lin_lines, gl, LM_TPB, 0, v);
+  if (v.n_pt && v.n_pt <= PT_WIDE_MAX) LLD_LAUNCH_S(c, s0, k_lin_points<4>, cdiv(v.n_pt * 4, LM_TPB), LM_TPB, 0, v);
+  else if (v.n_pt) LLD_LAUNCH_S(c, s0, k_lin_points<1>, gp, LM_TPB, 0, v);
+  if (v.n_ln && v.n_ln <= LN_WIDE_MAX) LLD_LAUNCH_S(c, s1, k_lin_lines<8>, cdiv(v.n_ln * 8, LM_TPB), LM_TPB, 0, v);
+  else if (v.n_ln) LLD_LAUNCH_S(c, s1, k_lin_lines<1>, cdiv(v.n_ln, LM_TPB), LM_TPB, 0, v);
   if (v.n_chunks) LLD_LAUNCH_S(c, s2, k_lin_poses, v.n_chunks, LM_TPB, 0, v);
   LLD_CUDA(c, join(0));
   LLD_CUDA(c, join(1));
@@ -970,8 +977,10 @@ static int ba_step_forked(LldCtx* c, int round, int stop_now) {
   { int r = launch_solve<true>(c, v, S->max_n); if (r) return r; }
   LLD_CUDA(c, cudaEventRecord(c->ev_fork, s0));
   LLD_CUDA(c, fork(s1));
-  if (v.n_pt) LLD_LAUNCH_S(c, s0, k_backsub_points, gp, LM_TPB, 0, v);
-  if (v.n_ln) LLD_LAUNCH_S(c, s1, k_backsub_lines, gl, LM_TPB, 0, v);
+  if (v.n_pt && v.n_pt <= PT_WIDE_MAX) LLD_LAUNCH_S(c, s0, k_backsub_points<4>, cdiv(v.n_pt * 4, LM_TPB), LM_TPB, 0, v);
+  else if (v.n_pt) LLD_LAUNCH_S(c, s0, k_backsub_points<1>, gp, LM_TPB, 0, v);
+  if (v.n_ln && v.n_ln <= LN_WIDE_MAX) LLD_LAUNCH_S(c, s1, k_backsub_lines<8>, cdiv(v.n_ln * 8, LM_TPB), LM_TPB, 0, v);
+  else if (v.n_ln) LLD_LAUNCH_S(c, s1, k_backsub_lines<1>, cdiv(v.n_ln, LM_TPB), LM_TPB, 0, v);
   LLD_CUDA(c, join(0));
   LLD_LAUNCH_S(c, s0, k_decide_fused, v.n_win, FUSED_RED_TPB, 0, v, round, stop_now);
   LLD_CUDA(c, cudaGetLastError());
@@ -984,8 +993,10 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   BaView& v = S->v;
   if (S->forked && !c->prof_on) return ba_step_forked(c, round, stop_now);
   const int gp = cdiv(std::max(v.n_pt, 1), LM_TPB), gl = cdiv(std::max(v.n_ln, 1), LM_TPB);
-  if (v.n_pt) LLD_LAUNCH(c, k_lin_points, gp, LM_TPB, 0, v);
-  if (v.n_ln) LLD_LAUNCH(c, k_lin_lines, gl, LM_TPB, 0, v);
+  if (v.n_pt && v.n_pt <= PT_WIDE_MAX) LLD_LAUNCH(c, k_lin_points<4>, cdiv(v.n_pt * 4, LM_TPB), LM_TPB, 0, v);
+  else if (v.n_pt) LLD_LAUNCH(c, k_lin_points<1>, gp, LM_TPB, 0, v);
+  if (v.n_ln && v.n_ln <= LN_WIDE_MAX) LLD_LAUNCH(c, k_lin_lines<8>, cdiv(v.n_ln * 8, LM_TPB), LM_TPB, 0, v);
+  else if (v.n_ln) LLD_LAUNCH(c, k_lin_lines<1>, cdiv(v.n_ln, LM_TPB), LM_TPB, 0, v);
   if (v.n_chunks) LLD_LAUNCH(c, k_lin_poses, v.n_chunks, LM_TPB, 0, v);
   const bool multi = S->global_mode && c->n_ranks > 1;
   const bool fused = !multi && v.n_slices == 1;
@@ -1030,8 +1041,10 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
     LLD_LAUNCH(c, k_solve_env, 1, 1024, S->env_smem, v);
   } else if (S->max_n <= SMEM_SOLVE_MAX_N) { int r = launch_solve<true>(c, v, S->max_n); if (r) return r; }
   else { int r = launch_solve<false>(c, v, S->max_n); if (r) return r; }
-  if (v.n_pt) LLD_LAUNCH(c, k_backsub_points, gp, LM_TPB, 0, v);
-  if (v.n_ln) LLD_LAUNCH(c, k_backsub_lines, gl, LM_TPB, 0, v);
+  if (v.n_pt && v.n_pt <= PT_WIDE_MAX) LLD_LAUNCH(c, k_backsub_points<4>, cdiv(v.n_pt * 4, LM_TPB), LM_TPB, 0, v);
+  else if (v.n_pt) LLD_LAUNCH(c, k_backsub_points<1>, gp, LM_TPB, 0, v);
+  if (v.n_ln && v.n_ln <= LN_WIDE_MAX) LLD_LAUNCH(c, k_backsub_lines<8>, cdiv(v.n_ln * 8, LM_TPB), LM_TPB, 0, v);
+  else if (v.n_ln) LLD_LAUNCH(c, k_backsub_lines<1>, cdiv(v.n_ln, LM_TPB), LM_TPB, 0, v);
   if (fused) {
     LLD_LAUNCH(c, k_decide_fused, v.n_win, FUSED_RED_TPB, 0, v, round, stop_now);
   } else {

@@ -137,11 +137,17 @@ __device__ __forceinline__ void make_line_obs(const BaView& v, int kf, const flo
   o.x2[2] = 1.0;
 }
 
+// PT_G lanes per map point (4 for single windows, where one lane per point fills a third of the SMs; 1 for batches):
+// lane g takes edges e0 + g, e0 + g + PT_G, ...; the sums are combined by a fixed xor butterfly inside the lane group.
+template <int PT_G>
 __global__ void __launch_bounds__(LM_TPB) k_lin_points(BaView v) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= v.n_pt) return;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pl = gt / PT_G, gl = gt - pl * PT_G;
+  const bool live = pl < v.n_pt;
+  const int p = live ? pl : v.n_pt - 1;  // dead lanes shadow the last point (shuffles stay full-warp), no stores
   const int w = v.pt_win[p];
-  if (v.w_phase[w] != PH_LIN) return;
+  const bool run = live && v.w_phase[w] == PH_LIN;
+  if (PT_G == 1 && !run) return;
   const int sel = v.w_sel[w];
   const double* Xp = v.pt_xyz[sel] + 3 * (size_t)p;
   const double X[3] = {Xp[0], Xp[1], Xp[2]};
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_points(BaView v) {
   double chi = 0;
   int nact = 0;
   const int e0 = v.pt_obs_off[p], e1 = v.pt_obs_off[p + 1];
-  for (int e = e0; e < e1; e++) {
+  for (int e = e0 + gl; e < e1 && run; e += PT_G) {
     const int kf = v.pe_kf[e];
     const int pos = v.dense_mode ? v.pe_wpos[e] : v.pe_pos[e];
     double* W = v.dense_mode ? v.pe_Wl + 18 * (size_t)(pos < 0 ? 0 : pos) : v.P_rec + 27 * (size_t)(pos < 0 ? 0 : pos);
@@ -195,6 +201,16 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_points(BaView v) {
         for (int c = 0; c < 3; c++) W[r * 3 + c] = Jp[r] * JW[c] + Jp[6 + r] * JW[3 + c] + Jp[12 + r] * JW[6 + c];
     }
   }
+#pragma unroll
+  for (int o = PT_G / 2; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) H[k] += __shfl_xor_sync(0xffffffffu, H[k], o);
+#pragma unroll
+    for (int k = 0; k < 3; k++) bl[k] += __shfl_xor_sync(0xffffffffu, bl[k], o);
+    chi += __shfl_xor_sync(0xffffffffu, chi, o);
+    nact += __shfl_xor_sync(0xffffffffu, nact, o);
+  }
+  if (!run || gl != 0) return;
   double* Ho = v.pt_H + 9 * (size_t)p;
 #pragma unroll
   for (int k = 0; k < 6; k++) Ho[k] = H[k];
@@ -207,13 +223,20 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_points(BaView v) {
 // index of (r,c), r<=c, in the packed upper triangle of a 4x4
 __device__ __forceinline__ constexpr int u4(int r, int c) { return r * 4 - (r * (r - 1)) / 2 + (c - r); }
 
+// Lines: LN_G lanes per map line, lane g linearises cells c0 + g, c0 + g + LN_G, ... (a cell = one keyframe's left + right
+// edge, ~1100 FP64 flops each with divisions and a square root: one thread per line is a 10-evaluation latency chain);
+// H_ll, b_l, chi2 and the active count are then summed over the group by a fixed xor-butterfly (deterministic).
+// (LN_G = 8 below ~8k lines, where one lane per line leaves the SMs idle; 1 for large batches, where the extra lanes only cost)
+template <int LN_G>
 __global__ void __launch_bounds__(LM_TPB) k_lin_lines(BaView v) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= v.n_ln) return;
-  const int w = v.ln_win[l];
-  if (v.w_phase[w] != PH_LIN) return;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = gt / LN_G, gl = gt - l * LN_G;
+  const bool live = l < v.n_ln;
+  const int lc = live ? l : v.n_ln - 1;      // dead lanes shadow the last line (no stores) so that shuffles stay full-warp
+  const int w = v.ln_win[lc];
+  const bool run = live && v.w_phase[w] == PH_LIN;
   const int sel = v.w_sel[w];
-  const double* stp = v.ln_st[sel] + 5 * (size_t)l;
+  const double* stp = v.ln_st[sel] + 5 * (size_t)lc;
   const double st[5] = {stp[0], stp[1], stp[2], stp[3], stp[4]};
   double r1[3], r2[3], X1[3], X2[3];
   line_axes(st, r1, r2);
@@ -227,9 +250,9 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_lines(BaView v) {
   for (int k = 0; k < 10; k++) H[k] = 0;
   double chi = 0;
   int nact = 0;
-  const bool removed = v.ln_removed[l] != 0;
-  const int c0 = v.ln_obs_off[l], c1 = v.ln_obs_off[l + 1];
-  for (int c = c0; c < c1; c++) {
+  const bool removed = v.ln_removed[lc] != 0;
+  const int c0 = v.ln_obs_off[lc], c1 = v.ln_obs_off[lc + 1];
+  for (int c = c0 + gl; c < c1 && run; c += LN_G) {
     const int kf = v.lc_kf[c];
     const int pos = v.dense_mode ? v.lc_wpos[c] : v.lc_pos[c];
     double W[24];
@@ -280,6 +303,17 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_lines(BaView v) {
       for (int k = 0; k < 24; k++) Wo[k] = W[k];
     }
   }
+  // group sum (xor 4, 2, 1 inside the aligned group of LN_G lanes): every lane ends with the line's totals
+#pragma unroll
+  for (int o = LN_G / 2; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 10; k++) H[k] += __shfl_xor_sync(0xffffffffu, H[k], o);
+#pragma unroll
+    for (int k = 0; k < 4; k++) bl[k] += __shfl_xor_sync(0xffffffffu, bl[k], o);
+    chi += __shfl_xor_sync(0xffffffffu, chi, o);
+    nact += __shfl_xor_sync(0xffffffffu, nact, o);
+  }
+  if (!run || gl != 0) return;
   double* Ho = v.ln_H + 14 * (size_t)l;
 #pragma unroll
   for (int k = 0; k < 10; k++) Ho[k] = H[k];
@@ -1603,14 +1637,28 @@ __global__ void __launch_bounds__(512) k_solve(BaView v) {
   if (n > 0) {
     for (int idx = tid; idx < n * n; idx += nt) A[idx] = 0.0;
     __syncthreads();
-    for (int a = 0; a < nf; a++) {
-      const int g = g0 + a;
-      const int nb0 = v.nb_off[g], nnb = v.nb_off[g + 1] - nb0;
-      for (int idx = tid; idx < nnb * 36; idx += nt) {
-        const int j = idx / 36, rc = idx - 36 * j, r = rc / 6, c = rc - 6 * r;
-        const int b = v.nb_g[nb0 + j] - g0;
+    if (v.dense_mode) {
+      // local BA: block row a of the window holds blocks (a, a..nf-1) at nb_off[g0] + a nf - a (a - 1) / 2: one flat sweep,
+      // no per-row dependent loads of the neighbour lists (this kernel is pure latency for a single window)
+      const int base = v.nb_off[g0], nblk = nf * (nf + 1) / 2;
+      for (int idx = tid; idx < nblk * 36; idx += nt) {
+        const int blk = idx / 36, rc = idx - 36 * blk, r = rc / 6, c = rc - 6 * r;
+        int a = 0, off = 0;
+        while (off + (nf - a) <= blk) { off += nf - a; a++; }
+        const int j = blk - off, b = a + j;
         if (j == 0 && c < r) continue;  // diagonal block: keep one triangle
-        A[(size_t)(6 * b + c) * n + (6 * a + r)] = v.S_blk[36 * (size_t)(nb0 + j) + rc];
+        A[(size_t)(6 * b + c) * n + (6 * a + r)] = v.S_blk[36 * (size_t)(base + blk) + rc];
+      }
+    } else {
+      for (int a = 0; a < nf; a++) {
+        const int g = g0 + a;
+        const int nb0 = v.nb_off[g], nnb = v.nb_off[g + 1] - nb0;
+        for (int idx = tid; idx < nnb * 36; idx += nt) {
+          const int j = idx / 36, rc = idx - 36 * j, r = rc / 6, c = rc - 6 * r;
+          const int b = v.nb_g[nb0 + j] - g0;
+          if (j == 0 && c < r) continue;  // diagonal block: keep one triangle
+          A[(size_t)(6 * b + c) * n + (6 * a + r)] = v.S_blk[36 * (size_t)(nb0 + j) + rc];
+        }
       }
     }
     for (int i = tid; i < n; i += nt) rhs[i] = v.g_bs[6 * (size_t)g0 + i];
@@ -1660,24 +1708,24 @@ __global__ void __launch_bounds__(512) k_solve(BaView v) {
 // ------------------------------------------------------------------------------------------------
 // back-substitution + update + error at the trial state (one thread per landmark)
 // ------------------------------------------------------------------------------------------------
+template <int PT_G>
 __global__ void __launch_bounds__(LM_TPB) k_backsub_points(BaView v) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= v.n_pt) return;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pl = gt / PT_G, gl = gt - pl * PT_G;
+  const bool live = pl < v.n_pt;
+  const int p = live ? pl : v.n_pt - 1;
   const int w = v.pt_win[p];
-  if (v.w_phase[w] == PH_DONE) return;
+  const bool run = live && v.w_phase[w] != PH_DONE;
+  if (PT_G == 1 && !run) return;
   const int sel = v.w_sel[w];
   const double* Xo = v.pt_xyz[sel] + 3 * (size_t)p;
   double* Xn = v.pt_xyz[sel ^ 1] + 3 * (size_t)p;
-  if (!v.lm_active[p]) {
-    Xn[0] = Xo[0]; Xn[1] = Xo[1]; Xn[2] = Xo[2];
-    v.lm_chi2[p] = 0.0;
-    v.lm_scale[p] = 0.0;
-    return;
-  }
+  const bool active = v.lm_active[p] != 0;
+  const bool go = run && active;
   const double* Dp = v.dense_mode ? v.pts_D + 10 * (size_t)v.pt_spos[p] : v.pt_D + 9 * (size_t)p;
   double s3[3] = {0, 0, 0};
   const int e0 = v.pt_obs_off[p], e1 = v.pt_obs_off[p + 1];
-  for (int e = e0; e < e1; e++) {
+  for (int e = e0 + gl; e < e1 && go; e += PT_G) {
     if (v.pe_level[e] != 0) continue;
     const int pos = v.dense_mode ? v.pe_wpos[e] : v.pe_pos[e];
     if (pos < 0) continue;
@@ -1689,18 +1737,20 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_points(BaView v) {
       s3[0] += W[3 * r] * x; s3[1] += W[3 * r + 1] * x; s3[2] += W[3 * r + 2] * x;
     }
   }
+#pragma unroll
+  for (int o = PT_G / 2; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 3; k++) s3[k] += __shfl_xor_sync(0xffffffffu, s3[k], o);
   // xl = Dinv (bl - W^T xp) = c - Dinv (W^T xp)
-  double xl[3];
-  xl[0] = Dp[6] - (Dp[0] * s3[0] + Dp[1] * s3[1] + Dp[2] * s3[2]);
-  xl[1] = Dp[7] - (Dp[1] * s3[0] + Dp[3] * s3[1] + Dp[4] * s3[2]);
-  xl[2] = Dp[8] - (Dp[2] * s3[0] + Dp[4] * s3[1] + Dp[5] * s3[2]);
+  double xl[3] = {0, 0, 0};
+  if (active) {
+    xl[0] = Dp[6] - (Dp[0] * s3[0] + Dp[1] * s3[1] + Dp[2] * s3[2]);
+    xl[1] = Dp[7] - (Dp[1] * s3[0] + Dp[3] * s3[1] + Dp[4] * s3[2]);
+    xl[2] = Dp[8] - (Dp[2] * s3[0] + Dp[4] * s3[1] + Dp[5] * s3[2]);
+  }
   const double X[3] = {Xo[0] + xl[0], Xo[1] + xl[1], Xo[2] + xl[2]};
-  Xn[0] = X[0]; Xn[1] = X[1]; Xn[2] = X[2];
-  const double lam = v.w_lambda[w];
-  const double* bl = v.pt_H + 9 * (size_t)p + 6;
-  v.lm_scale[p] = xl[0] * (lam * xl[0] + bl[0]) + xl[1] * (lam * xl[1] + bl[1]) + xl[2] * (lam * xl[2] + bl[2]);
   double chi = 0;
-  for (int e = e0; e < e1; e++) {
+  for (int e = e0 + gl; e < e1 && go; e += PT_G) {
     if (v.pe_level[e] != 0) continue;
     const int kf = v.pe_kf[e];
     const double* Rt = v.pose_Rt[sel ^ 1] + 12 * (size_t)kf;
@@ -1715,29 +1765,40 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_points(BaView v) {
     double wgt;
     chi += v.prm.robust_pt ? huber(c2, stereo ? v.prm.delta_pt_stereo : v.prm.delta_pt_mono, &wgt) : c2;
   }
+#pragma unroll
+  for (int o = PT_G / 2; o > 0; o >>= 1) chi += __shfl_xor_sync(0xffffffffu, chi, o);
+  if (!run || gl != 0) return;
+  if (!active) {
+    Xn[0] = Xo[0]; Xn[1] = Xo[1]; Xn[2] = Xo[2];
+    v.lm_chi2[p] = 0.0;
+    v.lm_scale[p] = 0.0;
+    return;
+  }
+  Xn[0] = X[0]; Xn[1] = X[1]; Xn[2] = X[2];
+  const double lam = v.w_lambda[w];
+  const double* bl = v.pt_H + 9 * (size_t)p + 6;
+  v.lm_scale[p] = xl[0] * (lam * xl[0] + bl[0]) + xl[1] * (lam * xl[1] + bl[1]) + xl[2] * (lam * xl[2] + bl[2]);
   v.lm_chi2[p] = chi;
 }
 
+template <int LN_G>
 __global__ void __launch_bounds__(LM_TPB) k_backsub_lines(BaView v) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= v.n_ln) return;
-  const int w = v.ln_win[l];
-  if (v.w_phase[w] == PH_DONE) return;
+  // LN_G lanes per line (as k_lin_lines): W^T x_p and the trial residuals are summed over the group in fixed order
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = gt / LN_G, gl = gt - l * LN_G;
+  const bool live = l < v.n_ln;
+  const int lc = live ? l : v.n_ln - 1;
+  const int w = v.ln_win[lc];
+  const bool run = live && v.w_phase[w] != PH_DONE;
   const int sel = v.w_sel[w];
-  const int li = v.n_pt + l;
-  const double* so = v.ln_st[sel] + 5 * (size_t)l;
-  double* sn = v.ln_st[sel ^ 1] + 5 * (size_t)l;
-  if (!v.lm_active[li]) {
-#pragma unroll
-    for (int k = 0; k < 5; k++) sn[k] = so[k];
-    v.lm_chi2[li] = 0.0;
-    v.lm_scale[li] = 0.0;
-    return;
-  }
-  const double* Dp = v.dense_mode ? v.lns_D + 14 * (size_t)v.ln_spos[l] : v.ln_D + 14 * (size_t)l;
+  const int li = v.n_pt + lc;
+  const double* so = v.ln_st[sel] + 5 * (size_t)lc;
+  double* sn = v.ln_st[sel ^ 1] + 5 * (size_t)lc;
+  const bool active = v.lm_active[li] != 0;
+  const double* Dp = v.dense_mode ? v.lns_D + 14 * (size_t)v.ln_spos[lc] : v.ln_D + 14 * (size_t)lc;
   double s4[4] = {0, 0, 0, 0};
-  const int c0 = v.ln_obs_off[l], c1 = v.ln_obs_off[l + 1];
-  for (int c = c0; c < c1; c++) {
+  const int c0 = v.ln_obs_off[lc], c1 = v.ln_obs_off[lc + 1];
+  for (int c = c0 + gl; c < c1 && run && active; c += LN_G) {
     const int pos = v.dense_mode ? v.lc_wpos[c] : v.lc_pos[c];
     if (pos < 0) continue;
     const double* W = v.dense_mode ? v.lc_Wl + 24 * (size_t)pos : v.L_rec + 38 * (size_t)pos;
@@ -1748,23 +1809,23 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_lines(BaView v) {
       s4[0] += W[4 * r] * x; s4[1] += W[4 * r + 1] * x; s4[2] += W[4 * r + 2] * x; s4[3] += W[4 * r + 3] * x;
     }
   }
-  double xl[4];
 #pragma unroll
-  for (int r = 0; r < 4; r++) {
-    double zz = 0;
+  for (int o = LN_G / 2; o > 0; o >>= 1)
 #pragma unroll
-    for (int k = 0; k < 4; k++) zz += Dp[r <= k ? u4(r, k) : u4(k, r)] * s4[k];
-    xl[r] = Dp[10 + r] - zz;
+    for (int k = 0; k < 4; k++) s4[k] += __shfl_xor_sync(0xffffffffu, s4[k], o);
+  double xl[4] = {0, 0, 0, 0};
+  double st[5] = {so[0], so[1], so[2], so[3], so[4]};
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      double zz = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) zz += Dp[r <= k ? u4(r, k) : u4(k, r)] * s4[k];
+      xl[r] = Dp[10 + r] - zz;
+    }
+    const double st0[5] = {so[0], so[1], so[2], so[3], so[4]};
+    line_oplus(st0, xl, st);
   }
-  const double st0[5] = {so[0], so[1], so[2], so[3], so[4]};
-  double st[5];
-  line_oplus(st0, xl, st);
-#pragma unroll
-  for (int k = 0; k < 5; k++) sn[k] = st[k];
-  const double lam = v.w_lambda[w];
-  const double* bl = v.ln_H + 14 * (size_t)l + 10;
-  v.lm_scale[li] = xl[0] * (lam * xl[0] + bl[0]) + xl[1] * (lam * xl[1] + bl[1]) + xl[2] * (lam * xl[2] + bl[2]) +
-                   xl[3] * (lam * xl[3] + bl[3]);
   double r1[3], r2[3], X1[3], X2[3];
   line_axes(st, r1, r2);
 #pragma unroll
@@ -1773,7 +1834,7 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_lines(BaView v) {
     X2[i] = X1[i] + r1[i];
   }
   double chi = 0;
-  for (int c = c0; c < c1; c++) {
+  for (int c = c0 + gl; c < c1 && run && active; c += LN_G) {
     const uint8_t lv0 = v.lc_level[2 * c], lv1 = v.lc_level[2 * c + 1];
     if (lv0 != 0 && lv1 != 0) continue;
     const int kf = v.lc_kf[c];
@@ -1797,6 +1858,22 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_lines(BaView v) {
       chi += v.prm.robust_ln ? huber(c2, delta, &wgt) : c2;
     }
   }
+#pragma unroll
+  for (int o = LN_G / 2; o > 0; o >>= 1) chi += __shfl_xor_sync(0xffffffffu, chi, o);
+  if (!run || gl != 0) return;
+  if (!active) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) sn[k] = so[k];
+    v.lm_chi2[li] = 0.0;
+    v.lm_scale[li] = 0.0;
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < 5; k++) sn[k] = st[k];
+  const double lam = v.w_lambda[w];
+  const double* bl = v.ln_H + 14 * (size_t)l + 10;
+  v.lm_scale[li] = xl[0] * (lam * xl[0] + bl[0]) + xl[1] * (lam * xl[1] + bl[1]) + xl[2] * (lam * xl[2] + bl[2]) +
+                   xl[3] * (lam * xl[3] + bl[3]);
   v.lm_chi2[li] = chi;
 }
 
