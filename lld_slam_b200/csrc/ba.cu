@@ -534,6 +534,9 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     slots(n_pt, p->pt_off, p->pt_obs_off, pe_kf, pt_order, pt_key, pt_spos, pts_mask, pts_w0, pe_wpos);
     slots(n_ln, p->ln_off, p->ln_obs_off, lc_kf, ln_order, ln_key, ln_spos, lns_mask, lns_w0, lc_wpos);
     n_pw = (size_t)pts_w0[n_pt]; n_lw = (size_t)lns_w0[n_ln];
+    static const bool schur_tile_env = getenv("LLD_SCHUR_TILE") ? atoi(getenv("LLD_SCHUR_TILE")) != 0 : true;
+    const bool schur_tile = schur_tile_env;
+    v.schur_tile = schur_tile ? 1 : 0;
     int PIECE_CAP = 128;  // shorter pieces when the batch is small, so that every SM gets warps
     while (PIECE_CAP > 8 && (long long)(n_pt + n_ln) * 5 / (2 * PIECE_CAP) < 16LL * c->sm_count) PIECE_CAP >>= 1;
     // pieces / items / gather entries: built per (kind, window) with local offsets, merged in order afterwards
@@ -565,7 +568,11 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
           for (int ia = 0; ia < n; ia++)
             for (int ib = ia; ib < n; ib++, pr++) J.gb.push_back({nb_off[g0 + hl[ia]] + (hl[ib] - hl[ia]), J.dsize + 36LL * pr});
           for (int ia = 0; ia < n; ia++) J.gv.push_back({g0 + hl[ia], J.dsize + 6LL * (6 * npair + ia)});
-          for (int t0 = 0; t0 < ntask; t0 += 32) { J.itp.push_back(pc); J.itt.push_back(t0); }
+          if (schur_tile) {
+            for (int t0 = 0; t0 < 2 * npair + n; t0 += SP_TPB) { J.itp.push_back(pc); J.itt.push_back(t0); }
+          } else {
+            for (int t0 = 0; t0 < ntask; t0 += 32) { J.itp.push_back(pc); J.itt.push_back(t0); }
+          }
           J.dsize += 6LL * ntask;
         }
         b = e;
@@ -968,9 +975,11 @@ static int ba_step_forked(LldCtx* c, int round, int stop_now) {
   LLD_CUDA(c, cudaEventRecord(c->ev_fork, s0));
   LLD_CUDA(c, fork(s1));
   if (v.n_pt) LLD_LAUNCH_S(c, s0, k_schur_points, gp, LM_TPB, 0, v);
-  if (nip) LLD_LAUNCH_S(c, s0, k_schur_piece<3>, cdiv(nip, 8), 256, 0, v, 0, nip);
+  if (nip && v.schur_tile) LLD_LAUNCH_S(c, s0, k_schur_tile<3>, nip, SP_TPB, SP_CAPD * sizeof(double), v, 0);
+  else if (nip) LLD_LAUNCH_S(c, s0, k_schur_piece<3>, cdiv(nip, 8), 256, 0, v, 0, nip);
   if (v.n_ln) LLD_LAUNCH_S(c, s1, k_schur_lines, gl, LM_TPB, 0, v);
-  if (nil) LLD_LAUNCH_S(c, s1, k_schur_piece<4>, cdiv(nil, 8), 256, 0, v, nip, nil);
+  if (nil && v.schur_tile) LLD_LAUNCH_S(c, s1, k_schur_tile<4>, nil, SP_TPB, SP_CAPD * sizeof(double), v, nip);
+  else if (nil) LLD_LAUNCH_S(c, s1, k_schur_piece<4>, cdiv(nil, 8), 256, 0, v, nip, nil);
   LLD_CUDA(c, join(0));
   const int nblk = (int)S->n_nb_total;
   LLD_LAUNCH_S(c, s0, k_reduce_piece, cdiv(nblk * 6 + v.n_free_total, 8), 256, 0, v, nblk);
@@ -1013,8 +1022,10 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   if (v.n_ln) LLD_LAUNCH(c, k_schur_lines, gl, LM_TPB, 0, v);
   if (v.dense_mode) {
     const int nip = v.n_items_pt, nil = v.n_items - v.n_items_pt;
-    if (nip) LLD_LAUNCH(c, k_schur_piece<3>, cdiv(nip, 8), 256, 0, v, 0, nip);
-    if (nil) LLD_LAUNCH(c, k_schur_piece<4>, cdiv(nil, 8), 256, 0, v, nip, nil);
+    if (nip && v.schur_tile) LLD_LAUNCH(c, k_schur_tile<3>, nip, SP_TPB, SP_CAPD * sizeof(double), v, 0);
+    else if (nip) LLD_LAUNCH(c, k_schur_piece<3>, cdiv(nip, 8), 256, 0, v, 0, nip);
+    if (nil && v.schur_tile) LLD_LAUNCH(c, k_schur_tile<4>, nil, SP_TPB, SP_CAPD * sizeof(double), v, nip);
+    else if (nil) LLD_LAUNCH(c, k_schur_piece<4>, cdiv(nil, 8), 256, 0, v, nip, nil);
     const int nblk = (int)S->n_nb_total;
     LLD_LAUNCH(c, k_reduce_piece, cdiv(nblk * 6 + v.n_free_total, 8), 256, 0, v, nblk);
   } else {

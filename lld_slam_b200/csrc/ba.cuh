@@ -181,6 +181,7 @@ struct BaView {
   double* band_A;             // [n_free_total][(band_B+1)*36 + 8] band rows in the solver's order (k_band_assemble)
   double* band_L;             // [n_free_total][(band_B+1)][36] column panels: block 0 = L_kk (strict lower) + D (diagonal)
   double* band_z;             // [6 * n_free_total] forward-substituted rhs
+  int schur_tile;             // dense mode: items are (piece, block of SP_TPB half-tile tasks) for k_schur_tile (1) or (piece, 32 column tasks) for k_schur_piece (0)
   int debug;                  // LLD_BAND_DEBUG: the band solver prints its phase cycle counts
   BaParams prm;
 };

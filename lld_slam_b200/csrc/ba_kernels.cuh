@@ -911,6 +911,160 @@ __global__ void __launch_bounds__(256) k_schur_piece(BaView v, int item_base, in
   for (int r = 0; r < 6; r++) out[r] = acc[r];
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_schur_tile: the same sums as k_schur_piece, staged through shared memory.  One CTA = (piece, block of <= SP_TPB
+// tasks); a task is half of a pair's 6x6 block (6 rows x 3 columns) or one b_schur vector.  Per chunk of landmarks the
+// CTA copies the piece's contiguous W blocks and inverse records with cp.async (every byte read once, coalesced),
+// forms Z_(l,b) = W_(l,b) Dinv_l once per (landmark, keyframe) in shared memory (plus a pseudo block [Dinv_l b_l, 0..] so
+// the b_schur tasks run the same code), and thread (task, slice s) accumulates  W_(l,ia) Z_(l,ib)^T  over the
+// landmarks l = s, s + S, ... of the chunk: 18 + 3 D shared loads per 18 D FMAs, no global loads in the loop.
+// The slices are summed in fixed order through shared memory; outputs land in the scratch slots k_reduce_piece gathers.
+// ------------------------------------------------------------------------------------------------
+constexpr int SP_TPB = 128;
+constexpr int SP_CAPD = 5120;  // doubles of dynamic shared memory per CTA (40 KB: 4-5 CTAs per SM)
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(src));
+}
+
+template <int D>
+__global__ void __launch_bounds__(SP_TPB, 4) k_schur_tile(BaView v, int item_base) {
+  constexpr int WS = 6 * D;
+  constexpr int DS = D == 3 ? 10 : 14;
+  constexpr int OFF_C = D * (D + 1) / 2;
+  extern __shared__ __align__(16) double sp_smem[];
+  const int item = item_base + blockIdx.x;
+  const int tid = threadIdx.x;
+  const int pc = v.it_piece[item];
+  const int l0 = v.pc_begin[pc], nl = v.pc_end[pc] - l0;
+  const int w = (D == 3 ? v.pt_win : v.ln_win)[(D == 3 ? v.pt_sorted : v.ln_sorted)[l0]];
+  if (v.w_phase[w] == PH_DONE) return;
+  const int n = v.pc_n[pc];
+  const int npair = n * (n + 1) / 2, ntask = 2 * npair + n;
+  const int t0 = v.it_task0[item];
+  const int ntb = min(SP_TPB, ntask - t0);
+  const int S = SP_TPB / ntb;
+  const int s = tid / ntb, tl = tid - s * ntb;
+  const bool act = s < S;
+  int ia = 0, zb = n, h = 0;
+  {
+    const int task = t0 + tl;
+    if (task < 2 * npair) {
+      int pr = task >> 1;
+      h = task & 1;
+      while (pr >= n - ia) { pr -= n - ia; ia++; }
+      zb = ia + pr;
+    } else {
+      ia = task - 2 * npair;
+    }
+  }
+  const int rowW = n * WS, rowZ = (n + 1) * WS;
+  const int Lc = min(nl, SP_CAPD / (rowW + rowZ + DS));
+  double* sW = sp_smem;
+  double* sZ = sW + Lc * rowW;
+  double* sD = sZ + Lc * rowZ;
+  const double* Wg = (D == 3 ? v.pe_Wl : v.lc_Wl) + (size_t)(D == 3 ? v.pts_w0 : v.lns_w0)[l0] * WS;
+  const double* Dg = (D == 3 ? v.pts_D : v.lns_D) + (size_t)l0 * DS;
+  double acc[18];
+#pragma unroll
+  for (int q = 0; q < 18; q++) acc[q] = 0.0;
+  for (int lc0 = 0; lc0 < nl; lc0 += Lc) {
+    const int m = min(Lc, nl - lc0);
+    {
+      const double* gW = Wg + (size_t)lc0 * rowW;
+      const int nW = m * rowW / 2;
+      for (int i = tid; i < nW; i += SP_TPB) cp_async16(sW + 2 * i, gW + 2 * i);
+      const double* gD = Dg + (size_t)lc0 * DS;
+      const int nD = m * DS / 2;
+      for (int i = tid; i < nD; i += SP_TPB) cp_async16(sD + 2 * i, gD + 2 * i);
+      asm volatile("cp.async.commit_group;\n" ::);
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }
+    __syncthreads();
+    for (int i = tid; i < m * (n + 1); i += SP_TPB) {
+      const int l = i / (n + 1), b = i - l * (n + 1);
+      const double* Dv = sD + l * DS;
+      double* z = sZ + l * rowZ + b * WS;
+      if (b < n) {
+        const double* wv = sW + l * rowW + b * WS;
+        double dm[D][D];
+#pragma unroll
+        for (int k = 0; k < D; k++)
+#pragma unroll
+          for (int j = 0; j < D; j++) {
+            const int r = k < j ? k : j, c2 = k < j ? j : k;
+            dm[k][j] = Dv[r * D - (r * (r - 1)) / 2 + (c2 - r)];
+          }
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          double wb[D];
+#pragma unroll
+          for (int j = 0; j < D; j++) wb[j] = wv[c * D + j];
+#pragma unroll
+          for (int k = 0; k < D; k++) {
+            double zz = 0;
+#pragma unroll
+            for (int j = 0; j < D; j++) zz += dm[k][j] * wb[j];
+            z[c * D + k] = zz;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < WS; k++) z[k] = k < D ? Dv[OFF_C + k] : 0.0;
+      }
+    }
+    __syncthreads();
+    if (act) {
+      const double* wa_p = sW + ia * WS;
+      const double* z_p = sZ + zb * WS + h * 3 * D;
+#pragma unroll 2
+      for (int l = s; l < m; l += S) {
+        double wa[WS];
+        const double* wp = wa_p + l * rowW;
+#pragma unroll
+        for (int k = 0; k < WS; k += 2) {
+          const double2 t2 = *reinterpret_cast<const double2*>(wp + k);
+          wa[k] = t2.x; wa[k + 1] = t2.y;
+        }
+        const double* zp = z_p + l * rowZ;
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++) {
+          double z[D];
+#pragma unroll
+          for (int k = 0; k < D; k++) z[k] = zp[cc * D + k];
+#pragma unroll
+          for (int r = 0; r < 6; r++) {
+            double a2 = acc[cc * 6 + r];
+#pragma unroll
+            for (int k = 0; k < D; k++) a2 += wa[D * r + k] * z[k];
+            acc[cc * 6 + r] = a2;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // slices summed in fixed order
+  double* red = sp_smem;
+  if (act)
+#pragma unroll
+    for (int q = 0; q < 18; q++) red[(s * ntb + tl) * 18 + q] = acc[q];
+  __syncthreads();
+  double* out = v.dpart + v.pc_out[pc];
+  for (int e = tid; e < ntb * 18; e += SP_TPB) {
+    const int tl2 = e / 18, q = e - 18 * tl2;
+    const int task = t0 + tl2;
+    size_t o;
+    if (task < 2 * npair) o = (size_t)(task >> 1) * 36 + (task & 1) * 18 + q;
+    else if (q < 6) o = (size_t)36 * npair + (size_t)(task - 2 * npair) * 6 + q;
+    else continue;
+    double sum = 0;
+    for (int s2 = 0; s2 < S; s2++) sum += red[(s2 * ntb + tl2) * 18 + q];
+    out[o] = sum;
+  }
+}
+
 // S(a,b) = [a==b] (Hpp_a + lambda I) - sum over contributing (piece, pair) ; bschur_a = bp_a - sum b tasks
 // one warp per (block, column c) and per free keyframe: lanes stride over the gather list, fixed-order shuffle tree
 __global__ void __launch_bounds__(256) k_reduce_piece(BaView v, int n_blocks) {
