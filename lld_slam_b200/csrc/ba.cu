@@ -118,6 +118,8 @@ struct BaHost {
   pvec<int> pt_spos, ln_spos, pts_w0, lns_w0, pe_wpos, lc_wpos;
   pvec<uint32_t> pts_mask, lns_mask;
   pvec<int> it_piece, it_task0, pc_begin, pc_end, pc_n, gb_off, gv_off;
+  pvec<SchurItem> it_rec, it_tmp;
+  std::vector<uint64_t> it_keys;
   pvec<long long> pc_out, gb_src, gv_src;
   std::vector<BaDenseJob> jobs;
   pvec<int> ch_g, ch_begin, ch_end, ch_seg0, seg_begin, seg_end, g_chp0, g_chl0;
@@ -589,7 +591,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     dpart_total = jd[n_jobs];
     n_items_pt = ji[std::min<size_t>((size_t)nw, n_jobs)];
     pc_begin.resize(jp[n_jobs]); pc_end.resize(jp[n_jobs]); pc_n.resize(jp[n_jobs]); pc_out.resize(jp[n_jobs]);
-    it_piece.resize(ji[n_jobs]); it_task0.resize(ji[n_jobs]);
+    it_piece.resize(ji[n_jobs]); it_task0.resize(ji[n_jobs]); H.it_rec.resize(std::max(ji[n_jobs], 1));
     gb_off.assign(nb_g.size() + 1, 0);
     gv_off.assign(nG + 1, 0);
     par_for((int)n_jobs, [&](int jid) {
@@ -598,8 +600,41 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
       for (size_t k = 0; k < J.pb.size(); k++) {
         pc_begin[pbase + k] = J.pb[k]; pc_end[pbase + k] = J.pe[k]; pc_n[pbase + k] = J.pn[k]; pc_out[pbase + k] = J.pout[k] + jd[jid];
       }
-      for (size_t k = 0; k < J.itp.size(); k++) { it_piece[ibase + k] = J.itp[k] + pbase; it_task0[ibase + k] = J.itt[k]; }
+      const int kind = jid / nw, jw = jid % nw;
+      for (size_t k = 0; k < J.itp.size(); k++) {
+        it_piece[ibase + k] = J.itp[k] + pbase; it_task0[ibase + k] = J.itt[k];
+        const int q = J.itp[k];
+        SchurItem& R = H.it_rec[ibase + k];
+        R.l0 = J.pb[q]; R.nl = J.pe[q] - J.pb[q]; R.n = J.pn[q]; R.t0 = J.itt[k];
+        R.w = jw; R.w0 = (kind == 0 ? pts_w0 : lns_w0)[J.pb[q]]; R.out = J.pout[q] + jd[jid];
+        schur_item_shape(kind == 0 ? 3 : 4, R.n, R.nl, R.t0, &R.lc, &R.S, &R.nchunk);
+      }
     });
+    if (schur_tile) {
+      // k_schur_tile's CTAs take items b, b + G, ... : order each kind by decreasing cost and deal the rows in snake
+      // order, so that every CTA gets about the same landmark x task volume
+      auto& tmp = H.it_tmp; auto& keys = H.it_keys;
+      tmp.resize(H.it_rec.size()); keys.resize(H.it_rec.size());
+      par_for(2, [&](int kind) {
+        const int i0 = kind == 0 ? 0 : n_items_pt, i1 = kind == 0 ? n_items_pt : ji[n_jobs];
+        const int cntk = i1 - i0;
+        if (cntk <= 0) return;
+        const int G = std::min(cntk, 4 * c->sm_count);
+        for (int i = i0; i < i1; i++) {
+          const SchurItem& R = H.it_rec[i];
+          const int ntask = R.n * (R.n + 1) + R.n;
+          const uint64_t cost = 64 + (uint64_t)R.nl * (uint64_t)(std::min(ntask - R.t0, (int)SP_TPB) + R.n + 1);
+          keys[i] = ((~cost) << 24) | (uint64_t)(i - i0);   // ascending key = descending cost, ties by index
+          tmp[i] = R;
+        }
+        std::sort(keys.begin() + i0, keys.begin() + i1);
+        for (int k = 0; k < cntk; k++) {
+          const int r = k / G, j = k - r * G, len = std::min(G, cntk - r * G);
+          const int pos = (r & 1) ? len - 1 - j : j;
+          H.it_rec[i0 + r * G + pos] = tmp[i0 + (int)(keys[i0 + k] & 0xffffffu)];
+        }
+      });
+    }
     // a block / keyframe belongs to one window: its contributions come from that window's point job, then its line job
     par_for(nw, [&](int w) {
       for (int kind = 0; kind < 2; kind++) {
@@ -773,6 +808,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   UP(tmp_i, ln_order.data(), n_ln); v.ln_sorted = tmp_i;
   UP(tmp_i, it_piece.data(), it_piece.size()); v.it_piece = tmp_i;
   UP(tmp_i, it_task0.data(), it_task0.size()); v.it_task0 = tmp_i;
+  { SchurItem* tmp_r; UP(tmp_r, H.it_rec.data(), it_piece.size()); v.it_rec = tmp_r; }
   UP(tmp_i, pc_begin.data(), pc_begin.size()); v.pc_begin = tmp_i;
   UP(tmp_i, pc_end.data(), pc_end.size()); v.pc_end = tmp_i;
   UP(tmp_i, pc_n.data(), pc_n.size()); v.pc_n = tmp_i;
@@ -864,6 +900,10 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     S->use_graph = allow && dense_single;
   }
   // dynamic shared memory opt-in of the solvers (once per upload, outside any stream capture)
+  if (v.dense_mode) {
+    LLD_CUDA(c, lld_raise_dyn_smem(k_schur_tile<3>, (size_t)SP_SMEM_BYTES));
+    LLD_CUDA(c, lld_raise_dyn_smem(k_schur_tile<4>, (size_t)SP_SMEM_BYTES));
+  }
   if (v.env_mode && S->use_band) LLD_CUDA(c, lld_raise_dyn_smem(k_solve_band<512>, (size_t)(int)S->band_smem) != cudaSuccess ? cudaErrorInvalidValue : lld_raise_dyn_smem(k_solve_band<1024>, (size_t)(int)S->band_smem));
   else if (v.env_mode) LLD_CUDA(c, lld_raise_dyn_smem(k_solve_env, (size_t)(int)S->env_smem));
   else if (S->max_n <= SMEM_SOLVE_MAX_N)
@@ -975,10 +1015,10 @@ static int ba_step_forked(LldCtx* c, int round, int stop_now) {
   LLD_CUDA(c, cudaEventRecord(c->ev_fork, s0));
   LLD_CUDA(c, fork(s1));
   if (v.n_pt) LLD_LAUNCH_S(c, s0, k_schur_points, gp, LM_TPB, 0, v);
-  if (nip && v.schur_tile) LLD_LAUNCH_S(c, s0, k_schur_tile<3>, nip, SP_TPB, SP_CAPD * sizeof(double), v, 0);
+  if (nip && v.schur_tile) LLD_LAUNCH_S(c, s0, k_schur_tile<3>, std::min(nip, 4 * c->sm_count), SP_TPB, SP_SMEM_BYTES, v, 0, nip);
   else if (nip) LLD_LAUNCH_S(c, s0, k_schur_piece<3>, cdiv(nip, 8), 256, 0, v, 0, nip);
   if (v.n_ln) LLD_LAUNCH_S(c, s1, k_schur_lines, gl, LM_TPB, 0, v);
-  if (nil && v.schur_tile) LLD_LAUNCH_S(c, s1, k_schur_tile<4>, nil, SP_TPB, SP_CAPD * sizeof(double), v, nip);
+  if (nil && v.schur_tile) LLD_LAUNCH_S(c, s1, k_schur_tile<4>, std::min(nil, 4 * c->sm_count), SP_TPB, SP_SMEM_BYTES, v, nip, nil);
   else if (nil) LLD_LAUNCH_S(c, s1, k_schur_piece<4>, cdiv(nil, 8), 256, 0, v, nip, nil);
   LLD_CUDA(c, join(0));
   const int nblk = (int)S->n_nb_total;
@@ -1022,9 +1062,9 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   if (v.n_ln) LLD_LAUNCH(c, k_schur_lines, gl, LM_TPB, 0, v);
   if (v.dense_mode) {
     const int nip = v.n_items_pt, nil = v.n_items - v.n_items_pt;
-    if (nip && v.schur_tile) LLD_LAUNCH(c, k_schur_tile<3>, nip, SP_TPB, SP_CAPD * sizeof(double), v, 0);
+    if (nip && v.schur_tile) LLD_LAUNCH(c, k_schur_tile<3>, std::min(nip, 4 * c->sm_count), SP_TPB, SP_SMEM_BYTES, v, 0, nip);
     else if (nip) LLD_LAUNCH(c, k_schur_piece<3>, cdiv(nip, 8), 256, 0, v, 0, nip);
-    if (nil && v.schur_tile) LLD_LAUNCH(c, k_schur_tile<4>, nil, SP_TPB, SP_CAPD * sizeof(double), v, nip);
+    if (nil && v.schur_tile) LLD_LAUNCH(c, k_schur_tile<4>, std::min(nil, 4 * c->sm_count), SP_TPB, SP_SMEM_BYTES, v, nip, nil);
     else if (nil) LLD_LAUNCH(c, k_schur_piece<4>, cdiv(nil, 8), 256, 0, v, nip, nil);
     const int nblk = (int)S->n_nb_total;
     LLD_LAUNCH(c, k_reduce_piece, cdiv(nblk * 6 + v.n_free_total, 8), 256, 0, v, nblk);

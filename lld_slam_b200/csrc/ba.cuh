@@ -23,6 +23,15 @@ struct BaParams {
   int ln_filter;
 };
 
+// one work item of k_schur_tile: a block of tasks of one piece, with everything the kernel needs in three 16-byte loads
+struct __align__(16) SchurItem {
+  int l0, nl, n, t0;   // first landmark (sorted position), landmarks, free keyframes per landmark, first task
+  int w, lc;           // window, landmarks per shared-memory chunk
+  long long w0;        // first W block of the piece
+  long long out;       // scratch offset of the piece's outputs
+  int S, nchunk;       // landmark slices per task, chunks of the piece
+};
+
 struct BaView {
   int n_win, n_kf, n_pt, n_ln, n_pe, n_lc;
   int n_free_total;  // sum of free poses over the batch
@@ -88,6 +97,7 @@ struct BaView {
   // its tasks are (pair of its keyframes, column c) plus one b_schur task per keyframe; 32 tasks = one warp item
   int n_items;             // warp work items (points first, then lines)
   int n_items_pt;
+  const SchurItem* it_rec; // [n_items] self-contained item records (k_schur_tile)
   const int* it_piece;     // [n_items] piece of the item
   const int* it_task0;     // [n_items] first task of the item
   const int* pc_begin;     // [n_pieces] first landmark (sorted position)

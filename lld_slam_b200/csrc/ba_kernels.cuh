@@ -912,156 +912,250 @@ __global__ void __launch_bounds__(256) k_schur_piece(BaView v, int item_base, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_schur_tile: the same sums as k_schur_piece, staged through shared memory.  One CTA = (piece, block of <= SP_TPB
-// tasks); a task is half of a pair's 6x6 block (6 rows x 3 columns) or one b_schur vector.  Per chunk of landmarks the
-// CTA copies the piece's contiguous W blocks and inverse records with cp.async (every byte read once, coalesced),
-// forms Z_(l,b) = W_(l,b) Dinv_l once per (landmark, keyframe) in shared memory (plus a pseudo block [Dinv_l b_l, 0..] so
-// the b_schur tasks run the same code), and thread (task, slice s) accumulates  W_(l,ia) Z_(l,ib)^T  over the
-// landmarks l = s, s + S, ... of the chunk: 18 + 3 D shared loads per 18 D FMAs, no global loads in the loop.
-// The slices are summed in fixed order through shared memory; outputs land in the scratch slots k_reduce_piece gathers.
+// k_schur_tile: the sums of k_schur_piece, staged through shared memory by persistent CTAs.
+// An item = (piece, block of <= SP_TPB tasks); a task is half of a pair's 6x6 block (6 rows x 3 columns) or one b_schur
+// vector.  Every CTA walks its items (blockIdx.x, + gridDim.x, ...; windows that are done are skipped 32 items at a
+// time) as one stream of landmark chunks: while chunk i is computed, chunk i + 1 (of the same or of the next item) is
+// already in flight (cp.async, two buffers), so the DRAM latency is paid once per CTA, not once per piece.  Per chunk:
+// the piece's contiguous W blocks and inverse records land in shared memory (every byte read once, coalesced),
+// Z_(l,b) = W_(l,b) Dinv_l is formed once per (landmark, keyframe) (plus a pseudo block [Dinv_l b_l, 0..], so that the
+// b_schur tasks run the same code), and thread (task, slice s) accumulates W_(l,ia) Z_(l,ib)^T over the landmarks
+// l = s, s + S, ... : 18 + 3 D shared loads per 18 D FMAs, no global loads in the loop.  Slices are summed in fixed
+// order through shared memory; outputs land in the scratch slots k_reduce_piece gathers.
 // ------------------------------------------------------------------------------------------------
 constexpr int SP_TPB = 128;
-constexpr int SP_CAPD = 5120;  // doubles of dynamic shared memory per CTA (40 KB: 4-5 CTAs per SM)
+constexpr int SP_CAP_WD = 2304;  // doubles per W + inverse-record buffer (two of them)
+constexpr int SP_CAP_Z = 2560;   // doubles of the Z buffer (>= SP_TPB * 18: it also carries the slice sums)
+constexpr int SP_SMEM_BYTES = (2 * SP_CAP_WD + SP_CAP_Z) * 8;
+constexpr int SP_MAX_S = 16;
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(dst_smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(src));
 }
 
+// host side: chunk length / slices of an item (D = 3 points, 4 lines)
+inline void schur_item_shape(int D, int n, int nl, int t0, int* lc, int* S, int* nchunk) {
+  const int WS = 6 * D, DS = D == 3 ? 10 : 14;
+  const int ntask = n * (n + 1) + n;
+  int ntb = ntask - t0 < SP_TPB ? ntask - t0 : SP_TPB;
+  if (ntb < 1) ntb = 1;
+  int L = SP_CAP_WD / (n * WS + DS);
+  const int Lz = SP_CAP_Z / ((n + 1) * WS);
+  if (Lz < L) L = Lz;
+  if (nl < L) L = nl;
+  int s = SP_TPB / ntb;
+  if (s > SP_MAX_S) s = SP_MAX_S;
+  if (s > L / 2) s = L / 2;
+  if (s < 1) s = 1;
+  *lc = L; *S = s; *nchunk = (nl + L - 1) / L;
+}
+
 template <int D>
-__global__ void __launch_bounds__(SP_TPB, 4) k_schur_tile(BaView v, int item_base) {
+__global__ void __launch_bounds__(SP_TPB, 4) k_schur_tile(BaView v, int item_base, int n_items) {
   constexpr int WS = 6 * D;
   constexpr int DS = D == 3 ? 10 : 14;
   constexpr int OFF_C = D * (D + 1) / 2;
   extern __shared__ __align__(16) double sp_smem[];
-  const int item = item_base + blockIdx.x;
-  const int tid = threadIdx.x;
-  const int pc = v.it_piece[item];
-  const int l0 = v.pc_begin[pc], nl = v.pc_end[pc] - l0;
-  const int w = (D == 3 ? v.pt_win : v.ln_win)[(D == 3 ? v.pt_sorted : v.ln_sorted)[l0]];
-  if (v.w_phase[w] == PH_DONE) return;
-  const int n = v.pc_n[pc];
-  const int npair = n * (n + 1) / 2, ntask = 2 * npair + n;
-  const int t0 = v.it_task0[item];
-  const int ntb = min(SP_TPB, ntask - t0);
-  const int S = SP_TPB / ntb;
-  const int s = tid / ntb, tl = tid - s * ntb;
-  const bool act = s < S;
-  int ia = 0, zb = n, h = 0;
-  {
-    const int task = t0 + tl;
-    if (task < 2 * npair) {
-      int pr = task >> 1;
-      h = task & 1;
-      while (pr >= n - ia) { pr -= n - ia; ia++; }
-      zb = ia + pr;
-    } else {
-      ia = task - 2 * npair;
+  double* const sZ = sp_smem + 2 * SP_CAP_WD;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int G = gridDim.x;
+  const int cnt = (n_items - (int)blockIdx.x + G - 1) / G;
+  const SchurItem* items = v.it_rec + item_base + blockIdx.x;
+  const double* Wbase = D == 3 ? v.pe_Wl : v.lc_Wl;
+  const double* Dbase = D == 3 ? v.pts_D : v.lns_D;
+
+  // the CTA's items whose window is still running, 32 at a time (every warp evaluates the same ballot)
+  int scan_base = -32;
+  unsigned scan_mask = 0;
+  auto next_item = [&]() -> int {
+    while (true) {
+      if (scan_mask) {
+        const int j = __ffs(scan_mask) - 1;
+        scan_mask &= scan_mask - 1;
+        return scan_base + j;
+      }
+      scan_base += 32;
+      if (scan_base >= cnt) return -1;
+      const int j = scan_base + lane;
+      bool a = false;
+      if (j < cnt) a = v.w_phase[items[(size_t)j * G].w] != PH_DONE;
+      scan_mask = __ballot_sync(0xffffffffu, a);
     }
-  }
-  const int rowW = n * WS, rowZ = (n + 1) * WS;
-  const int Lc = min(nl, SP_CAPD / (rowW + rowZ + DS));
-  double* sW = sp_smem;
-  double* sZ = sW + Lc * rowW;
-  double* sD = sZ + Lc * rowZ;
-  const double* Wg = (D == 3 ? v.pe_Wl : v.lc_Wl) + (size_t)(D == 3 ? v.pts_w0 : v.lns_w0)[l0] * WS;
-  const double* Dg = (D == 3 ? v.pts_D : v.lns_D) + (size_t)l0 * DS;
-  double acc[18];
-#pragma unroll
-  for (int q = 0; q < 18; q++) acc[q] = 0.0;
-  for (int lc0 = 0; lc0 < nl; lc0 += Lc) {
-    const int m = min(Lc, nl - lc0);
+  };
+  auto load_item = [&](int k, SchurItem& R) {
+    const int4* p = reinterpret_cast<const int4*>(items + (size_t)k * G);
+    const int4 a = p[0], b = p[1];
+    R.l0 = a.x; R.nl = a.y; R.n = a.z; R.t0 = a.w;
+    R.w = b.x;
+    R.w0 = ((long long)(unsigned)b.w << 32) | (unsigned)b.z;
+    const int4 c2 = p[2];
+    R.out = ((long long)(unsigned)c2.y << 32) | (unsigned)c2.x;
+    R.lc = b.y; R.S = c2.z; R.nchunk = c2.w;
+  };
+  auto issue = [&](const SchurItem& R, int c, int b) {
+    const int rowW = R.n * WS;
+    const int Lc = R.lc;
+    const int lc0 = c * Lc, m = min(Lc, R.nl - lc0);
+    double* sW = sp_smem + b * SP_CAP_WD;
+    double* sD = sW + Lc * rowW;
+    const double* gW = Wbase + (size_t)R.w0 * WS + (size_t)lc0 * rowW;
+    const int nW = m * rowW / 2;
+    for (int i = tid; i < nW; i += SP_TPB) cp_async16(sW + 2 * i, gW + 2 * i);
+    const double* gD = Dbase + (size_t)(R.l0 + lc0) * DS;
+    const int nD = m * DS / 2;
+    for (int i = tid; i < nD; i += SP_TPB) cp_async16(sD + 2 * i, gD + 2 * i);
+  };
+
+  int cur = next_item();
+  if (cur < 0) return;
+  SchurItem R, Rn;
+  load_item(cur, R);
+  issue(R, 0, 0);
+  asm volatile("cp.async.commit_group;\n" ::);
+  int nxt = next_item();
+  Rn = R;
+  if (nxt >= 0) load_item(nxt, Rn);
+  int buf = 0, c = 0;
+  while (true) {
+    // ---- per item: task of this thread ----
+    const int n = R.n, nl = R.nl;
+    const int npair = n * (n + 1) / 2, ntask = 2 * npair + n;
+    const int ntb = min(SP_TPB, ntask - R.t0);
+    const int rowW = n * WS, rowZ = (n + 1) * WS;
+    const int Lc = R.lc, nchunk = R.nchunk, S = R.S;
+    const int s = tid / ntb, tl = tid - s * ntb;
+    const bool act = s < S;
+    int ia = 0, zb = n, h = 0;
     {
-      const double* gW = Wg + (size_t)lc0 * rowW;
-      const int nW = m * rowW / 2;
-      for (int i = tid; i < nW; i += SP_TPB) cp_async16(sW + 2 * i, gW + 2 * i);
-      const double* gD = Dg + (size_t)lc0 * DS;
-      const int nD = m * DS / 2;
-      for (int i = tid; i < nD; i += SP_TPB) cp_async16(sD + 2 * i, gD + 2 * i);
-      asm volatile("cp.async.commit_group;\n" ::);
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    }
-    __syncthreads();
-    for (int i = tid; i < m * (n + 1); i += SP_TPB) {
-      const int l = i / (n + 1), b = i - l * (n + 1);
-      const double* Dv = sD + l * DS;
-      double* z = sZ + l * rowZ + b * WS;
-      if (b < n) {
-        const double* wv = sW + l * rowW + b * WS;
-        double dm[D][D];
-#pragma unroll
-        for (int k = 0; k < D; k++)
-#pragma unroll
-          for (int j = 0; j < D; j++) {
-            const int r = k < j ? k : j, c2 = k < j ? j : k;
-            dm[k][j] = Dv[r * D - (r * (r - 1)) / 2 + (c2 - r)];
-          }
-#pragma unroll
-        for (int c = 0; c < 6; c++) {
-          double wb[D];
-#pragma unroll
-          for (int j = 0; j < D; j++) wb[j] = wv[c * D + j];
-#pragma unroll
-          for (int k = 0; k < D; k++) {
-            double zz = 0;
-#pragma unroll
-            for (int j = 0; j < D; j++) zz += dm[k][j] * wb[j];
-            z[c * D + k] = zz;
-          }
-        }
+      const int task = R.t0 + tl;
+      if (task < 2 * npair) {
+        int pr = task >> 1;
+        h = task & 1;
+        while (pr >= n - ia) { pr -= n - ia; ia++; }
+        zb = ia + pr;
       } else {
-#pragma unroll
-        for (int k = 0; k < WS; k++) z[k] = k < D ? Dv[OFF_C + k] : 0.0;
+        ia = min(task - 2 * npair, n - 1);
       }
     }
-    __syncthreads();
-    if (act) {
-      const double* wa_p = sW + ia * WS;
-      const double* z_p = sZ + zb * WS + h * 3 * D;
-#pragma unroll 2
-      for (int l = s; l < m; l += S) {
-        double wa[WS];
-        const double* wp = wa_p + l * rowW;
+    // (landmark, block) of this thread's Z blocks: start and stride of tid + k SP_TPB in base n + 1
+    const int zl0 = tid / (n + 1), zb0 = tid - zl0 * (n + 1);
+    const int zdl = SP_TPB / (n + 1), zdb = SP_TPB - zdl * (n + 1);
+    double acc[18];
 #pragma unroll
-        for (int k = 0; k < WS; k += 2) {
-          const double2 t2 = *reinterpret_cast<const double2*>(wp + k);
-          wa[k] = t2.x; wa[k + 1] = t2.y;
+    for (int q = 0; q < 18; q++) acc[q] = 0.0;
+    for (c = 0; c < nchunk; c++, buf ^= 1) {
+      // next chunk of the stream into the other buffer
+      if (c + 1 < nchunk) issue(R, c + 1, buf ^ 1);
+      else if (nxt >= 0) issue(Rn, 0, buf ^ 1);
+      asm volatile("cp.async.commit_group;\n" ::);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+      __syncthreads();
+      const int m = min(Lc, nl - c * Lc);
+      const double* sW = sp_smem + buf * SP_CAP_WD;
+      const double* sD = sW + Lc * rowW;
+      for (int i = tid, l = zl0, b = zb0; i < m * (n + 1); i += SP_TPB) {
+        const double* Dv = sD + l * DS;
+        double* z = sZ + l * rowZ + b * WS;
+        if (b < n) {
+          const double* wv = sW + l * rowW + b * WS;
+          double dm[D][D];
+#pragma unroll
+          for (int k = 0; k < D; k++)
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+              const int r = k < j ? k : j, c2 = k < j ? j : k;
+              dm[k][j] = Dv[r * D - (r * (r - 1)) / 2 + (c2 - r)];
+            }
+#pragma unroll
+          for (int cc = 0; cc < 6; cc++) {
+            double wb[D];
+#pragma unroll
+            for (int j = 0; j < D; j++) wb[j] = wv[cc * D + j];
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+              double zz = 0;
+#pragma unroll
+              for (int j = 0; j < D; j++) zz += dm[k][j] * wb[j];
+              z[cc * D + k] = zz;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < WS; k++) z[k] = k < D ? Dv[OFF_C + k] : 0.0;
         }
-        const double* zp = z_p + l * rowZ;
+        l += zdl; b += zdb;
+        if (b > n) { b -= n + 1; l++; }
+      }
+      __syncthreads();
+      if (act) {
+        const double* wa_p = sW + ia * WS;
+        const double* z_p = sZ + zb * WS + h * 3 * D;
+#pragma unroll 2
+        for (int l = s; l < m; l += S) {
+          double wa[WS];
+          const double* wp = wa_p + l * rowW;
 #pragma unroll
-        for (int cc = 0; cc < 3; cc++) {
-          double z[D];
+          for (int k = 0; k < WS; k += 2) {
+            const double2 t2 = *reinterpret_cast<const double2*>(wp + k);
+            wa[k] = t2.x; wa[k + 1] = t2.y;
+          }
+          const double* zp = z_p + l * rowZ;
 #pragma unroll
-          for (int k = 0; k < D; k++) z[k] = zp[cc * D + k];
+          for (int cc = 0; cc < 3; cc++) {
+            double z[D];
 #pragma unroll
-          for (int r = 0; r < 6; r++) {
-            double a2 = acc[cc * 6 + r];
+            for (int k = 0; k < D; k++) z[k] = zp[cc * D + k];
 #pragma unroll
-            for (int k = 0; k < D; k++) a2 += wa[D * r + k] * z[k];
-            acc[cc * 6 + r] = a2;
+            for (int r = 0; r < 6; r++) {
+              double a2 = acc[cc * 6 + r];
+#pragma unroll
+              for (int k = 0; k < D; k++) a2 += wa[D * r + k] * z[k];
+              acc[cc * 6 + r] = a2;
+            }
           }
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
-  }
-  // slices summed in fixed order
-  double* red = sp_smem;
-  if (act)
+    // ---- outputs: slices summed in fixed order (the Z buffer is free until the next chunk's barrier) ----
+    double* out = v.dpart + R.out;
+    if (S == 1) {
+      if (tid < ntb) {
+        const int task = R.t0 + tl;
+        if (task < 2 * npair) {
+          double* o = out + (size_t)(task >> 1) * 36 + (task & 1) * 18;
 #pragma unroll
-    for (int q = 0; q < 18; q++) red[(s * ntb + tl) * 18 + q] = acc[q];
-  __syncthreads();
-  double* out = v.dpart + v.pc_out[pc];
-  for (int e = tid; e < ntb * 18; e += SP_TPB) {
-    const int tl2 = e / 18, q = e - 18 * tl2;
-    const int task = t0 + tl2;
-    size_t o;
-    if (task < 2 * npair) o = (size_t)(task >> 1) * 36 + (task & 1) * 18 + q;
-    else if (q < 6) o = (size_t)36 * npair + (size_t)(task - 2 * npair) * 6 + q;
-    else continue;
-    double sum = 0;
-    for (int s2 = 0; s2 < S; s2++) sum += red[(s2 * ntb + tl2) * 18 + q];
-    out[o] = sum;
+          for (int q = 0; q < 18; q++) o[q] = acc[q];
+        } else {
+          double* o = out + (size_t)36 * npair + (size_t)(task - 2 * npair) * 6;
+#pragma unroll
+          for (int q = 0; q < 6; q++) o[q] = acc[q];
+        }
+      }
+    } else {
+      double* red = sZ;
+      if (act)
+#pragma unroll
+        for (int q = 0; q < 18; q++) red[(s * ntb + tl) * 18 + q] = acc[q];
+      __syncthreads();
+      for (int e = tid; e < ntb * 18; e += SP_TPB) {
+        const int tl2 = e / 18, q = e - 18 * tl2;
+        const int task = R.t0 + tl2;
+        size_t o;
+        if (task < 2 * npair) o = (size_t)(task >> 1) * 36 + (task & 1) * 18 + q;
+        else if (q < 6) o = (size_t)36 * npair + (size_t)(task - 2 * npair) * 6 + q;
+        else continue;
+        double sum = 0;
+        for (int s2 = 0; s2 < S; s2++) sum += red[(s2 * ntb + tl2) * 18 + q];
+        out[o] = sum;
+      }
+    }
+    if (nxt < 0) break;
+    cur = nxt;
+    R = Rn;
+    nxt = next_item();
+    if (nxt >= 0) load_item(nxt, Rn);
   }
 }
 
