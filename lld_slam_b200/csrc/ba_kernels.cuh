@@ -155,51 +155,87 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_points(BaView v) {
   double chi = 0;
   int nact = 0;
   const int e0 = v.pt_obs_off[p], e1 = v.pt_obs_off[p + 1];
-  for (int e = e0 + gl; e < e1 && run; e += PT_G) {
-    const int kf = v.pe_kf[e];
-    const int pos = v.dense_mode ? v.pe_wpos[e] : v.pe_pos[e];
-    double* W = v.dense_mode ? v.pe_Wl + 18 * (size_t)(pos < 0 ? 0 : pos) : v.P_rec + 27 * (size_t)(pos < 0 ? 0 : pos);
-    if (v.pe_level[e] != 0) {
-      if (pos >= 0)
-#pragma unroll
-        for (int k = 0; k < 18; k++) W[k] = 0.0;
-      continue;
+  const bool dense = v.dense_mode != 0;
+  const int* epos = dense ? v.pe_wpos : v.pe_pos;
+  // edge header (keyframe, W slot, level, observation, information) one edge ahead of the arithmetic
+  int e = e0 + gl;
+  int kf = 0, pos = -1, lvl = 1;
+  float ou = 0.f, ov = 0.f, orr = 0.f, oinfo = 0.f;
+  if (e < e1 && run) {
+    kf = v.pe_kf[e]; pos = epos[e]; lvl = v.pe_level[e];
+    ou = v.pe_uvr[3 * (size_t)e]; ov = v.pe_uvr[3 * (size_t)e + 1]; orr = v.pe_uvr[3 * (size_t)e + 2];
+    oinfo = v.pe_info[e];
+  }
+  while (e < e1 && run) {
+    const int en = e + PT_G;
+    int kf_n = 0, pos_n = -1, lvl_n = 1;
+    float ou_n = 0.f, ov_n = 0.f, or_n = 0.f, oinfo_n = 0.f;
+    if (en < e1) {
+      kf_n = v.pe_kf[en]; pos_n = epos[en]; lvl_n = v.pe_level[en];
+      ou_n = v.pe_uvr[3 * (size_t)en]; ov_n = v.pe_uvr[3 * (size_t)en + 1]; or_n = v.pe_uvr[3 * (size_t)en + 2];
+      oinfo_n = v.pe_info[en];
     }
-    nact++;
-    const double* Rt = v.pose_Rt[sel] + 12 * (size_t)kf;
-    const double* intr = v.kf_intr + 5 * (size_t)kf;
-    const float* obs = v.pe_uvr + 3 * (size_t)e;
-    const bool stereo = !(obs[2] < 0.f);
-    double xc[3], err[3], Jl[9];
-    map_Rt(Rt, X, xc);
-    pt_residual<true>(xc, intr, obs, stereo, err);
-    const double info = (double)v.pe_info[e];
-    const double c2 = err[0] * (info * err[0]) + err[1] * (info * err[1]) + err[2] * (info * err[2]);
-    double wgt = 1.0, rho = c2;
-    if (v.prm.robust_pt) rho = huber(c2, stereo ? v.prm.delta_pt_stereo : v.prm.delta_pt_mono, &wgt);
-    chi += rho;
-    const double wo = wgt * info;
-    pt_jac_point(xc, Rt, intr, stereo, Jl);
-    // Hll += Jl^T wo Jl ; bl -= Jl^T wo err
-    double JW[9];
+    double* W = dense ? v.pe_Wl + 18 * (size_t)(pos < 0 ? 0 : pos) : v.P_rec + 27 * (size_t)(pos < 0 ? 0 : pos);
+    double Wv[18];
 #pragma unroll
-    for (int k = 0; k < 9; k++) JW[k] = wo * Jl[k];
-    H[0] += JW[0] * Jl[0] + JW[3] * Jl[3] + JW[6] * Jl[6];
-    H[1] += JW[0] * Jl[1] + JW[3] * Jl[4] + JW[6] * Jl[7];
-    H[2] += JW[0] * Jl[2] + JW[3] * Jl[5] + JW[6] * Jl[8];
-    H[3] += JW[1] * Jl[1] + JW[4] * Jl[4] + JW[7] * Jl[7];
-    H[4] += JW[1] * Jl[2] + JW[4] * Jl[5] + JW[7] * Jl[8];
-    H[5] += JW[2] * Jl[2] + JW[5] * Jl[5] + JW[8] * Jl[8];
+    for (int k = 0; k < 18; k++) Wv[k] = 0.0;
+    if (lvl == 0) {
+      nact++;
+      double Rt[12];
+      {
+        const double2* rp = reinterpret_cast<const double2*>(v.pose_Rt[sel] + 12 * (size_t)kf);
 #pragma unroll
-    for (int c = 0; c < 3; c++) bl[c] -= JW[c] * err[0] + JW[3 + c] * err[1] + JW[6 + c] * err[2];
-    if (pos >= 0) {
-      double Jp[18];
-      pt_jac_pose(xc, intr, stereo, Jp);
+        for (int k = 0; k < 6; k++) {
+          const double2 t2 = rp[k];
+          Rt[2 * k] = t2.x; Rt[2 * k + 1] = t2.y;
+        }
+      }
+      const double* intr = v.kf_intr + 5 * (size_t)kf;
+      const float obs[3] = {ou, ov, orr};
+      const bool stereo = !(orr < 0.f);
+      double xc[3], err[3], Jl[9];
+      map_Rt(Rt, X, xc);
+      pt_residual<true>(xc, intr, obs, stereo, err);
+      const double info = (double)oinfo;
+      const double c2 = err[0] * (info * err[0]) + err[1] * (info * err[1]) + err[2] * (info * err[2]);
+      double wgt = 1.0, rho = c2;
+      if (v.prm.robust_pt) rho = huber(c2, stereo ? v.prm.delta_pt_stereo : v.prm.delta_pt_mono, &wgt);
+      chi += rho;
+      const double wo = wgt * info;
+      pt_jac_point(xc, Rt, intr, stereo, Jl);
+      // Hll += Jl^T wo Jl ; bl -= Jl^T wo err
+      double JW[9];
 #pragma unroll
-      for (int r = 0; r < 6; r++)
+      for (int k = 0; k < 9; k++) JW[k] = wo * Jl[k];
+      H[0] += JW[0] * Jl[0] + JW[3] * Jl[3] + JW[6] * Jl[6];
+      H[1] += JW[0] * Jl[1] + JW[3] * Jl[4] + JW[6] * Jl[7];
+      H[2] += JW[0] * Jl[2] + JW[3] * Jl[5] + JW[6] * Jl[8];
+      H[3] += JW[1] * Jl[1] + JW[4] * Jl[4] + JW[7] * Jl[7];
+      H[4] += JW[1] * Jl[2] + JW[4] * Jl[5] + JW[7] * Jl[8];
+      H[5] += JW[2] * Jl[2] + JW[5] * Jl[5] + JW[8] * Jl[8];
 #pragma unroll
-        for (int c = 0; c < 3; c++) W[r * 3 + c] = Jp[r] * JW[c] + Jp[6 + r] * JW[3 + c] + Jp[12 + r] * JW[6 + c];
+      for (int c = 0; c < 3; c++) bl[c] -= JW[c] * err[0] + JW[3 + c] * err[1] + JW[6 + c] * err[2];
+      if (pos >= 0) {
+        double Jp[18];
+        pt_jac_pose(xc, intr, stereo, Jp);
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) Wv[r * 3 + c] = Jp[r] * JW[c] + Jp[6 + r] * JW[3 + c] + Jp[12 + r] * JW[6 + c];
+      }
     }
+    if (pos >= 0) {  // W of a gated-out edge is zero
+      if (dense) {   // 144-byte blocks: 16-byte stores
+        double2* wp = reinterpret_cast<double2*>(W);
+#pragma unroll
+        for (int k = 0; k < 9; k++) wp[k] = make_double2(Wv[2 * k], Wv[2 * k + 1]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 18; k++) W[k] = Wv[k];
+      }
+    }
+    e = en; kf = kf_n; pos = pos_n; lvl = lvl_n;
+    ou = ou_n; ov = ov_n; orr = or_n; oinfo = oinfo_n;
   }
 #pragma unroll
   for (int o = PT_G / 2; o > 0; o >>= 1) {
@@ -1973,16 +2009,46 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_points(BaView v) {
   const double* Dp = v.dense_mode ? v.pts_D + 10 * (size_t)v.pt_spos[p] : v.pt_D + 9 * (size_t)p;
   double s3[3] = {0, 0, 0};
   const int e0 = v.pt_obs_off[p], e1 = v.pt_obs_off[p + 1];
-  for (int e = e0 + gl; e < e1 && go; e += PT_G) {
-    if (v.pe_level[e] != 0) continue;
-    const int pos = v.dense_mode ? v.pe_wpos[e] : v.pe_pos[e];
-    if (pos < 0) continue;
-    const double* W = v.dense_mode ? v.pe_Wl + 18 * (size_t)pos : v.P_rec + 27 * (size_t)pos;
-    const double* xp = v.g_x + 6 * (size_t)v.kf_g[v.pe_kf[e]];
+  {
+    const bool dense = v.dense_mode != 0;
+    const int* epos = dense ? v.pe_wpos : v.pe_pos;
+    // (W slot, update block) of the edge one ahead of the arithmetic: the keyframe -> block -> x chain is three loads deep
+    int e = e0 + gl, pos = -1, g = 0;
+    if (e < e1 && go) {
+      pos = v.pe_level[e] != 0 ? -1 : epos[e];
+      g = v.kf_g[v.pe_kf[e]];
+    }
+    while (e < e1 && go) {
+      const int en = e + PT_G;
+      int pos_n = -1, g_n = 0;
+      if (en < e1) {
+        pos_n = v.pe_level[en] != 0 ? -1 : epos[en];
+        g_n = v.kf_g[v.pe_kf[en]];
+      }
+      if (pos >= 0) {
+        double Wv[18];
+        if (dense) {
+          const double2* wp = reinterpret_cast<const double2*>(v.pe_Wl + 18 * (size_t)pos);
 #pragma unroll
-    for (int r = 0; r < 6; r++) {
-      const double x = xp[r];
-      s3[0] += W[3 * r] * x; s3[1] += W[3 * r + 1] * x; s3[2] += W[3 * r + 2] * x;
+          for (int k = 0; k < 9; k++) {
+            const double2 t2 = wp[k];
+            Wv[2 * k] = t2.x; Wv[2 * k + 1] = t2.y;
+          }
+        } else {
+          const double* wp = v.P_rec + 27 * (size_t)pos;
+#pragma unroll
+          for (int k = 0; k < 18; k++) Wv[k] = wp[k];
+        }
+        const double2* xp2 = reinterpret_cast<const double2*>(v.g_x + 6 * (size_t)g);
+        const double2 x01 = xp2[0], x23 = xp2[1], x45 = xp2[2];
+        const double xp[6] = {x01.x, x01.y, x23.x, x23.y, x45.x, x45.y};
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+          const double x = xp[r];
+          s3[0] += Wv[3 * r] * x; s3[1] += Wv[3 * r + 1] * x; s3[2] += Wv[3 * r + 2] * x;
+        }
+      }
+      e = en; pos = pos_n; g = g_n;
     }
   }
 #pragma unroll
@@ -1998,20 +2064,45 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_points(BaView v) {
   }
   const double X[3] = {Xo[0] + xl[0], Xo[1] + xl[1], Xo[2] + xl[2]};
   double chi = 0;
-  for (int e = e0 + gl; e < e1 && go; e += PT_G) {
-    if (v.pe_level[e] != 0) continue;
-    const int kf = v.pe_kf[e];
-    const double* Rt = v.pose_Rt[sel ^ 1] + 12 * (size_t)kf;
-    const float* obs = v.pe_uvr + 3 * (size_t)e;
-    const bool stereo = !(obs[2] < 0.f);
-    double xc[3], err[3];
-    map_Rt(Rt, X, xc);
-    pt_residual<true>(xc, v.kf_intr + 5 * (size_t)kf, obs, stereo, err);
-    const double info = (double)v.pe_info[e];
-    const double c2 = err[0] * (info * err[0]) + err[1] * (info * err[1]) + err[2] * (info * err[2]);
-    v.pe_chi2[e] = c2;
-    double wgt;
-    chi += v.prm.robust_pt ? huber(c2, stereo ? v.prm.delta_pt_stereo : v.prm.delta_pt_mono, &wgt) : c2;
+  {
+    int e = e0 + gl, kf = 0, lvl = 1;
+    float ou = 0.f, ov = 0.f, orr = 0.f, oinfo = 0.f;
+    if (e < e1 && go) {
+      kf = v.pe_kf[e]; lvl = v.pe_level[e];
+      ou = v.pe_uvr[3 * (size_t)e]; ov = v.pe_uvr[3 * (size_t)e + 1]; orr = v.pe_uvr[3 * (size_t)e + 2];
+      oinfo = v.pe_info[e];
+    }
+    while (e < e1 && go) {
+      const int en = e + PT_G;
+      int kf_n = 0, lvl_n = 1;
+      float ou_n = 0.f, ov_n = 0.f, or_n = 0.f, oinfo_n = 0.f;
+      if (en < e1) {
+        kf_n = v.pe_kf[en]; lvl_n = v.pe_level[en];
+        ou_n = v.pe_uvr[3 * (size_t)en]; ov_n = v.pe_uvr[3 * (size_t)en + 1]; or_n = v.pe_uvr[3 * (size_t)en + 2];
+        oinfo_n = v.pe_info[en];
+      }
+      if (lvl == 0) {
+        double Rt[12];
+        const double2* rp = reinterpret_cast<const double2*>(v.pose_Rt[sel ^ 1] + 12 * (size_t)kf);
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          const double2 t2 = rp[k];
+          Rt[2 * k] = t2.x; Rt[2 * k + 1] = t2.y;
+        }
+        const float obs[3] = {ou, ov, orr};
+        const bool stereo = !(orr < 0.f);
+        double xc[3], err[3];
+        map_Rt(Rt, X, xc);
+        pt_residual<true>(xc, v.kf_intr + 5 * (size_t)kf, obs, stereo, err);
+        const double info = (double)oinfo;
+        const double c2 = err[0] * (info * err[0]) + err[1] * (info * err[1]) + err[2] * (info * err[2]);
+        v.pe_chi2[e] = c2;
+        double wgt;
+        chi += v.prm.robust_pt ? huber(c2, stereo ? v.prm.delta_pt_stereo : v.prm.delta_pt_mono, &wgt) : c2;
+      }
+      e = en; kf = kf_n; lvl = lvl_n;
+      ou = ou_n; ov = ov_n; orr = or_n; oinfo = oinfo_n;
+    }
   }
 #pragma unroll
   for (int o = PT_G / 2; o > 0; o >>= 1) chi += __shfl_xor_sync(0xffffffffu, chi, o);
