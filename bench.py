@@ -180,6 +180,8 @@ def kernel_bytes(name, p):
         "k_lin_points<1>": n_pe * 24 + n_pw * 144 + P * (24 + 72),
         "k_lin_points<4>": n_pe * 24 + n_pw * 144 + P * (24 + 72),
         "k_lin_lines<1>": n_lc * 56 + n_lw * 192 + L * (40 + 112),
+        "k_lin_lines<2>": n_lc * 56 + n_lw * 192 + L * (40 + 112),
+        "k_lin_lines<4>": n_lc * 56 + n_lw * 192 + L * (40 + 112),
         "k_lin_lines<8>": n_lc * 56 + n_lw * 192 + L * (40 + 112),
         "k_lin_poses": n_pe * 24 + n_lc * 56 + (n_pe + n_lc) * 24,
         "k_schur_points": P * (72 + 80),
@@ -191,6 +193,8 @@ def kernel_bytes(name, p):
         "k_backsub_points<1>": n_pw * 144 + n_pe * (24 + 8) + P * (24 + 24 + 80),
         "k_backsub_points<4>": n_pw * 144 + n_pe * (24 + 8) + P * (24 + 24 + 80),
         "k_backsub_lines<1>": n_lw * 192 + n_lc * (56 + 16) + L * (40 + 40 + 112),
+        "k_backsub_lines<2>": n_lw * 192 + n_lc * (56 + 16) + L * (40 + 40 + 112),
+        "k_backsub_lines<4>": n_lw * 192 + n_lc * (56 + 16) + L * (40 + 40 + 112),
         "k_backsub_lines<8>": n_lw * 192 + n_lc * (56 + 16) + L * (40 + 40 + 112),
     }
     return tbl.get(name)

@@ -36,6 +36,7 @@ struct BaState {
   int max_n = 0;       // largest reduced system dimension over the windows
   int max_nnb = 0;
   size_t n_nb_total = 0;
+  bool gather_long = false;   // dense mode: average S-block gather list longer than a warp -> k_reduce_piece_warp
   size_t env_smem = 0, band_smem = 0;
   bool use_band = false;
   bool global_mode = false;
@@ -659,6 +660,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
       });
     }
   }
+  S->gather_long = dense && gb_src.size() > 32 * std::max<size_t>(nb_g.size(), 1);
   v.n_items = (int)it_piece.size();
   v.n_items_pt = dense ? n_items_pt : 0;
 
@@ -761,7 +763,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   for (int w = 0; w < nw; w++) {
     const long long n = 6LL * (w_g0[w + 1] - w_g0[w]);
     w_scr[w] = scr_total;
-    if (S->max_n > SMEM_SOLVE_MAX_N && !v.env_mode) scr_total += n * n + 8 * n + 8;
+    if (S->max_n > SMEM_SOLVE_MAX_N && !v.env_mode) scr_total += n * n + 8 * n + 24;
   }
 
   stage("chunks");
@@ -907,7 +909,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   if (v.env_mode && S->use_band) LLD_CUDA(c, lld_raise_dyn_smem(k_solve_band<512>, (size_t)(int)S->band_smem) != cudaSuccess ? cudaErrorInvalidValue : lld_raise_dyn_smem(k_solve_band<1024>, (size_t)(int)S->band_smem));
   else if (v.env_mode) LLD_CUDA(c, lld_raise_dyn_smem(k_solve_env, (size_t)(int)S->env_smem));
   else if (S->max_n <= SMEM_SOLVE_MAX_N)
-    LLD_CUDA(c, lld_raise_dyn_smem(k_solve<true>, (size_t)(int)(sizeof(double) * ((size_t)S->max_n * S->max_n + 8 * (size_t)S->max_n + 8))));
+    LLD_CUDA(c, lld_raise_dyn_smem(k_solve<true>, (size_t)(int)(sizeof(double) * ((size_t)S->max_n * S->max_n + 8 * (size_t)S->max_n + 24))));
   return LLD_OK;
 }
 
@@ -975,7 +977,7 @@ static int ba_allreduce_rows(LldCtx* c) {
 
 template <bool SMEM>
 static int launch_solve(LldCtx* c, BaView& v, int max_n) {
-  size_t smem = SMEM ? sizeof(double) * ((size_t)max_n * max_n + 8 * (size_t)max_n + 8) : 0;
+  size_t smem = SMEM ? sizeof(double) * ((size_t)max_n * max_n + 8 * (size_t)max_n + 24) : 0;
   LLD_LAUNCH(c, k_solve<SMEM>, v.n_win, 512, smem, v);
   return LLD_OK;
 }
@@ -989,6 +991,32 @@ static int launch_solve(LldCtx* c, BaView& v, int max_n) {
 constexpr int LN_WIDE_MAX = 8192;
 // same for map points, four lanes per point
 constexpr int PT_WIDE_MAX = 32768;
+
+// lanes per map line in k_lin_lines / k_backsub_lines: enough threads to fill the SMs, no more (idle lanes still shuffle)
+static int lanes_per_line(const LldCtx* c, int n_ln) {
+  static const int forced = getenv("LLD_LN_G") ? atoi(getenv("LLD_LN_G")) : 0;
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
+  if (n_ln <= LN_WIDE_MAX) return 8;
+  return n_ln <= 1024 * c->sm_count ? 2 : 1;
+}
+static int launch_line_kernel(LldCtx* c, cudaStream_t strm, const BaView& v, bool lin) {
+  if (!v.n_ln) return LLD_OK;
+  const int g = lanes_per_line(c, v.n_ln);
+  const int grid = cdiv(v.n_ln * g, LM_TPB);
+#define LLD_LINE_CASE(G)                                                   \
+  case G:                                                                  \
+    if (lin) LLD_LAUNCH_S(c, strm, k_lin_lines<G>, grid, LM_TPB, 0, v);    \
+    else LLD_LAUNCH_S(c, strm, k_backsub_lines<G>, grid, LM_TPB, 0, v);    \
+    break;
+  switch (g) {
+    LLD_LINE_CASE(1)
+    LLD_LINE_CASE(2)
+    LLD_LINE_CASE(4)
+    LLD_LINE_CASE(8)
+  }
+#undef LLD_LINE_CASE
+  return LLD_OK;
+}
 
 static int ba_step_forked(LldCtx* c, int round, int stop_now) {
   BaState* S = c->ba;
@@ -1005,8 +1033,7 @@ static int ba_step_forked(LldCtx* c, int round, int stop_now) {
   LLD_CUDA(c, fork(s2));
   if (v.n_pt && v.n_pt <= PT_WIDE_MAX) LLD_LAUNCH_S(c, s0, k_lin_points<4>, cdiv(v.n_pt * 4, LM_TPB), LM_TPB, 0, v);
   else if (v.n_pt) LLD_LAUNCH_S(c, s0, k_lin_points<1>, gp, LM_TPB, 0, v);
-  if (v.n_ln && v.n_ln <= LN_WIDE_MAX) LLD_LAUNCH_S(c, s1, k_lin_lines<8>, cdiv(v.n_ln * 8, LM_TPB), LM_TPB, 0, v);
-  else if (v.n_ln) LLD_LAUNCH_S(c, s1, k_lin_lines<1>, cdiv(v.n_ln, LM_TPB), LM_TPB, 0, v);
+  { int r = launch_line_kernel(c, s1, v, true); if (r) return r; }
   if (v.n_chunks) LLD_LAUNCH_S(c, s2, k_lin_poses, v.n_chunks, LM_TPB, 0, v);
   LLD_CUDA(c, join(0));
   LLD_CUDA(c, join(1));
@@ -1022,14 +1049,14 @@ static int ba_step_forked(LldCtx* c, int round, int stop_now) {
   else if (nil) LLD_LAUNCH_S(c, s1, k_schur_piece<4>, cdiv(nil, 8), 256, 0, v, nip, nil);
   LLD_CUDA(c, join(0));
   const int nblk = (int)S->n_nb_total;
-  LLD_LAUNCH_S(c, s0, k_reduce_piece, cdiv(nblk * 6 + v.n_free_total, 8), 256, 0, v, nblk);
+  if (S->gather_long) LLD_LAUNCH_S(c, s0, k_reduce_piece_warp, cdiv(nblk * 6 + v.n_free_total, 8), 256, 0, v, nblk);
+  else LLD_LAUNCH_S(c, s0, k_reduce_piece, cdiv(nblk * 36 + 6 * v.n_free_total, 256), 256, 0, v, nblk);
   { int r = launch_solve<true>(c, v, S->max_n); if (r) return r; }
   LLD_CUDA(c, cudaEventRecord(c->ev_fork, s0));
   LLD_CUDA(c, fork(s1));
   if (v.n_pt && v.n_pt <= PT_WIDE_MAX) LLD_LAUNCH_S(c, s0, k_backsub_points<4>, cdiv(v.n_pt * 4, LM_TPB), LM_TPB, 0, v);
   else if (v.n_pt) LLD_LAUNCH_S(c, s0, k_backsub_points<1>, gp, LM_TPB, 0, v);
-  if (v.n_ln && v.n_ln <= LN_WIDE_MAX) LLD_LAUNCH_S(c, s1, k_backsub_lines<8>, cdiv(v.n_ln * 8, LM_TPB), LM_TPB, 0, v);
-  else if (v.n_ln) LLD_LAUNCH_S(c, s1, k_backsub_lines<1>, cdiv(v.n_ln, LM_TPB), LM_TPB, 0, v);
+  { int r = launch_line_kernel(c, s1, v, false); if (r) return r; }
   LLD_CUDA(c, join(0));
   LLD_LAUNCH_S(c, s0, k_decide_fused, v.n_win, FUSED_RED_TPB, 0, v, round, stop_now);
   LLD_CUDA(c, cudaGetLastError());
@@ -1044,8 +1071,7 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   const int gp = cdiv(std::max(v.n_pt, 1), LM_TPB), gl = cdiv(std::max(v.n_ln, 1), LM_TPB);
   if (v.n_pt && v.n_pt <= PT_WIDE_MAX) LLD_LAUNCH(c, k_lin_points<4>, cdiv(v.n_pt * 4, LM_TPB), LM_TPB, 0, v);
   else if (v.n_pt) LLD_LAUNCH(c, k_lin_points<1>, gp, LM_TPB, 0, v);
-  if (v.n_ln && v.n_ln <= LN_WIDE_MAX) LLD_LAUNCH(c, k_lin_lines<8>, cdiv(v.n_ln * 8, LM_TPB), LM_TPB, 0, v);
-  else if (v.n_ln) LLD_LAUNCH(c, k_lin_lines<1>, cdiv(v.n_ln, LM_TPB), LM_TPB, 0, v);
+  { int r = launch_line_kernel(c, c->stream, v, true); if (r) return r; }
   if (v.n_chunks) LLD_LAUNCH(c, k_lin_poses, v.n_chunks, LM_TPB, 0, v);
   const bool multi = S->global_mode && c->n_ranks > 1;
   const bool fused = !multi && v.n_slices == 1;
@@ -1067,7 +1093,8 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
     if (nil && v.schur_tile) LLD_LAUNCH(c, k_schur_tile<4>, std::min(nil, 4 * c->sm_count), SP_TPB, SP_SMEM_BYTES, v, nip, nil);
     else if (nil) LLD_LAUNCH(c, k_schur_piece<4>, cdiv(nil, 8), 256, 0, v, nip, nil);
     const int nblk = (int)S->n_nb_total;
-    LLD_LAUNCH(c, k_reduce_piece, cdiv(nblk * 6 + v.n_free_total, 8), 256, 0, v, nblk);
+    if (S->gather_long) LLD_LAUNCH(c, k_reduce_piece_warp, cdiv(nblk * 6 + v.n_free_total, 8), 256, 0, v, nblk);
+    else LLD_LAUNCH(c, k_reduce_piece, cdiv(nblk * 36 + 6 * v.n_free_total, 256), 256, 0, v, nblk);
   } else {
     const int tpb = 32 * cdiv(6 * S->max_nnb, 32);
     const int nl = v.n_chunks - v.n_chunks_pt;
@@ -1094,8 +1121,7 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   else { int r = launch_solve<false>(c, v, S->max_n); if (r) return r; }
   if (v.n_pt && v.n_pt <= PT_WIDE_MAX) LLD_LAUNCH(c, k_backsub_points<4>, cdiv(v.n_pt * 4, LM_TPB), LM_TPB, 0, v);
   else if (v.n_pt) LLD_LAUNCH(c, k_backsub_points<1>, gp, LM_TPB, 0, v);
-  if (v.n_ln && v.n_ln <= LN_WIDE_MAX) LLD_LAUNCH(c, k_backsub_lines<8>, cdiv(v.n_ln * 8, LM_TPB), LM_TPB, 0, v);
-  else if (v.n_ln) LLD_LAUNCH(c, k_backsub_lines<1>, cdiv(v.n_ln, LM_TPB), LM_TPB, 0, v);
+  { int r = launch_line_kernel(c, c->stream, v, false); if (r) return r; }
   if (fused) {
     LLD_LAUNCH(c, k_decide_fused, v.n_win, FUSED_RED_TPB, 0, v, round, stop_now);
   } else {

@@ -288,15 +288,36 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_lines(BaView v) {
   int nact = 0;
   const bool removed = v.ln_removed[lc] != 0;
   const int c0 = v.ln_obs_off[lc], c1 = v.ln_obs_off[lc + 1];
-  for (int c = c0 + gl; c < c1 && run; c += LN_G) {
-    const int kf = v.lc_kf[c];
-    const int pos = v.dense_mode ? v.lc_wpos[c] : v.lc_pos[c];
+  const int* cpos = v.dense_mode ? v.lc_wpos : v.lc_pos;
+  // cell header (keyframe, W slot, levels) one cell ahead of the arithmetic
+  int c = c0 + gl, kf = 0, pos = -1;
+  unsigned lv = 0x0101u;
+  if (c < c1 && run) {
+    kf = v.lc_kf[c]; pos = cpos[c];
+    lv = *reinterpret_cast<const unsigned short*>(v.lc_level + 2 * (size_t)c);
+  }
+  while (c < c1 && run) {
+    const int cn = c + LN_G;
+    int kf_n = 0, pos_n = -1;
+    unsigned lv_n = 0x0101u;
+    if (cn < c1) {
+      kf_n = v.lc_kf[cn]; pos_n = cpos[cn];
+      lv_n = *reinterpret_cast<const unsigned short*>(v.lc_level + 2 * (size_t)cn);
+    }
     double W[24];
 #pragma unroll
     for (int k = 0; k < 24; k++) W[k] = 0.0;
-    const uint8_t lv0 = v.lc_level[2 * c], lv1 = v.lc_level[2 * c + 1];
+    const unsigned lv0 = lv & 0xffu, lv1 = lv >> 8;
     if (!removed && (lv0 == 0 || lv1 == 0)) {
-      const double* Rt = v.pose_Rt[sel] + 12 * (size_t)kf;
+      double Rt[12];
+      {
+        const double2* rp = reinterpret_cast<const double2*>(v.pose_Rt[sel] + 12 * (size_t)kf);
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          const double2 t2 = rp[k];
+          Rt[2 * k] = t2.x; Rt[2 * k + 1] = t2.y;
+        }
+      }
       const double* cam = v.kf_lcam + 4 * (size_t)kf;
       double P1[3], P2[3];
       map_Rt(Rt, X1, P1);
@@ -333,11 +354,12 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_lines(BaView v) {
         }
       }
     }
-    if (pos >= 0) {
-      double* Wo = v.dense_mode ? v.lc_Wl + 24 * (size_t)pos : v.L_rec + 38 * (size_t)pos;
+    if (pos >= 0) {   // 192- / 304-byte records: 16-byte stores
+      double2* Wo = reinterpret_cast<double2*>(v.dense_mode ? v.lc_Wl + 24 * (size_t)pos : v.L_rec + 38 * (size_t)pos);
 #pragma unroll
-      for (int k = 0; k < 24; k++) Wo[k] = W[k];
+      for (int k = 0; k < 12; k++) Wo[k] = make_double2(W[2 * k], W[2 * k + 1]);
     }
+    c = cn; kf = kf_n; pos = pos_n; lv = lv_n;
   }
   // group sum (xor 4, 2, 1 inside the aligned group of LN_G lanes): every lane ends with the line's totals
 #pragma unroll
@@ -399,11 +421,23 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_poses(BaView v) {
   double acc[28];
 #pragma unroll
   for (int k = 0; k < 28; k++) acc[k] = 0.0;
-  for (int i = v.ch_begin[ch] + threadIdx.x; i < v.ch_end[ch]; i += blockDim.x) {
+  // entry header (edge / cell, its landmark) one entry ahead: the list -> edge -> landmark -> state chain is four loads deep
+  const int i_end = v.ch_end[ch];
+  int i = v.ch_begin[ch] + threadIdx.x, id = 0, lm = 0;
+  if (i < i_end) {
+    id = is_pt ? v.pl_edge[i] : v.ll_cell[i];
+    lm = is_pt ? v.pe_pt[id] : v.lc_ln[id];
+  }
+  for (; i < i_end; i += blockDim.x) {
+    const int id_c = id, lm_c = lm;
+    if (i + (int)blockDim.x < i_end) {
+      id = is_pt ? v.pl_edge[i + blockDim.x] : v.ll_cell[i + blockDim.x];
+      lm = is_pt ? v.pe_pt[id] : v.lc_ln[id];
+    }
     if (is_pt) {
-      const int e = v.pl_edge[i];
+      const int e = id_c;
       if (v.pe_level[e] != 0) continue;
-      const double* X = v.pt_xyz[sel] + 3 * (size_t)v.pe_pt[e];
+      const double* X = v.pt_xyz[sel] + 3 * (size_t)lm_c;
       const float* obs = v.pe_uvr + 3 * (size_t)e;
       const bool stereo = !(obs[2] < 0.f);
       double xc[3], err[3], Jp[18];
@@ -424,8 +458,8 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_poses(BaView v) {
       }
       acc[27] += 1.0;
     } else {
-      const int c = v.ll_cell[i];
-      const int l = v.lc_ln[c];
+      const int c = id_c;
+      const int l = lm_c;
       if (v.ln_removed[l]) continue;
       const uint8_t lv0 = v.lc_level[2 * c], lv1 = v.lc_level[2 * c + 1];
       if (lv0 != 0 && lv1 != 0) continue;
@@ -1196,8 +1230,52 @@ __global__ void __launch_bounds__(SP_TPB, 4) k_schur_tile(BaView v, int item_bas
 }
 
 // S(a,b) = [a==b] (Hpp_a + lambda I) - sum over contributing (piece, pair) ; bschur_a = bp_a - sum b tasks
-// one warp per (block, column c) and per free keyframe: lanes stride over the gather list, fixed-order shuffle tree
+// one thread per element of an S block (36 consecutive threads read 288 contiguous bytes of every contribution) and per
+// element of b_schur; the gather list is walked in its fixed order
 __global__ void __launch_bounds__(256) k_reduce_piece(BaView v, int n_blocks) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_blocks * 36) {
+    const int blk = t / 36, e = t - 36 * blk, c = e / 6, r = e - 6 * c;
+    int lo = 0, hi = v.n_free_total;   // owning free block row g: largest g with nb_off[g] <= blk
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (v.nb_off[mid] <= blk) lo = mid;
+      else hi = mid;
+    }
+    const int g = lo, j = blk - v.nb_off[g];
+    const int w = v.kf_win[v.g_kf[g]];
+    if (v.w_phase[w] == PH_DONE) return;
+    double s = 0;
+    const int q1 = v.gb_off[blk + 1];
+    int q = v.gb_off[blk];
+    for (; q + 4 <= q1; q += 4) {
+      const long long o0 = v.gb_src[q], o1 = v.gb_src[q + 1], o2 = v.gb_src[q + 2], o3 = v.gb_src[q + 3];
+      const double a0 = v.dpart[o0 + e], a1 = v.dpart[o1 + e], a2 = v.dpart[o2 + e], a3 = v.dpart[o3 + e];
+      s += a0; s += a1; s += a2; s += a3;
+    }
+    for (; q < q1; q++) s += v.dpart[v.gb_src[q] + e];
+    double d = 0.0;
+    if (j == 0) {
+      const int rr = r < c ? r : c, cc = r < c ? c : r;
+      d = v.g_Hpp[21 * (size_t)g + (rr * 6 - (rr * (rr - 1)) / 2 + (cc - rr))];
+      if (r == c) d += v.w_lambda[w];
+    }
+    v.S_blk[36 * (size_t)blk + 6 * r + c] = d - s;
+  } else {
+    const int u = t - n_blocks * 36;
+    const int g = u / 6, r = u - 6 * g;
+    if (g >= v.n_free_total) return;
+    const int w = v.kf_win[v.g_kf[g]];
+    if (v.w_phase[w] == PH_DONE) return;
+    double s = 0;
+    for (int q = v.gv_off[g]; q < v.gv_off[g + 1]; q++) s += v.dpart[v.gv_src[q] + r];
+    v.g_bs[6 * (size_t)g + r] = v.g_bp[6 * (size_t)g + r] - s;
+  }
+}
+
+// the same sums for long gather lists (few windows cut into many short pieces): one warp per (block, column c) and per
+// free keyframe, lanes stride over the gather list, fixed-order shuffle tree
+__global__ void __launch_bounds__(256) k_reduce_piece_warp(BaView v, int n_blocks) {
   const int wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (wi < n_blocks * 6) {
@@ -1256,68 +1334,63 @@ __global__ void __launch_bounds__(256) k_reduce_piece(BaView v, int n_blocks) {
 // stands in for LinearSolverEigen / LinearSolverDense (Thirdparty/g2o/g2o/solvers/*.h); failure = zero or
 // non-finite pivot.
 // ------------------------------------------------------------------------------------------------
-// Blocked (6-column supernode) LDL^T of the reduced camera system by one CTA: per block column
-//   (1) thread 0 factors the 6x6 diagonal block and forward-solves the rhs block,
-//   (2) one thread per row below solves its 1x6 panel row  T = A_ik L_kk^-T  and  L = T D^-1,
-//   (3) one warp per row applies the rank-6 update  A_ij -= sum_c L_ic T_jc  and  b_i -= sum_c L_ic z_c.
-// n is a multiple of 6.  tmp: >= 7n doubles (T transposed [6][n] + z[6]).
-__device__ bool ldlt_solve_cta(double* A, int n, int ld, double* b /*in: rhs, out: x*/, double* tmp, int* flag) {
+// Blocked (6-column supernode) LDL^T of the reduced camera system by one CTA, diagonal blocks factored one pivot ahead:
+//   (0) warp 0 factors diagonal block 0 (lanes 0..20 = lower-triangle entries, pivots broadcast by shuffles) and
+//       forward-solves its rhs block;
+//   per block column k:
+//   (1) one thread per row below solves its 1x6 panel row  T = A_ik L_kk^-T  and  L = T D^-1,
+//   (2) rank-6 trailing update  A_ij -= sum_c L_ic T_jc,  b_i -= sum_c L_ic z_c : warp 0 takes the six rows of
+//       diagonal block k + 1 and factors it at once (the ~900-cycle dependent chain of the 6x6 LDL^T runs under the
+//       other warps' update instead of between two barriers), the other warps take one row each.
+// n is a multiple of 6.  tmp: >= 6 n + 16 doubles (T transposed [6][n] + z[2][8]).
+__device__ bool ldlt_solve_cta(double* A, int n, int ld, double* b /*in: rhs, out: x*/, double* tmp, int* flag, bool dbg = false) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
   double* Tt = tmp;          // [6][n]
-  double* zb = tmp + 6 * n;  // [6]
+  double* zb = tmp + 6 * n;  // [2][8]
+  long long t_pan = 0, t_upd = 0, t_mark = 0, t_f0 = 0;
+  if (dbg) t_mark = clock64();
+  int li = 0, lj = lane;     // lanes 0..20: entry (li, lj), lj <= li, of a diagonal block
+  while (li < 5 && lj > li) { lj -= li + 1; li++; }
+  // unblocked LDL^T of the 6x6 diagonal block at k0 + forward substitution of its rhs block, by one warp
+  auto factor = [&](int k0, double* zq) -> bool {
+    double m = lane < 21 ? A[(size_t)(k0 + li) * ld + k0 + lj] : 0.0;
+    double zz = lane < 6 ? b[k0 + lane] : 0.0;
+    bool okk = true;
+#pragma unroll
+    for (int pv = 0; pv < 6; pv++) {
+      const double d = __shfl_sync(0xffffffffu, m, pv * (pv + 1) / 2 + pv);
+      if (!(d != 0.0) || !isfinite(d)) okk = false;
+      const double id = 1.0 / d;
+      const double tip = __shfl_sync(0xffffffffu, m, li * (li + 1) / 2 + pv);   // T(i, pv), used when li > pv
+      const double tjp = __shfl_sync(0xffffffffu, m, lj * (lj + 1) / 2 + pv);   // T(j, pv), used when lj > pv
+      if (lane < 21 && lj > pv) m -= (tip * id) * tjp;
+      if (lane < 21 && lj == pv && li > pv) m *= id;
+    }
+#pragma unroll
+    for (int pv = 0; pv < 5; pv++) {   // L z = b
+      const double zp = __shfl_sync(0xffffffffu, zz, pv);
+      const double lip = __shfl_sync(0xffffffffu, m, (lane < 6 ? lane * (lane + 1) / 2 : 0) + pv);
+      if (lane < 6 && lane > pv) zz -= lip * zp;
+    }
+    if (lane < 21) A[(size_t)(k0 + li) * ld + k0 + lj] = m;
+    if (lane < 6) {
+      zq[lane] = zz;
+      b[k0 + lane] = zz;
+    }
+    return okk;
+  };
   if (tid == 0) *flag = 1;
   __syncthreads();
-  for (int k0 = 0; k0 < n; k0 += 6) {
-    if (tid == 0) {
-      // unblocked LDL^T of the 6x6 diagonal block in registers (independent loads first), then written back
-      double M[6][6], zz[6];
-#pragma unroll
-      for (int i = 0; i < 6; i++) {
-        zz[i] = b[k0 + i];
-#pragma unroll
-        for (int j = 0; j < 6; j++) M[i][j] = (j <= i) ? A[(size_t)(k0 + i) * ld + k0 + j] : 0.0;
-      }
-      bool ok = true;
-#pragma unroll
-      for (int j = 0; j < 6; j++) {
-        double d = M[j][j];
-#pragma unroll
-        for (int q = 0; q < 6; q++)
-          if (q < j) d -= M[j][q] * M[j][q] * M[q][q];
-        if (!(d != 0.0) || !isfinite(d)) ok = false;
-        M[j][j] = d;
-        const double id = 1.0 / d;
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-          if (i > j) {
-            double s2 = M[i][j];
-#pragma unroll
-            for (int q = 0; q < 6; q++)
-              if (q < j) s2 -= M[i][q] * M[j][q] * M[q][q];
-            M[i][j] = s2 * id;
-          }
-      }
-      if (!ok) *flag = 0;
-      else {
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-#pragma unroll
-          for (int q = 0; q < 6; q++)
-            if (q < i) zz[i] -= M[i][q] * zz[q];
-        }
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-          zb[i] = zz[i];
-          b[k0 + i] = zz[i];
-#pragma unroll
-          for (int j = 0; j < 6; j++)
-            if (j <= i) A[(size_t)(k0 + i) * ld + k0 + j] = M[i][j];
-        }
-      }
-    }
-    __syncthreads();
-    if (!*flag) return false;
+  if (wid == 0 && n > 0) {
+    const bool okk = factor(0, zb);
+    if (!okk && lane == 0) *flag = 0;
+  }
+  __syncthreads();
+  if (!*flag) return false;
+  if (dbg) { const long long t = clock64(); t_f0 = t - t_mark; t_mark = t; }
+  for (int k0 = 0, kb = 0; k0 < n; k0 += 6, kb ^= 1) {
+    const double* zk = zb + 8 * kb;
     // panel rows: T_i = A_i,k L_kk^-T  (forward substitution along the row), L_i = T_i / D
     for (int i = k0 + 6 + tid; i < n; i += nt) {
       double* row = A + (size_t)i * ld + k0;
@@ -1337,15 +1410,42 @@ __device__ bool ldlt_solve_cta(double* A, int n, int ld, double* b /*in: rhs, ou
       }
     }
     __syncthreads();
-    // rank-6 trailing update, one warp per row
-    for (int i = k0 + 6 + wid; i < n; i += nw) {
-      double* row = A + (size_t)i * ld;
-      const double l0 = row[k0], l1 = row[k0 + 1], l2 = row[k0 + 2], l3 = row[k0 + 3], l4 = row[k0 + 4], l5 = row[k0 + 5];
-      for (int j = k0 + 6 + lane; j <= i; j += 32)
-        row[j] -= l0 * Tt[j] + l1 * Tt[n + j] + l2 * Tt[2 * n + j] + l3 * Tt[3 * n + j] + l4 * Tt[4 * n + j] + l5 * Tt[5 * n + j];
-      if (lane == 0) b[i] -= l0 * zb[0] + l1 * zb[1] + l2 * zb[2] + l3 * zb[3] + l4 * zb[4] + l5 * zb[5];
+    if (dbg) { const long long t = clock64(); t_pan += t - t_mark; t_mark = t; }
+    if (wid == 0) {
+      // rows of diagonal block k + 1 (they end inside that block), then its factorisation
+      if (k0 + 6 < n) {
+        if (lane < 21) {
+          const int i = k0 + 6 + li, j = k0 + 6 + lj;
+          const double* row = A + (size_t)i * ld;
+          double a2 = 0;
+#pragma unroll
+          for (int c = 0; c < 6; c++) a2 += row[k0 + c] * Tt[(size_t)c * n + j];
+          A[(size_t)i * ld + j] -= a2;
+        } else if (lane >= 26) {
+          const int i = k0 + 6 + (lane - 26);
+          const double* row = A + (size_t)i * ld;
+          double a2 = 0;
+#pragma unroll
+          for (int c = 0; c < 6; c++) a2 += row[k0 + c] * zk[c];
+          b[i] -= a2;
+        }
+        __syncwarp();
+        const bool okk = factor(k0 + 6, zb + 8 * (kb ^ 1));
+        if (!okk && lane == 0) *flag = 0;
+      }
+    } else {
+      // rank-6 trailing update of the rows below block k + 1, one warp per row
+      for (int i = k0 + 12 + (wid - 1); i < n; i += nw - 1) {
+        double* row = A + (size_t)i * ld;
+        const double l0 = row[k0], l1 = row[k0 + 1], l2 = row[k0 + 2], l3 = row[k0 + 3], l4 = row[k0 + 4], l5 = row[k0 + 5];
+        for (int j = k0 + 6 + lane; j <= i; j += 32)
+          row[j] -= l0 * Tt[j] + l1 * Tt[n + j] + l2 * Tt[2 * n + j] + l3 * Tt[3 * n + j] + l4 * Tt[4 * n + j] + l5 * Tt[5 * n + j];
+        if (lane == 0) b[i] -= l0 * zk[0] + l1 * zk[1] + l2 * zk[2] + l3 * zk[3] + l4 * zk[4] + l5 * zk[5];
+      }
     }
     __syncthreads();
+    if (dbg) { const long long t = clock64(); t_upd += t - t_mark; t_mark = t; }
+    if (!*flag) return false;
   }
   for (int i = tid; i < n; i += nt) b[i] /= A[(size_t)i * ld + i];
   __syncthreads();
@@ -1358,6 +1458,7 @@ __device__ bool ldlt_solve_cta(double* A, int n, int ld, double* b /*in: rhs, ou
     }
   }
   __syncthreads();
+  if (dbg) printf("ldlt n=%d cycles: first diag %lld  panels %lld  updates+lookahead %lld  backward %lld\n", n, t_f0, t_pan, t_upd, (long long)clock64() - t_mark);
   return true;
 }
 
@@ -1915,7 +2016,10 @@ __global__ void __launch_bounds__(512) k_solve(BaView v) {
   __shared__ double red[32];
   double* A = SMEM ? smem : (v.solve_scratch + v.w_scratch_off[w]);
   double* rhs = SMEM ? (smem + (size_t)n * n) : (A + (size_t)n * n);
-  double* tmp = rhs + n;  // 6n + 6 doubles
+  double* tmp = rhs + n;  // 6n + 16 doubles
+  long long tk[6] = {0, 0, 0, 0, 0, 0};
+  const bool dbg = v.debug && w == 0 && tid == 0;
+  if (dbg) tk[0] = clock64();
   const int sel = v.w_sel[w];
   bool ok = true;
   if (n > 0) {
@@ -1947,8 +2051,10 @@ __global__ void __launch_bounds__(512) k_solve(BaView v) {
     }
     for (int i = tid; i < n; i += nt) rhs[i] = v.g_bs[6 * (size_t)g0 + i];
     __syncthreads();
-    ok = ldlt_solve_cta(A, n, n, rhs, tmp, &flag);
+    if (dbg) tk[1] = clock64();
+    ok = ldlt_solve_cta(A, n, n, rhs, tmp, &flag, dbg);
     __syncthreads();
+    if (dbg) tk[2] = clock64();
     if (ok)
       for (int i = tid; i < n; i += nt) v.g_x[6 * (size_t)g0 + i] = rhs[i];
     __syncthreads();
@@ -1974,6 +2080,7 @@ __global__ void __launch_bounds__(512) k_solve(BaView v) {
     for (int q = 0; q < 12; q++) dr[q] = Rt[q];
   }
   // scale contribution of the poses: sum x (lambda x + b)   (computeScale, levenberg.cpp:182-189)
+  if (dbg) tk[3] = clock64();
   const double lam = v.w_lambda[w];
   double sc = 0;
   for (int i = tid; i < n; i += nt) {
@@ -1986,6 +2093,10 @@ __global__ void __launch_bounds__(512) k_solve(BaView v) {
   if (tid == 0) {
     v.w_scale_p[w] = sc;
     v.w_ok[w] = ok ? 1 : 0;
+  }
+  if (dbg) {
+    tk[4] = clock64();
+    printf("k_solve n=%d cycles: assemble %lld  ldlt %lld  pose %lld  scale %lld\n", n, tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3]);
   }
 }
 
@@ -2137,15 +2248,40 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_lines(BaView v) {
   const double* Dp = v.dense_mode ? v.lns_D + 14 * (size_t)v.ln_spos[lc] : v.ln_D + 14 * (size_t)lc;
   double s4[4] = {0, 0, 0, 0};
   const int c0 = v.ln_obs_off[lc], c1 = v.ln_obs_off[lc + 1];
-  for (int c = c0 + gl; c < c1 && run && active; c += LN_G) {
-    const int pos = v.dense_mode ? v.lc_wpos[c] : v.lc_pos[c];
-    if (pos < 0) continue;
-    const double* W = v.dense_mode ? v.lc_Wl + 24 * (size_t)pos : v.L_rec + 38 * (size_t)pos;
-    const double* xp = v.g_x + 6 * (size_t)v.kf_g[v.lc_kf[c]];
+  {
+    const int* cpos = v.dense_mode ? v.lc_wpos : v.lc_pos;
+    const bool go = run && active;
+    // (W slot, update block) of the cell one ahead of the arithmetic
+    int c = c0 + gl, pos = -1, g = 0;
+    if (c < c1 && go) {
+      pos = cpos[c];
+      g = v.kf_g[v.lc_kf[c]];
+    }
+    while (c < c1 && go) {
+      const int cn = c + LN_G;
+      int pos_n = -1, g_n = 0;
+      if (cn < c1) {
+        pos_n = cpos[cn];
+        g_n = v.kf_g[v.lc_kf[cn]];
+      }
+      if (pos >= 0) {
+        const double2* wp = reinterpret_cast<const double2*>(v.dense_mode ? v.lc_Wl + 24 * (size_t)pos : v.L_rec + 38 * (size_t)pos);
+        double W[24];
 #pragma unroll
-    for (int r = 0; r < 6; r++) {
-      const double x = xp[r];
-      s4[0] += W[4 * r] * x; s4[1] += W[4 * r + 1] * x; s4[2] += W[4 * r + 2] * x; s4[3] += W[4 * r + 3] * x;
+        for (int k = 0; k < 12; k++) {
+          const double2 t2 = wp[k];
+          W[2 * k] = t2.x; W[2 * k + 1] = t2.y;
+        }
+        const double2* xp2 = reinterpret_cast<const double2*>(v.g_x + 6 * (size_t)g);
+        const double2 x01 = xp2[0], x23 = xp2[1], x45 = xp2[2];
+        const double xp[6] = {x01.x, x01.y, x23.x, x23.y, x45.x, x45.y};
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+          const double x = xp[r];
+          s4[0] += W[4 * r] * x; s4[1] += W[4 * r + 1] * x; s4[2] += W[4 * r + 2] * x; s4[3] += W[4 * r + 3] * x;
+        }
+      }
+      c = cn; pos = pos_n; g = g_n;
     }
   }
 #pragma unroll
