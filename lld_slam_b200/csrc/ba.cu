@@ -24,6 +24,7 @@
 
 using namespace lld;
 
+static const int CHUNK_DENSE = 512;
 static const int CHUNK = 256;          // edge-list entries per chunk (k_lin_poses / k_schur_rows CTA)
 static const int SMEM_SOLVE_MAX_N = 156;  // dense LDL^T in shared memory up to this dimension (26 free KFs)
 
@@ -667,7 +668,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   stage("dense slots/pieces/gather");
   // chunks + segments (runs of entries whose table rows have the same -1 pattern)
   const long long n_list_total = (long long)n_plist + n_llist;
-  int CH = CHUNK;
+  int CH = dense ? CHUNK_DENSE : CHUNK;   // dense mode: the chunk is only the pose pass's reduction unit, longer amortises the CTA sum
   while (CH > 32 && n_list_total / CH < 2 * (long long)c->sm_count) CH >>= 1;
   auto& ch_g = H.ch_g; auto& ch_begin = H.ch_begin; auto& ch_end = H.ch_end; auto& ch_seg0 = H.ch_seg0;
   auto& seg_begin = H.seg_begin; auto& seg_end = H.seg_end; auto& g_chp0 = H.g_chp0; auto& g_chl0 = H.g_chl0;
@@ -763,7 +764,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   for (int w = 0; w < nw; w++) {
     const long long n = 6LL * (w_g0[w + 1] - w_g0[w]);
     w_scr[w] = scr_total;
-    if (S->max_n > SMEM_SOLVE_MAX_N && !v.env_mode) scr_total += n * n + 8 * n + 24;
+    if (S->max_n > SMEM_SOLVE_MAX_N && !v.env_mode) scr_total += n * n + 8 * n + 40;
   }
 
   stage("chunks");
@@ -909,7 +910,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   if (v.env_mode && S->use_band) LLD_CUDA(c, lld_raise_dyn_smem(k_solve_band<512>, (size_t)(int)S->band_smem) != cudaSuccess ? cudaErrorInvalidValue : lld_raise_dyn_smem(k_solve_band<1024>, (size_t)(int)S->band_smem));
   else if (v.env_mode) LLD_CUDA(c, lld_raise_dyn_smem(k_solve_env, (size_t)(int)S->env_smem));
   else if (S->max_n <= SMEM_SOLVE_MAX_N)
-    LLD_CUDA(c, lld_raise_dyn_smem(k_solve<true>, (size_t)(int)(sizeof(double) * ((size_t)S->max_n * S->max_n + 8 * (size_t)S->max_n + 24))));
+    LLD_CUDA(c, lld_raise_dyn_smem(k_solve<true>, (size_t)(int)(sizeof(double) * ((size_t)S->max_n * S->max_n + 8 * (size_t)S->max_n + 40))));
   return LLD_OK;
 }
 
@@ -977,7 +978,7 @@ static int ba_allreduce_rows(LldCtx* c) {
 
 template <bool SMEM>
 static int launch_solve(LldCtx* c, BaView& v, int max_n) {
-  size_t smem = SMEM ? sizeof(double) * ((size_t)max_n * max_n + 8 * (size_t)max_n + 24) : 0;
+  size_t smem = SMEM ? sizeof(double) * ((size_t)max_n * max_n + 8 * (size_t)max_n + 40) : 0;
   LLD_LAUNCH(c, k_solve<SMEM>, v.n_win, 512, smem, v);
   return LLD_OK;
 }

@@ -412,8 +412,8 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_poses(BaView v) {
   const int w = v.kf_win[kf];
   if (v.w_phase[w] != PH_LIN) return;
   const int sel = v.w_sel[w];
+  __shared__ double tr[28][LM_TPB + 1];        // per-thread partials, transposed (row stride 129: conflict-free)
   __shared__ double part[LM_TPB / 32][28];
-  __shared__ double red[28];
   const double* Rt = v.pose_Rt[sel] + 12 * (size_t)kf;
   const double* intr = v.kf_intr + 5 * (size_t)kf;
   const double* cam = v.kf_lcam + 4 * (size_t)kf;
@@ -498,8 +498,24 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_poses(BaView v) {
       }
     }
   }
-  block_reduce_nv<28>(acc, part, red);
-  if (threadIdx.x < 28) v.ch_pose[28 * (size_t)ch + threadIdx.x] = red[threadIdx.x];
+  // fixed-order sum over the CTA through shared memory: 28 stores + 32 loads per thread instead of 28 five-step shuffle trees
+#pragma unroll
+  for (int k = 0; k < 28; k++) tr[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < 28 * (LM_TPB / 32)) {
+    const int k = threadIdx.x % 28, q = threadIdx.x / 28;
+    double s2 = 0;
+#pragma unroll 8
+    for (int t = 0; t < 32; t++) s2 += tr[k][32 * q + t];
+    part[q][k] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 28) {
+    double s2 = 0;
+#pragma unroll
+    for (int q = 0; q < LM_TPB / 32; q++) s2 += part[q][threadIdx.x];
+    v.ch_pose[28 * (size_t)ch + threadIdx.x] = s2;
+  }
 }
 
 // sum the chunk partials of each free keyframe (fixed order)
@@ -1334,51 +1350,79 @@ __global__ void __launch_bounds__(256) k_reduce_piece_warp(BaView v, int n_block
 // stands in for LinearSolverEigen / LinearSolverDense (Thirdparty/g2o/g2o/solvers/*.h); failure = zero or
 // non-finite pivot.
 // ------------------------------------------------------------------------------------------------
+// reciprocal for the pivot chain of the small LDL^T factorisations: MUFU seed (~20 bits) + two Newton steps (<= 1 ulp),
+// a third of the latency of the IEEE division sequence; zero / non-finite pivots are rejected by the caller beforehand
+__device__ __forceinline__ double rcp_newton(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
 // Blocked (6-column supernode) LDL^T of the reduced camera system by one CTA, diagonal blocks factored one pivot ahead:
-//   (0) warp 0 factors diagonal block 0 (lanes 0..20 = lower-triangle entries, pivots broadcast by shuffles) and
-//       forward-solves its rhs block;
+//   (0) warp 0 factors diagonal block 0: lanes 0..20 hold the lower-triangle entries, lanes 21..26 the rhs block as a
+//       seventh row (its elimination is the forward substitution), pivots are broadcast by shuffles;
 //   per block column k:
-//   (1) one thread per row below solves its 1x6 panel row  T = A_ik L_kk^-T  and  L = T D^-1,
+//   (1) one thread per row below solves its 1x6 panel row  T = A_ik L_kk^-T  and  L = T D^-1  (L_kk and D^-1 in registers),
 //   (2) rank-6 trailing update  A_ij -= sum_c L_ic T_jc,  b_i -= sum_c L_ic z_c : warp 0 takes the six rows of
-//       diagonal block k + 1 and factors it at once (the ~900-cycle dependent chain of the 6x6 LDL^T runs under the
-//       other warps' update instead of between two barriers), the other warps take one row each.
-// n is a multiple of 6.  tmp: >= 6 n + 16 doubles (T transposed [6][n] + z[2][8]).
-__device__ bool ldlt_solve_cta(double* A, int n, int ld, double* b /*in: rhs, out: x*/, double* tmp, int* flag, bool dbg = false) {
+//       diagonal block k + 1 and factors it at once (the dependent chain of the 6x6 LDL^T runs under the other warps'
+//       update instead of between two barriers), the other warps take one row each;
+//   backward substitution by 6-column blocks in one warp (6x6 triangle by shuffles, one shared-memory round trip per block).
+// n is a multiple of 6.  tmp: >= 6 n + 32 doubles (T transposed [6][n] + {z[6], 1/D[6]} x 2).
+__device__ bool ldlt_solve_cta(double* __restrict__ A, int n, int ld, double* __restrict__ b /*in: rhs, out: x*/, double* __restrict__ tmp, int* flag) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
   double* Tt = tmp;          // [6][n]
-  double* zb = tmp + 6 * n;  // [2][8]
-  long long t_pan = 0, t_upd = 0, t_mark = 0, t_f0 = 0;
-  if (dbg) t_mark = clock64();
-  int li = 0, lj = lane;     // lanes 0..20: entry (li, lj), lj <= li, of a diagonal block
+  double* zb = tmp + 6 * n;  // [2][16]: z block at 0..5, 1/D at 8..13
+  int li = 0, lj = lane;     // lanes 0..20: entry (li, lj), lj <= li, of a diagonal block (look-ahead update below)
   while (li < 5 && lj > li) { lj -= li + 1; li++; }
-  // unblocked LDL^T of the 6x6 diagonal block at k0 + forward substitution of its rhs block, by one warp
+  // unblocked right-looking LDL^T of the 6x6 diagonal block at k0 with the rhs block as a seventh row (its elimination
+  // is the forward substitution), in the registers of one thread: the pivot chain is reciprocal -> multiply -> fma per
+  // pivot with no shuffle or shared-memory round trip in between (a lane-parallel variant measured 300 cycles / pivot)
   auto factor = [&](int k0, double* zq) -> bool {
-    double m = lane < 21 ? A[(size_t)(k0 + li) * ld + k0 + lj] : 0.0;
-    double zz = lane < 6 ? b[k0 + lane] : 0.0;
     bool okk = true;
+    if (lane == 0) {
+      double M[7][6];
 #pragma unroll
-    for (int pv = 0; pv < 6; pv++) {
-      const double d = __shfl_sync(0xffffffffu, m, pv * (pv + 1) / 2 + pv);
-      if (!(d != 0.0) || !isfinite(d)) okk = false;
-      const double id = 1.0 / d;
-      const double tip = __shfl_sync(0xffffffffu, m, li * (li + 1) / 2 + pv);   // T(i, pv), used when li > pv
-      const double tjp = __shfl_sync(0xffffffffu, m, lj * (lj + 1) / 2 + pv);   // T(j, pv), used when lj > pv
-      if (lane < 21 && lj > pv) m -= (tip * id) * tjp;
-      if (lane < 21 && lj == pv && li > pv) m *= id;
-    }
+      for (int i = 0; i < 6; i++)
 #pragma unroll
-    for (int pv = 0; pv < 5; pv++) {   // L z = b
-      const double zp = __shfl_sync(0xffffffffu, zz, pv);
-      const double lip = __shfl_sync(0xffffffffu, m, (lane < 6 ? lane * (lane + 1) / 2 : 0) + pv);
-      if (lane < 6 && lane > pv) zz -= lip * zp;
+        for (int j = 0; j < 6; j++)
+          if (j <= i) M[i][j] = A[(size_t)(k0 + i) * ld + k0 + j];
+#pragma unroll
+      for (int j = 0; j < 6; j++) M[6][j] = b[k0 + j];
+      double inv[6];
+#pragma unroll
+      for (int pv = 0; pv < 6; pv++) {
+        const double d = M[pv][pv];
+        if (!(d != 0.0) || !isfinite(d)) okk = false;
+        const double id = rcp_newton(d);
+        inv[pv] = id;
+#pragma unroll
+        for (int i = 0; i < 7; i++)
+          if (i > pv) {
+            const double l = M[i][pv] * id;
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+              if (k > pv && k <= i) M[i][k] -= l * M[k][pv];   // T(k, pv) is still unscaled: rows are scaled after use
+          }
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+          if (i > pv) M[i][pv] *= id;
+      }
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+#pragma unroll
+        for (int j = 0; j < 6; j++)
+          if (j <= i) A[(size_t)(k0 + i) * ld + k0 + j] = M[i][j];
+        zq[8 + i] = inv[i];
+        zq[i] = M[6][i];
+        b[k0 + i] = M[6][i];
+      }
     }
-    if (lane < 21) A[(size_t)(k0 + li) * ld + k0 + lj] = m;
-    if (lane < 6) {
-      zq[lane] = zz;
-      b[k0 + lane] = zz;
-    }
-    return okk;
+    return __shfl_sync(0xffffffffu, okk ? 1 : 0, 0) != 0;
   };
   if (tid == 0) *flag = 1;
   __syncthreads();
@@ -1388,29 +1432,33 @@ __device__ bool ldlt_solve_cta(double* A, int n, int ld, double* b /*in: rhs, ou
   }
   __syncthreads();
   if (!*flag) return false;
-  if (dbg) { const long long t = clock64(); t_f0 = t - t_mark; t_mark = t; }
   for (int k0 = 0, kb = 0; k0 < n; k0 += 6, kb ^= 1) {
-    const double* zk = zb + 8 * kb;
-    // panel rows: T_i = A_i,k L_kk^-T  (forward substitution along the row), L_i = T_i / D
+    const double* zk = zb + 16 * kb;
+    // panel rows: T_i = A_i,k L_kk^-T  (forward substitution along the row), L_i = T_i D^-1
     for (int i = k0 + 6 + tid; i < n; i += nt) {
-      double* row = A + (size_t)i * ld + k0;
-      double t6[6];
+      double Lk[15], invd[6], t6[6];
 #pragma unroll
-      for (int c = 0; c < 6; c++) {
-        double s2 = row[c];
+      for (int c = 1; c < 6; c++)
 #pragma unroll
         for (int q = 0; q < 6; q++)
-          if (q < c) s2 -= t6[q] * A[(size_t)(k0 + c) * ld + k0 + q];
-        t6[c] = s2;
-      }
+          if (q < c) Lk[c * (c - 1) / 2 + q] = A[(size_t)(k0 + c) * ld + k0 + q];
+#pragma unroll
+      for (int c = 0; c < 6; c++) invd[c] = zk[8 + c];
+      double* row = A + (size_t)i * ld + k0;
+#pragma unroll
+      for (int c = 0; c < 6; c++) t6[c] = row[c];
+#pragma unroll
+      for (int c = 1; c < 6; c++)
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+          if (q < c) t6[c] -= t6[q] * Lk[c * (c - 1) / 2 + q];
 #pragma unroll
       for (int c = 0; c < 6; c++) {
         Tt[(size_t)c * n + i] = t6[c];
-        row[c] = t6[c] / A[(size_t)(k0 + c) * ld + k0 + c];
+        row[c] = t6[c] * invd[c];
       }
     }
     __syncthreads();
-    if (dbg) { const long long t = clock64(); t_pan += t - t_mark; t_mark = t; }
     if (wid == 0) {
       // rows of diagonal block k + 1 (they end inside that block), then its factorisation
       if (k0 + 6 < n) {
@@ -1421,8 +1469,8 @@ __device__ bool ldlt_solve_cta(double* A, int n, int ld, double* b /*in: rhs, ou
 #pragma unroll
           for (int c = 0; c < 6; c++) a2 += row[k0 + c] * Tt[(size_t)c * n + j];
           A[(size_t)i * ld + j] -= a2;
-        } else if (lane >= 26) {
-          const int i = k0 + 6 + (lane - 26);
+        } else if (lane < 27) {
+          const int i = k0 + 6 + (lane - 21);
           const double* row = A + (size_t)i * ld;
           double a2 = 0;
 #pragma unroll
@@ -1430,7 +1478,7 @@ __device__ bool ldlt_solve_cta(double* A, int n, int ld, double* b /*in: rhs, ou
           b[i] -= a2;
         }
         __syncwarp();
-        const bool okk = factor(k0 + 6, zb + 8 * (kb ^ 1));
+        const bool okk = factor(k0 + 6, zb + 16 * (kb ^ 1));
         if (!okk && lane == 0) *flag = 0;
       }
     } else {
@@ -1444,21 +1492,37 @@ __device__ bool ldlt_solve_cta(double* A, int n, int ld, double* b /*in: rhs, ou
       }
     }
     __syncthreads();
-    if (dbg) { const long long t = clock64(); t_upd += t - t_mark; t_mark = t; }
     if (!*flag) return false;
   }
   for (int i = tid; i < n; i += nt) b[i] /= A[(size_t)i * ld + i];
   __syncthreads();
-  // backward: L^T x = z, one warp
+  // backward: L^T x = D^-1 z by 6-column blocks, one warp
   if (wid == 0) {
-    for (int j = n - 1; j >= 0; j--) {
-      const double xj = b[j];
-      for (int i = lane; i < j; i += 32) b[i] -= A[(size_t)j * ld + i] * xj;
+    for (int k0 = n - 6; k0 >= 0; k0 -= 6) {
+      // lane c < 6: x_c = z_c - sum_{q > c} L(k0 + q, k0 + c) x_q
+      double z = lane < 6 ? b[k0 + lane] : 0.0;
+      double Lc[5];
+#pragma unroll
+      for (int q = 1; q < 6; q++) Lc[q - 1] = (lane < q) ? A[(size_t)(k0 + q) * ld + k0 + lane] : 0.0;
+#pragma unroll
+      for (int q = 5; q >= 1; q--) {
+        const double xq = __shfl_sync(0xffffffffu, z, q);
+        z -= Lc[q - 1] * xq;   // lanes >= q hold Lc = 0
+      }
+      double x6[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) x6[c] = __shfl_sync(0xffffffffu, z, c);
+      if (lane < 6) b[k0 + lane] = z;
+      for (int i = lane; i < k0; i += 32) {
+        double a2 = 0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) a2 += A[(size_t)(k0 + c) * ld + i] * x6[c];
+        b[i] -= a2;
+      }
       __syncwarp();
     }
   }
   __syncthreads();
-  if (dbg) printf("ldlt n=%d cycles: first diag %lld  panels %lld  updates+lookahead %lld  backward %lld\n", n, t_f0, t_pan, t_upd, (long long)clock64() - t_mark);
   return true;
 }
 
@@ -2017,27 +2081,40 @@ __global__ void __launch_bounds__(512) k_solve(BaView v) {
   double* A = SMEM ? smem : (v.solve_scratch + v.w_scratch_off[w]);
   double* rhs = SMEM ? (smem + (size_t)n * n) : (A + (size_t)n * n);
   double* tmp = rhs + n;  // 6n + 16 doubles
-  long long tk[6] = {0, 0, 0, 0, 0, 0};
-  const bool dbg = v.debug && w == 0 && tid == 0;
-  if (dbg) tk[0] = clock64();
   const int sel = v.w_sel[w];
   bool ok = true;
   if (n > 0) {
-    for (int idx = tid; idx < n * n; idx += nt) A[idx] = 0.0;
-    __syncthreads();
     if (v.dense_mode) {
-      // local BA: block row a of the window holds blocks (a, a..nf-1) at nb_off[g0] + a nf - a (a - 1) / 2: one flat sweep,
-      // no per-row dependent loads of the neighbour lists (this kernel is pure latency for a single window)
-      const int base = v.nb_off[g0], nblk = nf * (nf + 1) / 2;
-      for (int idx = tid; idx < nblk * 36; idx += nt) {
-        const int blk = idx / 36, rc = idx - 36 * blk, r = rc / 6, c = rc - 6 * r;
-        int a = 0, off = 0;
-        while (off + (nf - a) <= blk) { off += nf - a; a++; }
-        const int j = blk - off, b = a + j;
-        if (j == 0 && c < r) continue;  // diagonal block: keep one triangle
-        A[(size_t)(6 * b + c) * n + (6 * a + r)] = v.S_blk[36 * (size_t)(base + blk) + rc];
+      // local BA: every block (a, b >= a) exists, block row a starts at nb_off[g0] + a nf - a (a - 1) / 2; nothing to
+      // zero (the factorisation reads the lower triangle only)
+      const int base = v.nb_off[g0], tot = 36 * (nf * (nf + 1) / 2);
+      const double* Sg = v.S_blk + 36 * (size_t)base;
+      // coalesced sweep, eight loads in flight per thread before the first store (A may alias S_blk for the compiler);
+      // the (a, j) of a thread's elements is found incrementally (their block index only grows)
+      int a = 0, off = 0;
+      for (int i0 = tid; i0 < tot; i0 += 8 * nt) {
+        double val[8];
+        int dst[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int idx = i0 + u * nt;
+          dst[u] = -1;
+          val[u] = 0.0;
+          if (idx < tot) {
+            const int blk = idx / 36, rc = idx - 36 * blk, r = rc / 6, c = rc - 6 * r;
+            while (off + (nf - a) <= blk) { off += nf - a; a++; }
+            const int j = blk - off;
+            if (!(j == 0 && c < r)) dst[u] = (6 * (a + j) + c) * n + (6 * a + r);   // diagonal block: keep one triangle
+            val[u] = Sg[idx];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          if (dst[u] >= 0) A[dst[u]] = val[u];
       }
     } else {
+      for (int idx = tid; idx < n * n; idx += nt) A[idx] = 0.0;
+      __syncthreads();
       for (int a = 0; a < nf; a++) {
         const int g = g0 + a;
         const int nb0 = v.nb_off[g], nnb = v.nb_off[g + 1] - nb0;
@@ -2051,10 +2128,8 @@ __global__ void __launch_bounds__(512) k_solve(BaView v) {
     }
     for (int i = tid; i < n; i += nt) rhs[i] = v.g_bs[6 * (size_t)g0 + i];
     __syncthreads();
-    if (dbg) tk[1] = clock64();
-    ok = ldlt_solve_cta(A, n, n, rhs, tmp, &flag, dbg);
+    ok = ldlt_solve_cta(A, n, n, rhs, tmp, &flag);
     __syncthreads();
-    if (dbg) tk[2] = clock64();
     if (ok)
       for (int i = tid; i < n; i += nt) v.g_x[6 * (size_t)g0 + i] = rhs[i];
     __syncthreads();
@@ -2080,7 +2155,6 @@ __global__ void __launch_bounds__(512) k_solve(BaView v) {
     for (int q = 0; q < 12; q++) dr[q] = Rt[q];
   }
   // scale contribution of the poses: sum x (lambda x + b)   (computeScale, levenberg.cpp:182-189)
-  if (dbg) tk[3] = clock64();
   const double lam = v.w_lambda[w];
   double sc = 0;
   for (int i = tid; i < n; i += nt) {
@@ -2093,10 +2167,6 @@ __global__ void __launch_bounds__(512) k_solve(BaView v) {
   if (tid == 0) {
     v.w_scale_p[w] = sc;
     v.w_ok[w] = ok ? 1 : 0;
-  }
-  if (dbg) {
-    tk[4] = clock64();
-    printf("k_solve n=%d cycles: assemble %lld  ldlt %lld  pose %lld  scale %lld\n", n, tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3]);
   }
 }
 
