@@ -189,6 +189,8 @@ def kernel_bytes(name, p):
         # dense-mode Schur complement by co-visibility class: every W block and every landmark inverse record once
         "k_schur_piece<3>": n_pw * 144 + P * 80,
         "k_schur_piece<4>": n_lw * 192 + L * 112,
+        "k_schur_tile<3>": n_pw * 144 + P * 80,
+        "k_schur_tile<4>": n_lw * 192 + L * 112,
         "k_schur_rows": n_pe * (144 + 144) + n_lc * (192 + 192) + nw * 8 * 36 * nf * (nf + 1) / 2,
         "k_backsub_points<1>": n_pw * 144 + n_pe * (24 + 8) + P * (24 + 24 + 80),
         "k_backsub_points<4>": n_pw * 144 + n_pe * (24 + 8) + P * (24 + 24 + 80),
@@ -331,7 +333,7 @@ def main():
         traffic = json.load(open(tpath)).get("batched_local_ba_64", {}).get(top_name.strip("()"))
     roofline = {"bound": "hbm", "kernel": top_name, "share_of_step": top_ms / tot_ms if tot_ms else None,
                 "avg_launch_us": 1e3 * top_ms / max(top_n, 1), "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
-                "traffic": traffic, "traffic_source": "ncu --set full capture, profiles/r1j_ba_kernels_full.txt" if traffic else None}
+                "traffic": traffic, "traffic_source": "ncu --set full capture, profiles/r1p_ba_kernels_full.txt" if traffic else None}
     if kb:
         ach = kb / (1e-3 * top_ms / max(top_n, 1)) / 1e9
         roofline.update({"achieved": ach, "frac": ach / hbm_peak, "algorithmic_bytes_per_launch": kb})

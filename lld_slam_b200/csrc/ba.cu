@@ -1323,6 +1323,7 @@ static int ba_local_pipelined(LldCtx* c, const lld_ba_problem* p, int its1, int 
   std::atomic<int> next{0}, rc{0};
   std::atomic<long long> launches{0}, h2d{0}, d2h{0};
   auto t0 = std::chrono::steady_clock::now();
+  static const bool timing = getenv("LLD_TIMING") != nullptr;
   auto worker = [&](int wi) {
     LldCtx* cc = c->child[wi];
     cc->prof_on = false;
@@ -1355,7 +1356,23 @@ static int ba_local_pipelined(LldCtx* c, const lld_ba_problem* p, int its1, int 
       so.lambda_log = out->lambda_log ? out->lambda_log + ls * w0 : nullptr;
       so.trials_log = out->trials_log ? out->trials_log + ls * w0 : nullptr;
       so.n_iter_done = out->n_iter_done ? out->n_iter_done + 2 * (size_t)w0 : nullptr;
-      const int r = ba_local_single(cc, &sp, its1, its2, stop, &so);
+      int r;
+      if (timing) {  // LLD_TIMING: wall-clock timeline of the sub-batch relative to the call
+        auto ms = [&]() { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+        const float ta = ms();
+        cc->launches = 0;
+        r = lld_ba_upload(cc, &sp, 0, its1 + its2 + 2);
+        const float tb = ms();
+        if (!r) r = cudaEventRecord(cc->ev[1], cc->stream) == cudaSuccess ? LLD_OK : LLD_ERR_CUDA;
+        if (!r) r = lld_ba_run_local(cc, its1, its2, stop);
+        const float tc = ms();
+        if (!r) r = ba_download(cc, &sp, &so, true);
+        const float td = ms();
+        fprintf(stderr, "[lld_ba_local] worker %d sub-batch %d (%d windows): start %.2f  indexed+uploaded %.2f  LM done %.2f  downloaded %.2f ms\n",
+                wi, k, m, ta, tb, tc, td);
+      } else {
+        r = ba_local_single(cc, &sp, its1, its2, stop, &so);
+      }
       if (r) {
         int z = 0;
         if (rc.compare_exchange_strong(z, r)) snprintf(c->err, sizeof(c->err), "%s", cc->err);
