@@ -119,10 +119,10 @@ struct BaHost {
   pvec<int> pl_off, pl_edge, pe_pos, ll_off, ll_cell, lc_pos;
   pvec<int> pt_spos, ln_spos, pts_w0, lns_w0, pe_wpos, lc_wpos;
   pvec<uint32_t> pts_mask, lns_mask;
-  pvec<int> it_piece, it_task0, pc_begin, pc_end, pc_n, gb_off, gv_off;
+  pvec<int> gb_off, gv_off;
   pvec<SchurItem> it_rec, it_tmp;
   std::vector<uint64_t> it_keys;
-  pvec<long long> pc_out, gb_src, gv_src;
+  pvec<long long> gb_src, gv_src;
   std::vector<BaDenseJob> jobs;
   pvec<int> ch_g, ch_begin, ch_end, ch_seg0, seg_begin, seg_end, g_chp0, g_chl0;
   pvec<long long> ch_S_off;
@@ -496,16 +496,14 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   // dense-mode structures
   auto& pt_spos = H.pt_spos; auto& ln_spos = H.ln_spos; auto& pts_w0 = H.pts_w0; auto& lns_w0 = H.lns_w0;
   auto& pts_mask = H.pts_mask; auto& lns_mask = H.lns_mask; auto& pe_wpos = H.pe_wpos; auto& lc_wpos = H.lc_wpos;
-  auto& it_piece = H.it_piece; auto& it_task0 = H.it_task0; auto& pc_begin = H.pc_begin; auto& pc_end = H.pc_end; auto& pc_n = H.pc_n;
-  auto& gb_off = H.gb_off; auto& gv_off = H.gv_off; auto& pc_out = H.pc_out; auto& gb_src = H.gb_src; auto& gv_src = H.gv_src;
+  auto& gb_off = H.gb_off; auto& gv_off = H.gv_off; auto& gb_src = H.gb_src; auto& gv_src = H.gv_src;
   pt_spos.resize(std::max(n_pt, 1)); ln_spos.resize(std::max(n_ln, 1)); pts_w0.resize(n_pt + 1); lns_w0.resize(n_ln + 1);
   pts_w0[0] = 0; lns_w0[0] = 0;
   pts_mask.resize(std::max(n_pt, 1)); lns_mask.resize(std::max(n_ln, 1));
   pe_wpos.resize(std::max(n_pe, 1)); lc_wpos.resize(std::max(n_lc, 1));   // -1 for fixed-keyframe edges is written below / not read otherwise
-  it_piece.clear(); it_task0.clear(); pc_begin.clear(); pc_end.clear(); pc_n.clear(); pc_out.clear();
   gb_off.assign(1, 0); gv_off.assign(1, 0); gb_src.assign(1, 0); gv_src.assign(1, 0);
   long long dpart_total = 0;
-  int n_items_pt = 0;
+  int n_items_pt = 0, n_items_all = 0;
   size_t n_pw = 0, n_lw = 0;
   if (dense) {
     // W slots: landmarks in signature order, each landmark's free edges sorted by keyframe
@@ -538,9 +536,6 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     slots(n_pt, p->pt_off, p->pt_obs_off, pe_kf, pt_order, pt_key, pt_spos, pts_mask, pts_w0, pe_wpos);
     slots(n_ln, p->ln_off, p->ln_obs_off, lc_kf, ln_order, ln_key, ln_spos, lns_mask, lns_w0, lc_wpos);
     n_pw = (size_t)pts_w0[n_pt]; n_lw = (size_t)lns_w0[n_ln];
-    static const bool schur_tile_env = getenv("LLD_SCHUR_TILE") ? atoi(getenv("LLD_SCHUR_TILE")) != 0 : true;
-    const bool schur_tile = schur_tile_env;
-    v.schur_tile = schur_tile ? 1 : 0;
     int PIECE_CAP = 128;  // shorter pieces when the batch is small, so that every SM gets warps
     while (PIECE_CAP > 8 && (long long)(n_pt + n_ln) * 5 / (2 * PIECE_CAP) < 16LL * c->sm_count) PIECE_CAP >>= 1;
     // pieces / items / gather entries: built per (kind, window) with local offsets, merged in order afterwards
@@ -572,11 +567,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
           for (int ia = 0; ia < n; ia++)
             for (int ib = ia; ib < n; ib++, pr++) J.gb.push_back({nb_off[g0 + hl[ia]] + (hl[ib] - hl[ia]), J.dsize + 36LL * pr});
           for (int ia = 0; ia < n; ia++) J.gv.push_back({g0 + hl[ia], J.dsize + 6LL * (6 * npair + ia)});
-          if (schur_tile) {
-            for (int t0 = 0; t0 < 2 * npair + n; t0 += SP_TPB) { J.itp.push_back(pc); J.itt.push_back(t0); }
-          } else {
-            for (int t0 = 0; t0 < ntask; t0 += 32) { J.itp.push_back(pc); J.itt.push_back(t0); }
-          }
+          for (int t0 = 0; t0 < 2 * npair + n; t0 += SP_TPB) { J.itp.push_back(pc); J.itt.push_back(t0); }
           J.dsize += 6LL * ntask;
         }
         b = e;
@@ -584,27 +575,22 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     });
     // merge the per-(kind, window) jobs: serial prefix over the job sizes, everything else per job / per window in parallel
     std::vector<long long> jd(n_jobs + 1, 0);
-    std::vector<int> jp(n_jobs + 1, 0), ji(n_jobs + 1, 0);
+    std::vector<int> ji(n_jobs + 1, 0);
     for (size_t jid = 0; jid < n_jobs; jid++) {
       jd[jid + 1] = jd[jid] + jobs[jid].dsize;
-      jp[jid + 1] = jp[jid] + (int)jobs[jid].pb.size();
       ji[jid + 1] = ji[jid] + (int)jobs[jid].itp.size();
     }
     dpart_total = jd[n_jobs];
     n_items_pt = ji[std::min<size_t>((size_t)nw, n_jobs)];
-    pc_begin.resize(jp[n_jobs]); pc_end.resize(jp[n_jobs]); pc_n.resize(jp[n_jobs]); pc_out.resize(jp[n_jobs]);
-    it_piece.resize(ji[n_jobs]); it_task0.resize(ji[n_jobs]); H.it_rec.resize(std::max(ji[n_jobs], 1));
+    n_items_all = ji[n_jobs];
+    H.it_rec.resize(std::max(ji[n_jobs], 1));
     gb_off.assign(nb_g.size() + 1, 0);
     gv_off.assign(nG + 1, 0);
     par_for((int)n_jobs, [&](int jid) {
       Job& J = jobs[jid];
-      const int pbase = jp[jid], ibase = ji[jid];
-      for (size_t k = 0; k < J.pb.size(); k++) {
-        pc_begin[pbase + k] = J.pb[k]; pc_end[pbase + k] = J.pe[k]; pc_n[pbase + k] = J.pn[k]; pc_out[pbase + k] = J.pout[k] + jd[jid];
-      }
+      const int ibase = ji[jid];
       const int kind = jid / nw, jw = jid % nw;
       for (size_t k = 0; k < J.itp.size(); k++) {
-        it_piece[ibase + k] = J.itp[k] + pbase; it_task0[ibase + k] = J.itt[k];
         const int q = J.itp[k];
         SchurItem& R = H.it_rec[ibase + k];
         R.l0 = J.pb[q]; R.nl = J.pe[q] - J.pb[q]; R.n = J.pn[q]; R.t0 = J.itt[k];
@@ -612,7 +598,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         schur_item_shape(kind == 0 ? 3 : 4, R.n, R.nl, R.t0, &R.lc, &R.S, &R.nchunk);
       }
     });
-    if (schur_tile) {
+    {
       // k_schur_tile's CTAs take items b, b + G, ... : order each kind by decreasing cost and deal the rows in snake
       // order, so that every CTA gets about the same landmark x task volume
       auto& tmp = H.it_tmp; auto& keys = H.it_keys;
@@ -662,7 +648,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     }
   }
   S->gather_long = dense && gb_src.size() > 32 * std::max<size_t>(nb_g.size(), 1);
-  v.n_items = (int)it_piece.size();
+  v.n_items = n_items_all;
   v.n_items_pt = dense ? n_items_pt : 0;
 
   stage("dense slots/pieces/gather");
@@ -809,13 +795,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   UP(tmp_i, lc_wpos.data(), n_lc); v.lc_wpos = tmp_i;
   UP(tmp_i, pt_order.data(), n_pt); v.pt_sorted = tmp_i;
   UP(tmp_i, ln_order.data(), n_ln); v.ln_sorted = tmp_i;
-  UP(tmp_i, it_piece.data(), it_piece.size()); v.it_piece = tmp_i;
-  UP(tmp_i, it_task0.data(), it_task0.size()); v.it_task0 = tmp_i;
-  { SchurItem* tmp_r; UP(tmp_r, H.it_rec.data(), it_piece.size()); v.it_rec = tmp_r; }
-  UP(tmp_i, pc_begin.data(), pc_begin.size()); v.pc_begin = tmp_i;
-  UP(tmp_i, pc_end.data(), pc_end.size()); v.pc_end = tmp_i;
-  UP(tmp_i, pc_n.data(), pc_n.size()); v.pc_n = tmp_i;
-  UP(tmp_l, pc_out.data(), pc_out.size()); v.pc_out = tmp_l;
+  { SchurItem* tmp_r; UP(tmp_r, H.it_rec.data(), (size_t)n_items_all); v.it_rec = tmp_r; }
   UP(tmp_i, gb_off.data(), gb_off.size()); v.gb_off = tmp_i;
   UP(tmp_l, gb_src.data(), gb_src.size()); v.gb_src = tmp_l;
   UP(tmp_i, gv_off.data(), gv_off.size()); v.gv_off = tmp_i;
@@ -1043,11 +1023,9 @@ static int ba_step_forked(LldCtx* c, int round, int stop_now) {
   LLD_CUDA(c, cudaEventRecord(c->ev_fork, s0));
   LLD_CUDA(c, fork(s1));
   if (v.n_pt) LLD_LAUNCH_S(c, s0, k_schur_points, gp, LM_TPB, 0, v);
-  if (nip && v.schur_tile) LLD_LAUNCH_S(c, s0, k_schur_tile<3>, std::min(nip, 4 * c->sm_count), SP_TPB, SP_SMEM_BYTES, v, 0, nip);
-  else if (nip) LLD_LAUNCH_S(c, s0, k_schur_piece<3>, cdiv(nip, 8), 256, 0, v, 0, nip);
+  if (nip) LLD_LAUNCH_S(c, s0, k_schur_tile<3>, std::min(nip, 4 * c->sm_count), SP_TPB, SP_SMEM_BYTES, v, 0, nip);
   if (v.n_ln) LLD_LAUNCH_S(c, s1, k_schur_lines, gl, LM_TPB, 0, v);
-  if (nil && v.schur_tile) LLD_LAUNCH_S(c, s1, k_schur_tile<4>, std::min(nil, 4 * c->sm_count), SP_TPB, SP_SMEM_BYTES, v, nip, nil);
-  else if (nil) LLD_LAUNCH_S(c, s1, k_schur_piece<4>, cdiv(nil, 8), 256, 0, v, nip, nil);
+  if (nil) LLD_LAUNCH_S(c, s1, k_schur_tile<4>, std::min(nil, 4 * c->sm_count), SP_TPB, SP_SMEM_BYTES, v, nip, nil);
   LLD_CUDA(c, join(0));
   const int nblk = (int)S->n_nb_total;
   if (S->gather_long) LLD_LAUNCH_S(c, s0, k_reduce_piece_warp, cdiv(nblk * 6 + v.n_free_total, 8), 256, 0, v, nblk);
@@ -1089,10 +1067,8 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   if (v.n_ln) LLD_LAUNCH(c, k_schur_lines, gl, LM_TPB, 0, v);
   if (v.dense_mode) {
     const int nip = v.n_items_pt, nil = v.n_items - v.n_items_pt;
-    if (nip && v.schur_tile) LLD_LAUNCH(c, k_schur_tile<3>, std::min(nip, 4 * c->sm_count), SP_TPB, SP_SMEM_BYTES, v, 0, nip);
-    else if (nip) LLD_LAUNCH(c, k_schur_piece<3>, cdiv(nip, 8), 256, 0, v, 0, nip);
-    if (nil && v.schur_tile) LLD_LAUNCH(c, k_schur_tile<4>, std::min(nil, 4 * c->sm_count), SP_TPB, SP_SMEM_BYTES, v, nip, nil);
-    else if (nil) LLD_LAUNCH(c, k_schur_piece<4>, cdiv(nil, 8), 256, 0, v, nip, nil);
+    if (nip) LLD_LAUNCH(c, k_schur_tile<3>, std::min(nip, 4 * c->sm_count), SP_TPB, SP_SMEM_BYTES, v, 0, nip);
+    if (nil) LLD_LAUNCH(c, k_schur_tile<4>, std::min(nil, 4 * c->sm_count), SP_TPB, SP_SMEM_BYTES, v, nip, nil);
     const int nblk = (int)S->n_nb_total;
     if (S->gather_long) LLD_LAUNCH(c, k_reduce_piece_warp, cdiv(nblk * 6 + v.n_free_total, 8), 256, 0, v, nblk);
     else LLD_LAUNCH(c, k_reduce_piece, cdiv(nblk * 36 + 6 * v.n_free_total, 256), 256, 0, v, nblk);

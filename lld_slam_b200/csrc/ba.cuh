@@ -98,12 +98,6 @@ struct BaView {
   int n_items;             // warp work items (points first, then lines)
   int n_items_pt;
   const SchurItem* it_rec; // [n_items] self-contained item records (k_schur_tile)
-  const int* it_piece;     // [n_items] piece of the item
-  const int* it_task0;     // [n_items] first task of the item
-  const int* pc_begin;     // [n_pieces] first landmark (sorted position)
-  const int* pc_end;
-  const int* pc_n;         // [n_pieces] free keyframes per landmark (popcount of the mask)
-  const long long* pc_out; // [n_pieces] offset of the piece's task outputs in dpart (6 doubles per task)
   // gather lists for the reduction: per unit (window, block (a,b)) the contributing (piece, pair) outputs
   const int* gb_off;       // [n_blocks_total+1]   blocks in nb order (same indexing as S_blk)
   const long long* gb_src; // dpart offsets of the pair's first task (6 columns x 6 doubles contiguous)
@@ -191,7 +185,6 @@ struct BaView {
   double* band_A;             // [n_free_total][(band_B+1)*36 + 8] band rows in the solver's order (k_band_assemble)
   double* band_L;             // [n_free_total][(band_B+1)][36] column panels: block 0 = L_kk (strict lower) + D (diagonal)
   double* band_z;             // [6 * n_free_total] forward-substituted rhs
-  int schur_tile;             // dense mode: items are (piece, block of SP_TPB half-tile tasks) for k_schur_tile (1) or (piece, 32 column tasks) for k_schur_piece (0)
   int debug;                  // LLD_BAND_DEBUG: the band solver prints its phase cycle counts
   BaParams prm;
 };

@@ -906,99 +906,11 @@ __global__ void k_reduce_rows(BaView v, int with_diag) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// dense mode Schur complement by co-visibility classes.
+// k_schur_tile: dense mode Schur complement by co-visibility classes, staged through shared memory by persistent CTAs.
 // Landmarks are stored in signature order; a "piece" is a run of landmarks seen by exactly the same n free keyframes,
-// with their W blocks contiguous and sorted by keyframe, so every address in the inner loop is affine in the landmark
-// index (no gathers, no tests).  One warp = 32 tasks of one piece; task = (pair (ia, ib) of the piece's keyframes,
-// column c) accumulating  sum_l W_(l,ia) Dinv_l W_(l,ib)[c,:]^T  (6 values) in registers, or one b_schur task per
-// keyframe accumulating  sum_l W_(l,ia) (Dinv_l b_l).  Outputs go to a scratch slot per task; k_reduce_piece sums
-// them per S block in fixed order (block_solver.hpp:381-440 without atomics).
-// ------------------------------------------------------------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(256) k_schur_piece(BaView v, int item_base, int n_items) {
-  constexpr int WS = 6 * D;                       // doubles per W block
-  constexpr int DS = D == 3 ? 10 : 14;            // doubles per landmark inverse record
-  constexpr int OFF_C = D * (D + 1) / 2;
-  const int item = item_base + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (item >= item_base + n_items) return;
-  const int lane = threadIdx.x & 31;
-  const int pc = v.it_piece[item];
-  const int l0 = v.pc_begin[pc], l1 = v.pc_end[pc];
-  const int w = (D == 3 ? v.pt_win : v.ln_win)[(D == 3 ? v.pt_sorted : v.ln_sorted)[l0]];
-  if (v.w_phase[w] == PH_DONE) return;
-  const int n = v.pc_n[pc];
-  const int npair = n * (n + 1) / 2;
-  const int ntask = 6 * npair + n;
-  const int task = v.it_task0[item] + lane;
-  if (task >= ntask) return;
-  const double* Wg = (D == 3 ? v.pe_Wl : v.lc_Wl) + (size_t)(D == 3 ? v.pts_w0 : v.lns_w0)[l0] * WS;
-  const double* Dg = (D == 3 ? v.pts_D : v.lns_D) + (size_t)l0 * DS;
-  double acc[6] = {0, 0, 0, 0, 0, 0};
-  const int nl = l1 - l0;
-  const size_t lstride = (size_t)n * WS;
-  if (task < 6 * npair) {
-    int pr = task / 6, ia = 0;
-    const int c = task - 6 * pr;
-    while (pr >= n - ia) { pr -= n - ia; ia++; }
-    const int ib = ia + pr;
-    const double* Wa = Wg + ia * WS;
-    const double* Wb = Wg + ib * WS + D * c;
-#pragma unroll 2
-    for (int l = 0; l < nl; l++, Wa += lstride, Wb += lstride) {
-      const double* Dv = Dg + (size_t)l * DS;
-      double wb[D], z[D];
-#pragma unroll
-      for (int k = 0; k < D; k++) wb[k] = Wb[k];
-      if (D == 3) {
-        const double2 d01 = *reinterpret_cast<const double2*>(Dv), d23 = *reinterpret_cast<const double2*>(Dv + 2),
-                      d45 = *reinterpret_cast<const double2*>(Dv + 4);
-        z[0] = d01.x * wb[0] + d01.y * wb[1] + d23.x * wb[2];
-        z[1] = d01.y * wb[0] + d23.y * wb[1] + d45.x * wb[2];
-        z[2] = d23.x * wb[0] + d45.x * wb[1] + d45.y * wb[2];
-      } else {
-#pragma unroll
-        for (int r = 0; r < D; r++) {
-          double zz = 0;
-#pragma unroll
-          for (int k = 0; k < D; k++) zz += Dv[r <= k ? u4(r, k) : u4(k, r)] * wb[k];
-          z[r] = zz;
-        }
-      }
-      double wa[WS];
-#pragma unroll
-      for (int k = 0; k < WS; k += 2) {
-        const double2 t2 = *reinterpret_cast<const double2*>(Wa + k);
-        wa[k] = t2.x; wa[k + 1] = t2.y;
-      }
-#pragma unroll
-      for (int r = 0; r < 6; r++) {
-        double a2 = 0;
-#pragma unroll
-        for (int k = 0; k < D; k++) a2 += wa[D * r + k] * z[k];
-        acc[r] += a2;
-      }
-    }
-  } else {
-    const int ia = task - 6 * npair;
-    const double* Wa = Wg + ia * WS;
-    for (int l = 0; l < nl; l++, Wa += lstride) {
-      const double* cv = Dg + (size_t)l * DS + OFF_C;
-#pragma unroll
-      for (int r = 0; r < 6; r++) {
-        double a2 = 0;
-#pragma unroll
-        for (int k = 0; k < D; k++) a2 += Wa[D * r + k] * cv[k];
-        acc[r] += a2;
-      }
-    }
-  }
-  double* out = v.dpart + v.pc_out[pc] + (size_t)task * 6;
-#pragma unroll
-  for (int r = 0; r < 6; r++) out[r] = acc[r];
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_schur_tile: the sums of k_schur_piece, staged through shared memory by persistent CTAs.
+// with their W blocks contiguous and sorted by keyframe.  Per piece: S_(a,b) += sum_l W_(l,a) Dinv_l W_(l,b)^T for every
+// pair a <= b of its keyframes and b_schur_a += sum_l W_(l,a) (Dinv_l b_l); outputs go to a scratch slot per task and
+// k_reduce_piece sums them per S block in fixed order (block_solver.hpp:381-440 without atomics).
 // An item = (piece, block of <= SP_TPB tasks); a task is half of a pair's 6x6 block (6 rows x 3 columns) or one b_schur
 // vector.  Every CTA walks its items (blockIdx.x, + gridDim.x, ...; windows that are done are skipped 32 items at a
 // time) as one stream of landmark chunks: while chunk i is computed, chunk i + 1 (of the same or of the next item) is
