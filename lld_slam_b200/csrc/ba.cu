@@ -366,10 +366,21 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
       const int b = lm_off[w], e = lm_off[w + 1];
       for (int i = b; i < e; i++) key[i] = signature(off, ekf, i, g0, nf);
       if (nf <= 32) {
-        std::vector<uint64_t> packed((size_t)(e - b));
+        // LSD radix sort on the nf mask bits, 8 bits per pass; the low word (window-local index) starts ascending and
+        // the passes are stable, so equal signatures keep the reference's insertion order
+        const int m = e - b;
+        std::vector<uint64_t> packed((size_t)m), tmp((size_t)m);
         for (int i = b; i < e; i++) packed[i - b] = (key[i] << 32) | (uint32_t)(i - b);
-        std::sort(packed.begin(), packed.end());
-        for (int i = b; i < e; i++) order[i] = b + (int)(packed[i - b] & 0xffffffffu);
+        uint64_t* src = packed.data();
+        uint64_t* dst = tmp.data();
+        for (int sh = 32; sh < 32 + nf; sh += 8) {
+          int cnt[257] = {0};
+          for (int i = 0; i < m; i++) cnt[((src[i] >> sh) & 0xffu) + 1]++;
+          for (int q = 0; q < 256; q++) cnt[q + 1] += cnt[q];
+          for (int i = 0; i < m; i++) dst[cnt[(src[i] >> sh) & 0xffu]++] = src[i];
+          std::swap(src, dst);
+        }
+        for (int i = b; i < e; i++) order[i] = b + (int)(src[i - b] & 0xffffffffu);
       } else {
         for (int i = b; i < e; i++) order[i] = i;
         std::stable_sort(order.begin() + b, order.begin() + e, [&](int x, int y) { return key[x] < key[y]; });
@@ -388,22 +399,28 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
                          pvec<int>& l_off, pvec<int>& l_ref, pvec<int>& e_pos) {
     l_off.assign(nG + 1, 0);
     const int n_e = n_lm ? off[n_lm] : 0;
-    par_for(nw, [&](int w) {   // a window's edges only touch the window's own free blocks
+    // a window's edges only touch the window's own free blocks; the counters of neighbouring windows share cache lines
+    // (19 ints per window), so every worker counts in a private array and touches the shared one once per block
+    par_for(nw, [&](int w) {
+      const int g0 = w_g0[w], nf = w_g0[w + 1] - g0;
+      std::vector<int> cnt((size_t)nf, 0);
       for (int e = off[lm_off[w]]; e < off[lm_off[w + 1]]; e++)
-        if (kf_g[ekf[e]] >= 0) l_off[kf_g[ekf[e]] + 1]++;
+        if (kf_g[ekf[e]] >= 0) cnt[kf_g[ekf[e]] - g0]++;
+      for (int j = 0; j < nf; j++) l_off[g0 + j + 1] = cnt[j];
     });
     for (int g = 0; g < nG; g++) l_off[g + 1] += l_off[g];
     l_ref.resize(std::max(l_off[nG], 1));
     e_pos.resize(std::max(n_e, 1));
-    std::vector<int> cur(l_off.begin(), l_off.end() - 1);
     par_for(nw, [&](int w) {
+      const int g0 = w_g0[w], nf = w_g0[w + 1] - g0;
+      std::vector<int> cur(l_off.begin() + g0, l_off.begin() + g0 + nf);
       for (int oi = lm_off[w]; oi < lm_off[w + 1]; oi++) {
         const int i = order[oi];
         for (int e = off[i]; e < off[i + 1]; e++) {
           const int g = kf_g[ekf[e]];
           if (g < 0) { e_pos[e] = -1; continue; }
-          e_pos[e] = cur[g];
-          l_ref[cur[g]++] = e;
+          e_pos[e] = cur[g - g0];
+          l_ref[cur[g - g0]++] = e;
         }
       }
     });
@@ -536,6 +553,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     slots(n_pt, p->pt_off, p->pt_obs_off, pe_kf, pt_order, pt_key, pt_spos, pts_mask, pts_w0, pe_wpos);
     slots(n_ln, p->ln_off, p->ln_obs_off, lc_kf, ln_order, ln_key, ln_spos, lns_mask, lns_w0, lc_wpos);
     n_pw = (size_t)pts_w0[n_pt]; n_lw = (size_t)lns_w0[n_ln];
+    stage("dense: W slots");
     int PIECE_CAP = 128;  // shorter pieces when the batch is small, so that every SM gets warps
     while (PIECE_CAP > 8 && (long long)(n_pt + n_ln) * 5 / (2 * PIECE_CAP) < 16LL * c->sm_count) PIECE_CAP >>= 1;
     // pieces / items / gather entries: built per (kind, window) with local offsets, merged in order afterwards
@@ -573,6 +591,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         b = e;
       }
     });
+    stage("dense: pieces");
     // merge the per-(kind, window) jobs: serial prefix over the job sizes, everything else per job / per window in parallel
     std::vector<long long> jd(n_jobs + 1, 0);
     std::vector<int> ji(n_jobs + 1, 0);
@@ -598,6 +617,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         schur_item_shape(kind == 0 ? 3 : 4, R.n, R.nl, R.t0, &R.lc, &R.S, &R.nchunk);
       }
     });
+    stage("dense: item records");
     {
       // k_schur_tile's CTAs take items b, b + G, ... : order each kind by decreasing cost and deal the rows in snake
       // order, so that every CTA gets about the same landmark x task volume
@@ -608,21 +628,28 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         const int cntk = i1 - i0;
         if (cntk <= 0) return;
         const int G = std::min(cntk, 4 * c->sm_count);
+        // counting sort by quantised cost (descending; 1024 buckets of 32 cost units, equal buckets keep their order)
+        constexpr int NB = 1024;
+        std::vector<int> cnt(NB + 1, 0);
         for (int i = i0; i < i1; i++) {
           const SchurItem& R = H.it_rec[i];
           const int ntask = R.n * (R.n + 1) + R.n;
           const uint64_t cost = 64 + (uint64_t)R.nl * (uint64_t)(std::min(ntask - R.t0, (int)SP_TPB) + R.n + 1);
-          keys[i] = ((~cost) << 24) | (uint64_t)(i - i0);   // ascending key = descending cost, ties by index
+          const int bkt = NB - 1 - (int)std::min<uint64_t>(cost >> 5, NB - 1);
+          keys[i] = (uint64_t)bkt;
+          cnt[bkt + 1]++;
           tmp[i] = R;
         }
-        std::sort(keys.begin() + i0, keys.begin() + i1);
-        for (int k = 0; k < cntk; k++) {
+        for (int q = 0; q < NB; q++) cnt[q + 1] += cnt[q];
+        for (int i = i0; i < i1; i++) {
+          const int k = cnt[(int)keys[i]]++;   // rank in cost order
           const int r = k / G, j = k - r * G, len = std::min(G, cntk - r * G);
           const int pos = (r & 1) ? len - 1 - j : j;
-          H.it_rec[i0 + r * G + pos] = tmp[i0 + (int)(keys[i0 + k] & 0xffffffu)];
+          H.it_rec[i0 + r * G + pos] = tmp[i];
         }
       });
     }
+    stage("dense: item order");
     // a block / keyframe belongs to one window: its contributions come from that window's point job, then its line job
     par_for(nw, [&](int w) {
       for (int kind = 0; kind < 2; kind++) {
@@ -651,7 +678,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   v.n_items = n_items_all;
   v.n_items_pt = dense ? n_items_pt : 0;
 
-  stage("dense slots/pieces/gather");
+  stage("dense: gather lists");
   // chunks + segments (runs of entries whose table rows have the same -1 pattern)
   const long long n_list_total = (long long)n_plist + n_llist;
   int CH = dense ? CHUNK_DENSE : CHUNK;   // dense mode: the chunk is only the pose pass's reduction unit, longer amortises the CTA sum
