@@ -117,7 +117,7 @@ struct BaHost {
   pvec<int> pt_order, ln_order;
   std::vector<uint64_t> pt_key, ln_key;
   pvec<int> pl_off, pl_edge, pe_pos, ll_off, ll_cell, lc_pos;
-  pvec<int> pt_spos, ln_spos, pts_w0, lns_w0, pe_wpos, lc_wpos;
+  pvec<int> pt_spos, ln_spos, pts_w0, lns_w0;
   pvec<uint32_t> pts_mask, lns_mask;
   pvec<int> gb_off, gv_off;
   pvec<SchurItem> it_rec, it_tmp;
@@ -219,6 +219,7 @@ int up(LldCtx* c, T** dst, const T* src, size_t n, size_t* bytes) {
 }
 #define UP(dst, src, n)                                                     \
   do {                                                                      \
+    if (getenv("LLD_UP_TRACE")) fprintf(stderr, "[up] %-28s %10.3f MB\n", #src, (double)(n) * sizeof(*(dst)) / 1e6); \
     int _r = up(c, &(dst), (src), (size_t)(n), &S->h2d_bytes);              \
     if (_r != LLD_OK) return _r;                                            \
   } while (0)
@@ -512,21 +513,20 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   stage("neighbours + tabs");
   // dense-mode structures
   auto& pt_spos = H.pt_spos; auto& ln_spos = H.ln_spos; auto& pts_w0 = H.pts_w0; auto& lns_w0 = H.lns_w0;
-  auto& pts_mask = H.pts_mask; auto& lns_mask = H.lns_mask; auto& pe_wpos = H.pe_wpos; auto& lc_wpos = H.lc_wpos;
+  auto& pts_mask = H.pts_mask; auto& lns_mask = H.lns_mask;
   auto& gb_off = H.gb_off; auto& gv_off = H.gv_off; auto& gb_src = H.gb_src; auto& gv_src = H.gv_src;
   pt_spos.resize(std::max(n_pt, 1)); ln_spos.resize(std::max(n_ln, 1)); pts_w0.resize(n_pt + 1); lns_w0.resize(n_ln + 1);
   pts_w0[0] = 0; lns_w0[0] = 0;
   pts_mask.resize(std::max(n_pt, 1)); lns_mask.resize(std::max(n_ln, 1));
-  pe_wpos.resize(std::max(n_pe, 1)); lc_wpos.resize(std::max(n_lc, 1));   // -1 for fixed-keyframe edges is written below / not read otherwise
   gb_off.assign(1, 0); gv_off.assign(1, 0); gb_src.assign(1, 0); gv_src.assign(1, 0);
   long long dpart_total = 0;
   int n_items_pt = 0, n_items_all = 0;
   size_t n_pw = 0, n_lw = 0;
   if (dense) {
     // W slots: landmarks in signature order, each landmark's free edges sorted by keyframe
-    auto slots = [&](int n_lm, const int* lm_off, const int* off, const pvec<int>& ekf, const pvec<int>& order,
-                     const std::vector<uint64_t>& key, pvec<int>& spos, pvec<uint32_t>& mask,
-                     pvec<int>& w0, pvec<int>& wpos) {
+    // (the W slot of an edge = w0 of its landmark + rank of its keyframe in the mask is derived on the device: k_dense_wpos)
+    auto slots = [&](int n_lm, const int* lm_off, const pvec<int>& order, const std::vector<uint64_t>& key, pvec<int>& spos,
+                     pvec<uint32_t>& mask, pvec<int>& w0) {
       par_for(nw, [&](int w) {
         for (int oi = lm_off[w]; oi < lm_off[w + 1]; oi++) {
           const int i = order[oi];
@@ -536,22 +536,9 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         }
       });
       for (int oi = 0; oi < n_lm; oi++) w0[oi + 1] += w0[oi];
-      par_for(nw, [&](int w) {
-        std::pair<int, int> ge[32];
-        for (int oi = lm_off[w]; oi < lm_off[w + 1]; oi++) {
-          const int i = order[oi];
-          int n = 0;
-          for (int e = off[i]; e < off[i + 1]; e++) {
-            if (kf_g[ekf[e]] >= 0) ge[n++] = {kf_g[ekf[e]], e};
-            else wpos[e] = -1;
-          }
-          std::sort(ge, ge + n);
-          for (int k = 0; k < n; k++) wpos[ge[k].second] = w0[oi] + k;
-        }
-      });
     };
-    slots(n_pt, p->pt_off, p->pt_obs_off, pe_kf, pt_order, pt_key, pt_spos, pts_mask, pts_w0, pe_wpos);
-    slots(n_ln, p->ln_off, p->ln_obs_off, lc_kf, ln_order, ln_key, ln_spos, lns_mask, lns_w0, lc_wpos);
+    slots(n_pt, p->pt_off, pt_order, pt_key, pt_spos, pts_mask, pts_w0);
+    slots(n_ln, p->ln_off, ln_order, ln_key, ln_spos, lns_mask, lns_w0);
     n_pw = (size_t)pts_w0[n_pt]; n_lw = (size_t)lns_w0[n_ln];
     stage("dense: W slots");
     int PIECE_CAP = 128;  // shorter pieces when the batch is small, so that every SM gets warps
@@ -783,15 +770,17 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   stage("chunks");
   // ---- upload (timed as h2d) ----
   UP(tmp_i, kf_win.data(), n_kf); v.kf_win = tmp_i;
-  UP(tmp_i, pt_win.data(), n_pt); v.pt_win = tmp_i;
-  UP(tmp_i, ln_win.data(), n_ln); v.ln_win = tmp_i;
+  // owner arrays (landmark -> window, edge -> landmark) and W slots are derived on the device from the offsets / masks
+  int *d_pt_win, *d_ln_win, *d_pe_pt, *d_lc_ln, *d_pe_wpos, *d_lc_wpos;
+  DEV(d_pt_win, int, n_pt); v.pt_win = d_pt_win;
+  DEV(d_ln_win, int, n_ln); v.ln_win = d_ln_win;
   UP(tmp_i, kf_g.data(), n_kf); v.kf_g = tmp_i;
   UP(tmp_i, g_kf.data(), nG); v.g_kf = tmp_i;
   UP(tmp_i, w_g0.data(), nw + 1); v.w_g0 = tmp_i;
   UP(tmp_i, pe_kf.data(), n_pe); v.pe_kf = tmp_i;
-  UP(tmp_i, pe_pt.data(), n_pe); v.pe_pt = tmp_i;
+  DEV(d_pe_pt, int, n_pe); v.pe_pt = d_pe_pt;
   UP(tmp_i, lc_kf.data(), n_lc); v.lc_kf = tmp_i;
-  UP(tmp_i, lc_ln.data(), n_lc); v.lc_ln = tmp_i;
+  DEV(d_lc_ln, int, n_lc); v.lc_ln = d_lc_ln;
   UP(tmp_i, pl_off.data(), nG + 1); v.pl_off = tmp_i;
   UP(tmp_i, pl_edge.data(), n_plist); v.pl_edge = tmp_i;
   UP(tmp_i, pe_pos.data(), dense ? 0 : n_pe); v.pe_pos = tmp_i;   // list positions are only read outside dense mode
@@ -818,8 +807,8 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   UP(tmp_i, ln_spos.data(), n_ln); v.ln_spos = tmp_i;
   UP(tmp_i, pts_w0.data(), n_pt + 1); v.pts_w0 = tmp_i;
   UP(tmp_i, lns_w0.data(), n_ln + 1); v.lns_w0 = tmp_i;
-  UP(tmp_i, pe_wpos.data(), n_pe); v.pe_wpos = tmp_i;
-  UP(tmp_i, lc_wpos.data(), n_lc); v.lc_wpos = tmp_i;
+  DEV(d_pe_wpos, int, n_pe); v.pe_wpos = d_pe_wpos;
+  DEV(d_lc_wpos, int, n_lc); v.lc_wpos = d_lc_wpos;
   UP(tmp_i, pt_order.data(), n_pt); v.pt_sorted = tmp_i;
   UP(tmp_i, ln_order.data(), n_ln); v.ln_sorted = tmp_i;
   { SchurItem* tmp_r; UP(tmp_r, H.it_rec.data(), (size_t)n_items_all); v.it_rec = tmp_r; }
@@ -908,6 +897,19 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     const bool dense_single = v.dense_mode && !(global_mode && c->n_ranks > 1) && v.n_slices == 1 && S->max_n <= SMEM_SOLVE_MAX_N && !v.env_mode;
     S->forked = allow && dense_single;
     S->use_graph = allow && dense_single;
+  }
+  // derived index arrays (stream-ordered after the uploads, before any consumer)
+  {
+    auto grid = [](int n) { return (n + 255) / 256; };
+    if (n_pt) LLD_LAUNCH(c, k_expand_owner, grid(n_pt), 256, 0, n_pt, nw, v.pt_off, d_pt_win);
+    if (n_ln) LLD_LAUNCH(c, k_expand_owner, grid(n_ln), 256, 0, n_ln, nw, v.ln_off, d_ln_win);
+    if (n_pe) LLD_LAUNCH(c, k_expand_owner, grid(n_pe), 256, 0, n_pe, n_pt, v.pt_obs_off, d_pe_pt);
+    if (n_lc) LLD_LAUNCH(c, k_expand_owner, grid(n_lc), 256, 0, n_lc, n_ln, v.ln_obs_off, d_lc_ln);
+    if (v.dense_mode) {
+      if (n_pe) LLD_LAUNCH(c, k_dense_wpos, grid(n_pe), 256, 0, n_pe, v.pe_pt, v.pe_kf, v.kf_g, v.pt_win, v.w_g0, v.pt_spos, v.pts_mask, v.pts_w0, d_pe_wpos);
+      if (n_lc) LLD_LAUNCH(c, k_dense_wpos, grid(n_lc), 256, 0, n_lc, v.lc_ln, v.lc_kf, v.kf_g, v.ln_win, v.w_g0, v.ln_spos, v.lns_mask, v.lns_w0, d_lc_wpos);
+    }
+    LLD_CUDA(c, cudaGetLastError());
   }
   // dynamic shared memory opt-in of the solvers (once per upload, outside any stream capture)
   if (v.dense_mode) {

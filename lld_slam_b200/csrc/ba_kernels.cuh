@@ -101,6 +101,39 @@ __global__ void k_init_state(BaView v, const double* __restrict__ kf_Tcw, const 
     for (int k = 0; k < 6; k++) v.g_x[6 * (size_t)i + k] = 0.0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// index arrays derived on the device at upload time (nothing to index on the host, nothing to move over PCIe)
+// ------------------------------------------------------------------------------------------------
+// out[e] = the segment i of the CSR offsets off[0..n] that contains e (largest i with off[i] <= e: skips empty segments)
+__global__ void k_expand_owner(int n_out, int n, const int* __restrict__ off, int* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_out) return;
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= e) lo = mid;
+    else hi = mid;
+  }
+  out[e] = lo;
+}
+
+// dense mode: the W blocks of a landmark are contiguous (first slot w0[sorted position]) and sorted by keyframe, so the
+// slot of an edge is w0 + the rank of its keyframe's block among the set bits of the landmark's mask; -1 = fixed keyframe
+__global__ void k_dense_wpos(int n_e, const int* __restrict__ e_lm, const int* __restrict__ e_kf, const int* __restrict__ kf_g,
+                             const int* __restrict__ lm_win, const int* __restrict__ w_g0, const int* __restrict__ spos,
+                             const uint32_t* __restrict__ mask, const int* __restrict__ w0, int* __restrict__ wpos) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_e) return;
+  const int g = kf_g[e_kf[e]];
+  if (g < 0) {
+    wpos[e] = -1;
+    return;
+  }
+  const int lm = e_lm[e], oi = spos[lm];
+  const int bit = g - w_g0[lm_win[lm]];
+  wpos[e] = w0[oi] + __popc(mask[oi] & ((1u << bit) - 1u));
+}
+
 __global__ void k_round_init(BaView v, int maxit, int round) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= v.n_win) return;
