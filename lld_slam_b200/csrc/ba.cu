@@ -194,6 +194,14 @@ void lld_ba_host_free(void* h) { delete reinterpret_cast<BaHost*>(h); }
 
 namespace {
 
+// LLD_UP_TRACE: FNV-1a of an uploaded array (host-stage refactors are checked to produce identical index arrays)
+static unsigned long long up_trace_hash(const void* p, size_t bytes) {
+  unsigned long long h = 1469598103934665603ull;
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  for (size_t i = 0; p && i < bytes; i++) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+
 template <typename T>
 int up(LldCtx* c, T** dst, const T* src, size_t n, size_t* bytes) {
   if (c->host_only) {  // lld_ba_index_only: time / test the host stage without a device
@@ -219,7 +227,8 @@ int up(LldCtx* c, T** dst, const T* src, size_t n, size_t* bytes) {
 }
 #define UP(dst, src, n)                                                     \
   do {                                                                      \
-    if (getenv("LLD_UP_TRACE")) fprintf(stderr, "[up] %-28s %10.3f MB\n", #src, (double)(n) * sizeof(*(dst)) / 1e6); \
+    if (getenv("LLD_UP_TRACE")) fprintf(stderr, "[up] %-28s %10.3f MB  fnv %016llx\n", #src, (double)(n) * sizeof(*(dst)) / 1e6, \
+                                        up_trace_hash((src), (size_t)(n) * sizeof(*(dst))));                \
     int _r = up(c, &(dst), (src), (size_t)(n), &S->h2d_bytes);              \
     if (_r != LLD_OK) return _r;                                            \
   } while (0)
@@ -312,30 +321,34 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   auto& pe_kf = H.pe_kf; auto& pe_pt = H.pe_pt; auto& lc_kf = H.lc_kf; auto& lc_ln = H.lc_ln;
   pe_kf.resize(n_pe); pe_pt.resize(n_pe); lc_kf.resize(n_lc); lc_ln.resize(n_lc);
   std::atomic<int> bad_arg{0};
-  par_for(nw, [&](int w) {
+  // Three per-window passes, run back to back by the same worker while the window's edges are in its cache:
+  //   (1) global keyframe / landmark ids of every edge (+ argument checks),
+  //   (2) co-visibility signature of every landmark (set of free blocks observing it) and the stable signature order:
+  //       landmarks with the same signature are adjacent in every keyframe's list, so k_schur_rows tests "does neighbour j
+  //       see these landmarks" once per segment, and dense mode cuts the order into pieces,
+  //   (3) lengths of the per-free-keyframe edge lists.
+  auto ids_window = [&](int w) -> bool {
+    bool ok = true;
     const int k0 = p->kf_off[w], nk = p->kf_off[w + 1] - k0;
     for (int i = p->pt_off[w]; i < p->pt_off[w + 1]; i++) {
-      if (p->pt_obs_off[i + 1] - p->pt_obs_off[i] > 254) bad_arg = 1;
+      if (p->pt_obs_off[i + 1] - p->pt_obs_off[i] > 254) ok = false;
       for (int e = p->pt_obs_off[i]; e < p->pt_obs_off[i + 1]; e++) {
-        if (p->pt_obs_kf[e] < 0 || p->pt_obs_kf[e] >= nk) { bad_arg = 1; continue; }
+        if (p->pt_obs_kf[e] < 0 || p->pt_obs_kf[e] >= nk) { ok = false; continue; }
         pe_kf[e] = k0 + p->pt_obs_kf[e];
         pe_pt[e] = i;
       }
     }
     for (int i = p->ln_off[w]; i < p->ln_off[w + 1]; i++) {
-      if (p->ln_obs_off[i + 1] - p->ln_obs_off[i] > 254) bad_arg = 1;
+      if (p->ln_obs_off[i + 1] - p->ln_obs_off[i] > 254) ok = false;
       for (int e = p->ln_obs_off[i]; e < p->ln_obs_off[i + 1]; e++) {
-        if (p->ln_obs_kf[e] < 0 || p->ln_obs_kf[e] >= nk) { bad_arg = 1; continue; }
+        if (p->ln_obs_kf[e] < 0 || p->ln_obs_kf[e] >= nk) { ok = false; continue; }
         lc_kf[e] = k0 + p->ln_obs_kf[e];
         lc_ln[e] = i;
       }
     }
-  });
-  LLD_ARG(c, bad_arg.load() == 0);
-  stage("ids");
-  // ---- co-visibility signature of every landmark (set of free blocks observing it) ----
-  // Landmarks with the same signature are made adjacent in every keyframe's list, so k_schur_rows can test
-  // "does neighbour j see these landmarks" once per segment instead of once per entry.
+    if (!ok) bad_arg = 1;
+    return ok;
+  };
   std::atomic<int> dup_free{0};   // a landmark observed twice by the same free keyframe (never happens in the reference)
   auto signature = [&](const int* off, const pvec<int>& ekf, int i, int g0, int nf) -> uint64_t {
     uint64_t key = 0;
@@ -360,7 +373,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   };
   auto& pt_order = H.pt_order; auto& ln_order = H.ln_order; auto& pt_key = H.pt_key; auto& ln_key = H.ln_key;
   pt_order.resize(n_pt); ln_order.resize(n_ln); pt_key.resize(n_pt); ln_key.resize(n_ln);
-  par_for(nw, [&](int w) {
+  auto sort_window = [&](int w) {
     const int g0 = w_g0[w], nf = w_g0[w + 1] - g0;
     // stable order by signature; with <= 32 free keyframes the key and the landmark's window-local index fit one 64-bit word
     auto sort_by_key = [&](const int* lm_off, const int* off, const pvec<int>& ekf, std::vector<uint64_t>& key, pvec<int>& order) {
@@ -389,47 +402,53 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     };
     sort_by_key(p->pt_off, p->pt_obs_off, pe_kf, pt_key, pt_order);
     sort_by_key(p->ln_off, p->ln_obs_off, lc_kf, ln_key, ln_order);
+  };
+  // per-free-keyframe lists (counting sort in signature order), separately for point edges and line cells.  A window's
+  // edges only touch the window's own free blocks; the counters of neighbouring windows share cache lines (19 ints per
+  // window), so every worker counts in a private array and touches the shared one once per block.
+  auto& pl_off = H.pl_off; auto& pl_edge = H.pl_edge; auto& pe_pos = H.pe_pos;
+  auto& ll_off = H.ll_off; auto& ll_cell = H.ll_cell; auto& lc_pos = H.lc_pos;
+  pl_off.assign(nG + 1, 0); ll_off.assign(nG + 1, 0);
+  auto count_window = [&](int w, const int* lm_off, const int* off, const pvec<int>& ekf, pvec<int>& l_off) {
+    const int g0 = w_g0[w], nf = w_g0[w + 1] - g0;
+    std::vector<int> cnt((size_t)nf, 0);
+    for (int e = off[lm_off[w]]; e < off[lm_off[w + 1]]; e++)
+      if (kf_g[ekf[e]] >= 0) cnt[kf_g[ekf[e]] - g0]++;
+    for (int j = 0; j < nf; j++) l_off[g0 + j + 1] = cnt[j];
+  };
+  auto fill_window = [&](int w, const int* lm_off, const int* off, const pvec<int>& ekf, const pvec<int>& order,
+                         const pvec<int>& l_off, pvec<int>& l_ref, pvec<int>& e_pos) {
+    const int g0 = w_g0[w], nf = w_g0[w + 1] - g0;
+    std::vector<int> cur(l_off.begin() + g0, l_off.begin() + g0 + nf);
+    for (int oi = lm_off[w]; oi < lm_off[w + 1]; oi++) {
+      const int i = order[oi];
+      for (int e = off[i]; e < off[i + 1]; e++) {
+        const int g = kf_g[ekf[e]];
+        if (g < 0) { e_pos[e] = -1; continue; }
+        e_pos[e] = cur[g - g0];
+        l_ref[cur[g - g0]++] = e;
+      }
+    }
+  };
+  par_for(nw, [&](int w) {
+    if (!ids_window(w)) return;   // malformed window: rejected below, nothing else may index with its ids
+    sort_window(w);
+    count_window(w, p->pt_off, p->pt_obs_off, pe_kf, pl_off);
+    count_window(w, p->ln_off, p->ln_obs_off, lc_kf, ll_off);
   });
-  stage("signature sort");
+  LLD_ARG(c, bad_arg.load() == 0);
+  stage("ids + signature order + list counts");
   // dense mode: every window small enough to keep its whole S in registers / one edge per (landmark, free KF)
   const bool dense = !global_mode && S->max_n <= 6 * 32 && dup_free.load() == 0;
   LLD_ARG(c, dup_free.load() == 0 || !global_mode);
   v.dense_mode = dense ? 1 : 0;
-  // per-free-keyframe lists (counting sort in signature order), separately for point edges and line cells
-  auto build_lists = [&](int n_lm, const int* lm_off, const int* off, const pvec<int>& ekf, const pvec<int>& order,
-                         pvec<int>& l_off, pvec<int>& l_ref, pvec<int>& e_pos) {
-    l_off.assign(nG + 1, 0);
-    const int n_e = n_lm ? off[n_lm] : 0;
-    // a window's edges only touch the window's own free blocks; the counters of neighbouring windows share cache lines
-    // (19 ints per window), so every worker counts in a private array and touches the shared one once per block
-    par_for(nw, [&](int w) {
-      const int g0 = w_g0[w], nf = w_g0[w + 1] - g0;
-      std::vector<int> cnt((size_t)nf, 0);
-      for (int e = off[lm_off[w]]; e < off[lm_off[w + 1]]; e++)
-        if (kf_g[ekf[e]] >= 0) cnt[kf_g[ekf[e]] - g0]++;
-      for (int j = 0; j < nf; j++) l_off[g0 + j + 1] = cnt[j];
-    });
-    for (int g = 0; g < nG; g++) l_off[g + 1] += l_off[g];
-    l_ref.resize(std::max(l_off[nG], 1));
-    e_pos.resize(std::max(n_e, 1));
-    par_for(nw, [&](int w) {
-      const int g0 = w_g0[w], nf = w_g0[w + 1] - g0;
-      std::vector<int> cur(l_off.begin() + g0, l_off.begin() + g0 + nf);
-      for (int oi = lm_off[w]; oi < lm_off[w + 1]; oi++) {
-        const int i = order[oi];
-        for (int e = off[i]; e < off[i + 1]; e++) {
-          const int g = kf_g[ekf[e]];
-          if (g < 0) { e_pos[e] = -1; continue; }
-          e_pos[e] = cur[g - g0];
-          l_ref[cur[g - g0]++] = e;
-        }
-      }
-    });
-  };
-  auto& pl_off = H.pl_off; auto& pl_edge = H.pl_edge; auto& pe_pos = H.pe_pos;
-  auto& ll_off = H.ll_off; auto& ll_cell = H.ll_cell; auto& lc_pos = H.lc_pos;
-  build_lists(n_pt, p->pt_off, p->pt_obs_off, pe_kf, pt_order, pl_off, pl_edge, pe_pos);
-  build_lists(n_ln, p->ln_off, p->ln_obs_off, lc_kf, ln_order, ll_off, ll_cell, lc_pos);
+  for (int g = 0; g < nG; g++) { pl_off[g + 1] += pl_off[g]; ll_off[g + 1] += ll_off[g]; }
+  pl_edge.resize(std::max(pl_off[nG], 1)); ll_cell.resize(std::max(ll_off[nG], 1));
+  pe_pos.resize(std::max(n_pe, 1)); lc_pos.resize(std::max(n_lc, 1));
+  par_for(nw, [&](int w) {
+    fill_window(w, p->pt_off, p->pt_obs_off, pe_kf, pt_order, pl_off, pl_edge, pe_pos);
+    fill_window(w, p->ln_off, p->ln_obs_off, lc_kf, ln_order, ll_off, ll_cell, lc_pos);
+  });
   const int n_plist = pl_off[nG], n_llist = ll_off[nG];
   stage("kf lists");
   // neighbour lists (block columns >= own row)
