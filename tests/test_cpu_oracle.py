@@ -296,3 +296,35 @@ def test_host_indexing_stage_runs_without_a_device(built):
     bad["pt_obs_kf"][5] = 10 ** 6           # keyframe index outside its window
     bprob, keep3 = capi.fill_struct(capi.BaProblem, bad)
     assert f(C.byref(bprob), 0) == -2       # LLD_ERR_ARG
+
+
+def test_host_indexing_is_deterministic(built, capfd, monkeypatch):
+    """The host stage runs per-window work on a thread pool; every index array it uploads must not depend on the thread
+    schedule: LLD_UP_TRACE prints an FNV hash of each uploaded array, two runs (and a run after an unrelated problem has
+    reused the persistent scratch) must print the same hashes."""
+    import ctypes as C
+    from lld_slam_b200 import capi, synth
+    lib = capi.load_library()
+    f = lib.dll.lld_ba_index_only
+    f.argtypes = [C.POINTER(capi.BaProblem), C.c_int]
+    f.restype = C.c_int
+    monkeypatch.setenv("LLD_UP_TRACE", "1")
+    p = synth.make_local_ba_batch(9, 12, 700, 150, 23)
+    q = synth.make_local_ba_batch(4, 6, 200, 40, 5)
+    prob, keep = capi.fill_struct(capi.BaProblem, p)
+    qrob, keep2 = capi.fill_struct(capi.BaProblem, q)
+
+    def hashes(pr):
+        capfd.readouterr()
+        assert f(C.byref(pr), 0) == 0
+        err = capfd.readouterr().err
+        # arrays that are only sized, not filled, in dense mode (sparse-mode tables) are skipped: their bytes are scratch
+        skip = ("pe_pos", "lc_pos", "pl_tab", "ll_tab")
+        return [ln for ln in err.splitlines() if ln.startswith("[up]") and not any(k in ln for k in skip)]
+
+    a = hashes(prob)
+    assert len(a) > 40
+    b = hashes(prob)
+    hashes(qrob)
+    c2 = hashes(prob)
+    assert a == b == c2
