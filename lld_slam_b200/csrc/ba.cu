@@ -437,6 +437,12 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     count_window(w, p->ln_off, p->ln_obs_off, lc_kf, ll_off);
   });
   LLD_ARG(c, bad_arg.load() == 0);
+  // arrays that are final from here on go to the device now: their DMA (queued behind the caller's raw arrays on the
+  // same stream) runs under the rest of the indexing instead of after it
+  UP(tmp_i, pe_kf.data(), n_pe); v.pe_kf = tmp_i;
+  UP(tmp_i, lc_kf.data(), n_lc); v.lc_kf = tmp_i;
+  UP(tmp_i, pt_order.data(), n_pt); v.pt_sorted = tmp_i;
+  UP(tmp_i, ln_order.data(), n_ln); v.ln_sorted = tmp_i;
   stage("ids + signature order + list counts");
   // dense mode: every window small enough to keep its whole S in registers / one edge per (landmark, free KF)
   const bool dense = !global_mode && S->max_n <= 6 * 32 && dup_free.load() == 0;
@@ -450,6 +456,10 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     fill_window(w, p->ln_off, p->ln_obs_off, lc_kf, ln_order, ll_off, ll_cell, lc_pos);
   });
   const int n_plist = pl_off[nG], n_llist = ll_off[nG];
+  UP(tmp_i, pl_off.data(), nG + 1); v.pl_off = tmp_i;
+  UP(tmp_i, pl_edge.data(), n_plist); v.pl_edge = tmp_i;
+  UP(tmp_i, ll_off.data(), nG + 1); v.ll_off = tmp_i;
+  UP(tmp_i, ll_cell.data(), n_llist); v.ll_cell = tmp_i;
   stage("kf lists");
   // neighbour lists (block columns >= own row)
   std::vector<int> nb_off(nG + 1, 0), nb_g;
@@ -796,15 +806,9 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   UP(tmp_i, kf_g.data(), n_kf); v.kf_g = tmp_i;
   UP(tmp_i, g_kf.data(), nG); v.g_kf = tmp_i;
   UP(tmp_i, w_g0.data(), nw + 1); v.w_g0 = tmp_i;
-  UP(tmp_i, pe_kf.data(), n_pe); v.pe_kf = tmp_i;
   DEV(d_pe_pt, int, n_pe); v.pe_pt = d_pe_pt;
-  UP(tmp_i, lc_kf.data(), n_lc); v.lc_kf = tmp_i;
   DEV(d_lc_ln, int, n_lc); v.lc_ln = d_lc_ln;
-  UP(tmp_i, pl_off.data(), nG + 1); v.pl_off = tmp_i;
-  UP(tmp_i, pl_edge.data(), n_plist); v.pl_edge = tmp_i;
   UP(tmp_i, pe_pos.data(), dense ? 0 : n_pe); v.pe_pos = tmp_i;   // list positions are only read outside dense mode
-  UP(tmp_i, ll_off.data(), nG + 1); v.ll_off = tmp_i;
-  UP(tmp_i, ll_cell.data(), n_llist); v.ll_cell = tmp_i;
   UP(tmp_i, lc_pos.data(), dense ? 0 : n_lc); v.lc_pos = tmp_i;
   UP(tmp_i, ch_g.data(), n_ch); v.ch_g = tmp_i;
   UP(tmp_i, ch_begin.data(), n_ch); v.ch_begin = tmp_i;
@@ -828,8 +832,6 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   UP(tmp_i, lns_w0.data(), n_ln + 1); v.lns_w0 = tmp_i;
   DEV(d_pe_wpos, int, n_pe); v.pe_wpos = d_pe_wpos;
   DEV(d_lc_wpos, int, n_lc); v.lc_wpos = d_lc_wpos;
-  UP(tmp_i, pt_order.data(), n_pt); v.pt_sorted = tmp_i;
-  UP(tmp_i, ln_order.data(), n_ln); v.ln_sorted = tmp_i;
   { SchurItem* tmp_r; UP(tmp_r, H.it_rec.data(), (size_t)n_items_all); v.it_rec = tmp_r; }
   UP(tmp_i, gb_off.data(), gb_off.size()); v.gb_off = tmp_i;
   UP(tmp_l, gb_src.data(), gb_src.size()); v.gb_src = tmp_l;
