@@ -328,3 +328,176 @@ def test_host_indexing_is_deterministic(built, capfd, monkeypatch):
     hashes(qrob)
     c2 = hashes(prob)
     assert a == b == c2
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY §8(f) row 1 (next round's kernel): Frame::ComputeStereoMatches, oracle pinned ahead of the product
+# ------------------------------------------------------------------------------------------------
+def _stereo_frame(seed, n_kp=400, rows=240, cols=376, n_levels=4, sf=1.2):
+    """A textured stereo pair (right = left shifted by a per-band disparity), its pyramids, keypoints at random places
+    with random octaves and ORB-like descriptors (right = left with a few flipped bits; a share are outliers)."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (rows // 4 + 2, (cols + 64) // 4 + 2), dtype=np.uint8)
+    wide = cv2.resize(base, (cols + 64, rows), interpolation=cv2.INTER_CUBIC)
+    left = np.ascontiguousarray(wide[:, 32:32 + cols])
+    disp_of_row = 4 + (np.arange(rows) // 40) * 3            # 4, 7, 10, ... pixels
+    right = np.empty_like(left)
+    for y in range(rows):
+        d = int(disp_of_row[y])
+        right[y] = wide[y, 32 + d:32 + d + cols]             # x_R = x_L - d
+    scale = np.array([sf ** i for i in range(n_levels)], np.float32)
+    inv = (1.0 / scale).astype(np.float32)
+    pyrL, pyrR = [left], [right]
+    for i in range(1, n_levels):
+        sz = (int(round(cols * float(inv[i]))), int(round(rows * float(inv[i]))))
+        pyrL.append(np.ascontiguousarray(cv2.resize(left, sz, interpolation=cv2.INTER_LINEAR)))
+        pyrR.append(np.ascontiguousarray(cv2.resize(right, sz, interpolation=cv2.INTER_LINEAR)))
+    kpL = np.stack([rng.uniform(30, cols - 30, n_kp), rng.uniform(24, rows - 24, n_kp)], 1).astype(np.float32)
+    octL = rng.integers(0, n_levels, n_kp).astype(np.int32)
+    descL = rng.integers(0, 256, (n_kp, 32), dtype=np.uint8)
+    d = disp_of_row[kpL[:, 1].astype(int)].astype(np.float32)
+    kpR = kpL.copy()
+    kpR[:, 0] -= d + rng.normal(0, 0.4, n_kp).astype(np.float32)
+    kpR[:, 1] += rng.normal(0, 0.5, n_kp).astype(np.float32)
+    octR = np.clip(octL + rng.integers(-1, 2, n_kp), 0, n_levels - 1).astype(np.int32)
+    descR = descL.copy()
+    for i in range(n_kp):
+        nflip = int(rng.integers(0, 40)) if rng.random() < 0.8 else 128   # inliers: a few bits; outliers: unrelated
+        for bpos in rng.integers(0, 256, nflip):
+            descR[i, bpos >> 3] ^= np.uint8(1 << (bpos & 7))
+    perm = rng.permutation(n_kp)
+    kpR, octR, descR = kpR[perm], octR[perm], np.ascontiguousarray(descR[perm])
+    keep = kpR[:, 0] > 20
+    return dict(kpL=kpL, octL=octL, descL=descL, kpR=np.ascontiguousarray(kpR[keep]), octR=np.ascontiguousarray(octR[keep]),
+                descR=np.ascontiguousarray(descR[keep]), scale=scale, inv=inv, pyrL=pyrL, pyrR=pyrR, mb=np.float32(0.54),
+                mbf=np.float32(0.54 * 45.0))
+
+
+def _stereo_matches_numpy(f):
+    """Independent transcription of src/Frame.cc:530-704 with cv2 for the two distances."""
+    import cv2
+    f32 = np.float32
+    N = len(f["kpL"])
+    uRight = np.full(N, -1.0, f32)
+    depth = np.full(N, -1.0, f32)
+    nRows = f["pyrL"][0].shape[0]
+    rowidx = [[] for _ in range(nRows)]
+    for iR, (kp, o) in enumerate(zip(f["kpR"], f["octR"])):
+        r = f32(2.0) * f["scale"][o]
+        for yi in range(int(np.floor(kp[1] - r)), int(np.ceil(kp[1] + r)) + 1):
+            if 0 <= yi < nRows:
+                rowidx[yi].append(iR)
+    maxD = f32(f["mbf"] / f["mb"])
+    cand = []
+    for iL in range(N):
+        uL, vL = f["kpL"][iL]
+        lvl = int(f["octL"][iL])
+        cs = rowidx[int(vL)]
+        if not cs or uL < 0:
+            continue
+        minU, maxU = f32(uL - maxD), uL
+        best, bestR = 100, 0
+        for iR in cs:
+            if abs(int(f["octR"][iR]) - lvl) > 1:
+                continue
+            uR = f["kpR"][iR, 0]
+            if minU <= uR <= maxU:
+                dist = int(cv2.norm(f["descL"][iL], f["descR"][iR], cv2.NORM_HAMMING))
+                if dist < best:
+                    best, bestR = dist, iR
+        if best >= 75:
+            continue
+        s = f["inv"][lvl]
+        rnd = lambda x: f32(np.floor(abs(x) + 0.5) * np.sign(x))       # C round(): half away from zero
+        su, sv, sr = rnd(f32(uL * s)), rnd(f32(vL * s)), rnd(f32(f["kpR"][bestR, 0] * s))
+        imL, imR = f["pyrL"][lvl], f["pyrR"][lvl]
+        rows, cols = imL.shape
+        r0, c0 = int(sv) - 5, int(su) - 5
+        if r0 < 0 or r0 + 11 > rows or c0 < 0 or c0 + 11 > cols:
+            continue
+        IL = imL[r0:r0 + 11, c0:c0 + 11].astype(f32)
+        IL = IL - IL[5, 5]
+        if sr < 0 or sr + 11 >= cols:
+            continue
+        dists, ok = [], True
+        bestS, bestinc = 2 ** 31 - 1, 0
+        for inc in range(-5, 6):
+            cr = int(sr) + inc - 5
+            if cr < 0 or cr + 11 > cols:
+                ok = False
+                break
+            IR = imR[r0:r0 + 11, cr:cr + 11].astype(f32)
+            IR = IR - IR[5, 5]
+            dist = f32(cv2.norm(IL, IR, cv2.NORM_L1))
+            if dist < f32(bestS):
+                bestS, bestinc = int(dist), inc
+            dists.append(dist)
+        if not ok or bestinc in (-5, 5):
+            continue
+        d1, d2, d3 = dists[5 + bestinc - 1], dists[5 + bestinc], dists[5 + bestinc + 1]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            delta = f32(f32(d1 - d3) / f32(f32(2.0) * f32(f32(d1 + d3) - f32(f32(2.0) * d2))))
+        if delta < -1 or delta > 1:
+            continue
+        bu = f32(f["scale"][lvl] * f32(f32(sr + f32(bestinc)) + delta))
+        disp = f32(uL - bu)
+        if disp >= 0 and disp < maxD:
+            if disp <= 0:
+                disp = f32(0.01)
+                bu = f32(np.float64(uL) - 0.01)
+            depth[iL] = f32(f["mbf"] / disp)
+            uRight[iL] = bu
+            cand.append((bestS, iL))
+    if cand:
+        cand.sort()
+        th = f32(f32(1.5) * f32(1.4)) * f32(cand[len(cand) // 2][0])
+        for dS, iL in reversed(cand):
+            if f32(dS) < th:
+                break
+            uRight[iL] = -1
+            depth[iL] = -1
+    return uRight, depth
+
+
+def _stereo_matches_oracle(f):
+    import ctypes as C
+    dll = capi.load_oracle().dll
+    fn = dll.lldo_stereo_matches
+    fn.restype = C.c_int
+    P = C.c_void_p
+    n_levels = len(f["pyrL"])
+    ptr = lambda a: a.ctypes.data_as(P)
+    arrL = (P * n_levels)(*[a.ctypes.data for a in f["pyrL"]])
+    arrR = (P * n_levels)(*[a.ctypes.data for a in f["pyrR"]])
+    rows = np.array([a.shape[0] for a in f["pyrL"]], np.int32)
+    cols = np.array([a.shape[1] for a in f["pyrL"]], np.int32)
+    stride = np.array([a.strides[0] for a in f["pyrL"]], np.int32)
+    N, Nr = len(f["kpL"]), len(f["kpR"])
+    uR, dep = np.empty(N, np.float32), np.empty(N, np.float32)
+    fn.argtypes = [C.c_int, P, P, P, C.c_int, P, P, P, C.c_int, P, P, P, P, P, P, P, C.c_float, C.c_float, P, P]
+    n = fn(N, ptr(f["kpL"]), ptr(f["octL"]), ptr(f["descL"]), Nr, ptr(f["kpR"]), ptr(f["octR"]), ptr(f["descR"]), n_levels,
+           ptr(f["scale"]), ptr(f["inv"]), C.cast(arrL, P), C.cast(arrR, P), ptr(rows), ptr(cols), ptr(stride),
+           C.c_float(float(f["mb"])), C.c_float(float(f["mbf"])), ptr(uR), ptr(dep))
+    return n, uR, dep
+
+
+def test_oracle_stereo_matches_against_numpy(built):
+    """Frame::ComputeStereoMatches (src/Frame.cc:530-704): the C++ oracle and an independent numpy / cv2 transcription give
+    the same mvuRight / mvDepth bit for bit, on frames where most points match and the disparity is recovered."""
+    for seed in (1, 2, 3):
+        f = _stereo_frame(seed)
+        n, uR, dep = _stereo_matches_oracle(f)
+        uR2, dep2 = _stereo_matches_numpy(f)
+        assert np.array_equal(uR, uR2) and np.array_equal(dep, dep2)
+        got = uR >= 0
+        assert n == int(got.sum()) and n > 0.4 * len(uR)
+        # the synthetic disparity is 4 + 3 * (row // 40): sub-pixel refinement must land within a pixel of it
+        true_d = 4 + (f["kpL"][got, 1].astype(int) // 40) * 3
+        err = np.abs((f["kpL"][got, 0] - uR[got]) - true_d)
+        assert np.median(err) < 0.6 and (err < 1.6).mean() > 0.9
+    # no keypoints on the right: nothing matches, nothing is read out of range
+    f = _stereo_frame(4)
+    f["kpR"], f["octR"], f["descR"] = f["kpR"][:0], f["octR"][:0], f["descR"][:0]
+    n, uR, dep = _stereo_matches_oracle(f)
+    assert n == 0 and (uR == -1).all() and (dep == -1).all()
