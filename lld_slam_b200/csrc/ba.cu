@@ -380,18 +380,19 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
       const int b = lm_off[w], e = lm_off[w + 1];
       for (int i = b; i < e; i++) key[i] = signature(off, ekf, i, g0, nf);
       if (nf <= 32) {
-        // LSD radix sort on the nf mask bits, 8 bits per pass; the low word (window-local index) starts ascending and
+        // LSD radix sort on the nf mask bits, 11 bits per pass; the low word (window-local index) starts ascending and
         // the passes are stable, so equal signatures keep the reference's insertion order
         const int m = e - b;
         std::vector<uint64_t> packed((size_t)m), tmp((size_t)m);
         for (int i = b; i < e; i++) packed[i - b] = (key[i] << 32) | (uint32_t)(i - b);
         uint64_t* src = packed.data();
         uint64_t* dst = tmp.data();
-        for (int sh = 32; sh < 32 + nf; sh += 8) {
-          int cnt[257] = {0};
-          for (int i = 0; i < m; i++) cnt[((src[i] >> sh) & 0xffu) + 1]++;
-          for (int q = 0; q < 256; q++) cnt[q + 1] += cnt[q];
-          for (int i = 0; i < m; i++) dst[cnt[(src[i] >> sh) & 0xffu]++] = src[i];
+        const int RB = 11;   // bits per pass: 19-20 free keyframes (the usual local window) sort in two passes
+        for (int sh = 32; sh < 32 + nf; sh += RB) {
+          int cnt[(1 << RB) + 1] = {0};
+          for (int i = 0; i < m; i++) cnt[((src[i] >> sh) & ((1u << RB) - 1)) + 1]++;
+          for (int q = 0; q < (1 << RB); q++) cnt[q + 1] += cnt[q];
+          for (int i = 0; i < m; i++) dst[cnt[(src[i] >> sh) & ((1u << RB) - 1)]++] = src[i];
           std::swap(src, dst);
         }
         for (int i = b; i < e; i++) order[i] = b + (int)(src[i - b] & 0xffffffffu);
@@ -639,7 +640,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
       // order, so that every CTA gets about the same landmark x task volume
       auto& tmp = H.it_tmp; auto& keys = H.it_keys;
       tmp.resize(H.it_rec.size()); keys.resize(H.it_rec.size());
-      par_for(2, [&](int kind) {
+      auto item_order = [&](int kind) {
         const int i0 = kind == 0 ? 0 : n_items_pt, i1 = kind == 0 ? n_items_pt : ji[n_jobs];
         const int cntk = i1 - i0;
         if (cntk <= 0) return;
@@ -663,17 +664,20 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
           const int pos = (r & 1) ? len - 1 - j : j;
           H.it_rec[i0 + r * G + pos] = tmp[i];
         }
+      };
+      // a block / keyframe belongs to one window: its contributions come from that window's point job, then its line job.
+      // The two item-order tasks (serial each) run in the same parallel region as the per-window gather counts.
+      par_for(nw + 2, [&](int t) {
+        if (t < 2) { item_order(t); return; }
+        const int w = t - 2;
+        for (int kind = 0; kind < 2; kind++) {
+          Job& J = jobs[(size_t)kind * nw + w];
+          for (auto& x : J.gb) gb_off[x.first + 1]++;
+          for (auto& x : J.gv) gv_off[x.first + 1]++;
+        }
       });
     }
-    stage("dense: item order");
-    // a block / keyframe belongs to one window: its contributions come from that window's point job, then its line job
-    par_for(nw, [&](int w) {
-      for (int kind = 0; kind < 2; kind++) {
-        Job& J = jobs[(size_t)kind * nw + w];
-        for (auto& x : J.gb) gb_off[x.first + 1]++;
-        for (auto& x : J.gv) gv_off[x.first + 1]++;
-      }
-    });
+    stage("dense: item order + gather counts");
     for (size_t i = 0; i < nb_g.size(); i++) gb_off[i + 1] += gb_off[i];
     for (int i = 0; i < nG; i++) gv_off[i + 1] += gv_off[i];
     gb_src.resize(std::max<size_t>((size_t)gb_off[nb_g.size()], 1));
