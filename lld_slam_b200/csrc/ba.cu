@@ -112,7 +112,7 @@ struct BaDenseJob {
   void clear() { pb.clear(); pe.clear(); pn.clear(); itp.clear(); itt.clear(); pout.clear(); gb.clear(); gv.clear(); dsize = 0; }
 };
 struct BaHost {
-  pvec<int> kf_win, pt_win, ln_win, kf_g, w_g0, g_kf;
+  pvec<int> kf_win, kf_g, w_g0, g_kf;
   pvec<int> pe_kf, pe_pt, lc_kf, lc_ln;
   pvec<int> pt_order, ln_order;
   std::vector<uint64_t> pt_key, ln_key;
@@ -297,9 +297,9 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   if (!c->ba_host) c->ba_host = new BaHost();
   BaHost& H = *reinterpret_cast<BaHost*>(c->ba_host);
   auto par_for = [&](int n, auto f) { H.par_for(n, f); };
-  auto& kf_win = H.kf_win; auto& pt_win = H.pt_win; auto& ln_win = H.ln_win; auto& kf_g = H.kf_g; auto& w_g0 = H.w_g0;
+  auto& kf_win = H.kf_win; auto& kf_g = H.kf_g; auto& w_g0 = H.w_g0;
   auto& g_kf = H.g_kf;
-  kf_win.resize(n_kf); pt_win.resize(n_pt); ln_win.resize(n_ln); kf_g.assign(n_kf, -1); w_g0.assign(nw + 1, 0);
+  kf_win.resize(n_kf); kf_g.assign(n_kf, -1); w_g0.assign(nw + 1, 0);   // (landmark -> window owners: device only)
   g_kf.clear();
   for (int w = 0; w < nw; w++) {
     w_g0[w] = (int)g_kf.size();
@@ -310,8 +310,6 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         g_kf.push_back(k);
       }
     }
-    for (int i = p->pt_off[w]; i < p->pt_off[w + 1]; i++) pt_win[i] = w;
-    for (int i = p->ln_off[w]; i < p->ln_off[w + 1]; i++) ln_win[i] = w;
     S->max_n = std::max(S->max_n, 6 * ((int)g_kf.size() - w_g0[w]));
   }
   w_g0[nw] = (int)g_kf.size();
@@ -335,7 +333,6 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
       for (int e = p->pt_obs_off[i]; e < p->pt_obs_off[i + 1]; e++) {
         if (p->pt_obs_kf[e] < 0 || p->pt_obs_kf[e] >= nk) { ok = false; continue; }
         pe_kf[e] = k0 + p->pt_obs_kf[e];
-        pe_pt[e] = i;
       }
     }
     for (int i = p->ln_off[w]; i < p->ln_off[w + 1]; i++) {
@@ -343,7 +340,6 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
       for (int e = p->ln_obs_off[i]; e < p->ln_obs_off[i + 1]; e++) {
         if (p->ln_obs_kf[e] < 0 || p->ln_obs_kf[e] >= nk) { ok = false; continue; }
         lc_kf[e] = k0 + p->ln_obs_kf[e];
-        lc_ln[e] = i;
       }
     }
     if (!ok) bad_arg = 1;
@@ -537,6 +533,13 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   std::vector<long long> pl_tab_off(std::max(nG, 1), 0), ll_tab_off(std::max(nG, 1), 0);
   std::vector<int> pl_tab(1, -1), ll_tab(1, -1);
   if (!dense) {
+    // edge -> landmark owners: only these sparse-mode tables read them on the host (the device derives its own copy)
+    par_for(nw, [&](int w) {
+      for (int i = p->pt_off[w]; i < p->pt_off[w + 1]; i++)
+        for (int e = p->pt_obs_off[i]; e < p->pt_obs_off[i + 1]; e++) pe_pt[e] = i;
+      for (int i = p->ln_off[w]; i < p->ln_off[w + 1]; i++)
+        for (int e = p->ln_obs_off[i]; e < p->ln_obs_off[i + 1]; e++) lc_ln[e] = i;
+    });
     build_tab(pl_off, pl_edge, p->pt_obs_off, pe_pt, pe_kf, pe_pos, pl_tab_off, pl_tab);
     build_tab(ll_off, ll_cell, p->ln_obs_off, lc_ln, lc_kf, lc_pos, ll_tab_off, ll_tab);
   }
