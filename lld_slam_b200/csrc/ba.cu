@@ -558,20 +558,23 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   if (dense) {
     // W slots: landmarks in signature order, each landmark's free edges sorted by keyframe
     // (the W slot of an edge = w0 of its landmark + rank of its keyframe in the mask is derived on the device: k_dense_wpos)
-    auto slots = [&](int n_lm, const int* lm_off, const pvec<int>& order, const std::vector<uint64_t>& key, pvec<int>& spos,
-                     pvec<uint32_t>& mask, pvec<int>& w0) {
+    // a landmark owns one W slot per free keyframe that sees it = one entry in one keyframe list, so the first slot of a
+    // window is the first list position of its first free block: every window writes its own absolute prefix in parallel
+    auto slots = [&](const int* lm_off, const pvec<int>& order, const std::vector<uint64_t>& key, pvec<int>& spos,
+                     pvec<uint32_t>& mask, pvec<int>& w0, const pvec<int>& l_off) {
       par_for(nw, [&](int w) {
+        int run = l_off[w_g0[w]];
         for (int oi = lm_off[w]; oi < lm_off[w + 1]; oi++) {
           const int i = order[oi];
           spos[i] = oi;
           mask[oi] = (uint32_t)key[i];
-          w0[oi + 1] = __builtin_popcountll(key[i]);
+          run += __builtin_popcountll(key[i]);
+          w0[oi + 1] = run;
         }
       });
-      for (int oi = 0; oi < n_lm; oi++) w0[oi + 1] += w0[oi];
     };
-    slots(n_pt, p->pt_off, pt_order, pt_key, pt_spos, pts_mask, pts_w0);
-    slots(n_ln, p->ln_off, ln_order, ln_key, ln_spos, lns_mask, lns_w0);
+    slots(p->pt_off, pt_order, pt_key, pt_spos, pts_mask, pts_w0, pl_off);
+    slots(p->ln_off, ln_order, ln_key, ln_spos, lns_mask, lns_w0, ll_off);
     n_pw = (size_t)pts_w0[n_pt]; n_lw = (size_t)lns_w0[n_ln];
     stage("dense: W slots");
     int PIECE_CAP = 128;  // shorter pieces when the batch is small, so that every SM gets warps
