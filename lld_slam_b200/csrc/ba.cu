@@ -379,7 +379,8 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         // LSD radix sort on the nf mask bits, 11 bits per pass; the low word (window-local index) starts ascending and
         // the passes are stable, so equal signatures keep the reference's insertion order
         const int m = e - b;
-        std::vector<uint64_t> packed((size_t)m), tmp((size_t)m);
+        static thread_local std::vector<uint64_t> packed, tmp;   // per worker thread, reused across windows and calls
+        if ((int)packed.size() < m) { packed.resize((size_t)m); tmp.resize((size_t)m); }
         for (int i = b; i < e; i++) packed[i - b] = (key[i] << 32) | (uint32_t)(i - b);
         uint64_t* src = packed.data();
         uint64_t* dst = tmp.data();
