@@ -87,6 +87,12 @@ if a.check and rank == 0:
                     "pose_t_max": float(np.abs(g["kf_Tcw"][:, 9:] - o["kf_Tcw"][:, 9:]).max()),
                     "pose_R_max": float(np.abs(g["kf_Tcw"][:, :9] - o["kf_Tcw"][:, :9]).max()),
                     "pt_max": float(np.abs(g["pt_xyz"] - o["pt_xyz"]).max())}
+    dT = np.abs(g["kf_Tcw"][:, 9:] - o["kf_Tcw"][:, 9:]).max(axis=1)
+    res["check"]["pose_t_deciles"] = [float(x) for x in np.quantile(dT, np.linspace(0, 1, 11))]
+    res["check"]["pose_t_worst_kf"] = [int(k) for k in np.argsort(-dT)[:8]]
+    os.makedirs("gpurun_out", exist_ok=True)
+    np.savez_compressed(f"gpurun_out/gba_state_n{world}.npz", g_kf=g["kf_Tcw"], o_kf=o["kf_Tcw"], g_chi2=g["chi2_log"], o_chi2=o["chi2_log"],
+                        g_lambda=g["lambda_log"], o_lambda=o["lambda_log"])
 if prof is not None:
     res["kernels_us_per_launch"] = {k: round(1e3 * v["ms"] / max(v["n"], 1), 1) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
 if rank == 0:
