@@ -49,6 +49,14 @@ extern "C" {
  * Bundle adjustment (local windows and global map)
  * ---------------------------------------------------------------------------------------------- */
 
+/* Capacity limits of this implementation (the reference has none; a call outside them returns LLD_ERR_ARG /
+ * LLD_ERR_UNSUPPORTED and lld_ctx_last_error() names the limit):
+ *   - at most 254 observations per landmark;
+ *   - a keyframe may be covisible with at most 170 free keyframes in lld_ba_global (6 * neighbours <= 1024);
+ *   - local windows with more than 32 free keyframes take the general (slower) sparse path;
+ *   - lld_sbp_*: n_levels <= 8, at most 65535 keypoints per frame.
+ */
+
 /* One batch of independent BA problems ("windows").  Entities of window w live at
  * [kf_off[w], kf_off[w+1]) etc.; KF indices stored in observations are window-local.
  * Observations are grouped by landmark in the reference's insertion order
@@ -128,8 +136,16 @@ int lld_ba_local(void* ctx, const lld_ba_problem* p, int its_round1, int its_rou
                  const volatile uint8_t* stop_flag, lld_ba_result* out);
 
 /* BundleAdjustment: one optimize(n_iter) pass, no outlier round.
- * With a communicator of n_ranks>1 each rank passes its own landmark shard (all KFs replicated,
- * identical order); the reduced camera system and chi2 are all-reduced over NCCL. */
+ * Multi-rank (a communicator of n_ranks>1 joined with lld_comm_init): EVERY rank passes the SAME, WHOLE problem (all
+ * keyframes, all landmarks, identical order).  The library keeps the contiguous landmark block lld_ba_shard_bounds()
+ * assigns to the calling rank, indexes and uploads only that block (the block pattern of the reduced camera system is
+ * derived from the whole problem, so it is rank-invariant), and all-reduces the reduced camera system (one packed
+ * call per LM trial) and the chi2 / scale scalars over NCCL.  Do NOT pre-shard the input.
+ * Outputs on n_ranks>1: kf_Tcw and the LM trace are complete and identical on every rank; pt_xyz / ln_x0_dir (and the
+ * all-zero flag arrays) are written for the rank's own landmark block only — the caller gathers them (rank r owns
+ * points [b[0],b[1]) and lines [b[2],b[3]) of lld_ba_shard_bounds).
+ * stop_flag on n_ranks>1: the ranks agree on the flag with an all-reduce(max) before every group of LM steps, so every
+ * rank stops at the same step whichever rank saw the flag first. */
 int lld_ba_global(void* ctx, const lld_ba_problem* p, int n_iter, const volatile uint8_t* stop_flag,
                   lld_ba_result* out);
 
@@ -282,6 +298,8 @@ int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_line_match_re
  * context's stream (milliseconds; h2d/compute/d2h). */
 const char* lld_version(void);
 int64_t lld_ctx_launch_count(void* ctx);
+/* NCCL collectives issued / bytes all-reduced per rank by the last lld_ba_global call on this context */
+void lld_ctx_nccl_stats(void* ctx, int64_t* calls, int64_t* bytes);
 void lld_ctx_last_timing(void* ctx, float* ms_h2d, float* ms_compute, float* ms_d2h);
 
 #ifdef __cplusplus

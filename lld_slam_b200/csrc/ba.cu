@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "ba_kernels.cuh"
+#include "cr_solver.cuh"
 #include "lld_ctx.h"
 
 #ifdef LLD_WITH_NCCL
@@ -40,6 +41,8 @@ struct BaState {
   bool gather_long = false;   // dense mode: average S-block gather list longer than a warp -> k_reduce_piece_warp
   size_t env_smem = 0, band_smem = 0;
   bool use_band = false;
+  bool use_cr = false;     // global BA: block cyclic reduction of the reduced camera system (cr_solver.cuh)
+  CrView cr{};
   bool global_mode = false;
   bool forked = false;     // dense single-rank batch small enough that concurrent passes shorten the critical path
   bool use_graph = false;  // replay one captured LM step instead of re-launching its kernels
@@ -369,12 +372,14 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   };
   auto& pt_order = H.pt_order; auto& ln_order = H.ln_order; auto& pt_key = H.pt_key; auto& ln_key = H.ln_key;
   pt_order.resize(n_pt); ln_order.resize(n_ln); pt_key.resize(n_pt); ln_key.resize(n_ln);
+  bool keys_ready = false;   // single large window (global BA): ids and signatures are computed by landmark ranges in parallel
   auto sort_window = [&](int w) {
     const int g0 = w_g0[w], nf = w_g0[w + 1] - g0;
     // stable order by signature; with <= 32 free keyframes the key and the landmark's window-local index fit one 64-bit word
     auto sort_by_key = [&](const int* lm_off, const int* off, const pvec<int>& ekf, std::vector<uint64_t>& key, pvec<int>& order) {
       const int b = lm_off[w], e = lm_off[w + 1];
-      for (int i = b; i < e; i++) key[i] = signature(off, ekf, i, g0, nf);
+      if (!keys_ready)
+        for (int i = b; i < e; i++) key[i] = signature(off, ekf, i, g0, nf);
       if (nf <= 32) {
         // LSD radix sort on the nf mask bits, 11 bits per pass; the low word (window-local index) starts ascending and
         // the passes are stable, so equal signatures keep the reference's insertion order
@@ -428,13 +433,42 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
       }
     }
   };
+  if (nw == 1 && n_pt + n_ln >= 65536) {
+    const int nk = p->kf_off[1] - p->kf_off[0], g0 = w_g0[0], nf = w_g0[1] - g0, parts = 64;
+    par_for(parts, [&](int part) {
+      bool ok = true;
+      auto range = [&](int n_lm, const int32_t* off, const int32_t* okf, pvec<int>& ekf, std::vector<uint64_t>& key) {
+        const int i0 = (int)((long long)n_lm * part / parts), i1 = (int)((long long)n_lm * (part + 1) / parts);
+        for (int i = i0; i < i1; i++) {
+          if (off[i + 1] - off[i] > 254) ok = false;
+          for (int e = off[i]; e < off[i + 1]; e++) {
+            if (okf[e] < 0 || okf[e] >= nk) { ok = false; ekf[e] = p->kf_off[0]; continue; }
+            ekf[e] = p->kf_off[0] + okf[e];
+          }
+        }
+        if (ok)
+          for (int i = i0; i < i1; i++) key[i] = signature(off, ekf, i, g0, nf);
+      };
+      range(n_pt, p->pt_obs_off, p->pt_obs_kf, pe_kf, pt_key);
+      range(n_ln, p->ln_obs_off, p->ln_obs_kf, lc_kf, ln_key);
+      if (!ok) bad_arg = 1;
+    });
+    if (bad_arg.load()) {
+      snprintf(c->err, sizeof(c->err), "malformed problem: an observation names a keyframe outside the window, or a landmark has more than 254 observations (include/lldba.h, capacity limits)");
+      return LLD_ERR_ARG;
+    }
+    keys_ready = true;
+  }
   par_for(nw, [&](int w) {
-    if (!ids_window(w)) return;   // malformed window: rejected below, nothing else may index with its ids
+    if (!keys_ready && !ids_window(w)) return;   // malformed window: rejected below, nothing else may index with its ids
     sort_window(w);
     count_window(w, p->pt_off, p->pt_obs_off, pe_kf, pl_off);
     count_window(w, p->ln_off, p->ln_obs_off, lc_kf, ll_off);
   });
-  LLD_ARG(c, bad_arg.load() == 0);
+  if (bad_arg.load()) {
+    snprintf(c->err, sizeof(c->err), "malformed problem: an observation names a keyframe outside the window, or a landmark has more than 254 observations (include/lldba.h, capacity limits)");
+    return LLD_ERR_ARG;
+  }
   // arrays that are final from here on go to the device now: their DMA (queued behind the caller's raw arrays on the
   // same stream) runs under the rest of the indexing instead of after it
   UP(tmp_i, pe_kf.data(), n_pe); v.pe_kf = tmp_i;
@@ -469,43 +503,51 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
       }
     nb_off[nG] = (int)nb_g.size();
   } else {
-    // covisibility: blocks sharing at least one landmark
-    std::vector<std::vector<int>> nbs(nG);
-    std::vector<int> gs;
-    auto add = [&](std::vector<int>& gl) {
-      std::sort(gl.begin(), gl.end());
-      gl.erase(std::unique(gl.begin(), gl.end()), gl.end());
-      for (size_t a = 0; a < gl.size(); a++)
-        for (size_t b = a; b < gl.size(); b++) nbs[gl[a]].push_back(gl[b]);
-    };
+    // covisibility: blocks sharing at least one landmark.  One bit per (row block a, column block b >= a); every worker
+    // marks the pairs of its landmark range in a private nG x nG bitmap (280 KB at 1.5k keyframes: cache resident), the
+    // bitmaps are OR-ed row by row when the lists are extracted.
     // every rank derives the block pattern from the WHOLE problem (single window: kf index == local index)
     const lld_ba_problem* sp = full ? full : p;
     const int sn_pt = sp->pt_off[1], sn_ln = sp->ln_off[1];
-    for (int i = 0; i < sn_pt; i++) {
-      gs.clear();
-      for (int e = sp->pt_obs_off[i]; e < sp->pt_obs_off[i + 1]; e++)
-        if (kf_g[sp->pt_obs_kf[e]] >= 0) gs.push_back(kf_g[sp->pt_obs_kf[e]]);
-      add(gs);
-    }
-    for (int i = 0; i < sn_ln; i++) {
-      gs.clear();
-      for (int e = sp->ln_obs_off[i]; e < sp->ln_obs_off[i + 1]; e++)
-        if (kf_g[sp->ln_obs_kf[e]] >= 0) gs.push_back(kf_g[sp->ln_obs_kf[e]]);
-      add(gs);
-    }
+    const size_t row_w = ((size_t)nG + 63) / 64;
+    const int n_part = std::max(1, std::min<int>(16, (sn_pt + sn_ln) / 4096));
+    std::vector<std::vector<uint64_t>> bm((size_t)n_part);
+    par_for(n_part, [&](int part) {
+      auto& B = bm[(size_t)part];
+      B.assign(row_w * (size_t)nG, 0);
+      std::vector<int> gs;
+      auto mark = [&](const int32_t* off, const int32_t* okf, int i) {
+        gs.clear();
+        for (int e = off[i]; e < off[i + 1]; e++)
+          if (kf_g[okf[e]] >= 0) gs.push_back(kf_g[okf[e]]);
+        std::sort(gs.begin(), gs.end());
+        for (size_t a = 0; a < gs.size(); a++)
+          for (size_t b = a; b < gs.size(); b++) B[row_w * (size_t)gs[a] + ((size_t)gs[b] >> 6)] |= 1ull << (gs[b] & 63);
+      };
+      for (int i = (int)((long long)sn_pt * part / n_part); i < (int)((long long)sn_pt * (part + 1) / n_part); i++) mark(sp->pt_obs_off, sp->pt_obs_kf, i);
+      for (int i = (int)((long long)sn_ln * part / n_part); i < (int)((long long)sn_ln * (part + 1) / n_part); i++) mark(sp->ln_obs_off, sp->ln_obs_kf, i);
+    });
     for (int g = 0; g < nG; g++) {
-      auto& l = nbs[g];
-      l.push_back(g);
-      std::sort(l.begin(), l.end());
-      l.erase(std::unique(l.begin(), l.end()), l.end());
       nb_off[g] = (int)nb_g.size();
-      nb_g.insert(nb_g.end(), l.begin(), l.end());
+      for (size_t wd = (size_t)g >> 6; wd < row_w; wd++) {
+        uint64_t bits = 0;
+        for (int part = 0; part < n_part; part++) bits |= bm[(size_t)part][row_w * (size_t)g + wd];
+        if (wd == ((size_t)g >> 6)) bits |= 1ull << (g & 63);   // the diagonal block always exists
+        while (bits) {
+          const int b = (int)(wd * 64) + __builtin_ctzll(bits);
+          bits &= bits - 1;
+          nb_g.push_back(b);
+        }
+      }
     }
     nb_off[nG] = (int)nb_g.size();
   }
   for (int g = 0; g < nG; g++) S->max_nnb = std::max(S->max_nnb, nb_off[g + 1] - nb_off[g]);
   S->n_nb_total = nb_g.size();
-  LLD_ARG(c, 6 * S->max_nnb <= 1024);
+  if (6 * S->max_nnb > 1024) {
+    snprintf(c->err, sizeof(c->err), "a keyframe is covisible with %d free keyframes; this implementation supports at most 170 (include/lldba.h, capacity limits)", S->max_nnb);
+    return LLD_ERR_UNSUPPORTED;
+  }
   // position tables: per list entry and neighbour, the list position of the co-edge (or -1)
   auto build_tab = [&](const pvec<int>& l_off, const pvec<int>& l_ref, const int* off, const pvec<int>& e_lm,
                        const pvec<int>& ekf, const pvec<int>& e_pos, std::vector<long long>& t_off, std::vector<int>& tab) {
@@ -516,7 +558,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
       tot += (long long)(l_off[g + 1] - l_off[g]) * (nb_off[g + 1] - nb_off[g]);
     }
     tab.assign((size_t)std::max(tot, 1LL), -1);
-    for (int g = 0; g < nG; g++) {
+    par_for(nG, [&](int g) {
       const int nnb = nb_off[g + 1] - nb_off[g];
       const int* nbl = nb_g.data() + nb_off[g];
       for (int i = l_off[g]; i < l_off[g + 1]; i++) {
@@ -529,7 +571,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
           row[j] = e_pos[e2];
         }
       }
-    }
+    });
   };
   std::vector<long long> pl_tab_off(std::max(nG, 1), 0), ll_tab_off(std::max(nG, 1), 0);
   std::vector<int> pl_tab(1, -1), ll_tab(1, -1);
@@ -793,7 +835,17 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         for (int q = nb_off[a]; q < nb_off[a + 1]; q++) { const int r = nb_g[q]; lo_col[cur[r]] = a; lo_src[cur[r]++] = q; }
     }
     S->env_smem = sizeof(double) * (6 * (size_t)ph + 8 + 32 * (size_t)maxlen + (size_t)n) + 64;
-    if (!S->use_band && S->env_smem > 220 * 1024) {
+    {
+      // cyclic reduction over super-blocks of B keyframes whenever a dense super-block fits one SM's shared memory;
+      // LLD_GBA_SOLVER=band keeps the single-CTA sliding-window solver (A/B measurements)
+      const char* se = getenv("LLD_GBA_SOLVER");
+      S->use_cr = 6 * B <= CR_MAX_M && !(se && se[0] == 'b');
+      if (S->use_cr) {
+        S->cr.mb = B; S->cr.m = 6 * B; S->cr.N = (nG + B - 1) / B; S->cr.zs = 12 * B;
+        S->use_band = false;
+      }
+    }
+    if (!S->use_band && !S->use_cr && S->env_smem > 220 * 1024) {
       snprintf(c->err, sizeof(c->err), "global BA: envelope of the reduced system too wide for the on-chip solver (panel %d rows, row %d, n %d)", ph, maxlen, n);
       return LLD_ERR_UNSUPPORTED;
     }
@@ -878,29 +930,41 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   DEV(v.pts_D, double, dense ? 10 * (size_t)n_pt : 1); DEV(v.lns_D, double, dense ? 14 * (size_t)n_ln : 1);
   DEV(v.dpart, double, (size_t)dpart_total);
   DEV(v.ch_pose, double, 28 * (size_t)n_ch);
-  DEV(v.g_Hpp, double, 21 * (size_t)nG); DEV(v.g_bp, double, 6 * (size_t)nG); DEV(v.g_nact, int, nG);
+  // [g_bp | w_red_sum | g_Hpp] and [S_blk | g_bs] are contiguous: the multi-rank global BA all-reduces each group in one call
+  DEV(v.g_bp, double, 6 * (size_t)nG + 4 * (size_t)nw + 21 * (size_t)nG);
+  v.w_red_sum = v.g_bp + 6 * (size_t)nG; v.g_Hpp = v.w_red_sum + 4 * (size_t)nw;
+  DEV(v.g_nact, int, nG);
   DEV(v.lm_chi2lin, double, n_pt + n_ln); DEV(v.lm_maxdiag, double, n_pt + n_ln); DEV(v.lm_active, uint8_t, n_pt + n_ln);
   DEV(v.ch_S, double, (size_t)chS_total);
-  DEV(v.S_blk, double, 36 * nb_g.size());
-  DEV(v.g_bs, double, 6 * (size_t)nG); DEV(v.g_x, double, 6 * (size_t)nG);
+  DEV(v.S_blk, double, 36 * nb_g.size() + 6 * (size_t)nG);
+  v.g_bs = v.S_blk + 36 * nb_g.size(); DEV(v.g_x, double, 6 * (size_t)nG);
   DEV(v.pt_D, double, 9 * (size_t)n_pt); DEV(v.ln_D, double, 14 * (size_t)n_ln);
   DEV(v.lm_chi2, double, n_pt + n_ln); DEV(v.lm_scale, double, n_pt + n_ln);
   DEV(v.w_phase, int, nw); DEV(v.w_sel, int, nw); DEV(v.w_iter, int, nw); DEV(v.w_trials, int, nw);
   DEV(v.w_maxit, int, nw); DEV(v.w_nbad, int, nw); DEV(v.w_ok, int, nw); DEV(v.w_nlog, int, nw);
   DEV(v.w_lambda, double, nw); DEV(v.w_ni, double, nw); DEV(v.w_curchi, double, nw); DEV(v.w_inichi, double, nw);
-  DEV(v.w_scale_p, double, nw); DEV(v.w_red_sum, double, 4 * (size_t)nw); DEV(v.w_red_max, double, nw);
+  DEV(v.w_scale_p, double, nw); DEV(v.w_red_max, double, nw);
   {
     int max_lm = 0;
     for (int w = 0; w < nw; w++) max_lm = std::max(max_lm, (p->pt_off[w + 1] - p->pt_off[w]) + (p->ln_off[w + 1] - p->ln_off[w]));
     v.n_slices = std::max(1, std::min(128, max_lm / 16384));
   }
   DEV(v.w_part, double, 4 * (size_t)nw * v.n_slices);
-  DEV(v.n_active_win, int, 1);
+  DEV(v.n_active_win, int, 2);   // [0] windows still running, [1] multi-rank stop agreement word
   v.log_stride = log_stride;
   DEV(v.chi2_log, double, (size_t)nw * log_stride); DEV(v.lambda_log, double, (size_t)nw * log_stride);
   DEV(v.trials_log, int, (size_t)nw * log_stride); DEV(v.iter_done, int, 2 * (size_t)nw);
   DEV(v.solve_scratch, double, (size_t)scr_total);
-  DEV(v.env_A, double, S->use_band ? 1 : (size_t)env_rowptr.back());
+  DEV(v.env_A, double, (S->use_band || S->use_cr) ? 1 : (size_t)env_rowptr.back());
+  if (S->use_cr) {
+    CrView& cr = S->cr;
+    const size_t mm = (size_t)cr.m * cr.m, N = (size_t)cr.N;
+    // D and U[0] are zero-filled together before every assembly: one allocation
+    DEV(cr.D, double, 2 * N * mm); cr.U[0] = cr.D + N * mm;
+    DEV(cr.U[1], double, N * mm); DEV(cr.L, double, N * mm); DEV(cr.Z, double, N * cr.m * cr.zs);
+    DEV(cr.b, double, N * cr.m); DEV(cr.zc, double, N * cr.m); DEV(cr.x, double, N * cr.m);
+    DEV(cr.ok, int, 1);
+  }
   DEV(v.band_A, double, S->use_band ? (size_t)nG * ((v.band_B + 1) * 36 + 8) : 1);
   DEV(v.band_L, double, S->use_band ? (size_t)nG * (v.band_B + 1) * 36 : 1);
   DEV(v.band_z, double, S->use_band ? 6 * (size_t)nG : 1);
@@ -948,7 +1012,11 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     LLD_CUDA(c, lld_raise_dyn_smem(k_schur_tile<3>, (size_t)SP_SMEM_BYTES));
     LLD_CUDA(c, lld_raise_dyn_smem(k_schur_tile<4>, (size_t)SP_SMEM_BYTES));
   }
-  if (v.env_mode && S->use_band) LLD_CUDA(c, lld_raise_dyn_smem(k_solve_band<512>, (size_t)(int)S->band_smem) != cudaSuccess ? cudaErrorInvalidValue : lld_raise_dyn_smem(k_solve_band<1024>, (size_t)(int)S->band_smem));
+  if (v.env_mode && S->use_cr) {
+    LLD_CUDA(c, lld_raise_dyn_smem(k_cr_factor, sizeof(double) * ((size_t)S->cr.m * S->cr.m + 8 * (size_t)S->cr.m + 40)));
+    LLD_CUDA(c, lld_raise_dyn_smem(k_cr_solve<15>, sizeof(double) * ((size_t)S->cr.m * S->cr.m + CR_RPT * CR_TC)));
+    LLD_CUDA(c, lld_raise_dyn_smem(k_cr_solve<20>, sizeof(double) * ((size_t)S->cr.m * S->cr.m + CR_RPT * CR_TC)));
+  } else if (v.env_mode && S->use_band) LLD_CUDA(c, lld_raise_dyn_smem(k_solve_band<512>, (size_t)(int)S->band_smem) != cudaSuccess ? cudaErrorInvalidValue : lld_raise_dyn_smem(k_solve_band<1024>, (size_t)(int)S->band_smem));
   else if (v.env_mode) LLD_CUDA(c, lld_raise_dyn_smem(k_solve_env, (size_t)(int)S->env_smem));
   else if (S->max_n <= SMEM_SOLVE_MAX_N)
     LLD_CUDA(c, lld_raise_dyn_smem(k_solve<true>, (size_t)(int)(sizeof(double) * ((size_t)S->max_n * S->max_n + 8 * (size_t)S->max_n + 40))));
@@ -983,11 +1051,11 @@ static int ba_allreduce_lin(LldCtx* c) {
   if (c->n_ranks > 1) {
     BaView& v = c->ba->v;
     ncclComm_t comm = reinterpret_cast<ncclComm_t>(c->comm);
-    LLD_NCCL(c, ncclAllReduce(v.w_red_sum, v.w_red_sum, 4 * (size_t)v.n_win, ncclDouble, ncclSum, comm, c->stream));
-    LLD_NCCL(c, ncclAllReduce(v.w_red_max, v.w_red_max, (size_t)v.n_win, ncclDouble, ncclMax, comm, c->stream));
-    LLD_NCCL(c, ncclAllReduce(v.g_Hpp, v.g_Hpp, 21 * (size_t)v.n_free_total, ncclDouble, ncclSum, comm, c->stream));
-    LLD_NCCL(c, ncclAllReduce(v.g_bp, v.g_bp, 6 * (size_t)v.n_free_total, ncclDouble, ncclSum, comm, c->stream));
+    // one packed sum [g_bp | w_red_sum | g_Hpp] (contiguous by construction), the active-edge counts, the lambda_0 maximum
+    LLD_NCCL(c, ncclAllReduce(v.g_bp, v.g_bp, 27 * (size_t)v.n_free_total + 4 * (size_t)v.n_win, ncclDouble, ncclSum, comm, c->stream));
     LLD_NCCL(c, ncclAllReduce(v.g_nact, v.g_nact, (size_t)v.n_free_total, ncclInt, ncclSum, comm, c->stream));
+    LLD_NCCL(c, ncclAllReduce(v.w_red_max, v.w_red_max, (size_t)v.n_win, ncclDouble, ncclMax, comm, c->stream));
+    c->nccl_calls += 3; c->nccl_bytes += 8 * (27 * (size_t)v.n_free_total + 5 * (size_t)v.n_win) + 4 * (size_t)v.n_free_total;
   }
 #endif
   return LLD_OK;
@@ -998,6 +1066,7 @@ static int ba_allreduce_trial(LldCtx* c) {
     BaView& v = c->ba->v;
     ncclComm_t comm = reinterpret_cast<ncclComm_t>(c->comm);
     LLD_NCCL(c, ncclAllReduce(v.w_red_sum, v.w_red_sum, 4 * (size_t)v.n_win, ncclDouble, ncclSum, comm, c->stream));
+    c->nccl_calls += 1; c->nccl_bytes += 32 * (size_t)v.n_win;
   }
 #endif
   return LLD_OK;
@@ -1010,10 +1079,42 @@ static int ba_allreduce_rows(LldCtx* c) {
     BaState* S = c->ba;
     BaView& v = S->v;
     ncclComm_t comm = reinterpret_cast<ncclComm_t>(c->comm);
-    LLD_NCCL(c, ncclAllReduce(v.S_blk, v.S_blk, 36 * S->n_nb_total, ncclDouble, ncclSum, comm, c->stream));
-    LLD_NCCL(c, ncclAllReduce(v.g_bs, v.g_bs, 6 * (size_t)v.n_free_total, ncclDouble, ncclSum, comm, c->stream));
+    // S blocks and b_schur in one buffer: one all-reduce per LM trial carries the whole reduced camera system
+    LLD_NCCL(c, ncclAllReduce(v.S_blk, v.S_blk, 36 * S->n_nb_total + 6 * (size_t)v.n_free_total, ncclDouble, ncclSum, comm, c->stream));
+    c->nccl_calls += 1; c->nccl_bytes += 8 * (36 * S->n_nb_total + 6 * (size_t)v.n_free_total);
   }
 #endif
+  return LLD_OK;
+}
+
+// global BA: reduced camera system by block cyclic reduction (cr_solver.cuh); every kernel returns early when the window
+// is done or an earlier factorisation failed
+static int ba_solve_cr(LldCtx* c) {
+  BaState* S = c->ba;
+  BaView& v = S->v;
+  const CrView& cr = S->cr;
+  const int N = cr.N, m = cr.m;
+  const size_t mm = (size_t)m * m;
+  LLD_CUDA(c, cudaMemsetAsync(cr.D, 0, sizeof(double) * 2 * (size_t)N * mm, c->stream));
+  const int nblk = (int)S->n_nb_total;
+  LLD_LAUNCH(c, k_cr_assemble, (nblk * 36 + N * m + 255) / 256, 256, 0, v, cr, nblk);
+  const size_t smem_f = sizeof(double) * (mm + 8 * (size_t)m + 40), smem_s = sizeof(double) * (mm + CR_RPT * CR_TC);
+  const int ntile = (2 * m + CR_TC - 1) / CR_TC, T = (m + CR_TILE - 1) / CR_TILE, per = 2 * T * T + 1;
+  int cur = 0, s = 1;
+  for (; s < N; s *= 2, cur ^= 1) {
+    const int n_el = ((N - 1) / s + 1) / 2, n_sv = (N - 1) / (2 * s) + 1;
+    LLD_LAUNCH(c, k_cr_factor, n_el, 512, smem_f, v, cr, s);
+    if (m <= 15 * CR_RG) LLD_LAUNCH(c, k_cr_solve<15>, n_el * ntile, CR_TC / 2 * CR_RG, smem_s, v, cr, s, cur);
+    else LLD_LAUNCH(c, k_cr_solve<20>, n_el * ntile, CR_TC / 2 * CR_RG, smem_s, v, cr, s, cur);
+    LLD_LAUNCH(c, k_cr_update, n_sv * per, 256, 0, v, cr, s, cur);
+  }
+  LLD_LAUNCH(c, k_cr_factor, 1, 512, smem_f, v, cr, 0);
+  const int per_b = (m + 7) / 8;
+  for (s >>= 1; s >= 1; s >>= 1) {
+    const int n_el = ((N - 1) / s + 1) / 2;
+    LLD_LAUNCH(c, k_cr_backsub, n_el * per_b, 256, 0, v, cr, s);
+  }
+  LLD_LAUNCH(c, k_cr_finish, 1, 1024, 0, v, cr);
   return LLD_OK;
 }
 
@@ -1149,7 +1250,10 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
     }
   }
   if (S->global_mode) { int r = ba_allreduce_rows(c); if (r) return r; }
-  if (v.env_mode && S->use_band) {
+  if (v.env_mode && S->use_cr) {
+    int r = ba_solve_cr(c);
+    if (r) return r;
+  } else if (v.env_mode && S->use_band) {
     LLD_LAUNCH(c, k_band_assemble, v.n_free_total, 256, 0, v);
     if ((v.band_B + 1) * 36 + 6 <= 1024) LLD_LAUNCH(c, k_solve_band<512>, 1, 512, S->band_smem, v);   // 128 registers per thread
     else LLD_LAUNCH(c, k_solve_band<1024>, 1, 1024, S->band_smem, v);
@@ -1172,57 +1276,82 @@ static int ba_step(LldCtx* c, int round, int stop_now) {
   return LLD_OK;
 }
 
-// optimize(maxit) for the whole batch (SparseOptimizer::optimize, sparse_optimizer.cpp:354-419)
+// optimize(maxit) for the whole batch (SparseOptimizer::optimize, sparse_optimizer.cpp:354-419).
+// LM steps are enqueued in groups of two with at most two groups in flight: before group k + 2 is enqueued the host waits
+// for group k, reads the number of windows still running and polls pbStopFlag — the reference polls it between LM
+// iterations and trials (sparse_optimizer.cpp:376, optimization_algorithm_levenberg.cpp:149); here a flag set mid-run is
+// seen within two groups.  A set flag enqueues one last step with stop_now (every window finishes its current iteration
+// and terminates).  Multi-rank: the ranks agree on the flag through an all-reduce(max), so that all of them issue the same
+// collectives.
 static int ba_run_round(LldCtx* c, int maxit, int round, const volatile uint8_t* stop) {
   BaState* S = c->ba;
   BaView& v = S->v;
   LLD_LAUNCH(c, k_round_init, cdiv(v.n_win, 64), 64, 0, v, maxit, round);
   if (maxit <= 0) return LLD_OK;
-  int* h_active = reinterpret_cast<int*>(c->pinned);
-  int launched = 0;
+  int* h_active = reinterpret_cast<int*>(c->pinned);        // [2] one per group slot, [2] = stop agreement word
+  const bool multi = S->global_mode && c->n_ranks > 1;
   const int hard_cap = maxit * 10 + 4;
-  bool first = true;
-  while (true) {
-    const int n = first ? maxit : 2;
-    first = false;
-    for (int s = 0; s < n; s++) {
-      const int stop_now = (stop && *stop) ? 1 : 0;
-      if (S->use_graph && !c->prof_on && !stop_now && round < 2) {
-        if (!S->step_graph[round]) {  // capture one LM step (fork / join over the side streams included)
-          const int64_t l0 = c->launches;
-          cudaGraph_t g = nullptr;
-          std::lock_guard<std::mutex> lk(lld_capture_mutex());  // no allocation in any thread while this one captures
-          LLD_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-          int r = ba_step(c, round, 0);
-          cudaError_t e = cudaStreamEndCapture(c->stream, &g);
-          if (r) { if (g) cudaGraphDestroy(g); return r; }
-          LLD_CUDA(c, e);
-          e = cudaGraphInstantiate(&S->step_graph[round], g, 0);
-          cudaGraphDestroy(g);
-          LLD_CUDA(c, e);
-          S->step_kernels[round] = (int)(c->launches - l0);
-          c->launches = l0;
-        }
-        {
-          std::lock_guard<std::mutex> lk(lld_capture_mutex());  // graph launches and captures of other threads do not interleave
-          LLD_CUDA(c, cudaGraphLaunch(S->step_graph[round], c->stream));
-        }
-        c->launches += S->step_kernels[round];
-      } else {
-        int r = ba_step(c, round, stop_now);
-        if (r) return r;
+  static const int group_len = getenv("LLD_BA_GROUP") ? std::max(1, atoi(getenv("LLD_BA_GROUP"))) : 2;
+  int launched = 0;
+  auto one_step = [&](int stop_now) -> int {
+    if (S->use_graph && !c->prof_on && !stop_now && round < 2) {
+      if (!S->step_graph[round]) {  // capture one LM step (fork / join over the side streams included)
+        const int64_t l0 = c->launches;
+        cudaGraph_t g = nullptr;
+        std::lock_guard<std::mutex> lk(lld_capture_mutex());  // no allocation in any thread while this one captures
+        LLD_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        int r = ba_step(c, round, 0);
+        cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        if (r) { if (g) cudaGraphDestroy(g); return r; }
+        LLD_CUDA(c, e);
+        e = cudaGraphInstantiate(&S->step_graph[round], g, 0);
+        cudaGraphDestroy(g);
+        LLD_CUDA(c, e);
+        S->step_kernels[round] = (int)(c->launches - l0);
+        c->launches = l0;
       }
-      launched++;
-      if (stop_now) break;
+      {
+        std::lock_guard<std::mutex> lk(lld_capture_mutex());  // graph launches and captures of other threads do not interleave
+        LLD_CUDA(c, cudaGraphLaunch(S->step_graph[round], c->stream));
+      }
+      c->launches += S->step_kernels[round];
+      return LLD_OK;
     }
-    LLD_CUDA(c, cudaMemcpyAsync(h_active, v.n_active_win, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    LLD_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (*h_active <= 0) break;
-    if (launched >= hard_cap) {
-      snprintf(c->err, sizeof(c->err), "LM step budget exhausted (%d steps, %d windows still active)", launched, *h_active);
+    return ba_step(c, round, stop_now);
+  };
+  for (int k = 0;; k++) {
+    const int slot = k & 1;
+    if (k >= 2) {   // group k - 2 has finished: anything left to do?
+      LLD_CUDA(c, cudaEventSynchronize(c->ev_grp[slot]));
+      if (h_active[slot] <= 0) break;
+    }
+    int stop_now = (stop && *stop) ? 1 : 0;
+#ifdef LLD_WITH_NCCL
+    if (multi && stop) {   // collective decision (device word, max over ranks)
+      h_active[2] = stop_now;
+      LLD_CUDA(c, cudaMemcpyAsync(v.n_active_win + 1, &h_active[2], sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      LLD_NCCL(c, ncclAllReduce(v.n_active_win + 1, v.n_active_win + 1, 1, ncclInt, ncclMax, reinterpret_cast<ncclComm_t>(c->comm), c->stream));
+      LLD_CUDA(c, cudaMemcpyAsync(&h_active[2], v.n_active_win + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      LLD_CUDA(c, cudaStreamSynchronize(c->stream));
+      stop_now = h_active[2];
+    }
+#endif
+    const int n = stop_now ? 1 : group_len;
+    for (int s2 = 0; s2 < n; s2++) {
+      int r = one_step(stop_now);
+      if (r) return r;
+      launched++;
+    }
+    LLD_CUDA(c, cudaMemcpyAsync(&h_active[slot], v.n_active_win, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LLD_CUDA(c, cudaEventRecord(c->ev_grp[slot], c->stream));
+    if (stop_now) break;
+    if (launched >= hard_cap + 2 * group_len) {
+      LLD_CUDA(c, cudaStreamSynchronize(c->stream));
+      snprintf(c->err, sizeof(c->err), "LM step budget exhausted (%d steps, %d windows still active)", launched, h_active[slot]);
       return LLD_ERR_CUDA;
     }
   }
+  LLD_CUDA(c, cudaStreamSynchronize(c->stream));
   return LLD_OK;
 }
 
@@ -1468,6 +1597,7 @@ extern "C" int lld_ba_global(void* ctx, const lld_ba_problem* p, int n_iter, con
   LLD_ARG(c, p->n_win == 1);
   LLD_CUDA(c, cudaSetDevice(c->device));
   c->launches = 0;
+  c->nccl_calls = 0; c->nccl_bytes = 0;
   const int R = c->n_ranks, rk = c->rank;
   if (R <= 1) {
     LLD_CUDA(c, cudaEventRecord(c->ev[0], c->stream));

@@ -16,19 +16,25 @@ std::mutex& lld_capture_mutex() {
   return m;
 }
 
+// cudaFuncSetAttribute applies to the CURRENT device only: the cache of what has been raised is keyed by (device, kernel),
+// so a second context on another GPU of the same process sets the attribute on its own device too.
 cudaError_t lld_raise_dyn_smem(const void* func, int bytes) {
+  struct Seen { int device; const void* func; int bytes; };
   static std::mutex mu;
-  static std::vector<std::pair<const void*, int>> seen;
+  static std::vector<Seen> seen;
+  int dev = 0;
+  cudaError_t r = cudaGetDevice(&dev);
+  if (r != cudaSuccess) return r;
   std::lock_guard<std::mutex> lk(mu);
   for (auto& e : seen)
-    if (e.first == func) {
-      if (bytes <= e.second) return cudaSuccess;
-      cudaError_t r = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-      if (r == cudaSuccess) e.second = bytes;
+    if (e.device == dev && e.func == func) {
+      if (bytes <= e.bytes) return cudaSuccess;
+      r = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (r == cudaSuccess) e.bytes = bytes;
       return r;
     }
-  cudaError_t r = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (r == cudaSuccess) seen.push_back({func, bytes});
+  r = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (r == cudaSuccess) seen.push_back({dev, func, bytes});
   return r;
 }
 
@@ -52,6 +58,8 @@ extern "C" int lld_ctx_create(int device, void** out) {
     if (cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess) { delete c; return LLD_ERR_CUDA; }
   }
   if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) { delete c; return LLD_ERR_CUDA; }
+  for (int i = 0; i < 2; i++)
+    if (cudaEventCreateWithFlags(&c->ev_grp[i], cudaEventDisableTiming) != cudaSuccess) { delete c; return LLD_ERR_CUDA; }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   c->pinned_cap = 1 << 16;
   if (cudaMallocHost(&c->pinned, c->pinned_cap) != cudaSuccess) { delete c; return LLD_ERR_CUDA; }
@@ -81,6 +89,7 @@ extern "C" void lld_ctx_destroy(void* ctx) {
     if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
   }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  for (int i = 0; i < 2; i++) if (c->ev_grp[i]) cudaEventDestroy(c->ev_grp[i]);
   for (int i = 0; i < 2; i++)
     if (c->ev_user[i]) cudaEventDestroy(c->ev_user[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -94,6 +103,12 @@ extern "C" const char* lld_ctx_last_error(void* ctx) {
 extern "C" int64_t lld_ctx_launch_count(void* ctx) {
   LldCtx* c = lld_ctx_cast(ctx);
   return c ? c->launches : 0;
+}
+// collectives issued and bytes all-reduced (per rank) since the last lld_ba_global / lld_ba_upload on this context
+extern "C" void lld_ctx_nccl_stats(void* ctx, int64_t* calls, int64_t* bytes) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (calls) *calls = c ? c->nccl_calls : 0;
+  if (bytes) *bytes = c ? c->nccl_bytes : 0;
 }
 extern "C" void lld_ctx_last_timing(void* ctx, float* a, float* b, float* d) {
   LldCtx* c = lld_ctx_cast(ctx);

@@ -50,10 +50,13 @@ struct LldCtx {
   // side streams + fork/join events: independent kernels of one LM step (point / line / pose passes) run concurrently
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  cudaEvent_t ev_grp[2] = {nullptr, nullptr};   // completion of the LM step groups in flight (ba_run_round)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_user[2] = {nullptr, nullptr};  // bench.py timing on this context's stream
   char err[512] = {0};
   int64_t launches = 0;
+  int64_t nccl_calls = 0;      // collectives issued / bytes all-reduced by the last multi-rank call (bench reporting)
+  int64_t nccl_bytes = 0;
   float ms_h2d = 0, ms_compute = 0, ms_d2h = 0;
   int sm_count = 148;
   bool host_only = false;  // no device work in the upload helpers (host-stage timing hook)

@@ -117,6 +117,40 @@ def test_local_ba_stop_flag(gpu_ctx):
     assert np.abs(g["pt_xyz"] - p["pt_xyz"]).max() == 0
 
 
+def test_local_ba_stop_flag_mid_run(gpu_ctx):
+    """pbStopFlag raised by another thread while the LM steps run: the library polls it between groups of two steps
+    (reference: between iterations and trials, sparse_optimizer.cpp:376), finishes the current iteration of every window and
+    returns a consistent state.  The delay is swept because the host stage in front of the LM steps takes a few ms."""
+    import threading
+    import time
+    p = synth.make_local_ba_batch(8, 20, 5000, 1000, 77)     # < 16 windows: the single-context path, ~1 ms per LM step
+    full = api.ba_local(p, 5, 15, impl="gpu", ctx=gpu_ctx)
+    n_full = int(full["n_iter_done"].sum())
+    mid = 0
+    for delay_ms in (1, 2, 3, 4, 5, 6, 8, 10, 12, 15, 20):
+        stop = np.zeros(1, np.uint8)
+
+        def setter():
+            time.sleep(delay_ms * 1e-3)
+            stop[0] = 1
+
+        th = threading.Thread(target=setter)
+        th.start()
+        g = api.ba_local(p, 5, 15, impl="gpu", ctx=gpu_ctx, stop=stop)
+        th.join()
+        n = int(g["n_iter_done"].sum())
+        assert 0 <= n <= n_full
+        assert np.all(g["n_iter_done"] <= full["n_iter_done"])
+        assert np.all(np.isfinite(g["kf_Tcw"])) and np.all(np.isfinite(g["pt_xyz"]))
+        for w in range(8):   # the iterations that did run are the ones of the uninterrupted run (same trajectory, cut short)
+            k = int(g["n_iter_done"][w, 0])
+            if k:
+                assert np.allclose(g["chi2_log"][w, :k + 1], full["chi2_log"][w, :k + 1], rtol=1e-12, atol=0)
+        if 0 < n < n_full:
+            mid += 1
+    assert mid >= 1, "no run was interrupted between its first and its last LM iteration"
+
+
 @pytest.mark.parametrize("robust", [False, True])
 def test_global_ba_small(gpu_ctx, robust):
     p = synth.make_global_ba(40, 4000, 800, 11, robust_points=robust)
@@ -327,8 +361,8 @@ def test_line_match_single_small_pair(gpu_ctx, line_path):
 
 # ------------------------------------------------------------------------------------------------------------------
 # BASELINE.json full sizes.  The oracle is fast enough for a complete comparison of the matchers and of one GPU's share
-# of the batched configurations; the global BA is compared through its LM trace (chi2 per iteration, iteration and trial
-# counts): along a 1500-keyframe chain the final poses are gauge-weak and are not a stable quantity to compare.
+# of the batched configurations.  Global BA: LM trace plus final poses, the latter with a tolerance that follows the
+# conditioning the oracle itself exhibits (see test_full_size_global_ba_config).
 # ------------------------------------------------------------------------------------------------------------------
 def _point_edge_chi2(p, out, e):
     """chi2 of point edge e at the final state (double precision restatement of the stereo / mono residual) and its gate"""
@@ -405,11 +439,55 @@ def test_full_size_batched_local_ba_config(gpu_ctx):
     assert rel.max() <= CHI2_RTOL, rel.max()
 
 
+def _permute_landmarks(p, seed):
+    """the same problem with points and lines in a shuffled order: only the order of the floating-point sums changes"""
+    rng = np.random.default_rng(seed)
+    q = dict(p)
+    orders = []
+    for off_key, lm_keys, obs_keys, n_key in (("pt_obs_off", ["pt_xyz"], ["pt_obs_kf", "pt_obs_uvr", "pt_obs_info"], "pt_off"),
+                                              ("ln_obs_off", ["ln_x0_dir"], ["ln_obs_kf", "ln_obs_left", "ln_obs_right", "ln_obs_info", "ln_obs_stereo"], "ln_off")):
+        n = int(p[n_key][-1])
+        order = rng.permutation(n)
+        off = p[off_key].astype(np.int64)
+        cnt = (off[1:] - off[:-1])[order]
+        start = off[:-1][order]
+        idx = np.repeat(start - np.concatenate([[0], np.cumsum(cnt)[:-1]]), cnt) + np.arange(int(cnt.sum()))
+        for k in lm_keys:
+            q[k] = np.ascontiguousarray(p[k][order])
+        for k in obs_keys:
+            q[k] = np.ascontiguousarray(p[k][idx])
+        q[off_key] = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+        orders.append(order)
+    return q, orders
+
+
 def test_full_size_global_ba_config(gpu_ctx):
-    """configs[4]: 1.5k keyframes / 300k points / 60k lines, 10 iterations: LM trace against the oracle"""
+    """configs[4]: 1.5k keyframes / 300k points / 60k lines, 10 iterations (bRobust = false as LoopClosing.cc:652).
+
+    LM trace: iterations, trials, chi2 per iteration within 1e-6 (measured 4e-14 at iteration 0, 3e-11 up to iteration 6,
+    4e-8 at iteration 10 — the float `invz` of the stereo edge separates any two correct implementations, see
+    tests/test_oracle_pin.py).
+    Final poses: the problem is far from converged after 10 iterations (chi2 1.1e9) and has ONE weakly determined mode,
+    localised at keyframes 1283-1299 of this trajectory.  The oracle run twice on the same problem with the landmark order
+    permuted (tools/gba_spread.py, profiles/r2_gba_oracle_spread*.json) moves by 1.1e-4 m there and by 2e-8 m (median)
+    elsewhere although only its summation order changed; the GPU-vs-oracle difference has exactly that shape (a constant
+    multiple of the oracle's own spread at every keyframe, ratio 88-103 over 99 % of the keyframes).  So the 1e-5 m bar is
+    applied where the problem determines the pose to that level — every keyframe whose position the GPU itself reproduces
+    to 1e-5 m under a landmark permutation (98.8 % of them) — and the remaining ones must stay within 30x of the GPU's own
+    spread at that keyframe (measured: 0.25x ... 0.6x)."""
     p = synth.make_global_ba(1500, 300000, 60000, synth.seed_for(5))
     g = api.ba_global(p, 10, impl="gpu", ctx=gpu_ctx)
     o = api.ba_global(p, 10, impl="oracle")
     assert np.array_equal(g["n_iter_done"], o["n_iter_done"]) and np.array_equal(g["trials_log"], o["trials_log"])
     rel = np.abs(g["chi2_log"] - o["chi2_log"]) / np.maximum(np.abs(o["chi2_log"]), 1e-9)
     assert rel.max() <= CHI2_RTOL, rel.max()
+    assert rel[0, :3].max() <= 1e-9, rel[0, :3]
+    q, _ = _permute_landmarks(p, 7)
+    g2 = api.ba_global(q, 10, impl="gpu", ctx=gpu_ctx)
+    spread = np.abs(g["kf_Tcw"][:, 9:] - g2["kf_Tcw"][:, 9:]).max(axis=1)     # keyframes keep their order
+    dT = np.abs(g["kf_Tcw"][:, 9:] - o["kf_Tcw"][:, 9:]).max(axis=1)
+    well = spread <= POS_TOL
+    assert well.mean() >= 0.95, well.mean()
+    assert dT[well].max() <= POS_TOL, dT[well].max()
+    assert np.all(dT[~well] <= 30 * spread[~well]), (dT[~well] / spread[~well]).max()
+    assert np.median(dT) <= 1e-5 and np.median(rot_angle(g["kf_Tcw"], o["kf_Tcw"])) <= ROT_TOL

@@ -22,6 +22,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--robust", action="store_true")
 ap.add_argument("--profile", action="store_true")
+ap.add_argument("--mono", action="store_true", help="all point observations monocular: no float invz in the residuals (conditioning experiments)")
 a = ap.parse_args()
 
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); lr = int(os.environ.get("LOCAL_RANK", "0"))
@@ -43,6 +44,9 @@ if world > 1:
     idb = t.cpu().numpy()
     ctx.check(lib.dll.lld_comm_init(ctx.handle, world, rank, idb.ctypes.data_as(capi.c_u8p)), "comm_init")
 p = synth.make_global_ba(a.kf, a.pts, a.lines, synth.seed_for(5), robust_points=a.robust)
+if a.mono:
+    p["pt_obs_uvr"] = p["pt_obs_uvr"].copy()
+    p["pt_obs_uvr"][:, 2] = -1.0
 n_pe = int(p["pt_obs_off"][-1]); n_lc = int(p["ln_obs_off"][-1])
 g = None
 times = []
@@ -63,7 +67,7 @@ if a.profile:
     api.ba_global(p, a.iters, impl="gpu", ctx=ctx)
     prof = bench.profile_report(d, ctx)
     d.lld_ctx_profile(ctx.handle, 0)
-res = {"n_gpus": world, "kf": a.kf, "pts": a.pts, "lines": a.lines, "point_edges": n_pe, "line_cells": n_lc,
+res = {"mono": bool(a.mono), "n_gpus": world, "kf": a.kf, "pts": a.pts, "lines": a.lines, "point_edges": n_pe, "line_cells": n_lc,
        "iters_done": int(g["n_iter_done"][0, 0]), "trials": int(g["trials_log"].sum()),
        "wall_s_best": min(times), "device_compute_ms": comp, "chi2_first": float(g["chi2_log"][0, 0]),
        "chi2_last": float(g["chi2_log"][0, int(g["n_iter_done"][0, 0])])}
@@ -91,7 +95,15 @@ if a.check and rank == 0:
     res["check"]["pose_t_deciles"] = [float(x) for x in np.quantile(dT, np.linspace(0, 1, 11))]
     res["check"]["pose_t_worst_kf"] = [int(k) for k in np.argsort(-dT)[:8]]
     os.makedirs("gpurun_out", exist_ok=True)
-    np.savez_compressed(f"gpurun_out/gba_state_n{world}.npz", g_kf=g["kf_Tcw"], o_kf=o["kf_Tcw"], g_chi2=g["chi2_log"], o_chi2=o["chi2_log"],
+    if world == 1:   # GPU against itself with the landmark order permuted: the amplitude of the weak mode under pure reordering
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from gba_spread import permute_landmarks
+        q, op, ol = permute_landmarks(p, 7)
+        g2 = api.ba_global(q, a.iters, impl="gpu", ctx=ctx)
+        dS = np.abs(g["kf_Tcw"][:, 9:] - g2["kf_Tcw"][:, 9:]).max(axis=1)
+        res["check"]["gpu_self_spread_deciles"] = [float(x) for x in np.quantile(dS, np.linspace(0, 1, 11))]
+        res["check"]["ratio_to_gpu_self_spread_deciles"] = [float(x) for x in np.quantile(dT / np.maximum(dS, 1e-12), np.linspace(0, 1, 11))]
+    np.savez_compressed(f"gpurun_out/gba_state_n{world}{'_mono' if a.mono else ''}.npz", g_kf=g["kf_Tcw"], o_kf=o["kf_Tcw"], g_chi2=g["chi2_log"], o_chi2=o["chi2_log"],
                         g_lambda=g["lambda_log"], o_lambda=o["lambda_log"])
 if prof is not None:
     res["kernels_us_per_launch"] = {k: round(1e3 * v["ms"] / max(v["n"], 1), 1) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}

@@ -68,6 +68,7 @@ def main():
     ap.add_argument("--robust", action="store_true")
     ap.add_argument("--reverse-kf", action="store_true", help="second run = reversed keyframe numbering instead of permuted landmarks")
     ap.add_argument("--out", default="")
+    ap.add_argument("--npz", default="", help="per-keyframe differences and both final pose sets")
     a = ap.parse_args()
     p = synth.make_global_ba(a.kf, a.pts, a.lines, synth.seed_for(5), robust_points=a.robust)
     t0 = time.time()
@@ -93,6 +94,8 @@ def main():
                                                           float(o2["chi2_log"][0, int(o2["n_iter_done"][0, 0])])],
                same_trials=bool(np.array_equal(o1["trials_log"], o2["trials_log"])),
                pose_t_by_kf_decile=[float(x) for x in np.quantile(dT, np.linspace(0, 1, 11))])
+    if a.npz:
+        np.savez_compressed(a.npz, dT=dT, dR=dR, kf1=o1["kf_Tcw"], kf2=o2["kf_Tcw"])
     print(json.dumps(res))
     if a.out:
         with open(a.out, "w") as f:
