@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "ba_kernels.cuh"
+#include "ba_fused.cuh"
 #include "cr_solver.cuh"
 #include "lld_ctx.h"
 
@@ -57,16 +58,25 @@ struct BaState {
   uint8_t* d_pt_bad = nullptr;
   uint8_t* d_ln_bad = nullptr;
   // one LM step captured as a CUDA graph per round (kernel arguments differ: round, robust flags)
-  cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
-  int step_kernels[2] = {0, 0};
+  // fused linearise -> Schur path (ba_fused.cuh): piece records and the flat edge maps it walks
+  bool fused = false;
+  const FusedPiece* d_pieces = nullptr;
+  int n_pieces_pt = 0, n_pieces_ln = 0;
+  const int *d_ws_edge_p = nullptr, *d_ws_edge_l = nullptr;
+  const int *d_fx_off_p = nullptr, *d_fx_edge_p = nullptr, *d_fx_lm_p = nullptr;
+  const int *d_fx_off_l = nullptr, *d_fx_edge_l = nullptr, *d_fx_lm_l = nullptr;
+  // [round][0: first step of the round (separate kernels, lambda_0), 1: fused step]
+  cudaGraphExec_t step_graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  int step_kernels[2][2] = {{0, 0}, {0, 0}};
   void drop_graphs() {
-    if (!step_graph[0] && !step_graph[1]) return;
+    if (!step_graph[0][0] && !step_graph[0][1] && !step_graph[1][0] && !step_graph[1][1]) return;
     std::lock_guard<std::mutex> lk(lld_capture_mutex());
-    for (int r = 0; r < 2; r++) {
-      if (step_graph[r]) cudaGraphExecDestroy(step_graph[r]);
-      step_graph[r] = nullptr;
-      step_kernels[r] = 0;
-    }
+    for (int r = 0; r < 2; r++)
+      for (int k = 0; k < 2; k++) {
+        if (step_graph[r][k]) cudaGraphExecDestroy(step_graph[r][k]);
+        step_graph[r][k] = nullptr;
+        step_kernels[r][k] = 0;
+      }
   }
 };
 
@@ -124,6 +134,8 @@ struct BaHost {
   pvec<uint32_t> pts_mask, lns_mask;
   pvec<int> gb_off, gv_off;
   pvec<SchurItem> it_rec, it_tmp;
+  pvec<FusedPiece> pc_rec, pc_tmp;
+  pvec<int> fx_off_p, fx_edge_p, fx_lm_p, fx_off_l, fx_edge_l, fx_lm_l;
   std::vector<uint64_t> it_keys;
   pvec<long long> gb_src, gv_src;
   std::vector<BaDenseJob> jobs;
@@ -640,7 +652,9 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         while (e < loff[w + 1] && mask[e] == mask[b] && e - b < PIECE_CAP) e++;
         const uint32_t m = mask[b];
         const int n = __builtin_popcount(m);
-        if (n > 0) {
+        if (n == 0) {   // seen by fixed keyframes only: a piece for the fused kernel (inverse records), no Schur tasks
+          J.pb.push_back(b); J.pe.push_back(e); J.pn.push_back(0); J.pout.push_back(J.dsize);
+        } else {
           const int pc = (int)J.pb.size();
           J.pb.push_back(b); J.pe.push_back(e); J.pn.push_back(n); J.pout.push_back(J.dsize);
           const int npair = n * (n + 1) / 2, ntask = 6 * npair + n;
@@ -650,9 +664,9 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
           int pr = 0;
           for (int ia = 0; ia < n; ia++)
             for (int ib = ia; ib < n; ib++, pr++) J.gb.push_back({nb_off[g0 + hl[ia]] + (hl[ib] - hl[ia]), J.dsize + 36LL * pr});
-          for (int ia = 0; ia < n; ia++) J.gv.push_back({g0 + hl[ia], J.dsize + 6LL * (6 * npair + ia)});
+          for (int ia = 0; ia < n; ia++) J.gv.push_back({g0 + hl[ia], J.dsize + 36LL * npair + (long long)SCHUR_KS * ia});
           for (int t0 = 0; t0 < 2 * npair + n; t0 += SP_TPB) { J.itp.push_back(pc); J.itt.push_back(t0); }
-          J.dsize += 6LL * ntask;
+          J.dsize += 36LL * npair + (long long)SCHUR_KS * n;
         }
         b = e;
       }
@@ -683,7 +697,73 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         schur_item_shape(kind == 0 ? 3 : 4, R.n, R.nl, R.t0, &R.lc, &R.S, &R.nchunk);
       }
     });
-    stage("dense: item records");
+    // piece records of the fused path: one per piece, ordered per kind by decreasing cost and dealt in snake order over the
+    // persistent CTAs (same balancing as the items above)
+    std::vector<int> jp(n_jobs + 1, 0);
+    for (size_t jid = 0; jid < n_jobs; jid++) jp[jid + 1] = jp[jid] + (int)jobs[jid].pb.size();
+    S->n_pieces_pt = jp[std::min<size_t>((size_t)nw, n_jobs)];
+    S->n_pieces_ln = jp[n_jobs] - S->n_pieces_pt;
+    H.pc_rec.resize(std::max(jp[n_jobs], 1)); H.pc_tmp.resize(std::max(jp[n_jobs], 1));
+    par_for((int)n_jobs, [&](int jid) {
+      Job& J = jobs[jid];
+      const int kind = jid / nw, jw = jid % nw;
+      for (size_t q = 0; q < J.pb.size(); q++) {
+        FusedPiece& R = H.pc_tmp[jp[jid] + q];
+        R.l0 = J.pb[q]; R.nl = J.pe[q] - J.pb[q]; R.n = J.pn[q]; R.w = jw;
+        R.w0 = (kind == 0 ? pts_w0 : lns_w0)[J.pb[q]]; R.out = J.pout[q] + jd[jid];
+        R.lc = fused_chunk_len(kind == 0 ? 3 : 4, R.n, R.nl); R.pad0 = R.pad1 = R.pad2 = 0;
+      }
+    });
+    auto piece_order = [&](int kind) {
+      const int i0 = kind == 0 ? 0 : S->n_pieces_pt, i1 = kind == 0 ? S->n_pieces_pt : jp[n_jobs];
+      const int cntk = i1 - i0;
+      if (cntk <= 0) return;
+      const int G = std::min(cntk, (kind == 0 ? 4 : 2) * c->sm_count);
+      constexpr int NB = 2048;
+      std::vector<int> cnt(NB + 1, 0), bk((size_t)cntk);
+      for (int i = i0; i < i1; i++) {
+        const FusedPiece& R = H.pc_tmp[i];
+        const int ntask = R.n * (R.n + 1) + R.n, passes = (ntask + FU_TPB - 1) / FU_TPB;
+        const uint64_t cost = 32 + (uint64_t)R.nl * (uint64_t)(passes * (kind == 0 ? 6 : 14) * R.n + ntask);
+        const int b = NB - 1 - (int)std::min<uint64_t>(cost >> 5, NB - 1);
+        bk[(size_t)(i - i0)] = b;
+        cnt[b + 1]++;
+      }
+      for (int q = 0; q < NB; q++) cnt[q + 1] += cnt[q];
+      for (int i = i0; i < i1; i++) {
+        const int k = cnt[bk[(size_t)(i - i0)]]++;
+        const int r = k / G, j = k - r * G, len = std::min(G, cntk - r * G);
+        const int pos = (r & 1) ? len - 1 - j : j;
+        H.pc_rec[i0 + r * G + pos] = H.pc_tmp[i];
+      }
+    };
+    // edges to fixed keyframes by sorted landmark position (they feed H_ll / b_l only): offsets, edge ids, owners
+    auto fixed_lists = [&](const int* lm_off, const int* off, const pvec<int>& ekf, const pvec<int>& order, int n_lm,
+                           pvec<int>& f_off, pvec<int>& f_edge, pvec<int>& f_lm) {
+      f_off.assign((size_t)n_lm + 1, 0);
+      par_for(nw, [&](int w) {
+        for (int oi = lm_off[w]; oi < lm_off[w + 1]; oi++) {
+          const int i = order[oi];
+          int k = 0;
+          for (int e = off[i]; e < off[i + 1]; e++) k += kf_g[ekf[e]] < 0;
+          f_off[(size_t)oi + 1] = k;
+        }
+      });
+      for (int i = 0; i < n_lm; i++) f_off[(size_t)i + 1] += f_off[(size_t)i];
+      f_edge.resize(std::max(f_off[(size_t)n_lm], 1)); f_lm.resize(std::max(f_off[(size_t)n_lm], 1));
+      par_for(nw, [&](int w) {
+        for (int oi = lm_off[w]; oi < lm_off[w + 1]; oi++) {
+          const int i = order[oi];
+          int k = f_off[(size_t)oi];
+          for (int e = off[i]; e < off[i + 1]; e++)
+            if (kf_g[ekf[e]] < 0) { f_edge[(size_t)k] = e; f_lm[(size_t)k] = oi; k++; }
+        }
+      });
+    };
+    par_for(2, [&](int kind) { piece_order(kind); });
+    fixed_lists(p->pt_off, p->pt_obs_off, pe_kf, pt_order, n_pt, H.fx_off_p, H.fx_edge_p, H.fx_lm_p);
+    fixed_lists(p->ln_off, p->ln_obs_off, lc_kf, ln_order, n_ln, H.fx_off_l, H.fx_edge_l, H.fx_lm_l);
+    stage("dense: item records + pieces + fixed-edge lists");
     {
       // k_schur_tile's CTAs take items b, b + G, ... : order each kind by decreasing cost and deal the rows in snake
       // order, so that every CTA gets about the same landmark x task volume
@@ -900,6 +980,18 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   UP(tmp_l, gb_src.data(), gb_src.size()); v.gb_src = tmp_l;
   UP(tmp_i, gv_off.data(), gv_off.size()); v.gv_off = tmp_i;
   UP(tmp_l, gv_src.data(), gv_src.size()); v.gv_src = tmp_l;
+  int *d_ws_p = nullptr, *d_ws_l = nullptr;
+  if (dense) {
+    FusedPiece* tmp_p; UP(tmp_p, H.pc_rec.data(), (size_t)(S->n_pieces_pt + S->n_pieces_ln)); S->d_pieces = tmp_p;
+    UP(tmp_i, H.fx_off_p.data(), H.fx_off_p.size()); S->d_fx_off_p = tmp_i;
+    UP(tmp_i, H.fx_edge_p.data(), H.fx_edge_p.size()); S->d_fx_edge_p = tmp_i;
+    UP(tmp_i, H.fx_lm_p.data(), H.fx_lm_p.size()); S->d_fx_lm_p = tmp_i;
+    UP(tmp_i, H.fx_off_l.data(), H.fx_off_l.size()); S->d_fx_off_l = tmp_i;
+    UP(tmp_i, H.fx_edge_l.data(), H.fx_edge_l.size()); S->d_fx_edge_l = tmp_i;
+    UP(tmp_i, H.fx_lm_l.data(), H.fx_lm_l.size()); S->d_fx_lm_l = tmp_i;
+    DEV(d_ws_p, int, n_pw); S->d_ws_edge_p = d_ws_p;
+    DEV(d_ws_l, int, n_lw); S->d_ws_edge_l = d_ws_l;
+  }
   {
     uint32_t* tmp_m;
     UP(tmp_m, pts_mask.data(), n_pt); v.pts_mask = tmp_m;
@@ -993,6 +1085,11 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     const bool dense_single = v.dense_mode && !(global_mode && c->n_ranks > 1) && v.n_slices == 1 && S->max_n <= SMEM_SOLVE_MAX_N && !v.env_mode;
     S->forked = allow && dense_single;
     S->use_graph = allow && dense_single;
+    // fused linearise -> Schur steps after the first step of a round (ba_fused.cuh).  Opt-in (LLD_BA_FUSED=1): measured on the
+    // bench workload it moves 2.3x fewer DRAM bytes per step but is slower than the separate kernels (per-piece overheads and
+    // barrier-separated phases on ~37-landmark pieces; profiles/r2f_k_fused_full.txt), so the separate kernels stay the default.
+    const char* f = getenv("LLD_BA_FUSED");
+    S->fused = dense_single && !S->gather_long && (f && f[0] == '1');
   }
   // derived index arrays (stream-ordered after the uploads, before any consumer)
   {
@@ -1004,11 +1101,15 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     if (v.dense_mode) {
       if (n_pe) LLD_LAUNCH(c, k_dense_wpos, grid(n_pe), 256, 0, n_pe, v.pe_pt, v.pe_kf, v.kf_g, v.pt_win, v.w_g0, v.pt_spos, v.pts_mask, v.pts_w0, d_pe_wpos);
       if (n_lc) LLD_LAUNCH(c, k_dense_wpos, grid(n_lc), 256, 0, n_lc, v.lc_ln, v.lc_kf, v.kf_g, v.ln_win, v.w_g0, v.ln_spos, v.lns_mask, v.lns_w0, d_lc_wpos);
+      if (n_pe) LLD_LAUNCH(c, k_ws_edge, grid(n_pe), 256, 0, n_pe, d_pe_wpos, d_ws_p);
+      if (n_lc) LLD_LAUNCH(c, k_ws_edge, grid(n_lc), 256, 0, n_lc, d_lc_wpos, d_ws_l);
     }
     LLD_CUDA(c, cudaGetLastError());
   }
   // dynamic shared memory opt-in of the solvers (once per upload, outside any stream capture)
   if (v.dense_mode) {
+    LLD_CUDA(c, lld_raise_dyn_smem(k_fused<3>, (size_t)FU_SMEM_BYTES));
+    LLD_CUDA(c, lld_raise_dyn_smem(k_fused<4>, (size_t)FU_SMEM_BYTES));
     LLD_CUDA(c, lld_raise_dyn_smem(k_schur_tile<3>, (size_t)SP_SMEM_BYTES));
     LLD_CUDA(c, lld_raise_dyn_smem(k_schur_tile<4>, (size_t)SP_SMEM_BYTES));
   }
@@ -1204,10 +1305,50 @@ static int ba_step_forked(LldCtx* c, int round, int stop_now) {
   return LLD_OK;
 }
 
-// one LM step of every window still running
-static int ba_step(LldCtx* c, int round, int stop_now) {
+// Fused LM step (every step of a round but the first): 7 launches
+//   [k_fused<3> | k_fused<4>] -> k_reduce_fused -> k_solve -> [k_backsub_points | k_backsub_lines] -> k_decide_carry
+static int ba_step_fused(LldCtx* c, int round, int stop_now) {
   BaState* S = c->ba;
   BaView& v = S->v;
+  const int gp = cdiv(std::max(v.n_pt, 1), LM_TPB);
+  const bool par = S->forked && !c->prof_on;
+  cudaStream_t s0 = c->stream, s1 = par ? c->side[0] : c->stream;
+  auto fork = [&]() -> cudaError_t {
+    if (!par) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(c->ev_fork, s0);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(s1, c->ev_fork, 0);
+  };
+  auto join = [&]() -> cudaError_t {
+    if (!par) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(c->ev_join[0], s1);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(s0, c->ev_join[0], 0);
+  };
+  LLD_CUDA(c, fork());
+  if (S->n_pieces_pt)
+    LLD_LAUNCH_S(c, s0, k_fused<3>, std::min(S->n_pieces_pt, 4 * c->sm_count), FU_TPB, FU_SMEM_BYTES, v, S->d_pieces, S->n_pieces_pt,
+                 S->d_ws_edge_p, S->d_fx_off_p, S->d_fx_edge_p, S->d_fx_lm_p);
+  if (S->n_pieces_ln)
+    LLD_LAUNCH_S(c, s1, k_fused<4>, std::min(S->n_pieces_ln, 2 * c->sm_count), FU_TPB, FU_SMEM_BYTES, v, S->d_pieces + S->n_pieces_pt,
+                 S->n_pieces_ln, S->d_ws_edge_l, S->d_fx_off_l, S->d_fx_edge_l, S->d_fx_lm_l);
+  LLD_CUDA(c, join());
+  const int nblk = (int)S->n_nb_total;
+  LLD_LAUNCH_S(c, s0, k_reduce_fused, cdiv(nblk * 36 + 7 * v.n_free_total, 256), 256, 0, v, nblk);
+  { int r = launch_solve<true>(c, v, S->max_n); if (r) return r; }
+  LLD_CUDA(c, fork());
+  if (v.n_pt && v.n_pt <= PT_WIDE_MAX) LLD_LAUNCH_S(c, s0, k_backsub_points<4>, cdiv(v.n_pt * 4, LM_TPB), LM_TPB, 0, v);
+  else if (v.n_pt) LLD_LAUNCH_S(c, s0, k_backsub_points<1>, gp, LM_TPB, 0, v);
+  { int r = launch_line_kernel(c, s1, v, false); if (r) return r; }
+  LLD_CUDA(c, join());
+  LLD_LAUNCH_S(c, s0, k_decide_carry, v.n_win, FUSED_RED_TPB, 0, v, round, stop_now);
+  LLD_CUDA(c, cudaGetLastError());
+  return LLD_OK;
+}
+
+// one LM step of every window still running; first = first step of the round (every window at iteration 0)
+static int ba_step(LldCtx* c, int round, int stop_now, bool first = true) {
+  BaState* S = c->ba;
+  BaView& v = S->v;
+  if (S->fused && !first) return ba_step_fused(c, round, stop_now);
   if (S->forked && !c->prof_on) return ba_step_forked(c, round, stop_now);
   const int gp = cdiv(std::max(v.n_pt, 1), LM_TPB), gl = cdiv(std::max(v.n_ln, 1), LM_TPB);
   if (v.n_pt && v.n_pt <= PT_WIDE_MAX) LLD_LAUNCH(c, k_lin_points<4>, cdiv(v.n_pt * 4, LM_TPB), LM_TPB, 0, v);
@@ -1294,30 +1435,32 @@ static int ba_run_round(LldCtx* c, int maxit, int round, const volatile uint8_t*
   static const int group_len = getenv("LLD_BA_GROUP") ? std::max(1, atoi(getenv("LLD_BA_GROUP"))) : 2;
   int launched = 0;
   auto one_step = [&](int stop_now) -> int {
+    const bool first = launched == 0;
+    const int kind = (S->fused && !first) ? 1 : 0;
     if (S->use_graph && !c->prof_on && !stop_now && round < 2) {
-      if (!S->step_graph[round]) {  // capture one LM step (fork / join over the side streams included)
+      if (!S->step_graph[round][kind]) {  // capture one LM step (fork / join over the side streams included)
         const int64_t l0 = c->launches;
         cudaGraph_t g = nullptr;
         std::lock_guard<std::mutex> lk(lld_capture_mutex());  // no allocation in any thread while this one captures
         LLD_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        int r = ba_step(c, round, 0);
+        int r = ba_step(c, round, 0, first);
         cudaError_t e = cudaStreamEndCapture(c->stream, &g);
         if (r) { if (g) cudaGraphDestroy(g); return r; }
         LLD_CUDA(c, e);
-        e = cudaGraphInstantiate(&S->step_graph[round], g, 0);
+        e = cudaGraphInstantiate(&S->step_graph[round][kind], g, 0);
         cudaGraphDestroy(g);
         LLD_CUDA(c, e);
-        S->step_kernels[round] = (int)(c->launches - l0);
+        S->step_kernels[round][kind] = (int)(c->launches - l0);
         c->launches = l0;
       }
       {
         std::lock_guard<std::mutex> lk(lld_capture_mutex());  // graph launches and captures of other threads do not interleave
-        LLD_CUDA(c, cudaGraphLaunch(S->step_graph[round], c->stream));
+        LLD_CUDA(c, cudaGraphLaunch(S->step_graph[round][kind], c->stream));
       }
-      c->launches += S->step_kernels[round];
+      c->launches += S->step_kernels[round][kind];
       return LLD_OK;
     }
-    return ba_step(c, round, stop_now);
+    return ba_step(c, round, stop_now, first);
   };
   for (int k = 0;; k++) {
     const int slot = k & 1;

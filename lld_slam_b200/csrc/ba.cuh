@@ -15,6 +15,10 @@ namespace lld {
 
 enum : int { PH_LIN = 0, PH_RETRY = 1, PH_DONE = 2 };
 
+// dense mode, per keyframe slot of a piece in the partial-sum scratch (dpart): b_schur part (6) + H_pp upper triangle (21)
+// + b_p (6) + number of active edges (1); k_schur_tile fills the first 6, k_fused all of them
+constexpr int SCHUR_KS = 34;
+
 struct BaParams {
   int robust_pt, robust_ln;
   double delta_pt_mono, delta_pt_stereo, delta_ln_mono, delta_ln_stereo;

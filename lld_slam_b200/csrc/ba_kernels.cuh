@@ -1159,7 +1159,7 @@ __global__ void __launch_bounds__(SP_TPB, 4) k_schur_tile(BaView v, int item_bas
 #pragma unroll
           for (int q = 0; q < 18; q++) o[q] = acc[q];
         } else {
-          double* o = out + (size_t)36 * npair + (size_t)(task - 2 * npair) * 6;
+          double* o = out + (size_t)36 * npair + (size_t)(task - 2 * npair) * SCHUR_KS;
 #pragma unroll
           for (int q = 0; q < 6; q++) o[q] = acc[q];
         }
@@ -1175,7 +1175,7 @@ __global__ void __launch_bounds__(SP_TPB, 4) k_schur_tile(BaView v, int item_bas
         const int task = R.t0 + tl2;
         size_t o;
         if (task < 2 * npair) o = (size_t)(task >> 1) * 36 + (task & 1) * 18 + q;
-        else if (q < 6) o = (size_t)36 * npair + (size_t)(task - 2 * npair) * 6 + q;
+        else if (q < 6) o = (size_t)36 * npair + (size_t)(task - 2 * npair) * SCHUR_KS + q;
         else continue;
         double sum = 0;
         for (int s2 = 0; s2 < S; s2++) sum += red[(s2 * ntb + tl2) * 18 + q];

@@ -7,10 +7,15 @@
 // (INTEGRATION.md).  Header-only, C++14, no dependency besides include/lldba.h.
 //
 //   lld::Optimizer::LocalBundleAdjustment   <- src/Optimizer.cc:936-1388   (graph construction :1037-1218, write-back :1334-1386)
-//   lld::Optimizer::BundleAdjustment        <- src/Optimizer.cc:321-559
+//   lld::Optimizer::BundleAdjustment        <- src/Optimizer.cc:321-559     (+ AddLineMinimalGlobal :149-247)
+//   lld::Optimizer::GlobalBundleAdjustemnt  <- src/Optimizer.cc:312-319     (sic, the reference's spelling)
 //   lld::Optimizer::PoseOptimization        <- src/Optimizer.cc:653-932
-//   lld::ORBmatcher::SearchByProjection     <- src/ORBmatcher.cc:1328-1470
+//   lld::LineOptimizer                      <- include/LineOptimizer.h:11-33, src/LineOptimizer.cc:28-201
+//   lld::ORBmatcher::SearchByProjection     <- src/ORBmatcher.cc:1328-1470 (frame to frame) and :45-129 (frame to map points)
 //   lld::TwoFrameLineMatcher::MatchLines    <- src/TwoFrameLineMatcher.cc:26-77
+// Every entry point takes the library context as an extra first argument (the reference keeps its g2o optimizer on the
+// stack instead); Flatten* expose the flattened problem so that tests can compare it array by array with a reference
+// flattening (tests/hostcheck/shim_run.cpp).
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -47,15 +52,31 @@ struct MapPoint {
   float pos[3];                                      // GetWorldPos(), CV_32F
   std::map<KeyFrame*, size_t> observations;          // GetObservations()
   bool bad = false;
+  bool isBad() const { return bad; }
+  int Observations() const { return (int)observations.size(); }
   float mPosGBA[3];
   unsigned long mnBAGlobalForKF = 0;
+  // Frame::isInFrustum results read by SearchByProjection(Frame&, vector<MapPoint*>&, th)  (include/MapPoint.h:88-95)
+  bool mbTrackInView = false;
+  float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, mTrackViewCos = 0;
+  int mnTrackScaleLevel = 0;
+  uint8_t mDescriptor[32] = {0};                     // GetDescriptor()
 };
 struct MapLine {
   unsigned long mnId = 0;
   double X0[3], line_dir[3];                         // GetMinimalPos(): doubles (include/MapLine.h:120)
   std::map<KeyFrame*, size_t> observations;
   bool bad = false;
+  bool isBad() const { return bad; }
   int Observations() const { return (int)observations.size(); }
+};
+struct Map {                                          // the three getters GlobalBundleAdjustemnt uses (src/Optimizer.cc:314-317)
+  std::vector<KeyFrame*> keyframes;
+  std::vector<MapPoint*> points;
+  std::vector<MapLine*> lines;
+  std::vector<KeyFrame*> GetAllKeyFrames() const { return keyframes; }
+  std::vector<MapPoint*> GetAllMapPoints() const { return points; }
+  std::vector<MapLine*> GetAllMapLines() const { return lines; }
 };
 struct Frame {
   float mTcw[12];
@@ -87,6 +108,109 @@ namespace detail {
 inline void widen12(const float* T, std::vector<double>& out) { for (int i = 0; i < 12; i++) out.push_back((double)T[i]); }
 }
 
+// The flattened bundle-adjustment problem of ONE window (lld_ba_problem with n_win = 1) plus the owners needed to write
+// the result back into the caller's objects.
+struct FlatBA {
+  std::vector<KeyFrame*> kfs;                    // window-local keyframe index -> object
+  std::map<KeyFrame*, int> kf_index;
+  std::map<int, int> kf_index_by_id;             // mnId -> window-local index (LineOptimizer::AddLineMinimal is keyed by id)
+  std::vector<double> T, intr, lcam, pxyz, lxd, linfo;
+  std::vector<uint8_t> fixed, lstereo;
+  std::vector<int32_t> poff{0}, pkf, loff{0}, lkf;
+  std::vector<float> puvr, pinfo, lleft, lright;
+  std::vector<std::pair<KeyFrame*, MapPoint*>> edge_owner;   // one per point observation
+  std::vector<MapPoint*> points;                              // one per flattened point
+  std::vector<int> line_ids;                                  // one per flattened line (AddLineMinimal's line_id)
+  int32_t one_kf[2] = {0, 0}, one_pt[2] = {0, 0}, one_ln[2] = {0, 0};
+  lld_ba_problem p;
+  // results
+  std::vector<double> oT, oP, oL;
+  std::vector<uint8_t> pbad, lbad, lrem;
+  lld_ba_result r;
+
+  int AddKeyFrame(KeyFrame* k, bool is_fixed, const double line_cam[4]) {
+    const int i = (int)kfs.size();
+    kfs.push_back(k); kf_index[k] = i; kf_index_by_id[(int)k->mnId] = i;
+    for (int c = 0; c < 12; c++) T.push_back((double)k->Tcw[c]);          // Converter::toSE3Quat(pKF->GetPose())
+    fixed.push_back(is_fixed);
+    const double in[5] = {k->fx, k->fy, k->cx, k->cy, k->mbf};
+    intr.insert(intr.end(), in, in + 5);
+    lcam.insert(lcam.end(), line_cam, line_cam + 4);
+    return i;
+  }
+  // binds the pointers; call after the last Add*
+  void Finish() {
+    one_kf[1] = (int32_t)kfs.size(); one_pt[1] = (int32_t)points.size(); one_ln[1] = (int32_t)line_ids.size();
+    std::memset(&p, 0, sizeof(p));
+    p.n_win = 1; p.kf_off = one_kf; p.pt_off = one_pt; p.ln_off = one_ln;
+    p.kf_Tcw = T.data(); p.kf_fixed = fixed.data(); p.kf_intr = intr.data(); p.kf_line_cam = lcam.data();
+    p.pt_xyz = pxyz.data(); p.pt_obs_off = poff.data(); p.pt_obs_kf = pkf.data(); p.pt_obs_uvr = puvr.data(); p.pt_obs_info = pinfo.data();
+    p.ln_x0_dir = lxd.data(); p.ln_obs_off = loff.data(); p.ln_obs_kf = lkf.data(); p.ln_obs_left = lleft.data();
+    p.ln_obs_right = lright.data(); p.ln_obs_info = linfo.data(); p.ln_obs_stereo = lstereo.data();
+    oT.assign(T.size(), 0.0); oP.assign(pxyz.size(), 0.0); oL.assign(lxd.size(), 0.0);
+    pbad.assign(pkf.size() + 1, 0); lbad.assign(2 * lkf.size() + 2, 0); lrem.assign(line_ids.size() + 1, 0);
+    std::memset(&r, 0, sizeof(r));
+    r.kf_Tcw = oT.data(); r.pt_xyz = oP.data(); r.ln_x0_dir = oL.data();
+    r.pt_obs_bad = pbad.data(); r.ln_obs_bad = lbad.data(); r.ln_removed = lrem.data();
+  }
+};
+
+// include/LineOptimizer.h:11-33.  The reference class adds VertexSBALine / EdgeSE3ProjectLine objects to a g2o optimizer;
+// here it appends the same edges, in the same order, to the flattened problem.  DisableOutliers runs on the device between
+// the two rounds of lld_ba_local (k_flag_lines), GetLineData reads the result arrays.
+class LineOptimizer {
+ public:
+  LineOptimizer(FlatBA& flat, int maxPtId, double thHuberLinesStereo, double thHuberLinesMono, double gamma)
+      : flat_(flat), maxPtId_(maxPtId), thStereo_(thHuberLinesStereo * gamma), thMono_(thHuberLinesMono * gamma), infoLines_(gamma * gamma) {}
+  double thHuberLinesStereo() const { return thStereo_; }
+  double thHuberLinesMono() const { return thMono_; }
+  // src/LineOptimizer.cc:39-127.  proj_map: keyframe id -> (left KeyLine, right KeyLine with startPointX < 0 when absent).
+  // K and stereo_b are per call in the reference but LocalBundleAdjustment passes the current keyframe's for every line
+  // (src/Optimizer.cc:1211-1215); they were given to FlatBA::AddKeyFrame as line_cam.
+  void AddLineMinimal(int line_id, const double X0[3], const double line_dir[3],
+                      const std::map<int, std::pair<KeyLine, KeyLine>>& proj_map) {
+    for (int c = 0; c < 3; c++) flat_.lxd.push_back(X0[c]);
+    for (int c = 0; c < 3; c++) flat_.lxd.push_back(line_dir[c]);
+    line_row_[line_id] = (int)flat_.line_ids.size();
+    flat_.line_ids.push_back(line_id);
+    for (auto& kv : proj_map) {                       // std::map order = ascending keyframe id (:59)
+      const auto it = flat_.kf_index_by_id.find(kv.first);
+      if (it == flat_.kf_index_by_id.end()) continue;  // optimizer.vertex(kf_id) would be null in the reference
+      const KeyLine& kl = kv.second.first;
+      const KeyLine& kr = kv.second.second;
+      const bool stereo = !(kr.startPointX < 0);      // :65-68, 83-88
+      flat_.lkf.push_back(it->second);
+      const float l4[4] = {kl.startPointX, kl.startPointY, kl.endPointX, kl.endPointY};
+      flat_.lleft.insert(flat_.lleft.end(), l4, l4 + 4);
+      const float r4[4] = {stereo ? kr.startPointX : -1.f, stereo ? kr.startPointY : -1.f, stereo ? kr.endPointX : -1.f, stereo ? kr.endPointY : -1.f};
+      flat_.lright.insert(flat_.lright.end(), r4, r4 + 4);
+      const double thrL = GetReprojThrPyramid(1.0, kl.octave), thrR = stereo ? GetReprojThrPyramid(1.0, kr.octave) : thrL;
+      flat_.linfo.push_back(infoLines_ / (thrL * thrL));   // :97-101
+      flat_.linfo.push_back(infoLines_ / (thrR * thrR));
+      flat_.lstereo.push_back(stereo);
+    }
+    flat_.loff.push_back((int32_t)flat_.lkf.size());
+  }
+  void DisableOutliers() {}   // src/LineOptimizer.cc:129-170: part of lld_ba_local
+  // src/LineOptimizer.cc:172-201; valid after the optimisation ran.  false: the line vertex was removed by DisableOutliers.
+  bool GetLineData(int line_id, double X0[3], double line_dir[3], std::vector<int>* outlier_projs) const {
+    const auto it = line_row_.find(line_id);
+    if (it == line_row_.end()) return false;
+    const int i = it->second;
+    if (flat_.lrem[(size_t)i]) return false;
+    for (int c = 0; c < 3; c++) { X0[c] = flat_.oL[6 * (size_t)i + c]; line_dir[c] = flat_.oL[6 * (size_t)i + 3 + c]; }
+    for (int c = flat_.loff[(size_t)i]; c < flat_.loff[(size_t)i + 1]; c++)
+      for (int s = 0; s < 2; s++)
+        if (flat_.lbad[2 * (size_t)c + s]) outlier_projs->push_back((int)flat_.kfs[(size_t)flat_.lkf[(size_t)c]]->mnId);   // one entry per bad edge
+    return true;
+  }
+ private:
+  FlatBA& flat_;
+  int maxPtId_;
+  double thStereo_, thMono_, infoLines_;
+  std::map<int, int> line_row_;
+};
+
 // The sets LocalBundleAdjustment gathers before building the graph (src/Optimizer.cc:938-1018).
 struct LocalWindow {
   KeyFrame* pKF = nullptr;                    // current keyframe (its K and baseline drive every line edge)
@@ -102,119 +226,206 @@ struct LocalBAResult {
 
 class Optimizer {
  public:
+  // graph construction of LocalBundleAdjustment, src/Optimizer.cc:1037-1218, as flat arrays
+  static void FlattenLocal(const LocalWindow& w, double gamma, FlatBA* F, LineOptimizer** lo_out = nullptr) {
+    const float baseline = w.pKF->mbf / w.pKF->fx;   // pKF->mbf / pKF->mK.at<float>(0,0): float division (:1215)
+    const double lc[4] = {w.pKF->fx, w.pKF->cx, w.pKF->cy, baseline};  // current KF's K for every line edge (:1211-1215)
+    for (KeyFrame* k : w.lLocalKeyFrames) F->AddKeyFrame(k, k->mnId == 0, lc);   // :1043
+    for (KeyFrame* k : w.lFixedCameras) F->AddKeyFrame(k, true, lc);             // :1057
+    unsigned long maxPtId = 0;
+    for (MapPoint* mp : w.lLocalMapPoints) {
+      for (int c = 0; c < 3; c++) F->pxyz.push_back((double)mp->pos[c]);
+      F->points.push_back(mp);
+      if (mp->mnId > maxPtId) maxPtId = mp->mnId;
+      for (auto& ob : mp->observations) {          // std::map<KeyFrame*, size_t>: pointer order, as the reference iterates (:1107-1110)
+        KeyFrame* k = ob.first;
+        if (k->isBad() || !F->kf_index.count(k)) continue;
+        const KeyPoint& kp = k->mvKeysUn[ob.second];
+        F->pkf.push_back(F->kf_index[k]);
+        F->puvr.push_back(kp.x); F->puvr.push_back(kp.y); F->puvr.push_back(k->mvuRight[ob.second]);
+        F->pinfo.push_back(k->mvInvLevelSigma2[kp.octave]);
+        F->edge_owner.push_back({k, mp});
+      }
+      F->poff.push_back((int32_t)F->pkf.size());
+    }
+    const float thHuberMono = (float)std::sqrt(5.991), thHuberStereo = (float)std::sqrt(7.815);   // const float = sqrt(double) (:1088-1089)
+    LineOptimizer* lo = new LineOptimizer(*F, (int)maxPtId, thHuberStereo, thHuberMono, gamma);    // :1180-1182
+    for (MapLine* ml : w.lLocalMapLines) {
+      std::map<int, std::pair<KeyLine, KeyLine>> proj_map;      // keyed by keyframe id (:1189-1209)
+      for (auto& ob : ml->observations) {
+        KeyFrame* k = ob.first;
+        if (k->isBad() || !F->kf_index.count(k)) continue;
+        const size_t li = ob.second;
+        KeyLine right;
+        right.startPointX = -1;                                   // "no right line" marker (:1200-1206)
+        right.startPointY = right.endPointX = right.endPointY = -1; right.octave = 0;
+        if (k->line_matches[li] >= 0) right = k->mvLinesRight[k->line_matches[li]];
+        proj_map[(int)k->mnId] = {k->mvLinesLeft[li], right};
+      }
+      lo->AddLineMinimal((int)ml->mnId, ml->X0, ml->line_dir, proj_map);
+    }
+    F->Finish();
+    lld_ba_problem& p = F->p;
+    p.robust_points = 1;
+    p.delta_pt_mono = thHuberMono; p.delta_pt_stereo = thHuberStereo;
+    p.delta_ln_mono = lo->thHuberLinesMono(); p.delta_ln_stereo = lo->thHuberLinesStereo();
+    p.chi2_pt_mono = 5.991; p.chi2_pt_stereo = 7.815; p.ln_endpoints_normalized = 0; p.ln_filter = 4;
+    if (lo_out) *lo_out = lo;
+    else delete lo;
+  }
+
   // void static LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, double gamma = 1.0)  include/Optimizer.h:49
   static int LocalBundleAdjustment(void* ctx, const LocalWindow& w, bool* pbStopFlag, double gamma, LocalBAResult* res) {
-    std::vector<KeyFrame*> kfs(w.lLocalKeyFrames);
-    kfs.insert(kfs.end(), w.lFixedCameras.begin(), w.lFixedCameras.end());
-    std::map<KeyFrame*, int> kfi;
-    std::vector<double> T, intr, lcam, pxyz, lxd, linfo;
-    std::vector<uint8_t> fixed, lstereo;
-    std::vector<int32_t> poff{0}, pkf, loff{0}, lkf;
-    std::vector<float> puvr, pinfo, lleft, lright;
-    const float baseline = w.pKF->mbf / w.pKF->fx;   // pKF->mbf / pKF->mK.at<float>(0,0): float division (:1215)
-    for (size_t i = 0; i < kfs.size(); i++) {
-      KeyFrame* k = kfs[i];
-      kfi[k] = (int)i;
-      detail::widen12(k->Tcw, T);
-      fixed.push_back(i >= w.lLocalKeyFrames.size() || k->mnId == 0);   // :1043,1057
-      const double in[5] = {k->fx, k->fy, k->cx, k->cy, k->mbf};
-      intr.insert(intr.end(), in, in + 5);
-      const double lc[4] = {w.pKF->fx, w.pKF->cx, w.pKF->cy, baseline};  // current KF's K for every line edge (:1211-1215)
-      lcam.insert(lcam.end(), lc, lc + 4);
-    }
-    std::vector<std::pair<KeyFrame*, MapPoint*>> edge_owner;
-    for (MapPoint* mp : w.lLocalMapPoints) {
-      for (int c = 0; c < 3; c++) pxyz.push_back((double)mp->pos[c]);
-      for (auto& ob : mp->observations) {
-        KeyFrame* k = ob.first;
-        if (k->isBad() || !kfi.count(k)) continue;
-        const KeyPoint& kp = k->mvKeysUn[ob.second];
-        pkf.push_back(kfi[k]);
-        puvr.push_back(kp.x); puvr.push_back(kp.y); puvr.push_back(k->mvuRight[ob.second]);
-        pinfo.push_back(k->mvInvLevelSigma2[kp.octave]);
-        edge_owner.push_back({k, mp});
-      }
-      poff.push_back((int32_t)pkf.size());
-    }
-    std::vector<std::pair<KeyFrame*, MapLine*>> cell_owner;
-    for (MapLine* ml : w.lLocalMapLines) {
-      for (int c = 0; c < 3; c++) lxd.push_back(ml->X0[c]);
-      for (int c = 0; c < 3; c++) lxd.push_back(ml->line_dir[c]);
-      std::map<int, std::pair<KeyFrame*, size_t>> by_id;     // proj_map is keyed by mnId (:1189-1209)
-      for (auto& ob : ml->observations)
-        if (!ob.first->isBad() && kfi.count(ob.first)) by_id[(int)ob.first->mnId] = {ob.first, ob.second};
-      for (auto& kv : by_id) {
-        KeyFrame* k = kv.second.first;
-        const size_t li = kv.second.second;
-        const KeyLine& kl = k->mvLinesLeft[li];
-        lkf.push_back(kfi[k]);
-        const float l4[4] = {kl.startPointX, kl.startPointY, kl.endPointX, kl.endPointY};
-        lleft.insert(lleft.end(), l4, l4 + 4);
-        double thrL = GetReprojThrPyramid(1.0, kl.octave), thrR = thrL;
-        if (k->line_matches[li] >= 0) {
-          const KeyLine& kr = k->mvLinesRight[k->line_matches[li]];
-          const float r4[4] = {kr.startPointX, kr.startPointY, kr.endPointX, kr.endPointY};
-          lright.insert(lright.end(), r4, r4 + 4);
-          thrR = GetReprojThrPyramid(1.0, kr.octave);
-          lstereo.push_back(1);
-        } else {
-          const float r4[4] = {-1, -1, -1, -1};
-          lright.insert(lright.end(), r4, r4 + 4);
-          lstereo.push_back(0);
-        }
-        linfo.push_back(gamma * gamma / (thrL * thrL));   // src/LineOptimizer.cc:33-36,97-101
-        linfo.push_back(gamma * gamma / (thrR * thrR));
-        cell_owner.push_back({k, ml});
-      }
-      loff.push_back((int32_t)lkf.size());
-    }
-    const int32_t one_kf[2] = {0, (int32_t)kfs.size()}, one_pt[2] = {0, (int32_t)w.lLocalMapPoints.size()},
-                  one_ln[2] = {0, (int32_t)w.lLocalMapLines.size()};
-    lld_ba_problem p;
-    std::memset(&p, 0, sizeof(p));
-    p.n_win = 1; p.kf_off = one_kf; p.pt_off = one_pt; p.ln_off = one_ln;
-    p.kf_Tcw = T.data(); p.kf_fixed = fixed.data(); p.kf_intr = intr.data(); p.kf_line_cam = lcam.data();
-    p.pt_xyz = pxyz.data(); p.pt_obs_off = poff.data(); p.pt_obs_kf = pkf.data(); p.pt_obs_uvr = puvr.data(); p.pt_obs_info = pinfo.data();
-    p.ln_x0_dir = lxd.data(); p.ln_obs_off = loff.data(); p.ln_obs_kf = lkf.data(); p.ln_obs_left = lleft.data();
-    p.ln_obs_right = lright.data(); p.ln_obs_info = linfo.data(); p.ln_obs_stereo = lstereo.data();
-    const float thHuberMono = std::sqrt(5.991f), thHuberStereo = std::sqrt(7.815f);   // const float = sqrt(double) (:1088-1089)
-    p.robust_points = 1;
-    p.delta_pt_mono = (float)std::sqrt(5.991); p.delta_pt_stereo = (float)std::sqrt(7.815);
-    (void)thHuberMono; (void)thHuberStereo;
-    p.delta_ln_mono = p.delta_pt_mono * gamma; p.delta_ln_stereo = p.delta_pt_stereo * gamma;
-    p.chi2_pt_mono = 5.991; p.chi2_pt_stereo = 7.815; p.ln_endpoints_normalized = 0; p.ln_filter = 4;
-    std::vector<double> oT(T.size()), oP(pxyz.size()), oL(lxd.size());
-    std::vector<uint8_t> pbad(pkf.size()), lbad(2 * lkf.size()), lrem(w.lLocalMapLines.size());
-    lld_ba_result r;
-    std::memset(&r, 0, sizeof(r));
-    r.kf_Tcw = oT.data(); r.pt_xyz = oP.data(); r.ln_x0_dir = oL.data();
-    r.pt_obs_bad = pbad.data(); r.ln_obs_bad = lbad.data(); r.ln_removed = lrem.data();
-    volatile uint8_t stop = (pbStopFlag && *pbStopFlag) ? 1 : 0;
-    // pbStopFlag is a bool written by another thread; bool and uint8_t share their object representation here
-    const volatile uint8_t* sp = pbStopFlag ? reinterpret_cast<const volatile uint8_t*>(pbStopFlag) : &stop;
+    FlatBA F;
+    LineOptimizer* lo = nullptr;
+    FlattenLocal(w, gamma, &F, &lo);
+    struct Guard { LineOptimizer* p; ~Guard() { delete p; } } guard{lo};
     if (pbStopFlag && *pbStopFlag) return 0;   // :1220-1222 nothing is written back
-    const int rc = lld_ba_local(ctx, &p, 5, 15, sp, &r);
+    // pbStopFlag is a bool written by another thread; bool and uint8_t share their object representation here
+    const volatile uint8_t* sp = pbStopFlag ? reinterpret_cast<const volatile uint8_t*>(pbStopFlag) : nullptr;
+    const int rc = lld_ba_local(ctx, &F.p, 5, 15, sp, &F.r);
     if (rc) return rc;
-    // write-back under the map mutex in the reference (:1334-1386); float narrowing as Converter::toCvMat
+    // write-back (under the map mutex in the reference, :1334-1386); float narrowing as Converter::toCvMat
     if (res) {
-      for (size_t e = 0; e < pbad.size(); e++)
-        if (pbad[e]) res->vToErase.push_back(edge_owner[e]);
-      for (size_t c = 0; c < lkf.size(); c++) {
-        const size_t line = std::upper_bound(loff.begin(), loff.end(), (int32_t)c) - loff.begin() - 1;
-        if (lrem[line]) continue;
-        for (int s = 0; s < 2; s++)
-          if (lbad[2 * c + s]) res->vToEraseLines.push_back(cell_owner[c]);   // one entry per bad edge, as GetLineData
+      for (size_t e = 0; e < F.pkf.size(); e++)
+        if (F.pbad[e] && !F.edge_owner[e].second->isBad()) res->vToErase.push_back(F.edge_owner[e]);   // pMP->isBad() is skipped (:1284,1299)
+      for (size_t i = 0; i < w.lLocalMapLines.size(); i++) {                                             // :1313-1329
+        double X0[3], dir[3];
+        std::vector<int> bad_obs;
+        if (!lo->GetLineData((int)w.lLocalMapLines[i]->mnId, X0, dir, &bad_obs)) continue;
+        for (int id : bad_obs) res->vToEraseLines.push_back({F.kfs[(size_t)F.kf_index_by_id[id]], w.lLocalMapLines[i]});
       }
     }
     for (size_t i = 0; i < w.lLocalKeyFrames.size(); i++)
-      for (int c = 0; c < 12; c++) kfs[i]->Tcw[c] = (float)oT[12 * i + c];
+      for (int c = 0; c < 12; c++) F.kfs[i]->Tcw[c] = (float)F.oT[12 * i + c];
     for (size_t i = 0; i < w.lLocalMapPoints.size(); i++)
-      for (int c = 0; c < 3; c++) w.lLocalMapPoints[i]->pos[c] = (float)oP[3 * i + c];
+      for (int c = 0; c < 3; c++) w.lLocalMapPoints[i]->pos[c] = (float)F.oP[3 * i + c];
     for (size_t i = 0; i < w.lLocalMapLines.size(); i++) {
-      if (lrem[i]) continue;   // GetLineData returned false: SetMinimalPos is not called
-      for (int c = 0; c < 3; c++) { w.lLocalMapLines[i]->X0[c] = oL[6 * i + c]; w.lLocalMapLines[i]->line_dir[c] = oL[6 * i + 3 + c]; }
+      double X0[3], dir[3];
+      std::vector<int> unused;
+      if (!lo->GetLineData((int)w.lLocalMapLines[i]->mnId, X0, dir, &unused)) continue;   // removed: SetMinimalPos is not called
+      for (int c = 0; c < 3; c++) { w.lLocalMapLines[i]->X0[c] = X0[c]; w.lLocalMapLines[i]->line_dir[c] = dir[c]; }
     }
     return 0;
+  }
+
+  // graph construction of BundleAdjustment, src/Optimizer.cc:341-488 (+ AddLineMinimalGlobal :149-247).
+  // included_pt / included_ln: !vbNotIncludedMP / !vbNotIncludedML.
+  // Carve-outs of undefined behaviour in the reference, resolved as documented in DESIGN.md: mvInvLevelSigma2[octave*2]
+  // (:405,428) reads past the 8-level table for octave >= 4 — the index is clamped to the last level; a line observation
+  // without a right match makes AddLineMinimalGlobal read mvLinesRight[-1] (:226-230) — no right edge is created.
+  static void FlattenGlobal(const std::vector<KeyFrame*>& vpKFs, const std::vector<MapPoint*>& vpMP, const std::vector<MapLine*>& vpML,
+                            bool bRobust, FlatBA* F, std::vector<bool>* included_pt, std::vector<bool>* included_ln) {
+    unsigned long maxKFid = 0;
+    for (KeyFrame* k : vpKFs) {
+      if (k->isBad()) continue;
+      const float bl = k->mbf / k->fx;                       // pKFi->mbf / pKFi->mK.at<float>(0,0)  (:207)
+      const double lc[4] = {k->fx, k->cx, k->cy, bl};        // each keyframe's own K (:200-202)
+      F->AddKeyFrame(k, k->mnId == 0, lc);                   // :348-352
+      if (k->mnId > maxKFid) maxKFid = k->mnId;
+    }
+    included_pt->assign(vpMP.size(), false);
+    included_ln->assign(vpML.size(), false);
+    for (size_t i = 0; i < vpMP.size(); i++) {
+      MapPoint* mp = vpMP[i];
+      if (mp->isBad()) continue;
+      const size_t e0 = F->pkf.size();
+      for (auto& ob : mp->observations) {
+        KeyFrame* k = ob.first;
+        if (k->isBad() || k->mnId > maxKFid || !F->kf_index.count(k)) continue;   // :393-394
+        const KeyPoint& kp = k->mvKeysUn[ob.second];
+        F->pkf.push_back(F->kf_index[k]);
+        F->puvr.push_back(kp.x); F->puvr.push_back(kp.y); F->puvr.push_back(k->mvuRight[ob.second]);
+        const size_t lvl = std::min<size_t>((size_t)kp.octave * 2, k->mvInvLevelSigma2.size() - 1);
+        F->pinfo.push_back(k->mvInvLevelSigma2[lvl]);
+        F->edge_owner.push_back({k, mp});
+      }
+      if (F->pkf.size() == e0) continue;                     // nEdges == 0: vertex removed (:456-460)
+      (*included_pt)[i] = true;
+      for (int c = 0; c < 3; c++) F->pxyz.push_back((double)mp->pos[c]);
+      F->points.push_back(mp);
+      F->poff.push_back((int32_t)F->pkf.size());
+    }
+    for (size_t i = 0; i < vpML.size(); i++) {
+      MapLine* ml = vpML[i];
+      if (!ml || ml->isBad() || ml->Observations() < 4) continue;   // :473
+      const size_t c0 = F->lkf.size();
+      for (auto& ob : ml->observations) {                    // std::map<KeyFrame*, size_t>: pointer order (:176)
+        KeyFrame* k = ob.first;
+        if (k->isBad() || !F->kf_index.count(k)) continue;
+        const size_t li = ob.second;
+        const KeyLine& kl = k->mvLinesLeft[li];
+        F->lkf.push_back(F->kf_index[k]);
+        const float l4[4] = {kl.startPointX, kl.startPointY, kl.endPointX, kl.endPointY};
+        F->lleft.insert(F->lleft.end(), l4, l4 + 4);
+        if (k->line_matches[li] >= 0) {
+          const KeyLine& kr = k->mvLinesRight[k->line_matches[li]];
+          const float r4[4] = {kr.startPointX, kr.startPointY, kr.endPointX, kr.endPointY};
+          F->lright.insert(F->lright.end(), r4, r4 + 4);
+        } else {
+          const float r4[4] = {-1, -1, -1, -1};
+          F->lright.insert(F->lright.end(), r4, r4 + 4);
+        }
+        F->linfo.push_back(1.0); F->linfo.push_back(1.0);    // setInformation(Identity) (:216)
+        F->lstereo.push_back(1);                             // one Huber delta for every line edge (:218-220)
+      }
+      if (F->lkf.size() == c0) continue;                     // edge_cnt == 0 (:242-245)
+      (*included_ln)[i] = true;
+      for (int c = 0; c < 3; c++) F->lxd.push_back(ml->X0[c]);
+      for (int c = 0; c < 3; c++) F->lxd.push_back(ml->line_dir[c]);
+      F->line_ids.push_back((int)ml->mnId);
+      F->loff.push_back((int32_t)F->lkf.size());
+    }
+    F->Finish();
+    lld_ba_problem& p = F->p;
+    const float thHuber2D = (float)std::sqrt(5.99), thHuber3D = (float)std::sqrt(7.815);   // :359-360
+    p.robust_points = bRobust ? 1 : 0;
+    p.delta_pt_mono = thHuber2D; p.delta_pt_stereo = thHuber3D;
+    p.delta_ln_mono = p.delta_ln_stereo = thHuber3D / 2.0;                                  // :361
+    p.chi2_pt_mono = 5.991; p.chi2_pt_stereo = 7.815; p.ln_endpoints_normalized = 1; p.ln_filter = 4;
+  }
+
+  // void static BundleAdjustment(const vector<KeyFrame*>&, const vector<MapPoint*>&, const vector<MapLine*>&, int nIterations = 5,
+  //                              bool* pbStopFlag = NULL, const unsigned long nLoopKF = 0, const bool bRobust = true)   include/Optimizer.h:43-45
+  static int BundleAdjustment(void* ctx, const std::vector<KeyFrame*>& vpKFs, const std::vector<MapPoint*>& vpMP,
+                              const std::vector<MapLine*>& vpML, int nIterations = 5, bool* pbStopFlag = nullptr,
+                              const unsigned long nLoopKF = 0, const bool bRobust = true) {
+    FlatBA F;
+    std::vector<bool> inc_pt, inc_ln;
+    FlattenGlobal(vpKFs, vpMP, vpML, bRobust, &F, &inc_pt, &inc_ln);
+    const volatile uint8_t* sp = pbStopFlag ? reinterpret_cast<const volatile uint8_t*>(pbStopFlag) : nullptr;
+    const int rc = lld_ba_global(ctx, &F.p, nIterations, sp, &F.r);
+    if (rc) return rc;
+    // :494-557: live state when nLoopKF == 0, the *GBA shadow fields otherwise
+    for (size_t i = 0; i < F.kfs.size(); i++) {
+      KeyFrame* k = F.kfs[i];
+      float* dst = nLoopKF == 0 ? k->Tcw : k->mTcwGBA;
+      for (int c = 0; c < 12; c++) dst[c] = (float)F.oT[12 * i + c];
+      if (nLoopKF != 0) k->mnBAGlobalForKF = nLoopKF;
+    }
+    for (size_t i = 0; i < F.points.size(); i++) {
+      MapPoint* mp = F.points[i];
+      float* dst = nLoopKF == 0 ? mp->pos : mp->mPosGBA;
+      for (int c = 0; c < 3; c++) dst[c] = (float)F.oP[3 * i + c];
+      if (nLoopKF != 0) mp->mnBAGlobalForKF = nLoopKF;
+    }
+    // lines: SetMinimalPos for every included line (the reference tests vbNotIncludedMP[i] here, :542 — a typo that indexes
+    // the point flags with a line index; the shim uses the line flags)
+    size_t row = 0;
+    for (size_t i = 0; i < vpML.size(); i++) {
+      if (!inc_ln[i]) continue;
+      for (int c = 0; c < 3; c++) { vpML[i]->X0[c] = F.oL[6 * row + c]; vpML[i]->line_dir[c] = F.oL[6 * row + 3 + c]; }
+      row++;
+    }
+    return 0;
+  }
+
+  // void static GlobalBundleAdjustemnt(Map* pMap, int nIterations = 5, bool* pbStopFlag = NULL, const unsigned long nLoopKF = 0,
+  //                                    const bool bRobust = true)    include/Optimizer.h:46-47, src/Optimizer.cc:312-319
+  static int GlobalBundleAdjustemnt(void* ctx, Map* pMap, int nIterations = 5, bool* pbStopFlag = nullptr, const unsigned long nLoopKF = 0,
+                                    const bool bRobust = true) {
+    return BundleAdjustment(ctx, pMap->GetAllKeyFrames(), pMap->GetAllMapPoints(), pMap->GetAllMapLines(), nIterations, pbStopFlag,
+                            nLoopKF, bRobust);
   }
 
   // int static PoseOptimization(Frame* pFrame, double gamma = 1.0)   include/Optimizer.h:50
@@ -342,6 +553,48 @@ class ORBmatcher {
     for (int i = 0; i < Cur.N; i++)
       if (match[i] >= 0) Cur.mvpMapPoints[i] = Last.mvpMapPoints[match[i]];
     if (match_out) match_out->assign(match.begin(), match.end());
+    return nm;
+  }
+  // int SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, const float th = 3)   include/ORBmatcher.h:47
+  int SearchByProjection(void* ctx, Frame& F, const std::vector<MapPoint*>& vpMapPoints, float th = 3.f, std::vector<int>* match_out = nullptr) {
+    lld_sbp_mp_problem p;
+    std::memset(&p, 0, sizeof(p));
+    p.n_pairs = 1;
+    p.geom.fx = F.fx; p.geom.fy = F.fy; p.geom.cx = F.cx; p.geom.cy = F.cy; p.geom.bf = F.mbf; p.geom.b = F.mb;
+    p.geom.min_x = F.mnMinX; p.geom.max_x = F.mnMaxX; p.geom.min_y = F.mnMinY; p.geom.max_y = F.mnMaxY;
+    p.geom.n_levels = (int)F.mvScaleFactors.size(); p.geom.scale_factors = F.mvScaleFactors.data();
+    p.th = th; p.nn_ratio = mfNNratio;
+    std::vector<float> cxy, proj, vcos;
+    std::vector<uint8_t> coct, cclaimed, valid, has, desc(32 * vpMapPoints.size(), 0);
+    std::vector<int32_t> lvl;
+    for (int i = 0; i < F.N; i++) {
+      cxy.push_back(F.mvKeysUn[i].x); cxy.push_back(F.mvKeysUn[i].y);
+      coct.push_back((uint8_t)F.mvKeysUn[i].octave);
+      cclaimed.push_back(F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0);   // :87-89
+    }
+    for (size_t i = 0; i < vpMapPoints.size(); i++) {
+      MapPoint* mp = vpMapPoints[i];
+      valid.push_back(mp->mbTrackInView && !mp->isBad());                               // :54-58
+      proj.push_back(mp->mTrackProjX); proj.push_back(mp->mTrackProjY); proj.push_back(mp->mTrackProjXR);
+      lvl.push_back(mp->mnTrackScaleLevel); vcos.push_back(mp->mTrackViewCos);
+      has.push_back(mp->Observations() > 0);
+      std::memcpy(&desc[32 * i], mp->mDescriptor, 32);
+    }
+    const int32_t co[2] = {0, F.N}, mo[2] = {0, (int32_t)vpMapPoints.size()};
+    p.cur_off = co; p.cur_xy = cxy.data(); p.cur_octave = coct.data(); p.cur_uright = F.mvuRight.data();
+    p.cur_desc = F.mDescriptors.data(); p.cur_claimed = cclaimed.data();
+    p.mp_off = mo; p.mp_valid = valid.data(); p.mp_proj = proj.data(); p.mp_level = lvl.data(); p.mp_viewcos = vcos.data();
+    p.mp_desc = desc.data(); p.mp_has_obs = has.data();
+    std::vector<int32_t> match((size_t)F.N + 1, -1);
+    int32_t nm = 0;
+    lld_sbp_result r;
+    std::memset(&r, 0, sizeof(r));
+    r.match = match.data(); r.n_matches = &nm;
+    const int rc = lld_sbp_mappoints(ctx, &p, &r);
+    if (rc) return rc;
+    for (int i = 0; i < F.N; i++)
+      if (match[(size_t)i] >= 0) F.mvpMapPoints[i] = vpMapPoints[(size_t)match[(size_t)i]];   // F.mvpMapPoints[bestIdx] = pMP (:123)
+    if (match_out) match_out->assign(match.begin(), match.begin() + F.N);
     return nm;
   }
  private:

@@ -26,6 +26,11 @@ def f32(x):
     return np.asarray(x, dtype=np.float32)
 
 
+def inv_level_sigma2():
+    """mvInvLevelSigma2 of the ORB pyramid (src/ORBextractor.cc:415-430): float 1 / 1.2^(2 level)"""
+    return f32(1.0 / (f32(SCALE) ** (2 * np.arange(N_LEVELS))).astype(np.float32))
+
+
 def seed_for(config_index: int) -> int:
     return 0x11D51A00 + config_index
 
@@ -129,7 +134,7 @@ def make_ba_window(n_kf, n_pt, n_ln, rng, *, mean_track=5.0, track_mode="normal"
     # keep uR>=0 semantics: stereo obs must not go negative
     our = np.where((our >= 0) | (our == -1.0), our, 0.0)
     pt_obs_uvr = f32(np.stack([ou, ov, our], axis=1))
-    inv_sigma2 = f32(1.0 / (f32(SCALE) ** (2 * np.arange(N_LEVELS))).astype(np.float32))
+    inv_sigma2 = inv_level_sigma2()
     if global_mode:
         # reference quirk (src/Optimizer.cc:407,435): mvInvLevelSigma2[octave*2]; the shim resolves the index,
         # octaves >= 4 would read out of range, so the synthetic GBA keeps octaves in {0..3}
@@ -350,7 +355,7 @@ def make_pose_batch(n_frames, n_pt, n_ln, seed, gamma=0.5, outlier_frac=0.08, st
     ur = np.where(stereo, np.maximum(ur, 0.0), -1.0)
     outl = rng.random((F, n_pt)) < outlier_frac
     un = un + outl * rng.uniform(10, 50, u.shape) * rng.choice([-1.0, 1.0], u.shape)
-    inv_sigma2 = f32(1.0 / (f32(SCALE) ** (2 * np.arange(N_LEVELS))).astype(np.float32))
+    inv_sigma2 = inv_level_sigma2()
     # lines
     P = np.stack([rng.uniform(-12, 12, (F, n_ln)), rng.uniform(-2, 3, (F, n_ln)), rng.uniform(5, 40, (F, n_ln))], axis=-1)
     dc = rng.normal(0, 1, (F, n_ln, 3))
