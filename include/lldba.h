@@ -293,11 +293,61 @@ typedef struct lld_line_match_result {
 
 int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_line_match_result* out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Stereo keypoint matching of a frame: Frame::ComputeStereoMatches  include/Frame.h:86, src/Frame.cc:530-704
+ * (row-banded Hamming candidates, 11x11 SAD slide at the keypoint's pyramid level, parabola fit, median gate).
+ * Batched over frames; every frame brings its own left / right image pyramids (ORBextractor::mvImagePyramid).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct lld_stereo_problem {
+  int32_t n_frames;
+  const int32_t* left_off;     /* [n_frames+1] */
+  const int32_t* right_off;    /* [n_frames+1]; at most 65535 right keypoints per frame */
+  const float* left_xy;        /* [n_left][2]  mvKeys[i].pt (level-0 pixel coordinates) */
+  const uint8_t* left_octave;  /* [n_left]     mvKeys[i].octave */
+  const uint8_t* left_desc;    /* [n_left][32] mDescriptors */
+  const float* right_xy;       /* mvKeysRight, mDescriptorsRight */
+  const uint8_t* right_octave;
+  const uint8_t* right_desc;
+  int32_t n_levels;            /* <= 8 */
+  const float* scale_factors;      /* [n_levels] mvScaleFactors */
+  const float* inv_scale_factors;  /* [n_levels] mvInvScaleFactors */
+  const uint8_t* pyr;          /* all pyramid images of the batch, 8-bit, concatenated */
+  int64_t pyr_bytes;
+  const int64_t* pyr_off;      /* [n_frames][2][n_levels] byte offset of image (frame, 0 = left / 1 = right, level) in pyr */
+  const int32_t* pyr_rows;     /* [n_levels] the same geometry for every frame */
+  const int32_t* pyr_cols;
+  const int32_t* pyr_stride;   /* row stride in bytes */
+  float mb, mbf;               /* baseline in metres, baseline * fx */
+} lld_stereo_problem;
+
+typedef struct lld_stereo_result {
+  float* uright;       /* [n_left] mvuRight, -1 = no stereo match */
+  float* depth;        /* [n_left] mvDepth,  -1 = no stereo match */
+  int32_t* n_matched;  /* [n_frames] may be NULL */
+} lld_stereo_result;
+
+int lld_stereo_matches(void* ctx, const lld_stereo_problem* p, lld_stereo_result* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Distinctive (medoid) descriptors: MapPoint::ComputeDistinctiveDescriptors  include/MapPoint.h:62, src/MapPoint.cc:242-307
+ *                                   MapLine::ComputeDistinctiveDescriptors   include/MapLine.h:66,  src/MapLine.cc:133-201
+ * Batched over landmarks: landmark l owns descriptors [off[l], off[l+1]) — the rows of its observations in non-bad
+ * keyframes, in std::map<KeyFrame*, size_t> order.  best[l] = landmark-local index of the descriptor with the least median
+ * distance to the others (the first one on ties), -1 for a landmark without descriptors.  At most 256 per landmark.
+ * ---------------------------------------------------------------------------------------------- */
+int lld_medoid_orb(void* ctx, int32_t n_lm, const int32_t* off, const uint8_t* desc /*[n][32]*/, int32_t* best);
+int lld_medoid_float(void* ctx, int32_t n_lm, const int32_t* off, int32_t desc_dim, const float* desc /*[n][desc_dim]*/, int32_t* best);
+
 /* Library self-description (for tests and the bench): version string, number of kernels launched by the
  * last call on this context, device-side duration of the last call measured with CUDA events on the
  * context's stream (milliseconds; h2d/compute/d2h). */
 const char* lld_version(void);
 int64_t lld_ctx_launch_count(void* ctx);
+/* lld_ba_local / lld_ba_global keep the index tables of the last problem on the device; a call whose STRUCTURE (windows,
+ * observation lists, fixed flags: a 64-bit hash of those arrays) equals the previous one's skips the host indexing stage
+ * and only uploads the value arrays.  on = 1 / 0 switches this per context, -1 restores the default (on; the environment
+ * variable LLD_BA_TOPO_CACHE=0 turns the default off). */
+void lld_ctx_set_topo_cache(void* ctx, int on);
 /* NCCL collectives issued / bytes all-reduced per rank by the last lld_ba_global call on this context */
 void lld_ctx_nccl_stats(void* ctx, int64_t* calls, int64_t* bytes);
 void lld_ctx_last_timing(void* ctx, float* ms_h2d, float* ms_compute, float* ms_d2h);

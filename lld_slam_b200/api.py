@@ -135,3 +135,64 @@ def descriptor_distance(a: np.ndarray, b: np.ndarray, *, impl: str = "gpu") -> i
     a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
     assert a.size == 32 and b.size == 32
     return int(lib.descriptor_distance(a.ctypes.data_as(capi.c_u8p), b.ctypes.data_as(capi.c_u8p)))
+
+
+def stereo_matches(p: Dict[str, Any], *, impl: str = "gpu", ctx=None):
+    """Frame::ComputeStereoMatches on a batch (synth.batch_stereo).  The oracle has a per-frame entry point."""
+    n_left = int(p["left_off"][-1]); F = int(p["n_frames"])
+    out = dict(uright=np.full(n_left, -1, np.float32), depth=np.full(n_left, -1, np.float32), n_matched=np.zeros(F, np.int32))
+    if impl == "gpu":
+        lib = _lib(impl)
+        prob, keep = capi.fill_struct(capi.StereoProblem, {k: v for k, v in p.items() if k != "frames"})
+        res, keep2 = capi.fill_struct(capi.StereoResult, out)
+        rc = lib.dll.lld_stereo_matches(_handle(impl, ctx), C.byref(prob), C.byref(res))
+        _check(impl, ctx, rc, "lld_stereo_matches")
+        return out
+    dll = capi.load_oracle().dll
+    fn = dll.lldo_stereo_matches
+    fn.restype = C.c_int
+    P = C.c_void_p
+    fn.argtypes = [C.c_int, P, P, P, C.c_int, P, P, P, C.c_int, P, P, P, P, P, P, P, C.c_float, C.c_float, P, P]
+    L = int(p["n_levels"])
+    ptr = lambda a: a.ctypes.data_as(P)   # noqa: E731
+    for f in range(F):
+        a, b = int(p["left_off"][f]), int(p["left_off"][f + 1])
+        ra, rb = int(p["right_off"][f]), int(p["right_off"][f + 1])
+        base = p["pyr"].ctypes.data
+        arrL = (P * L)(*[base + int(p["pyr_off"][(f * 2 + 0) * L + l]) for l in range(L)])
+        arrR = (P * L)(*[base + int(p["pyr_off"][(f * 2 + 1) * L + l]) for l in range(L)])
+        kl = np.ascontiguousarray(p["left_xy"][a:b]); ol = np.ascontiguousarray(p["left_octave"][a:b].astype(np.int32)); dl = np.ascontiguousarray(p["left_desc"][a:b])
+        kr = np.ascontiguousarray(p["right_xy"][ra:rb]); orr = np.ascontiguousarray(p["right_octave"][ra:rb].astype(np.int32)); dr = np.ascontiguousarray(p["right_desc"][ra:rb])
+        uR, dep = np.empty(b - a, np.float32), np.empty(b - a, np.float32)
+        n = fn(b - a, ptr(kl), ptr(ol), ptr(dl), rb - ra, ptr(kr), ptr(orr), ptr(dr), L, ptr(p["scale_factors"]), ptr(p["inv_scale_factors"]),
+               C.cast(arrL, P), C.cast(arrR, P), ptr(p["pyr_rows"]), ptr(p["pyr_cols"]), ptr(p["pyr_stride"]),
+               C.c_float(float(p["mb"])), C.c_float(float(p["mbf"])), ptr(uR), ptr(dep))
+        out["uright"][a:b] = uR; out["depth"][a:b] = dep; out["n_matched"][f] = n
+    return out
+
+
+def medoid_orb(off, desc, *, impl: str = "gpu", ctx=None):
+    """MapPoint::ComputeDistinctiveDescriptors, batched: best descriptor index per landmark"""
+    off = np.ascontiguousarray(off, np.int32); desc = np.ascontiguousarray(desc, np.uint8)
+    best = np.full(len(off) - 1, -2, np.int32)
+    dll = _lib(impl).dll
+    fn = getattr(dll, ("lld_" if impl == "gpu" else "lldo_") + "medoid_orb")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int32, capi.c_i32p, capi.c_u8p, capi.c_i32p]
+    rc = fn(_handle(impl, ctx), len(off) - 1, off.ctypes.data_as(capi.c_i32p), desc.ctypes.data_as(capi.c_u8p), best.ctypes.data_as(capi.c_i32p))
+    _check(impl, ctx, rc, "lld_medoid_orb")
+    return best
+
+
+def medoid_float(off, desc, *, impl: str = "gpu", ctx=None):
+    """MapLine::ComputeDistinctiveDescriptors, batched"""
+    off = np.ascontiguousarray(off, np.int32); desc = np.ascontiguousarray(desc, np.float32)
+    best = np.full(len(off) - 1, -2, np.int32)
+    dll = _lib(impl).dll
+    fn = getattr(dll, ("lld_" if impl == "gpu" else "lldo_") + "medoid_float")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int32, capi.c_i32p, C.c_int32, capi.c_f32p, capi.c_i32p]
+    rc = fn(_handle(impl, ctx), len(off) - 1, off.ctypes.data_as(capi.c_i32p), int(desc.shape[1]), desc.ctypes.data_as(capi.c_f32p),
+            best.ctypes.data_as(capi.c_i32p))
+    _check(impl, ctx, rc, "lld_medoid_float")
+    return best

@@ -124,6 +124,26 @@ class LineMatchResult(C.Structure):
     _fields_ = [("match", c_i32p), ("dist", c_f32p)]
 
 
+c_i64p = C.POINTER(C.c_int64)
+_NP2C[np.dtype(np.int64)] = c_i64p
+
+
+class StereoProblem(C.Structure):
+    _fields_ = [
+        ("n_frames", C.c_int32), ("left_off", c_i32p), ("right_off", c_i32p),
+        ("left_xy", c_f32p), ("left_octave", c_u8p), ("left_desc", c_u8p),
+        ("right_xy", c_f32p), ("right_octave", c_u8p), ("right_desc", c_u8p),
+        ("n_levels", C.c_int32), ("scale_factors", c_f32p), ("inv_scale_factors", c_f32p),
+        ("pyr", c_u8p), ("pyr_bytes", C.c_int64), ("pyr_off", c_i64p),
+        ("pyr_rows", c_i32p), ("pyr_cols", c_i32p), ("pyr_stride", c_i32p),
+        ("mb", C.c_float), ("mbf", C.c_float),
+    ]
+
+
+class StereoResult(C.Structure):
+    _fields_ = [("uright", c_f32p), ("depth", c_f32p), ("n_matched", c_i32p)]
+
+
 def fill_struct(struct_cls, fields: Dict[str, Any]):
     """Build a ctypes struct from a dict of numpy arrays / scalars.  Returns (struct, keepalive list)."""
     s = struct_cls()
@@ -200,6 +220,12 @@ class _Lib:
             d.lld_comm_init.restype = C.c_int
             d.lld_ba_shard_bounds.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i32p]
             d.lld_ba_shard_bounds.restype = None
+            d.lld_stereo_matches.argtypes = [vp, C.POINTER(StereoProblem), C.POINTER(StereoResult)]
+            d.lld_stereo_matches.restype = C.c_int
+            d.lld_ctx_set_topo_cache.argtypes = [vp, C.c_int]
+            d.lld_ctx_set_topo_cache.restype = None
+            d.lld_ctx_nccl_stats.argtypes = [vp, c_i64p, c_i64p]
+            d.lld_ctx_nccl_stats.restype = None
 
     def _sig(self, name, argtypes):
         f = getattr(self.dll, self.prefix + name)

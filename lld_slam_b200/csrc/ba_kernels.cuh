@@ -172,15 +172,19 @@ __device__ __forceinline__ void make_line_obs(const BaView& v, int kf, const flo
 
 // PT_G lanes per map point (4 for single windows, where one lane per point fills a third of the SMs; 1 for batches):
 // lane g takes edges e0 + g, e0 + g + PT_G, ...; the sums are combined by a fixed xor butterfly inside the lane group.
-template <int PT_G>
+// WITH_D (dense mode, every LM step but the first of a round, where lambda is known when the step starts): the kernel also
+// forms (H_ll + lambda I)^-1 and D^-1 b_l (k_schur_points' work, block_solver.hpp:389) — for windows that retry a rejected
+// step with a new lambda from the stored H_ll, without linearising again.
+template <int PT_G, bool WITH_D = false>
 __global__ void __launch_bounds__(LM_TPB) k_lin_points(BaView v) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int pl = gt / PT_G, gl = gt - pl * PT_G;
   const bool live = pl < v.n_pt;
   const int p = live ? pl : v.n_pt - 1;  // dead lanes shadow the last point (shuffles stay full-warp), no stores
   const int w = v.pt_win[p];
-  const bool run = live && v.w_phase[w] == PH_LIN;
-  if (PT_G == 1 && !run) return;
+  const int phase = v.w_phase[w];
+  const bool run = live && phase == PH_LIN;
+  if (PT_G == 1 && !run && !(WITH_D && live && phase == PH_RETRY)) return;
   const int sel = v.w_sel[w];
   const double* Xp = v.pt_xyz[sel] + 3 * (size_t)p;
   const double X[3] = {Xp[0], Xp[1], Xp[2]};
@@ -279,14 +283,34 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_points(BaView v) {
     chi += __shfl_xor_sync(0xffffffffu, chi, o);
     nact += __shfl_xor_sync(0xffffffffu, nact, o);
   }
-  if (!run || gl != 0) return;
+  if (gl != 0 || !live) return;
   double* Ho = v.pt_H + 9 * (size_t)p;
+  if (run) {
 #pragma unroll
-  for (int k = 0; k < 6; k++) Ho[k] = H[k];
-  Ho[6] = bl[0]; Ho[7] = bl[1]; Ho[8] = bl[2];
-  v.lm_chi2lin[p] = chi;
-  v.lm_maxdiag[p] = nact ? fmax(fabs(H[0]), fmax(fabs(H[3]), fabs(H[5]))) : 0.0;
-  v.lm_active[p] = nact > 0;
+    for (int k = 0; k < 6; k++) Ho[k] = H[k];
+    Ho[6] = bl[0]; Ho[7] = bl[1]; Ho[8] = bl[2];
+    v.lm_chi2lin[p] = chi;
+    v.lm_maxdiag[p] = nact ? fmax(fabs(H[0]), fmax(fabs(H[3]), fabs(H[5]))) : 0.0;
+    v.lm_active[p] = nact > 0;
+  } else if (WITH_D && phase == PH_RETRY) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) H[k] = Ho[k];
+    bl[0] = Ho[6]; bl[1] = Ho[7]; bl[2] = Ho[8];
+  } else {
+    return;
+  }
+  if (WITH_D) {
+    const double lam = v.w_lambda[w];
+    double Di[9];
+    {
+      const double A[9] = {H[0] + lam, H[1], H[2], H[1], H[3] + lam, H[4], H[2], H[4], H[5] + lam};
+      inv3_sym(A, Di);
+    }
+    double* Do = v.pts_D + 10 * (size_t)v.pt_spos[p];
+    Do[0] = Di[0]; Do[1] = Di[1]; Do[2] = Di[2]; Do[3] = Di[4]; Do[4] = Di[5]; Do[5] = Di[8];
+#pragma unroll
+    for (int i = 0; i < 3; i++) Do[6 + i] = Di[3 * i] * bl[0] + Di[3 * i + 1] * bl[1] + Di[3 * i + 2] * bl[2];
+  }
 }
 
 // index of (r,c), r<=c, in the packed upper triangle of a 4x4
@@ -296,14 +320,15 @@ __device__ __forceinline__ constexpr int u4(int r, int c) { return r * 4 - (r * 
 // edge, ~1100 FP64 flops each with divisions and a square root: one thread per line is a 10-evaluation latency chain);
 // H_ll, b_l, chi2 and the active count are then summed over the group by a fixed xor-butterfly (deterministic).
 // (LN_G = 8 below ~8k lines, where one lane per line leaves the SMs idle; 1 for large batches, where the extra lanes only cost)
-template <int LN_G>
+template <int LN_G, bool WITH_D = false>
 __global__ void __launch_bounds__(LM_TPB) k_lin_lines(BaView v) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int l = gt / LN_G, gl = gt - l * LN_G;
   const bool live = l < v.n_ln;
   const int lc = live ? l : v.n_ln - 1;      // dead lanes shadow the last line (no stores) so that shuffles stay full-warp
   const int w = v.ln_win[lc];
-  const bool run = live && v.w_phase[w] == PH_LIN;
+  const int phase = v.w_phase[w];
+  const bool run = live && phase == PH_LIN;
   const int sel = v.w_sel[w];
   const double* stp = v.ln_st[sel] + 5 * (size_t)lc;
   const double st[5] = {stp[0], stp[1], stp[2], stp[3], stp[4]};
@@ -404,16 +429,41 @@ __global__ void __launch_bounds__(LM_TPB) k_lin_lines(BaView v) {
     chi += __shfl_xor_sync(0xffffffffu, chi, o);
     nact += __shfl_xor_sync(0xffffffffu, nact, o);
   }
-  if (!run || gl != 0) return;
+  if (gl != 0 || !live) return;
   double* Ho = v.ln_H + 14 * (size_t)l;
+  if (run) {
 #pragma unroll
-  for (int k = 0; k < 10; k++) Ho[k] = H[k];
+    for (int k = 0; k < 10; k++) Ho[k] = H[k];
 #pragma unroll
-  for (int k = 0; k < 4; k++) Ho[10 + k] = bl[k];
-  const int li = v.n_pt + l;
-  v.lm_chi2lin[li] = chi;
-  v.lm_maxdiag[li] = nact ? fmax(fmax(fabs(H[u4(0, 0)]), fabs(H[u4(1, 1)])), fmax(fabs(H[u4(2, 2)]), fabs(H[u4(3, 3)]))) : 0.0;
-  v.lm_active[li] = nact > 0;
+    for (int k = 0; k < 4; k++) Ho[10 + k] = bl[k];
+    const int li = v.n_pt + l;
+    v.lm_chi2lin[li] = chi;
+    v.lm_maxdiag[li] = nact ? fmax(fmax(fabs(H[u4(0, 0)]), fabs(H[u4(1, 1)])), fmax(fabs(H[u4(2, 2)]), fabs(H[u4(3, 3)]))) : 0.0;
+    v.lm_active[li] = nact > 0;
+  } else if (WITH_D && phase == PH_RETRY) {
+#pragma unroll
+    for (int k = 0; k < 10; k++) H[k] = Ho[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) bl[k] = Ho[10 + k];
+  } else {
+    return;
+  }
+  if (WITH_D) {   // k_schur_lines' work
+    const double lam = v.w_lambda[w];
+    double A[16], Di[16];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int c2 = 0; c2 < 4; c2++) A[4 * r + c2] = H[r <= c2 ? u4(r, c2) : u4(c2, r)] + (r == c2 ? lam : 0.0);
+    inv4(A, Di);
+    double* Do = v.lns_D + 14 * (size_t)v.ln_spos[l];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int c2 = r; c2 < 4; c2++) Do[u4(r, c2)] = Di[4 * r + c2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) Do[10 + i] = Di[4 * i] * bl[0] + Di[4 * i + 1] * bl[1] + Di[4 * i + 2] * bl[2] + Di[4 * i + 3] * bl[3];
+  }
 }
 
 // fixed-order reduction of NV per-thread values over the CTA (LM_TPB threads); result in out[0..NV) for all threads
@@ -741,6 +791,30 @@ __global__ void __launch_bounds__(FUSED_RED_TPB) k_begin_fused(BaView v) {
     v.w_red_max[w] = mx;
   }
   if (tid == 0) begin_window(v, w, true);
+}
+
+// per free keyframe: fixed-order sum of its chunk partials (k_lin_poses) into H_pp, b_p and the active-edge count; the
+// part of k_begin_fused that every LM step needs (the rest of it is the lambda_0 / chi2 bookkeeping of a first step)
+__global__ void __launch_bounds__(128) k_pose_sum(BaView v) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = t / 28, k = t - 28 * g;
+  if (g >= v.n_free_total) return;
+  const int w = v.kf_win[v.g_kf[g]];
+  if (v.w_phase[w] != PH_LIN) return;
+  double s2 = 0;
+  for (int rng = 0; rng < 2; rng++) {
+    const int c0 = rng == 0 ? v.g_chp0[g] : v.g_chl0[g], c1 = rng == 0 ? v.g_chp0[g + 1] : v.g_chl0[g + 1];
+    int ch = c0;
+    for (; ch + 4 <= c1; ch += 4) {
+      const double a0 = v.ch_pose[28 * (size_t)ch + k], a1 = v.ch_pose[28 * (size_t)(ch + 1) + k],
+                   a2 = v.ch_pose[28 * (size_t)(ch + 2) + k], a3 = v.ch_pose[28 * (size_t)(ch + 3) + k];
+      s2 += a0; s2 += a1; s2 += a2; s2 += a3;
+    }
+    for (; ch < c1; ch++) s2 += v.ch_pose[28 * (size_t)ch + k];
+  }
+  if (k < 21) v.g_Hpp[21 * (size_t)g + k] = s2;
+  else if (k < 27) v.g_bp[6 * (size_t)g + (k - 21)] = s2;
+  else v.g_nact[g] = (int)(s2 + 0.5);
 }
 
 // ------------------------------------------------------------------------------------------------

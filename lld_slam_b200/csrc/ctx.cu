@@ -88,6 +88,9 @@ extern "C" void lld_ctx_destroy(void* ctx) {
     if (c->side[i]) cudaStreamDestroy(c->side[i]);
     if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
   }
+  for (int r = 0; r < 2; r++)
+    for (int k = 0; k < 2; k++)
+      if (c->ba_graph[r][k]) cudaGraphExecDestroy(c->ba_graph[r][k]);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (int i = 0; i < 2; i++) if (c->ev_grp[i]) cudaEventDestroy(c->ev_grp[i]);
   for (int i = 0; i < 2; i++)
@@ -103,6 +106,11 @@ extern "C" const char* lld_ctx_last_error(void* ctx) {
 extern "C" int64_t lld_ctx_launch_count(void* ctx) {
   LldCtx* c = lld_ctx_cast(ctx);
   return c ? c->launches : 0;
+}
+// BA topology cache of this context (and of its pipeline workers): 1 = on, 0 = off, -1 = default
+extern "C" void lld_ctx_set_topo_cache(void* ctx, int on) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (c) c->topo_cache = on;
 }
 // collectives issued and bytes all-reduced (per rank) since the last lld_ba_global / lld_ba_upload on this context
 extern "C" void lld_ctx_nccl_stats(void* ctx, int64_t* calls, int64_t* bytes) {

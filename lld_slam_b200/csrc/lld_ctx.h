@@ -88,7 +88,15 @@ struct LldCtx {
     return ev_pool[ev_next++];
   }
 
-  void pool_reset() { pool_next = 0; }
+  // every entry point that (re)uses the pooled buffers bumps the generation: state that lives in them (the uploaded BA
+  // problem and its captured graphs, the resident matcher / pose inputs) is valid only while the generation is unchanged
+  uint64_t pool_gen = 0;
+  // executable graphs of one LM step [round][first / later step], kept across uploads: a new problem re-captures the step
+  // and updates the executable in place (cudaGraphExecUpdate) instead of instantiating a new one
+  cudaGraphExec_t ba_graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  int ba_graph_kernels[2][2] = {{0, 0}, {0, 0}};
+  int topo_cache = -1;   // BA topology cache: -1 = default (on unless LLD_BA_TOPO_CACHE=0), 0 = off, 1 = on (lld_ctx_set_topo_cache)
+  void pool_reset() { pool_next = 0; pool_gen++; }
   template <typename T>
   T* alloc(size_t n, cudaError_t* e) {
     if (pool_next >= pool.size()) pool.emplace_back();

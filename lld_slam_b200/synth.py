@@ -589,3 +589,75 @@ def make_line_match_batch(n_pairs, n_lines, desc_dim, seed, tau=2.0, min_len=10,
         left_desc=f32(dl[lsel]), right_desc=f32(dr[rsel]),
         K=K, baseline=baseline, tau=float(tau), min_line_length=int(min_len),
     )
+
+
+# ---------------------------------------------------------------------------------------------
+# stereo frames for Frame::ComputeStereoMatches
+# ---------------------------------------------------------------------------------------------
+def make_stereo_frame(seed, n_kp=400, rows=240, cols=376, n_levels=4, sf=1.2):
+    """A textured stereo pair (right = left shifted by a per-band disparity), its pyramids, keypoints at random places
+    with random octaves and ORB-like descriptors (right = left with a few flipped bits; a share are outliers)."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (rows // 4 + 2, (cols + 64) // 4 + 2), dtype=np.uint8)
+    wide = cv2.resize(base, (cols + 64, rows), interpolation=cv2.INTER_CUBIC)
+    left = np.ascontiguousarray(wide[:, 32:32 + cols])
+    disp_of_row = 4 + (np.arange(rows) // 40) * 3            # 4, 7, 10, ... pixels
+    right = np.empty_like(left)
+    for y in range(rows):
+        d = int(disp_of_row[y])
+        right[y] = wide[y, 32 + d:32 + d + cols]             # x_R = x_L - d
+    scale = np.array([sf ** i for i in range(n_levels)], np.float32)
+    inv = (1.0 / scale).astype(np.float32)
+    pyrL, pyrR = [left], [right]
+    for i in range(1, n_levels):
+        sz = (int(round(cols * float(inv[i]))), int(round(rows * float(inv[i]))))
+        pyrL.append(np.ascontiguousarray(cv2.resize(left, sz, interpolation=cv2.INTER_LINEAR)))
+        pyrR.append(np.ascontiguousarray(cv2.resize(right, sz, interpolation=cv2.INTER_LINEAR)))
+    kpL = np.stack([rng.uniform(30, cols - 30, n_kp), rng.uniform(24, rows - 24, n_kp)], 1).astype(np.float32)
+    octL = rng.integers(0, n_levels, n_kp).astype(np.int32)
+    descL = rng.integers(0, 256, (n_kp, 32), dtype=np.uint8)
+    d = disp_of_row[kpL[:, 1].astype(int)].astype(np.float32)
+    kpR = kpL.copy()
+    kpR[:, 0] -= d + rng.normal(0, 0.4, n_kp).astype(np.float32)
+    kpR[:, 1] += rng.normal(0, 0.5, n_kp).astype(np.float32)
+    octR = np.clip(octL + rng.integers(-1, 2, n_kp), 0, n_levels - 1).astype(np.int32)
+    flips = np.where(rng.random(n_kp) < 0.8, rng.integers(0, 40, n_kp), 128)   # inliers: a few bits; outliers: unrelated
+    descR = descL.copy()
+    for i in range(n_kp):
+        for bpos in rng.integers(0, 256, int(flips[i])):
+            descR[i, bpos >> 3] ^= np.uint8(1 << (bpos & 7))
+    perm = rng.permutation(n_kp)
+    kpR, octR, descR = kpR[perm], octR[perm], np.ascontiguousarray(descR[perm])
+    keep = kpR[:, 0] > 20
+    return dict(kpL=kpL, octL=octL, descL=descL, kpR=np.ascontiguousarray(kpR[keep]), octR=np.ascontiguousarray(octR[keep]),
+                descR=np.ascontiguousarray(descR[keep]), scale=scale, inv=inv, pyrL=pyrL, pyrR=pyrR, mb=np.float32(0.54),
+                mbf=np.float32(0.54 * 45.0))
+
+
+def batch_stereo(frames):
+    """frames from make_stereo_frame (same pyramid geometry) -> lld_stereo_problem field dict"""
+    f0 = frames[0]
+    n_levels = len(f0["pyrL"])
+    rows = np.array([a.shape[0] for a in f0["pyrL"]], np.int32)
+    cols = np.array([a.shape[1] for a in f0["pyrL"]], np.int32)
+    stride = cols.copy()
+    offs, blobs, pos = [], [], 0
+    for f in frames:
+        for side in ("pyrL", "pyrR"):
+            for l in range(n_levels):
+                a = np.ascontiguousarray(f[side][l])
+                assert a.shape == (rows[l], cols[l])
+                offs.append(pos); blobs.append(a.reshape(-1)); pos += a.size
+    pyr = np.concatenate(blobs)
+    return dict(
+        n_frames=len(frames), left_off=_csr([len(f["kpL"]) for f in frames]), right_off=_csr([len(f["kpR"]) for f in frames]),
+        left_xy=np.ascontiguousarray(np.concatenate([f["kpL"] for f in frames]), np.float32),
+        left_octave=np.ascontiguousarray(np.concatenate([f["octL"] for f in frames]), np.uint8),
+        left_desc=np.ascontiguousarray(np.concatenate([f["descL"] for f in frames])),
+        right_xy=np.ascontiguousarray(np.concatenate([f["kpR"] for f in frames]).reshape(-1, 2), np.float32),
+        right_octave=np.ascontiguousarray(np.concatenate([f["octR"] for f in frames]), np.uint8),
+        right_desc=np.ascontiguousarray(np.concatenate([f["descR"] for f in frames]).reshape(-1, 32)),
+        n_levels=n_levels, scale_factors=f0["scale"], inv_scale_factors=f0["inv"],
+        pyr=pyr, pyr_bytes=int(pyr.size), pyr_off=np.array(offs, np.int64), pyr_rows=rows, pyr_cols=cols, pyr_stride=stride,
+        mb=float(f0["mb"]), mbf=float(f0["mbf"]), frames=frames)

@@ -11,6 +11,7 @@
 // (alexandervakhitov/lbdmod; call sites src/TwoFrameLineMatcher.cc:112, src/Tracking.cc:1092,1532).
 // PARITY UNPINNED: we define it as the float32-input L2 norm ||a-b||_2 evaluated in double
 // (in-tree evidence: cv::norm(a-b) in src/MapLine.cc:175, threshold scale mdThr: 2.0).
+#include <climits>
 #include <algorithm>
 #include <cmath>
 #include <limits>
@@ -329,6 +330,71 @@ int lldo_line_match(void*, const lld_line_match_problem* p, lld_line_match_resul
       out->match[a0 + j] = min_j;
       if (out->dist) out->dist[a0 + j] = min_j >= 0 ? (float)min_d : std::numeric_limits<float>::infinity();
     }
+  }
+  return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Medoid descriptor of a landmark: MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307) and
+// MapLine::ComputeDistinctiveDescriptors (src/MapLine.cc:133-201).  SURVEY §8(f) row 4.
+// Landmark l owns descriptors [off[l], off[l+1]) (the observations of non-bad keyframes, in std::map order); best[l] is
+// the index (landmark-local) of the descriptor with the least median distance to the others, -1 for an empty landmark.
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int lldo_medoid_orb(void*, int n_lm, const int32_t* off, const uint8_t* desc, int32_t* best) {
+  for (int l = 0; l < n_lm; l++) {
+    const int N = off[l + 1] - off[l];
+    best[l] = -1;
+    if (N <= 0) continue;
+    const uint8_t* d = desc + 32 * (size_t)off[l];
+    std::vector<float> Dm((size_t)N * N, 0.f);   // float Distances[N][N]  (:277)
+    for (int i = 0; i < N; i++)
+      for (int j = i + 1; j < N; j++) {
+        const int dij = lldo_descriptor_distance(d + 32 * (size_t)i, d + 32 * (size_t)j);
+        Dm[(size_t)i * N + j] = (float)dij;
+        Dm[(size_t)j * N + i] = (float)dij;
+      }
+    int BestMedian = INT_MAX, BestIdx = 0;
+    for (int i = 0; i < N; i++) {
+      std::vector<int> v(Dm.begin() + (size_t)i * N, Dm.begin() + (size_t)(i + 1) * N);   // vector<int> from floats (:293)
+      std::sort(v.begin(), v.end());
+      const int median = v[(size_t)(0.5 * (N - 1))];
+      if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+    }
+    best[l] = BestIdx;
+  }
+  return 0;
+}
+
+int lldo_medoid_float(void*, int n_lm, const int32_t* off, int D, const float* desc, int32_t* best) {
+  for (int l = 0; l < n_lm; l++) {
+    const int N = off[l + 1] - off[l];
+    best[l] = -1;
+    if (N <= 0) continue;
+    const float* d = desc + (size_t)D * off[l];
+    std::vector<float> Dm((size_t)N * N, 0.f);
+    for (int i = 0; i < N; i++)
+      for (int j = i + 1; j < N; j++) {
+        double s = 0;   // cv::norm(a - b): float difference, squares accumulated in double (:175)
+        for (int k = 0; k < D; k++) {
+          const float df = d[(size_t)i * D + k] - d[(size_t)j * D + k];
+          s += (double)df * (double)df;
+        }
+        const double dij = std::sqrt(s);
+        Dm[(size_t)i * N + j] = (float)dij;
+        Dm[(size_t)j * N + i] = (float)dij;
+      }
+    int BestMedian = INT_MAX, BestIdx = 0;
+    for (int i = 0; i < N; i++) {
+      std::vector<float> v(Dm.begin() + (size_t)i * N, Dm.begin() + (size_t)(i + 1) * N);
+      std::sort(v.begin(), v.end());
+      const int median = (int)v[(size_t)(0.5 * (N - 1))];   // `int median = vDists[...]`: the float is truncated (:190)
+      if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+    }
+    best[l] = BestIdx;
   }
   return 0;
 }

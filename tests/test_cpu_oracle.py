@@ -333,45 +333,8 @@ def test_host_indexing_is_deterministic(built, capfd, monkeypatch):
 # ------------------------------------------------------------------------------------------------
 # SURVEY §8(f) row 1 (next round's kernel): Frame::ComputeStereoMatches, oracle pinned ahead of the product
 # ------------------------------------------------------------------------------------------------
-def _stereo_frame(seed, n_kp=400, rows=240, cols=376, n_levels=4, sf=1.2):
-    """A textured stereo pair (right = left shifted by a per-band disparity), its pyramids, keypoints at random places
-    with random octaves and ORB-like descriptors (right = left with a few flipped bits; a share are outliers)."""
-    import cv2
-    rng = np.random.default_rng(seed)
-    base = rng.integers(0, 256, (rows // 4 + 2, (cols + 64) // 4 + 2), dtype=np.uint8)
-    wide = cv2.resize(base, (cols + 64, rows), interpolation=cv2.INTER_CUBIC)
-    left = np.ascontiguousarray(wide[:, 32:32 + cols])
-    disp_of_row = 4 + (np.arange(rows) // 40) * 3            # 4, 7, 10, ... pixels
-    right = np.empty_like(left)
-    for y in range(rows):
-        d = int(disp_of_row[y])
-        right[y] = wide[y, 32 + d:32 + d + cols]             # x_R = x_L - d
-    scale = np.array([sf ** i for i in range(n_levels)], np.float32)
-    inv = (1.0 / scale).astype(np.float32)
-    pyrL, pyrR = [left], [right]
-    for i in range(1, n_levels):
-        sz = (int(round(cols * float(inv[i]))), int(round(rows * float(inv[i]))))
-        pyrL.append(np.ascontiguousarray(cv2.resize(left, sz, interpolation=cv2.INTER_LINEAR)))
-        pyrR.append(np.ascontiguousarray(cv2.resize(right, sz, interpolation=cv2.INTER_LINEAR)))
-    kpL = np.stack([rng.uniform(30, cols - 30, n_kp), rng.uniform(24, rows - 24, n_kp)], 1).astype(np.float32)
-    octL = rng.integers(0, n_levels, n_kp).astype(np.int32)
-    descL = rng.integers(0, 256, (n_kp, 32), dtype=np.uint8)
-    d = disp_of_row[kpL[:, 1].astype(int)].astype(np.float32)
-    kpR = kpL.copy()
-    kpR[:, 0] -= d + rng.normal(0, 0.4, n_kp).astype(np.float32)
-    kpR[:, 1] += rng.normal(0, 0.5, n_kp).astype(np.float32)
-    octR = np.clip(octL + rng.integers(-1, 2, n_kp), 0, n_levels - 1).astype(np.int32)
-    descR = descL.copy()
-    for i in range(n_kp):
-        nflip = int(rng.integers(0, 40)) if rng.random() < 0.8 else 128   # inliers: a few bits; outliers: unrelated
-        for bpos in rng.integers(0, 256, nflip):
-            descR[i, bpos >> 3] ^= np.uint8(1 << (bpos & 7))
-    perm = rng.permutation(n_kp)
-    kpR, octR, descR = kpR[perm], octR[perm], np.ascontiguousarray(descR[perm])
-    keep = kpR[:, 0] > 20
-    return dict(kpL=kpL, octL=octL, descL=descL, kpR=np.ascontiguousarray(kpR[keep]), octR=np.ascontiguousarray(octR[keep]),
-                descR=np.ascontiguousarray(descR[keep]), scale=scale, inv=inv, pyrL=pyrL, pyrR=pyrR, mb=np.float32(0.54),
-                mbf=np.float32(0.54 * 45.0))
+def _stereo_frame(seed, **kw):
+    return synth.make_stereo_frame(seed, **kw)
 
 
 def _stereo_matches_numpy(f):
@@ -501,3 +464,61 @@ def test_oracle_stereo_matches_against_numpy(built):
     f["kpR"], f["octR"], f["descR"] = f["kpR"][:0], f["octR"][:0], f["descR"][:0]
     n, uR, dep = _stereo_matches_oracle(f)
     assert n == 0 and (uR == -1).all() and (dep == -1).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# medoid (distinctive) descriptors of map points / map lines
+# ------------------------------------------------------------------------------------------------
+def _medoid_landmarks(seed, n_lm=150, max_obs=14, dim=None):
+    rng = np.random.default_rng(seed)
+    cnt = rng.integers(0, max_obs, n_lm)
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    if dim is None:
+        base = rng.integers(0, 256, (n_lm, 32), dtype=np.uint8)
+        desc = np.zeros((int(off[-1]), 32), np.uint8)
+        for l in range(n_lm):
+            for j in range(off[l], off[l + 1]):
+                d = base[l].copy()
+                for b in rng.integers(0, 256, int(rng.integers(0, 60))):
+                    d[b >> 3] ^= np.uint8(1 << (b & 7))
+                desc[j] = d
+        return off, desc
+    base = rng.normal(0, 1, (n_lm, dim))
+    desc = np.zeros((int(off[-1]), dim), np.float32)
+    for l in range(n_lm):
+        for j in range(off[l], off[l + 1]):
+            desc[j] = (base[l] * rng.uniform(0.5, 3.0) + rng.normal(0, 0.6, dim)).astype(np.float32)   # distances straddle 1, 2, 3 ...
+    return off, desc
+
+
+def test_oracle_medoid_descriptors_against_numpy(built):
+    """MapPoint / MapLine::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307, src/MapLine.cc:133-201): the oracle against a
+    transcription with cv2.norm (NORM_HAMMING / NORM_L2), float distance table, truncated int median, first index on ties"""
+    import cv2
+
+    def ref(off, desc, ham):
+        out = []
+        for l in range(len(off) - 1):
+            N = int(off[l + 1] - off[l])
+            if N == 0:
+                out.append(-1)
+                continue
+            d = desc[off[l]:off[l + 1]]
+            Dm = np.zeros((N, N), np.float32)
+            for i in range(N):
+                for j in range(i + 1, N):
+                    Dm[i, j] = Dm[j, i] = cv2.norm(d[i], d[j], cv2.NORM_HAMMING) if ham else cv2.norm(d[i] - d[j])
+            bm, bi = 2 ** 31 - 1, 0
+            for i in range(N):
+                m = int(np.sort(Dm[i])[int(0.5 * (N - 1))])
+                if m < bm:
+                    bm, bi = m, i
+            out.append(bi)
+        return np.array(out, np.int32)
+
+    off, desc = _medoid_landmarks(1)
+    assert np.array_equal(api.medoid_orb(off, desc, impl="oracle"), ref(off, desc, True))
+    off, desc = _medoid_landmarks(2, dim=64)
+    got = api.medoid_float(off, desc, impl="oracle")
+    assert np.array_equal(got, ref(off, desc, False))
+    assert len(set(got.tolist())) > 3     # not everything collapses onto index 0

@@ -491,3 +491,44 @@ def test_full_size_global_ba_config(gpu_ctx):
     assert dT[well].max() <= POS_TOL, dT[well].max()
     assert np.all(dT[~well] <= 30 * spread[~well]), (dT[~well] / spread[~well]).max()
     assert np.median(dT) <= 1e-5 and np.median(rot_angle(g["kf_Tcw"], o["kf_Tcw"])) <= ROT_TOL
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Frame::ComputeStereoMatches
+# ------------------------------------------------------------------------------------------------------------------
+def test_stereo_matches_bit_exact(gpu_ctx):
+    """row-banded Hamming candidates + 11x11 SAD slide + parabola fit + median gate: mvuRight / mvDepth bit for bit against
+    the oracle (itself pinned against a numpy / cv2 transcription in test_cpu_oracle.py), ragged batch, one empty frame"""
+    frames = [synth.make_stereo_frame(s, n_kp=n) for s, n in ((1, 400), (2, 650), (3, 120), (5, 900))]
+    e = synth.make_stereo_frame(4)
+    e["kpR"], e["octR"], e["descR"] = e["kpR"][:0], e["octR"][:0], e["descR"][:0]     # no right keypoints at all
+    frames.append(e)
+    p = synth.batch_stereo(frames)
+    g = api.stereo_matches(p, impl="gpu", ctx=gpu_ctx)
+    o = api.stereo_matches(p, impl="oracle")
+    assert np.array_equal(g["n_matched"], o["n_matched"]) and o["n_matched"][:4].min() > 40 and o["n_matched"][4] == 0
+    assert np.array_equal(g["uright"], o["uright"])
+    assert np.array_equal(g["depth"], o["depth"])
+
+
+def test_stereo_matches_full_frame_size(gpu_ctx):
+    """KITTI-sized frames: 2000 keypoints, 1241 x 376, 8 pyramid levels, batch of 8"""
+    frames = [synth.make_stereo_frame(40 + s, n_kp=2000, rows=376, cols=1241, n_levels=8) for s in range(8)]
+    p = synth.batch_stereo(frames)
+    g = api.stereo_matches(p, impl="gpu", ctx=gpu_ctx)
+    o = api.stereo_matches(p, impl="oracle")
+    assert np.array_equal(g["n_matched"], o["n_matched"]) and o["n_matched"].min() > 500
+    assert np.array_equal(g["uright"], o["uright"]) and np.array_equal(g["depth"], o["depth"])
+
+
+def test_medoid_descriptors(gpu_ctx):
+    """distinctive descriptors of map points (Hamming) and map lines (L2), batched, index-exact"""
+    import test_cpu_oracle as tco
+    off, desc = tco._medoid_landmarks(11, n_lm=3000, max_obs=40)
+    assert np.array_equal(api.medoid_orb(off, desc, impl="gpu", ctx=gpu_ctx), api.medoid_orb(off, desc, impl="oracle"))
+    off, desc = tco._medoid_landmarks(12, n_lm=1000, max_obs=30, dim=72)
+    assert np.array_equal(api.medoid_float(off, desc, impl="gpu", ctx=gpu_ctx), api.medoid_float(off, desc, impl="oracle"))
+    off, desc = tco._medoid_landmarks(13, n_lm=4, max_obs=250)      # long tracks: several descriptors per lane
+    off = np.array([0, 0, 200, 201, 201 + 255], np.int32)
+    desc = np.random.default_rng(5).integers(0, 256, (int(off[-1]), 32), dtype=np.uint8)
+    assert np.array_equal(api.medoid_orb(off, desc, impl="gpu", ctx=gpu_ctx), api.medoid_orb(off, desc, impl="oracle"))
