@@ -14,7 +14,7 @@
 //      (distance, index) pairs; only the distance of the middle element is used), reject distance >= 1.5 * 1.4 * median
 //      (:692-703).
 // Undefined behaviour of the reference (unchecked row index, patches leaving the pyramid image, median of an empty list)
-// is resolved as in oracle/lldo_stereo.cpp: the point gets no stereo match.
+// is resolved as DESIGN.md documents (and as the test oracle does): the point gets no stereo match.
 #include <algorithm>
 #include <cfloat>
 #include <climits>
