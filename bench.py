@@ -636,6 +636,7 @@ def run_extra(lib, d, ctx, hbm_peak, R):
         m = synth.make_sbp_frame_batch(P, N, synth.seed_for(2) + 31 * rank)
         geom, gk = capi.make_geom(m["geom"])
         f = dict(m); f["geom"] = geom
+        f.setdefault("th_high", 0); f.setdefault("allow_negative_depth", 0)
         prob, keep = capi.fill_struct(capi.SbpFrameProblem, f)
         ctx.check(d.lld_sbp_frame_upload(ctx.handle, C.byref(prob)), "sbp upload")
         passes = C.c_int()

@@ -232,6 +232,14 @@ typedef struct lld_sbp_frame_problem {
   const float* last_angle;   /* [n_last] mvKeysUn[i].angle */
   const uint8_t* last_desc;  /* [n_last][32] pMP->GetDescriptor() */
   const uint8_t* last_has_obs;/* [n_last] pMP->Observations()>0 : a kp claimed by this point blocks later points */
+  /* The relocalisation variant ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist)
+   * (include/ORBmatcher.h:56, src/ORBmatcher.cc:1472-1599) is the same search with: "last" = the keyframe's map points
+   * (last_valid = non-null, not bad, not in sAlreadyFound, dist3D inside the scale-invariance range; last_octave = the
+   * PredictScale level; last_angle = pKF->mvKeysUn[i].angle; last_has_obs = 1: every accepted match claims its keypoint),
+   * mono = 1 (levels [l-1, l+1]), cur_uright = -1 (no stereo test), cur_claimed = mvpMapPoints[i] != NULL, and the two
+   * fields below.  Zero (a memset struct) selects the frame-to-frame behaviour. */
+  int32_t th_high;              /* accept bestDist <= th_high; 0 = TH_HIGH (100).  Relocalisation: ORBdist */
+  int32_t allow_negative_depth; /* 1: no `invzc < 0` rejection (src/ORBmatcher.cc:1497-1502 has none) */
 } lld_sbp_frame_problem;
 
 typedef struct lld_sbp_result {
@@ -337,6 +345,46 @@ int lld_stereo_matches(void* ctx, const lld_stereo_problem* p, lld_stereo_result
  * ---------------------------------------------------------------------------------------------- */
 int lld_medoid_orb(void* ctx, int32_t n_lm, const int32_t* off, const uint8_t* desc /*[n][32]*/, int32_t* best);
 int lld_medoid_float(void* ctx, int32_t n_lm, const int32_t* off, int32_t desc_dim, const float* desc /*[n][desc_dim]*/, int32_t* best);
+
+/* ------------------------------------------------------------------------------------------------
+ * Temporal line association: Tracking::AddLinesFrom  include/Tracking.h, src/Tracking.cc:996-1124
+ * (reprojection gate vgl::LineReprojErrorL1 src/vgl.cc:548-559 in the left and the right image, octave-scaled threshold
+ * GetReprojThrPyramid src/LineMatching.cc:239-247, smallest descriptor distance, sequential claim of current lines).
+ * Batched over frames.  The candidate lists are an input: the reference takes them from Frame::lines_grid through
+ * SubselectWithGrid, but the release never fills that grid; the caller decides which current lines a map line sees.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct lld_line_assoc_problem {
+  int32_t n_frames;
+  const int32_t* ml_off;         /* [n_frames+1] map lines offered to the frame (lines_last), in call order */
+  const uint8_t* ml_valid;       /* [n_ml] pML && pML->tracked_last_id != frame id && !pML->isBad() */
+  const double* ml_x0_dir;       /* [n_ml][6] GetMinimalPos */
+  const double* ml_x1x2;         /* [n_ml][6] GetMainPoints3D */
+  const float* ml_desc;          /* [n_ml][desc_dim] descs[i] / mLastFrame.mDescriptorsLines.row(i) */
+  const int32_t* cand_off;       /* [n_ml+1] */
+  const int32_t* cand_idx;       /* sub_inds: frame-local indices of current left lines, in SubselectWithGrid order */
+  const int32_t* cur_off;        /* [n_frames+1] current frame left lines */
+  const float* cur_left;         /* [n_cur][4] mvLinesLeft start / end point */
+  const int32_t* cur_octave;     /* [n_cur] mvLinesLeft[si].octave */
+  const int32_t* cur_line_match; /* [n_cur] line_matches[si]: frame-local right line or -1 */
+  const uint8_t* cur_taken;      /* [n_cur] mvpMapLines[si] != NULL on entry */
+  const float* cur_desc;         /* [n_cur][desc_dim] mDescriptorsLines */
+  const int32_t* right_off;      /* [n_frames+1] */
+  const float* cur_right;        /* [n_right][4] mvLinesRight */
+  int32_t desc_dim;
+  const double* T_curr;          /* [n_frames][16] row-major 4x4, the convention of vgl::MapPoint: R^T (X - c) */
+  const double* T_right;         /* [n_frames][16] GetTForRight(T_curr, mb) */
+  double K[9];
+  double thr_reproj_base;        /* thrReprojLineBase */
+  double md_thr;                 /* mdThr */
+  int32_t monocular;             /* mSensor == System::MONOCULAR */
+} lld_line_assoc_problem;
+
+typedef struct lld_line_assoc_result {
+  int32_t* cur_assoc;  /* [n_cur] frame-local index of the map line newly associated with the current line, -1 = none */
+  int32_t* n_added;    /* [n_frames] cnt_added; may be NULL */
+} lld_line_assoc_result;
+
+int lld_line_associate(void* ctx, const lld_line_assoc_problem* p, lld_line_assoc_result* out);
 
 /* Library self-description (for tests and the bench): version string, number of kernels launched by the
  * last call on this context, device-side duration of the last call measured with CUDA events on the

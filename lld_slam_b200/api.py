@@ -99,6 +99,7 @@ def sbp_frame(p: Dict[str, Any], *, impl: str = "gpu", ctx=None):
     lib = _lib(impl)
     geom, gk = capi.make_geom(p["geom"])
     f = dict(p); f["geom"] = geom
+    f.setdefault("th_high", 0); f.setdefault("allow_negative_depth", 0)
     prob, keep = capi.fill_struct(capi.SbpFrameProblem, f)
     out = _sbp_out(int(p["cur_off"][-1]), int(p["last_off"][-1]), int(p["n_pairs"]))
     res, keep2 = capi.fill_struct(capi.SbpResult, out)
@@ -196,3 +197,31 @@ def medoid_float(off, desc, *, impl: str = "gpu", ctx=None):
             best.ctypes.data_as(capi.c_i32p))
     _check(impl, ctx, rc, "lld_medoid_float")
     return best
+
+
+class LineAssocProblem(C.Structure):
+    _fields_ = [
+        ("n_frames", C.c_int32), ("ml_off", capi.c_i32p), ("ml_valid", capi.c_u8p), ("ml_x0_dir", capi.c_f64p), ("ml_x1x2", capi.c_f64p),
+        ("ml_desc", capi.c_f32p), ("cand_off", capi.c_i32p), ("cand_idx", capi.c_i32p), ("cur_off", capi.c_i32p), ("cur_left", capi.c_f32p),
+        ("cur_octave", capi.c_i32p), ("cur_line_match", capi.c_i32p), ("cur_taken", capi.c_u8p), ("cur_desc", capi.c_f32p),
+        ("right_off", capi.c_i32p), ("cur_right", capi.c_f32p), ("desc_dim", C.c_int32), ("T_curr", capi.c_f64p), ("T_right", capi.c_f64p),
+        ("K", C.c_double * 9), ("thr_reproj_base", C.c_double), ("md_thr", C.c_double), ("monocular", C.c_int32),
+    ]
+
+
+class LineAssocResult(C.Structure):
+    _fields_ = [("cur_assoc", capi.c_i32p), ("n_added", capi.c_i32p)]
+
+
+def line_associate(p: Dict[str, Any], *, impl: str = "gpu", ctx=None):
+    """Tracking::AddLinesFrom, batched over frames"""
+    dll = _lib(impl).dll
+    fn = getattr(dll, ("lld_" if impl == "gpu" else "lldo_") + "line_associate")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.POINTER(LineAssocProblem), C.POINTER(LineAssocResult)]
+    prob, keep = capi.fill_struct(LineAssocProblem, p)
+    out = dict(cur_assoc=np.full(int(p["cur_off"][-1]), -2, np.int32), n_added=np.zeros(int(p["n_frames"]), np.int32))
+    res, keep2 = capi.fill_struct(LineAssocResult, out)
+    rc = fn(_handle(impl, ctx), C.byref(prob), C.byref(res))
+    _check(impl, ctx, rc, "lld_line_associate")
+    return out

@@ -93,6 +93,7 @@ class SbpFrameProblem(C.Structure):
         ("cur_desc", c_u8p), ("cur_claimed", c_u8p), ("cur_Tcw", c_f32p), ("last_Tcw", c_f32p),
         ("last_off", c_i32p), ("last_valid", c_u8p), ("last_xw", c_f32p), ("last_octave", c_u8p), ("last_angle", c_f32p),
         ("last_desc", c_u8p), ("last_has_obs", c_u8p),
+        ("th_high", C.c_int32), ("allow_negative_depth", C.c_int32),
     ]
 
 

@@ -1770,6 +1770,7 @@ extern "C" int lld_ba_run_global(void* ctx, int n_iter, const volatile uint8_t* 
   if (!c || !c->ba) return LLD_ERR_ARG;
   { int r0 = ba_state_valid(c); if (r0) return r0; }
   LLD_CUDA(c, cudaSetDevice(c->device));
+  c->nccl_calls = 0; c->nccl_bytes = 0;
   int r = ba_init_state(c);
   if (r) return r;
   c->ba->v.prm.robust_ln = 1;

@@ -41,7 +41,7 @@ constexpr int CR_RG = 8;        // row groups (a thread owns RPT consecutive row
 constexpr int CR_RPT = 20;
 constexpr int CR_MAX_M = 156;   // shared-memory capacity of k_cr_factor: (m^2 + 8 m + 40) doubles
 constexpr int CR_TILE = 64;     // k_cr_update output tile
-constexpr int CR_KC = 8;        // k-chunk of the tile products
+constexpr int CR_KC = 16;       // k-chunk of the tile products
 
 // scatter the block rows of S (upper blocks, nb lists) and b_schur into the super-block arrays (zeroed beforehand);
 // padding rows of the last super-block get a unit diagonal
@@ -251,29 +251,44 @@ __global__ void __launch_bounds__(CR_TC / 2 * CR_RG) k_cr_solve(BaView v, CrView
   }
 }
 
-// acc[u][w] += sum_k A(k, r0 + ty + 16 u) B(k, c0 + tx + 16 w) over one 64x64 tile (256 threads = 16 x 16); TA: A is stored [r][k] (row-major m x m), else [k][r]
+// acc[u][w] += sum_k A(k, r0 + ty + 16 u) B(k, c0 + tx + 16 w) over one 64x64 tile (256 threads = 16 x 16);
+// TA: A is stored [r][k] (row-major m x m), else [k][r].  The k-chunk after the one being multiplied is already in
+// registers (global loads issued before the FMAs of the current chunk), so the L2 latency is paid once per tile.
 template <bool TA>
 __device__ __forceinline__ void cr_tile_product(const double* __restrict__ Ag, int lda, const double* __restrict__ Bg, int ldb,
                                                 int m, int r0, int c0, double (*As)[CR_TILE + 4], double (*Bs)[CR_TILE + 4],
                                                 double acc[4][4]) {
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  for (int k0 = 0; k0 < m; k0 += CR_KC) {
-    __syncthreads();
-    for (int e = tid; e < CR_KC * CR_TILE; e += 256) {
+  constexpr int PER = CR_KC * CR_TILE / 256;   // elements of each operand chunk per thread
+  double pa[PER], pb[PER];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+      const int e = tid + 256 * q;
       int kk, rr;
       if (TA) { kk = e % CR_KC; rr = e / CR_KC; }      // consecutive threads walk k (contiguous in memory)
       else { rr = e % CR_TILE; kk = e / CR_TILE; }
       const int k = k0 + kk, r = r0 + rr;
-      double a = 0.0;
-      if (k < m && r < m) a = TA ? Ag[(size_t)r * lda + k] : Ag[(size_t)k * lda + r];
-      As[kk][rr] = a;
+      pa[q] = (k < m && r < m) ? (TA ? Ag[(size_t)r * lda + k] : Ag[(size_t)k * lda + r]) : 0.0;
+      const int cc = e % CR_TILE, kb = e / CR_TILE;
+      const int k2 = k0 + kb, c = c0 + cc;
+      pb[q] = (k2 < m && c < m) ? Bg[(size_t)k2 * ldb + c] : 0.0;
     }
-    for (int e = tid; e < CR_KC * CR_TILE; e += 256) {
-      const int cc = e % CR_TILE, kk = e / CR_TILE;
-      const int k = k0 + kk, c = c0 + cc;
-      Bs[kk][cc] = (k < m && c < m) ? Bg[(size_t)k * ldb + c] : 0.0;
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < m; k0 += CR_KC) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+      const int e = tid + 256 * q;
+      int kk, rr;
+      if (TA) { kk = e % CR_KC; rr = e / CR_KC; }
+      else { rr = e % CR_TILE; kk = e / CR_TILE; }
+      As[kk][rr] = pa[q];
+      Bs[e / CR_TILE][e % CR_TILE] = pb[q];
     }
     __syncthreads();
+    if (k0 + CR_KC < m) fetch(k0 + CR_KC);
 #pragma unroll
     for (int kk = 0; kk < CR_KC; kk++) {
       double a[4], b[4];

@@ -528,18 +528,26 @@ __device__ __forceinline__ float warp_exact_d2(const float* a, const float* b, i
 // far are put through the FP64 gates at once, and the loop ends when no lane can beat that key.  The result is the
 // smallest admissible untaken key, exactly as an exhaustive evaluation would give it, with ~40 gate evaluations per line
 // instead of ~150 (k_line_gate remains for the statistics run).  The next line's list is prefetched meanwhile.
+// The kernel handles the left lines [j_begin, j_end) of every pair and keeps the pair's "taken" mask in global memory in
+// between, so that the host can launch it once per 128-row block as soon as k_line_tc has produced that block's lists
+// (the contraction of block r + 1 then runs under the greedy of block r: the greedy CTAs are one warp with 64 B of
+// shared memory, so several of them fit beside a k_line_tc CTA on every SM).
 constexpr int GL_NE = TC_CAND / 32;   // list entries per lane
-__global__ void __launch_bounds__(128) k_line_greedy_lazy(LineTcView t) {
-  __shared__ uint32_t s_taken[4][TC_COLS / 32];
+constexpr int GL_WARPS = 1;           // pairs per CTA
+__global__ void __launch_bounds__(32 * GL_WARPS) k_line_greedy_lazy(LineTcView t, int j_begin, int j_end, uint32_t* __restrict__ taken_g) {
+  __shared__ uint32_t s_taken[GL_WARPS][TC_COLS / 32];
   const LineMatchView& v = t.v;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = blockIdx.x * 4 + wid;
+  const int p = blockIdx.x * GL_WARPS + wid;
   if (p >= v.n_pairs) return;
-  const int a0 = v.left_off[p], na = v.left_off[p + 1] - a0;
+  const int a0 = v.left_off[p], na_all = v.left_off[p + 1] - a0;
   const int b0 = v.right_off[p], nb = v.right_off[p + 1] - b0;
+  const int na = min(na_all, j_end);
+  if (j_begin >= na) return;
   uint32_t* taken = s_taken[wid];
-  if (lane < TC_COLS / 32) taken[lane] = 0;
-  __syncwarp();
+  if (lane < TC_COLS / 32) taken[lane] = j_begin == 0 ? 0u : taken_g[(size_t)p * (TC_COLS / 32) + lane];
+  const double* rleq = v.right_leq + 3 * (size_t)b0;   // (staging these 12 KB in shared memory bought nothing and left room
+  __syncwarp();                                        //  for only one greedy CTA beside a k_line_tc CTA: measured)
   // entry e = lane + 32 i of the line's list, in the order (column half 0 slots, column half 1 slots)
   uint32_t nd2[GL_NE];
   uint16_t ncol[GL_NE];
@@ -561,8 +569,8 @@ __global__ void __launch_bounds__(128) k_line_greedy_lazy(LineTcView t) {
       }
     }
   };
-  if (na > 0) fetch(0);
-  for (int j = 0; j < na; j++) {
+  fetch(j_begin);
+  for (int j = j_begin; j < na; j++) {
     unsigned long long ke[GL_NE];
     const int cnt0 = ncnt0, cnt1 = ncnt1;
 #pragma unroll
@@ -588,8 +596,7 @@ __global__ void __launch_bounds__(128) k_line_greedy_lazy(LineTcView t) {
         if (!__any_sync(0xffffffffu, act)) break;
         unsigned long long mine = ~0ull;
         if (act) {
-          const int gc = b0 + (int)(cand & 0xFFFFull);
-          if (line_pair_gate_fast(v, v.left_seg + 4 * (size_t)gl, v.left_leq + 3 * (size_t)gl, v.right_leq + 3 * (size_t)gc)) {
+          if (line_pair_gate_fast(v, v.left_seg + 4 * (size_t)gl, v.left_leq + 3 * (size_t)gl, rleq + 3 * (int)(cand & 0xFFFFull))) {
             mine = cand;
             done = true;   // this lane's later keys are larger
           }
@@ -640,6 +647,7 @@ __global__ void __launch_bounds__(128) k_line_greedy_lazy(LineTcView t) {
     }
     __syncwarp();
   }
+  if (lane < TC_COLS / 32) taken_g[(size_t)p * (TC_COLS / 32) + lane] = taken[lane];
 }
 
 // exact distance of every match (FP32, difference form, as the tile path reports it): one warp per left line
@@ -756,12 +764,19 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
   int* d_tc_err = nullptr;
   LLD_LAUNCH(c, k_line_prep, cdiv(nmax, 128), 128, 0, v, n_left, n_right);
   if (use_tc) {
-    std::vector<int> ttp, ttr;
-    for (int i = 0; i < P; i++) {
-      const int na = p->left_off[i + 1] - p->left_off[i];
-      if (p->right_off[i + 1] - p->right_off[i] == 0) continue;   // no right lines: every left line stays unmatched
-      for (int r = 0; r < cdiv(na, TC_ROWS); r++) { ttp.push_back(i); ttr.push_back(r); }
+    // tiles ordered by row block: block r of every pair is contracted by one launch, after which the greedy can advance
+    // through the left lines [128 r, 128 (r + 1)) of every pair while the next block is being contracted
+    std::vector<int> ttp, ttr, blk_begin;
+    const int n_blk = cdiv(std::max(max_na, 1), TC_ROWS);
+    for (int r = 0; r < n_blk; r++) {
+      blk_begin.push_back((int)ttp.size());
+      for (int i = 0; i < P; i++) {
+        const int na = p->left_off[i + 1] - p->left_off[i];
+        if (p->right_off[i + 1] - p->right_off[i] == 0) continue;   // no right lines: every left line stays unmatched
+        if (r < cdiv(na, TC_ROWS)) { ttp.push_back(i); ttr.push_back(r); }
+      }
     }
+    blk_begin.push_back((int)ttp.size());
     LineTcView t;
     t.v = v;
     int *d_ttp, *d_ttr;
@@ -776,17 +791,38 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
     LLD_CUDA(c, cudaMemsetAsync(t.err_flag, 0, 8 * sizeof(int), c->stream));
     d_tc_err = t.err_flag;
     LLD_CUDA(c, cudaMemsetAsync(t.cand_cnt, 0, sizeof(uint16_t) * 2 * (size_t)n_left, c->stream));
-    if (!ttp.empty()) {
-      const size_t smem = (size_t)(TC_ROWS + TC_HALF) * v.D * 8 + TC_COLS * 16 + TC_COLS + 16 + 64;
-      LLD_CUDA(c, lld_raise_dyn_smem(k_line_tc, (size_t)(int)smem));
-      LLD_LAUNCH(c, k_line_tc, (int)ttp.size(), TC_NT, smem, t);
+    uint32_t* d_taken_bits;
+    UPM(d_taken_bits, uint32_t, nullptr, (size_t)P * (TC_COLS / 32));
+    const size_t smem = (size_t)(TC_ROWS + TC_HALF) * v.D * 8 + TC_COLS * 16 + TC_COLS + 16 + 64;
+    if (!ttp.empty()) LLD_CUDA(c, lld_raise_dyn_smem(k_line_tc, (size_t)(int)smem));
+    const bool stats = getenv("LLD_LINE_STATS") != nullptr;
+    cudaStream_t s0 = c->stream, s1 = (c->prof_on || stats) ? c->stream : c->side[0];
+    if (s1 != s0) {   // the side stream starts after everything enqueued so far (uploads, prep, memsets)
+      LLD_CUDA(c, cudaEventRecord(c->ev_fork, s0));
+      LLD_CUDA(c, cudaStreamWaitEvent(s1, c->ev_fork, 0));
     }
-    if (getenv("LLD_LINE_STATS")) {   // exhaustive gate pass: candidate / admissibility counts, 3xTF32 distance error
-      LLD_CUDA(c, cudaMemsetAsync(t.cand_adm, 0, sizeof(uint32_t) * (size_t)TC_AW * n_left, c->stream));
-      LLD_LAUNCH(c, k_line_gate, cdiv(n_left, 16), 256, 0, t, n_left, 1);
+    for (int r = 0; r < n_blk; r++) {
+      const int nt = blk_begin[r + 1] - blk_begin[r];
+      if (nt > 0) {
+        LineTcView tr2 = t;
+        tr2.tile_pair = d_ttp + blk_begin[r]; tr2.tile_r = d_ttr + blk_begin[r];
+        LLD_LAUNCH_S(c, s0, k_line_tc, nt, TC_NT, smem, tr2);
+      }
+      if (stats && r == n_blk - 1) {   // exhaustive gate pass: candidate / admissibility counts, 3xTF32 distance error
+        LLD_CUDA(c, cudaMemsetAsync(t.cand_adm, 0, sizeof(uint32_t) * (size_t)TC_AW * n_left, s0));
+        LLD_LAUNCH_S(c, s0, k_line_gate, cdiv(n_left, 16), 256, 0, t, n_left, 1);
+      }
+      if (s1 != s0) {
+        LLD_CUDA(c, cudaEventRecord(c->ev_fork, s0));
+        LLD_CUDA(c, cudaStreamWaitEvent(s1, c->ev_fork, 0));
+      }
+      LLD_LAUNCH_S(c, s1, k_line_greedy_lazy, cdiv(P, GL_WARPS), 32 * GL_WARPS, 0, t, r * TC_ROWS, (r + 1) * TC_ROWS, d_taken_bits);
     }
-    LLD_LAUNCH(c, k_line_greedy_lazy, cdiv(P, 4), 128, 0, t);
-    LLD_LAUNCH(c, k_line_exact, cdiv(n_left, 8), 256, 0, t, n_left);
+    LLD_LAUNCH_S(c, s1, k_line_exact, cdiv(n_left, 8), 256, 0, t, n_left);
+    if (s1 != s0) {
+      LLD_CUDA(c, cudaEventRecord(c->ev_join[0], s1));
+      LLD_CUDA(c, cudaStreamWaitEvent(s0, c->ev_join[0], 0));
+    }
   } else if (!tp.empty()) {
     const size_t smem = sizeof(float) * 2 * LT * (v.D + 1);
     LLD_CUDA(c, lld_raise_dyn_smem(k_line_dist, (size_t)(int)smem));

@@ -74,6 +74,8 @@ struct MatchView {
   int* q_ncand;    // [n_q] number of admissible candidates seen by the scan
   int* match;      // [n_cur]
   int* n_matches;  // [n_pairs]
+  int th_high;         // acceptance threshold on the best distance (TH_HIGH, or ORBdist of the relocalisation variant)
+  int allow_neg_z;     // no invzc < 0 rejection (relocalisation variant)
   int max_cur, max_q;  // largest pair (host side dispatch)
   int fused_ok;
 };
@@ -223,7 +225,7 @@ __device__ __forceinline__ QueryWin query_window(const MatchView& v, int q, int 
     const float yc = gemm_row(Tc + 3, Xw, Tc[10]);
     const float zc = gemm_row(Tc + 6, Xw, Tc[11]);
     const float invzc = (float)(1.0 / (double)zc);
-    if (invzc < 0) w.valid = false;
+    if (invzc < 0 && !v.allow_neg_z) w.valid = false;
     w.x = __fadd_rn(__fmul_rn(__fmul_rn(v.fx, xc), invzc), v.cx);
     w.y = __fadd_rn(__fmul_rn(__fmul_rn(v.fy, yc), invzc), v.cy);
     if (w.x < v.min_x || w.x > v.max_x) w.valid = false;
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(128) k_match_resolve(MatchView v, int pass) {
     k2 = t[1];
   }
   int best = -1, bdist = 256;
-  if (k1 != EMPTY_KEY && key_dist(k1) <= TH_HIGH) {
+  if (k1 != EMPTY_KEY && key_dist(k1) <= v.th_high) {
     bool ok = true;
     if (v.variant == 1) {
       // ratio test only when best and second best share the level  (src/ORBmatcher.cc:118-121)
@@ -753,7 +755,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_match_fused(MatchView v, FusedL
   for (int u = 0; u < FUSED_QPT; u++) bestkey[u] = EMPTY32;
   constexpr int need = VARIANT == 1 ? 2 : 1;
   auto decide = [&](unsigned k1, unsigned k2) -> unsigned {
-    if (k1 == EMPTY32 || (int)(k1 >> 16) > TH_HIGH) return EMPTY32;
+    if (k1 == EMPTY32 || (int)(k1 >> 16) > v.th_high) return EMPTY32;
     if (VARIANT == 1) {  // ratio test only when best and second best share the level  (src/ORBmatcher.cc:118-121)
       const int d2 = k2 != EMPTY32 ? (int)(k2 >> 16) : 256;
       const int l1 = (hdr_w[4 * (k1 & 0xFFFFu) + 3] >> 1) & 7;
@@ -1050,6 +1052,7 @@ static int sbp_frame_upload(LldCtx* c, const lld_sbp_frame_problem* p, MatchView
   v.variant = 0;
   set_geom(v, p->geom);
   v.th = p->th; v.nn_ratio = 0; v.mono = p->mono; v.check_ori = p->check_orientation;
+  v.th_high = p->th_high > 0 ? p->th_high : TH_HIGH; v.allow_neg_z = p->allow_negative_depth != 0;
   UPC(v.scale, float, p->geom.scale_factors, p->geom.n_levels);
   UPC(v.cur_off, int, p->cur_off, p->n_pairs + 1);
   UPC(v.cur_xy, float, p->cur_xy, 2 * (size_t)v.n_cur);
@@ -1083,6 +1086,7 @@ static int sbp_mp_upload(LldCtx* c, const lld_sbp_mp_problem* p, MatchView& v) {
   v.variant = 1;
   set_geom(v, p->geom);
   v.th = p->th; v.nn_ratio = p->nn_ratio; v.mono = 0; v.check_ori = 0;
+  v.th_high = TH_HIGH; v.allow_neg_z = 0;
   UPC(v.scale, float, p->geom.scale_factors, p->geom.n_levels);
   UPC(v.cur_off, int, p->cur_off, p->n_pairs + 1);
   UPC(v.cur_xy, float, p->cur_xy, 2 * (size_t)v.n_cur);

@@ -11,7 +11,8 @@
 //   lld::Optimizer::GlobalBundleAdjustemnt  <- src/Optimizer.cc:312-319     (sic, the reference's spelling)
 //   lld::Optimizer::PoseOptimization        <- src/Optimizer.cc:653-932
 //   lld::LineOptimizer                      <- include/LineOptimizer.h:11-33, src/LineOptimizer.cc:28-201
-//   lld::ORBmatcher::SearchByProjection     <- src/ORBmatcher.cc:1328-1470 (frame to frame) and :45-129 (frame to map points)
+//   lld::ORBmatcher::SearchByProjection     <- src/ORBmatcher.cc:1328-1470 (frame to frame), :45-129 (frame to map points) and
+//                                              :1472-1599 (frame to keyframe, relocalisation)
 //   lld::TwoFrameLineMatcher::MatchLines    <- src/TwoFrameLineMatcher.cc:26-77
 // Every entry point takes the library context as an extra first argument (the reference keeps its g2o optimizer on the
 // stack instead); Flatten* expose the flattened problem so that tests can compare it array by array with a reference
@@ -22,6 +23,7 @@
 #include <cstdint>
 #include <cstring>
 #include <map>
+#include <set>
 #include <utility>
 #include <vector>
 
@@ -43,6 +45,7 @@ struct KeyFrame {
   std::vector<int> line_matches;
   bool bad = false;
   bool isBad() const { return bad; }
+  std::vector<struct MapPoint*> mvpMapPoints;   // GetMapPointMatches()
   // GBA shadow fields (src/Optimizer.cc:509-512)
   float mTcwGBA[12];
   unsigned long mnBAGlobalForKF = 0;
@@ -61,6 +64,17 @@ struct MapPoint {
   float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, mTrackViewCos = 0;
   int mnTrackScaleLevel = 0;
   uint8_t mDescriptor[32] = {0};                     // GetDescriptor()
+  float mfMinDistance = 0, mfMaxDistance = 0;        // scale-invariance range (src/MapPoint.cc:373-383)
+  float GetMinDistanceInvariance() const { return 0.8f * mfMinDistance; }
+  float GetMaxDistanceInvariance() const { return 1.2f * mfMaxDistance; }
+  // int MapPoint::PredictScale(const float&, Frame*)  src/MapPoint.cc:402-417
+  int PredictScale(float currentDist, float mfLogScaleFactor, int mnScaleLevels) const {
+    const float ratio = mfMaxDistance / currentDist;
+    int nScale = (int)std::ceil(std::log(ratio) / mfLogScaleFactor);
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= mnScaleLevels) nScale = mnScaleLevels - 1;
+    return nScale;
+  }
 };
 struct MapLine {
   unsigned long mnId = 0;
@@ -83,6 +97,8 @@ struct Frame {
   float fx, fy, cx, cy, mbf, mb;
   float mnMinX, mnMaxX, mnMinY, mnMaxY;
   std::vector<float> mvScaleFactors, mvInvLevelSigma2;
+  float mfLogScaleFactor = 0;
+  int mnScaleLevels = 0;
   int N = 0;
   std::vector<KeyPoint> mvKeys, mvKeysUn;
   std::vector<float> mvuRight;
@@ -553,6 +569,62 @@ class ORBmatcher {
     for (int i = 0; i < Cur.N; i++)
       if (match[i] >= 0) Cur.mvpMapPoints[i] = Last.mvpMapPoints[match[i]];
     if (match_out) match_out->assign(match.begin(), match.end());
+    return nm;
+  }
+  // int SearchByProjection(Frame &CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*> &sAlreadyFound, const float th, const int ORBdist)
+  //   include/ORBmatcher.h:56, src/ORBmatcher.cc:1472-1599 (relocalisation).  The per-point tests that need the MapPoint object
+  //   (already found, scale-invariance range, PredictScale) run here; projection, window search, claims and the rotation
+  //   histogram run in lld_sbp_frame with the relocalisation parameters.
+  int SearchByProjection(void* ctx, Frame& Cur, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, float th, int ORBdist,
+                         std::vector<int>* match_out = nullptr) {
+    lld_sbp_frame_problem p;
+    std::memset(&p, 0, sizeof(p));
+    p.n_pairs = 1;
+    p.geom.fx = Cur.fx; p.geom.fy = Cur.fy; p.geom.cx = Cur.cx; p.geom.cy = Cur.cy; p.geom.bf = Cur.mbf; p.geom.b = Cur.mb;
+    p.geom.min_x = Cur.mnMinX; p.geom.max_x = Cur.mnMaxX; p.geom.min_y = Cur.mnMinY; p.geom.max_y = Cur.mnMaxY;
+    p.geom.n_levels = (int)Cur.mvScaleFactors.size(); p.geom.scale_factors = Cur.mvScaleFactors.data();
+    p.th = th; p.mono = 1; p.check_orientation = mbCheckOrientation;
+    p.th_high = ORBdist; p.allow_negative_depth = 1;
+    // Ow = -Rcw^T tcw: cv::Mat float product (double accumulation, one rounding)  :1476-1478
+    float Ow[3];
+    for (int i = 0; i < 3; i++)
+      Ow[i] = (float)(-((double)Cur.mTcw[i] * (double)Cur.mTcw[9] + (double)Cur.mTcw[3 + i] * (double)Cur.mTcw[10] + (double)Cur.mTcw[6 + i] * (double)Cur.mTcw[11]));
+    const std::vector<MapPoint*>& vpMPs = pKF->mvpMapPoints;
+    const int nq = (int)vpMPs.size();
+    std::vector<float> cxy, cang, cur(Cur.N > 0 ? Cur.N : 1, -1.0f), lxw(3 * (size_t)nq, 0.f), lang((size_t)nq, 0.f);
+    std::vector<uint8_t> coct, cclaimed, lvalid((size_t)nq, 0), loct((size_t)nq, 0), lhas((size_t)nq, 1), ldesc(32 * (size_t)nq, 0);
+    for (int i = 0; i < Cur.N; i++) {
+      cxy.push_back(Cur.mvKeysUn[i].x); cxy.push_back(Cur.mvKeysUn[i].y);
+      coct.push_back((uint8_t)Cur.mvKeysUn[i].octave); cang.push_back(Cur.mvKeysUn[i].angle);
+      cclaimed.push_back(Cur.mvpMapPoints[i] != nullptr);                    // :1534
+    }
+    for (int i = 0; i < nq; i++) {
+      MapPoint* mp = vpMPs[(size_t)i];
+      if (!mp || mp->isBad() || sAlreadyFound.count(mp)) continue;           // :1490-1493
+      const float PO[3] = {mp->pos[0] - Ow[0], mp->pos[1] - Ow[1], mp->pos[2] - Ow[2]};
+      const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);   // cv::norm :1512
+      if (dist3D < mp->GetMinDistanceInvariance() || dist3D > mp->GetMaxDistanceInvariance()) continue;              // :1518
+      lvalid[(size_t)i] = 1;
+      loct[(size_t)i] = (uint8_t)mp->PredictScale(dist3D, Cur.mfLogScaleFactor, Cur.mnScaleLevels);                   // :1521
+      for (int c = 0; c < 3; c++) lxw[3 * (size_t)i + c] = mp->pos[c];
+      lang[(size_t)i] = pKF->mvKeysUn[(size_t)i].angle;
+      std::memcpy(&ldesc[32 * (size_t)i], mp->mDescriptor, 32);
+    }
+    const int32_t co[2] = {0, Cur.N}, lo[2] = {0, nq};
+    p.cur_off = co; p.cur_xy = cxy.data(); p.cur_octave = coct.data(); p.cur_angle = cang.data(); p.cur_uright = cur.data();
+    p.cur_desc = Cur.mDescriptors.data(); p.cur_claimed = cclaimed.data(); p.cur_Tcw = Cur.mTcw; p.last_Tcw = Cur.mTcw;
+    p.last_off = lo; p.last_valid = lvalid.data(); p.last_xw = lxw.data(); p.last_octave = loct.data(); p.last_angle = lang.data();
+    p.last_desc = ldesc.data(); p.last_has_obs = lhas.data();
+    std::vector<int32_t> match((size_t)Cur.N + 1, -1);
+    int32_t nm = 0;
+    lld_sbp_result r;
+    std::memset(&r, 0, sizeof(r));
+    r.match = match.data(); r.n_matches = &nm;
+    const int rc = lld_sbp_frame(ctx, &p, &r);
+    if (rc) return rc;
+    for (int i = 0; i < Cur.N; i++)
+      if (match[(size_t)i] >= 0) Cur.mvpMapPoints[i] = vpMPs[(size_t)match[(size_t)i]];
+    if (match_out) match_out->assign(match.begin(), match.begin() + Cur.N);
     return nm;
   }
   // int SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, const float th = 3)   include/ORBmatcher.h:47

@@ -661,3 +661,71 @@ def batch_stereo(frames):
         n_levels=n_levels, scale_factors=f0["scale"], inv_scale_factors=f0["inv"],
         pyr=pyr, pyr_bytes=int(pyr.size), pyr_off=np.array(offs, np.int64), pyr_rows=rows, pyr_cols=cols, pyr_stride=stride,
         mb=float(f0["mb"]), mbf=float(f0["mbf"]), frames=frames)
+
+
+# ---------------------------------------------------------------------------------------------
+# temporal line association (Tracking::AddLinesFrom)
+# ---------------------------------------------------------------------------------------------
+def make_line_assoc_batch(n_frames, n_ml, n_cur, desc_dim, seed, n_cand=12):
+    """Per frame: n_ml map lines in front of a stereo camera, n_cur current left lines (the projections of a subset of the
+    map lines with pixel noise, plus clutter), right lines for most of them, candidate lists that contain the true line
+    among random others, descriptors = map line descriptor + noise."""
+    rng = np.random.default_rng(seed)
+    K = np.array([[FX, 0, CX], [0, FY, CY], [0, 0, 1.0]])
+    b = float(np.float32(BF) / np.float32(FX))
+    out = dict(n_frames=n_frames, desc_dim=desc_dim, K=K.reshape(-1), thr_reproj_base=3.0, md_thr=2.0, monocular=0)
+    ml_off, cur_off, right_off, cand_off = [0], [0], [0], [0]
+    ml_valid, ml_xd, ml_x12, ml_desc, cand_idx = [], [], [], [], []
+    cur_left, cur_oct, cur_lm, cur_taken, cur_desc, cur_right, Tc, Tr = [], [], [], [], [], [], [], []
+    for f in range(n_frames):
+        yaw = rng.normal(0, 0.05)
+        R = _rot_y(np.array(yaw))                        # camera-to-world
+        c = rng.normal(0, 0.3, 3)
+        T = np.eye(4); T[:3, :3] = R; T[:3, 3] = c
+        T2 = T.copy(); T2[:3, 3] = c + R @ np.array([b, 0, 0])
+        Tc.append(T.reshape(-1)); Tr.append(T2.reshape(-1))
+        X1c = np.stack([rng.uniform(-8, 8, n_ml), rng.uniform(-2, 2, n_ml), rng.uniform(4, 30, n_ml)], 1)
+        dirc = rng.normal(0, 1, (n_ml, 3)); dirc[:, 2] *= 0.3
+        dirc /= np.linalg.norm(dirc, axis=1, keepdims=True)
+        X2c = X1c + dirc * rng.uniform(1, 4, n_ml)[:, None]
+        X1 = (R @ X1c.T).T + c; X2 = (R @ X2c.T).T + c
+        d = (X2 - X1) / np.linalg.norm(X2 - X1, axis=1, keepdims=True)
+        X0 = X1 - (X1 * d).sum(1, keepdims=True) * d
+        desc = rng.normal(0, 1, (n_ml, desc_dim)); desc /= np.linalg.norm(desc, axis=1, keepdims=True)
+
+        def proj(Xc):
+            x = (K @ Xc.T).T
+            return x[:, :2] / x[:, 2:3]
+        owner = rng.permutation(n_ml)[:n_cur] if n_cur <= n_ml else rng.integers(0, n_ml, n_cur)
+        noise = lambda: rng.normal(0, 0.6, (n_cur, 2))   # noqa: E731
+        s, e = proj(X1c[owner]) + noise(), proj(X2c[owner]) + noise()
+        clutter = rng.random(n_cur) < 0.25
+        s[clutter] += rng.uniform(-60, 60, (int(clutter.sum()), 2))
+        left = np.concatenate([s, e], 1)
+        shift = np.array([b, 0, 0])
+        sr, er = proj(X1c[owner] - shift) + noise(), proj(X2c[owner] - shift) + noise()
+        has_r = rng.random(n_cur) < 0.85
+        lm = np.full(n_cur, -1, np.int64); lm[has_r] = np.arange(int(has_r.sum()))
+        right = np.concatenate([sr, er], 1)[has_r]
+        cdesc = desc[owner] + rng.normal(0, 0.05, (n_cur, desc_dim))
+        cdesc[clutter] = rng.normal(0, 1, (int(clutter.sum()), desc_dim))
+        inv = {int(o): i for i, o in enumerate(owner)}
+        for i in range(n_ml):
+            cs = list(rng.integers(0, n_cur, n_cand))
+            if i in inv and rng.random() < 0.9:
+                cs[int(rng.integers(0, n_cand))] = inv[i]
+            cand_idx += cs
+            cand_off.append(len(cand_idx))
+        ml_valid.append((rng.random(n_ml) < 0.9).astype(np.uint8)); ml_xd.append(np.concatenate([X0, d], 1)); ml_x12.append(np.concatenate([X1, X2], 1))
+        ml_desc.append(desc); cur_left.append(left); cur_oct.append(rng.integers(0, 3, n_cur)); cur_lm.append(lm)
+        cur_taken.append((rng.random(n_cur) < 0.1).astype(np.uint8)); cur_desc.append(cdesc); cur_right.append(right)
+        ml_off.append(ml_off[-1] + n_ml); cur_off.append(cur_off[-1] + n_cur); right_off.append(right_off[-1] + len(right))
+    out.update(ml_off=np.array(ml_off, np.int32), ml_valid=np.concatenate(ml_valid), ml_x0_dir=np.ascontiguousarray(np.concatenate(ml_xd)),
+               ml_x1x2=np.ascontiguousarray(np.concatenate(ml_x12)), ml_desc=np.ascontiguousarray(np.concatenate(ml_desc), np.float32),
+               cand_off=np.array(cand_off, np.int32), cand_idx=np.array(cand_idx, np.int32), cur_off=np.array(cur_off, np.int32),
+               cur_left=np.ascontiguousarray(np.concatenate(cur_left), np.float32), cur_octave=np.concatenate(cur_oct).astype(np.int32),
+               cur_line_match=np.concatenate(cur_lm).astype(np.int32), cur_taken=np.concatenate(cur_taken),
+               cur_desc=np.ascontiguousarray(np.concatenate(cur_desc), np.float32), right_off=np.array(right_off, np.int32),
+               cur_right=np.ascontiguousarray(np.concatenate(cur_right), np.float32).reshape(-1, 4),
+               T_curr=np.ascontiguousarray(np.stack(Tc)), T_right=np.ascontiguousarray(np.stack(Tr)))
+    return out

@@ -146,7 +146,7 @@ int lldo_sbp_frame(void*, const lld_sbp_frame_problem* p, lld_sbp_result* out) {
       const float yc = gemm_row(Tc + 3, Xw, Tc[10]);
       const float zc = gemm_row(Tc + 6, Xw, Tc[11]);
       const float invzc = 1.0 / zc;
-      if (invzc < 0) continue;
+      if (invzc < 0 && !p->allow_negative_depth) continue;   // the relocalisation variant (:1497-1502) has no such test
       float u = g.fx * xc * invzc + g.cx;
       float v = g.fy * yc * invzc + g.cy;
       if (u < g.min_x || u > g.max_x) continue;
@@ -169,7 +169,7 @@ int lldo_sbp_frame(void*, const lld_sbp_frame_problem* p, lld_sbp_result* out) {
         const int dist = descriptor_distance(dMP, p->cur_desc + 32 * (size_t)(c0 + i2));
         if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
       }
-      if (bestDist <= TH_HIGH) {
+      if (bestDist <= (p->th_high > 0 ? p->th_high : TH_HIGH)) {   // ORBdist in the relocalisation variant (:1547)
         match[bestIdx2] = i;
         if (p->last_has_obs[l0 + i]) claimed[bestIdx2] = 1;
         nmatches++;
@@ -400,3 +400,87 @@ int lldo_medoid_float(void*, int n_lm, const int32_t* off, int D, const float* d
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Temporal line association: Tracking::AddLinesFrom (src/Tracking.cc:996-1124) with the reprojection gate
+// GetReprojErrPixelsL1 -> vgl::LineReprojErrorL1 (src/LineMatching.cc:270-275, src/vgl.cc:548-559), vgl::MapPoint
+// (src/vgl.cc:587-590) and GetReprojThrPyramid (src/LineMatching.cc:239-247).  SURVEY §8(f) row 3.
+// The candidate lists (sub_inds of SubselectWithGrid over Frame::lines_grid) are an INPUT: the release never populates
+// lines_grid, so the caller decides which current lines a map line is compared with.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+inline void map_point_c2w(const double* T, const double* X, double* o) {   // T row-major 4x4: R^T (X - c)
+  const double d[3] = {X[0] - T[3], X[1] - T[7], X[2] - T[11]};
+  for (int i = 0; i < 3; i++) o[i] = T[0 * 4 + i] * d[0] + T[1 * 4 + i] * d[1] + T[2 * 4 + i] * d[2];
+}
+inline double line_reproj_err_l1(const float* seg, const double* T, const double* X0, const double* dir, const double* K) {
+  double Xa[3], Xb[3], P2[3] = {X0[0] + dir[0], X0[1] + dir[1], X0[2] + dir[2]};
+  map_point_c2w(T, X0, Xa);
+  map_point_c2w(T, P2, Xb);
+  double c1[3], c2[3];
+  for (int i = 0; i < 3; i++) {
+    c1[i] = K[3 * i] * Xa[0] + K[3 * i + 1] * Xa[1] + K[3 * i + 2] * Xa[2];
+    c2[i] = K[3 * i] * Xb[0] + K[3 * i + 1] * Xb[1] + K[3 * i + 2] * Xb[2];
+  }
+  double l[3] = {c1[1] * c2[2] - c1[2] * c2[1], c1[2] * c2[0] - c1[0] * c2[2], c1[0] * c2[1] - c1[1] * c2[0]};
+  const double n = std::sqrt(l[0] * l[0] + l[1] * l[1]);
+  l[0] /= n; l[1] /= n; l[2] /= n;
+  const double e1 = std::fabs((double)seg[0] * l[0] + (double)seg[1] * l[1] + l[2]);
+  const double e2 = std::fabs((double)seg[2] * l[0] + (double)seg[3] * l[1] + l[2]);
+  return e1 + e2;
+}
+}  // namespace
+
+extern "C" int lldo_line_associate(void*, const lld_line_assoc_problem* p, lld_line_assoc_result* out) {
+  const int D = p->desc_dim;
+  for (int f = 0; f < p->n_frames; f++) {
+    const int m0 = p->ml_off[f], m1 = p->ml_off[f + 1];
+    const int c0 = p->cur_off[f], nc = p->cur_off[f + 1] - c0;
+    const int r0 = p->right_off[f];
+    const double* Tc = p->T_curr + 16 * (size_t)f;
+    const double* Tr = p->T_right + 16 * (size_t)f;
+    std::vector<uint8_t> taken(p->cur_taken + c0, p->cur_taken + c0 + nc);
+    for (int i = 0; i < nc; i++) out->cur_assoc[c0 + i] = -1;
+    int added = 0;
+    for (int i = m0; i < m1; i++) {
+      if (!p->ml_valid[i]) continue;
+      const double* X0 = p->ml_x0_dir + 6 * (size_t)i;
+      const double* dir = X0 + 3;
+      double X1c[3], X2c[3];
+      map_point_c2w(Tc, p->ml_x1x2 + 6 * (size_t)i, X1c);
+      map_point_c2w(Tc, p->ml_x1x2 + 6 * (size_t)i + 3, X2c);
+      int match_id = -1;
+      double md = 1e10;
+      for (int q = p->cand_off[i]; q < p->cand_off[i + 1]; q++) {
+        const int si = p->cand_idx[q];
+        if (taken[si]) continue;
+        const int ri = p->cur_line_match[c0 + si];
+        if (ri < 0 && !p->monocular) continue;
+        if (X1c[2] < 0 || X2c[2] < 0) continue;
+        double thr = p->thr_reproj_base;
+        for (int l = 0; l < p->cur_octave[c0 + si]; l++) thr *= 1.44;
+        const double se = line_reproj_err_l1(p->cur_left + 4 * (size_t)(c0 + si), Tc, X0, dir, p->K);
+        double se2 = 0;
+        if (!p->monocular) se2 = line_reproj_err_l1(p->cur_right + 4 * (size_t)(r0 + ri), Tr, X0, dir, p->K);
+        if (se > thr || se2 > thr) continue;
+        const float* da = p->ml_desc + (size_t)D * i;
+        const float* db = p->cur_desc + (size_t)D * (c0 + si);
+        double ss = 0;
+        for (int k = 0; k < D; k++) {
+          const double df = (double)da[k] - (double)db[k];
+          ss += df * df;
+        }
+        const double cd = std::sqrt(ss);
+        if (cd < md) { md = cd; match_id = si; }
+      }
+      if (md > p->md_thr) continue;
+      if (match_id >= 0 && !taken[match_id]) {
+        taken[match_id] = 1;
+        out->cur_assoc[c0 + match_id] = i - m0;
+        added++;
+      }
+    }
+    if (out->n_added) out->n_added[f] = added;
+  }
+  return 0;
+}

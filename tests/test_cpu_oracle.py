@@ -522,3 +522,72 @@ def test_oracle_medoid_descriptors_against_numpy(built):
     got = api.medoid_float(off, desc, impl="oracle")
     assert np.array_equal(got, ref(off, desc, False))
     assert len(set(got.tolist())) > 3     # not everything collapses onto index 0
+
+
+# ------------------------------------------------------------------------------------------------
+# temporal line association (Tracking::AddLinesFrom)
+# ------------------------------------------------------------------------------------------------
+def _add_lines_from_numpy(p):
+    """transcription of src/Tracking.cc:996-1124 with vgl::LineReprojErrorL1 (src/vgl.cc:548-559) in numpy"""
+    K = np.asarray(p["K"], np.float64).reshape(3, 3)
+    out = np.full(int(p["cur_off"][-1]), -1, np.int32)
+    added = []
+
+    def map_point(T, X):
+        return T[:3, :3].T @ (X - T[:3, 3])
+
+    def err_l1(seg, T, X0, d):
+        Xc1 = K @ map_point(T, X0)
+        Xc2 = K @ map_point(T, X0 + d)
+        leq = np.cross(Xc1, Xc2)
+        leq = leq / np.linalg.norm(leq[:2])
+        return abs(np.dot(seg[:2].astype(np.float64), leq[:2]) + leq[2]) + abs(np.dot(seg[2:].astype(np.float64), leq[:2]) + leq[2])
+
+    for f in range(int(p["n_frames"])):
+        T = p["T_curr"][f].reshape(4, 4); Tr = p["T_right"][f].reshape(4, 4)
+        c0, r0 = int(p["cur_off"][f]), int(p["right_off"][f])
+        taken = p["cur_taken"][c0:int(p["cur_off"][f + 1])].astype(bool).copy()
+        n = 0
+        for i in range(int(p["ml_off"][f]), int(p["ml_off"][f + 1])):
+            if not p["ml_valid"][i]:
+                continue
+            X0, d = p["ml_x0_dir"][i, :3], p["ml_x0_dir"][i, 3:]
+            X1c, X2c = map_point(T, p["ml_x1x2"][i, :3]), map_point(T, p["ml_x1x2"][i, 3:])
+            match_id, md = -1, 1e10
+            for si in p["cand_idx"][int(p["cand_off"][i]):int(p["cand_off"][i + 1])]:
+                si = int(si)
+                if taken[si]:
+                    continue
+                ri = int(p["cur_line_match"][c0 + si])
+                if ri < 0 and not p["monocular"]:
+                    continue
+                if X1c[2] < 0 or X2c[2] < 0:
+                    continue
+                thr = float(p["thr_reproj_base"])
+                for _ in range(int(p["cur_octave"][c0 + si])):
+                    thr *= 1.44
+                se = err_l1(p["cur_left"][c0 + si], T, X0, d)
+                se2 = 0.0 if p["monocular"] else err_l1(p["cur_right"][r0 + ri], Tr, X0, d)
+                if se > thr or se2 > thr:
+                    continue
+                cd = float(np.linalg.norm(p["ml_desc"][i].astype(np.float64) - p["cur_desc"][c0 + si].astype(np.float64)))
+                if cd < md:
+                    md, match_id = cd, si
+            if md > p["md_thr"]:
+                continue
+            if match_id >= 0 and not taken[match_id]:
+                taken[match_id] = True
+                out[c0 + match_id] = i - int(p["ml_off"][f])
+                n += 1
+        added.append(n)
+    return out, np.array(added, np.int32)
+
+
+def test_oracle_line_association_against_numpy(built):
+    p = synth.make_line_assoc_batch(4, 150, 120, 32, 3)
+    o = api.line_associate(p, impl="oracle")
+    ref, added = _add_lines_from_numpy(p)
+    assert np.array_equal(o["cur_assoc"], ref) and np.array_equal(o["n_added"], added)
+    assert added.min() > 20
+    # the true map line is what gets associated for the unambiguous (non-clutter) lines
+    assert (ref >= 0).sum() > 100

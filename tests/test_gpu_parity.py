@@ -532,3 +532,38 @@ def test_medoid_descriptors(gpu_ctx):
     off = np.array([0, 0, 200, 201, 201 + 255], np.int32)
     desc = np.random.default_rng(5).integers(0, 256, (int(off[-1]), 32), dtype=np.uint8)
     assert np.array_equal(api.medoid_orb(off, desc, impl="gpu", ctx=gpu_ctx), api.medoid_orb(off, desc, impl="oracle"))
+
+
+def test_sbp_relocalisation_variant(gpu_ctx):
+    """SURVEY §8(f) row 2, ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1472-1599):
+    the frame-to-frame search with levels [l-1, l+1] around a predicted level, no stereo test, every match claiming its
+    keypoint, acceptance at ORBdist and no negative-depth rejection; bit-exact against the oracle on 64 pairs"""
+    p = synth.make_sbp_frame_batch(64, 1500, 777, th=10.0)
+    p["mono"] = 1
+    p["cur_uright"] = np.full_like(p["cur_uright"], -1.0)
+    p["last_has_obs"] = np.ones_like(p["last_has_obs"])
+    rng = np.random.default_rng(9)
+    p["last_valid"] = (rng.random(len(p["last_valid"])) < 0.8).astype(np.uint8)       # sAlreadyFound / distance range rejections
+    for th_high in (18, 100):   # matched descriptors differ by ~20 bits: 18 rejects about half of them
+        p["th_high"] = th_high
+        p["allow_negative_depth"] = 1
+        g = api.sbp_frame(p, impl="gpu", ctx=gpu_ctx)
+        o = api.sbp_frame(p, impl="oracle")
+        for k in ("match", "n_matches", "best_idx", "best_dist"):
+            assert np.array_equal(g[k], o[k]), (k, th_high)
+        assert o["best_dist"][o["best_idx"] >= 0].max() <= th_high
+    assert int(o["n_matches"].sum()) > 1000
+
+
+def test_temporal_line_association(gpu_ctx):
+    """SURVEY §8(f) row 3, Tracking::AddLinesFrom: reprojection gates in both images, descriptor argmin with first-wins ties,
+    sequential claims; index-exact against the oracle, ragged frames, more candidates than lanes"""
+    p = synth.make_line_assoc_batch(32, 300, 250, 64, 21, n_cand=40)
+    g = api.line_associate(p, impl="gpu", ctx=gpu_ctx)
+    o = api.line_associate(p, impl="oracle")
+    assert np.array_equal(g["cur_assoc"], o["cur_assoc"]) and np.array_equal(g["n_added"], o["n_added"])
+    assert o["n_added"].min() > 50
+    p = synth.make_line_assoc_batch(3, 20, 15, 32, 22, n_cand=3)
+    g = api.line_associate(p, impl="gpu", ctx=gpu_ctx)
+    o = api.line_associate(p, impl="oracle")
+    assert np.array_equal(g["cur_assoc"], o["cur_assoc"]) and np.array_equal(g["n_added"], o["n_added"])

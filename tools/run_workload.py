@@ -31,6 +31,7 @@ elif a.workload == "match":
     m = synth.make_sbp_frame_batch(a.pairs, 2000, 3)
     geom, gk = capi.make_geom(m["geom"])
     f = dict(m); f["geom"] = geom
+    f.setdefault("th_high", 0); f.setdefault("allow_negative_depth", 0)
     prob, keep = capi.fill_struct(capi.SbpFrameProblem, f)
     ctx.check(d.lld_sbp_frame_upload(ctx.handle, C.byref(prob)), "upload")
     n = C.c_int()
