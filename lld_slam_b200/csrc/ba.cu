@@ -35,6 +35,7 @@ static const int CHUNK = 256;          // edge-list entries per chunk (k_lin_pos
 static const int SMEM_SOLVE_MAX_N = 156;  // dense LDL^T in shared memory up to this dimension (26 free KFs)
 
 void lld_ba_state_free(struct BaState* s);
+static cudaError_t ba_set_carveout(int device);
 
 struct BaState {
   BaView v{};
@@ -1147,6 +1148,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   DEV(v.S_blk, double, 36 * nb_g.size() + 6 * (size_t)nG);
   v.g_bs = v.S_blk + 36 * nb_g.size(); DEV(v.g_x, double, 6 * (size_t)nG);
   DEV(v.pt_D, double, 9 * (size_t)n_pt); DEV(v.ln_D, double, 14 * (size_t)n_ln);
+  DEV(v.pt_xl, double, 3 * (size_t)n_pt); DEV(v.ln_xl, double, 4 * (size_t)n_ln);
   DEV(v.lm_chi2, double, n_pt + n_ln); DEV(v.lm_scale, double, n_pt + n_ln);
   DEV(v.w_phase, int, nw); DEV(v.w_sel, int, nw); DEV(v.w_iter, int, nw); DEV(v.w_trials, int, nw);
   DEV(v.w_maxit, int, nw); DEV(v.w_nbad, int, nw); DEV(v.w_ok, int, nw); DEV(v.w_nlog, int, nw);
@@ -1220,6 +1222,7 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   }
   // dynamic shared memory opt-in of the solvers (once per upload, outside any stream capture)
   if (v.dense_mode) {
+    LLD_CUDA(c, ba_set_carveout(c->device));
     LLD_CUDA(c, lld_raise_dyn_smem(k_fused<3>, (size_t)FU_SMEM_BYTES));
     LLD_CUDA(c, lld_raise_dyn_smem(k_fused<4>, (size_t)FU_SMEM_BYTES));
     LLD_CUDA(c, lld_raise_dyn_smem(k_schur_tile<3>, (size_t)SP_SMEM_BYTES));
@@ -1238,6 +1241,38 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// The shared-memory carve-out is a per-SM setting that only changes on an idle SM, so kernels with different preferences
+// cannot share an SM: the point / line / pose passes that the dense LM step forks onto three streams would run one after
+// the other behind k_schur_tile (4 x 56 KB) and k_solve (> 100 KB).  LLD_BA_CARVEOUT=1 makes every kernel of the step ask
+// for the maximal shared-memory split so that they can co-reside.  Measured on B200 (cfg1, 64 windows): 20.0 ms per
+// step with the common split against 16.1 ms with the driver's per-kernel choice -- the linearisation and back-substitution
+// passes lose more from the smaller L1 than the step gains from overlap -- so the default leaves the driver's choice.
+template <typename F>
+static cudaError_t carve_max(F* f) {
+  return cudaFuncSetAttribute(reinterpret_cast<const void*>(f), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+static cudaError_t ba_set_carveout(int device) {
+  static std::mutex mu;
+  static std::vector<int> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (std::find(done.begin(), done.end(), device) != done.end()) return cudaSuccess;
+  const char* e = getenv("LLD_BA_CARVEOUT");
+  if (!e || e[0] != '1') { done.push_back(device); return cudaSuccess; }
+  cudaError_t r = cudaSuccess;
+#define CARVE(k) if (r == cudaSuccess) r = carve_max(k)
+  CARVE((k_lin_points<1, false>)); CARVE((k_lin_points<4, false>)); CARVE((k_lin_points<1, true>)); CARVE((k_lin_points<4, true>));
+  CARVE((k_lin_lines<1, false>)); CARVE((k_lin_lines<2, false>)); CARVE((k_lin_lines<4, false>)); CARVE((k_lin_lines<8, false>));
+  CARVE((k_lin_lines<1, true>)); CARVE((k_lin_lines<2, true>)); CARVE((k_lin_lines<4, true>)); CARVE((k_lin_lines<8, true>));
+  CARVE(k_lin_poses); CARVE(k_pose_sum); CARVE(k_begin_fused); CARVE(k_schur_points); CARVE(k_schur_lines);
+  CARVE(k_schur_tile<3>); CARVE(k_schur_tile<4>); CARVE(k_reduce_piece); CARVE(k_reduce_piece_warp); CARVE(k_solve<true>);
+  CARVE(k_backsub_points<1>); CARVE(k_backsub_points<4>);
+  CARVE(k_backsub_lines<1>); CARVE(k_backsub_lines<2>); CARVE(k_backsub_lines<4>); CARVE(k_backsub_lines<8>);
+  CARVE(k_decide_fused); CARVE(k_decide_carry);
+#undef CARVE
+  if (r == cudaSuccess) done.push_back(device);
+  return r;
+}
 
 static int ba_init_state(LldCtx* c) {
   BaState* S = c->ba;

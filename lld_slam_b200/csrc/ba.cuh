@@ -140,6 +140,8 @@ struct BaView {
   double* S_blk;  // [n_nb_total][36]
   double* g_bs;   // [n_free_total][6] bschur
   double* g_x;    // [n_free_total][6] pose solution (kept on failure)
+  double* pt_xl;  // [n_pt][3] landmark solution of the last successful solve (applied again when a solve fails, as g2o does)
+  double* ln_xl;  // [n_ln][4]
   double* pt_D;   // [n_pt][9]  (Hll+lambda I)^-1 packed (6) + D^-1 b_l (3)
   double* ln_D;   // [n_ln][14] inverse packed (10) + D^-1 b_l (4)
   double* lm_chi2;

@@ -99,6 +99,10 @@ __global__ void k_init_state(BaView v, const double* __restrict__ kf_Tcw, const 
   }
   if (i < v.n_free_total)
     for (int k = 0; k < 6; k++) v.g_x[6 * (size_t)i + k] = 0.0;
+  if (i < v.n_pt)
+    for (int k = 0; k < 3; k++) v.pt_xl[3 * (size_t)i + k] = 0.0;
+  if (i < v.n_ln)
+    for (int k = 0; k < 4; k++) v.ln_xl[4 * (size_t)i + k] = 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2256,11 +2260,20 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_points(BaView v) {
 #pragma unroll
     for (int k = 0; k < 3; k++) s3[k] += __shfl_xor_sync(0xffffffffu, s3[k], o);
   // xl = Dinv (bl - W^T xp) = c - Dinv (W^T xp)
+  // A failed linear solve leaves the solver's x untouched and the reference still applies it (update(_solver->x()) and
+  // computeScale() run before the failure is looked at, optimization_algorithm_levenberg.cpp:112-131): the landmark
+  // keeps the update of its last successful solve (zero before the first one).
   double xl[3] = {0, 0, 0};
+  double* xs = v.pt_xl + 3 * (size_t)p;
   if (active) {
-    xl[0] = Dp[6] - (Dp[0] * s3[0] + Dp[1] * s3[1] + Dp[2] * s3[2]);
-    xl[1] = Dp[7] - (Dp[1] * s3[0] + Dp[3] * s3[1] + Dp[4] * s3[2]);
-    xl[2] = Dp[8] - (Dp[2] * s3[0] + Dp[4] * s3[1] + Dp[5] * s3[2]);
+    if (v.w_ok[w]) {
+      xl[0] = Dp[6] - (Dp[0] * s3[0] + Dp[1] * s3[1] + Dp[2] * s3[2]);
+      xl[1] = Dp[7] - (Dp[1] * s3[0] + Dp[3] * s3[1] + Dp[4] * s3[2]);
+      xl[2] = Dp[8] - (Dp[2] * s3[0] + Dp[4] * s3[1] + Dp[5] * s3[2]);
+      if (run && gl == 0) { xs[0] = xl[0]; xs[1] = xl[1]; xs[2] = xl[2]; }
+    } else {
+      xl[0] = xs[0]; xl[1] = xs[1]; xl[2] = xs[2];
+    }
   }
   const double X[3] = {Xo[0] + xl[0], Xo[1] + xl[1], Xo[2] + xl[2]};
   double chi = 0;
@@ -2380,12 +2393,18 @@ __global__ void __launch_bounds__(LM_TPB) k_backsub_lines(BaView v) {
   double xl[4] = {0, 0, 0, 0};
   double st[5] = {so[0], so[1], so[2], so[3], so[4]};
   if (active) {
+    double* xs = v.ln_xl + 4 * (size_t)lc;
+    if (v.w_ok[w]) {
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-      double zz = 0;
+      for (int r = 0; r < 4; r++) {
+        double zz = 0;
 #pragma unroll
-      for (int k = 0; k < 4; k++) zz += Dp[r <= k ? u4(r, k) : u4(k, r)] * s4[k];
-      xl[r] = Dp[10 + r] - zz;
+        for (int k = 0; k < 4; k++) zz += Dp[r <= k ? u4(r, k) : u4(k, r)] * s4[k];
+        xl[r] = Dp[10 + r] - zz;
+      }
+      if (run && gl == 0) { xs[0] = xl[0]; xs[1] = xl[1]; xs[2] = xl[2]; xs[3] = xl[3]; }
+    } else {   // failed linear solve: the stale update is applied, as in the reference (see k_backsub_points)
+      xl[0] = xs[0]; xl[1] = xs[1]; xl[2] = xs[2]; xl[3] = xs[3];
     }
     const double st0[5] = {so[0], so[1], so[2], so[3], so[4]};
     line_oplus(st0, xl, st);

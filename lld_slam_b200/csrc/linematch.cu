@@ -795,6 +795,17 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
     UPM(d_taken_bits, uint32_t, nullptr, (size_t)P * (TC_COLS / 32));
     const size_t smem = (size_t)(TC_ROWS + TC_HALF) * v.D * 8 + TC_COLS * 16 + TC_COLS + 16 + 64;
     if (!ttp.empty()) LLD_CUDA(c, lld_raise_dyn_smem(k_line_tc, (size_t)(int)smem));
+    {
+      // k_line_tc needs the SM's maximal shared-memory carve-out; a kernel that prefers another split of L1 / shared
+      // memory cannot share an SM with it (the carve-out is per SM and only changes on an idle SM).  Ask for the same
+      // split for the kernels that are meant to run beside it.
+      static int carve_dev = -1;
+      if (carve_dev != c->device) {
+        LLD_CUDA(c, cudaFuncSetAttribute(k_line_greedy_lazy, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        LLD_CUDA(c, cudaFuncSetAttribute(k_line_exact, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        carve_dev = c->device;
+      }
+    }
     const bool stats = getenv("LLD_LINE_STATS") != nullptr;
     cudaStream_t s0 = c->stream, s1 = (c->prof_on || stats) ? c->stream : c->side[0];
     if (s1 != s0) {   // the side stream starts after everything enqueued so far (uploads, prep, memsets)

@@ -567,3 +567,49 @@ def test_temporal_line_association(gpu_ctx):
     g = api.line_associate(p, impl="gpu", ctx=gpu_ctx)
     o = api.line_associate(p, impl="oracle")
     assert np.array_equal(g["cur_assoc"], o["cur_assoc"]) and np.array_equal(g["n_added"], o["n_added"])
+
+
+def test_solver_failure_rejects_the_step(gpu_ctx):
+    """LinearSolver failure => tempChi = DBL_MAX => the trial is rejected, lambda grows, ten trials, Terminate
+    (optimization_algorithm_levenberg.cpp:118-161; linear_solver_eigen.h:94-124).  A window whose edges all carry zero
+    information has H = 0 and lambda_0 = 0: the landmark blocks are singular, the reduced system is not finite, every
+    factorisation fails.  The neighbouring window of the batch must be unaffected."""
+    p = synth.make_local_ba_batch(2, 6, 200, 40, 101)
+    a, b = int(p["pt_obs_off"][p["pt_off"][1]]), int(p["pt_obs_off"][-1])
+    p["pt_obs_info"] = p["pt_obs_info"].copy(); p["pt_obs_info"][a:b] = 0
+    c, d = int(p["ln_obs_off"][p["ln_off"][1]]), int(p["ln_obs_off"][-1])
+    p["ln_obs_info"] = p["ln_obs_info"].copy(); p["ln_obs_info"][c:d] = 0
+    g = api.ba_local(p, 5, 15, impl="gpu", ctx=gpu_ctx)
+    o = api.ba_local(p, 5, 15, impl="oracle")
+    assert o["n_iter_done"].tolist() == [[5, 15], [1, 1]] and o["trials_log"][1, :2].tolist() == [10, 10]
+    assert np.array_equal(g["n_iter_done"], o["n_iter_done"]) and np.array_equal(g["trials_log"], o["trials_log"])
+    assert np.all(np.isfinite(g["kf_Tcw"])) and np.all(np.isfinite(g["pt_xyz"])) and np.all(np.isfinite(g["ln_x0_dir"]))
+    assert np.abs(g["kf_Tcw"] - o["kf_Tcw"]).max() <= POS_TOL            # window 0 optimised, window 1 untouched
+    assert np.abs(g["pt_xyz"][int(p["pt_off"][1]):] - p["pt_xyz"][int(p["pt_off"][1]):]).max() == 0
+    rel = np.abs(g["chi2_log"][0] - o["chi2_log"][0]) / np.maximum(np.abs(o["chi2_log"][0]), 1e-9)
+    assert rel.max() <= CHI2_RTOL
+
+
+def test_line_update_outside_the_unit_ball_is_rejected(gpu_ctx):
+    """VertexSBALine::oplusImpl takes sqrt(1 - |delta|^2) (types_sba.h:97-108): a rotation update longer than 1 gives NaN, the
+    trial's chi2 is not finite and Levenberg rejects it.  Lines whose direction starts 75 degrees off provoke such steps;
+    the LM trace (including the rejected trials) must match the oracle."""
+    hit = 0
+    for seed in range(6):
+        rng = np.random.default_rng(seed)
+        p = synth.batch_ba([synth.make_ba_window(5, 0, 60, rng)], "local")
+        xd = p["ln_x0_dir"].copy()
+        for i in range(0, 60, 3):
+            d, x0 = xd[i, 3:], xd[i, :3]
+            n = np.cross(d, x0); n /= np.linalg.norm(n)
+            d2 = np.cos(1.3) * d + np.sin(1.3) * n
+            xd[i, 3:] = d2 / np.linalg.norm(d2)
+        p["ln_x0_dir"] = xd
+        g = api.ba_local(p, 5, 15, impl="gpu", ctx=gpu_ctx)
+        o = api.ba_local(p, 5, 15, impl="oracle")
+        assert np.array_equal(g["n_iter_done"], o["n_iter_done"]) and np.array_equal(g["trials_log"], o["trials_log"]), seed
+        assert np.all(np.isfinite(g["ln_x0_dir"]))
+        rel = np.abs(g["chi2_log"] - o["chi2_log"]) / np.maximum(np.abs(o["chi2_log"]), 1e-9)
+        assert rel.max() <= CHI2_RTOL, (seed, rel.max())
+        hit += int(o["trials_log"].max() > 1)
+    assert hit >= 1
