@@ -669,6 +669,488 @@ __global__ void __launch_bounds__(256) k_line_exact(LineTcView t, int n_left) {
   if (lane == 0) v.mdist[i] = d;
 }
 
+// ================================================================================================
+// Tensor-core path, second generation (default).  One persistent CTA per SM walks over stereo pairs; inside it the work
+// is split by warp role so that staging, tensor-core contraction and candidate selection of consecutive steps overlap:
+//   producers (4 warps) : split the descriptors into TF32 hi / lo parts while staging them into the canonical K-major
+//                         UMMA layout; one elected thread issues the 3xTF32 tcgen05.mma sequence of a step
+//   selectors (16 warps): read the finished accumulator from TMEM and compact the survivors of the cheap gates
+//   step = (chunk of NL left lines) x (block of 128 right lines); the accumulator is TRANSPOSED with respect to the first
+//   generation: TMEM lane = right line, TMEM column = left line.  A selector thread therefore owns one right line (its
+//   |b|^2, unit normal and octave live in registers), a warp looks at 32 consecutive right lines of ONE left line per
+//   step, and the survivors of that left line are appended with a ballot + one shared-memory atomic: the stores of a
+//   warp land in one or two 32 B sectors instead of 32 (the first generation spent most of its time in scattered
+//   4-byte stores).  Two accumulators (2 x 256 TMEM columns) are in flight.
+//   k_line_prep2  : per line |d|^2 and FP32 copies of the geometry the selection and the gates read
+//   k_line_tc2    : as above; candidate list per left line = (3xTF32 d^2, right line), any order
+//   k_line_gate32 : the remaining gates of CheckLinePair over the lists.  Decided in FP32 with a running error bound;
+//                   an entry closer to a threshold than the bound is decided by the FP64 formulas the FP32 tile path uses
+//                   (LLD_LINE_CHECK=1 evaluates both for every entry and fails the call on a disagreement)
+//   k_line_greedy2: one warp per pair, sequential over the left lines: smallest (d^2, right line) among the admissible
+//                   untaken entries -- two warp reductions per line
+//   k_line_exact2 : exact FP32 distance of each match
+// ================================================================================================
+constexpr int T2_M = 128;                 // right lines per block = TMEM lanes
+constexpr int T2_ROWS = 512;              // lines per side of a pair at most
+constexpr int T2_CAP = 256;               // candidate slots per left line
+constexpr int T2_SEL_WARPS = 16, T2_PROD_WARPS = 4;
+constexpr int T2_SEL = 32 * T2_SEL_WARPS, T2_PROD = 32 * T2_PROD_WARPS, T2_NT = T2_SEL + T2_PROD;
+
+struct LineTc2View {
+  LineMatchView v;
+  int nl_chunk;             // left lines per step (256, or 128 for wide descriptors)
+  float4* lrec;             // [n_left]  {|a|^2, unit plane normal}
+  float4* rrec;             // [n_right]
+  int8_t* loct;             // [n_left]  octave, -2 when the line is too short
+  int8_t* roct;             // [n_right] octave, -1 when the line is too short
+  float4* lleq;             // [n_left]  {K^T l normalised, 0}
+  float4* rleq;             // [n_right] {K^T l normalised, beta = l_x * baseline}
+  uint32_t* cand_d2;        // [n_left][T2_CAP]
+  uint16_t* cand_col;       // [n_left][T2_CAP]
+  uint16_t* cand_cnt;       // [n_left] listed candidates (> T2_CAP: overflow)
+  int* err_flag;            // 0: barrier time-out; 1: overflow rows; 2: listed; 3: admissible; 4: borderline (FP64); 5: FP32 / FP64 disagreements
+};
+
+// 8 lanes per line
+__global__ void __launch_bounds__(256) k_line_prep2(LineTc2View t, int n_left, int n_right) {
+  const LineMatchView& v = t.v;
+  const int gl = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
+  const int side = gl >= n_left;
+  const int i = side ? gl - n_left : gl;
+  const bool live = gl < n_left + n_right;   // (no early return: the shuffles below are full-warp)
+  float s2 = 0.f;
+  if (live) {
+    const float* g = (side ? v.right_desc : v.left_desc) + (size_t)i * v.D;
+    for (int k = 4 * sub; k < v.D; k += 32) {
+      const float4 x = *reinterpret_cast<const float4*>(g + k);
+      s2 = fmaf(x.x, x.x, s2); s2 = fmaf(x.y, x.y, s2); s2 = fmaf(x.z, x.z, s2); s2 = fmaf(x.w, x.w, s2);
+    }
+  }
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+  if (!live || sub) return;
+  const double* un = (side ? v.right_un : v.left_un) + 3 * (size_t)i;
+  const double* lq = (side ? v.right_leq : v.left_leq) + 3 * (size_t)i;
+  const bool too_short = (side ? v.right_len : v.left_len)[i] < (double)v.min_len;
+  const int oct = min(max((side ? v.right_oct : v.left_oct)[i], 0), 127);
+  const float4 rec = make_float4(s2, (float)un[0], (float)un[1], (float)un[2]);
+  if (side) {
+    t.rrec[i] = rec;
+    t.roct[i] = (int8_t)(too_short ? -1 : oct);
+    t.rleq[i] = make_float4((float)lq[0], (float)lq[1], (float)lq[2], (float)(lq[0] * v.baseline));
+  } else {
+    t.lrec[i] = rec;
+    t.loct[i] = (int8_t)(too_short ? -2 : oct);
+    t.lleq[i] = make_float4((float)lq[0], (float)lq[1], (float)lq[2], 0.f);
+  }
+}
+
+__device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+// stage `rows` descriptors as TF32 hi / lo parts (layout as stage_split); warp w of nw, two row groups in flight
+__device__ __forceinline__ void stage_split2(const float* __restrict__ g, int n_valid, int rows, int D, uint8_t* hi, uint8_t* lo,
+                                             int w, int nw, int lane) {
+  const int chunks = D >> 2, sbo = chunks * 128;
+  const int r_in = lane & 7, c_in = lane >> 3;
+  const int n_groups = rows >> 3;
+  constexpr int U = 5;  // chunks <= 18 -> at most 5 chunks per lane and row
+  for (int rg0 = w; rg0 < n_groups; rg0 += 2 * nw) {
+    float4 x[2][U];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int rg = rg0 + h * nw;
+      const int r = rg * 8 + r_in;
+      const bool rv = rg < n_groups && r < n_valid;
+      const float* grow = g + (size_t)r * D;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int kc = c_in + 4 * u;
+        x[h][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rv && kc < chunks) x[h][u] = __ldg(reinterpret_cast<const float4*>(grow + 4 * kc));
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int rg = rg0 + h * nw;
+      if (rg >= n_groups) continue;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int kc = c_in + 4 * u;
+        if (kc >= chunks) continue;
+        const float4 q = x[h][u];
+        uint4 hh, ll;
+        hh.x = to_tf32(q.x); hh.y = to_tf32(q.y); hh.z = to_tf32(q.z); hh.w = to_tf32(q.w);
+        ll.x = to_tf32(q.x - __uint_as_float(hh.x)); ll.y = to_tf32(q.y - __uint_as_float(hh.y));
+        ll.z = to_tf32(q.z - __uint_as_float(hh.z)); ll.w = to_tf32(q.w - __uint_as_float(hh.w));
+        const int off = rg * sbo + kc * 128 + r_in * 16;
+        *reinterpret_cast<uint4*>(hi + off) = hh;
+        *reinterpret_cast<uint4*>(lo + off) = ll;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(T2_NT, 1) k_line_tc2(LineTc2View t) {
+  extern __shared__ __align__(1024) uint8_t tsm[];
+  const LineMatchView& v = t.v;
+  const int D = v.D, NL = t.nl_chunk;
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const uint32_t l_bytes = (uint32_t)NL * D * 4, r_bytes = (uint32_t)T2_M * D * 4;
+  uint8_t* L_hi = tsm;
+  uint8_t* L_lo = L_hi + l_bytes;
+  uint8_t* R_hi = L_lo + l_bytes;
+  uint8_t* R_lo = R_hi + r_bytes;
+  float4* rowv = reinterpret_cast<float4*>(R_lo + r_bytes);      // [2][T2_ROWS] records of the pair's left lines
+  int* s_cnt = reinterpret_cast<int*>(rowv + 2 * T2_ROWS);       // [2][T2_ROWS] list lengths
+  int8_t* rowm = reinterpret_cast<int8_t*>(s_cnt + 2 * T2_ROWS); // [2][T2_ROWS] octaves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rowm + 2 * T2_ROWS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  // a barrier that never completes is reported instead of hanging the device: the role that timed out raises its flag,
+  // keeps walking through its named barriers without waiting any more, and leaves at the next point where all of its
+  // threads agree on the flag; the other role runs into its own time-outs in turn
+  volatile int* dead_prod = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  volatile int* dead_sel = dead_prod + 1;
+  const uint32_t bar_mma = smem_u32(bars), bar_free = smem_u32(bars + 2), bar_row = smem_u32(bars + 4);
+
+  if (wid == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    for (int b = 0; b < 2; b++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_mma + 8 * b), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_free + 8 * b), "r"(T2_SEL));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_row + 8 * b), "r"(T2_PROD));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::);
+  }
+  for (int j = tid; j < 2 * T2_ROWS; j += T2_NT) s_cnt[j] = 0;
+  if (tid == 0) { *dead_prod = 0; *dead_sel = 0; }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::);
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t sbo = (uint32_t)(D >> 2) * 128u;
+  // instruction descriptor: D fp32, A / B TF32, both K-major, N = NL, M = 128
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NL >> 3) << 17) | ((uint32_t)(T2_M >> 4) << 24);
+  auto wait_or_flag = [&](uint32_t bar, uint32_t parity, volatile int* flag) {
+    if (*flag) return;
+    if (!mbar_wait(bar, parity)) *flag = 1;
+  };
+
+  if (wid >= T2_SEL_WARPS) {
+    // ------------------------------------------------------------------ producers
+    const int pw = wid - T2_SEL_WARPS, ptid = tid - T2_SEL;
+    uint32_t it = 0, freed = 0;     // steps issued; accumulator releases consumed by the issuing thread (in order)
+    int end1 = -1, end2 = -1;       // last step of the previous pair / of the pair before it
+    int pp = 0;
+    auto consume_free = [&](int upto) {   // issuing thread only
+      while ((int)freed <= upto) {
+        wait_or_flag(bar_free + 8 * (freed & 1), (freed >> 1) & 1, dead_prod);
+        freed++;
+      }
+    };
+    bool out = false;
+    for (int p = blockIdx.x; p < v.n_pairs && !out; p += gridDim.x) {
+      const int a0 = v.left_off[p], na = v.left_off[p + 1] - a0;
+      const int b0 = v.right_off[p], nb = v.right_off[p + 1] - b0;
+      if (na == 0 || nb == 0) continue;
+      // the selectors must be through with the pair that used this half of the row tables
+      if (ptid == 0) consume_free(end2);
+      named_bar(1, T2_PROD);
+      if (*dead_prod) break;
+      for (int j = ptid; j < T2_ROWS; j += T2_PROD) {
+        rowv[pp * T2_ROWS + j] = j < na ? t.lrec[a0 + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        rowm[pp * T2_ROWS + j] = j < na ? t.loct[a0 + j] : (int8_t)-2;
+      }
+      mbar_arrive(bar_row + 8 * pp);
+      const int n_lc = (na + NL - 1) / NL, n_m = (nb + T2_M - 1) / T2_M;
+      for (int lc = 0; lc < n_lc && !out; lc++)
+        for (int m = 0; m < n_m; m++) {
+          // the MMAs of the previous step have read the R (and L) buffers
+          if (it >= 1) wait_or_flag(bar_mma + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1, dead_prod);
+          if (m == 0) stage_split2(v.left_desc + (size_t)(a0 + lc * NL) * D, na - lc * NL, NL, D, L_hi, L_lo, pw, T2_PROD_WARPS, lane);
+          stage_split2(v.right_desc + (size_t)(b0 + m * T2_M) * D, nb - m * T2_M, T2_M, D, R_hi, R_lo, pw, T2_PROD_WARPS, lane);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          named_bar(1, T2_PROD);
+          if (*dead_prod) { out = true; break; }
+          if (ptid == 0) {
+            if (it >= 2) consume_free((int)it - 2);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::);
+            const uint32_t d_tmem = tmem + (it & 1) * 256u;
+            uint32_t acc = 0;
+            for (int ks = 0; ks < D / 8; ks++) {
+              const uint32_t koff = (uint32_t)ks * 256u;
+              const uint64_t rh = umma_desc(smem_u32(R_hi) + koff, 128, sbo), rl = umma_desc(smem_u32(R_lo) + koff, 128, sbo);
+              const uint64_t lh = umma_desc(smem_u32(L_hi) + koff, 128, sbo), ll = umma_desc(smem_u32(L_lo) + koff, 128, sbo);
+              umma_tf32(d_tmem, rh, lh, idesc, acc);
+              umma_tf32(d_tmem, rh, ll, idesc, 1);
+              umma_tf32(d_tmem, rl, lh, idesc, 1);
+              acc = 1;
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_mma + 8 * (it & 1)) : "memory");
+          }
+          it++;
+        }
+      end2 = end1; end1 = (int)it - 1; pp ^= 1;
+    }
+    if (*dead_prod && ptid == 0) atomicExch(t.err_flag, 1);
+  } else {
+    // ------------------------------------------------------------------ selectors
+    const int q = wid & 3, part = wid >> 2;            // TMEM lane quarter; share of the accumulator's column groups
+    const int n_grp = NL >> 5, gpw = n_grp / (T2_SEL_WARPS / 4);   // 32-column groups per accumulator / per warp
+    const float tau2 = (float)(v.tau * v.tau);
+    uint32_t it = 0, rows_seen[2] = {0, 0};
+    int pp = 0;
+    for (int p = blockIdx.x; p < v.n_pairs; p += gridDim.x) {
+      const int a0 = v.left_off[p], na = v.left_off[p + 1] - a0;
+      const int b0 = v.right_off[p], nb = v.right_off[p + 1] - b0;
+      if (na == 0 || nb == 0) continue;
+      wait_or_flag(bar_row + 8 * pp, rows_seen[pp] & 1, dead_sel);
+      rows_seen[pp]++;
+      const float4* rv = rowv + pp * T2_ROWS;
+      const int8_t* rm = rowm + pp * T2_ROWS;
+      int* cnt = s_cnt + pp * T2_ROWS;
+      const int n_lc = (na + NL - 1) / NL, n_m = (nb + T2_M - 1) / T2_M;
+      for (int lc = 0; lc < n_lc; lc++)
+        for (int m = 0; m < n_m; m++) {
+          const int c = m * T2_M + 32 * q + lane;     // this thread's right line
+          float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+          int octc = -1;
+          if (c < nb) { cv = t.rrec[b0 + c]; octc = t.roct[b0 + c]; }
+          wait_or_flag(bar_mma + 8 * (it & 1), (it >> 1) & 1, dead_sel);
+          // (warp-uniform: the flag is only ever raised, and a warp that disagrees on it for one step merely reads an
+          //  accumulator that is reported as invalid anyway)
+          const bool skip = __any_sync(0xffffffffu, *dead_sel != 0);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::);
+          for (int gi = 0; gi < gpw && !skip; gi++) {
+            const int g = part * gpw + gi;
+            const int j0 = lc * NL + 32 * g;
+            if (j0 >= na) break;   // warp-uniform
+            uint32_t r[32];
+            TMEM_LD32(r, tmem + ((uint32_t)(32 * q) << 16) + (it & 1) * 256u + (uint32_t)(32 * g));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int jj = 0; jj < 32; jj++) {
+              const int j = j0 + jj;       // rows past the pair carry octave -2 and never pass
+              const float4 lv = rv[j];
+              const float d2 = fmaxf(lv.x + cv.x - 2.f * __uint_as_float(r[jj]), 0.f);
+              const float cs = fabsf(fmaf(lv.y, cv.y, fmaf(lv.z, cv.z, lv.w * cv.w)));
+              bool pass = ((int)rm[j] == octc) & (d2 < tau2) & !(cs > 0.975f + 1e-5f);
+              if (pass && cs > 0.975f - 1e-5f) {  // parallax test of vgl::TriangulateLine within 1e-5 of its threshold: FP64
+                const double* ul = v.left_un + 3 * (size_t)(a0 + j);
+                const double* un = v.right_un + 3 * (size_t)(b0 + c);
+                pass = !(fabs(ul[0] * un[0] + ul[1] * un[1] + ul[2] * un[2]) > 0.975);
+              }
+              const unsigned mask = __ballot_sync(0xffffffffu, pass);
+              if (mask) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&cnt[j], __popc(mask));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const int slot = base + __popc(mask & ((1u << lane) - 1u));
+                if (pass && slot < T2_CAP) {
+                  const size_t o = (size_t)(a0 + j) * T2_CAP + slot;
+                  t.cand_d2[o] = __float_as_uint(d2);
+                  t.cand_col[o] = (uint16_t)c;
+                }
+              }
+            }
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::);
+          mbar_arrive(bar_free + 8 * (it & 1));
+          it++;
+        }
+      named_bar(2, T2_SEL);
+      if (*dead_sel) break;
+      for (int j = tid; j < na; j += T2_SEL) {
+        t.cand_cnt[a0 + j] = (uint16_t)min(cnt[j], T2_CAP + 1);
+        cnt[j] = 0;
+      }
+      pp ^= 1;
+    }
+    if (*dead_sel && tid == 0) atomicExch(t.err_flag, 1);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::);
+  __syncthreads();
+  if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// FP32 evaluation of the gates that line_pair_gate_fast applies in FP64, with a bound on its own rounding error:
+// 1 admissible, 0 not admissible, -1 too close to a threshold to tell.  Products that cancel are formed as cross
+// products (Lagrange / Binet-Cauchy: aa cc - ac^2 = |a x c|^2, aa cy - ac ay = (a x c).(a x y)), so that the error of the
+// endpoint parameter grows with 1 / sin(angle(a, c)) instead of its square.
+struct GateK { float K[9]; float kn; };
+__device__ __forceinline__ void cross3f(const float* a, const float* b, float* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ float dot3f(const float* a, const float* b) { return fmaf(a[0], b[0], fmaf(a[1], b[1], a[2] * b[2])); }
+__device__ __forceinline__ int line_gate32(const GateK& gk, const float* s1, const float* l1, const float* l2, float beta) {
+  float dir[3], c1[3], c2[3];
+  cross3f(l1, l2, dir);
+  const float dd = dot3f(dir, dir);
+  cross3f(dir, l1, c1);
+  cross3f(l2, dir, c2);
+  const float det = dot3f(l1, c2);          // = |dir|^2 up to rounding
+  if (!(det > 0.5f * dd) || !(dd > 1e-12f)) return -1;
+  const float f = beta / det;
+  const float X0[3] = {f * c1[0], f * c1[1], f * c1[2]};
+  const float n2 = dot3f(X0, X0);
+  if (n2 < 0.25f * (1.f - 1e-3f)) return 0;
+  if (!(n2 > 0.25f * (1.f + 1e-3f))) return -1;
+  const float* K = gk.K;
+  const float y[3] = {fmaf(K[0], X0[0], fmaf(K[1], X0[1], K[2] * X0[2])), fmaf(K[3], X0[0], fmaf(K[4], X0[1], K[5] * X0[2])),
+                      fmaf(K[6], X0[0], fmaf(K[7], X0[1], K[8] * X0[2]))};
+  const float c[3] = {-fmaf(K[0], dir[0], fmaf(K[1], dir[1], K[2] * dir[2])), -fmaf(K[3], dir[0], fmaf(K[4], dir[1], K[5] * dir[2])),
+                      -fmaf(K[6], dir[0], fmaf(K[7], dir[1], K[8] * dir[2]))};
+  const float nx = sqrtf(n2), nd = sqrtf(dd);
+  const float ec2 = gk.kn * gk.kn * dd;     // bound on |c|^2 that also covers the cancellation inside K dir
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    const float a[3] = {s1[2 * e], s1[2 * e + 1], 1.f};
+    float axc[3], axy[3];
+    cross3f(a, c, axc);
+    cross3f(a, y, axy);
+    const float det2 = dot3f(axc, axc), num = dot3f(axc, axy), aa = dot3f(a, a);
+    const float rho = det2 / (aa * ec2);
+    if (!(rho > 1e-6f)) return -1;
+    const float s = num / det2;
+    const float sigma = sqrtf(dot3f(axy, axy) / det2);
+    const float depth = fmaf(s, dir[2], X0[2]);
+    const float tol = 2e-5f * (1.f + rsqrtf(rho)) * (nx + 3.f * sigma * nd);
+    if (!(fabsf(depth) > tol)) return -1;
+    if (depth < 0.f) return 0;
+  }
+  return 1;
+}
+
+// one warp per left line; grid (rows / 8, pairs) or (pairs, rows / 8) when there are more than 65535 pairs
+__global__ void __launch_bounds__(256) k_line_gate32(LineTc2View t, GateK gk, int swap_grid, int check) {
+  const LineMatchView& v = t.v;
+  const int p = swap_grid ? blockIdx.x : blockIdx.y, jb = swap_grid ? blockIdx.y : blockIdx.x;
+  const int lane = threadIdx.x & 31, j = jb * 8 + (threadIdx.x >> 5);
+  const int a0 = v.left_off[p], na = v.left_off[p + 1] - a0, b0 = v.right_off[p];
+  if (j >= na) return;
+  const int gl = a0 + j;
+  const int cnt = min((int)t.cand_cnt[gl], T2_CAP);
+  const float4 l1v = t.lleq[gl];
+  const float l1[3] = {l1v.x, l1v.y, l1v.z};
+  const float4 sv = *reinterpret_cast<const float4*>(v.left_seg + 4 * (size_t)gl);
+  const float s1[4] = {sv.x, sv.y, sv.z, sv.w};
+  int n_adm = 0, n_border = 0, n_bad = 0;
+  for (int e = lane; e < cnt; e += 32) {
+    const size_t slot = (size_t)gl * T2_CAP + e;
+    const int c = b0 + t.cand_col[slot];
+    const float4 l2v = t.rleq[c];
+    const float l2[3] = {l2v.x, l2v.y, l2v.z};
+    int g = line_gate32(gk, s1, l1, l2, l2v.w);
+    if (g < 0 || check) {
+      const bool g64 = line_pair_gate_fast(v, v.left_seg + 4 * (size_t)gl, v.left_leq + 3 * (size_t)gl, v.right_leq + 3 * (size_t)c);
+      if (g < 0) n_border++;
+      else if ((g != 0) != g64) n_bad++;
+      g = g64;
+    }
+    if (g) n_adm++;
+    else t.cand_d2[slot] = 0xFFFFFFFFu;
+  }
+  if (check) {
+    if (lane == 0) atomicAdd(t.err_flag + 2, cnt);
+    if (n_adm) atomicAdd(t.err_flag + 3, n_adm);
+    if (n_border) atomicAdd(t.err_flag + 4, n_border);
+    if (n_bad) atomicAdd(t.err_flag + 5, n_bad);
+  }
+}
+
+constexpr int G2_NE = T2_CAP / 32;
+__global__ void __launch_bounds__(32) k_line_greedy2(LineTc2View t) {
+  __shared__ uint32_t taken[T2_ROWS / 32];
+  const LineMatchView& v = t.v;
+  const int lane = threadIdx.x, p = blockIdx.x;
+  const int a0 = v.left_off[p], na = v.left_off[p + 1] - a0;
+  const int b0 = v.right_off[p], nb = v.right_off[p + 1] - b0;
+  if (na == 0) return;
+  if (lane < T2_ROWS / 32) taken[lane] = 0u;
+  __syncwarp();
+  uint32_t nd2[G2_NE];
+  uint16_t ncol[G2_NE];
+  int ncnt = 0;
+  auto fetch = [&](int j) {
+    ncnt = t.cand_cnt[a0 + j];
+    const int tot = min(ncnt, T2_CAP);
+    const size_t o = (size_t)(a0 + j) * T2_CAP;
+#pragma unroll
+    for (int i = 0; i < G2_NE; i++) {
+      const int e = lane + 32 * i;
+      nd2[i] = 0xFFFFFFFFu;
+      ncol[i] = 0;
+      if (e < tot) { nd2[i] = t.cand_d2[o + e]; ncol[i] = t.cand_col[o + e]; }
+    }
+  };
+  fetch(0);
+  for (int j = 0; j < na; j++) {
+    const int cnt = ncnt;
+    uint32_t bd = 0xFFFFFFFFu, bc = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < G2_NE; i++) {
+      const uint32_t c = ncol[i];
+      const bool live = nd2[i] != 0xFFFFFFFFu && !((taken[c >> 5] >> (c & 31)) & 1u);
+      if (live && (nd2[i] < bd || (nd2[i] == bd && c < bc))) { bd = nd2[i]; bc = c; }
+    }
+    if (j + 1 < na) fetch(j + 1);
+    int bi = -1;
+    if (cnt <= T2_CAP) {
+      const uint32_t m = __reduce_min_sync(0xffffffffu, bd);
+      if (m != 0xFFFFFFFFu) bi = (int)__reduce_min_sync(0xffffffffu, bd == m ? bc : 0xFFFFFFFFu);
+    } else {
+      if (lane == 0) atomicAdd(t.err_flag + 1, 1);
+      // overflowed list: exact scan of the row.  Pass A: lanes stride over the right lines and apply every gate of
+      // CheckLinePair; pass B: exact FP32 distances of the few admissible ones, computed by the whole warp per line.
+      const int gl = a0 + j;
+      const bool l_ok = !(v.left_len[gl] < (double)v.min_len);
+      const double* ul = v.left_un + 3 * (size_t)gl;
+      float best = INFINITY;
+      for (int cb = 0; cb < nb && l_ok; cb += 32) {
+        const int c = cb + lane;
+        bool ok = false;
+        if (c < nb && !((taken[c >> 5] >> (c & 31)) & 1u)) {
+          const int gc = b0 + c;
+          if (v.left_oct[gl] == v.right_oct[gc] && !(v.right_len[gc] < (double)v.min_len)) {
+            const double* un = v.right_un + 3 * (size_t)gc;
+            if (!(fabs(ul[0] * un[0] + ul[1] * un[1] + ul[2] * un[2]) > 0.975))
+              ok = line_pair_gate(v, v.left_seg + 4 * (size_t)gl, v.left_leq + 3 * (size_t)gl, v.right_leq + 3 * (size_t)gc);
+          }
+        }
+        unsigned mm = __ballot_sync(0xffffffffu, ok);
+        while (mm) {  // ascending column order, strict <: the first minimum wins as in the reference
+          const int c2 = cb + __ffs(mm) - 1;
+          mm &= mm - 1;
+          const float d = sqrtf(warp_exact_d2(v.left_desc + (size_t)gl * v.D, v.right_desc + (size_t)(b0 + c2) * v.D, v.D, lane));
+          if ((double)d < v.tau && d < best) { best = d; bi = c2; }
+        }
+      }
+    }
+    if (lane == 0) {
+      v.match[a0 + j] = bi;
+      if (bi >= 0) taken[bi >> 5] |= 1u << (bi & 31);
+    }
+    __syncwarp();
+  }
+}
+
+// exact distance of every match: one warp per left line, grid as k_line_gate32
+__global__ void __launch_bounds__(256) k_line_exact2(LineTc2View t, int swap_grid) {
+  const LineMatchView& v = t.v;
+  const int p = swap_grid ? blockIdx.x : blockIdx.y, jb = swap_grid ? blockIdx.y : blockIdx.x;
+  const int lane = threadIdx.x & 31, j = jb * 8 + (threadIdx.x >> 5);
+  const int a0 = v.left_off[p], na = v.left_off[p + 1] - a0;
+  if (j >= na) return;
+  const int bi = v.match[a0 + j];
+  float d = INFINITY;
+  if (bi >= 0) d = sqrtf(warp_exact_d2(v.left_desc + (size_t)(a0 + j) * v.D, v.right_desc + (size_t)(v.right_off[p] + bi) * v.D, v.D, lane));
+  if (lane == 0) v.mdist[a0 + j] = d;
+}
+
 template <typename T>
 int upm(LldCtx* c, T** dst, const T* src, size_t n) {
   cudaError_t e = cudaSuccess;
@@ -720,6 +1202,8 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
   }
   const char* e_tc = getenv("LLD_LINE_TC");
   const bool use_tc = !(e_tc && e_tc[0] == '0') && v.D % 8 == 0 && v.D >= 8 && v.D <= 72 && max_nb <= TC_COLS && max_nb >= 1 && max_na >= 1;
+  // second generation (persistent, warp-specialised) unless LLD_LINE_TC=old; needs <= 512 left lines per pair as well
+  const bool use_tc2 = use_tc && !(e_tc && e_tc[0] == 'o') && max_na <= T2_ROWS;
   // tiles + matrix offsets
   std::vector<long long> mat_off(P), taken_off(P);
   std::vector<int> tp, tr, tc;
@@ -763,7 +1247,39 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
   const int nmax = std::max(std::max(n_left, n_right), 1);
   int* d_tc_err = nullptr;
   LLD_LAUNCH(c, k_line_prep, cdiv(nmax, 128), 128, 0, v, n_left, n_right);
-  if (use_tc) {
+  if (use_tc2) {
+    LineTc2View t;
+    t.v = v;
+    t.nl_chunk = v.D <= 64 ? 256 : 128;
+    UPM(t.lrec, float4, nullptr, n_left);
+    UPM(t.rrec, float4, nullptr, n_right);
+    UPM(t.loct, int8_t, nullptr, n_left);
+    UPM(t.roct, int8_t, nullptr, n_right);
+    UPM(t.lleq, float4, nullptr, n_left);
+    UPM(t.rleq, float4, nullptr, n_right);
+    UPM(t.cand_d2, uint32_t, nullptr, (size_t)n_left * T2_CAP);
+    UPM(t.cand_col, uint16_t, nullptr, (size_t)n_left * T2_CAP);
+    UPM(t.cand_cnt, uint16_t, nullptr, n_left);
+    UPM(t.err_flag, int, nullptr, 8);
+    d_tc_err = t.err_flag;
+    LLD_CUDA(c, cudaMemsetAsync(t.err_flag, 0, 8 * sizeof(int), c->stream));
+    LLD_CUDA(c, cudaMemsetAsync(t.cand_cnt, 0, sizeof(uint16_t) * (size_t)n_left, c->stream));   // pairs without right lines
+    LLD_CUDA(c, cudaMemsetAsync(v.match, 0xFF, sizeof(int) * (size_t)n_left, c->stream));
+    const size_t smem = (size_t)(t.nl_chunk + T2_M) * v.D * 8 + 2 * T2_ROWS * (16 + 4 + 1) + 6 * 8 + 16;
+    LLD_CUDA(c, lld_raise_dyn_smem(k_line_tc2, (size_t)(int)smem));
+    GateK gk;
+    double kn = 0;
+    for (int i = 0; i < 9; i++) { gk.K[i] = (float)v.K[i]; kn += v.K[i] * v.K[i]; }
+    gk.kn = (float)sqrt(kn);
+    const int check = getenv("LLD_LINE_CHECK") != nullptr || getenv("LLD_LINE_STATS") != nullptr;
+    const int swap_grid = P > 65535;
+    const dim3 grid_rows = swap_grid ? dim3(P, cdiv(max_na, 8)) : dim3(cdiv(max_na, 8), P);
+    LLD_LAUNCH(c, k_line_prep2, cdiv(8 * (n_left + n_right), 256), 256, 0, t, n_left, n_right);
+    LLD_LAUNCH(c, k_line_tc2, std::min(P, c->sm_count), T2_NT, smem, t);
+    LLD_LAUNCH(c, k_line_gate32, grid_rows, 256, 0, t, gk, swap_grid, check);
+    LLD_LAUNCH(c, k_line_greedy2, P, 32, 0, t);
+    LLD_LAUNCH(c, k_line_exact2, grid_rows, 256, 0, t, swap_grid);
+  } else if (use_tc) {
     // tiles ordered by row block: block r of every pair is contracted by one launch, after which the greedy can advance
     // through the left lines [128 r, 128 (r + 1)) of every pair while the next block is being contracted
     std::vector<int> ttp, ttr, blk_begin;
@@ -854,9 +1370,16 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
   cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->ms_compute, c->ev[1], c->ev[2]);
   cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]);
-  if (getenv("LLD_LINE_STATS") && d_tc_err)
+  if (getenv("LLD_LINE_STATS") && d_tc_err && !use_tc2)
     fprintf(stderr, "[lld_line_match] fallback rows %d, listed candidates %d, geometrically admissible %d, max |d2_tc - d2_exact| %.3e\n",
             h_err[1], h_err[2], h_err[3], (double)*reinterpret_cast<float*>(h_err + 4));
+  if (getenv("LLD_LINE_STATS") && d_tc_err && use_tc2)
+    fprintf(stderr, "[lld_line_match] fallback rows %d, listed candidates %d, admissible %d, decided in FP64 %d, FP32/FP64 disagreements %d\n",
+            h_err[1], h_err[2], h_err[3], h_err[4], h_err[5]);
+  if (use_tc2 && h_err[5]) {
+    snprintf(c->err, sizeof(c->err), "line matcher: %d FP32 gate decisions differ from FP64 (LLD_LINE_CHECK)", h_err[5]);
+    return LLD_ERR_CUDA;
+  }
   if (*h_err) {
     snprintf(c->err, sizeof(c->err), "line matcher: tensor-core completion barrier timed out");
     return LLD_ERR_CUDA;
