@@ -699,16 +699,18 @@ constexpr int T2_SEL = 32 * T2_SEL_WARPS, T2_PROD = 32 * T2_PROD_WARPS, T2_NT = 
 struct LineTc2View {
   LineMatchView v;
   int nl_chunk;             // left lines per step (256, or 128 for wide descriptors)
+  int dbg;                  // timing experiments (LLD_LINE_DBG): 1 selectors idle, 2 no staging, 4 no MMA
   float4* lrec;             // [n_left]  {|a|^2, unit plane normal}
   float4* rrec;             // [n_right]
   int8_t* loct;             // [n_left]  octave, -2 when the line is too short
   int8_t* roct;             // [n_right] octave, -1 when the line is too short
-  float4* lleq;             // [n_left]  {K^T l normalised, 0}
+  float4* lgeo;             // [n_left][7] FP32 left-line geometry of the gates: {l1, |l1|^2}, {|l1|, |a0|^2, |a1|^2, -}, M0 | M1 (M = [a]_x K)
   float4* rleq;             // [n_right] {K^T l normalised, beta = l_x * baseline}
-  uint32_t* cand_d2;        // [n_left][T2_CAP]
-  uint16_t* cand_col;       // [n_left][T2_CAP]
+  float* rh;                // [n_right] |X0| >= 1/2 as a bound on the parallax cosine: cs >= rh (see k_line_prep2)
+  uint2* cand;              // [n_left][T2_CAP] {float bits of the 3xTF32 d^2 (0xFFFFFFFF: dead), right line}
   uint16_t* cand_cnt;       // [n_left] listed candidates (> T2_CAP: overflow)
-  int* err_flag;            // 0: barrier time-out; 1: overflow rows; 2: listed; 3: admissible; 4: borderline (FP64); 5: FP32 / FP64 disagreements
+  int* err_flag;            // 0: barrier time-out; 1: overflow rows; 2: listed; 4: decided in FP64; 5: FP32 / FP64 disagreements;
+                            // 6: float bits of the largest observed |T_fp32 - T_fp64| / bound (check runs)
 };
 
 // 8 lanes per line
@@ -739,10 +741,32 @@ __global__ void __launch_bounds__(256) k_line_prep2(LineTc2View t, int n_left, i
     t.rrec[i] = rec;
     t.roct[i] = (int8_t)(too_short ? -1 : oct);
     t.rleq[i] = make_float4((float)lq[0], (float)lq[1], (float)lq[2], (float)(lq[0] * v.baseline));
+    // |X0|^2 = beta^2 |l1|^2 / |l1 x l2|^2 and |l1 x l2|^2 = |l1|^2 |l2|^2 (1 - cs^2) with cs the cosine between the unit
+    // normals: |X0| >= 1/2  <=>  cs^2 >= 1 - 4 beta^2 / |l2|^2, a per-right-line bound the selectors test for free
+    const double beta = lq[0] * v.baseline, l2sq = lq[0] * lq[0] + lq[1] * lq[1] + lq[2] * lq[2];
+    t.rh[i] = (float)sqrt(fmax(0.0, 1.0 - 4.0 * beta * beta / l2sq));
   } else {
     t.lrec[i] = rec;
     t.loct[i] = (int8_t)(too_short ? -2 : oct);
-    t.lleq[i] = make_float4((float)lq[0], (float)lq[1], (float)lq[2], 0.f);
+    const float* sg = v.left_seg + 4 * (size_t)i;
+    float m[20];
+    float sa[2];   // |a|^2 of the two endpoints
+    for (int e = 0; e < 2; e++) {
+      const double a[3] = {sg[2 * e], sg[2 * e + 1], 1.0};
+      const double* K = v.K;
+      for (int cc = 0; cc < 3; cc++) {   // [a]_x K, column cc
+        m[9 * e + 0 + cc] = (float)(-a[2] * K[3 + cc] + a[1] * K[6 + cc]);
+        m[9 * e + 3 + cc] = (float)(a[2] * K[cc] - a[0] * K[6 + cc]);
+        m[9 * e + 6 + cc] = (float)(-a[1] * K[cc] + a[0] * K[3 + cc]);
+      }
+      sa[e] = (float)(a[0] * a[0] + a[1] * a[1] + 1.0);
+    }
+    m[18] = m[19] = 0.f;
+    const double l1sq = lq[0] * lq[0] + lq[1] * lq[1] + lq[2] * lq[2];
+    float4* g = t.lgeo + 7 * (size_t)i;
+    g[0] = make_float4((float)lq[0], (float)lq[1], (float)lq[2], (float)l1sq);
+    g[1] = make_float4((float)sqrt(l1sq), sa[0], sa[1], 0.f);
+    for (int k = 0; k < 5; k++) g[2 + k] = make_float4(m[4 * k], m[4 * k + 1], m[4 * k + 2], m[4 * k + 3]);
   }
 }
 
@@ -821,7 +845,7 @@ __global__ void __launch_bounds__(T2_NT, 1) k_line_tc2(LineTc2View t) {
   if (tid == 0) {
     for (int b = 0; b < 2; b++) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_mma + 8 * b), "r"(1));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_free + 8 * b), "r"(T2_SEL));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_free + 8 * b), "r"(T2_SEL_WARPS));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_row + 8 * b), "r"(T2_PROD));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::);
@@ -871,8 +895,10 @@ __global__ void __launch_bounds__(T2_NT, 1) k_line_tc2(LineTc2View t) {
         for (int m = 0; m < n_m; m++) {
           // the MMAs of the previous step have read the R (and L) buffers
           if (it >= 1) wait_or_flag(bar_mma + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1, dead_prod);
-          if (m == 0) stage_split2(v.left_desc + (size_t)(a0 + lc * NL) * D, na - lc * NL, NL, D, L_hi, L_lo, pw, T2_PROD_WARPS, lane);
-          stage_split2(v.right_desc + (size_t)(b0 + m * T2_M) * D, nb - m * T2_M, T2_M, D, R_hi, R_lo, pw, T2_PROD_WARPS, lane);
+          if (!(t.dbg & 2)) {
+            if (m == 0) stage_split2(v.left_desc + (size_t)(a0 + lc * NL) * D, na - lc * NL, NL, D, L_hi, L_lo, pw, T2_PROD_WARPS, lane);
+            stage_split2(v.right_desc + (size_t)(b0 + m * T2_M) * D, nb - m * T2_M, T2_M, D, R_hi, R_lo, pw, T2_PROD_WARPS, lane);
+          }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           named_bar(1, T2_PROD);
           if (*dead_prod) { out = true; break; }
@@ -881,7 +907,7 @@ __global__ void __launch_bounds__(T2_NT, 1) k_line_tc2(LineTc2View t) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::);
             const uint32_t d_tmem = tmem + (it & 1) * 256u;
             uint32_t acc = 0;
-            for (int ks = 0; ks < D / 8; ks++) {
+            for (int ks = 0; ks < ((t.dbg & 4) ? 0 : D / 8); ks++) {
               const uint32_t koff = (uint32_t)ks * 256u;
               const uint64_t rh = umma_desc(smem_u32(R_hi) + koff, 128, sbo), rl = umma_desc(smem_u32(R_lo) + koff, 128, sbo);
               const uint64_t lh = umma_desc(smem_u32(L_hi) + koff, 128, sbo), ll = umma_desc(smem_u32(L_lo) + koff, 128, sbo);
@@ -919,11 +945,12 @@ __global__ void __launch_bounds__(T2_NT, 1) k_line_tc2(LineTc2View t) {
           const int c = m * T2_M + 32 * q + lane;     // this thread's right line
           float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
           int octc = -1;
-          if (c < nb) { cv = t.rrec[b0 + c]; octc = t.roct[b0 + c]; }
+          float hc = 0.f;
+          if (c < nb) { cv = t.rrec[b0 + c]; octc = t.roct[b0 + c]; hc = t.rh[b0 + c] - 1e-4f; }
           wait_or_flag(bar_mma + 8 * (it & 1), (it >> 1) & 1, dead_sel);
           // (warp-uniform: the flag is only ever raised, and a warp that disagrees on it for one step merely reads an
           //  accumulator that is reported as invalid anyway)
-          const bool skip = __any_sync(0xffffffffu, *dead_sel != 0);
+          const bool skip = __any_sync(0xffffffffu, *dead_sel != 0) || (t.dbg & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::);
           for (int gi = 0; gi < gpw && !skip; gi++) {
             const int g = part * gpw + gi;
@@ -932,34 +959,60 @@ __global__ void __launch_bounds__(T2_NT, 1) k_line_tc2(LineTc2View t) {
             uint32_t r[32];
             TMEM_LD32(r, tmem + ((uint32_t)(32 * q) << 16) + (it & 1) * 256u + (uint32_t)(32 * g));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // pass 1 (branch-free): survivors of the 32 left lines of this group; lane jj keeps the ballot of row j0 + jj.
+            // cheap gates of CheckLinePair, the parallax test of vgl::TriangulateLine and a superset of |X0| >= 1/2
+            unsigned my_mask = 0;
+            bool edge_any = false;
 #pragma unroll
             for (int jj = 0; jj < 32; jj++) {
               const int j = j0 + jj;       // rows past the pair carry octave -2 and never pass
               const float4 lv = rv[j];
               const float d2 = fmaxf(lv.x + cv.x - 2.f * __uint_as_float(r[jj]), 0.f);
               const float cs = fabsf(fmaf(lv.y, cv.y, fmaf(lv.z, cv.z, lv.w * cv.w)));
-              bool pass = ((int)rm[j] == octc) & (d2 < tau2) & !(cs > 0.975f + 1e-5f);
-              if (pass && cs > 0.975f - 1e-5f) {  // parallax test of vgl::TriangulateLine within 1e-5 of its threshold: FP64
-                const double* ul = v.left_un + 3 * (size_t)(a0 + j);
-                const double* un = v.right_un + 3 * (size_t)(b0 + c);
-                pass = !(fabs(ul[0] * un[0] + ul[1] * un[1] + ul[2] * un[2]) > 0.975);
-              }
+              const bool pass = ((int)rm[j] == octc) & (d2 < tau2) & !(cs > 0.975f + 1e-5f) & (cs >= hc);
+              edge_any |= pass & (cs > 0.975f - 1e-5f);
               const unsigned mask = __ballot_sync(0xffffffffu, pass);
-              if (mask) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&cnt[j], __popc(mask));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const int slot = base + __popc(mask & ((1u << lane) - 1u));
-                if (pass && slot < T2_CAP) {
-                  const size_t o = (size_t)(a0 + j) * T2_CAP + slot;
-                  t.cand_d2[o] = __float_as_uint(d2);
-                  t.cand_col[o] = (uint16_t)c;
+              if (lane == jj) my_mask = mask;
+            }
+            if (__any_sync(0xffffffffu, edge_any)) {
+              // some pair of the tile has its parallax cosine within 1e-5 of the threshold (rare): the masks are formed
+              // again with those pairs decided in FP64, as the reference computes the test
+#pragma unroll 1
+              for (int jj = 0; jj < 32; jj++) {
+                const int j = j0 + jj;
+                const float4 lv = rv[j];
+                uint32_t rj;      // column jj of the group, read again from TMEM (no dynamic register indexing)
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(rj) : "r"(tmem + ((uint32_t)(32 * q) << 16) + (it & 1) * 256u + (uint32_t)(32 * g + jj)));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const float d2 = fmaxf(lv.x + cv.x - 2.f * __uint_as_float(rj), 0.f);
+                const float cs = fabsf(fmaf(lv.y, cv.y, fmaf(lv.z, cv.z, lv.w * cv.w)));
+                bool pass = ((int)rm[j] == octc) & (d2 < tau2) & !(cs > 0.975f + 1e-5f) & (cs >= hc);
+                if (pass && cs > 0.975f - 1e-5f) {
+                  const double* ul = v.left_un + 3 * (size_t)(a0 + j);
+                  const double* un = v.right_un + 3 * (size_t)(b0 + c);
+                  pass = !(fabs(ul[0] * un[0] + ul[1] * un[1] + ul[2] * un[2]) > 0.975);
                 }
+                const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                if (lane == jj) my_mask = mask;
               }
+            }
+            // one shared-memory atomic per row, all 32 rows at once
+            int my_base = 0;
+            if (my_mask) my_base = atomicAdd(&cnt[j0 + lane], __popc(my_mask));
+            // pass 2 (branch-free): the survivors of a row go to consecutive slots of its list
+            const unsigned lt = (1u << lane) - 1u;
+            uint2* const out0 = t.cand + (size_t)(a0 + j0) * T2_CAP;
+#pragma unroll
+            for (int jj = 0; jj < 32; jj++) {
+              const unsigned mask = __shfl_sync(0xffffffffu, my_mask, jj);
+              const int slot = __shfl_sync(0xffffffffu, my_base, jj) + __popc(mask & lt);
+              const float d2 = fmaxf(rv[j0 + jj].x + cv.x - 2.f * __uint_as_float(r[jj]), 0.f);
+              if (((mask >> lane) & 1u) && slot < T2_CAP) out0[jj * T2_CAP + slot] = make_uint2(__float_as_uint(d2), (uint32_t)c);
             }
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::);
-          mbar_arrive(bar_free + 8 * (it & 1));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_free + 8 * (it & 1));
           it++;
         }
       named_bar(2, T2_SEL);
@@ -977,92 +1030,185 @@ __global__ void __launch_bounds__(T2_NT, 1) k_line_tc2(LineTc2View t) {
   if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-// FP32 evaluation of the gates that line_pair_gate_fast applies in FP64, with a bound on its own rounding error:
-// 1 admissible, 0 not admissible, -1 too close to a threshold to tell.  Products that cancel are formed as cross
-// products (Lagrange / Binet-Cauchy: aa cc - ac^2 = |a x c|^2, aa cy - ac ay = (a x c).(a x y)), so that the error of the
-// endpoint parameter grows with 1 / sin(angle(a, c)) instead of its square.
-struct GateK { float K[9]; float kn; };
+// FP32 evaluation of the gates that line_pair_gate_fast applies in FP64, division-free and with a bound on its own
+// rounding error: 1 admissible, 0 not admissible, -1 too close to a threshold to tell (the caller decides those in FP64).
+// With dir = l1 x l2, c1 = dir x l1, f = beta / |dir|^2 (X0 = f c1), and, per endpoint a = (px, py, 1), u = a x (K dir),
+// w = a x (K c1) (both as products with the per-endpoint matrix M = [a]_x K that k_line_prep2 forms in FP64):
+//   |X0|^2 >= 1/4            <=>  beta^2 |l1|^2 >= |dir|^2 / 4                  (dir is perpendicular to l1; the selectors
+//                                                                                 have applied a superset of this test)
+//   endpoint depth >= 0      <=>  beta T >= 0,  T = c1_z |u|^2 - (u.w) dir_z    (Binet-Cauchy: aa cy - ac ay = (a x c).(a x y);
+//                                                                                 depth = f T / |u|^2)
+// Error model: every computed vector carries an absolute error of k eps times the product of the norms that went into
+// it; with E = |K|_F |a| |dir| >= |u| and q = |u| this gives |dT| <= k eps |dir| (q + E) 3 (|l1| q + |w|), tested in the
+// square-root-free form T^2 > (k eps)^2 |dir|^2 2 (q^2 + E^2) 9 2 (|l1|^2 q^2 + |w|^2).
+struct GateK { float kn2; float c_tol2; };
+struct GateL {     // per left line (registers, warp-uniform)
+  float l1[3], l1sq, aa[2];
+  float M[2][9];
+};
 __device__ __forceinline__ void cross3f(const float* a, const float* b, float* o) {
   o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
 }
 __device__ __forceinline__ float dot3f(const float* a, const float* b) { return fmaf(a[0], b[0], fmaf(a[1], b[1], a[2] * b[2])); }
-__device__ __forceinline__ int line_gate32(const GateK& gk, const float* s1, const float* l1, const float* l2, float beta) {
-  float dir[3], c1[3], c2[3];
-  cross3f(l1, l2, dir);
+__device__ __forceinline__ void mat3f(const float* M, const float* x, float* o) {
+  o[0] = fmaf(M[0], x[0], fmaf(M[1], x[1], M[2] * x[2]));
+  o[1] = fmaf(M[3], x[0], fmaf(M[4], x[1], M[5] * x[2]));
+  o[2] = fmaf(M[6], x[0], fmaf(M[7], x[1], M[8] * x[2]));
+}
+__device__ __forceinline__ GateL load_gate_left(const float4* g) {
+  GateL L;
+  const float4 g0 = g[0], g1 = g[1], g2 = g[2], g3 = g[3], g4 = g[4], g5 = g[5], g6 = g[6];
+  L.l1[0] = g0.x; L.l1[1] = g0.y; L.l1[2] = g0.z; L.l1sq = g0.w;
+  L.aa[0] = g1.y; L.aa[1] = g1.z;
+  const float m[20] = {g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w, g4.x, g4.y, g4.z, g4.w, g5.x, g5.y, g5.z, g5.w, g6.x, g6.y, g6.z, g6.w};
+#pragma unroll
+  for (int k = 0; k < 9; k++) { L.M[0][k] = m[k]; L.M[1][k] = m[9 + k]; }
+  return L;
+}
+// T and its bound for endpoint e (shared by the decision and by the check statistics)
+__device__ __forceinline__ void gate32_endpoint(const GateK& gk, const GateL& L, int e, const float* dir, const float* c1, float dd,
+                                                float* T, float* tol2, bool* cond) {
+  float u[3], w[3];
+  mat3f(L.M[e], dir, u);
+  mat3f(L.M[e], c1, w);
+  const float det2 = dot3f(u, u), uw = dot3f(u, w), ww = dot3f(w, w);
+  *T = c1[2] * det2 - uw * dir[2];
+  const float E2 = gk.kn2 * dd * L.aa[e];
+  *cond = det2 > 1e-6f * E2;
+  *tol2 = gk.c_tol2 * (det2 + E2) * dd * fmaf(L.l1sq, det2, ww);
+}
+__device__ __forceinline__ int line_gate32(const GateK& gk, const GateL& L, const float* l2, float beta) {
+  float dir[3], c1[3];
+  cross3f(L.l1, l2, dir);
   const float dd = dot3f(dir, dir);
-  cross3f(dir, l1, c1);
-  cross3f(l2, dir, c2);
-  const float det = dot3f(l1, c2);          // = |dir|^2 up to rounding
-  if (!(det > 0.5f * dd) || !(dd > 1e-12f)) return -1;
-  const float f = beta / det;
-  const float X0[3] = {f * c1[0], f * c1[1], f * c1[2]};
-  const float n2 = dot3f(X0, X0);
-  if (n2 < 0.25f * (1.f - 1e-3f)) return 0;
-  if (!(n2 > 0.25f * (1.f + 1e-3f))) return -1;
-  const float* K = gk.K;
-  const float y[3] = {fmaf(K[0], X0[0], fmaf(K[1], X0[1], K[2] * X0[2])), fmaf(K[3], X0[0], fmaf(K[4], X0[1], K[5] * X0[2])),
-                      fmaf(K[6], X0[0], fmaf(K[7], X0[1], K[8] * X0[2]))};
-  const float c[3] = {-fmaf(K[0], dir[0], fmaf(K[1], dir[1], K[2] * dir[2])), -fmaf(K[3], dir[0], fmaf(K[4], dir[1], K[5] * dir[2])),
-                      -fmaf(K[6], dir[0], fmaf(K[7], dir[1], K[8] * dir[2]))};
-  const float nx = sqrtf(n2), nd = sqrtf(dd);
-  const float ec2 = gk.kn * gk.kn * dd;     // bound on |c|^2 that also covers the cancellation inside K dir
+  if (!(dd > 1e-12f)) return -1;
+  const float lhs = beta * beta * L.l1sq, rhs = 0.25f * dd;
+  if (lhs < rhs * (1.f - 2e-3f)) return 0;
+  if (!(lhs > rhs * (1.f + 2e-3f))) return -1;
+  cross3f(dir, L.l1, c1);
+  int r = 1;
 #pragma unroll
   for (int e = 0; e < 2; e++) {
-    const float a[3] = {s1[2 * e], s1[2 * e + 1], 1.f};
-    float axc[3], axy[3];
-    cross3f(a, c, axc);
-    cross3f(a, y, axy);
-    const float det2 = dot3f(axc, axc), num = dot3f(axc, axy), aa = dot3f(a, a);
-    const float rho = det2 / (aa * ec2);
-    if (!(rho > 1e-6f)) return -1;
-    const float s = num / det2;
-    const float sigma = sqrtf(dot3f(axy, axy) / det2);
-    const float depth = fmaf(s, dir[2], X0[2]);
-    const float tol = 2e-5f * (1.f + rsqrtf(rho)) * (nx + 3.f * sigma * nd);
-    if (!(fabsf(depth) > tol)) return -1;
-    if (depth < 0.f) return 0;
+    float T, tol2;
+    bool cond;
+    gate32_endpoint(gk, L, e, dir, c1, dd, &T, &tol2, &cond);
+    if (!cond || !(T * T > tol2)) r = r == 0 ? 0 : -1;   // undecided (a clear rejection by the other endpoint stands)
+    else if (beta * T < 0.f) r = 0;
   }
-  return 1;
+  return r;
+}
+// FP64 value of T for the check statistics (same formula from the FP64 line equations)
+__device__ __forceinline__ double gate64_T(const LineMatchView& v, const float* s1, const double* l1, const double* l2, int e) {
+  double dir[3], c1[3];
+  cross3(l1, l2, dir);
+  cross3(dir, l1, c1);
+  const double* K = v.K;
+  const double kd[3] = {K[0] * dir[0] + K[1] * dir[1] + K[2] * dir[2], K[3] * dir[0] + K[4] * dir[1] + K[5] * dir[2], K[6] * dir[0] + K[7] * dir[1] + K[8] * dir[2]};
+  const double kc[3] = {K[0] * c1[0] + K[1] * c1[1] + K[2] * c1[2], K[3] * c1[0] + K[4] * c1[1] + K[5] * c1[2], K[6] * c1[0] + K[7] * c1[1] + K[8] * c1[2]};
+  const double a[3] = {s1[2 * e], s1[2 * e + 1], 1.0};
+  double u[3], w[3];
+  cross3(a, kd, u);
+  cross3(a, kc, w);
+  return c1[2] * dot3(u, u) - dot3(u, w) * dir[2];
 }
 
-// one warp per left line; grid (rows / 8, pairs) or (pairs, rows / 8) when there are more than 65535 pairs
-__global__ void __launch_bounds__(256) k_line_gate32(LineTc2View t, GateK gk, int swap_grid, int check) {
+// The remaining gates of CheckLinePair over the candidate lists, and compaction of each list to its admissible entries
+// (in place: the write position never passes the read position).  A warp takes G32_ROWS consecutive left lines of a pair;
+// entries the FP32 evaluation cannot decide stay in the list provisionally and are queued (per warp, shared memory);
+// the queue is worked off 32 entries at a time by the FP64 formulas, so that the FP64 path runs with full warps
+// instead of one or two lanes per list; an entry that fails there is overwritten by the dead key.
+// grid (row blocks, pairs), or (pairs, row blocks) when there are more than 65535 pairs.
+constexpr int G32_ROWS = 8, G32_WARPS = 8;
+struct GateQ { uint32_t slot_lo; uint32_t slot_hi; int gl; int c; };   // list slot, left line, right line (global indices)
+__global__ void __launch_bounds__(32 * G32_WARPS) k_line_gate32(LineTc2View t, GateK gk, int swap_grid, int check) {
+  __shared__ GateQ queue[G32_WARPS][64];
   const LineMatchView& v = t.v;
   const int p = swap_grid ? blockIdx.x : blockIdx.y, jb = swap_grid ? blockIdx.y : blockIdx.x;
-  const int lane = threadIdx.x & 31, j = jb * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int a0 = v.left_off[p], na = v.left_off[p + 1] - a0, b0 = v.right_off[p];
-  if (j >= na) return;
-  const int gl = a0 + j;
-  const int cnt = min((int)t.cand_cnt[gl], T2_CAP);
-  const float4 l1v = t.lleq[gl];
-  const float l1[3] = {l1v.x, l1v.y, l1v.z};
-  const float4 sv = *reinterpret_cast<const float4*>(v.left_seg + 4 * (size_t)gl);
-  const float s1[4] = {sv.x, sv.y, sv.z, sv.w};
-  int n_adm = 0, n_border = 0, n_bad = 0;
-  for (int e = lane; e < cnt; e += 32) {
-    const size_t slot = (size_t)gl * T2_CAP + e;
-    const int c = b0 + t.cand_col[slot];
-    const float4 l2v = t.rleq[c];
-    const float l2[3] = {l2v.x, l2v.y, l2v.z};
-    int g = line_gate32(gk, s1, l1, l2, l2v.w);
-    if (g < 0 || check) {
-      const bool g64 = line_pair_gate_fast(v, v.left_seg + 4 * (size_t)gl, v.left_leq + 3 * (size_t)gl, v.right_leq + 3 * (size_t)c);
-      if (g < 0) n_border++;
-      else if ((g != 0) != g64) n_bad++;
-      g = g64;
+  const int j_begin = (jb * G32_WARPS + wid) * G32_ROWS;
+  if (j_begin >= na) return;
+  const int j_end = min(j_begin + G32_ROWS, na);
+  GateQ* q = queue[wid];
+  int qn = 0;
+  int n_listed = 0, n_border = 0, n_bad = 0;
+  float worst = 0.f;
+  const unsigned lt = (1u << lane) - 1u;
+  auto settle = [&](const GateQ& it) {   // FP64 verdict for a queued entry
+    if (!line_pair_gate_fast(v, v.left_seg + 4 * (size_t)it.gl, v.left_leq + 3 * (size_t)it.gl, v.right_leq + 3 * (size_t)it.c))
+      t.cand[((size_t)it.slot_hi << 32) | it.slot_lo].x = 0xFFFFFFFFu;
+  };
+  for (int j = j_begin; j < j_end; j++) {
+    const int gl = a0 + j;
+    const int cnt_raw = t.cand_cnt[gl], cnt = min(cnt_raw, T2_CAP);
+    const GateL L = load_gate_left(t.lgeo + 7 * (size_t)gl);
+    const size_t row = (size_t)gl * T2_CAP;
+    int out = 0;
+    for (int e0 = 0; e0 < cnt; e0 += 32) {
+      const int e = e0 + lane;
+      const bool valid = e < cnt;
+      uint32_t d2 = 0xFFFFFFFFu;
+      int col = 0, g = 0;
+      if (valid) {
+        const uint2 en = t.cand[row + e];
+        d2 = en.x;
+        col = (int)en.y;
+        const float4 l2v = t.rleq[b0 + col];
+        const float l2[3] = {l2v.x, l2v.y, l2v.z};
+        g = line_gate32(gk, L, l2, l2v.w);
+        if (check) {
+          const float* s1 = v.left_seg + 4 * (size_t)gl;
+          const bool g64 = line_pair_gate_fast(v, s1, v.left_leq + 3 * (size_t)gl, v.right_leq + 3 * (size_t)(b0 + col));
+          if (g >= 0 && (g != 0) != g64) n_bad++;
+          // observed error of T against its bound (both endpoints), in units of the bound
+          float dir[3], c1[3];
+          cross3f(L.l1, l2, dir);
+          cross3f(dir, L.l1, c1);
+          const float dd = dot3f(dir, dir);
+          for (int ep = 0; ep < 2; ep++) {
+            float T, tol2;
+            bool cond;
+            gate32_endpoint(gk, L, ep, dir, c1, dd, &T, &tol2, &cond);
+            const double T64 = gate64_T(v, s1, v.left_leq + 3 * (size_t)gl, v.right_leq + 3 * (size_t)(b0 + col), ep);
+            if (cond && tol2 > 0.f) worst = fmaxf(worst, (float)(fabs((double)T - T64) / sqrt((double)tol2)));
+          }
+        }
+      }
+      const bool keep = valid && g != 0, border = valid && g < 0;
+      const unsigned km = __ballot_sync(0xffffffffu, keep), bm = __ballot_sync(0xffffffffu, border);
+      const int pos = out + __popc(km & lt);
+      if (keep) t.cand[row + pos] = make_uint2(d2, (uint32_t)col);
+      if (border) {
+        GateQ it;
+        const size_t slot = row + pos;
+        it.slot_lo = (uint32_t)slot; it.slot_hi = (uint32_t)(slot >> 32); it.gl = gl; it.c = b0 + col;
+        q[qn + __popc(bm & lt)] = it;
+      }
+      out += __popc(km);
+      qn += __popc(bm);
+      n_border += __popc(bm);
+      __syncwarp();
+      if (qn >= 32) {
+        qn -= 32;
+        settle(q[qn + lane]);
+        __syncwarp();
+      }
     }
-    if (g) n_adm++;
-    else t.cand_d2[slot] = 0xFFFFFFFFu;
+    if (lane == 0 && cnt_raw <= T2_CAP) t.cand_cnt[gl] = (uint16_t)out;   // (an overflowed row keeps its marker: exact scan in the greedy)
+    n_listed += cnt;
   }
+  if (lane < qn) settle(q[lane]);
   if (check) {
-    if (lane == 0) atomicAdd(t.err_flag + 2, cnt);
-    if (n_adm) atomicAdd(t.err_flag + 3, n_adm);
-    if (n_border) atomicAdd(t.err_flag + 4, n_border);
+    if (lane == 0) { atomicAdd(t.err_flag + 2, n_listed); atomicAdd(t.err_flag + 4, n_border); }
     if (n_bad) atomicAdd(t.err_flag + 5, n_bad);
+    atomicMax(reinterpret_cast<unsigned*>(t.err_flag) + 6, __float_as_uint(worst));
   }
 }
 
-constexpr int G2_NE = T2_CAP / 32;
+// One warp per pair replays the sequential greedy over the compacted lists: smallest (d^2, right line) among the
+// untaken live entries of the row, two warp reductions per left line.  The first 64 entries of the next G2_PF rows are
+// kept in registers (the lists stream from HBM: ~1 us per row otherwise); longer lists read their tail on demand.
+constexpr int G2_PF = 4;
 __global__ void __launch_bounds__(32) k_line_greedy2(LineTc2View t) {
   __shared__ uint32_t taken[T2_ROWS / 32];
   const LineMatchView& v = t.v;
@@ -1072,69 +1218,77 @@ __global__ void __launch_bounds__(32) k_line_greedy2(LineTc2View t) {
   if (na == 0) return;
   if (lane < T2_ROWS / 32) taken[lane] = 0u;
   __syncwarp();
-  uint32_t nd2[G2_NE];
-  uint16_t ncol[G2_NE];
-  int ncnt = 0;
-  auto fetch = [&](int j) {
-    ncnt = t.cand_cnt[a0 + j];
-    const int tot = min(ncnt, T2_CAP);
-    const size_t o = (size_t)(a0 + j) * T2_CAP;
-#pragma unroll
-    for (int i = 0; i < G2_NE; i++) {
-      const int e = lane + 32 * i;
-      nd2[i] = 0xFFFFFFFFu;
-      ncol[i] = 0;
-      if (e < tot) { nd2[i] = t.cand_d2[o + e]; ncol[i] = t.cand_col[o + e]; }
+  uint32_t pd2[G2_PF][2];
+  uint32_t pcol[G2_PF][2];
+  int pcnt[G2_PF];
+  auto fetch = [&](int j, int u) {
+    pcnt[u] = 0;
+    pd2[u][0] = pd2[u][1] = 0xFFFFFFFFu;
+    pcol[u][0] = pcol[u][1] = 0;
+    if (j < na) {
+      pcnt[u] = t.cand_cnt[a0 + j];
+      const int tot = min(pcnt[u], T2_CAP);
+      const size_t o = (size_t)(a0 + j) * T2_CAP;
+      if (lane < tot) { const uint2 en = t.cand[o + lane]; pd2[u][0] = en.x; pcol[u][0] = en.y; }
+      if (lane + 32 < tot) { const uint2 en = t.cand[o + lane + 32]; pd2[u][1] = en.x; pcol[u][1] = en.y; }
     }
   };
-  fetch(0);
-  for (int j = 0; j < na; j++) {
-    const int cnt = ncnt;
-    uint32_t bd = 0xFFFFFFFFu, bc = 0xFFFFFFFFu;
 #pragma unroll
-    for (int i = 0; i < G2_NE; i++) {
-      const uint32_t c = ncol[i];
-      const bool live = nd2[i] != 0xFFFFFFFFu && !((taken[c >> 5] >> (c & 31)) & 1u);
-      if (live && (nd2[i] < bd || (nd2[i] == bd && c < bc))) { bd = nd2[i]; bc = c; }
-    }
-    if (j + 1 < na) fetch(j + 1);
-    int bi = -1;
-    if (cnt <= T2_CAP) {
-      const uint32_t m = __reduce_min_sync(0xffffffffu, bd);
-      if (m != 0xFFFFFFFFu) bi = (int)__reduce_min_sync(0xffffffffu, bd == m ? bc : 0xFFFFFFFFu);
-    } else {
-      if (lane == 0) atomicAdd(t.err_flag + 1, 1);
-      // overflowed list: exact scan of the row.  Pass A: lanes stride over the right lines and apply every gate of
-      // CheckLinePair; pass B: exact FP32 distances of the few admissible ones, computed by the whole warp per line.
-      const int gl = a0 + j;
-      const bool l_ok = !(v.left_len[gl] < (double)v.min_len);
-      const double* ul = v.left_un + 3 * (size_t)gl;
-      float best = INFINITY;
-      for (int cb = 0; cb < nb && l_ok; cb += 32) {
-        const int c = cb + lane;
-        bool ok = false;
-        if (c < nb && !((taken[c >> 5] >> (c & 31)) & 1u)) {
-          const int gc = b0 + c;
-          if (v.left_oct[gl] == v.right_oct[gc] && !(v.right_len[gc] < (double)v.min_len)) {
-            const double* un = v.right_un + 3 * (size_t)gc;
-            if (!(fabs(ul[0] * un[0] + ul[1] * un[1] + ul[2] * un[2]) > 0.975))
-              ok = line_pair_gate(v, v.left_seg + 4 * (size_t)gl, v.left_leq + 3 * (size_t)gl, v.right_leq + 3 * (size_t)gc);
+  for (int u = 0; u < G2_PF; u++) fetch(u, u);
+  for (int jb = 0; jb < na; jb += G2_PF) {
+#pragma unroll
+    for (int u = 0; u < G2_PF; u++) {
+      const int j = jb + u;
+      if (j >= na) break;
+      const int cnt = pcnt[u];
+      uint32_t bd = 0xFFFFFFFFu, bc = 0xFFFFFFFFu;
+      auto offer = [&](uint32_t d2, uint32_t c) {
+        const bool live = d2 != 0xFFFFFFFFu && !((taken[c >> 5] >> (c & 31)) & 1u);
+        if (live && (d2 < bd || (d2 == bd && c < bc))) { bd = d2; bc = c; }
+      };
+      offer(pd2[u][0], pcol[u][0]);
+      offer(pd2[u][1], pcol[u][1]);
+      fetch(j + G2_PF, u);
+      int bi = -1;
+      if (cnt <= T2_CAP) {
+        const size_t o = (size_t)(a0 + j) * T2_CAP;
+        for (int e = 64 + lane; e < cnt; e += 32) { const uint2 en = t.cand[o + e]; offer(en.x, en.y); }
+        const uint32_t m = __reduce_min_sync(0xffffffffu, bd);
+        if (m != 0xFFFFFFFFu) bi = (int)__reduce_min_sync(0xffffffffu, bd == m ? bc : 0xFFFFFFFFu);
+      } else {
+        if (lane == 0) atomicAdd(t.err_flag + 1, 1);
+        // overflowed list: exact scan of the row.  Pass A: lanes stride over the right lines and apply every gate of
+        // CheckLinePair; pass B: exact FP32 distances of the few admissible ones, computed by the whole warp per line.
+        const int gl = a0 + j;
+        const bool l_ok = !(v.left_len[gl] < (double)v.min_len);
+        const double* ul = v.left_un + 3 * (size_t)gl;
+        float best = INFINITY;
+        for (int cb = 0; cb < nb && l_ok; cb += 32) {
+          const int c = cb + lane;
+          bool ok = false;
+          if (c < nb && !((taken[c >> 5] >> (c & 31)) & 1u)) {
+            const int gc = b0 + c;
+            if (v.left_oct[gl] == v.right_oct[gc] && !(v.right_len[gc] < (double)v.min_len)) {
+              const double* un = v.right_un + 3 * (size_t)gc;
+              if (!(fabs(ul[0] * un[0] + ul[1] * un[1] + ul[2] * un[2]) > 0.975))
+                ok = line_pair_gate(v, v.left_seg + 4 * (size_t)gl, v.left_leq + 3 * (size_t)gl, v.right_leq + 3 * (size_t)gc);
+            }
+          }
+          unsigned mm = __ballot_sync(0xffffffffu, ok);
+          while (mm) {  // ascending column order, strict <: the first minimum wins as in the reference
+            const int c2 = cb + __ffs(mm) - 1;
+            mm &= mm - 1;
+            const float d = sqrtf(warp_exact_d2(v.left_desc + (size_t)gl * v.D, v.right_desc + (size_t)(b0 + c2) * v.D, v.D, lane));
+            if ((double)d < v.tau && d < best) { best = d; bi = c2; }
           }
         }
-        unsigned mm = __ballot_sync(0xffffffffu, ok);
-        while (mm) {  // ascending column order, strict <: the first minimum wins as in the reference
-          const int c2 = cb + __ffs(mm) - 1;
-          mm &= mm - 1;
-          const float d = sqrtf(warp_exact_d2(v.left_desc + (size_t)gl * v.D, v.right_desc + (size_t)(b0 + c2) * v.D, v.D, lane));
-          if ((double)d < v.tau && d < best) { best = d; bi = c2; }
-        }
       }
+      if (lane == 0) {
+        v.match[a0 + j] = bi;
+        if (bi >= 0) taken[bi >> 5] |= 1u << (bi & 31);
+      }
+      __syncwarp();
     }
-    if (lane == 0) {
-      v.match[a0 + j] = bi;
-      if (bi >= 0) taken[bi >> 5] |= 1u << (bi & 31);
-    }
-    __syncwarp();
   }
 }
 
@@ -1251,14 +1405,15 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
     LineTc2View t;
     t.v = v;
     t.nl_chunk = v.D <= 64 ? 256 : 128;
+    t.dbg = getenv("LLD_LINE_DBG") ? atoi(getenv("LLD_LINE_DBG")) : 0;
     UPM(t.lrec, float4, nullptr, n_left);
     UPM(t.rrec, float4, nullptr, n_right);
     UPM(t.loct, int8_t, nullptr, n_left);
     UPM(t.roct, int8_t, nullptr, n_right);
-    UPM(t.lleq, float4, nullptr, n_left);
+    UPM(t.lgeo, float4, nullptr, 7 * (size_t)n_left);
     UPM(t.rleq, float4, nullptr, n_right);
-    UPM(t.cand_d2, uint32_t, nullptr, (size_t)n_left * T2_CAP);
-    UPM(t.cand_col, uint16_t, nullptr, (size_t)n_left * T2_CAP);
+    UPM(t.rh, float, nullptr, n_right);
+    UPM(t.cand, uint2, nullptr, (size_t)n_left * T2_CAP);
     UPM(t.cand_cnt, uint16_t, nullptr, n_left);
     UPM(t.err_flag, int, nullptr, 8);
     d_tc_err = t.err_flag;
@@ -1269,14 +1424,19 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
     LLD_CUDA(c, lld_raise_dyn_smem(k_line_tc2, (size_t)(int)smem));
     GateK gk;
     double kn = 0;
-    for (int i = 0; i < 9; i++) { gk.K[i] = (float)v.K[i]; kn += v.K[i] * v.K[i]; }
-    gk.kn = (float)sqrt(kn);
+    for (int i = 0; i < 9; i++) kn += v.K[i] * v.K[i];
+    gk.kn2 = (float)kn;
+    double c_tol = 2e-6;   // k eps with k = 32; check runs report the largest observed error in units of the bound (err_flag[6])
+    if (const char* e_c = getenv("LLD_LINE_CTOL")) c_tol = atof(e_c);
+    gk.c_tol2 = (float)(36.0 * c_tol * c_tol);
     const int check = getenv("LLD_LINE_CHECK") != nullptr || getenv("LLD_LINE_STATS") != nullptr;
     const int swap_grid = P > 65535;
     const dim3 grid_rows = swap_grid ? dim3(P, cdiv(max_na, 8)) : dim3(cdiv(max_na, 8), P);
+    const int gate_blocks = cdiv(max_na, G32_ROWS * G32_WARPS);
+    const dim3 grid_gate = swap_grid ? dim3(P, gate_blocks) : dim3(gate_blocks, P);
     LLD_LAUNCH(c, k_line_prep2, cdiv(8 * (n_left + n_right), 256), 256, 0, t, n_left, n_right);
     LLD_LAUNCH(c, k_line_tc2, std::min(P, c->sm_count), T2_NT, smem, t);
-    LLD_LAUNCH(c, k_line_gate32, grid_rows, 256, 0, t, gk, swap_grid, check);
+    LLD_LAUNCH(c, k_line_gate32, grid_gate, 32 * G32_WARPS, 0, t, gk, swap_grid, check);
     LLD_LAUNCH(c, k_line_greedy2, P, 32, 0, t);
     LLD_LAUNCH(c, k_line_exact2, grid_rows, 256, 0, t, swap_grid);
   } else if (use_tc) {
@@ -1374,8 +1534,8 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
     fprintf(stderr, "[lld_line_match] fallback rows %d, listed candidates %d, geometrically admissible %d, max |d2_tc - d2_exact| %.3e\n",
             h_err[1], h_err[2], h_err[3], (double)*reinterpret_cast<float*>(h_err + 4));
   if (getenv("LLD_LINE_STATS") && d_tc_err && use_tc2)
-    fprintf(stderr, "[lld_line_match] fallback rows %d, listed candidates %d, admissible %d, decided in FP64 %d, FP32/FP64 disagreements %d\n",
-            h_err[1], h_err[2], h_err[3], h_err[4], h_err[5]);
+    fprintf(stderr, "[lld_line_match] fallback rows %d, listed candidates %d, decided in FP64 %d, FP32/FP64 disagreements %d, largest FP32 error / bound %.3g\n",
+            h_err[1], h_err[2], h_err[4], h_err[5], (double)*reinterpret_cast<float*>(h_err + 6));
   if (use_tc2 && h_err[5]) {
     snprintf(c->err, sizeof(c->err), "line matcher: %d FP32 gate decisions differ from FP64 (LLD_LINE_CHECK)", h_err[5]);
     return LLD_ERR_CUDA;
