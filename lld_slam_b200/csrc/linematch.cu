@@ -5,8 +5,8 @@
 // The descriptor distance LineMatcher::MatchLineDescriptors lives in the un-vendored LBDMOD library
 // (un-vendored and unpinned, so parity is unpinned): defined here as the L2 norm of the float rows.
 //
-// Two device plans per stereo pair: the tensor-core path below (tcgen05, default: D multiple of 8 up to 72 floats and
-// <= 512 right lines) and the FP32 tile path for everything else:
+// Two device plans per batch: the tensor-core path further down (tcgen05, default: D multiple of 8 up to 72 floats and
+// <= 512 lines per side of a pair) and the FP32 tile path for everything else:
 //   k_line_prep   : per line, K^T-normalised image line equation, unit plane normal and pixel length
 //   k_line_dist   : 32x32 tiles of the (left x right) pair matrix; descriptors staged in shared memory, dense
 //                   ||a-b||^2 contraction in FP32, fused epilogue = the geometric gates of CheckLinePair
@@ -15,7 +15,8 @@
 //   k_line_greedy : one warp per pair replays the reference's sequential greedy assignment (left lines in index
 //                   order, first minimum wins, matched right lines are removed)
 // Tolerance (stated, because LBDMOD is unpinned): |d_gpu - d_oracle| <= 1e-5 * max(1, d); identical matches unless
-// the two best candidates of a row are closer than that.
+// the two best candidates of a row are closer than that.  (The tensor-core path ranks by 3xTF32 distances, |error| ~ 1e-6
+// in d^2, and reports exact FP32 distances.)
 #include <cfloat>
 #include <cstdlib>
 #include <vector>
@@ -53,7 +54,18 @@ struct LineMatchView {
   float* mdist;
 };
 
-__global__ void k_line_prep(LineMatchView v, int n_left, int n_right) {
+// FP32 records of the second-generation tensor-core path (formed here, where the FP64 values are in registers)
+struct LineRecs {
+  float4* lrec;    // [n_left]  {|a|^2 (filled by k_line_prep2), unit plane normal}
+  float4* rrec;    // [n_right] {|b|^2 (filled by k_line_prep2), unit plane normal}
+  float* rh;       // [n_right] |X0| >= 1/2  <=>  parallax cosine >= rh
+  int8_t* loct;    // [n_left]  octave, -2 when the line is too short
+  int8_t* roct;    // [n_right] octave, -1 when the line is too short
+  float4* rleq;    // [n_right] {K^T l normalised, beta = l_x * baseline}
+  float4* lgeo;    // [n_left][7] {l1, |l1|^2}, {-, |a0|^2, |a1|^2, -}, M0 | M1 with M = [a]_x K per endpoint a
+};
+template <bool WITH_RECS>
+__global__ void k_line_prep(LineMatchView v, LineRecs t, int n_left, int n_right) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   for (int side = 0; side < 2; side++) {
     const int n = side ? n_right : n_left;
@@ -71,7 +83,46 @@ __global__ void k_line_prep(LineMatchView v, int n_left, int n_right) {
     double* u = (side ? v.right_un : v.left_un) + 3 * (size_t)i;
     u[0] = o[0] / n3; u[1] = o[1] / n3; u[2] = o[2] / n3;
     const double dx = (double)s[0] - (double)s[2], dy = (double)s[1] - (double)s[3];
-    (side ? v.right_len : v.left_len)[i] = sqrt(dx * dx + dy * dy);
+    const double len = sqrt(dx * dx + dy * dy);
+    (side ? v.right_len : v.left_len)[i] = len;
+    if (WITH_RECS) {
+      const bool too_short = len < (double)v.min_len;
+      const int oct = min(max((side ? v.right_oct : v.left_oct)[i], 0), 127);
+      const double l1sq = o[0] * o[0] + o[1] * o[1] + o[2] * o[2];
+      if (side) {
+        // |X0|^2 = beta^2 |l1|^2 / |l1 x l2|^2 and |l1 x l2|^2 = |l1|^2 |l2|^2 (1 - cs^2) with cs the cosine between the
+        // unit normals: |X0| >= 1/2  <=>  cs^2 >= 1 - 4 beta^2 / |l2|^2, a per-right-line bound the selectors test for free
+        const double beta = o[0] * v.baseline;
+        float* rr = reinterpret_cast<float*>(t.rrec + i);
+        rr[1] = (float)u[0]; rr[2] = (float)u[1]; rr[3] = (float)u[2];
+        t.rh[i] = (float)sqrt(fmax(0.0, 1.0 - 4.0 * beta * beta / l1sq));
+        t.roct[i] = (int8_t)(too_short ? -1 : oct);
+        t.rleq[i] = make_float4((float)o[0], (float)o[1], (float)o[2], (float)beta);
+      } else {
+        float* lr = reinterpret_cast<float*>(t.lrec + i);
+        lr[1] = (float)u[0]; lr[2] = (float)u[1]; lr[3] = (float)u[2];
+        t.loct[i] = (int8_t)(too_short ? -2 : oct);
+        float m[20], aa[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const double a[3] = {s[2 * e], s[2 * e + 1], 1.0};
+          const double* K = v.K;
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) {   // [a]_x K, column cc
+            m[9 * e + 0 + cc] = (float)(-a[2] * K[3 + cc] + a[1] * K[6 + cc]);
+            m[9 * e + 3 + cc] = (float)(a[2] * K[cc] - a[0] * K[6 + cc]);
+            m[9 * e + 6 + cc] = (float)(-a[1] * K[cc] + a[0] * K[3 + cc]);
+          }
+          aa[e] = (float)(a[0] * a[0] + a[1] * a[1] + 1.0);
+        }
+        m[18] = m[19] = 0.f;
+        float4* g = t.lgeo + 7 * (size_t)i;
+        g[0] = make_float4((float)o[0], (float)o[1], (float)o[2], (float)l1sq);
+        g[1] = make_float4(0.f, aa[0], aa[1], 0.f);
+#pragma unroll
+        for (int k = 0; k < 5; k++) g[2 + k] = make_float4(m[4 * k], m[4 * k + 1], m[4 * k + 2], m[4 * k + 3]);
+      }
+    }
   }
 }
 
@@ -221,27 +272,7 @@ __global__ void __launch_bounds__(32) k_line_greedy(LineMatchView v, int* taken_
 }
 
 
-// ================================================================================================
-// Tensor-core path (sm_100a tcgen05): the left x right descriptor contraction of one 128-row block of a stereo pair
-// as 3xTF32 UMMAs (a = a_hi + a_lo, a.b ~ a_hi.b_hi + a_hi.b_lo + a_lo.b_hi, fp32 accumulation in TMEM), with the
-// candidate selection fused into the TMEM epilogue:
-//   k_line_tc    : CTA = (pair, 128 left lines); descriptors split into TF32 hi / lo parts while being staged into the
-//                  canonical K-major no-swizzle UMMA layout in shared memory; D[128 x 512] fp32 lives in TMEM (all 512
-//                  columns); epilogue thread = (row, column half): d^2 = |a|^2 + |b|^2 - 2 a.b, cheap gates of
-//                  CheckLinePair (octave, lengths, tau) and the parallax test of vgl::TriangulateLine, survivors appended
-//                  to the row's candidate list (<= 128 per column half, in column order)
-//   k_line_greedy_lazy : one warp per pair replays the sequential greedy; the FP64 geometry (triangulation, |X0|,
-//                  endpoint depths) is evaluated lazily, smallest keys first, until no unexamined key can win; a row
-//                  whose list overflowed takes an exact scan of the pair
-//   k_line_exact : the distance reported for a match is recomputed exactly in FP32 from the descriptors
-//   k_line_gate  : exhaustive gate pass, statistics runs only (LLD_LINE_STATS)
-// The ranking uses the 3xTF32 distances (|error| ~ 1e-6 in d^2), the reported distances are exact: within the stated
-// tolerance 1e-5 * max(1, d), identical matches unless two candidates are closer than that.
-// ================================================================================================
-constexpr int TC_ROWS = 128, TC_HALF = 256, TC_COLS = 512, TC_K = 8, TC_NT = 256;
-constexpr int TC_HCAP = 128, TC_CAND = 2 * TC_HCAP;  // candidate slots per (row, column half) / per row
-constexpr int TC_AW = TC_CAND / 32;                  // admissibility mask words per row
-
+// ---- tcgen05 / TMEM / mbarrier helpers of the tensor-core path
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t to_tf32(float x) {
   uint32_t r;
@@ -281,235 +312,6 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])   \
                : "r"(taddr))
 
-struct LineTcView {
-  LineMatchView v;
-  const int* tile_pair;   // [n_tiles]
-  const int* tile_r;      // [n_tiles] 128-row block inside the pair
-  uint32_t* cand_d2;      // [n_left][TC_CAND] float bits of the 3xTF32 squared distance; slots [HCAP h, HCAP h + cnt[h]) of column half h
-  uint16_t* cand_col;     // [n_left][TC_CAND] pair-local right line
-  uint16_t* cand_cnt;     // [n_left][2] candidates per column half that pass the cheap gates and the parallax test (> HCAP: overflow)
-  uint32_t* cand_adm;     // [n_left][TC_AW] bit k: candidate slot k passes the remaining geometric gates
-  int* err_flag;          // [4] 0: a tensor-core completion barrier timed out; 1: rows that took the exact fallback scan;
-                          //     2: listed candidates; 3: listed candidates passing the geometric gates
-};
-
-// stage `rows` descriptors (global row-major fp32, D multiple of 8) as TF32 hi / lo parts into the UMMA K-major layout:
-// element (r, k) at (r/8) * sbo + (k/4) * 128 + (r%8) * 16 + (k%4) * 4 ; a warp writes 512 contiguous bytes per step
-__device__ __forceinline__ void stage_split(const float* __restrict__ g, int n_valid, int rows, int D, uint8_t* hi, uint8_t* lo) {
-  const int chunks = D >> 2, sbo = chunks * 128;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int r_in = lane & 7, c_in = lane >> 3;  // 8 rows x 4 chunks per warp step
-  const int n_groups = rows >> 3, quads = (chunks + 3) >> 2;
-  // warp w takes row groups w, w + nw, ...; inside a group it walks the quads of four 16 B chunks
-  for (int rg = wid; rg < n_groups; rg += nw) {
-    const int r = rg * 8 + r_in;
-    const float* grow = g + (size_t)r * D;
-    const bool rv = r < n_valid;
-    for (int cq = 0; cq < quads; cq += 2) {
-      const int kc0 = cq * 4 + c_in, kc1 = kc0 + 4;
-      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-      if (rv && kc0 < chunks) x0 = *reinterpret_cast<const float4*>(grow + 4 * kc0);
-      if (rv && kc1 < chunks && cq + 1 < quads) x1 = *reinterpret_cast<const float4*>(grow + 4 * kc1);
-#pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const int kc = u ? kc1 : kc0;
-        if (kc >= chunks || (u && cq + 1 >= quads)) continue;
-        const float4 x = u ? x1 : x0;
-        uint4 h, l;
-        h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
-        l.x = to_tf32(x.x - __uint_as_float(h.x)); l.y = to_tf32(x.y - __uint_as_float(h.y));
-        l.z = to_tf32(x.z - __uint_as_float(h.z)); l.w = to_tf32(x.w - __uint_as_float(h.w));
-        const int off = rg * sbo + kc * 128 + r_in * 16;
-        *reinterpret_cast<uint4*>(hi + off) = h;
-        *reinterpret_cast<uint4*>(lo + off) = l;
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(TC_NT, 1) k_line_tc(LineTcView t) {
-  extern __shared__ __align__(1024) uint8_t tsm[];
-  const LineMatchView& v = t.v;
-  const int p = t.tile_pair[blockIdx.x];
-  const int a0 = v.left_off[p], na = v.left_off[p + 1] - a0;
-  const int b0 = v.right_off[p], nb = v.right_off[p + 1] - b0;
-  const int r0 = t.tile_r[blockIdx.x] * TC_ROWS;
-  const int D = v.D, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-  const int a_bytes = TC_ROWS * D * 4, b_bytes = TC_HALF * D * 4;
-  uint8_t* A_hi = tsm;
-  uint8_t* A_lo = A_hi + a_bytes;
-  uint8_t* B_hi = A_lo + a_bytes;
-  uint8_t* B_lo = B_hi + b_bytes;
-  float4* colv = reinterpret_cast<float4*>(B_lo + b_bytes);   // [512] {|b|^2, unit plane normal of the right line (FP32)}
-  int8_t* colm = reinterpret_cast<int8_t*>(colv + TC_COLS);   // [512] octave of the right line, -1 = not a candidate
-  uint64_t* bar = reinterpret_cast<uint64_t*>(colm + TC_COLS);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-
-  if (wid == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(1));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::);
-  }
-  // per-column data of the cheap gates and |b|^2 (one thread per right line, two rounds)
-  for (int c = tid; c < TC_COLS; c += TC_NT) {
-    float s2 = 0.f;
-    int m = -1;
-    float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < nb) {
-      const float* g = v.right_desc + (size_t)(b0 + c) * D;
-      for (int k = 0; k < D; k += 4) {
-        const float4 x = *reinterpret_cast<const float4*>(g + k);
-        s2 = fmaf(x.x, x.x, s2); s2 = fmaf(x.y, x.y, s2); s2 = fmaf(x.z, x.z, s2); s2 = fmaf(x.w, x.w, s2);
-      }
-      if (!(v.right_len[b0 + c] < (double)v.min_len)) m = (int8_t)min(v.right_oct[b0 + c], 127);
-      const double* un = v.right_un + 3 * (size_t)(b0 + c);
-      cv = make_float4(s2, (float)un[0], (float)un[1], (float)un[2]);
-    }
-    colv[c] = cv;
-    colm[c] = (int8_t)m;
-  }
-  stage_split(v.left_desc + (size_t)(a0 + r0) * D, na - r0, TC_ROWS, D, A_hi, A_lo);
-  asm volatile("tcgen05.fence::before_thread_sync;" ::);
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::);
-  const uint32_t tmem = *tmem_slot;
-  // instruction descriptor: D fp32, A / B TF32, both K-major, N = 256, M = 128  (cute::UMMA::InstrDescriptor)
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_HALF >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
-  const uint32_t sbo = (uint32_t)(D >> 2) * 128u;
-  for (int h = 0; h < 2; h++) {
-    if (h * TC_HALF < nb) {
-      stage_split(v.right_desc + (size_t)(b0 + h * TC_HALF) * D, nb - h * TC_HALF, TC_HALF, D, B_hi, B_lo);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
-      __syncthreads();
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::);
-        const uint32_t d_tmem = tmem + (uint32_t)(h * TC_HALF);
-        uint32_t acc = 0;
-        for (int ks = 0; ks < D / TC_K; ks++) {
-          const uint32_t koff = (uint32_t)ks * 256u;  // two 16 B chunks x 128 B per k-step
-          const uint64_t ah = umma_desc(smem_u32(A_hi) + koff, 128, sbo), al = umma_desc(smem_u32(A_lo) + koff, 128, sbo);
-          const uint64_t bh = umma_desc(smem_u32(B_hi) + koff, 128, sbo), bl = umma_desc(smem_u32(B_lo) + koff, 128, sbo);
-          umma_tf32(d_tmem, ah, bh, idesc, acc);
-          umma_tf32(d_tmem, ah, bl, idesc, 1);
-          umma_tf32(d_tmem, al, bh, idesc, 1);
-          acc = 1;
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-      }
-      // the MMAs have read B: the buffer may be refilled, D is complete
-      if (!mbar_wait(smem_u32(bar), (uint32_t)(h & 1)) && tid == 0) atomicExch(t.err_flag, 1);
-    }
-  }
-  asm volatile("tcgen05.fence::after_thread_sync;" ::);
-
-  // ---- epilogue: thread = (row = 32 * (warp % 4) + lane, column half = warp / 4)
-  const int q = wid & 3, ch = wid >> 2;
-  const int row = 32 * q + lane, gr = r0 + row;
-  const bool row_ok = gr < na;
-  float na2 = 0.f;
-  int octl = -2;
-  if (row_ok) {
-    const float* g = v.left_desc + (size_t)(a0 + gr) * D;
-    for (int k = 0; k < D; k += 4) {
-      const float4 x = *reinterpret_cast<const float4*>(g + k);
-      na2 = fmaf(x.x, x.x, na2); na2 = fmaf(x.y, x.y, na2); na2 = fmaf(x.z, x.z, na2); na2 = fmaf(x.w, x.w, na2);
-    }
-    if (!(v.left_len[a0 + gr] < (double)v.min_len)) octl = min(v.left_oct[a0 + gr], 127);
-  }
-  const float tau2 = (float)(v.tau * v.tau);
-  double ul0 = 0, ul1 = 0, ul2 = 0;
-  if (row_ok) {
-    const double* u = v.left_un + 3 * (size_t)(a0 + gr);
-    ul0 = u[0]; ul1 = u[1]; ul2 = u[2];
-  }
-  const float fl0 = (float)ul0, fl1 = (float)ul1, fl2 = (float)ul2;
-  // candidates of this (row, column half): cheap gates of CheckLinePair + the parallax test of vgl::TriangulateLine
-  // (src/vgl.cc:84), appended in column order; the remaining FP64 geometry runs in k_line_gate over the lists.
-  // The parallax test is decided in FP32 from shared memory unless it is within 1e-5 of the threshold (then FP64, as the
-  // reference computes it); the per-column work is branch-free, only the append diverges.
-  int cnt = 0;
-  const size_t o = row_ok ? (size_t)(a0 + gr) * TC_CAND + (size_t)ch * TC_HCAP : 0;
-  if (ch * TC_HALF < nb) {
-    for (int cb = 0; cb < TC_HALF; cb += 32) {
-      const int c_base = ch * TC_HALF + cb;
-      if (c_base >= nb) break;  // warp-uniform
-      uint32_t r[32];
-      TMEM_LD32(r, tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c_base);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int j = 0; j < 32; j++) {
-        const int c = c_base + j;
-        const float4 cv = colv[c];
-        const float d2 = fmaxf(na2 + cv.x - 2.f * __uint_as_float(r[j]), 0.f);
-        const float cs = fabsf(fmaf(fl0, cv.y, fmaf(fl1, cv.z, fl2 * cv.w)));
-        bool pass = ((int)colm[c] == octl) & (d2 < tau2) & !(cs > 0.975f + 1e-5f);
-        if (pass && cs > 0.975f - 1e-5f) {  // borderline: decide in FP64
-          const double* un = v.right_un + 3 * (size_t)(b0 + c);
-          pass = !(fabs(ul0 * un[0] + ul1 * un[1] + ul2 * un[2]) > 0.975);
-        }
-        if (pass) {
-          if (cnt < TC_HCAP) {
-            t.cand_d2[o + cnt] = __float_as_uint(d2);
-            t.cand_col[o + cnt] = (uint16_t)c;
-          }
-          cnt++;
-        }
-      }
-    }
-  }
-  if (row_ok) t.cand_cnt[2 * (size_t)(a0 + gr) + ch] = (uint16_t)min(cnt, TC_HCAP + 1);
-  asm volatile("tcgen05.fence::before_thread_sync;" ::);
-  __syncthreads();
-  if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_COLS));
-}
-
-// remaining geometric gates of CheckLinePair (triangulation, |X0|, endpoint depths; FP64) over the candidate lists:
-// half a warp per left line, lanes stride over the listed slots of both column halves as one sequence; admissible slots
-// set their bit in the row's mask.  (Bench workload: ~150 listed and ~30 admissible candidates per line.)
-__global__ void __launch_bounds__(256) k_line_gate(LineTcView t, int n_left, int stats) {
-  const LineMatchView& v = t.v;
-  const int hw = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, sl = threadIdx.x & 15;
-  const int i = hw;
-  if (i >= n_left) return;
-  int lo = 0, hi = v.n_pairs;  // right lines are pair-local: the pair of left line i
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (v.left_off[mid] <= i) lo = mid;
-    else hi = mid;
-  }
-  const int b0 = v.right_off[lo];
-  const int cnt0 = min((int)t.cand_cnt[2 * (size_t)i], TC_HCAP), cnt1 = min((int)t.cand_cnt[2 * (size_t)i + 1], TC_HCAP);
-  const int tot = cnt0 + cnt1;
-  int n_adm = 0;
-  for (int e = sl; e < tot; e += 16) {
-    const int k = e < cnt0 ? e : TC_HCAP + (e - cnt0);
-    const size_t slot = (size_t)i * TC_CAND + k;
-    const int c = b0 + t.cand_col[slot];
-    const bool adm = line_pair_gate(v, v.left_seg + 4 * (size_t)i, v.left_leq + 3 * (size_t)i, v.right_leq + 3 * (size_t)c);
-    if (adm) {
-      atomicOr(&t.cand_adm[(size_t)i * TC_AW + (k >> 5)], 1u << (k & 31));
-      n_adm++;
-    }
-    if (stats) {  // diagnostic: largest |3xTF32 - exact FP32| squared distance over the listed candidates
-      const float* da = v.left_desc + (size_t)i * v.D;
-      const float* db = v.right_desc + (size_t)c * v.D;
-      float s2 = 0.f;
-      for (int q = 0; q < v.D; q++) {
-        const float df = da[q] - db[q];
-        s2 = fmaf(df, df, s2);
-      }
-      atomicMax(reinterpret_cast<unsigned*>(t.err_flag) + 4, __float_as_uint(fabsf(s2 - __uint_as_float(t.cand_d2[slot]))));
-    }
-  }
-  if (stats) {
-    if (sl == 0) atomicAdd(t.err_flag + 2, tot);
-    if (n_adm) atomicAdd(t.err_flag + 3, n_adm);
-  }
-}
-
 // exact squared distance of one (left, right) pair by a warp (FP32, difference form)
 __device__ __forceinline__ float warp_exact_d2(const float* a, const float* b, int D, int lane) {
   float s2 = 0.f;
@@ -522,165 +324,20 @@ __device__ __forceinline__ float warp_exact_d2(const float* a, const float* b, i
   return s2;
 }
 
-// One warp per pair replays the sequential greedy of MatchLines with LAZY geometry: a line's listed candidates (cheap
-// gates + parallax test passed, ~150 per line in the bench workload) are held one per lane and slot; taken right lines
-// drop out first; then every lane offers its smallest unexamined key, all offers below the best admissible key found so
-// far are put through the FP64 gates at once, and the loop ends when no lane can beat that key.  The result is the
-// smallest admissible untaken key, exactly as an exhaustive evaluation would give it, with ~40 gate evaluations per line
-// instead of ~150 (k_line_gate remains for the statistics run).  The next line's list is prefetched meanwhile.
-// The kernel handles the left lines [j_begin, j_end) of every pair and keeps the pair's "taken" mask in global memory in
-// between, so that the host can launch it once per 128-row block as soon as k_line_tc has produced that block's lists
-// (the contraction of block r + 1 then runs under the greedy of block r: the greedy CTAs are one warp with 64 B of
-// shared memory, so several of them fit beside a k_line_tc CTA on every SM).
-constexpr int GL_NE = TC_CAND / 32;   // list entries per lane
-constexpr int GL_WARPS = 1;           // pairs per CTA
-__global__ void __launch_bounds__(32 * GL_WARPS) k_line_greedy_lazy(LineTcView t, int j_begin, int j_end, uint32_t* __restrict__ taken_g) {
-  __shared__ uint32_t s_taken[GL_WARPS][TC_COLS / 32];
-  const LineMatchView& v = t.v;
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = blockIdx.x * GL_WARPS + wid;
-  if (p >= v.n_pairs) return;
-  const int a0 = v.left_off[p], na_all = v.left_off[p + 1] - a0;
-  const int b0 = v.right_off[p], nb = v.right_off[p + 1] - b0;
-  const int na = min(na_all, j_end);
-  if (j_begin >= na) return;
-  uint32_t* taken = s_taken[wid];
-  if (lane < TC_COLS / 32) taken[lane] = j_begin == 0 ? 0u : taken_g[(size_t)p * (TC_COLS / 32) + lane];
-  const double* rleq = v.right_leq + 3 * (size_t)b0;   // (staging these 12 KB in shared memory bought nothing and left room
-  __syncwarp();                                        //  for only one greedy CTA beside a k_line_tc CTA: measured)
-  // entry e = lane + 32 i of the line's list, in the order (column half 0 slots, column half 1 slots)
-  uint32_t nd2[GL_NE];
-  uint16_t ncol[GL_NE];
-  int ncnt0 = 0, ncnt1 = 0;
-  auto fetch = [&](int j) {
-    ncnt0 = t.cand_cnt[2 * (size_t)(a0 + j)];
-    ncnt1 = t.cand_cnt[2 * (size_t)(a0 + j) + 1];
-    const int c0 = min(ncnt0, TC_HCAP), tot = c0 + min(ncnt1, TC_HCAP);
-    const size_t o = (size_t)(a0 + j) * TC_CAND;
-#pragma unroll
-    for (int i = 0; i < GL_NE; i++) {
-      const int e = lane + 32 * i;
-      nd2[i] = 0xFFFFFFFFu;
-      ncol[i] = 0;
-      if (e < tot) {
-        const int k = e < c0 ? e : TC_HCAP + (e - c0);
-        nd2[i] = t.cand_d2[o + k];
-        ncol[i] = t.cand_col[o + k];
-      }
-    }
-  };
-  fetch(j_begin);
-  for (int j = j_begin; j < na; j++) {
-    unsigned long long ke[GL_NE];
-    const int cnt0 = ncnt0, cnt1 = ncnt1;
-#pragma unroll
-    for (int i = 0; i < GL_NE; i++) {
-      const int c = ncol[i];
-      const bool live = nd2[i] != 0xFFFFFFFFu && !((taken[c >> 5] >> (c & 31)) & 1u);
-      ke[i] = live ? (((unsigned long long)nd2[i] << 16) | (unsigned long long)c) : ~0ull;
-    }
-    if (j + 1 < na) fetch(j + 1);
-    int bi = -1;
-    if (cnt0 <= TC_HCAP && cnt1 <= TC_HCAP) {
-      const int gl = a0 + j;
-      unsigned long long prev = 0, W = ~0ull;   // keys are > 0 unless d2 == 0 and column 0: handled by the first-round flag
-      bool first = true, done = false;
-      for (;;) {
-        unsigned long long cand = ~0ull;
-        if (!done) {
-#pragma unroll
-          for (int i = 0; i < GL_NE; i++)
-            if ((first || ke[i] > prev) && ke[i] < cand) cand = ke[i];
-        }
-        const bool act = cand < W;
-        if (!__any_sync(0xffffffffu, act)) break;
-        unsigned long long mine = ~0ull;
-        if (act) {
-          if (line_pair_gate_fast(v, v.left_seg + 4 * (size_t)gl, v.left_leq + 3 * (size_t)gl, rleq + 3 * (int)(cand & 0xFFFFull))) {
-            mine = cand;
-            done = true;   // this lane's later keys are larger
-          }
-          prev = cand;
-          first = false;
-        } else {
-          done = true;     // nothing below W left on this lane (W only decreases)
-        }
-#pragma unroll
-        for (int o2 = 16; o2 > 0; o2 >>= 1) {
-          const unsigned long long u = __shfl_xor_sync(0xffffffffu, mine, o2);
-          mine = u < mine ? u : mine;
-        }
-        W = mine < W ? mine : W;
-      }
-      if (W != ~0ull) bi = (int)(W & 0xFFFFull);
-    } else {
-      if (lane == 0) atomicAdd(t.err_flag + 1, 1);
-      // overflowed list: exact scan of the row.  Pass A: lanes stride over the right lines and apply every gate of
-      // CheckLinePair; pass B: exact FP32 distances of the few admissible ones, computed by the whole warp per line.
-      const int gl = a0 + j;
-      const bool l_ok = !(v.left_len[gl] < (double)v.min_len);
-      const double* ul = v.left_un + 3 * (size_t)gl;
-      float best = INFINITY;
-      for (int cb = 0; cb < nb && l_ok; cb += 32) {
-        const int c = cb + lane;
-        bool ok = false;
-        if (c < nb && !((taken[c >> 5] >> (c & 31)) & 1u)) {
-          const int gc = b0 + c;
-          if (v.left_oct[gl] == v.right_oct[gc] && !(v.right_len[gc] < (double)v.min_len)) {
-            const double* un = v.right_un + 3 * (size_t)gc;
-            if (!(fabs(ul[0] * un[0] + ul[1] * un[1] + ul[2] * un[2]) > 0.975))
-              ok = line_pair_gate(v, v.left_seg + 4 * (size_t)gl, v.left_leq + 3 * (size_t)gl, v.right_leq + 3 * (size_t)gc);
-          }
-        }
-        unsigned m = __ballot_sync(0xffffffffu, ok);
-        while (m) {  // ascending column order, strict <: the first minimum wins as in the reference
-          const int c2 = cb + __ffs(m) - 1;
-          m &= m - 1;
-          const float d = sqrtf(warp_exact_d2(v.left_desc + (size_t)gl * v.D, v.right_desc + (size_t)(b0 + c2) * v.D, v.D, lane));
-          if ((double)d < v.tau && d < best) { best = d; bi = c2; }
-        }
-      }
-    }
-    if (lane == 0) {
-      v.match[a0 + j] = bi;
-      if (bi >= 0) taken[bi >> 5] |= 1u << (bi & 31);
-    }
-    __syncwarp();
-  }
-  if (lane < TC_COLS / 32) taken_g[(size_t)p * (TC_COLS / 32) + lane] = taken[lane];
-}
-
-// exact distance of every match (FP32, difference form, as the tile path reports it): one warp per left line
-__global__ void __launch_bounds__(256) k_line_exact(LineTcView t, int n_left) {
-  const LineMatchView& v = t.v;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (i >= n_left) return;
-  const int bi = v.match[i];
-  float d = INFINITY;
-  if (bi >= 0) {
-    int lo = 0, hi = v.n_pairs;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (v.left_off[mid] <= i) lo = mid;
-      else hi = mid;
-    }
-    d = sqrtf(warp_exact_d2(v.left_desc + (size_t)i * v.D, v.right_desc + (size_t)(v.right_off[lo] + bi) * v.D, v.D, lane));
-  }
-  if (lane == 0) v.mdist[i] = d;
-}
-
 // ================================================================================================
-// Tensor-core path, second generation (default).  One persistent CTA per SM walks over stereo pairs; inside it the work
+// Tensor-core path (sm_100a tcgen05, default): the left x right descriptor contraction as 3xTF32 UMMAs (a = a_hi + a_lo,
+// a.b ~ a_hi.b_hi + a_hi.b_lo + a_lo.b_hi, fp32 accumulation in TMEM; |error| ~ 1e-6 in d^2) with the candidate
+// selection fused into the TMEM epilogue.  One persistent CTA per SM walks over stereo pairs; inside it the work
 // is split by warp role so that staging, tensor-core contraction and candidate selection of consecutive steps overlap:
 //   producers (4 warps) : split the descriptors into TF32 hi / lo parts while staging them into the canonical K-major
 //                         UMMA layout; one elected thread issues the 3xTF32 tcgen05.mma sequence of a step
 //   selectors (16 warps): read the finished accumulator from TMEM and compact the survivors of the cheap gates
-//   step = (chunk of NL left lines) x (block of 128 right lines); the accumulator is TRANSPOSED with respect to the first
-//   generation: TMEM lane = right line, TMEM column = left line.  A selector thread therefore owns one right line (its
-//   |b|^2, unit normal and octave live in registers), a warp looks at 32 consecutive right lines of ONE left line per
-//   step, and the survivors of that left line are appended with a ballot + one shared-memory atomic: the stores of a
-//   warp land in one or two 32 B sectors instead of 32 (the first generation spent most of its time in scattered
-//   4-byte stores).  Two accumulators (2 x 256 TMEM columns) are in flight.
+//   step = (chunk of NL left lines) x (block of 128 right lines); the accumulator is TRANSPOSED: TMEM lane = right line,
+//   TMEM column = left line.  A selector thread therefore owns one right line (its |b|^2, unit normal, octave and |X0|
+//   bound live in registers), a warp looks at 32 consecutive right lines of ONE left line at a time, and the survivors
+//   of that left line are appended with a ballot + one shared-memory atomic per 32 lines: the stores of a warp land in
+//   one or two 32 B sectors (a row-per-thread epilogue scatters 4-byte stores over 32 sectors and is bound by them).
+//   Two accumulators (2 x 256 TMEM columns) are in flight.
 //   k_line_prep2  : per line |d|^2 and FP32 copies of the geometry the selection and the gates read
 //   k_line_tc2    : as above; candidate list per left line = (3xTF32 d^2, right line), any order
 //   k_line_gate32 : the remaining gates of CheckLinePair over the lists.  Decided in FP32 with a running error bound;
@@ -699,21 +356,14 @@ constexpr int T2_SEL = 32 * T2_SEL_WARPS, T2_PROD = 32 * T2_PROD_WARPS, T2_NT = 
 struct LineTc2View {
   LineMatchView v;
   int nl_chunk;             // left lines per step (256, or 128 for wide descriptors)
-  int dbg;                  // timing experiments (LLD_LINE_DBG): 1 selectors idle, 2 no staging, 4 no MMA
-  float4* lrec;             // [n_left]  {|a|^2, unit plane normal}
-  float4* rrec;             // [n_right]
-  int8_t* loct;             // [n_left]  octave, -2 when the line is too short
-  int8_t* roct;             // [n_right] octave, -1 when the line is too short
-  float4* lgeo;             // [n_left][7] FP32 left-line geometry of the gates: {l1, |l1|^2}, {|l1|, |a0|^2, |a1|^2, -}, M0 | M1 (M = [a]_x K)
-  float4* rleq;             // [n_right] {K^T l normalised, beta = l_x * baseline}
-  float* rh;                // [n_right] |X0| >= 1/2 as a bound on the parallax cosine: cs >= rh (see k_line_prep2)
+  LineRecs rc;              // FP32 geometry records (k_line_prep)
   uint2* cand;              // [n_left][T2_CAP] {float bits of the 3xTF32 d^2 (0xFFFFFFFF: dead), right line}
   uint16_t* cand_cnt;       // [n_left] listed candidates (> T2_CAP: overflow)
   int* err_flag;            // 0: barrier time-out; 1: overflow rows; 2: listed; 4: decided in FP64; 5: FP32 / FP64 disagreements;
                             // 6: float bits of the largest observed |T_fp32 - T_fp64| / bound (check runs)
 };
 
-// 8 lanes per line
+// squared descriptor norms, 8 lanes per line
 __global__ void __launch_bounds__(256) k_line_prep2(LineTc2View t, int n_left, int n_right) {
   const LineMatchView& v = t.v;
   const int gl = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
@@ -731,49 +381,15 @@ __global__ void __launch_bounds__(256) k_line_prep2(LineTc2View t, int n_left, i
   s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
   s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
   s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
-  if (!live || sub) return;
-  const double* un = (side ? v.right_un : v.left_un) + 3 * (size_t)i;
-  const double* lq = (side ? v.right_leq : v.left_leq) + 3 * (size_t)i;
-  const bool too_short = (side ? v.right_len : v.left_len)[i] < (double)v.min_len;
-  const int oct = min(max((side ? v.right_oct : v.left_oct)[i], 0), 127);
-  const float4 rec = make_float4(s2, (float)un[0], (float)un[1], (float)un[2]);
-  if (side) {
-    t.rrec[i] = rec;
-    t.roct[i] = (int8_t)(too_short ? -1 : oct);
-    t.rleq[i] = make_float4((float)lq[0], (float)lq[1], (float)lq[2], (float)(lq[0] * v.baseline));
-    // |X0|^2 = beta^2 |l1|^2 / |l1 x l2|^2 and |l1 x l2|^2 = |l1|^2 |l2|^2 (1 - cs^2) with cs the cosine between the unit
-    // normals: |X0| >= 1/2  <=>  cs^2 >= 1 - 4 beta^2 / |l2|^2, a per-right-line bound the selectors test for free
-    const double beta = lq[0] * v.baseline, l2sq = lq[0] * lq[0] + lq[1] * lq[1] + lq[2] * lq[2];
-    t.rh[i] = (float)sqrt(fmax(0.0, 1.0 - 4.0 * beta * beta / l2sq));
-  } else {
-    t.lrec[i] = rec;
-    t.loct[i] = (int8_t)(too_short ? -2 : oct);
-    const float* sg = v.left_seg + 4 * (size_t)i;
-    float m[20];
-    float sa[2];   // |a|^2 of the two endpoints
-    for (int e = 0; e < 2; e++) {
-      const double a[3] = {sg[2 * e], sg[2 * e + 1], 1.0};
-      const double* K = v.K;
-      for (int cc = 0; cc < 3; cc++) {   // [a]_x K, column cc
-        m[9 * e + 0 + cc] = (float)(-a[2] * K[3 + cc] + a[1] * K[6 + cc]);
-        m[9 * e + 3 + cc] = (float)(a[2] * K[cc] - a[0] * K[6 + cc]);
-        m[9 * e + 6 + cc] = (float)(-a[1] * K[cc] + a[0] * K[3 + cc]);
-      }
-      sa[e] = (float)(a[0] * a[0] + a[1] * a[1] + 1.0);
-    }
-    m[18] = m[19] = 0.f;
-    const double l1sq = lq[0] * lq[0] + lq[1] * lq[1] + lq[2] * lq[2];
-    float4* g = t.lgeo + 7 * (size_t)i;
-    g[0] = make_float4((float)lq[0], (float)lq[1], (float)lq[2], (float)l1sq);
-    g[1] = make_float4((float)sqrt(l1sq), sa[0], sa[1], 0.f);
-    for (int k = 0; k < 5; k++) g[2 + k] = make_float4(m[4 * k], m[4 * k + 1], m[4 * k + 2], m[4 * k + 3]);
-  }
+  if (live && sub == 0) reinterpret_cast<float*>((side ? t.rc.rrec : t.rc.lrec) + i)[0] = s2;
 }
 
 __device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
-// stage `rows` descriptors as TF32 hi / lo parts (layout as stage_split); warp w of nw, two row groups in flight
+// stage `rows` descriptors (global row-major fp32, D multiple of 8) as TF32 hi / lo parts into the UMMA K-major layout:
+// element (r, k) at (r/8) * sbo + (k/4) * 128 + (r%8) * 16 + (k%4) * 4 ; a warp writes 512 contiguous bytes per step;
+// warp w of nw, two row groups in flight
 __device__ __forceinline__ void stage_split2(const float* __restrict__ g, int n_valid, int rows, int D, uint8_t* hi, uint8_t* lo,
                                              int w, int nw, int lane) {
   const int chunks = D >> 2, sbo = chunks * 128;
@@ -886,8 +502,8 @@ __global__ void __launch_bounds__(T2_NT, 1) k_line_tc2(LineTc2View t) {
       named_bar(1, T2_PROD);
       if (*dead_prod) break;
       for (int j = ptid; j < T2_ROWS; j += T2_PROD) {
-        rowv[pp * T2_ROWS + j] = j < na ? t.lrec[a0 + j] : make_float4(0.f, 0.f, 0.f, 0.f);
-        rowm[pp * T2_ROWS + j] = j < na ? t.loct[a0 + j] : (int8_t)-2;
+        rowv[pp * T2_ROWS + j] = j < na ? t.rc.lrec[a0 + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        rowm[pp * T2_ROWS + j] = j < na ? t.rc.loct[a0 + j] : (int8_t)-2;
       }
       mbar_arrive(bar_row + 8 * pp);
       const int n_lc = (na + NL - 1) / NL, n_m = (nb + T2_M - 1) / T2_M;
@@ -895,10 +511,8 @@ __global__ void __launch_bounds__(T2_NT, 1) k_line_tc2(LineTc2View t) {
         for (int m = 0; m < n_m; m++) {
           // the MMAs of the previous step have read the R (and L) buffers
           if (it >= 1) wait_or_flag(bar_mma + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1, dead_prod);
-          if (!(t.dbg & 2)) {
-            if (m == 0) stage_split2(v.left_desc + (size_t)(a0 + lc * NL) * D, na - lc * NL, NL, D, L_hi, L_lo, pw, T2_PROD_WARPS, lane);
-            stage_split2(v.right_desc + (size_t)(b0 + m * T2_M) * D, nb - m * T2_M, T2_M, D, R_hi, R_lo, pw, T2_PROD_WARPS, lane);
-          }
+          if (m == 0) stage_split2(v.left_desc + (size_t)(a0 + lc * NL) * D, na - lc * NL, NL, D, L_hi, L_lo, pw, T2_PROD_WARPS, lane);
+          stage_split2(v.right_desc + (size_t)(b0 + m * T2_M) * D, nb - m * T2_M, T2_M, D, R_hi, R_lo, pw, T2_PROD_WARPS, lane);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           named_bar(1, T2_PROD);
           if (*dead_prod) { out = true; break; }
@@ -907,7 +521,7 @@ __global__ void __launch_bounds__(T2_NT, 1) k_line_tc2(LineTc2View t) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::);
             const uint32_t d_tmem = tmem + (it & 1) * 256u;
             uint32_t acc = 0;
-            for (int ks = 0; ks < ((t.dbg & 4) ? 0 : D / 8); ks++) {
+            for (int ks = 0; ks < D / 8; ks++) {
               const uint32_t koff = (uint32_t)ks * 256u;
               const uint64_t rh = umma_desc(smem_u32(R_hi) + koff, 128, sbo), rl = umma_desc(smem_u32(R_lo) + koff, 128, sbo);
               const uint64_t lh = umma_desc(smem_u32(L_hi) + koff, 128, sbo), ll = umma_desc(smem_u32(L_lo) + koff, 128, sbo);
@@ -946,11 +560,11 @@ __global__ void __launch_bounds__(T2_NT, 1) k_line_tc2(LineTc2View t) {
           float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
           int octc = -1;
           float hc = 0.f;
-          if (c < nb) { cv = t.rrec[b0 + c]; octc = t.roct[b0 + c]; hc = t.rh[b0 + c] - 1e-4f; }
+          if (c < nb) { cv = t.rc.rrec[b0 + c]; octc = t.rc.roct[b0 + c]; hc = t.rc.rh[b0 + c] - 1e-4f; }
           wait_or_flag(bar_mma + 8 * (it & 1), (it >> 1) & 1, dead_sel);
           // (warp-uniform: the flag is only ever raised, and a warp that disagrees on it for one step merely reads an
           //  accumulator that is reported as invalid anyway)
-          const bool skip = __any_sync(0xffffffffu, *dead_sel != 0) || (t.dbg & 1);
+          const bool skip = __any_sync(0xffffffffu, *dead_sel != 0);
           asm volatile("tcgen05.fence::after_thread_sync;" ::);
           for (int gi = 0; gi < gpw && !skip; gi++) {
             const int g = part * gpw + gi;
@@ -999,7 +613,11 @@ __global__ void __launch_bounds__(T2_NT, 1) k_line_tc2(LineTc2View t) {
             // one shared-memory atomic per row, all 32 rows at once
             int my_base = 0;
             if (my_mask) my_base = atomicAdd(&cnt[j0 + lane], __popc(my_mask));
-            // pass 2 (branch-free): the survivors of a row go to consecutive slots of its list
+            // pass 2 (branch-free): the survivors of a row go to consecutive slots of its list.  The accumulator is read
+            // from TMEM a second time: keeping the 32 values of pass 1 alive across both passes costs more registers than
+            // the kernel has (it runs at the 96-register limit of a 640-thread CTA) and the compiler spills them
+            TMEM_LD32(r, tmem + ((uint32_t)(32 * q) << 16) + (it & 1) * 256u + (uint32_t)(32 * g));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const unsigned lt = (1u << lane) - 1u;
             uint2* const out0 = t.cand + (size_t)(a0 + j0) * T2_CAP;
 #pragma unroll
@@ -1113,14 +731,25 @@ __device__ __forceinline__ double gate64_T(const LineMatchView& v, const float* 
 }
 
 // The remaining gates of CheckLinePair over the candidate lists, and compaction of each list to its admissible entries
-// (in place: the write position never passes the read position).  A warp takes G32_ROWS consecutive left lines of a pair;
-// entries the FP32 evaluation cannot decide stay in the list provisionally and are queued (per warp, shared memory);
-// the queue is worked off 32 entries at a time by the FP64 formulas, so that the FP64 path runs with full warps
-// instead of one or two lanes per list; an entry that fails there is overwritten by the dead key.
+// (in place: the write position never passes the read position).  A warp takes G32_ROWS consecutive left lines of a pair.
+// The kernel is latency-bound (two dependent loads per entry and ~150 instructions), so the warp first pulls everything
+// it will read from HBM -- the list heads (64 entries per line) and the left-line geometry -- into shared memory with
+// one burst of cp.async, and only then walks the lines.  Entries the FP32 evaluation cannot decide stay in the list
+// provisionally and are queued (per warp, shared memory); the queue is worked off 32 entries at a time by the FP64
+// formulas, so that the FP64 path runs with full warps instead of one or two lanes per list; an entry that fails there
+// is overwritten by the dead key.
 // grid (row blocks, pairs), or (pairs, row blocks) when there are more than 65535 pairs.
-constexpr int G32_ROWS = 8, G32_WARPS = 8;
+constexpr int G32_ROWS = 8, G32_WARPS = 4, G32_HEAD = 64;
 struct GateQ { uint32_t slot_lo; uint32_t slot_hi; int gl; int c; };   // list slot, left line, right line (global indices)
+__device__ __forceinline__ void cp_async8(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
+}
 __global__ void __launch_bounds__(32 * G32_WARPS) k_line_gate32(LineTc2View t, GateK gk, int swap_grid, int check) {
+  __shared__ __align__(16) uint2 s_ent[G32_WARPS][G32_ROWS][G32_HEAD];
+  __shared__ __align__(16) float4 s_geo[G32_WARPS][G32_ROWS][7];
   __shared__ GateQ queue[G32_WARPS][64];
   const LineMatchView& v = t.v;
   const int p = swap_grid ? blockIdx.x : blockIdx.y, jb = swap_grid ? blockIdx.y : blockIdx.x;
@@ -1128,7 +757,19 @@ __global__ void __launch_bounds__(32 * G32_WARPS) k_line_gate32(LineTc2View t, G
   const int a0 = v.left_off[p], na = v.left_off[p + 1] - a0, b0 = v.right_off[p];
   const int j_begin = (jb * G32_WARPS + wid) * G32_ROWS;
   if (j_begin >= na) return;
-  const int j_end = min(j_begin + G32_ROWS, na);
+  const int n_rows = min(G32_ROWS, na - j_begin);
+  // ---- one burst: list lengths, list heads, left-line geometry
+  int my_cnt = 0;
+  if (lane < n_rows) my_cnt = t.cand_cnt[a0 + j_begin + lane];
+  for (int r = 0; r < n_rows; r++) {
+    const uint2* src = t.cand + (size_t)(a0 + j_begin + r) * T2_CAP;
+    cp_async8(&s_ent[wid][r][lane], src + lane);
+    cp_async8(&s_ent[wid][r][lane + 32], src + lane + 32);
+  }
+  for (int k = lane; k < 7 * n_rows; k += 32) cp_async16(&s_geo[wid][0][0] + k, t.rc.lgeo + 7 * (size_t)(a0 + j_begin) + k);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
   GateQ* q = queue[wid];
   int qn = 0;
   int n_listed = 0, n_border = 0, n_bad = 0;
@@ -1138,28 +779,38 @@ __global__ void __launch_bounds__(32 * G32_WARPS) k_line_gate32(LineTc2View t, G
     if (!line_pair_gate_fast(v, v.left_seg + 4 * (size_t)it.gl, v.left_leq + 3 * (size_t)it.gl, v.right_leq + 3 * (size_t)it.c))
       t.cand[((size_t)it.slot_hi << 32) | it.slot_lo].x = 0xFFFFFFFFu;
   };
-  for (int j = j_begin; j < j_end; j++) {
-    const int gl = a0 + j;
-    const int cnt_raw = t.cand_cnt[gl], cnt = min(cnt_raw, T2_CAP);
-    const GateL L = load_gate_left(t.lgeo + 7 * (size_t)gl);
+  for (int r = 0; r < n_rows; r++) {
+    const int gl = a0 + j_begin + r;
+    const int cnt_raw = __shfl_sync(0xffffffffu, my_cnt, r), cnt = min(cnt_raw, T2_CAP);
+    const GateL L = load_gate_left(s_geo[wid][r]);
     const size_t row = (size_t)gl * T2_CAP;
     int out = 0;
-    for (int e0 = 0; e0 < cnt; e0 += 32) {
-      const int e = e0 + lane;
-      const bool valid = e < cnt;
-      uint32_t d2 = 0xFFFFFFFFu;
-      int col = 0, g = 0;
-      if (valid) {
-        const uint2 en = t.cand[row + e];
-        d2 = en.x;
-        col = (int)en.y;
-        const float4 l2v = t.rleq[b0 + col];
-        const float l2[3] = {l2v.x, l2v.y, l2v.z};
-        g = line_gate32(gk, L, l2, l2v.w);
-        if (check) {
+    for (int e0 = 0; e0 < cnt; e0 += 64) {
+      // two entries per lane and trip: two independent dependency chains (the kernel is latency-bound)
+      bool valid[2];
+      uint32_t d2[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+      int col[2] = {0, 0}, g[2] = {0, 0};
+      float4 l2v[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int e = e0 + 32 * h + lane;
+        valid[h] = e < cnt;
+        l2v[h] = make_float4(1.f, 0.f, 0.f, 0.f);
+        if (valid[h]) {
+          const uint2 en = e < G32_HEAD ? s_ent[wid][r][e] : t.cand[row + e];
+          d2[h] = en.x;
+          col[h] = (int)en.y;
+          l2v[h] = t.rc.rleq[b0 + col[h]];
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const float l2[3] = {l2v[h].x, l2v[h].y, l2v[h].z};
+        g[h] = valid[h] ? line_gate32(gk, L, l2, l2v[h].w) : 0;
+        if (check && valid[h]) {
           const float* s1 = v.left_seg + 4 * (size_t)gl;
-          const bool g64 = line_pair_gate_fast(v, s1, v.left_leq + 3 * (size_t)gl, v.right_leq + 3 * (size_t)(b0 + col));
-          if (g >= 0 && (g != 0) != g64) n_bad++;
+          const bool g64 = line_pair_gate_fast(v, s1, v.left_leq + 3 * (size_t)gl, v.right_leq + 3 * (size_t)(b0 + col[h]));
+          if (g[h] >= 0 && (g[h] != 0) != g64) n_bad++;
           // observed error of T against its bound (both endpoints), in units of the bound
           float dir[3], c1[3];
           cross3f(L.l1, l2, dir);
@@ -1169,29 +820,32 @@ __global__ void __launch_bounds__(32 * G32_WARPS) k_line_gate32(LineTc2View t, G
             float T, tol2;
             bool cond;
             gate32_endpoint(gk, L, ep, dir, c1, dd, &T, &tol2, &cond);
-            const double T64 = gate64_T(v, s1, v.left_leq + 3 * (size_t)gl, v.right_leq + 3 * (size_t)(b0 + col), ep);
+            const double T64 = gate64_T(v, s1, v.left_leq + 3 * (size_t)gl, v.right_leq + 3 * (size_t)(b0 + col[h]), ep);
             if (cond && tol2 > 0.f) worst = fmaxf(worst, (float)(fabs((double)T - T64) / sqrt((double)tol2)));
           }
         }
       }
-      const bool keep = valid && g != 0, border = valid && g < 0;
-      const unsigned km = __ballot_sync(0xffffffffu, keep), bm = __ballot_sync(0xffffffffu, border);
-      const int pos = out + __popc(km & lt);
-      if (keep) t.cand[row + pos] = make_uint2(d2, (uint32_t)col);
-      if (border) {
-        GateQ it;
-        const size_t slot = row + pos;
-        it.slot_lo = (uint32_t)slot; it.slot_hi = (uint32_t)(slot >> 32); it.gl = gl; it.c = b0 + col;
-        q[qn + __popc(bm & lt)] = it;
-      }
-      out += __popc(km);
-      qn += __popc(bm);
-      n_border += __popc(bm);
-      __syncwarp();
-      if (qn >= 32) {
-        qn -= 32;
-        settle(q[qn + lane]);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const bool keep = valid[h] && g[h] != 0, border = valid[h] && g[h] < 0;
+        const unsigned km = __ballot_sync(0xffffffffu, keep), bm = __ballot_sync(0xffffffffu, border);
+        const int pos = out + __popc(km & lt);
+        if (keep) t.cand[row + pos] = make_uint2(d2[h], (uint32_t)col[h]);
+        if (border) {
+          GateQ it;
+          const size_t slot = row + pos;
+          it.slot_lo = (uint32_t)slot; it.slot_hi = (uint32_t)(slot >> 32); it.gl = gl; it.c = b0 + col[h];
+          q[qn + __popc(bm & lt)] = it;
+        }
+        out += __popc(km);
+        qn += __popc(bm);
+        n_border += __popc(bm);
         __syncwarp();
+        if (qn >= 32) {
+          qn -= 32;
+          settle(q[qn + lane]);
+          __syncwarp();
+        }
       }
     }
     if (lane == 0 && cnt_raw <= T2_CAP) t.cand_cnt[gl] = (uint16_t)out;   // (an overflowed row keeps its marker: exact scan in the greedy)
@@ -1206,31 +860,33 @@ __global__ void __launch_bounds__(32 * G32_WARPS) k_line_gate32(LineTc2View t, G
 }
 
 // One warp per pair replays the sequential greedy over the compacted lists: smallest (d^2, right line) among the
-// untaken live entries of the row, two warp reductions per left line.  The first 64 entries of the next G2_PF rows are
-// kept in registers (the lists stream from HBM: ~1 us per row otherwise); longer lists read their tail on demand.
+// untaken live entries of the row, two warp reductions per left line.  Nothing on the per-line dependency chain touches
+// memory: the "taken" set lives in registers (lane w holds the bits of right lines [32 w, 32 w + 32), looked up by
+// shuffle), the first 64 entries of the next G2_PF rows are prefetched into registers (the lists stream from HBM), and
+// the matches are collected in shared memory and written out at the end.  Longer lists read their tail on demand.
 constexpr int G2_PF = 4;
 __global__ void __launch_bounds__(32) k_line_greedy2(LineTc2View t) {
-  __shared__ uint32_t taken[T2_ROWS / 32];
+  __shared__ uint16_t s_cnt[T2_ROWS];
+  __shared__ int16_t s_match[T2_ROWS];
   const LineMatchView& v = t.v;
   const int lane = threadIdx.x, p = blockIdx.x;
   const int a0 = v.left_off[p], na = v.left_off[p + 1] - a0;
   const int b0 = v.right_off[p], nb = v.right_off[p + 1] - b0;
   if (na == 0) return;
-  if (lane < T2_ROWS / 32) taken[lane] = 0u;
+  for (int j = lane; j < na; j += 32) s_cnt[j] = t.cand_cnt[a0 + j];
   __syncwarp();
+  uint32_t taken = 0u;   // lane w < 16: right lines [32 w, 32 w + 32)
   uint32_t pd2[G2_PF][2];
   uint32_t pcol[G2_PF][2];
-  int pcnt[G2_PF];
+  // both loads of a row are issued unconditionally (every slot of a list exists); the list length masks them at use
   auto fetch = [&](int j, int u) {
-    pcnt[u] = 0;
     pd2[u][0] = pd2[u][1] = 0xFFFFFFFFu;
     pcol[u][0] = pcol[u][1] = 0;
     if (j < na) {
-      pcnt[u] = t.cand_cnt[a0 + j];
-      const int tot = min(pcnt[u], T2_CAP);
-      const size_t o = (size_t)(a0 + j) * T2_CAP;
-      if (lane < tot) { const uint2 en = t.cand[o + lane]; pd2[u][0] = en.x; pcol[u][0] = en.y; }
-      if (lane + 32 < tot) { const uint2 en = t.cand[o + lane + 32]; pd2[u][1] = en.x; pcol[u][1] = en.y; }
+      const uint2* o = t.cand + (size_t)(a0 + j) * T2_CAP;
+      const uint2 e0 = o[lane], e1 = o[lane + 32];
+      pd2[u][0] = e0.x; pcol[u][0] = e0.y;
+      pd2[u][1] = e1.x; pcol[u][1] = e1.y;
     }
   };
 #pragma unroll
@@ -1240,19 +896,27 @@ __global__ void __launch_bounds__(32) k_line_greedy2(LineTc2View t) {
     for (int u = 0; u < G2_PF; u++) {
       const int j = jb + u;
       if (j >= na) break;
-      const int cnt = pcnt[u];
+      const int cnt = s_cnt[j];
       uint32_t bd = 0xFFFFFFFFu, bc = 0xFFFFFFFFu;
-      auto offer = [&](uint32_t d2, uint32_t c) {
-        const bool live = d2 != 0xFFFFFFFFu && !((taken[c >> 5] >> (c & 31)) & 1u);
+      auto offer = [&](bool valid, uint32_t d2, uint32_t c) {   // (the shuffle is executed by every lane)
+        const uint32_t w = __shfl_sync(0xffffffffu, taken, (c >> 5) & 31);
+        const bool live = valid && d2 != 0xFFFFFFFFu && !((w >> (c & 31)) & 1u);
         if (live && (d2 < bd || (d2 == bd && c < bc))) { bd = d2; bc = c; }
       };
-      offer(pd2[u][0], pcol[u][0]);
-      offer(pd2[u][1], pcol[u][1]);
+      offer(lane < cnt, pd2[u][0], pcol[u][0]);
+      offer(lane + 32 < cnt, pd2[u][1], pcol[u][1]);
       fetch(j + G2_PF, u);
       int bi = -1;
       if (cnt <= T2_CAP) {
-        const size_t o = (size_t)(a0 + j) * T2_CAP;
-        for (int e = 64 + lane; e < cnt; e += 32) { const uint2 en = t.cand[o + e]; offer(en.x, en.y); }
+        if (cnt > 64) {   // warp-uniform
+          const uint2* o = t.cand + (size_t)(a0 + j) * T2_CAP;
+          for (int e0 = 64; e0 < cnt; e0 += 32) {
+            const int e = e0 + lane;
+            uint2 en = make_uint2(0xFFFFFFFFu, 0u);
+            if (e < cnt) en = o[e];
+            offer(e < cnt, en.x, en.y);
+          }
+        }
         const uint32_t m = __reduce_min_sync(0xffffffffu, bd);
         if (m != 0xFFFFFFFFu) bi = (int)__reduce_min_sync(0xffffffffu, bd == m ? bc : 0xFFFFFFFFu);
       } else {
@@ -1265,8 +929,9 @@ __global__ void __launch_bounds__(32) k_line_greedy2(LineTc2View t) {
         float best = INFINITY;
         for (int cb = 0; cb < nb && l_ok; cb += 32) {
           const int c = cb + lane;
+          const uint32_t w = __shfl_sync(0xffffffffu, taken, cb >> 5);
           bool ok = false;
-          if (c < nb && !((taken[c >> 5] >> (c & 31)) & 1u)) {
+          if (c < nb && !((w >> lane) & 1u)) {
             const int gc = b0 + c;
             if (v.left_oct[gl] == v.right_oct[gc] && !(v.right_len[gc] < (double)v.min_len)) {
               const double* un = v.right_un + 3 * (size_t)gc;
@@ -1283,26 +948,39 @@ __global__ void __launch_bounds__(32) k_line_greedy2(LineTc2View t) {
           }
         }
       }
-      if (lane == 0) {
-        v.match[a0 + j] = bi;
-        if (bi >= 0) taken[bi >> 5] |= 1u << (bi & 31);
-      }
-      __syncwarp();
+      if (bi >= 0 && lane == (bi >> 5)) taken |= 1u << (bi & 31);
+      if (lane == 0) s_match[j] = (int16_t)bi;
     }
   }
+  __syncwarp();
+  for (int j = lane; j < na; j += 32) v.match[a0 + j] = s_match[j];
 }
 
-// exact distance of every match: one warp per left line, grid as k_line_gate32
+// exact distance of every match (FP32, difference form): 8 lanes per left line, 32 lines per block
 __global__ void __launch_bounds__(256) k_line_exact2(LineTc2View t, int swap_grid) {
   const LineMatchView& v = t.v;
   const int p = swap_grid ? blockIdx.x : blockIdx.y, jb = swap_grid ? blockIdx.y : blockIdx.x;
-  const int lane = threadIdx.x & 31, j = jb * 8 + (threadIdx.x >> 5);
+  const int sub = threadIdx.x & 7, j = jb * 32 + (threadIdx.x >> 3);
   const int a0 = v.left_off[p], na = v.left_off[p + 1] - a0;
-  if (j >= na) return;
-  const int bi = v.match[a0 + j];
-  float d = INFINITY;
-  if (bi >= 0) d = sqrtf(warp_exact_d2(v.left_desc + (size_t)(a0 + j) * v.D, v.right_desc + (size_t)(v.right_off[p] + bi) * v.D, v.D, lane));
-  if (lane == 0) v.mdist[a0 + j] = d;
+  const bool live = j < na;
+  const int bi = live ? v.match[a0 + j] : -1;
+  float s2 = 0.f;
+  if (bi >= 0) {
+    const float* a = v.left_desc + (size_t)(a0 + j) * v.D;
+    const float* b = v.right_desc + (size_t)(v.right_off[p] + bi) * v.D;
+    for (int k = 4 * sub; k < v.D; k += 32) {
+      const float4 x = *reinterpret_cast<const float4*>(a + k), y = *reinterpret_cast<const float4*>(b + k);
+      float d;
+      d = x.x - y.x; s2 = fmaf(d, d, s2);
+      d = x.y - y.y; s2 = fmaf(d, d, s2);
+      d = x.z - y.z; s2 = fmaf(d, d, s2);
+      d = x.w - y.w; s2 = fmaf(d, d, s2);
+    }
+  }
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+  if (live && sub == 0) v.mdist[a0 + j] = bi >= 0 ? sqrtf(s2) : INFINITY;
 }
 
 template <typename T>
@@ -1348,23 +1026,22 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
   v.n_pairs = P; v.D = p->desc_dim;
   for (int i = 0; i < 9; i++) v.K[i] = p->K[i];
   v.baseline = p->baseline; v.tau = p->tau; v.min_len = p->min_line_length;
-  // tensor-core path: D multiple of 8 up to 72 floats, at most 512 right lines per pair (LLD_LINE_TC=0 forces the FP32 tile path)
+  // tensor-core path: D multiple of 8 up to 72 floats, at most 512 lines per side of a pair (LLD_LINE_TC=0 forces the
+  // FP32 tile path, which takes everything else)
   int max_na = 0, max_nb = 0;
   for (int i = 0; i < P; i++) {
     max_na = std::max(max_na, p->left_off[i + 1] - p->left_off[i]);
     max_nb = std::max(max_nb, p->right_off[i + 1] - p->right_off[i]);
   }
   const char* e_tc = getenv("LLD_LINE_TC");
-  const bool use_tc = !(e_tc && e_tc[0] == '0') && v.D % 8 == 0 && v.D >= 8 && v.D <= 72 && max_nb <= TC_COLS && max_nb >= 1 && max_na >= 1;
-  // second generation (persistent, warp-specialised) unless LLD_LINE_TC=old; needs <= 512 left lines per pair as well
-  const bool use_tc2 = use_tc && !(e_tc && e_tc[0] == 'o') && max_na <= T2_ROWS;
-  // tiles + matrix offsets
+  const bool use_tc = !(e_tc && e_tc[0] == '0') && v.D % 8 == 0 && v.D >= 8 && v.D <= 72 && max_nb <= T2_ROWS && max_na <= T2_ROWS &&
+                      max_nb >= 1 && max_na >= 1;
+  // tile path: tiles + matrix offsets
   std::vector<long long> mat_off(P), taken_off(P);
   std::vector<int> tp, tr, tc;
   long long tot = 0, ttot = 0;
-  for (int i = 0; i < P; i++) {
+  for (int i = 0; i < P && !use_tc; i++) {
     const int na = p->left_off[i + 1] - p->left_off[i], nb = p->right_off[i + 1] - p->right_off[i];
-    if (use_tc) continue;
     mat_off[i] = tot; tot += (long long)na * nb;
     taken_off[i] = ttot; ttot += nb;
     for (int r = 0; r < cdiv(na, LT); r++)
@@ -1400,26 +1077,24 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
   LLD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   const int nmax = std::max(std::max(n_left, n_right), 1);
   int* d_tc_err = nullptr;
-  LLD_LAUNCH(c, k_line_prep, cdiv(nmax, 128), 128, 0, v, n_left, n_right);
-  if (use_tc2) {
+  const bool check = getenv("LLD_LINE_CHECK") != nullptr || getenv("LLD_LINE_STATS") != nullptr;
+  if (use_tc) {
     LineTc2View t;
     t.v = v;
     t.nl_chunk = v.D <= 64 ? 256 : 128;
-    t.dbg = getenv("LLD_LINE_DBG") ? atoi(getenv("LLD_LINE_DBG")) : 0;
-    UPM(t.lrec, float4, nullptr, n_left);
-    UPM(t.rrec, float4, nullptr, n_right);
-    UPM(t.loct, int8_t, nullptr, n_left);
-    UPM(t.roct, int8_t, nullptr, n_right);
-    UPM(t.lgeo, float4, nullptr, 7 * (size_t)n_left);
-    UPM(t.rleq, float4, nullptr, n_right);
-    UPM(t.rh, float, nullptr, n_right);
+    UPM(t.rc.lrec, float4, nullptr, n_left);
+    UPM(t.rc.rrec, float4, nullptr, n_right);
+    UPM(t.rc.rh, float, nullptr, n_right);
+    UPM(t.rc.loct, int8_t, nullptr, n_left);
+    UPM(t.rc.roct, int8_t, nullptr, n_right);
+    UPM(t.rc.lgeo, float4, nullptr, 7 * (size_t)n_left);
+    UPM(t.rc.rleq, float4, nullptr, n_right);
     UPM(t.cand, uint2, nullptr, (size_t)n_left * T2_CAP);
     UPM(t.cand_cnt, uint16_t, nullptr, n_left);
     UPM(t.err_flag, int, nullptr, 8);
     d_tc_err = t.err_flag;
     LLD_CUDA(c, cudaMemsetAsync(t.err_flag, 0, 8 * sizeof(int), c->stream));
     LLD_CUDA(c, cudaMemsetAsync(t.cand_cnt, 0, sizeof(uint16_t) * (size_t)n_left, c->stream));   // pairs without right lines
-    LLD_CUDA(c, cudaMemsetAsync(v.match, 0xFF, sizeof(int) * (size_t)n_left, c->stream));
     const size_t smem = (size_t)(t.nl_chunk + T2_M) * v.D * 8 + 2 * T2_ROWS * (16 + 4 + 1) + 6 * 8 + 16;
     LLD_CUDA(c, lld_raise_dyn_smem(k_line_tc2, (size_t)(int)smem));
     GateK gk;
@@ -1429,97 +1104,29 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
     double c_tol = 2e-6;   // k eps with k = 32; check runs report the largest observed error in units of the bound (err_flag[6])
     if (const char* e_c = getenv("LLD_LINE_CTOL")) c_tol = atof(e_c);
     gk.c_tol2 = (float)(36.0 * c_tol * c_tol);
-    const int check = getenv("LLD_LINE_CHECK") != nullptr || getenv("LLD_LINE_STATS") != nullptr;
     const int swap_grid = P > 65535;
-    const dim3 grid_rows = swap_grid ? dim3(P, cdiv(max_na, 8)) : dim3(cdiv(max_na, 8), P);
-    const int gate_blocks = cdiv(max_na, G32_ROWS * G32_WARPS);
+    const int gate_blocks = cdiv(max_na, G32_ROWS * G32_WARPS), exact_blocks = cdiv(max_na, 32);
     const dim3 grid_gate = swap_grid ? dim3(P, gate_blocks) : dim3(gate_blocks, P);
+    const dim3 grid_exact = swap_grid ? dim3(P, exact_blocks) : dim3(exact_blocks, P);
+    LLD_LAUNCH(c, k_line_prep<true>, cdiv(nmax, 128), 128, 0, v, t.rc, n_left, n_right);
     LLD_LAUNCH(c, k_line_prep2, cdiv(8 * (n_left + n_right), 256), 256, 0, t, n_left, n_right);
     LLD_LAUNCH(c, k_line_tc2, std::min(P, c->sm_count), T2_NT, smem, t);
-    LLD_LAUNCH(c, k_line_gate32, grid_gate, 32 * G32_WARPS, 0, t, gk, swap_grid, check);
+    LLD_LAUNCH(c, k_line_gate32, grid_gate, 32 * G32_WARPS, 0, t, gk, swap_grid, (int)check);
     LLD_LAUNCH(c, k_line_greedy2, P, 32, 0, t);
-    LLD_LAUNCH(c, k_line_exact2, grid_rows, 256, 0, t, swap_grid);
-  } else if (use_tc) {
-    // tiles ordered by row block: block r of every pair is contracted by one launch, after which the greedy can advance
-    // through the left lines [128 r, 128 (r + 1)) of every pair while the next block is being contracted
-    std::vector<int> ttp, ttr, blk_begin;
-    const int n_blk = cdiv(std::max(max_na, 1), TC_ROWS);
-    for (int r = 0; r < n_blk; r++) {
-      blk_begin.push_back((int)ttp.size());
-      for (int i = 0; i < P; i++) {
-        const int na = p->left_off[i + 1] - p->left_off[i];
-        if (p->right_off[i + 1] - p->right_off[i] == 0) continue;   // no right lines: every left line stays unmatched
-        if (r < cdiv(na, TC_ROWS)) { ttp.push_back(i); ttr.push_back(r); }
-      }
+    LLD_LAUNCH(c, k_line_exact2, grid_exact, 256, 0, t, swap_grid);
+  } else {
+    LLD_LAUNCH(c, k_line_prep<false>, cdiv(nmax, 128), 128, 0, v, LineRecs(), n_left, n_right);
+    if (!tp.empty()) {
+      const size_t smem = sizeof(float) * 2 * LT * (v.D + 1);
+      LLD_CUDA(c, lld_raise_dyn_smem(k_line_dist, (size_t)(int)smem));
+      LLD_LAUNCH(c, k_line_dist, (int)tp.size(), 256, smem, v, d_tp, d_tr, d_tc);
     }
-    blk_begin.push_back((int)ttp.size());
-    LineTcView t;
-    t.v = v;
-    int *d_ttp, *d_ttr;
-    UPM(d_ttp, int, ttp.data(), ttp.size());
-    UPM(d_ttr, int, ttr.data(), ttr.size());
-    t.tile_pair = d_ttp; t.tile_r = d_ttr;
-    UPM(t.cand_d2, uint32_t, nullptr, (size_t)n_left * TC_CAND);
-    UPM(t.cand_col, uint16_t, nullptr, (size_t)n_left * TC_CAND);
-    UPM(t.cand_cnt, uint16_t, nullptr, 2 * (size_t)n_left);
-    UPM(t.cand_adm, uint32_t, nullptr, (size_t)TC_AW * n_left);
-    UPM(t.err_flag, int, nullptr, 8);
-    LLD_CUDA(c, cudaMemsetAsync(t.err_flag, 0, 8 * sizeof(int), c->stream));
-    d_tc_err = t.err_flag;
-    LLD_CUDA(c, cudaMemsetAsync(t.cand_cnt, 0, sizeof(uint16_t) * 2 * (size_t)n_left, c->stream));
-    uint32_t* d_taken_bits;
-    UPM(d_taken_bits, uint32_t, nullptr, (size_t)P * (TC_COLS / 32));
-    const size_t smem = (size_t)(TC_ROWS + TC_HALF) * v.D * 8 + TC_COLS * 16 + TC_COLS + 16 + 64;
-    if (!ttp.empty()) LLD_CUDA(c, lld_raise_dyn_smem(k_line_tc, (size_t)(int)smem));
-    {
-      // k_line_tc needs the SM's maximal shared-memory carve-out; a kernel that prefers another split of L1 / shared
-      // memory cannot share an SM with it (the carve-out is per SM and only changes on an idle SM).  Ask for the same
-      // split for the kernels that are meant to run beside it.
-      static int carve_dev = -1;
-      if (carve_dev != c->device) {
-        LLD_CUDA(c, cudaFuncSetAttribute(k_line_greedy_lazy, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        LLD_CUDA(c, cudaFuncSetAttribute(k_line_exact, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        carve_dev = c->device;
-      }
-    }
-    const bool stats = getenv("LLD_LINE_STATS") != nullptr;
-    cudaStream_t s0 = c->stream, s1 = (c->prof_on || stats) ? c->stream : c->side[0];
-    if (s1 != s0) {   // the side stream starts after everything enqueued so far (uploads, prep, memsets)
-      LLD_CUDA(c, cudaEventRecord(c->ev_fork, s0));
-      LLD_CUDA(c, cudaStreamWaitEvent(s1, c->ev_fork, 0));
-    }
-    for (int r = 0; r < n_blk; r++) {
-      const int nt = blk_begin[r + 1] - blk_begin[r];
-      if (nt > 0) {
-        LineTcView tr2 = t;
-        tr2.tile_pair = d_ttp + blk_begin[r]; tr2.tile_r = d_ttr + blk_begin[r];
-        LLD_LAUNCH_S(c, s0, k_line_tc, nt, TC_NT, smem, tr2);
-      }
-      if (stats && r == n_blk - 1) {   // exhaustive gate pass: candidate / admissibility counts, 3xTF32 distance error
-        LLD_CUDA(c, cudaMemsetAsync(t.cand_adm, 0, sizeof(uint32_t) * (size_t)TC_AW * n_left, s0));
-        LLD_LAUNCH_S(c, s0, k_line_gate, cdiv(n_left, 16), 256, 0, t, n_left, 1);
-      }
-      if (s1 != s0) {
-        LLD_CUDA(c, cudaEventRecord(c->ev_fork, s0));
-        LLD_CUDA(c, cudaStreamWaitEvent(s1, c->ev_fork, 0));
-      }
-      LLD_LAUNCH_S(c, s1, k_line_greedy_lazy, cdiv(P, GL_WARPS), 32 * GL_WARPS, 0, t, r * TC_ROWS, (r + 1) * TC_ROWS, d_taken_bits);
-    }
-    LLD_LAUNCH_S(c, s1, k_line_exact, cdiv(n_left, 8), 256, 0, t, n_left);
-    if (s1 != s0) {
-      LLD_CUDA(c, cudaEventRecord(c->ev_join[0], s1));
-      LLD_CUDA(c, cudaStreamWaitEvent(s0, c->ev_join[0], 0));
-    }
-  } else if (!tp.empty()) {
-    const size_t smem = sizeof(float) * 2 * LT * (v.D + 1);
-    LLD_CUDA(c, lld_raise_dyn_smem(k_line_dist, (size_t)(int)smem));
-    LLD_LAUNCH(c, k_line_dist, (int)tp.size(), 256, smem, v, d_tp, d_tr, d_tc);
+    LLD_LAUNCH(c, k_line_greedy, P, 32, 0, v, d_taken, d_taken_off);
   }
-  if (!use_tc) LLD_LAUNCH(c, k_line_greedy, P, 32, 0, v, d_taken, d_taken_off);
   LLD_CUDA(c, cudaGetLastError());
   LLD_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
   int* h_err = reinterpret_cast<int*>(c->pinned);
-  *h_err = 0;
+  for (int i = 0; i < 8; i++) h_err[i] = 0;
   if (d_tc_err) LLD_CUDA(c, cudaMemcpyAsync(h_err, d_tc_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   if (n_left) {
     LLD_CUDA(c, cudaMemcpyAsync(out->match, v.match, sizeof(int) * (size_t)n_left, cudaMemcpyDeviceToHost, c->stream));
@@ -1530,18 +1137,15 @@ extern "C" int lld_line_match(void* ctx, const lld_line_match_problem* p, lld_li
   cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->ms_compute, c->ev[1], c->ev[2]);
   cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]);
-  if (getenv("LLD_LINE_STATS") && d_tc_err && !use_tc2)
-    fprintf(stderr, "[lld_line_match] fallback rows %d, listed candidates %d, geometrically admissible %d, max |d2_tc - d2_exact| %.3e\n",
-            h_err[1], h_err[2], h_err[3], (double)*reinterpret_cast<float*>(h_err + 4));
-  if (getenv("LLD_LINE_STATS") && d_tc_err && use_tc2)
-    fprintf(stderr, "[lld_line_match] fallback rows %d, listed candidates %d, decided in FP64 %d, FP32/FP64 disagreements %d, largest FP32 error / bound %.3g\n",
+  if (getenv("LLD_LINE_STATS") && d_tc_err)
+    fprintf(stderr, "[lld_line_match] rows with an overflowed list %d, listed candidates %d, decided in FP64 %d, FP32/FP64 disagreements %d, largest FP32 error / bound %.3g\n",
             h_err[1], h_err[2], h_err[4], h_err[5], (double)*reinterpret_cast<float*>(h_err + 6));
-  if (use_tc2 && h_err[5]) {
-    snprintf(c->err, sizeof(c->err), "line matcher: %d FP32 gate decisions differ from FP64 (LLD_LINE_CHECK)", h_err[5]);
+  if (h_err[0]) {
+    snprintf(c->err, sizeof(c->err), "line matcher: a tensor-core pipeline barrier timed out");
     return LLD_ERR_CUDA;
   }
-  if (*h_err) {
-    snprintf(c->err, sizeof(c->err), "line matcher: tensor-core completion barrier timed out");
+  if (check && h_err[5]) {
+    snprintf(c->err, sizeof(c->err), "line matcher: %d FP32 gate decisions differ from FP64 (LLD_LINE_CHECK)", h_err[5]);
     return LLD_ERR_CUDA;
   }
   return LLD_OK;

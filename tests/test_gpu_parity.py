@@ -287,6 +287,34 @@ def test_line_match(gpu_ctx, D, line_path):
     check_line_match(g, o)
 
 
+def test_line_match_fp32_gates_agree_with_fp64(gpu_ctx, monkeypatch):
+    """LLD_LINE_CHECK evaluates every listed candidate with both the FP32 gate (error bound + FP64 fallback) and the FP64
+    formulas and fails the call on a single disagreement; 64 pairs = ~2 million candidates"""
+    monkeypatch.setenv("LLD_LINE_TC", "1")
+    monkeypatch.setenv("LLD_LINE_CHECK", "1")
+    p = synth.make_line_match_batch(64, 500, 64, 77)
+    g = api.line_match(p, impl="gpu", ctx=gpu_ctx)   # raises on a disagreement
+    assert (g["match"] >= 0).sum() > 64 * 100
+
+
+def test_line_match_overflowing_candidate_lists(gpu_ctx, monkeypatch):
+    """a 20x baseline lets nearly every pair through the |X0| gate: more than 256 candidates per left line, so the greedy
+    takes its exact scan of the row; same matches as the oracle"""
+    monkeypatch.setenv("LLD_LINE_TC", "1")
+    p = synth.make_line_match_batch(3, 512, 64, 31)
+    p = dict(p); p["baseline"] = 20.0 * p["baseline"]
+    p["left_octave"] = np.zeros_like(p["left_octave"]); p["right_octave"] = np.zeros_like(p["right_octave"])
+    g = api.line_match(p, impl="gpu", ctx=gpu_ctx)
+    o = api.line_match(p, impl="oracle")
+    assert (o["match"] >= 0).sum() > 100
+    check_line_match(g, o)
+
+
+def test_line_match_more_than_512_lines_takes_tile_path(gpu_ctx):
+    p = synth.make_line_match_batch(2, 700, 64, 5)
+    check_line_match(api.line_match(p, impl="gpu", ctx=gpu_ctx), api.line_match(p, impl="oracle"))
+
+
 def test_line_match_ragged(gpu_ctx, line_path):
     p = synth.make_line_match_batch(5, 60, 64, 2, ragged=True)
     check_line_match(api.line_match(p, impl="gpu", ctx=gpu_ctx), api.line_match(p, impl="oracle"))
