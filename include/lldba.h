@@ -274,6 +274,42 @@ typedef struct lld_sbp_mp_problem {
 
 int lld_sbp_mappoints(void* ctx, const lld_sbp_mp_problem* p, lld_sbp_result* out);
 
+/* Windowed Hamming search of projected map points in a KEYFRAME, batched over (keyframe, point set) pairs:
+ *   ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th)                      src/ORBmatcher.cc:825-975   chi2_gate = 1, sequential_claims = 0
+ *   ORBmatcher::Fuse(KeyFrame*, cv::Mat Scw, const vector<MapPoint*>&, th, ...)   src/ORBmatcher.cc:977-1100  chi2_gate = 0, sequential_claims = 0
+ *   ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) src/ORBmatcher.cc:290-403 chi2_gate = 0, sequential_claims = 1,
+ *                                                                                   kp_claimed = (vpMatched[idx] != NULL) on entry
+ * The caller does what precedes the search in those functions (projection with Rcw / tcw or the decomposed Scw, depth, image bounds,
+ * distance-invariance and viewing-angle tests, MapPoint::PredictScale -- its logf stays on the host) and passes u, v, ur and the predicted
+ * level; invalid points are flagged in mp_valid.  The library runs KeyFrame::GetFeaturesInArea (radius th * mvScaleFactors[level], same
+ * 64 x 48 grid as the Frame), the level window [level - 1, level], the optional reprojection gate of Fuse
+ * (e2 * mvInvLevelSigma2[kpLevel] > 7.8 with mvuRight >= 0, > 5.99 otherwise; :905-925), strict-< first-minimum selection, acceptance at
+ * bestDist <= th_low, and -- with sequential_claims -- the rule that an accepted match removes its keypoint for the points after it.
+ * What follows the search in Fuse (Replace / AddObservation under the map mutex) stays with the caller, fed from best_idx.
+ * Result: lld_sbp_result; best_idx / best_dist per map point (-1 / 256 when not accepted), match = last accepted point per keypoint. */
+typedef struct lld_kf_search_problem {
+  int32_t n_pairs;
+  lld_frame_geom geom;
+  float th;
+  int32_t th_low;             /* TH_LOW = 50 */
+  int32_t chi2_gate;
+  int32_t sequential_claims;
+  float inv_level_sigma2[8];  /* mvInvLevelSigma2 */
+  const int32_t* kp_off;      /* [n_pairs+1] keyframe keypoints */
+  const float* kp_xy;         /* [n_kp][2] mvKeysUn */
+  const uint8_t* kp_octave;
+  const float* kp_uright;     /* mvuRight (< 0: monocular keypoint) */
+  const uint8_t* kp_desc;     /* [n_kp][32] */
+  const uint8_t* kp_claimed;  /* [n_kp] skipped keypoints (vpMatched[idx] on entry); zeros for Fuse */
+  const int32_t* mp_off;      /* [n_pairs+1] */
+  const uint8_t* mp_valid;    /* [n_mp] passed every test before GetFeaturesInArea */
+  const float* mp_proj;       /* [n_mp][3] u, v, ur */
+  const int32_t* mp_level;    /* [n_mp] nPredictedLevel */
+  const uint8_t* mp_desc;     /* [n_mp][32] */
+} lld_kf_search_problem;
+
+int lld_kf_search(void* ctx, const lld_kf_search_problem* p, lld_sbp_result* out);
+
 /* ------------------------------------------------------------------------------------------------
  * Stereo line matching (float line descriptors)
  * ---------------------------------------------------------------------------------------------- */

@@ -120,6 +120,19 @@ def sbp_mappoints(p: Dict[str, Any], *, impl: str = "gpu", ctx=None):
     return out
 
 
+def kf_search(p: Dict[str, Any], *, impl: str = "gpu", ctx=None):
+    """ORBmatcher::Fuse / Fuse(Scw) / SearchByProjection(KeyFrame*, Scw, ...): windowed search of projected map points in keyframes"""
+    lib = _lib(impl)
+    geom, gk = capi.make_geom(p["geom"])
+    f = dict(p); f["geom"] = geom
+    prob, keep = capi.fill_struct(capi.KfSearchProblem, f)
+    out = _sbp_out(int(p["kp_off"][-1]), int(p["mp_off"][-1]), int(p["n_pairs"]))
+    res, keep2 = capi.fill_struct(capi.SbpResult, out)
+    rc = lib.kf_search(_handle(impl, ctx), C.byref(prob), C.byref(res))
+    _check(impl, ctx, rc, "lld_kf_search")
+    return out
+
+
 def line_match(p: Dict[str, Any], *, impl: str = "gpu", ctx=None):
     lib = _lib(impl)
     prob, keep = capi.fill_struct(capi.LineMatchProblem, p)

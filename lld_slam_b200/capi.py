@@ -111,6 +111,15 @@ class SbpMpProblem(C.Structure):
     ]
 
 
+class KfSearchProblem(C.Structure):
+    _fields_ = [
+        ("n_pairs", C.c_int32), ("geom", FrameGeom), ("th", C.c_float), ("th_low", C.c_int32), ("chi2_gate", C.c_int32),
+        ("sequential_claims", C.c_int32), ("inv_level_sigma2", C.c_float * 8),
+        ("kp_off", c_i32p), ("kp_xy", c_f32p), ("kp_octave", c_u8p), ("kp_uright", c_f32p), ("kp_desc", c_u8p), ("kp_claimed", c_u8p),
+        ("mp_off", c_i32p), ("mp_valid", c_u8p), ("mp_proj", c_f32p), ("mp_level", c_i32p), ("mp_desc", c_u8p),
+    ]
+
+
 class LineMatchProblem(C.Structure):
     _fields_ = [
         ("n_pairs", C.c_int32), ("desc_dim", C.c_int32),
@@ -201,6 +210,7 @@ class _Lib:
         self._sig("pose_opt", [vp, C.POINTER(PoseProblem), C.POINTER(PoseResult)])
         self._sig("sbp_frame", [vp, C.POINTER(SbpFrameProblem), C.POINTER(SbpResult)])
         self._sig("sbp_mappoints", [vp, C.POINTER(SbpMpProblem), C.POINTER(SbpResult)])
+        self._sig("kf_search", [vp, C.POINTER(KfSearchProblem), C.POINTER(SbpResult)])
         self._sig("line_match", [vp, C.POINTER(LineMatchProblem), C.POINTER(LineMatchResult)])
         self._sig("descriptor_distance", [c_u8p, c_u8p])
         if not self.is_oracle:

@@ -29,7 +29,7 @@ constexpr int TH_HIGH = 100, HISTO_LENGTH = 30;
 
 struct MatchView {
   int n_pairs, n_cur, n_q;
-  int variant;  // 0: frame-frame (best only), 1: map points (best / second best + ratio)
+  int variant;  // 0: frame-frame (best only), 1: map points (best / second best + ratio), 2: map points -> keyframe (Fuse / Sim3 search)
   // geometry
   float fx, fy, cx, cy, bf, b;
   float min_x, max_x, min_y, max_y, winv, hinv;
@@ -76,6 +76,8 @@ struct MatchView {
   int* n_matches;  // [n_pairs]
   int th_high;         // acceptance threshold on the best distance (TH_HIGH, or ORBdist of the relocalisation variant)
   int allow_neg_z;     // no invzc < 0 rejection (relocalisation variant)
+  int chi2_gate;       // variant 2: Fuse's reprojection gate (src/ORBmatcher.cc:905-925)
+  float inv_sigma2[8]; // variant 2: mvInvLevelSigma2
   int max_cur, max_q;  // largest pair (host side dispatch)
   int fused_ok;
 };
@@ -236,6 +238,12 @@ __device__ __forceinline__ QueryWin query_window(const MatchView& v, int q, int 
     if (mode == 1) { w.minLevel = oct; w.maxLevel = -1; }
     else if (mode == 2) { w.minLevel = 0; w.maxLevel = oct; }
     else { w.minLevel = oct - 1; w.maxLevel = oct + 1; }
+  } else if (v.variant == 2) {   // Fuse / SearchByProjection(KeyFrame*, Scw, ...): radius = th * mvScaleFactors[nPredictedLevel]
+    const float* pj = v.q_xw + 3 * (size_t)q;
+    w.x = pj[0]; w.y = pj[1]; w.urq = pj[2];
+    const int lvl = v.q_level[q];
+    w.r = __fmul_rn(v.th, v.scale[lvl]);
+    w.minLevel = lvl - 1; w.maxLevel = lvl;
   } else {
     const float* pj = v.q_xw + 3 * (size_t)q;
     w.x = pj[0]; w.y = pj[1]; w.urq = pj[2];
@@ -246,6 +254,20 @@ __device__ __forceinline__ QueryWin query_window(const MatchView& v, int q, int 
     w.minLevel = lvl - 1; w.maxLevel = lvl;
   }
   return w;
+}
+
+// Per-candidate test after the window test: stereo consistency of the Frame-level searches (|ur_q - ur| <= r when the keypoint
+// has a right coordinate; src/ORBmatcher.cc:91-96,1407-1413), or, for the keyframe searches, Fuse's reprojection gate
+// e2 * mvInvLevelSigma2[kpLevel] > 7.8 (mvuRight >= 0) / 5.99 (:905-925) -- float products, compared in double like the reference
+__device__ __forceinline__ bool candidate_gate(const MatchView& v, const QueryWin& w, float dx, float dy, float ur, int oct) {
+  if (v.variant != 2) return !(ur > 0 && fabsf(__fsub_rn(w.urq, ur)) > w.r);
+  if (!v.chi2_gate) return true;
+  const float exy = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+  if (ur >= 0) {
+    const float er = __fsub_rn(w.urq, ur);
+    return !((double)__fmul_rn(__fadd_rn(exy, __fmul_rn(er, er)), v.inv_sigma2[oct]) > 7.8);
+  }
+  return !((double)__fmul_rn(exy, v.inv_sigma2[oct]) > 5.99);
 }
 
 // Scan the window of one query (one thread).  excl_below >= 0: skip keypoints owned by a query < excl_below.
@@ -286,10 +308,7 @@ __device__ __forceinline__ int scan_window(const MatchView& v, int q, int p, con
       const int idx = meta & 0xFFFF;
       if (excl_below >= 0 && own[idx] < excl_below) continue;  // owned by an earlier accepted query
       const float ur = __uint_as_float(h.z);
-      if (ur > 0) {
-        const float er = fabsf(__fsub_rn(w.urq, ur));
-        if (er > w.r) continue;
-      }
+      if (!candidate_gate(v, w, dx, dy, ur, oct)) continue;
       const int d = popc256(a0, a1, b0, b1);
       ncand++;
       unsigned long long k = pack_key(d, (meta >> 16) & 0xFFF, idx, oct);
@@ -527,12 +546,11 @@ __device__ __forceinline__ int fused_scan(const MatchView& v, const QueryWin& w,
       const int oct = (meta >> 1) & 7;
       const float dx = __fsub_rn(__uint_as_float(h.x), w.x), dy = __fsub_rn(__uint_as_float(h.y), w.y);
       const float ur = __uint_as_float(h.z);
-      const float er = fabsf(__fsub_rn(w.urq, ur));
       bool ok = !(meta & 1u);                          // not claimed on entry
       ok = ok && oct >= lvl_lo && oct <= lvl_hi;       // level range (Frame::GetFeaturesInArea)
       ok = ok && fabsf(dx) < w.r && fabsf(dy) < w.r;
       ok = ok && (int)(meta >> 16) >= excl;            // not owned by an earlier accepted query
-      ok = ok && !(ur > 0 && er > w.r);                // stereo consistency
+      ok = ok && candidate_gate(v, w, dx, dy, ur, oct);   // stereo consistency / Fuse's reprojection gate
       if (ok) {
         if (np == 4) drain();
         pend = (pend << 16) | (unsigned long long)s;
@@ -936,9 +954,12 @@ static int match_run(LldCtx* c, MatchView& v, int* passes_out) {
     if (v.variant == 0) {
       LLD_CUDA(c, lld_raise_dyn_smem(k_match_fused<0>, (size_t)L.total));
       LLD_LAUNCH(c, k_match_fused<0>, v.n_pairs, FUSED_NT, L.total, v, L);
-    } else {
+    } else if (v.variant == 1) {
       LLD_CUDA(c, lld_raise_dyn_smem(k_match_fused<1>, (size_t)L.total));
       LLD_LAUNCH(c, k_match_fused<1>, v.n_pairs, FUSED_NT, L.total, v, L);
+    } else {
+      LLD_CUDA(c, lld_raise_dyn_smem(k_match_fused<2>, (size_t)L.total));
+      LLD_LAUNCH(c, k_match_fused<2>, v.n_pairs, FUSED_NT, L.total, v, L);
     }
     LLD_CUDA(c, cudaGetLastError());
     if (passes_out) *passes_out = 0;
@@ -1103,6 +1124,60 @@ static int sbp_mp_upload(LldCtx* c, const lld_sbp_mp_problem* p, MatchView& v) {
   UPC(v.q_desc, uint8_t, p->mp_desc, 32 * (size_t)v.n_q);
   UPC(v.q_has_obs, uint8_t, p->mp_has_obs, v.n_q);
   return match_alloc_common(c, v);
+}
+
+// keyframe searches (Fuse, Fuse with Sim3, SearchByProjection with Sim3): variant 2
+static int kf_search_upload(LldCtx* c, const lld_kf_search_problem* p, MatchView& v) {
+  c->pool_reset();
+  v = MatchView();
+  v.n_pairs = p->n_pairs;
+  LLD_ARG(c, p->n_pairs >= 1);
+  v.n_cur = p->kp_off[p->n_pairs];
+  v.n_q = p->mp_off[p->n_pairs];
+  LLD_ARG(c, p->geom.n_levels >= 1 && p->geom.n_levels <= 8);
+  for (int i = 0; i < p->n_pairs; i++) LLD_ARG(c, p->kp_off[i + 1] - p->kp_off[i] <= 65535);
+  set_dispatch(v, p->kp_off, p->mp_off);
+  v.variant = 2;
+  set_geom(v, p->geom);
+  v.th = p->th; v.nn_ratio = 0.f; v.mono = 0; v.check_ori = 0;
+  v.th_high = p->th_low; v.allow_neg_z = 0;
+  v.chi2_gate = p->chi2_gate != 0;
+  for (int i = 0; i < 8; i++) v.inv_sigma2[i] = p->inv_level_sigma2[i];
+  UPC(v.scale, float, p->geom.scale_factors, p->geom.n_levels);
+  UPC(v.cur_off, int, p->kp_off, p->n_pairs + 1);
+  UPC(v.cur_xy, float, p->kp_xy, 2 * (size_t)v.n_cur);
+  UPC(v.cur_octave, uint8_t, p->kp_octave, v.n_cur);
+  UPC(v.cur_uright, float, p->kp_uright, v.n_cur);
+  UPC(v.cur_desc, uint8_t, p->kp_desc, 32 * (size_t)v.n_cur);
+  UPC(v.cur_claimed, uint8_t, p->kp_claimed, v.n_cur);
+  v.cur_angle = nullptr;
+  UPC(v.q_off, int, p->mp_off, p->n_pairs + 1);
+  UPC(v.q_valid, uint8_t, p->mp_valid, v.n_q);
+  UPC(v.q_xw, float, p->mp_proj, 3 * (size_t)v.n_q);
+  UPC(v.q_level, int, p->mp_level, v.n_q);
+  v.q_viewcos = nullptr;
+  UPC(v.q_desc, uint8_t, p->mp_desc, 32 * (size_t)v.n_q);
+  // every accepted point claims its keypoint (vpMatched[bestIdx] = pMP) or none does (Fuse)
+  uint8_t* has = nullptr;
+  UPC(has, uint8_t, nullptr, v.n_q);
+  LLD_CUDA(c, cudaMemsetAsync(has, p->sequential_claims ? 1 : 0, v.n_q ? v.n_q : 1, c->stream));
+  v.q_has_obs = has;
+  return match_alloc_common(c, v);
+}
+
+extern "C" int lld_kf_search(void* ctx, const lld_kf_search_problem* p, lld_sbp_result* out) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (!c || !p || !out) return LLD_ERR_ARG;
+  LLD_CUDA(c, cudaSetDevice(c->device));
+  c->launches = 0;
+  MatchView v;
+  LLD_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+  int r = kf_search_upload(c, p, v);
+  if (r) return r;
+  LLD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  r = match_run(c, v, nullptr);
+  if (r) return r;
+  return match_download(c, v, out);
 }
 
 extern "C" int lld_sbp_frame(void* ctx, const lld_sbp_frame_problem* p, lld_sbp_result* out) {

@@ -46,6 +46,13 @@ struct KeyFrame {
   bool bad = false;
   bool isBad() const { return bad; }
   std::vector<struct MapPoint*> mvpMapPoints;   // GetMapPointMatches()
+  // what the keyframe-targeted searches read (ORBmatcher::Fuse, SearchByProjection(KeyFrame*, Scw, ...)): include/KeyFrame.h:160-200
+  float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0;
+  std::vector<float> mvScaleFactors;
+  float mfLogScaleFactor = 0;
+  int mnScaleLevels = 0;
+  std::vector<uint8_t> mDescriptors;            // N x 32
+  bool IsInImage(float x, float y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }   // src/KeyFrame.cc:639-642
   // GBA shadow fields (src/Optimizer.cc:509-512)
   float mTcwGBA[12];
   unsigned long mnBAGlobalForKF = 0;
@@ -64,6 +71,8 @@ struct MapPoint {
   float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, mTrackViewCos = 0;
   int mnTrackScaleLevel = 0;
   uint8_t mDescriptor[32] = {0};                     // GetDescriptor()
+  float mNormalVector[3] = {0, 0, 1};                // GetNormal()
+  bool IsInKeyFrame(KeyFrame* pKF) const { return observations.count(pKF) != 0; }
   float mfMinDistance = 0, mfMaxDistance = 0;        // scale-invariance range (src/MapPoint.cc:373-383)
   float GetMinDistanceInvariance() const { return 0.8f * mfMinDistance; }
   float GetMaxDistanceInvariance() const { return 1.2f * mfMaxDistance; }
@@ -668,6 +677,84 @@ class ORBmatcher {
       if (match[(size_t)i] >= 0) F.mvpMapPoints[i] = vpMapPoints[(size_t)match[(size_t)i]];   // F.mvpMapPoints[bestIdx] = pMP (:123)
     if (match_out) match_out->assign(match.begin(), match.begin() + F.N);
     return nm;
+  }
+  // What ORBmatcher::Fuse decides for one map point (src/ORBmatcher.cc:949-968); Replace() itself is map bookkeeping and stays
+  // with the caller: `survivor` replaces `replaced`; both null = a new observation was added (done here)
+  struct FuseAction { MapPoint* pMP; int bestIdx; MapPoint* survivor; MapPoint* replaced; };
+  // int Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th = 3.0)   include/ORBmatcher.h:80, src/ORBmatcher.cc:825-975
+  // Host part = everything before GetFeaturesInArea, in the reference's float arithmetic (cv::Mat CV_32F products accumulate in
+  // double and round once); the windowed search with the reprojection gate is lld_kf_search; the sequential Replace / Add logic
+  // runs afterwards over the accepted points in order.
+  int Fuse(void* ctx, KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, float th = 3.0f, std::vector<FuseAction>* actions = nullptr) {
+    const float* T = pKF->Tcw;
+    auto row = [&](int r, const float* x, float t) { return (float)((double)T[3 * r] * x[0] + (double)T[3 * r + 1] * x[1] + (double)T[3 * r + 2] * x[2] + (double)t); };
+    float Ow[3];   // KeyFrame::SetPose: Ow = -Rcw.t() * tcw  (src/KeyFrame.cc:75-90)
+    for (int k = 0; k < 3; k++) Ow[k] = (float)(-((double)T[k] * T[9] + (double)T[3 + k] * T[10] + (double)T[6 + k] * T[11]));
+    const size_t n = vpMapPoints.size(), N = pKF->mvKeysUn.size();
+    std::vector<uint8_t> valid(n, 0), desc(32 * n, 0), koct(N), claimed(N, 0);
+    std::vector<float> proj(3 * n, 0.f), kxy(2 * N);
+    std::vector<int32_t> lvl(n, 0);
+    for (size_t i = 0; i < n; i++) {
+      MapPoint* pMP = vpMapPoints[i];
+      if (!pMP) continue;
+      if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+      const float* Xw = pMP->pos;
+      const float xc = row(0, Xw, T[9]), yc = row(1, Xw, T[10]), zc = row(2, Xw, T[11]);
+      if (zc < 0.0f) continue;                                          // :851
+      const float invz = 1 / zc;
+      const float x = xc * invz, y = yc * invz;
+      const float u = pKF->fx * x + pKF->cx, v = pKF->fy * y + pKF->cy;
+      if (!pKF->IsInImage(u, v)) continue;                              // :862
+      const float ur = u - pKF->mbf * invz;
+      const float PO[3] = {Xw[0] - Ow[0], Xw[1] - Ow[1], Xw[2] - Ow[2]};
+      const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);   // cv::norm
+      if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;            // :873
+      const float* Pn = pMP->mNormalVector;
+      if ((double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2] < 0.5 * dist3D) continue;            // :879
+      valid[i] = 1;
+      proj[3 * i] = u; proj[3 * i + 1] = v; proj[3 * i + 2] = ur;
+      lvl[i] = pMP->PredictScale(dist3D, pKF->mfLogScaleFactor, pKF->mnScaleLevels);
+      std::memcpy(&desc[32 * i], pMP->mDescriptor, 32);
+    }
+    for (size_t i = 0; i < N; i++) { kxy[2 * i] = pKF->mvKeysUn[i].x; kxy[2 * i + 1] = pKF->mvKeysUn[i].y; koct[i] = (uint8_t)pKF->mvKeysUn[i].octave; }
+    lld_kf_search_problem p;
+    std::memset(&p, 0, sizeof(p));
+    p.n_pairs = 1;
+    p.geom.fx = pKF->fx; p.geom.fy = pKF->fy; p.geom.cx = pKF->cx; p.geom.cy = pKF->cy; p.geom.bf = pKF->mbf;
+    p.geom.min_x = pKF->mnMinX; p.geom.max_x = pKF->mnMaxX; p.geom.min_y = pKF->mnMinY; p.geom.max_y = pKF->mnMaxY;
+    p.geom.n_levels = (int)pKF->mvScaleFactors.size(); p.geom.scale_factors = pKF->mvScaleFactors.data();
+    p.th = th; p.th_low = 50; p.chi2_gate = 1; p.sequential_claims = 0;
+    for (size_t l = 0; l < 8 && l < pKF->mvInvLevelSigma2.size(); l++) p.inv_level_sigma2[l] = pKF->mvInvLevelSigma2[l];
+    const int32_t ko[2] = {0, (int32_t)N}, mo[2] = {0, (int32_t)n};
+    p.kp_off = ko; p.kp_xy = kxy.data(); p.kp_octave = koct.data(); p.kp_uright = pKF->mvuRight.data(); p.kp_desc = pKF->mDescriptors.data();
+    p.kp_claimed = claimed.data();
+    p.mp_off = mo; p.mp_valid = valid.data(); p.mp_proj = proj.data(); p.mp_level = lvl.data(); p.mp_desc = desc.data();
+    std::vector<int32_t> match(N + 1, -1), best(n + 1, -1), bdist(n + 1, 256);
+    int32_t nm = 0;
+    lld_sbp_result r;
+    std::memset(&r, 0, sizeof(r));
+    r.match = match.data(); r.n_matches = &nm; r.best_idx = best.data(); r.best_dist = bdist.data();
+    const int rc = lld_kf_search(ctx, &p, &r);
+    if (rc) return rc;
+    int nFused = 0;
+    for (size_t i = 0; i < n; i++) {                                    // :949-968, in the order of vpMapPoints
+      if (best[i] < 0) continue;
+      MapPoint* pMP = vpMapPoints[i];
+      MapPoint* pMPinKF = pKF->mvpMapPoints[(size_t)best[i]];
+      FuseAction a{pMP, best[i], nullptr, nullptr};
+      if (pMPinKF) {
+        if (!pMPinKF->isBad()) {
+          if (pMPinKF->Observations() > pMP->Observations()) { a.survivor = pMPinKF; a.replaced = pMP; }
+          else { a.survivor = pMP; a.replaced = pMPinKF; }
+        }
+      } else {
+        pMP->observations[pKF] = (size_t)best[i];
+        pKF->mvpMapPoints[(size_t)best[i]] = pMP;
+      }
+      if (actions) actions->push_back(a);
+      nFused++;
+    }
+    return nFused;
   }
  private:
   float mfNNratio;

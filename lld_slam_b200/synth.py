@@ -544,6 +544,23 @@ def make_sbp_mp_batch(n_pairs, n_kp, n_mp, seed, th=3.0, nn_ratio=0.8):
     )
 
 
+def make_kf_search_batch(n_pairs, n_kp, n_mp, seed, th=3.0, th_low=50, chi2_gate=1, sequential_claims=0):
+    """Fuse / SearchByProjection(KeyFrame*, Scw, ...): map points already projected into the keyframes (u, v, ur, predicted level);
+    most of them sit within a few pixels of a keypoint whose descriptor they share up to a few bits, so that the reprojection gate
+    and TH_LOW both cut; several points per keypoint, so that the sequential claims matter"""
+    m = make_sbp_mp_batch(n_pairs, n_kp, n_mp, seed, th=th)
+    rng = np.random.default_rng(seed + 17)
+    ur = m["cur_uright"].copy()
+    ur[ur < 0] = -1.0
+    return dict(
+        n_pairs=n_pairs, geom=m["geom"], th=float(th), th_low=int(th_low), chi2_gate=int(chi2_gate), sequential_claims=int(sequential_claims),
+        inv_level_sigma2=np.pad(inv_level_sigma2(), (0, max(0, 8 - N_LEVELS)))[:8],
+        kp_off=m["cur_off"], kp_xy=m["cur_xy"], kp_octave=m["cur_octave"], kp_uright=ur, kp_desc=m["cur_desc"],
+        kp_claimed=m["cur_claimed"] if sequential_claims else np.zeros_like(m["cur_claimed"]),
+        mp_off=m["mp_off"], mp_valid=m["mp_valid"], mp_proj=m["mp_proj"], mp_level=m["mp_level"], mp_desc=m["mp_desc"],
+    )
+
+
 def make_line_match_batch(n_pairs, n_lines, desc_dim, seed, tau=2.0, min_len=10, ragged=False):
     rng = np.random.default_rng(seed)
     P, N, D = n_pairs, n_lines, desc_dim

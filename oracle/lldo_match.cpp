@@ -257,6 +257,66 @@ int lldo_sbp_mappoints(void*, const lld_sbp_mp_problem* p, lld_sbp_result* out) 
   return 0;
 }
 
+// ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) src/ORBmatcher.cc:825-975, Fuse(KeyFrame*, Scw, ...) :977-1100 and
+// SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) :290-403: the part from KeyFrame::GetFeaturesInArea to the acceptance
+int lldo_kf_search(void*, const lld_kf_search_problem* p, lld_sbp_result* out) {
+  const lld_frame_geom& g = p->geom;
+  std::vector<int> cand;
+  for (int pr = 0; pr < p->n_pairs; pr++) {
+    const int c0 = p->kp_off[pr], nc = p->kp_off[pr + 1] - c0;
+    const int m0 = p->mp_off[pr], nm = p->mp_off[pr + 1] - m0;
+    const float* xy = p->kp_xy + 2 * (size_t)c0;
+    const uint8_t* oct = p->kp_octave + c0;
+    Grid G;
+    G.build(g, xy, nc);
+    std::vector<int> match(nc, -1);
+    std::vector<uint8_t> matched(p->kp_claimed + c0, p->kp_claimed + c0 + nc);   // vpMatched[idx] != NULL
+    int nmatches = 0;
+    for (int iMP = 0; iMP < nm; iMP++) {
+      if (out->best_idx) out->best_idx[m0 + iMP] = -1;
+      if (out->best_dist) out->best_dist[m0 + iMP] = 256;
+      if (!p->mp_valid[m0 + iMP]) continue;
+      const int nPredictedLevel = p->mp_level[m0 + iMP];
+      const float* pj = p->mp_proj + 3 * (size_t)(m0 + iMP);
+      const float u = pj[0], v = pj[1], ur = pj[2];
+      const float radius = p->th * g.scale_factors[nPredictedLevel];
+      G.features_in_area(u, v, radius, -1, -1, xy, oct, cand);   // KeyFrame::GetFeaturesInArea has no level filter
+      if (cand.empty()) continue;
+      const uint8_t* dMP = p->mp_desc + 32 * (size_t)(m0 + iMP);
+      int bestDist = 256, bestIdx = -1;
+      for (int idx : cand) {
+        if (matched[idx]) continue;
+        const int kpLevel = oct[idx];
+        if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+        if (p->chi2_gate) {
+          const float kpx = xy[2 * idx], kpy = xy[2 * idx + 1];
+          const float ex = u - kpx, ey = v - kpy;
+          if (p->kp_uright[c0 + idx] >= 0) {
+            const float er = ur - p->kp_uright[c0 + idx];
+            const float e2 = ex * ex + ey * ey + er * er;
+            if (e2 * p->inv_level_sigma2[kpLevel] > 7.8) continue;
+          } else {
+            const float e2 = ex * ex + ey * ey;
+            if (e2 * p->inv_level_sigma2[kpLevel] > 5.99) continue;
+          }
+        }
+        const int dist = descriptor_distance(dMP, p->kp_desc + 32 * (size_t)(c0 + idx));
+        if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+      }
+      if (bestDist <= p->th_low) {
+        match[bestIdx] = iMP;
+        if (p->sequential_claims) matched[bestIdx] = 1;
+        nmatches++;
+        if (out->best_idx) out->best_idx[m0 + iMP] = bestIdx;
+        if (out->best_dist) out->best_dist[m0 + iMP] = bestDist;
+      }
+    }
+    for (int i = 0; i < nc; i++) out->match[c0 + i] = match[i];
+    out->n_matches[pr] = nmatches;
+  }
+  return 0;
+}
+
 // ---- TwoFrameLineMatcher ----------------------------------------------------------------------
 static double line_length(const float* s) {  // LineLength src/LineMatching.cc:50-59
   const double dx = (double)s[0] - (double)s[2], dy = (double)s[1] - (double)s[3];

@@ -3,7 +3,7 @@
 // what they wrote back into the objects.  It also compares the shim's own flattening with the input arrays element by
 // element, which catches ordering bugs (std::map<KeyFrame*> iteration, proj_map by mnId, local-then-fixed keyframes).
 //
-//   shim_run <mode> <in.bin> <out.bin>      mode = local | global | pose
+//   shim_run <mode> <in.bin> <out.bin>      mode = local | global | pose | fuse
 // Built twice by the tests: against liblldba.so (GPU) and, with -DLLD_SHIM_ORACLE, against oracle/liblld_oracle.so (the
 // same C-ABI under the lldo_ prefix) so that the host logic is covered on a CPU-only box.
 #ifdef LLD_SHIM_ORACLE
@@ -12,6 +12,7 @@
 #define lld_pose_opt lldo_pose_opt
 #define lld_sbp_frame lldo_sbp_frame
 #define lld_sbp_mappoints lldo_sbp_mappoints
+#define lld_kf_search lldo_kf_search
 #define lld_line_match lldo_line_match
 #define lld_descriptor_distance lldo_descriptor_distance
 #endif
@@ -298,6 +299,65 @@ int main(int argc, char** argv) {
     }
     out("Tcw", 'f', Tout.data(), Tout.size()); out("n_inliers", 'i', ninl.data(), ninl.size());
     out("pt_outlier", 'b', pout.data(), pout.size()); out("ln_outlier", 'b', lout.data(), lout.size());
+  } else if (mode == "fuse") {
+    // one keyframe, its keypoints (some already carrying a map point), a list of candidate map points: ORBmatcher::Fuse
+    lld::KeyFrame kf;
+    for (int c = 0; c < 12; c++) kf.Tcw[c] = in<float>("Tcw")[c];
+    const float* it = in<float>("intr");
+    kf.fx = it[0]; kf.fy = it[1]; kf.cx = it[2]; kf.cy = it[3]; kf.mbf = it[4];
+    const float* bd = in<float>("bounds");
+    kf.mnMinX = bd[0]; kf.mnMaxX = bd[1]; kf.mnMinY = bd[2]; kf.mnMaxY = bd[3];
+    const int nl = (int)in_n("scale_factors");
+    kf.mvScaleFactors.assign(in<float>("scale_factors"), in<float>("scale_factors") + nl);
+    kf.mvInvLevelSigma2.assign(in<float>("inv_level_sigma2"), in<float>("inv_level_sigma2") + nl);
+    kf.mfLogScaleFactor = in<float>("log_scale_factor")[0];
+    kf.mnScaleLevels = nl;
+    const int N = (int)in_n("kp_octave");
+    for (int i = 0; i < N; i++) {
+      lld::KeyPoint kp;
+      kp.x = in<float>("kp_xy")[2 * i]; kp.y = in<float>("kp_xy")[2 * i + 1]; kp.octave = in<int32_t>("kp_octave")[i]; kp.angle = 0;
+      kf.mvKeysUn.push_back(kp);
+    }
+    kf.mvuRight.assign(in<float>("kp_uright"), in<float>("kp_uright") + N);
+    kf.mDescriptors.assign(in<uint8_t>("kp_desc"), in<uint8_t>("kp_desc") + 32 * (size_t)N);
+    const int M = (int)in_n("mp_nobs");
+    std::vector<lld::MapPoint> mps(M), existing(N);
+    std::vector<lld::KeyFrame> others(8);             // observers that only make Observations() count
+    kf.mvpMapPoints.assign(N, nullptr);
+    for (int i = 0; i < N; i++) {
+      const int nobs = in<int32_t>("kp_mp_nobs")[i];  // < 0: the keypoint has no map point
+      if (nobs < 0) continue;
+      existing[i].mnId = 100000 + i;
+      for (int o = 0; o < nobs && o < 8; o++) existing[i].observations[&others[o]] = 0;
+      kf.mvpMapPoints[i] = &existing[i];
+    }
+    std::vector<lld::MapPoint*> vp;
+    for (int i = 0; i < M; i++) {
+      lld::MapPoint& m = mps[i];
+      m.mnId = i;
+      for (int c = 0; c < 3; c++) { m.pos[c] = in<float>("mp_pos")[3 * i + c]; m.mNormalVector[c] = in<float>("mp_normal")[3 * i + c]; }
+      m.mfMinDistance = in<float>("mp_minmax")[2 * i]; m.mfMaxDistance = in<float>("mp_minmax")[2 * i + 1];
+      std::memcpy(m.mDescriptor, in<uint8_t>("mp_desc") + 32 * (size_t)i, 32);
+      m.bad = in<uint8_t>("mp_bad")[i] != 0;
+      for (int o = 0; o < in<int32_t>("mp_nobs")[i] && o < 8; o++) m.observations[&others[o]] = 0;
+      if (in<uint8_t>("mp_in_kf")[i]) m.observations[&kf] = 0;
+      vp.push_back(in<uint8_t>("mp_null")[i] ? nullptr : &m);
+    }
+    lld::ORBmatcher matcher(0.6f, true);
+    std::vector<lld::ORBmatcher::FuseAction> acts;
+    const int nFused = matcher.Fuse(ctx, &kf, vp, in<float>("th")[0], &acts);
+    if (nFused < 0) rc = nFused;
+    std::vector<int32_t> a_mp, a_idx, a_kind, kf_mp(N, -1);
+    for (auto& a : acts) {
+      a_mp.push_back((int32_t)a.pMP->mnId); a_idx.push_back(a.bestIdx);
+      a_kind.push_back(a.survivor == nullptr ? 0 : (a.survivor == a.pMP ? 1 : 2));   // 0 added, 1 the new point survives, 2 the keyframe's point survives
+    }
+    for (int i = 0; i < N; i++)
+      if (kf.mvpMapPoints[i]) kf_mp[i] = (int32_t)kf.mvpMapPoints[i]->mnId;
+    const int32_t nf = nFused;
+    out("n_fused", 'i', &nf, 1);
+    out("act_mp", 'i', a_mp.data(), a_mp.size()); out("act_idx", 'i', a_idx.data(), a_idx.size()); out("act_kind", 'i', a_kind.data(), a_kind.size());
+    out("kf_mp", 'i', kf_mp.data(), kf_mp.size());
   } else {
     return 2;
   }

@@ -591,3 +591,83 @@ def test_oracle_line_association_against_numpy(built):
     assert added.min() > 20
     # the true map line is what gets associated for the unambiguous (non-clutter) lines
     assert (ref >= 0).sum() > 100
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# keyframe searches (Fuse, Fuse with Sim3, SearchByProjection with Sim3)
+# ------------------------------------------------------------------------------------------------------------------
+def _kf_search_python(p):
+    """Independent transcription of the loop bodies of ORBmatcher::Fuse (src/ORBmatcher.cc:886-972), Fuse(Scw) (:1040-1097) and
+    SearchByProjection(KeyFrame*, Scw, ...) (:350-399) from KeyFrame::GetFeaturesInArea (src/KeyFrame.cc: cell range by floor / ceil of
+    (x - mnMinX -+ r) * mfGridElementWidthInv, |dx| < r && |dy| < r) on, in float32 arithmetic, plain loops, its own grid."""
+    f = np.float32
+    g = p["geom"]
+    minx, miny = f(g["min_x"]), f(g["min_y"])
+    winv = f(64) / (f(g["max_x"]) - minx)
+    hinv = f(48) / (f(g["max_y"]) - miny)
+    sf = np.asarray(g["scale_factors"], np.float32)
+    inv = np.asarray(p["inv_level_sigma2"], np.float32)
+    n_mp = int(p["mp_off"][-1])
+    best_idx = np.full(n_mp, -1, np.int32); best_dist = np.full(n_mp, 256, np.int32)
+    match = np.full(int(p["kp_off"][-1]), -1, np.int32); n_matches = np.zeros(p["n_pairs"], np.int32)
+    for pr in range(p["n_pairs"]):
+        c0, c1 = int(p["kp_off"][pr]), int(p["kp_off"][pr + 1])
+        xy = p["kp_xy"][c0:c1]; octv = p["kp_octave"][c0:c1]; kur = p["kp_uright"][c0:c1]; kd = p["kp_desc"][c0:c1]
+        cells = {}
+        for i in range(c1 - c0):                                   # KeyFrame keeps Frame::AssignFeaturesToGrid's grid
+            px = int(np.round((xy[i, 0] - minx) * winv)); py = int(np.round((xy[i, 1] - miny) * hinv))
+            if 0 <= px < 64 and 0 <= py < 48:
+                cells.setdefault((px, py), []).append(i)
+        matched = p["kp_claimed"][c0:c1].astype(bool).copy()
+        for q in range(int(p["mp_off"][pr]), int(p["mp_off"][pr + 1])):
+            if not p["mp_valid"][q]:
+                continue
+            u, v, ur = (f(x) for x in p["mp_proj"][q]); lvl = int(p["mp_level"][q])
+            r = f(p["th"]) * sf[lvl]
+            x0 = max(0, int(np.floor((u - minx - r) * winv))); x1 = min(63, int(np.ceil((u - minx + r) * winv)))
+            y0 = max(0, int(np.floor((v - miny - r) * hinv))); y1 = min(47, int(np.ceil((v - miny + r) * hinv)))
+            if x0 >= 64 or x1 < 0 or y0 >= 48 or y1 < 0:
+                continue
+            bd, bi = 256, -1
+            for ix in range(x0, x1 + 1):
+                for iy in range(y0, y1 + 1):
+                    for idx in cells.get((ix, iy), ()):
+                        if not (abs(xy[idx, 0] - u) < r and abs(xy[idx, 1] - v) < r):
+                            continue
+                        if matched[idx]:
+                            continue
+                        kl = int(octv[idx])
+                        if kl < lvl - 1 or kl > lvl:
+                            continue
+                        if p["chi2_gate"]:
+                            ex = u - xy[idx, 0]; ey = v - xy[idx, 1]
+                            if kur[idx] >= 0:
+                                er = ur - kur[idx]
+                                e2 = f(f(ex * ex) + f(ey * ey)) + f(er * er)
+                                if float(f(e2) * inv[kl]) > 7.8:
+                                    continue
+                            else:
+                                e2 = f(ex * ex) + f(ey * ey)
+                                if float(f(e2) * inv[kl]) > 5.99:
+                                    continue
+                        d = int(np.unpackbits(np.bitwise_xor(p["mp_desc"][q], kd[idx])).sum())
+                        if d < bd:
+                            bd, bi = d, idx
+            if bd <= p["th_low"]:
+                match[c0 + bi] = q - int(p["mp_off"][pr])
+                if p["sequential_claims"]:
+                    matched[bi] = True
+                n_matches[pr] += 1
+                best_idx[q] = bi; best_dist[q] = bd
+    return dict(match=match, n_matches=n_matches, best_idx=best_idx, best_dist=best_dist)
+
+
+@pytest.mark.parametrize("mode", [(1, 0), (0, 0), (0, 1)])
+def test_oracle_kf_search_against_python(built, mode):
+    from lld_slam_b200 import api, synth
+    p = synth.make_kf_search_batch(2, 500, 400, 41 + mode[0] + 2 * mode[1], chi2_gate=mode[0], sequential_claims=mode[1])
+    o = api.kf_search(p, impl="oracle")
+    r = _kf_search_python(p)
+    for k in ("match", "n_matches", "best_idx", "best_dist"):
+        assert np.array_equal(o[k], r[k]), k
+    assert int(o["n_matches"].sum()) > 100

@@ -604,6 +604,18 @@ def test_sbp_relocalisation_variant(gpu_ctx):
     assert int(o["n_matches"].sum()) > 1000
 
 
+@pytest.mark.parametrize("mode", [(1, 0), (0, 0), (0, 1)])
+def test_kf_search_variants(gpu_ctx, match_path, mode):
+    """SURVEY §8(f) row 2: ORBmatcher::Fuse (reprojection gate), Fuse with Sim3 (no gate) and SearchByProjection(KeyFrame*, Scw, ...)
+    (sequential claims): bit-exact against the oracle (itself pinned by a Python transcription), fused and multi-kernel paths"""
+    p = synth.make_kf_search_batch(48, 1800, 1500, 300 + mode[0] + 2 * mode[1], chi2_gate=mode[0], sequential_claims=mode[1])
+    g = api.kf_search(p, impl="gpu", ctx=gpu_ctx)
+    o = api.kf_search(p, impl="oracle")
+    for k in ("match", "n_matches", "best_idx", "best_dist"):
+        assert np.array_equal(g[k], o[k]), (k, mode)
+    assert int(o["n_matches"].sum()) > 48 * 300
+
+
 def test_temporal_line_association(gpu_ctx):
     """SURVEY §8(f) row 3, Tracking::AddLinesFrom: reprojection gates in both images, descriptor argmin with first-wins ties,
     sequential claims; index-exact against the oracle, ragged frames, more candidates than lanes"""

@@ -121,6 +121,133 @@ def _check_pose(exe, tmp_path, impl, ctx=None):
     assert np.array_equal(got["n_inliers"], ref["n_inliers"])
 
 
+def _fuse_scene(seed, n_kp=900, n_mp=700):
+    """one keyframe looking down +z, keypoints = projections of random 3D points (70 % stereo), candidate map points = those 3D
+    points moved by a few centimetres (+ unrelated ones, bad ones, null entries, points already in the keyframe, points behind
+    the camera, outside the distance range or seen from behind)"""
+    rng = np.random.default_rng(seed)
+    f32 = np.float32
+    g = synth.frame_geom()
+    sf = np.asarray(g["scale_factors"], f32)
+    nl = len(sf)
+    yaw = 0.1
+    R = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+    t = np.array([0.3, -0.1, 0.5])
+    Tcw = np.concatenate([R.reshape(-1), t]).astype(f32)
+    Xc = np.stack([rng.uniform(-8, 8, n_kp), rng.uniform(-2.5, 2.5, n_kp), rng.uniform(4, 30, n_kp)], 1)
+    Xw = (R.T @ (Xc - t).T).T
+    u = g["fx"] * Xc[:, 0] / Xc[:, 2] + g["cx"]; v = g["fy"] * Xc[:, 1] / Xc[:, 2] + g["cy"]
+    keep = (u > g["min_x"] + 5) & (u < g["max_x"] - 5) & (v > g["min_y"] + 5) & (v < g["max_y"] - 5)
+    Xw, Xc, u, v = Xw[keep], Xc[keep], u[keep], v[keep]
+    N = len(u)
+    kp_oct = rng.integers(0, nl, N).astype(np.int32)
+    stereo = rng.random(N) < 0.7
+    kp_ur = np.where(stereo, u - g["bf"] / Xc[:, 2], -1.0).astype(f32)
+    kp_desc = rng.integers(0, 256, (N, 32), dtype=np.uint8)
+    kp_mp_nobs = np.where(rng.random(N) < 0.3, rng.integers(0, 6, N), -1).astype(np.int32)
+    src = rng.integers(0, N, n_mp)
+    rel = rng.random(n_mp) < 0.75
+    pos = np.where(rel[:, None], Xw[src] + rng.normal(0, 0.02, (n_mp, 3)), rng.uniform(-10, 10, (n_mp, 3)) + np.array([0, 0, 12.0]))
+    Ow = -R.T @ t
+    dist = np.linalg.norm(pos - Ow, axis=1)
+    lvl = np.where(rel, kp_oct[src], rng.integers(0, nl, n_mp))
+    # mfMaxDistance such that PredictScale lands on (about) the keypoint's level: ratio = max / dist = 1.2^level
+    maxd = dist * sf[0] ** 0 * (1.2 ** (lvl - 0.3))
+    mind = maxd / 1.2 ** (nl - 1)
+    normal = (Ow - pos) / dist[:, None] * -1.0            # viewing direction from the camera: PO.Pn = dist
+    back = rng.random(n_mp) < 0.05
+    normal[back] *= -1                                     # seen from behind: rejected
+    far = rng.random(n_mp) < 0.05
+    maxd[far] = dist[far] * 0.5                            # outside the scale-invariance range
+    desc = np.where(rel[:, None], synth._flip_bits(kp_desc[src][None], 0.07, rng)[0], rng.integers(0, 256, (n_mp, 32), dtype=np.uint8)).astype(np.uint8)
+    return dict(
+        Tcw=Tcw, intr=np.array([g["fx"], g["fy"], g["cx"], g["cy"], g["bf"]], f32),
+        bounds=np.array([g["min_x"], g["max_x"], g["min_y"], g["max_y"]], f32), scale_factors=sf,
+        inv_level_sigma2=np.ascontiguousarray(synth.inv_level_sigma2()[:nl], f32), log_scale_factor=np.array([np.log(f32(1.2))], f32),
+        kp_xy=np.ascontiguousarray(np.stack([u, v], 1), f32), kp_octave=kp_oct, kp_uright=kp_ur, kp_desc=np.ascontiguousarray(kp_desc),
+        kp_mp_nobs=kp_mp_nobs,
+        mp_pos=np.ascontiguousarray(pos, f32), mp_normal=np.ascontiguousarray(normal, f32),
+        mp_minmax=np.ascontiguousarray(np.stack([mind, maxd], 1), f32), mp_desc=np.ascontiguousarray(desc),
+        mp_bad=(rng.random(n_mp) < 0.03).astype(np.uint8), mp_in_kf=(rng.random(n_mp) < 0.03).astype(np.uint8),
+        mp_null=(rng.random(n_mp) < 0.02).astype(np.uint8), mp_nobs=rng.integers(0, 6, n_mp).astype(np.int32),
+        th=np.array([3.0], f32)), g
+
+
+def _fuse_expected(d, g, impl, ctx):
+    """the reference's Fuse from numpy: float32 projection with double accumulation (cv::Mat products), the tests of
+    src/ORBmatcher.cc:851-880, MapPoint::PredictScale, then lld_kf_search through the C-ABI and the sequential Replace / Add rule"""
+    f32, f64 = np.float32, np.float64
+    T = d["Tcw"]; R = T[:9].reshape(3, 3).astype(f64); t = T[9:].astype(f64)
+    M = len(d["mp_nobs"])
+    Ow = (-(R.T @ t)).astype(f32)
+    valid = np.zeros(M, np.uint8); proj = np.zeros((M, 3), f32); lvl = np.zeros(M, np.int32)
+    fx, fy, cx, cy, bf = (f32(x) for x in d["intr"])
+    minx, maxx, miny, maxy = (f32(x) for x in d["bounds"])
+    nl = len(d["scale_factors"])
+    for i in range(M):
+        if d["mp_null"][i] or d["mp_bad"][i] or d["mp_in_kf"][i]:
+            continue
+        X = d["mp_pos"][i]
+        pc = (R @ X.astype(f64) + t).astype(f32)
+        if pc[2] < 0:
+            continue
+        invz = f32(1) / pc[2]
+        x = pc[0] * invz; y = pc[1] * invz
+        u = fx * x + cx; v = fy * y + cy
+        if not (u >= minx and u < maxx and v >= miny and v < maxy):
+            continue
+        ur = u - bf * invz
+        PO = X - Ow
+        dist = f32(np.sqrt(np.sum(PO.astype(f64) ** 2)))
+        mind, maxd = d["mp_minmax"][i]
+        if dist < f32(0.8) * mind or dist > f32(1.2) * maxd:
+            continue
+        if float(np.dot(PO.astype(f64), d["mp_normal"][i].astype(f64))) < 0.5 * float(dist):
+            continue
+        ratio = maxd / dist
+        ns = int(np.ceil(np.log(f32(ratio)) / d["log_scale_factor"][0]))
+        lvl[i] = min(max(ns, 0), nl - 1)
+        valid[i] = 1; proj[i] = (u, v, ur)
+    N = len(d["kp_octave"])
+    p = dict(n_pairs=1, geom=g, th=float(d["th"][0]), th_low=50, chi2_gate=1, sequential_claims=0,
+             inv_level_sigma2=np.pad(d["inv_level_sigma2"], (0, 8 - nl)),
+             kp_off=np.array([0, N], np.int32), kp_xy=d["kp_xy"], kp_octave=d["kp_octave"].astype(np.uint8), kp_uright=d["kp_uright"],
+             kp_desc=d["kp_desc"], kp_claimed=np.zeros(N, np.uint8),
+             mp_off=np.array([0, M], np.int32), mp_valid=valid, mp_proj=proj, mp_level=lvl, mp_desc=d["mp_desc"])
+    r = api.kf_search(p, impl=impl, ctx=ctx)
+    kf_mp = np.where(d["kp_mp_nobs"] >= 0, 100000 + np.arange(N), -1).astype(np.int32)
+    kf_nobs = d["kp_mp_nobs"].copy()
+    acts = []
+    for i in range(M):
+        b = int(r["best_idx"][i])
+        if b < 0:
+            continue
+        if kf_mp[b] >= 0:
+            in_kf_nobs = int(kf_nobs[b])
+            acts.append((i, b, 2 if in_kf_nobs > int(d["mp_nobs"][i]) else 1))
+        else:
+            kf_mp[b] = i; kf_nobs[b] = int(d["mp_nobs"][i]) + 1
+            acts.append((i, b, 0))
+    return acts, kf_mp, int(valid.sum())
+
+
+def _check_fuse(exe, tmp_path, impl, ctx=None):
+    d, g = _fuse_scene(77)
+    got = _run(exe, "fuse", d, tmp_path)
+    acts, kf_mp, n_valid = _fuse_expected(d, g, impl, ctx)
+    assert n_valid > 300 and len(acts) > 150 and len({k for _, _, k in acts}) == 3        # all three outcomes occur
+    assert int(got["n_fused"][0]) == len(acts)
+    assert np.array_equal(got["act_mp"], [a[0] for a in acts]) and np.array_equal(got["act_idx"], [a[1] for a in acts])
+    assert np.array_equal(got["act_kind"], [a[2] for a in acts])
+    assert np.array_equal(got["kf_mp"], kf_mp)
+
+
+def test_shim_fuse_on_host(tmp_path):
+    """ORBmatcher::Fuse through the shim (projection and gates on the host, lld_kf_search, sequential Replace / Add) against the
+    same function assembled in numpy around the C-ABI call"""
+    _check_fuse(_build(tmp_path, True), tmp_path, "oracle")
+
+
 def test_shim_local_ba_on_host(tmp_path):
     _check_local(_build(tmp_path, True), tmp_path, "oracle")
 
@@ -142,3 +269,4 @@ def test_shim_entry_points_on_gpu(tmp_path, gpu_ctx):
     _check_local(exe, tmp_path, "gpu", gpu_ctx)
     _check_global(exe, tmp_path, "gpu", gpu_ctx)
     _check_pose(exe, tmp_path, "gpu", gpu_ctx)
+    _check_fuse(exe, tmp_path, "gpu", gpu_ctx)
