@@ -310,6 +310,55 @@ typedef struct lld_kf_search_problem {
 
 int lld_kf_search(void* ctx, const lld_kf_search_problem* p, lld_sbp_result* out);
 
+/* ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, vMatchedPairs, bOnlyStereo)
+ * src/ORBmatcher.cc:657-823 with CheckDistEpipolarLine (:140-157), batched over keyframe pairs.
+ * Keypoints of the two keyframes that share a vocabulary node (DBoW2::FeatureVector: node id -> keypoint indices; passed as CSR
+ * lists sorted by node id, the order std::map iterates in) are compared all against all; per keypoint of KF1 without a map point the
+ * LAST keypoint of KF2's bucket (bucket order) with dist <= TH_LOW and dist <= the best so far that has no map point, is not
+ * within 10 sqrt(scale) px of the epipole (both monocular) and lies within 3.84 sigma^2 of the epipolar line wins; then the
+ * rotation-histogram filter.  (vbMatched2 is never set by the reference, so the keypoints of KF1 are independent.)
+ * The caller computes the epipole (ex, ey) (:665-671). */
+typedef struct lld_tri_search_problem {
+  int32_t n_pairs;
+  int32_t only_stereo;          /* bOnlyStereo */
+  int32_t check_orientation;    /* mbCheckOrientation */
+  int32_t n_levels;
+  float scale_factors[8];       /* pKF2->mvScaleFactors */
+  float level_sigma2[8];        /* pKF2->mvLevelSigma2 */
+  const float* F12;             /* [n_pairs][9] row-major */
+  const float* epipole;         /* [n_pairs][2] ex, ey */
+  /* keyframe 1 / keyframe 2 keypoints, CSR over pairs */
+  const int32_t* kp1_off;       /* [n_pairs+1] */
+  const float* kp1_xy;          /* [n1][2] mvKeysUn */
+  const float* kp1_angle;       /* [n1] */
+  const float* kp1_uright;      /* [n1] mvuRight */
+  const uint8_t* kp1_has_mp;    /* [n1] GetMapPoint(idx) != NULL */
+  const uint8_t* kp1_desc;      /* [n1][32] */
+  const int32_t* kp2_off;
+  const float* kp2_xy;
+  const uint8_t* kp2_octave;
+  const float* kp2_angle;
+  const float* kp2_uright;
+  const uint8_t* kp2_has_mp;
+  const uint8_t* kp2_desc;
+  /* feature vectors: per pair a run of nodes (ascending node id), per node a run of pair-local keypoint indices */
+  const int32_t* fv1_node_off;  /* [n_pairs+1] into fv1_node / fv1_idx_off */
+  const int32_t* fv1_node;      /* [n_nodes1] node ids */
+  const int32_t* fv1_idx_off;   /* [n_nodes1+1] into fv1_idx */
+  const int32_t* fv1_idx;       /* keypoint indices (pair-local) */
+  const int32_t* fv2_node_off;
+  const int32_t* fv2_node;
+  const int32_t* fv2_idx_off;
+  const int32_t* fv2_idx;
+} lld_tri_search_problem;
+
+typedef struct lld_tri_search_result {
+  int32_t* match12;    /* [n1] vMatches12: pair-local index in keyframe 2 or -1 (after the rotation filter) */
+  int32_t* n_matches;  /* [n_pairs] */
+} lld_tri_search_result;
+
+int lld_tri_search(void* ctx, const lld_tri_search_problem* p, lld_tri_search_result* out);
+
 /* ------------------------------------------------------------------------------------------------
  * Stereo line matching (float line descriptors)
  * ---------------------------------------------------------------------------------------------- */

@@ -133,6 +133,18 @@ def kf_search(p: Dict[str, Any], *, impl: str = "gpu", ctx=None):
     return out
 
 
+def tri_search(p: Dict[str, Any], *, impl: str = "gpu", ctx=None):
+    """ORBmatcher::SearchForTriangulation, batched over keyframe pairs"""
+    lib = _lib(impl)
+    prob, keep = capi.fill_struct(capi.TriSearchProblem, p)
+    out = dict(match12=np.full(max(int(p["kp1_off"][-1]), 1), -1, np.int32), n_matches=np.zeros(int(p["n_pairs"]), np.int32))
+    res, keep2 = capi.fill_struct(capi.TriSearchResult, out)
+    rc = lib.tri_search(_handle(impl, ctx), C.byref(prob), C.byref(res))
+    _check(impl, ctx, rc, "lld_tri_search")
+    out["match12"] = out["match12"][:int(p["kp1_off"][-1])]
+    return out
+
+
 def line_match(p: Dict[str, Any], *, impl: str = "gpu", ctx=None):
     lib = _lib(impl)
     prob, keep = capi.fill_struct(capi.LineMatchProblem, p)

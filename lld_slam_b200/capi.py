@@ -120,6 +120,22 @@ class KfSearchProblem(C.Structure):
     ]
 
 
+class TriSearchProblem(C.Structure):
+    _fields_ = [
+        ("n_pairs", C.c_int32), ("only_stereo", C.c_int32), ("check_orientation", C.c_int32), ("n_levels", C.c_int32),
+        ("scale_factors", C.c_float * 8), ("level_sigma2", C.c_float * 8), ("F12", c_f32p), ("epipole", c_f32p),
+        ("kp1_off", c_i32p), ("kp1_xy", c_f32p), ("kp1_angle", c_f32p), ("kp1_uright", c_f32p), ("kp1_has_mp", c_u8p), ("kp1_desc", c_u8p),
+        ("kp2_off", c_i32p), ("kp2_xy", c_f32p), ("kp2_octave", c_u8p), ("kp2_angle", c_f32p), ("kp2_uright", c_f32p), ("kp2_has_mp", c_u8p),
+        ("kp2_desc", c_u8p),
+        ("fv1_node_off", c_i32p), ("fv1_node", c_i32p), ("fv1_idx_off", c_i32p), ("fv1_idx", c_i32p),
+        ("fv2_node_off", c_i32p), ("fv2_node", c_i32p), ("fv2_idx_off", c_i32p), ("fv2_idx", c_i32p),
+    ]
+
+
+class TriSearchResult(C.Structure):
+    _fields_ = [("match12", c_i32p), ("n_matches", c_i32p)]
+
+
 class LineMatchProblem(C.Structure):
     _fields_ = [
         ("n_pairs", C.c_int32), ("desc_dim", C.c_int32),
@@ -211,6 +227,7 @@ class _Lib:
         self._sig("sbp_frame", [vp, C.POINTER(SbpFrameProblem), C.POINTER(SbpResult)])
         self._sig("sbp_mappoints", [vp, C.POINTER(SbpMpProblem), C.POINTER(SbpResult)])
         self._sig("kf_search", [vp, C.POINTER(KfSearchProblem), C.POINTER(SbpResult)])
+        self._sig("tri_search", [vp, C.POINTER(TriSearchProblem), C.POINTER(TriSearchResult)])
         self._sig("line_match", [vp, C.POINTER(LineMatchProblem), C.POINTER(LineMatchResult)])
         self._sig("descriptor_distance", [c_u8p, c_u8p])
         if not self.is_oracle:

@@ -259,8 +259,9 @@ __device__ __forceinline__ QueryWin query_window(const MatchView& v, int q, int 
 // Per-candidate test after the window test: stereo consistency of the Frame-level searches (|ur_q - ur| <= r when the keypoint
 // has a right coordinate; src/ORBmatcher.cc:91-96,1407-1413), or, for the keyframe searches, Fuse's reprojection gate
 // e2 * mvInvLevelSigma2[kpLevel] > 7.8 (mvuRight >= 0) / 5.99 (:905-925) -- float products, compared in double like the reference
+template <int VARIANT = -1>   // -1: read the variant from the view (multi-kernel path)
 __device__ __forceinline__ bool candidate_gate(const MatchView& v, const QueryWin& w, float dx, float dy, float ur, int oct) {
-  if (v.variant != 2) return !(ur > 0 && fabsf(__fsub_rn(w.urq, ur)) > w.r);
+  if ((VARIANT >= 0 ? VARIANT : v.variant) != 2) return !(ur > 0 && fabsf(__fsub_rn(w.urq, ur)) > w.r);
   if (!v.chi2_gate) return true;
   const float exy = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
   if (ur >= 0) {
@@ -497,6 +498,7 @@ static FusedLayout fused_layout(int max_cur) {
 // |dx| < r; this drops the outermost column / row that floor / ceil add (none of their keypoints can pass the test).
 // The admission test is branch-free on one 16 B header; admitted slots go to a 4-deep pending list that is drained
 // through the 256-bit popcount + top-4 insertion when full and once after the walk, where the lanes have reconverged.
+template <int VARIANT>
 __device__ __forceinline__ int fused_scan(const MatchView& v, const QueryWin& w, const uint4& a0, const uint4& a1,
                                           const uint4* __restrict__ hdr, const uint4* __restrict__ dsc,
                                           const unsigned short* __restrict__ cstart, int excl_below, unsigned* t) {
@@ -550,7 +552,7 @@ __device__ __forceinline__ int fused_scan(const MatchView& v, const QueryWin& w,
       ok = ok && oct >= lvl_lo && oct <= lvl_hi;       // level range (Frame::GetFeaturesInArea)
       ok = ok && fabsf(dx) < w.r && fabsf(dy) < w.r;
       ok = ok && (int)(meta >> 16) >= excl;            // not owned by an earlier accepted query
-      ok = ok && candidate_gate(v, w, dx, dy, ur, oct);   // stereo consistency / Fuse's reprojection gate
+      ok = ok && candidate_gate<VARIANT>(v, w, dx, dy, ur, oct);   // stereo consistency / Fuse's reprojection gate
       if (ok) {
         if (np == 4) drain();
         pend = (pend << 16) | (unsigned long long)s;
@@ -763,7 +765,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_match_fused(MatchView v, FusedL
       a1 = qd[1];
       if (v.q_has_obs[q]) hasobs |= 1u << u;
     }
-    const int n = fused_scan(v, w, a0, a1, hdr, dsc, cstart, -1, t[u]);
+    const int n = fused_scan<VARIANT>(v, w, a0, a1, hdr, dsc, cstart, -1, t[u]);
     if (n > 4) many |= 1u << u;
   }
 
@@ -822,7 +824,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_match_fused(MatchView v, FusedL
         a1 = qd[1];
       }
       unsigned tt[4];
-      fused_scan(v, w, a0, a1, hdr, dsc, cstart, qi, tt);
+      fused_scan<VARIANT>(v, w, a0, a1, hdr, dsc, cstart, qi, tt);
       if (u >= 0) {
         const unsigned acc = decide(tt[0], tt[1]);
 #pragma unroll

@@ -52,6 +52,8 @@ struct KeyFrame {
   float mfLogScaleFactor = 0;
   int mnScaleLevels = 0;
   std::vector<uint8_t> mDescriptors;            // N x 32
+  std::map<unsigned, std::vector<unsigned>> mFeatVec;   // DBoW2::FeatureVector: vocabulary node -> keypoint indices
+  std::vector<float> mvLevelSigma2;
   bool IsInImage(float x, float y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }   // src/KeyFrame.cc:639-642
   // GBA shadow fields (src/Optimizer.cc:509-512)
   float mTcwGBA[12];
@@ -676,6 +678,58 @@ class ORBmatcher {
     for (int i = 0; i < F.N; i++)
       if (match[(size_t)i] >= 0) F.mvpMapPoints[i] = vpMapPoints[(size_t)match[(size_t)i]];   // F.mvpMapPoints[bestIdx] = pMP (:123)
     if (match_out) match_out->assign(match.begin(), match.begin() + F.N);
+    return nm;
+  }
+  // int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, vector<pair<size_t,size_t>>& vMatchedPairs, bool bOnlyStereo)
+  // include/ORBmatcher.h:71-72, src/ORBmatcher.cc:657-823.  Host part: the epipole (:665-671) and the flattening of the two feature
+  // vectors (std::map iteration order = ascending node id, as the reference's merge walks them).
+  int SearchForTriangulation(void* ctx, KeyFrame* pKF1, KeyFrame* pKF2, const float F12[9],
+                             std::vector<std::pair<size_t, size_t>>& vMatchedPairs, bool bOnlyStereo, float* epipole_out = nullptr) {
+    // Cw = -R1w' t1w (KeyFrame::GetCameraCenter), C2 = R2w Cw + t2w: cv::Mat CV_32F products, double accumulation, one rounding
+    const float* T1 = pKF1->Tcw; const float* T2 = pKF2->Tcw;
+    float Cw[3], C2[3];
+    for (int k = 0; k < 3; k++) Cw[k] = (float)(-((double)T1[k] * T1[9] + (double)T1[3 + k] * T1[10] + (double)T1[6 + k] * T1[11]));
+    for (int r = 0; r < 3; r++) C2[r] = (float)((double)T2[3 * r] * Cw[0] + (double)T2[3 * r + 1] * Cw[1] + (double)T2[3 * r + 2] * Cw[2] + (double)T2[9 + r]);
+    const float invz = 1.0f / C2[2];
+    const float ep[2] = {pKF2->fx * C2[0] * invz + pKF2->cx, pKF2->fy * C2[1] * invz + pKF2->cy};
+    if (epipole_out) { epipole_out[0] = ep[0]; epipole_out[1] = ep[1]; }
+    lld_tri_search_problem p;
+    std::memset(&p, 0, sizeof(p));
+    p.n_pairs = 1; p.only_stereo = bOnlyStereo; p.check_orientation = mbCheckOrientation;
+    p.n_levels = (int)pKF2->mvScaleFactors.size();
+    for (int l = 0; l < p.n_levels && l < 8; l++) { p.scale_factors[l] = pKF2->mvScaleFactors[(size_t)l]; p.level_sigma2[l] = pKF2->mvLevelSigma2[(size_t)l]; }
+    p.F12 = F12; p.epipole = ep;
+    struct Flat { std::vector<float> xy, ang; std::vector<uint8_t> oct, has; std::vector<int32_t> node, ioff{0}, idx; int32_t koff[2], noff[2]; };
+    auto flatten = [](KeyFrame* k, Flat& f) {
+      const size_t N = k->mvKeysUn.size();
+      for (size_t i = 0; i < N; i++) {
+        f.xy.push_back(k->mvKeysUn[i].x); f.xy.push_back(k->mvKeysUn[i].y); f.ang.push_back(k->mvKeysUn[i].angle);
+        f.oct.push_back((uint8_t)k->mvKeysUn[i].octave); f.has.push_back(k->mvpMapPoints[i] != nullptr);
+      }
+      for (auto& kv : k->mFeatVec) {
+        f.node.push_back((int32_t)kv.first);
+        for (unsigned i : kv.second) f.idx.push_back((int32_t)i);
+        f.ioff.push_back((int32_t)f.idx.size());
+      }
+      f.koff[0] = 0; f.koff[1] = (int32_t)N; f.noff[0] = 0; f.noff[1] = (int32_t)f.node.size();
+    };
+    Flat a, b;
+    flatten(pKF1, a); flatten(pKF2, b);
+    p.kp1_off = a.koff; p.kp1_xy = a.xy.data(); p.kp1_angle = a.ang.data(); p.kp1_uright = pKF1->mvuRight.data(); p.kp1_has_mp = a.has.data();
+    p.kp1_desc = pKF1->mDescriptors.data();
+    p.kp2_off = b.koff; p.kp2_xy = b.xy.data(); p.kp2_octave = b.oct.data(); p.kp2_angle = b.ang.data(); p.kp2_uright = pKF2->mvuRight.data();
+    p.kp2_has_mp = b.has.data(); p.kp2_desc = pKF2->mDescriptors.data();
+    p.fv1_node_off = a.noff; p.fv1_node = a.node.data(); p.fv1_idx_off = a.ioff.data(); p.fv1_idx = a.idx.data();
+    p.fv2_node_off = b.noff; p.fv2_node = b.node.data(); p.fv2_idx_off = b.ioff.data(); p.fv2_idx = b.idx.data();
+    std::vector<int32_t> m12(pKF1->mvKeysUn.size() + 1, -1);
+    int32_t nm = 0;
+    lld_tri_search_result r{m12.data(), &nm};
+    const int rc = lld_tri_search(ctx, &p, &r);
+    if (rc) return rc;
+    vMatchedPairs.clear();
+    vMatchedPairs.reserve((size_t)nm);
+    for (size_t i = 0; i < pKF1->mvKeysUn.size(); i++)
+      if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));   // :813-818
     return nm;
   }
   // What ORBmatcher::Fuse decides for one map point (src/ORBmatcher.cc:949-968); Replace() itself is map bookkeeping and stays

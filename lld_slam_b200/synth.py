@@ -561,6 +561,88 @@ def make_kf_search_batch(n_pairs, n_kp, n_mp, seed, th=3.0, th_low=50, chi2_gate
     )
 
 
+def make_tri_search_batch(n_pairs, n_kp, seed, n_nodes=300, only_stereo=0, check_orientation=1):
+    """SearchForTriangulation: two keyframes a small baseline apart looking at the same random 3D points; a keypoint and its
+    counterpart share a vocabulary node (most of the time) and a descriptor up to a few bits; F12 from the relative pose;
+    30 % of the keypoints already carry a map point, 60 % have a right coordinate."""
+    rng = np.random.default_rng(seed)
+    g = frame_geom()
+    K = np.array([[g["fx"], 0, g["cx"]], [0, g["fy"], g["cy"]], [0, 0, 1.0]])
+    Ki = np.linalg.inv(K)
+    sf = np.asarray(g["scale_factors"], np.float32)
+    nl = len(sf)
+    out = dict(n_pairs=n_pairs, only_stereo=int(only_stereo), check_orientation=int(check_orientation), n_levels=nl,
+               scale_factors=np.pad(sf, (0, 8 - nl)), level_sigma2=np.pad((sf * sf).astype(np.float32), (0, 8 - nl)))
+    F12s, epis = [], []
+    acc = {k: [] for k in ("kp1_xy", "kp1_angle", "kp1_uright", "kp1_has_mp", "kp1_desc", "kp2_xy", "kp2_octave", "kp2_angle", "kp2_uright",
+                           "kp2_has_mp", "kp2_desc", "fv1_node", "fv1_idx", "fv2_node", "fv2_idx")}
+    kp1_off, kp2_off, n1o, n2o = [0], [0], [0], [0]
+
+    def fv(nodes):
+        order = np.argsort(nodes, kind="stable")          # DBoW2 pushes the indices of a node in keypoint order
+        ids, cnt = np.unique(nodes, return_counts=True)
+        return ids.astype(np.int32), np.cumsum(cnt), order.astype(np.int32)
+
+    for pr in range(n_pairs):
+        N = n_kp
+        X = np.stack([rng.uniform(-10, 10, N), rng.uniform(-3, 3, N), rng.uniform(5, 40, N)], 1)
+        yaw = rng.normal(0, 0.03)
+        R21 = _rot_y(np.array(yaw))                          # camera 1 -> camera 2
+        t21 = np.array([rng.uniform(0.5, 1.5), rng.normal(0, 0.05), rng.normal(0, 0.2)])
+        X2 = (R21 @ X.T).T + t21
+
+        def proj(Xc):
+            return np.stack([g["fx"] * Xc[:, 0] / Xc[:, 2] + g["cx"], g["fy"] * Xc[:, 1] / Xc[:, 2] + g["cy"]], 1)
+        p1 = proj(X) + rng.normal(0, 0.4, (N, 2))
+        p2 = proj(X2) + rng.normal(0, 0.4, (N, 2))
+        unrel = rng.random(N) < 0.15
+        p2[unrel] = np.stack([rng.uniform(0, IMG_W, unrel.sum()), rng.uniform(0, IMG_H, unrel.sum())], 1)
+        perm = rng.permutation(N)                            # keyframe 2 stores its keypoints in another order
+        tx = np.array([[0, -t21[2], t21[1]], [t21[2], 0, -t21[0]], [-t21[1], t21[0], 0]])
+        F12 = (Ki.T @ (tx @ R21).T @ Ki)                     # x1' F12 x2 = 0
+        F12s.append(F12.reshape(-1))
+        C2 = t21                                             # camera centre of keyframe 1 in camera 2
+        epis.append([g["fx"] * C2[0] / C2[2] + g["cx"], g["fy"] * C2[1] / C2[2] + g["cy"]])
+        d1 = rng.integers(0, 256, (N, 32), dtype=np.uint8)
+        d2 = np.where(unrel[:, None], rng.integers(0, 256, (N, 32), dtype=np.uint8), _flip_bits(d1[None], 0.06, rng)[0]).astype(np.uint8)
+        node1 = rng.integers(0, n_nodes, N)
+        node2 = np.where(rng.random(N) < 0.9, node1, rng.integers(0, n_nodes, N))
+        ang1 = rng.uniform(0, 360, N); ang2 = (ang1 + rng.normal(3, 4, N) + np.where(rng.random(N) < 0.1, rng.uniform(0, 360, N), 0)) % 360
+        ur1 = np.where(rng.random(N) < 0.6, p1[:, 0] - g["bf"] / X[:, 2], -1.0)
+        ur2 = np.where(rng.random(N) < 0.6, p2[:, 0] - g["bf"] / np.maximum(X2[:, 2], 1.0), -1.0)
+        acc["kp1_xy"].append(p1); acc["kp1_angle"].append(ang1); acc["kp1_uright"].append(ur1)
+        acc["kp1_has_mp"].append(rng.random(N) < 0.3); acc["kp1_desc"].append(d1)
+        acc["kp2_xy"].append(p2[perm]); acc["kp2_octave"].append(rng.integers(0, nl, N)); acc["kp2_angle"].append(ang2[perm])
+        acc["kp2_uright"].append(ur2[perm]); acc["kp2_has_mp"].append(rng.random(N) < 0.3); acc["kp2_desc"].append(d2[perm])
+        ids, ends, order = fv(node1)
+        acc["fv1_node"].append(ids); acc["fv1_idx"].append(order); n1o.append(n1o[-1] + len(ids))
+        f1_ends = ends
+        ids2, ends2, order2 = fv(node2[perm])
+        acc["fv2_node"].append(ids2); acc["fv2_idx"].append(order2); n2o.append(n2o[-1] + len(ids2))
+        out.setdefault("_e1", []).append(f1_ends); out.setdefault("_e2", []).append(ends2)
+        kp1_off.append(kp1_off[-1] + N); kp2_off.append(kp2_off[-1] + N)
+    # global CSR of the feature-vector entries
+    def idx_off(ends_list):
+        off, base = [0], 0
+        for e in ends_list:
+            off += list(base + e); base += int(e[-1]) if len(e) else 0
+        return np.asarray(off, np.int32)
+    out["fv1_idx_off"] = idx_off(out.pop("_e1")); out["fv2_idx_off"] = idx_off(out.pop("_e2"))
+    out["F12"] = f32(np.stack(F12s)); out["epipole"] = f32(np.asarray(epis))
+    out["kp1_off"] = np.asarray(kp1_off, np.int32); out["kp2_off"] = np.asarray(kp2_off, np.int32)
+    out["fv1_node_off"] = np.asarray(n1o, np.int32); out["fv2_node_off"] = np.asarray(n2o, np.int32)
+    for k, v in acc.items():
+        a = np.concatenate(v)
+        if k.endswith("_xy") or k.endswith("_angle") or k.endswith("_uright"):
+            a = f32(a)
+        elif k.endswith("_has_mp") or k.endswith("_octave") or k.endswith("_desc"):
+            a = a.astype(np.uint8)
+        else:
+            a = a.astype(np.int32)
+        out[k] = np.ascontiguousarray(a)
+    return out
+
+
 def make_line_match_batch(n_pairs, n_lines, desc_dim, seed, tau=2.0, min_len=10, ragged=False):
     rng = np.random.default_rng(seed)
     P, N, D = n_pairs, n_lines, desc_dim

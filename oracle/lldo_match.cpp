@@ -317,6 +317,86 @@ int lldo_kf_search(void*, const lld_kf_search_problem* p, lld_sbp_result* out) {
   return 0;
 }
 
+// ORBmatcher::SearchForTriangulation  src/ORBmatcher.cc:657-823, CheckDistEpipolarLine :140-157
+int lldo_tri_search(void*, const lld_tri_search_problem* p, lld_tri_search_result* out) {
+  const int TH_LOW = 50, HISTO_LENGTH = 30;
+  for (int pr = 0; pr < p->n_pairs; pr++) {
+    const int a0 = p->kp1_off[pr], n1 = p->kp1_off[pr + 1] - a0;
+    const int b0 = p->kp2_off[pr];
+    const float* F12 = p->F12 + 9 * (size_t)pr;
+    const float ex = p->epipole[2 * pr], ey = p->epipole[2 * pr + 1];
+    int nmatches = 0;
+    std::vector<int> vMatches12(n1, -1);
+    std::vector<int> rotHist[30];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int f1 = p->fv1_node_off[pr], f2 = p->fv2_node_off[pr];
+    const int f1end = p->fv1_node_off[pr + 1], f2end = p->fv2_node_off[pr + 1];
+    while (f1 != f1end && f2 != f2end) {
+      if (p->fv1_node[f1] == p->fv2_node[f2]) {
+        for (int i1 = p->fv1_idx_off[f1]; i1 < p->fv1_idx_off[f1 + 1]; i1++) {
+          const int idx1 = p->fv1_idx[i1];
+          if (p->kp1_has_mp[a0 + idx1]) continue;
+          const bool bStereo1 = p->kp1_uright[a0 + idx1] >= 0;
+          if (p->only_stereo && !bStereo1) continue;
+          const float k1x = p->kp1_xy[2 * (size_t)(a0 + idx1)], k1y = p->kp1_xy[2 * (size_t)(a0 + idx1) + 1];
+          const uint8_t* d1 = p->kp1_desc + 32 * (size_t)(a0 + idx1);
+          int bestDist = TH_LOW, bestIdx2 = -1;
+          for (int i2 = p->fv2_idx_off[f2]; i2 < p->fv2_idx_off[f2 + 1]; i2++) {
+            const int idx2 = p->fv2_idx[i2];
+            if (p->kp2_has_mp[b0 + idx2]) continue;      // (vbMatched2 is never set)
+            const bool bStereo2 = p->kp2_uright[b0 + idx2] >= 0;
+            if (p->only_stereo && !bStereo2) continue;
+            const int dist = descriptor_distance(d1, p->kp2_desc + 32 * (size_t)(b0 + idx2));
+            if (dist > TH_LOW || dist > bestDist) continue;
+            const float k2x = p->kp2_xy[2 * (size_t)(b0 + idx2)], k2y = p->kp2_xy[2 * (size_t)(b0 + idx2) + 1];
+            const int oct2 = p->kp2_octave[b0 + idx2];
+            if (!bStereo1 && !bStereo2) {
+              const float distex = ex - k2x, distey = ey - k2y;
+              if (distex * distex + distey * distey < 100 * p->scale_factors[oct2]) continue;
+            }
+            // CheckDistEpipolarLine
+            const float a = k1x * F12[0] + k1y * F12[3] + F12[6];
+            const float b = k1x * F12[1] + k1y * F12[4] + F12[7];
+            const float c = k1x * F12[2] + k1y * F12[5] + F12[8];
+            const float num = a * k2x + b * k2y + c;
+            const float den = a * a + b * b;
+            if (den == 0) continue;
+            const float dsqr = num * num / den;
+            if (dsqr < 3.84 * p->level_sigma2[oct2]) { bestIdx2 = idx2; bestDist = dist; }
+          }
+          if (bestIdx2 >= 0) {
+            vMatches12[idx1] = bestIdx2;
+            nmatches++;
+            if (p->check_orientation) {
+              float rot = p->kp1_angle[a0 + idx1] - p->kp2_angle[b0 + bestIdx2];
+              if (rot < 0.0) rot += 360.0f;
+              int bin = (int)std::round(rot * factor);
+              if (bin == HISTO_LENGTH) bin = 0;
+              rotHist[bin].push_back(idx1);
+            }
+          }
+        }
+        f1++; f2++;
+      } else if (p->fv1_node[f1] < p->fv2_node[f2]) {
+        while (f1 != f1end && p->fv1_node[f1] < p->fv2_node[f2]) f1++;   // lower_bound
+      } else {
+        while (f2 != f2end && p->fv2_node[f2] < p->fv1_node[f1]) f2++;
+      }
+    }
+    if (p->check_orientation) {
+      int ind1 = -1, ind2 = -1, ind3 = -1;
+      three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+      for (int i = 0; i < HISTO_LENGTH; i++) {
+        if (i == ind1 || i == ind2 || i == ind3) continue;
+        for (int j : rotHist[i]) { vMatches12[j] = -1; nmatches--; }
+      }
+    }
+    for (int i = 0; i < n1; i++) out->match12[a0 + i] = vMatches12[i];
+    out->n_matches[pr] = nmatches;
+  }
+  return 0;
+}
+
 // ---- TwoFrameLineMatcher ----------------------------------------------------------------------
 static double line_length(const float* s) {  // LineLength src/LineMatching.cc:50-59
   const double dx = (double)s[0] - (double)s[2], dy = (double)s[1] - (double)s[3];

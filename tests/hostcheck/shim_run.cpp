@@ -3,7 +3,7 @@
 // what they wrote back into the objects.  It also compares the shim's own flattening with the input arrays element by
 // element, which catches ordering bugs (std::map<KeyFrame*> iteration, proj_map by mnId, local-then-fixed keyframes).
 //
-//   shim_run <mode> <in.bin> <out.bin>      mode = local | global | pose | fuse
+//   shim_run <mode> <in.bin> <out.bin>      mode = local | global | pose | fuse | tri
 // Built twice by the tests: against liblldba.so (GPU) and, with -DLLD_SHIM_ORACLE, against oracle/liblld_oracle.so (the
 // same C-ABI under the lldo_ prefix) so that the host logic is covered on a CPU-only box.
 #ifdef LLD_SHIM_ORACLE
@@ -13,6 +13,7 @@
 #define lld_sbp_frame lldo_sbp_frame
 #define lld_sbp_mappoints lldo_sbp_mappoints
 #define lld_kf_search lldo_kf_search
+#define lld_tri_search lldo_tri_search
 #define lld_line_match lldo_line_match
 #define lld_descriptor_distance lldo_descriptor_distance
 #endif
@@ -358,6 +359,48 @@ int main(int argc, char** argv) {
     out("n_fused", 'i', &nf, 1);
     out("act_mp", 'i', a_mp.data(), a_mp.size()); out("act_idx", 'i', a_idx.data(), a_idx.size()); out("act_kind", 'i', a_kind.data(), a_kind.size());
     out("kf_mp", 'i', kf_mp.data(), kf_mp.size());
+  } else if (mode == "tri") {
+    // two keyframes with feature vectors: ORBmatcher::SearchForTriangulation
+    lld::KeyFrame kf[2];
+    for (int k = 0; k < 2; k++) {
+      const std::string sfx = k ? "2" : "1";
+      auto key = [&](const char* base) { return std::string(base) + sfx; };
+      lld::KeyFrame& K = kf[k];
+      for (int c = 0; c < 12; c++) K.Tcw[c] = in<float>(key("Tcw").c_str())[c];
+      const float* it = in<float>("intr");
+      K.fx = it[0]; K.fy = it[1]; K.cx = it[2]; K.cy = it[3]; K.mbf = it[4];
+      const int nl = (int)in_n("scale_factors");
+      K.mvScaleFactors.assign(in<float>("scale_factors"), in<float>("scale_factors") + nl);
+      K.mvLevelSigma2.assign(in<float>("level_sigma2"), in<float>("level_sigma2") + nl);
+      const int N = (int)in_n(key("kp_angle").c_str());
+      for (int i = 0; i < N; i++) {
+        lld::KeyPoint kp;
+        kp.x = in<float>(key("kp_xy").c_str())[2 * i]; kp.y = in<float>(key("kp_xy").c_str())[2 * i + 1];
+        kp.octave = in<uint8_t>(key("kp_octave").c_str())[i]; kp.angle = in<float>(key("kp_angle").c_str())[i];
+        K.mvKeysUn.push_back(kp);
+      }
+      K.mvuRight.assign(in<float>(key("kp_uright").c_str()), in<float>(key("kp_uright").c_str()) + N);
+      K.mDescriptors.assign(in<uint8_t>(key("kp_desc").c_str()), in<uint8_t>(key("kp_desc").c_str()) + 32 * (size_t)N);
+      static lld::MapPoint dummy;
+      K.mvpMapPoints.assign(N, nullptr);
+      for (int i = 0; i < N; i++)
+        if (in<uint8_t>(key("kp_has_mp").c_str())[i]) K.mvpMapPoints[i] = &dummy;
+      const int nn = (int)in_n(key("fv_node").c_str());
+      for (int n = 0; n < nn; n++) {
+        auto& lst = K.mFeatVec[(unsigned)in<int32_t>(key("fv_node").c_str())[n]];
+        for (int e = in<int32_t>(key("fv_idx_off").c_str())[n]; e < in<int32_t>(key("fv_idx_off").c_str())[n + 1]; e++)
+          lst.push_back((unsigned)in<int32_t>(key("fv_idx").c_str())[e]);
+      }
+    }
+    lld::ORBmatcher matcher(0.6f, in<uint8_t>("check_orientation")[0] != 0);
+    std::vector<std::pair<size_t, size_t>> pairs;
+    float ep[2] = {0, 0};
+    const int nm = matcher.SearchForTriangulation(ctx, &kf[0], &kf[1], in<float>("F12"), pairs, in<uint8_t>("only_stereo")[0] != 0, ep);
+    if (nm < 0) rc = nm;
+    std::vector<int32_t> flat;
+    for (auto& pr : pairs) { flat.push_back((int32_t)pr.first); flat.push_back((int32_t)pr.second); }
+    const int32_t n32 = nm;
+    out("n_matches", 'i', &n32, 1); out("pairs", 'i', flat.data(), flat.size()); out("epipole", 'f', ep, 2);
   } else {
     return 2;
   }

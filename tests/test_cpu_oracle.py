@@ -671,3 +671,97 @@ def test_oracle_kf_search_against_python(built, mode):
     for k in ("match", "n_matches", "best_idx", "best_dist"):
         assert np.array_equal(o[k], r[k]), k
     assert int(o["n_matches"].sum()) > 100
+
+
+def _tri_search_python(p):
+    """Independent transcription of ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:657-823) and CheckDistEpipolarLine
+    (:140-157): dictionaries for the feature vectors, float32 arithmetic, the rotation histogram as lists"""
+    f = np.float32
+    match12 = np.full(int(p["kp1_off"][-1]), -1, np.int32); nm = np.zeros(p["n_pairs"], np.int32)
+    for pr in range(p["n_pairs"]):
+        a0, a1 = int(p["kp1_off"][pr]), int(p["kp1_off"][pr + 1]); b0 = int(p["kp2_off"][pr])
+        F = p["F12"][pr].reshape(3, 3); ex, ey = p["epipole"][pr]
+
+        def fv(k):
+            d = {}
+            for n in range(int(p[f"fv{k}_node_off"][pr]), int(p[f"fv{k}_node_off"][pr + 1])):
+                d[int(p[f"fv{k}_node"][n])] = [int(i) for i in p[f"fv{k}_idx"][int(p[f"fv{k}_idx_off"][n]):int(p[f"fv{k}_idx_off"][n + 1])]]
+            return d
+        fv1, fv2 = fv(1), fv(2)
+        m12 = np.full(a1 - a0, -1, np.int32)
+        hist = [[] for _ in range(30)]
+        n = 0
+        for node in sorted(set(fv1) & set(fv2)):
+            for idx1 in fv1[node]:
+                if p["kp1_has_mp"][a0 + idx1]:
+                    continue
+                s1 = p["kp1_uright"][a0 + idx1] >= 0
+                if p["only_stereo"] and not s1:
+                    continue
+                x1, y1 = p["kp1_xy"][a0 + idx1]
+                best, bi = 50, -1
+                for idx2 in fv2[node]:
+                    if p["kp2_has_mp"][b0 + idx2]:
+                        continue
+                    s2 = p["kp2_uright"][b0 + idx2] >= 0
+                    if p["only_stereo"] and not s2:
+                        continue
+                    dist = int(np.unpackbits(np.bitwise_xor(p["kp1_desc"][a0 + idx1], p["kp2_desc"][b0 + idx2])).sum())
+                    if dist > 50 or dist > best:
+                        continue
+                    x2, y2 = p["kp2_xy"][b0 + idx2]; o2 = int(p["kp2_octave"][b0 + idx2])
+                    if not s1 and not s2:
+                        dx = f(ex) - x2; dy = f(ey) - y2
+                        if f(dx * dx) + f(dy * dy) < f(100) * p["scale_factors"][o2]:
+                            continue
+                    a = f(f(x1 * F[0, 0]) + f(y1 * F[1, 0])) + F[2, 0]
+                    b = f(f(x1 * F[0, 1]) + f(y1 * F[1, 1])) + F[2, 1]
+                    c = f(f(x1 * F[0, 2]) + f(y1 * F[1, 2])) + F[2, 2]
+                    num = f(f(a * x2) + f(b * y2)) + c
+                    den = f(a * a) + f(b * b)
+                    if den == 0:
+                        continue
+                    dsqr = f(f(num * num) / den)
+                    if float(dsqr) < 3.84 * float(p["level_sigma2"][o2]):
+                        bi, best = idx2, dist
+                if bi >= 0:
+                    m12[idx1] = bi; n += 1
+                    if p["check_orientation"]:
+                        rot = p["kp1_angle"][a0 + idx1] - p["kp2_angle"][b0 + bi]
+                        if rot < 0:
+                            rot = f(rot + f(360))
+                        b_ = int(np.floor(float(f(rot * f(1.0 / 30))) + 0.5))     # C round(): half away from zero, rot >= 0
+                        if b_ == 30:
+                            b_ = 0
+                        hist[b_].append(idx1)
+        if p["check_orientation"]:
+            sizes = [len(h) for h in hist]
+            m1 = m2 = m3 = 0; i1 = i2 = i3 = -1
+            for i, s_ in enumerate(sizes):
+                if s_ > m1:
+                    m3, m2, m1 = m2, m1, s_; i3, i2, i1 = i2, i1, i
+                elif s_ > m2:
+                    m3, m2 = m2, s_; i3, i2 = i2, i
+                elif s_ > m3:
+                    m3, i3 = s_, i
+            if m2 < 0.1 * m1:
+                i2 = i3 = -1
+            elif m3 < 0.1 * m1:
+                i3 = -1
+            for i in range(30):
+                if i in (i1, i2, i3):
+                    continue
+                for j in hist[i]:
+                    m12[j] = -1; n -= 1
+        match12[a0:a1] = m12; nm[pr] = n
+    return dict(match12=match12, n_matches=nm)
+
+
+@pytest.mark.parametrize("mode", [(0, 1), (1, 0)])
+def test_oracle_tri_search_against_python(built, mode):
+    from lld_slam_b200 import api, synth
+    p = synth.make_tri_search_batch(2, 500, 61 + mode[0], n_nodes=120, only_stereo=mode[0], check_orientation=mode[1])
+    o = api.tri_search(p, impl="oracle")
+    r = _tri_search_python(p)
+    assert np.array_equal(o["match12"], r["match12"]) and np.array_equal(o["n_matches"], r["n_matches"])
+    assert int(o["n_matches"].sum()) > (60 if mode[0] else 150)

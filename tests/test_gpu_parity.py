@@ -616,6 +616,17 @@ def test_kf_search_variants(gpu_ctx, match_path, mode):
     assert int(o["n_matches"].sum()) > 48 * 300
 
 
+@pytest.mark.parametrize("mode", [(0, 1), (1, 0)])
+def test_tri_search(gpu_ctx, mode):
+    """SURVEY §8(f) row 2: ORBmatcher::SearchForTriangulation (vocabulary-node buckets, epipole and epipolar-line gates in float,
+    last-of-equals selection, rotation histogram): vMatches12 bit-exact against the oracle, 64 keyframe pairs of 2000 keypoints"""
+    p = synth.make_tri_search_batch(64, 2000, 500 + mode[0], only_stereo=mode[0], check_orientation=mode[1])
+    g = api.tri_search(p, impl="gpu", ctx=gpu_ctx)
+    o = api.tri_search(p, impl="oracle")
+    assert np.array_equal(g["match12"], o["match12"]) and np.array_equal(g["n_matches"], o["n_matches"])
+    assert int(o["n_matches"].sum()) > 64 * (100 if mode[0] else 400)
+
+
 def test_temporal_line_association(gpu_ctx):
     """SURVEY §8(f) row 3, Tracking::AddLinesFrom: reprojection gates in both images, descriptor argmin with first-wins ties,
     sequential claims; index-exact against the oracle, ragged frames, more candidates than lanes"""

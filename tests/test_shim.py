@@ -248,6 +248,46 @@ def test_shim_fuse_on_host(tmp_path):
     _check_fuse(_build(tmp_path, True), tmp_path, "oracle")
 
 
+def _check_tri(exe, tmp_path, impl, ctx=None):
+    """SearchForTriangulation through the shim (epipole from the two poses, std::map feature vectors flattened in node order)
+    against lld_tri_search called on the flat problem with the epipole computed here the same way"""
+    p = synth.make_tri_search_batch(1, 900, 91)
+    rng = np.random.default_rng(3)
+    f32, f64 = np.float32, np.float64
+    g = synth.frame_geom()
+    # any two poses: the matcher only sees F12 and the epipole; F12 is taken from the synthetic problem, the epipole must
+    # come out of the shim's own arithmetic on these poses
+    T1 = np.concatenate([np.eye(3).reshape(-1), [0.1, -0.2, 0.3]]).astype(f32)
+    yaw = 0.05
+    R2 = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+    T2 = np.concatenate([R2.reshape(-1), [0.9, 0.02, 0.4]]).astype(f32)
+    R1 = T1[:9].reshape(3, 3).astype(f64); t1 = T1[9:].astype(f64)
+    Cw = (-(R1.T @ t1)).astype(f32)
+    C2 = (T2[:9].reshape(3, 3).astype(f64) @ Cw.astype(f64) + T2[9:].astype(f64)).astype(f32)
+    invz = f32(1.0) / C2[2]
+    ep = np.array([f32(g["fx"]) * C2[0] * invz + f32(g["cx"]), f32(g["fy"]) * C2[1] * invz + f32(g["cy"])], f32)
+    nl = int(p["n_levels"])
+    d = dict(Tcw1=T1, Tcw2=T2, intr=np.array([g["fx"], g["fy"], g["cx"], g["cy"], g["bf"]], f32),
+             scale_factors=p["scale_factors"][:nl], level_sigma2=p["level_sigma2"][:nl], F12=p["F12"][0],
+             check_orientation=np.array([p["check_orientation"]], np.uint8), only_stereo=np.array([p["only_stereo"]], np.uint8))
+    for k in (1, 2):
+        d[f"kp_xy{k}"] = p[f"kp{k}_xy"]; d[f"kp_angle{k}"] = p[f"kp{k}_angle"]; d[f"kp_uright{k}"] = p[f"kp{k}_uright"]
+        d[f"kp_has_mp{k}"] = p[f"kp{k}_has_mp"]; d[f"kp_desc{k}"] = p[f"kp{k}_desc"]
+        d[f"kp_octave{k}"] = p["kp2_octave"] if k == 2 else np.zeros(len(p["kp1_angle"]), np.uint8)
+        d[f"fv_node{k}"] = p[f"fv{k}_node"]; d[f"fv_idx_off{k}"] = p[f"fv{k}_idx_off"]; d[f"fv_idx{k}"] = p[f"fv{k}_idx"]
+    got = _run(exe, "tri", d, tmp_path)
+    assert np.array_equal(got["epipole"], ep)
+    q = dict(p); q["epipole"] = ep.reshape(1, 2)
+    ref = api.tri_search(q, impl=impl, ctx=ctx)
+    idx1 = np.nonzero(ref["match12"] >= 0)[0]
+    assert int(got["n_matches"][0]) == int(ref["n_matches"][0]) == len(idx1) and len(idx1) > 150
+    assert np.array_equal(got["pairs"].reshape(-1, 2), np.stack([idx1, ref["match12"][idx1]], 1))
+
+
+def test_shim_search_for_triangulation_on_host(tmp_path):
+    _check_tri(_build(tmp_path, True), tmp_path, "oracle")
+
+
 def test_shim_local_ba_on_host(tmp_path):
     _check_local(_build(tmp_path, True), tmp_path, "oracle")
 
@@ -270,3 +310,4 @@ def test_shim_entry_points_on_gpu(tmp_path, gpu_ctx):
     _check_global(exe, tmp_path, "gpu", gpu_ctx)
     _check_pose(exe, tmp_path, "gpu", gpu_ctx)
     _check_fuse(exe, tmp_path, "gpu", gpu_ctx)
+    _check_tri(exe, tmp_path, "gpu", gpu_ctx)

@@ -52,6 +52,21 @@ o, tc = cpu(lambda: api.sbp_mappoints(synth.make_sbp_mp_batch(8, 2000, 1500, 5),
 out["sbp_mappoints"] = {"frames": 256, "keypoints": 2000, "map_points": 1500, "device_ms": ms, "call_ms": wall,
                         "queries_per_s_device": 256 * 1500 / ms * 1e3, "cpu_oracle_ms_per_frame": tc / 8}
 
+# ---- keyframe searches (Fuse with the reprojection gate; SearchByProjection(KeyFrame*, Scw) with sequential claims)
+for name, gate, claims in (("fuse_search", 1, 0), ("sim3_search_by_projection", 0, 1)):
+    pk = synth.make_kf_search_batch(256, 2000, 1500, 9, chi2_gate=gate, sequential_claims=claims)
+    g, ms, wall = timed(lambda: api.kf_search(pk, impl="gpu", ctx=ctx))
+    o, tc = cpu(lambda: api.kf_search(synth.make_kf_search_batch(8, 2000, 1500, 9, chi2_gate=gate, sequential_claims=claims), impl="oracle"))
+    out[name] = {"keyframes": 256, "keypoints": 2000, "map_points": 1500, "device_ms": ms, "call_ms": wall,
+                 "queries_per_s_device": 256 * 1500 / ms * 1e3, "cpu_oracle_ms_per_keyframe": tc / 8}
+
+# ---- SearchForTriangulation
+pt = synth.make_tri_search_batch(256, 2000, 13)
+g, ms, wall = timed(lambda: api.tri_search(pt, impl="gpu", ctx=ctx))
+o, tc = cpu(lambda: api.tri_search(synth.make_tri_search_batch(8, 2000, 13), impl="oracle"))
+out["search_for_triangulation"] = {"keyframe_pairs": 256, "keypoints": 2000, "vocabulary_nodes": 300, "device_ms": ms, "call_ms": wall,
+                                   "pairs_per_s_device": 256 / ms * 1e3, "cpu_oracle_ms_per_pair": tc / 8}
+
 # ---- temporal line association
 pa = synth.make_line_assoc_batch(256, 300, 250, 64, 21, n_cand=40)
 g, ms, wall = timed(lambda: api.line_associate(pa, impl="gpu", ctx=ctx))
