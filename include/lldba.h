@@ -359,6 +359,39 @@ typedef struct lld_tri_search_result {
 
 int lld_tri_search(void* ctx, const lld_tri_search_problem* p, lld_tri_search_result* out);
 
+/* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches)        src/ORBmatcher.cc:159-288   strict_th = 0, kp2_valid = all ones
+ * ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12)         src/ORBmatcher.cc:522-655   strict_th = 1, kp2_valid = good map point
+ * batched over pairs.  Keypoints of side 1 that carry a good map point (kp1_valid) are matched against the keypoints of side 2 in the
+ * same vocabulary node: best and second best Hamming distance over the bucket (strict <, bucket order), acceptance at
+ * bestDist1 <= TH_LOW (< TH_LOW when strict_th) and bestDist1 < nn_ratio * bestDist2 (float), an accepted match removes its side-2
+ * keypoint for the entries after it (vpMapPointMatches[realIdxF] / vbMatched2[idx2]; only entries of the same node can compete for
+ * it), then the rotation-histogram filter.  match12[i] = matched side-2 keypoint of side-1 keypoint i (each side-2 keypoint at most
+ * once, so the first overload's vpMapPointMatches[match12[i]] = pMP_i is the inverse map). */
+typedef struct lld_bow_search_problem {
+  int32_t n_pairs;
+  int32_t strict_th;
+  int32_t check_orientation;
+  float nn_ratio;
+  const int32_t* kp1_off;       /* [n_pairs+1] */
+  const float* kp1_angle;       /* [n1] mvKeysUn[i].angle */
+  const uint8_t* kp1_valid;     /* [n1] map point present and not bad */
+  const uint8_t* kp1_desc;      /* [n1][32] */
+  const int32_t* kp2_off;
+  const float* kp2_angle;       /* F.mvKeys[i].angle / mvKeysUn[i].angle */
+  const uint8_t* kp2_valid;
+  const uint8_t* kp2_desc;
+  const int32_t* fv1_node_off;  /* feature vectors as in lld_tri_search_problem */
+  const int32_t* fv1_node;
+  const int32_t* fv1_idx_off;
+  const int32_t* fv1_idx;
+  const int32_t* fv2_node_off;
+  const int32_t* fv2_node;
+  const int32_t* fv2_idx_off;
+  const int32_t* fv2_idx;
+} lld_bow_search_problem;
+
+int lld_bow_search(void* ctx, const lld_bow_search_problem* p, lld_tri_search_result* out);
+
 /* ------------------------------------------------------------------------------------------------
  * Stereo line matching (float line descriptors)
  * ---------------------------------------------------------------------------------------------- */

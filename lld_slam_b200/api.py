@@ -145,6 +145,18 @@ def tri_search(p: Dict[str, Any], *, impl: str = "gpu", ctx=None):
     return out
 
 
+def bow_search(p: Dict[str, Any], *, impl: str = "gpu", ctx=None):
+    """ORBmatcher::SearchByBoW (KeyFrame -> Frame, KeyFrame -> KeyFrame), batched over pairs"""
+    lib = _lib(impl)
+    prob, keep = capi.fill_struct(capi.BowSearchProblem, p)
+    out = dict(match12=np.full(max(int(p["kp1_off"][-1]), 1), -1, np.int32), n_matches=np.zeros(int(p["n_pairs"]), np.int32))
+    res, keep2 = capi.fill_struct(capi.TriSearchResult, out)
+    rc = lib.bow_search(_handle(impl, ctx), C.byref(prob), C.byref(res))
+    _check(impl, ctx, rc, "lld_bow_search")
+    out["match12"] = out["match12"][:int(p["kp1_off"][-1])]
+    return out
+
+
 def line_match(p: Dict[str, Any], *, impl: str = "gpu", ctx=None):
     lib = _lib(impl)
     prob, keep = capi.fill_struct(capi.LineMatchProblem, p)

@@ -132,6 +132,16 @@ class TriSearchProblem(C.Structure):
     ]
 
 
+class BowSearchProblem(C.Structure):
+    _fields_ = [
+        ("n_pairs", C.c_int32), ("strict_th", C.c_int32), ("check_orientation", C.c_int32), ("nn_ratio", C.c_float),
+        ("kp1_off", c_i32p), ("kp1_angle", c_f32p), ("kp1_valid", c_u8p), ("kp1_desc", c_u8p),
+        ("kp2_off", c_i32p), ("kp2_angle", c_f32p), ("kp2_valid", c_u8p), ("kp2_desc", c_u8p),
+        ("fv1_node_off", c_i32p), ("fv1_node", c_i32p), ("fv1_idx_off", c_i32p), ("fv1_idx", c_i32p),
+        ("fv2_node_off", c_i32p), ("fv2_node", c_i32p), ("fv2_idx_off", c_i32p), ("fv2_idx", c_i32p),
+    ]
+
+
 class TriSearchResult(C.Structure):
     _fields_ = [("match12", c_i32p), ("n_matches", c_i32p)]
 
@@ -228,6 +238,7 @@ class _Lib:
         self._sig("sbp_mappoints", [vp, C.POINTER(SbpMpProblem), C.POINTER(SbpResult)])
         self._sig("kf_search", [vp, C.POINTER(KfSearchProblem), C.POINTER(SbpResult)])
         self._sig("tri_search", [vp, C.POINTER(TriSearchProblem), C.POINTER(TriSearchResult)])
+        self._sig("bow_search", [vp, C.POINTER(BowSearchProblem), C.POINTER(TriSearchResult)])
         self._sig("line_match", [vp, C.POINTER(LineMatchProblem), C.POINTER(LineMatchResult)])
         self._sig("descriptor_distance", [c_u8p, c_u8p])
         if not self.is_oracle:

@@ -83,6 +83,8 @@ extern "C" void lld_ctx_destroy(void* ctx) {
   for (int i = 0; i < 4; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   lld_ba_state_free(c->ba);  // graphs first: they reference the streams
+  for (int i = 0; i < 2; i++)
+    if (c->resident[i] && c->resident_free[i]) c->resident_free[i](c->resident[i]);
   lld_ba_host_free(c->ba_host);
   for (int i = 0; i < 2; i++) {
     if (c->side[i]) cudaStreamDestroy(c->side[i]);

@@ -70,6 +70,11 @@ struct LldCtx {
   void* pinned = nullptr;
   size_t pinned_cap = 0;
   BaState* ba = nullptr;
+  // resident-mode problem views of the matcher / pose kernels (bench entry points lld_sbp_frame_upload / lld_pose_upload): owned by
+  // the context (slot 0: match.cu, slot 1: pose.cu), valid while the pool generation they were uploaded under is current
+  void* resident[2] = {nullptr, nullptr};
+  void (*resident_free[2])(void*) = {nullptr, nullptr};
+  unsigned long long resident_gen[2] = {0, 0};
   void* ba_host = nullptr;                // BaHost: persistent host scratch + worker threads of the indexing stage (ba.cu)
   LldCtx* child[2] = {nullptr, nullptr};  // worker contexts of the pipelined batched local BA (ba.cu)
   size_t last_h2d_bytes = 0, last_d2h_bytes = 0;

@@ -1059,8 +1059,20 @@ static int match_download(LldCtx* c, MatchView& v, lld_sbp_result* out) {
   return LLD_OK;
 }
 
-static MatchView g_resident;  // resident-mode view (bench): uploaded once, run many times
-static bool g_resident_valid = false;
+// resident-mode view (bench): uploaded once, run many times; owned by the context, invalid as soon as another entry point of the
+// same context recycles the device pool
+static MatchView* resident_view(LldCtx* c, bool create) {
+  if (!c->resident[0] && create) {
+    c->resident[0] = new MatchView();
+    c->resident_free[0] = [](void* p) { delete static_cast<MatchView*>(p); };
+  }
+  return static_cast<MatchView*>(c->resident[0]);
+}
+static bool resident_valid(LldCtx* c) {
+  if (c->resident[0] && c->resident_gen[0] == c->pool_gen) return true;
+  snprintf(c->err, sizeof(c->err), "no resident matcher problem (not uploaded, or another call on this context recycled the device pool)");
+  return false;
+}
 
 static int sbp_frame_upload(LldCtx* c, const lld_sbp_frame_problem* p, MatchView& v) {
   c->pool_reset();
@@ -1217,24 +1229,24 @@ extern "C" int lld_sbp_frame_upload(void* ctx, const lld_sbp_frame_problem* p) {
   LldCtx* c = lld_ctx_cast(ctx);
   if (!c || !p) return LLD_ERR_ARG;
   LLD_CUDA(c, cudaSetDevice(c->device));
-  int r = sbp_frame_upload(c, p, g_resident);
+  int r = sbp_frame_upload(c, p, *resident_view(c, true));
+  c->resident_gen[0] = r ? 0 : c->pool_gen;
   if (r) return r;
-  g_resident_valid = true;
   LLD_CUDA(c, cudaStreamSynchronize(c->stream));
   return LLD_OK;
 }
 extern "C" int lld_sbp_run(void* ctx, int* passes) {
   LldCtx* c = lld_ctx_cast(ctx);
-  if (!c || !g_resident_valid) return LLD_ERR_ARG;
+  if (!c || !resident_valid(c)) return LLD_ERR_ARG;
   LLD_CUDA(c, cudaSetDevice(c->device));
-  return match_run(c, g_resident, passes);
+  return match_run(c, *resident_view(c, false), passes);
 }
 extern "C" int lld_sbp_download(void* ctx, lld_sbp_result* out) {
   LldCtx* c = lld_ctx_cast(ctx);
-  if (!c || !g_resident_valid || !out) return LLD_ERR_ARG;
+  if (!c || !out || !resident_valid(c)) return LLD_ERR_ARG;
   LLD_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
   LLD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-  return match_download(c, g_resident, out);
+  return match_download(c, *resident_view(c, false), out);
 }
 
 // host inline popcount distance (ORBmatcher::DescriptorDistance): API completeness, no device involved

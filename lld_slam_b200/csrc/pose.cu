@@ -453,9 +453,20 @@ int upl(LldCtx* c, T** dst, const T* src, size_t n) {
     (dst) = _p;                                            \
   } while (0)
 
-PoseView g_pose;
-bool g_pose_valid = false;
-size_t g_pose_smem = 0;
+// resident-mode view (bench), owned by the context; invalid once another entry point of the context recycles the device pool
+struct PoseResident { PoseView v; size_t smem = 0; };
+PoseResident* pose_resident(LldCtx* c, bool create) {
+  if (!c->resident[1] && create) {
+    c->resident[1] = new PoseResident();
+    c->resident_free[1] = [](void* p) { delete static_cast<PoseResident*>(p); };
+  }
+  return static_cast<PoseResident*>(c->resident[1]);
+}
+bool pose_resident_valid(LldCtx* c) {
+  if (c->resident[1] && c->resident_gen[1] == c->pool_gen) return true;
+  snprintf(c->err, sizeof(c->err), "no resident pose problem (not uploaded, or another call on this context recycled the device pool)");
+  return false;
+}
 
 int pose_upload(LldCtx* c, const lld_pose_problem* p, PoseView& v, size_t* smem_out) {
   c->pool_reset();
@@ -554,22 +565,24 @@ extern "C" int lld_pose_upload(void* ctx, const lld_pose_problem* p) {
   LldCtx* c = lld_ctx_cast(ctx);
   if (!c || !p) return LLD_ERR_ARG;
   LLD_CUDA(c, cudaSetDevice(c->device));
-  int r = pose_upload(c, p, g_pose, &g_pose_smem);
+  PoseResident* R = pose_resident(c, true);
+  int r = pose_upload(c, p, R->v, &R->smem);
+  c->resident_gen[1] = r ? 0 : c->pool_gen;
   if (r) return r;
-  g_pose_valid = true;
   LLD_CUDA(c, cudaStreamSynchronize(c->stream));
   return LLD_OK;
 }
 extern "C" int lld_pose_run(void* ctx) {
   LldCtx* c = lld_ctx_cast(ctx);
-  if (!c || !g_pose_valid) return LLD_ERR_ARG;
+  if (!c || !pose_resident_valid(c)) return LLD_ERR_ARG;
   LLD_CUDA(c, cudaSetDevice(c->device));
-  return pose_run(c, g_pose, g_pose_smem);
+  PoseResident* R = pose_resident(c, false);
+  return pose_run(c, R->v, R->smem);
 }
 extern "C" int lld_pose_download(void* ctx, const lld_pose_problem* p, lld_pose_result* out) {
   LldCtx* c = lld_ctx_cast(ctx);
-  if (!c || !g_pose_valid || !out) return LLD_ERR_ARG;
+  if (!c || !out || !pose_resident_valid(c)) return LLD_ERR_ARG;
   LLD_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
   LLD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-  return pose_download(c, g_pose, p, out);
+  return pose_download(c, pose_resident(c, false)->v, p, out);
 }

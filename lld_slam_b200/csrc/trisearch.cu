@@ -140,7 +140,158 @@ __global__ void __launch_bounds__(TS_NT) k_tri_search(TriView v) {
   if (tid == 0) v.n_matches[pr] = s_n;
 }
 
+// ORBmatcher::SearchByBoW (src/ORBmatcher.cc:159-288, :522-655): one thread per vocabulary node of side 1.  The claims
+// (vpMapPointMatches[realIdxF] / vbMatched2[idx2]) only ever concern keypoints of the same node -- a keypoint belongs to exactly
+// one node -- so a thread that walks its node's side-1 entries in order, each against the node's side-2 bucket in order, reproduces
+// the reference's sequential result without any exchange between threads.
+struct BowView {
+  lld_bow_search_problem p;   // device pointers
+  int* match12;
+  int* n_matches;
+  uint8_t* matched2;          // [n2] zeroed
+};
+
+__global__ void __launch_bounds__(TS_NT) k_bow_search(BowView v) {
+  __shared__ int s_hist[HISTO_LENGTH];
+  __shared__ int s_keep[3];
+  __shared__ int s_n;
+  const lld_bow_search_problem& p = v.p;
+  const int pr = blockIdx.x, tid = threadIdx.x;
+  const int a0 = p.kp1_off[pr], n1 = p.kp1_off[pr + 1] - a0;
+  const int b0 = p.kp2_off[pr];
+  const int f1b = p.fv1_node_off[pr], f1e = p.fv1_node_off[pr + 1];
+  const int f2b = p.fv2_node_off[pr], f2e = p.fv2_node_off[pr + 1];
+  if (tid < HISTO_LENGTH) s_hist[tid] = 0;
+  if (tid == 0) s_n = 0;
+  for (int i = tid; i < n1; i += TS_NT) v.match12[a0 + i] = -1;
+  __syncthreads();
+  const float factor = 1.0f / HISTO_LENGTH;
+  for (int f1 = f1b + tid; f1 < f1e; f1 += TS_NT) {
+    const int node = p.fv1_node[f1];
+    int l2 = f2b, h2 = f2e;
+    while (l2 < h2) {
+      const int mid = (l2 + h2) >> 1;
+      if (p.fv2_node[mid] < node) l2 = mid + 1;
+      else h2 = mid;
+    }
+    if (l2 >= f2e || p.fv2_node[l2] != node) continue;
+    const int s2b = p.fv2_idx_off[l2], s2e = p.fv2_idx_off[l2 + 1];
+    for (int i1 = p.fv1_idx_off[f1]; i1 < p.fv1_idx_off[f1 + 1]; i1++) {
+      const int idx1 = p.fv1_idx[i1];
+      if (!p.kp1_valid[a0 + idx1]) continue;
+      const uint4* d1 = reinterpret_cast<const uint4*>(p.kp1_desc + 32 * (size_t)(a0 + idx1));
+      const uint4 q0 = d1[0], q1 = d1[1];
+      int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+      for (int i2 = s2b; i2 < s2e; i2++) {
+        const int idx2 = p.fv2_idx[i2];
+        if (v.matched2[b0 + idx2] || !p.kp2_valid[b0 + idx2]) continue;
+        const uint4* d2 = reinterpret_cast<const uint4*>(p.kp2_desc + 32 * (size_t)(b0 + idx2));
+        const int dist = popc256(q0, q1, d2[0], d2[1]);
+        if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+        else if (dist < bestDist2) bestDist2 = dist;
+      }
+      if (!(p.strict_th ? bestDist1 < TH_LOW : bestDist1 <= TH_LOW)) continue;
+      if (!((float)bestDist1 < __fmul_rn(p.nn_ratio, (float)bestDist2))) continue;
+      v.match12[a0 + idx1] = bestIdx2;
+      v.matched2[b0 + bestIdx2] = 1;          // read again only by this thread (same node)
+      atomicAdd(&s_n, 1);
+      if (p.check_orientation) {
+        float rot = __fsub_rn(p.kp1_angle[a0 + idx1], p.kp2_angle[b0 + bestIdx2]);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, factor));
+        if (bin == HISTO_LENGTH) bin = 0;
+        atomicAdd(&s_hist[bin], 1);
+      }
+    }
+  }
+  __syncthreads();
+  if (p.check_orientation) {
+    if (tid == 0) {  // ORBmatcher::ComputeThreeMaxima
+      int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+      for (int i = 0; i < HISTO_LENGTH; i++) {
+        const int s = s_hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+      }
+      if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+      else if ((float)max3 < 0.1f * (float)max1) { ind3 = -1; }
+      s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+    }
+    __syncthreads();
+    for (int i = tid; i < n1; i += TS_NT) {
+      const int m = v.match12[a0 + i];
+      if (m < 0) continue;
+      float rot = __fsub_rn(p.kp1_angle[a0 + i], p.kp2_angle[b0 + m]);
+      if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+      int bin = (int)roundf(__fmul_rn(rot, factor));
+      if (bin == HISTO_LENGTH) bin = 0;
+      if (bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) {
+        v.match12[a0 + i] = -1;
+        atomicSub(&s_n, 1);
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) v.n_matches[pr] = s_n;
+}
+
 }  // namespace
+
+extern "C" int lld_bow_search(void* ctx, const lld_bow_search_problem* p, lld_tri_search_result* out) {
+  LldCtx* c = lld_ctx_cast(ctx);
+  if (!c || !p || !out) return LLD_ERR_ARG;
+  LLD_ARG(c, p->n_pairs >= 1);
+  LLD_CUDA(c, cudaSetDevice(c->device));
+  c->launches = 0;
+  c->pool_reset();
+  const int P = p->n_pairs, n1 = p->kp1_off[P], n2 = p->kp2_off[P];
+  const int nn1 = p->fv1_node_off[P], nn2 = p->fv2_node_off[P];
+  const int ne1 = nn1 ? p->fv1_idx_off[nn1] : 0, ne2 = nn2 ? p->fv2_idx_off[nn2] : 0;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](const void* src, size_t bytes) -> void* {
+    if (e != cudaSuccess) return nullptr;
+    uint8_t* d = c->alloc<uint8_t>(bytes ? bytes : 1, &e);
+    if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, c->stream);
+    return d;
+  };
+  BowView v{};
+  v.p = *p;
+  LLD_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+  v.p.kp1_off = (const int32_t*)up(p->kp1_off, 4 * (size_t)(P + 1));
+  v.p.kp1_angle = (const float*)up(p->kp1_angle, 4 * (size_t)n1);
+  v.p.kp1_valid = (const uint8_t*)up(p->kp1_valid, (size_t)n1);
+  v.p.kp1_desc = (const uint8_t*)up(p->kp1_desc, 32 * (size_t)n1);
+  v.p.kp2_off = (const int32_t*)up(p->kp2_off, 4 * (size_t)(P + 1));
+  v.p.kp2_angle = (const float*)up(p->kp2_angle, 4 * (size_t)n2);
+  v.p.kp2_valid = (const uint8_t*)up(p->kp2_valid, (size_t)n2);
+  v.p.kp2_desc = (const uint8_t*)up(p->kp2_desc, 32 * (size_t)n2);
+  v.p.fv1_node_off = (const int32_t*)up(p->fv1_node_off, 4 * (size_t)(P + 1));
+  v.p.fv1_node = (const int32_t*)up(p->fv1_node, 4 * (size_t)nn1);
+  v.p.fv1_idx_off = (const int32_t*)up(p->fv1_idx_off, 4 * (size_t)(nn1 + 1));
+  v.p.fv1_idx = (const int32_t*)up(p->fv1_idx, 4 * (size_t)ne1);
+  v.p.fv2_node_off = (const int32_t*)up(p->fv2_node_off, 4 * (size_t)(P + 1));
+  v.p.fv2_node = (const int32_t*)up(p->fv2_node, 4 * (size_t)nn2);
+  v.p.fv2_idx_off = (const int32_t*)up(p->fv2_idx_off, 4 * (size_t)(nn2 + 1));
+  v.p.fv2_idx = (const int32_t*)up(p->fv2_idx, 4 * (size_t)ne2);
+  if (e == cudaSuccess) v.match12 = c->alloc<int>((size_t)std::max(n1, 1), &e);
+  if (e == cudaSuccess) v.n_matches = c->alloc<int>((size_t)P, &e);
+  if (e == cudaSuccess) v.matched2 = c->alloc<uint8_t>((size_t)std::max(n2, 1), &e);
+  LLD_CUDA(c, e);
+  LLD_CUDA(c, cudaMemsetAsync(v.matched2, 0, (size_t)std::max(n2, 1), c->stream));
+  LLD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  LLD_LAUNCH(c, k_bow_search, P, TS_NT, 0, v);
+  LLD_CUDA(c, cudaGetLastError());
+  LLD_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  if (n1) LLD_CUDA(c, cudaMemcpyAsync(out->match12, v.match12, 4 * (size_t)n1, cudaMemcpyDeviceToHost, c->stream));
+  LLD_CUDA(c, cudaMemcpyAsync(out->n_matches, v.n_matches, 4 * (size_t)P, cudaMemcpyDeviceToHost, c->stream));
+  LLD_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+  LLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]);
+  cudaEventElapsedTime(&c->ms_compute, c->ev[1], c->ev[2]);
+  cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]);
+  return LLD_OK;
+}
 
 extern "C" int lld_tri_search(void* ctx, const lld_tri_search_problem* p, lld_tri_search_result* out) {
   LldCtx* c = lld_ctx_cast(ctx);

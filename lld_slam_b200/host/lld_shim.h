@@ -732,6 +732,43 @@ class ORBmatcher {
       if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));   // :813-818
     return nm;
   }
+  // int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)   include/ORBmatcher.h:60, src/ORBmatcher.cc:522-655
+  // (the KeyFrame -> Frame overload :159-288 flattens the same way with kp2_valid = 1, strict_th = 0 and inverts match12 into
+  // vpMapPointMatches[match12[i]] = vpMapPointsKF[i])
+  int SearchByBoW(void* ctx, KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12) {
+    lld_bow_search_problem p;
+    std::memset(&p, 0, sizeof(p));
+    p.n_pairs = 1; p.strict_th = 1; p.check_orientation = mbCheckOrientation; p.nn_ratio = mfNNratio;
+    struct Flat { std::vector<float> ang; std::vector<uint8_t> valid; std::vector<int32_t> node, ioff{0}, idx; int32_t koff[2], noff[2]; };
+    auto flatten = [](KeyFrame* k, Flat& f) {
+      const size_t N = k->mvKeysUn.size();
+      for (size_t i = 0; i < N; i++) {
+        f.ang.push_back(k->mvKeysUn[i].angle);
+        f.valid.push_back(k->mvpMapPoints[i] != nullptr && !k->mvpMapPoints[i]->isBad());     // :552-557, :573-578
+      }
+      for (auto& kv : k->mFeatVec) {
+        f.node.push_back((int32_t)kv.first);
+        for (unsigned i : kv.second) f.idx.push_back((int32_t)i);
+        f.ioff.push_back((int32_t)f.idx.size());
+      }
+      f.koff[0] = 0; f.koff[1] = (int32_t)N; f.noff[0] = 0; f.noff[1] = (int32_t)f.node.size();
+    };
+    Flat a, b;
+    flatten(pKF1, a); flatten(pKF2, b);
+    p.kp1_off = a.koff; p.kp1_angle = a.ang.data(); p.kp1_valid = a.valid.data(); p.kp1_desc = pKF1->mDescriptors.data();
+    p.kp2_off = b.koff; p.kp2_angle = b.ang.data(); p.kp2_valid = b.valid.data(); p.kp2_desc = pKF2->mDescriptors.data();
+    p.fv1_node_off = a.noff; p.fv1_node = a.node.data(); p.fv1_idx_off = a.ioff.data(); p.fv1_idx = a.idx.data();
+    p.fv2_node_off = b.noff; p.fv2_node = b.node.data(); p.fv2_idx_off = b.ioff.data(); p.fv2_idx = b.idx.data();
+    std::vector<int32_t> m12(pKF1->mvKeysUn.size() + 1, -1);
+    int32_t nm = 0;
+    lld_tri_search_result r{m12.data(), &nm};
+    const int rc = lld_bow_search(ctx, &p, &r);
+    if (rc) return rc;
+    vpMatches12.assign(pKF1->mvKeysUn.size(), nullptr);                                       // :536
+    for (size_t i = 0; i < pKF1->mvKeysUn.size(); i++)
+      if (m12[i] >= 0) vpMatches12[i] = pKF2->mvpMapPoints[(size_t)m12[i]];                   // :597
+    return nm;
+  }
   // What ORBmatcher::Fuse decides for one map point (src/ORBmatcher.cc:949-968); Replace() itself is map bookkeeping and stays
   // with the caller: `survivor` replaces `replaced`; both null = a new observation was added (done here)
   struct FuseAction { MapPoint* pMP; int bestIdx; MapPoint* survivor; MapPoint* replaced; };

@@ -643,6 +643,22 @@ def make_tri_search_batch(n_pairs, n_kp, seed, n_nodes=300, only_stereo=0, check
     return out
 
 
+def make_bow_search_batch(n_pairs, n_kp, seed, n_nodes=150, strict_th=0, nn_ratio=0.7, check_orientation=1):
+    """SearchByBoW: the keyframe pairs of make_tri_search_batch with fewer vocabulary nodes (larger buckets, so that second-best
+    distances, the ratio test and the claims inside a bucket all matter); side 1 keypoints carry a good map point with
+    probability 0.7, side 2 keypoints are all valid (frame) or carry one with probability 0.8 (keyframe, strict_th)"""
+    t = make_tri_search_batch(n_pairs, n_kp, seed, n_nodes=n_nodes)
+    rng = np.random.default_rng(seed + 5)
+    n1, n2 = int(t["kp1_off"][-1]), int(t["kp2_off"][-1])
+    out = dict(n_pairs=n_pairs, strict_th=int(strict_th), check_orientation=int(check_orientation), nn_ratio=float(nn_ratio),
+               kp1_off=t["kp1_off"], kp1_angle=t["kp1_angle"], kp1_valid=(rng.random(n1) < 0.7).astype(np.uint8), kp1_desc=t["kp1_desc"],
+               kp2_off=t["kp2_off"], kp2_angle=t["kp2_angle"],
+               kp2_valid=(rng.random(n2) < 0.8).astype(np.uint8) if strict_th else np.ones(n2, np.uint8), kp2_desc=t["kp2_desc"])
+    for k in ("fv1_node_off", "fv1_node", "fv1_idx_off", "fv1_idx", "fv2_node_off", "fv2_node", "fv2_idx_off", "fv2_idx"):
+        out[k] = t[k]
+    return out
+
+
 def make_line_match_batch(n_pairs, n_lines, desc_dim, seed, tau=2.0, min_len=10, ragged=False):
     rng = np.random.default_rng(seed)
     P, N, D = n_pairs, n_lines, desc_dim

@@ -397,6 +397,69 @@ int lldo_tri_search(void*, const lld_tri_search_problem* p, lld_tri_search_resul
   return 0;
 }
 
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) src/ORBmatcher.cc:159-288 and SearchByBoW(KeyFrame*, KeyFrame*, ...) :522-655
+int lldo_bow_search(void*, const lld_bow_search_problem* p, lld_tri_search_result* out) {
+  const int TH_LOW = 50, HISTO_LENGTH = 30;
+  for (int pr = 0; pr < p->n_pairs; pr++) {
+    const int a0 = p->kp1_off[pr], n1 = p->kp1_off[pr + 1] - a0;
+    const int b0 = p->kp2_off[pr], n2 = p->kp2_off[pr + 1] - b0;
+    std::vector<int> m12(n1, -1);
+    std::vector<uint8_t> matched2(n2, 0);
+    std::vector<int> rotHist[30];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int nmatches = 0;
+    int f1 = p->fv1_node_off[pr], f2 = p->fv2_node_off[pr];
+    const int f1end = p->fv1_node_off[pr + 1], f2end = p->fv2_node_off[pr + 1];
+    while (f1 != f1end && f2 != f2end) {
+      if (p->fv1_node[f1] == p->fv2_node[f2]) {
+        for (int i1 = p->fv1_idx_off[f1]; i1 < p->fv1_idx_off[f1 + 1]; i1++) {
+          const int idx1 = p->fv1_idx[i1];
+          if (!p->kp1_valid[a0 + idx1]) continue;
+          const uint8_t* d1 = p->kp1_desc + 32 * (size_t)(a0 + idx1);
+          int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+          for (int i2 = p->fv2_idx_off[f2]; i2 < p->fv2_idx_off[f2 + 1]; i2++) {
+            const int idx2 = p->fv2_idx[i2];
+            if (matched2[idx2] || !p->kp2_valid[b0 + idx2]) continue;
+            const int dist = descriptor_distance(d1, p->kp2_desc + 32 * (size_t)(b0 + idx2));
+            if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+          }
+          if (p->strict_th ? bestDist1 < TH_LOW : bestDist1 <= TH_LOW) {
+            if (static_cast<float>(bestDist1) < p->nn_ratio * static_cast<float>(bestDist2)) {
+              m12[idx1] = bestIdx2;
+              matched2[bestIdx2] = 1;
+              if (p->check_orientation) {
+                float rot = p->kp1_angle[a0 + idx1] - p->kp2_angle[b0 + bestIdx2];
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(idx1);
+              }
+              nmatches++;
+            }
+          }
+        }
+        f1++; f2++;
+      } else if (p->fv1_node[f1] < p->fv2_node[f2]) {
+        while (f1 != f1end && p->fv1_node[f1] < p->fv2_node[f2]) f1++;
+      } else {
+        while (f2 != f2end && p->fv2_node[f2] < p->fv1_node[f1]) f2++;
+      }
+    }
+    if (p->check_orientation) {
+      int ind1 = -1, ind2 = -1, ind3 = -1;
+      three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+      for (int i = 0; i < HISTO_LENGTH; i++) {
+        if (i == ind1 || i == ind2 || i == ind3) continue;
+        for (int j : rotHist[i]) { m12[j] = -1; nmatches--; }
+      }
+    }
+    for (int i = 0; i < n1; i++) out->match12[a0 + i] = m12[i];
+    out->n_matches[pr] = nmatches;
+  }
+  return 0;
+}
+
 // ---- TwoFrameLineMatcher ----------------------------------------------------------------------
 static double line_length(const float* s) {  // LineLength src/LineMatching.cc:50-59
   const double dx = (double)s[0] - (double)s[2], dy = (double)s[1] - (double)s[3];

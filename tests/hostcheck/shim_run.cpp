@@ -3,7 +3,7 @@
 // what they wrote back into the objects.  It also compares the shim's own flattening with the input arrays element by
 // element, which catches ordering bugs (std::map<KeyFrame*> iteration, proj_map by mnId, local-then-fixed keyframes).
 //
-//   shim_run <mode> <in.bin> <out.bin>      mode = local | global | pose | fuse | tri
+//   shim_run <mode> <in.bin> <out.bin>      mode = local | global | pose | fuse | tri | bow
 // Built twice by the tests: against liblldba.so (GPU) and, with -DLLD_SHIM_ORACLE, against oracle/liblld_oracle.so (the
 // same C-ABI under the lldo_ prefix) so that the host logic is covered on a CPU-only box.
 #ifdef LLD_SHIM_ORACLE
@@ -14,6 +14,7 @@
 #define lld_sbp_mappoints lldo_sbp_mappoints
 #define lld_kf_search lldo_kf_search
 #define lld_tri_search lldo_tri_search
+#define lld_bow_search lldo_bow_search
 #define lld_line_match lldo_line_match
 #define lld_descriptor_distance lldo_descriptor_distance
 #endif
@@ -359,7 +360,7 @@ int main(int argc, char** argv) {
     out("n_fused", 'i', &nf, 1);
     out("act_mp", 'i', a_mp.data(), a_mp.size()); out("act_idx", 'i', a_idx.data(), a_idx.size()); out("act_kind", 'i', a_kind.data(), a_kind.size());
     out("kf_mp", 'i', kf_mp.data(), kf_mp.size());
-  } else if (mode == "tri") {
+  } else if (mode == "tri" || mode == "bow") {
     // two keyframes with feature vectors: ORBmatcher::SearchForTriangulation
     lld::KeyFrame kf[2];
     for (int k = 0; k < 2; k++) {
@@ -381,16 +382,33 @@ int main(int argc, char** argv) {
       }
       K.mvuRight.assign(in<float>(key("kp_uright").c_str()), in<float>(key("kp_uright").c_str()) + N);
       K.mDescriptors.assign(in<uint8_t>(key("kp_desc").c_str()), in<uint8_t>(key("kp_desc").c_str()) + 32 * (size_t)N);
-      static lld::MapPoint dummy;
+      static std::vector<lld::MapPoint> pool[2];      // one map point object per keypoint that has one (mnId = keypoint index)
+      pool[k].assign((size_t)N, lld::MapPoint());
       K.mvpMapPoints.assign(N, nullptr);
       for (int i = 0; i < N; i++)
-        if (in<uint8_t>(key("kp_has_mp").c_str())[i]) K.mvpMapPoints[i] = &dummy;
+        if (in<uint8_t>(key("kp_has_mp").c_str())[i]) { pool[k][(size_t)i].mnId = (unsigned long)i; K.mvpMapPoints[i] = &pool[k][(size_t)i]; }
       const int nn = (int)in_n(key("fv_node").c_str());
       for (int n = 0; n < nn; n++) {
         auto& lst = K.mFeatVec[(unsigned)in<int32_t>(key("fv_node").c_str())[n]];
         for (int e = in<int32_t>(key("fv_idx_off").c_str())[n]; e < in<int32_t>(key("fv_idx_off").c_str())[n + 1]; e++)
           lst.push_back((unsigned)in<int32_t>(key("fv_idx").c_str())[e]);
       }
+    }
+    if (mode == "bow") {
+      lld::ORBmatcher bm(in<float>("nn_ratio")[0], in<uint8_t>("check_orientation")[0] != 0);
+      std::vector<lld::MapPoint*> m12;
+      const int nb = bm.SearchByBoW(ctx, &kf[0], &kf[1], m12);
+      if (nb < 0) rc = nb;
+      std::vector<int32_t> flat(m12.size(), -1);
+      for (size_t i = 0; i < m12.size(); i++)
+        if (m12[i]) flat[i] = (int32_t)m12[i]->mnId;
+      const int32_t n32 = nb;
+      out("n_matches", 'i', &n32, 1); out("match12", 'i', flat.data(), flat.size());
+#ifndef LLD_SHIM_ORACLE
+      lld_ctx_destroy(ctx);
+#endif
+      if (rc) { fprintf(stderr, "shim entry point failed with %d\n", rc); return 6; }
+      return write_all(argv[3]) ? 0 : 7;
     }
     lld::ORBmatcher matcher(0.6f, in<uint8_t>("check_orientation")[0] != 0);
     std::vector<std::pair<size_t, size_t>> pairs;

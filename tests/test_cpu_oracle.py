@@ -765,3 +765,75 @@ def test_oracle_tri_search_against_python(built, mode):
     r = _tri_search_python(p)
     assert np.array_equal(o["match12"], r["match12"]) and np.array_equal(o["n_matches"], r["n_matches"])
     assert int(o["n_matches"].sum()) > (60 if mode[0] else 150)
+
+
+def _bow_search_python(p):
+    """Independent transcription of the two ORBmatcher::SearchByBoW overloads (src/ORBmatcher.cc:159-288, :522-655)"""
+    f = np.float32
+    match12 = np.full(int(p["kp1_off"][-1]), -1, np.int32); nm = np.zeros(p["n_pairs"], np.int32)
+    for pr in range(p["n_pairs"]):
+        a0, a1 = int(p["kp1_off"][pr]), int(p["kp1_off"][pr + 1]); b0, b1 = int(p["kp2_off"][pr]), int(p["kp2_off"][pr + 1])
+
+        def fv(k):
+            d = {}
+            for n in range(int(p[f"fv{k}_node_off"][pr]), int(p[f"fv{k}_node_off"][pr + 1])):
+                d[int(p[f"fv{k}_node"][n])] = [int(i) for i in p[f"fv{k}_idx"][int(p[f"fv{k}_idx_off"][n]):int(p[f"fv{k}_idx_off"][n + 1])]]
+            return d
+        fv1, fv2 = fv(1), fv(2)
+        m12 = np.full(a1 - a0, -1, np.int32); taken = np.zeros(b1 - b0, bool)
+        hist = [[] for _ in range(30)]
+        n = 0
+        for node in sorted(set(fv1) & set(fv2)):
+            for idx1 in fv1[node]:
+                if not p["kp1_valid"][a0 + idx1]:
+                    continue
+                bd1, bi, bd2 = 256, -1, 256
+                for idx2 in fv2[node]:
+                    if taken[idx2] or not p["kp2_valid"][b0 + idx2]:
+                        continue
+                    dist = int(np.unpackbits(np.bitwise_xor(p["kp1_desc"][a0 + idx1], p["kp2_desc"][b0 + idx2])).sum())
+                    if dist < bd1:
+                        bd2, bd1, bi = bd1, dist, idx2
+                    elif dist < bd2:
+                        bd2 = dist
+                ok = bd1 < 50 if p["strict_th"] else bd1 <= 50
+                if ok and f(bd1) < f(p["nn_ratio"]) * f(bd2):
+                    m12[idx1] = bi; taken[bi] = True; n += 1
+                    if p["check_orientation"]:
+                        rot = p["kp1_angle"][a0 + idx1] - p["kp2_angle"][b0 + bi]
+                        if rot < 0:
+                            rot = f(rot + f(360))
+                        b_ = int(np.floor(float(f(rot * f(1.0 / 30))) + 0.5))
+                        hist[0 if b_ == 30 else b_].append(idx1)
+        if p["check_orientation"]:
+            sizes = [len(h) for h in hist]
+            m1 = m2 = m3 = 0; i1 = i2 = i3 = -1
+            for i, s_ in enumerate(sizes):
+                if s_ > m1:
+                    m3, m2, m1 = m2, m1, s_; i3, i2, i1 = i2, i1, i
+                elif s_ > m2:
+                    m3, m2 = m2, s_; i3, i2 = i2, i
+                elif s_ > m3:
+                    m3, i3 = s_, i
+            if m2 < 0.1 * m1:
+                i2 = i3 = -1
+            elif m3 < 0.1 * m1:
+                i3 = -1
+            for i in range(30):
+                if i not in (i1, i2, i3):
+                    for j in hist[i]:
+                        m12[j] = -1; n -= 1
+        match12[a0:a1] = m12; nm[pr] = n
+    return dict(match12=match12, n_matches=nm)
+
+
+@pytest.mark.parametrize("strict", [0, 1])
+def test_oracle_bow_search_against_python(built, strict):
+    from lld_slam_b200 import api, synth
+    p = synth.make_bow_search_batch(2, 500, 71 + strict, n_nodes=40, strict_th=strict, nn_ratio=0.7 if strict else 0.75)
+    o = api.bow_search(p, impl="oracle")
+    r = _bow_search_python(p)
+    assert np.array_equal(o["match12"], r["match12"]) and np.array_equal(o["n_matches"], r["n_matches"])
+    assert int(o["n_matches"].sum()) > 150
+    m = o["match12"][o["match12"] >= 0]           # a side-2 keypoint is matched at most once per pair
+    assert len(np.unique(m + 100000 * np.repeat(np.arange(2), 500)[o["match12"] >= 0])) == len(m)

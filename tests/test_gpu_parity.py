@@ -627,6 +627,18 @@ def test_tri_search(gpu_ctx, mode):
     assert int(o["n_matches"].sum()) > 64 * (100 if mode[0] else 400)
 
 
+@pytest.mark.parametrize("strict", [0, 1])
+def test_bow_search(gpu_ctx, strict):
+    """SURVEY §8(f) row 2: both ORBmatcher::SearchByBoW overloads (vocabulary-node buckets, best / second best with the ratio test,
+    claims inside a bucket, rotation histogram): bit-exact against the oracle, 64 pairs of 2000 keypoints, large and small buckets"""
+    for n_nodes in (60, 400):
+        p = synth.make_bow_search_batch(64, 2000, 600 + strict + n_nodes, n_nodes=n_nodes, strict_th=strict)
+        g = api.bow_search(p, impl="gpu", ctx=gpu_ctx)
+        o = api.bow_search(p, impl="oracle")
+        assert np.array_equal(g["match12"], o["match12"]) and np.array_equal(g["n_matches"], o["n_matches"])
+        assert int(o["n_matches"].sum()) > 64 * 300
+
+
 def test_temporal_line_association(gpu_ctx):
     """SURVEY §8(f) row 3, Tracking::AddLinesFrom: reprojection gates in both images, descriptor argmin with first-wins ties,
     sequential claims; index-exact against the oracle, ragged frames, more candidates than lanes"""

@@ -284,6 +284,31 @@ def _check_tri(exe, tmp_path, impl, ctx=None):
     assert np.array_equal(got["pairs"].reshape(-1, 2), np.stack([idx1, ref["match12"][idx1]], 1))
 
 
+def _check_bow(exe, tmp_path, impl, ctx=None):
+    """SearchByBoW(KeyFrame*, KeyFrame*) through the shim against lld_bow_search on the flat problem"""
+    p = synth.make_bow_search_batch(1, 900, 93, n_nodes=60, strict_th=1, nn_ratio=0.75)
+    f32 = np.float32
+    g = synth.frame_geom()
+    T = np.concatenate([np.eye(3).reshape(-1), [0, 0, 0]]).astype(f32)
+    n = len(p["kp1_angle"])
+    d = dict(Tcw1=T, Tcw2=T, intr=np.array([g["fx"], g["fy"], g["cx"], g["cy"], g["bf"]], f32),
+             scale_factors=np.asarray(g["scale_factors"], f32), level_sigma2=np.asarray(g["scale_factors"], f32) ** 2,
+             F12=np.zeros(9, f32), check_orientation=np.array([p["check_orientation"]], np.uint8), only_stereo=np.zeros(1, np.uint8),
+             nn_ratio=np.array([p["nn_ratio"]], f32))
+    for k in (1, 2):
+        d[f"kp_xy{k}"] = np.zeros((n, 2), f32); d[f"kp_angle{k}"] = p[f"kp{k}_angle"]; d[f"kp_uright{k}"] = np.full(n, -1, f32)
+        d[f"kp_has_mp{k}"] = p[f"kp{k}_valid"]; d[f"kp_desc{k}"] = p[f"kp{k}_desc"]; d[f"kp_octave{k}"] = np.zeros(n, np.uint8)
+        d[f"fv_node{k}"] = p[f"fv{k}_node"]; d[f"fv_idx_off{k}"] = p[f"fv{k}_idx_off"]; d[f"fv_idx{k}"] = p[f"fv{k}_idx"]
+    got = _run(exe, "bow", d, tmp_path)
+    ref = api.bow_search(p, impl=impl, ctx=ctx)
+    assert int(got["n_matches"][0]) == int(ref["n_matches"][0]) > 100
+    assert np.array_equal(got["match12"], ref["match12"])       # the driver's map points carry the keypoint index as their id
+
+
+def test_shim_search_by_bow_on_host(tmp_path):
+    _check_bow(_build(tmp_path, True), tmp_path, "oracle")
+
+
 def test_shim_search_for_triangulation_on_host(tmp_path):
     _check_tri(_build(tmp_path, True), tmp_path, "oracle")
 
@@ -311,3 +336,4 @@ def test_shim_entry_points_on_gpu(tmp_path, gpu_ctx):
     _check_pose(exe, tmp_path, "gpu", gpu_ctx)
     _check_fuse(exe, tmp_path, "gpu", gpu_ctx)
     _check_tri(exe, tmp_path, "gpu", gpu_ctx)
+    _check_bow(exe, tmp_path, "gpu", gpu_ctx)

@@ -67,6 +67,13 @@ o, tc = cpu(lambda: api.tri_search(synth.make_tri_search_batch(8, 2000, 13), imp
 out["search_for_triangulation"] = {"keyframe_pairs": 256, "keypoints": 2000, "vocabulary_nodes": 300, "device_ms": ms, "call_ms": wall,
                                    "pairs_per_s_device": 256 / ms * 1e3, "cpu_oracle_ms_per_pair": tc / 8}
 
+# ---- SearchByBoW (keyframe -> frame)
+pb = synth.make_bow_search_batch(256, 2000, 17, n_nodes=300)
+g, ms, wall = timed(lambda: api.bow_search(pb, impl="gpu", ctx=ctx))
+o, tc = cpu(lambda: api.bow_search(synth.make_bow_search_batch(8, 2000, 17, n_nodes=300), impl="oracle"))
+out["search_by_bow"] = {"pairs": 256, "keypoints": 2000, "vocabulary_nodes": 300, "device_ms": ms, "call_ms": wall,
+                        "pairs_per_s_device": 256 / ms * 1e3, "cpu_oracle_ms_per_pair": tc / 8}
+
 # ---- temporal line association
 pa = synth.make_line_assoc_batch(256, 300, 250, 64, 21, n_cand=40)
 g, ms, wall = timed(lambda: api.line_associate(pa, impl="gpu", ctx=ctx))
