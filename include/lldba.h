@@ -15,6 +15,14 @@
  *   lld_sbp_frame          <- ORBmatcher::SearchByProjection(Frame&,const Frame&,th,bMono)   include/ORBmatcher.h:52, src/ORBmatcher.cc:1328-1470
  *   lld_sbp_mappoints      <- ORBmatcher::SearchByProjection(Frame&,vector<MapPoint*>&,th)   include/ORBmatcher.h:47, src/ORBmatcher.cc:45-129
  *   lld_line_match         <- TwoFrameLineMatcher::MatchLines        include/TwoFrameLineMatcher.h:39, src/TwoFrameLineMatcher.cc:26-124
+ *   the callers either side of that path:
+ *   lld_stereo_matches     <- Frame::ComputeStereoMatches            src/Frame.cc:530-704
+ *   lld_sbp_frame(th_high) <- ORBmatcher::SearchByProjection(Frame&,KeyFrame*,sAlreadyFound,th,ORBdist)  src/ORBmatcher.cc:1472-1599
+ *   lld_kf_search          <- ORBmatcher::Fuse x2, SearchByProjection(KeyFrame*,Scw,...)     src/ORBmatcher.cc:825-975, 977-1100, 290-403
+ *   lld_tri_search         <- ORBmatcher::SearchForTriangulation     src/ORBmatcher.cc:657-823
+ *   lld_bow_search         <- ORBmatcher::SearchByBoW x2             src/ORBmatcher.cc:159-288, 522-655
+ *   lld_line_associate     <- Tracking::AddLinesFrom                 src/Tracking.cc:996-1124
+ *   lld_medoid_orb / _float<- MapPoint / MapLine::ComputeDistinctiveDescriptors              src/MapPoint.cc:242-307, src/MapLine.cc:133-201
  *
  * Conventions
  *   - Plain pointers and sizes only.  All arrays are caller-owned HOST memory, contiguous, little endian.
@@ -54,7 +62,10 @@ extern "C" {
  *   - at most 254 observations per landmark;
  *   - a keyframe may be covisible with at most 170 free keyframes in lld_ba_global (6 * neighbours <= 1024);
  *   - local windows with more than 32 free keyframes take the general (slower) sparse path;
- *   - lld_sbp_*: n_levels <= 8, at most 65535 keypoints per frame.
+ *   - lld_sbp_*, lld_kf_search: n_levels <= 8, at most 65535 keypoints per frame; pairs with more than 2048 keypoints or queries
+ *     take the multi-kernel path instead of the single-CTA one;
+ *   - lld_line_match: descriptor widths that are a multiple of 8 up to 72 floats and at most 512 lines per side of a pair run on the
+ *     tensor cores, everything else on the FP32 tile path (no failure).
  */
 
 /* One batch of independent BA problems ("windows").  Entities of window w live at

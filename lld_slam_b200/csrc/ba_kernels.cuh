@@ -492,7 +492,10 @@ __device__ __forceinline__ void block_reduce_nv(const double* acc, double (*part
 
 // pose pass: one CTA per chunk of a free keyframe's edge list; recomputes residual, weight and the pose Jacobian
 // and reduces Jp^T (w Omega) Jp and -Jp^T (w Omega) r in fixed order.
-__global__ void __launch_bounds__(LM_TPB) k_lin_poses(BaView v) {
+#ifndef LLD_POSES_MINB
+#define LLD_POSES_MINB 1
+#endif
+__global__ void __launch_bounds__(LM_TPB, LLD_POSES_MINB) k_lin_poses(BaView v) {
   const int ch = blockIdx.x;
   const int g = v.ch_g[ch];
   const int kf = v.g_kf[g];
