@@ -492,8 +492,13 @@ __device__ __forceinline__ void block_reduce_nv(const double* acc, double (*part
 
 // pose pass: one CTA per chunk of a free keyframe's edge list; recomputes residual, weight and the pose Jacobian
 // and reduces Jp^T (w Omega) Jp and -Jp^T (w Omega) r in fixed order.
+// measured on B200 (64 windows of 20/5k/1k, ms per bench step / ms in this kernel): plain 16.09 / 2.86, four resident CTAs per
+// SM (128 registers) 15.77 / 2.55, data prefetch 15.88 / 2.67, both 15.67 / 2.45, five CTAs (96 registers, spills) 16.14 / 2.96
 #ifndef LLD_POSES_MINB
-#define LLD_POSES_MINB 1
+#define LLD_POSES_MINB 4
+#endif
+#ifndef LLD_POSES_PREFETCH
+#define LLD_POSES_PREFETCH 1
 #endif
 __global__ void __launch_bounds__(LM_TPB, LLD_POSES_MINB) k_lin_poses(BaView v) {
   const int ch = blockIdx.x;
@@ -518,6 +523,53 @@ __global__ void __launch_bounds__(LM_TPB, LLD_POSES_MINB) k_lin_poses(BaView v) 
     id = is_pt ? v.pl_edge[i] : v.ll_cell[i];
     lm = is_pt ? v.pe_pt[id] : v.lc_ln[id];
   }
+#if LLD_POSES_PREFETCH
+  if (is_pt) {
+    // point chunks: the DATA of the next entry (level, landmark position, observation, information) is loaded before the
+    // arithmetic of the current one as well -- the kernel is bound by the latency of these gathers (ncu: 8.5 warps stalled
+    // on the long scoreboard per issue at 12 warps per SM)
+    struct PtData { uint8_t lvl; double X[3]; float obs[3]; float info; };
+    auto load = [&](int e, int l, PtData& d) {
+      d.lvl = v.pe_level[e];
+      const double* X = v.pt_xyz[sel] + 3 * (size_t)l;
+      d.X[0] = X[0]; d.X[1] = X[1]; d.X[2] = X[2];
+      const float* o = v.pe_uvr + 3 * (size_t)e;
+      d.obs[0] = o[0]; d.obs[1] = o[1]; d.obs[2] = o[2];
+      d.info = v.pe_info[e];
+    };
+    PtData nxt;
+    nxt.lvl = 1;
+    if (i < i_end) load(id, lm, nxt);
+    for (; i < i_end; i += blockDim.x) {
+      const PtData cur = nxt;
+      const int i2 = i + (int)blockDim.x;
+      if (i2 < i_end) {
+        const int e2 = v.pl_edge[i2];
+        load(e2, v.pe_pt[e2], nxt);
+      }
+      if (cur.lvl != 0) continue;
+      const bool stereo = !(cur.obs[2] < 0.f);
+      double xc[3], err[3], Jp[18];
+      map_Rt(Rt, cur.X, xc);
+      pt_residual<true>(xc, intr, cur.obs, stereo, err);
+      const double info = (double)cur.info;
+      const double c2 = err[0] * (info * err[0]) + err[1] * (info * err[1]) + err[2] * (info * err[2]);
+      double wgt = 1.0;
+      if (v.prm.robust_pt) huber(c2, stereo ? v.prm.delta_pt_stereo : v.prm.delta_pt_mono, &wgt);
+      const double wo = wgt * info;
+      pt_jac_pose(xc, intr, stereo, Jp);
+      int k = 0;
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+#pragma unroll
+        for (int c = r; c < 6; c++, k++) acc[k] += wo * (Jp[r] * Jp[c] + Jp[6 + r] * Jp[6 + c] + Jp[12 + r] * Jp[12 + c]);
+        acc[21 + r] -= wo * (Jp[r] * err[0] + Jp[6 + r] * err[1] + Jp[12 + r] * err[2]);
+      }
+      acc[27] += 1.0;
+    }
+    i = i_end;
+  }
+#endif
   for (; i < i_end; i += blockDim.x) {
     const int id_c = id, lm_c = lm;
     if (i + (int)blockDim.x < i_end) {
@@ -1290,6 +1342,16 @@ __global__ void __launch_bounds__(256) k_reduce_piece(BaView v, int n_blocks) {
     double s = 0;
     const int q1 = v.gb_off[blk + 1];
     int q = v.gb_off[blk];
+    for (; q + 8 <= q1; q += 8) {   // eight gathers in flight (the kernel is bound by their latency); the sum stays in list order
+      long long o[8];
+      double a[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) o[k] = v.gb_src[q + k];
+#pragma unroll
+      for (int k = 0; k < 8; k++) a[k] = v.dpart[o[k] + e];
+#pragma unroll
+      for (int k = 0; k < 8; k++) s += a[k];
+    }
     for (; q + 4 <= q1; q += 4) {
       const long long o0 = v.gb_src[q], o1 = v.gb_src[q + 1], o2 = v.gb_src[q + 2], o3 = v.gb_src[q + 3];
       const double a0 = v.dpart[o0 + e], a1 = v.dpart[o1 + e], a2 = v.dpart[o2 + e], a3 = v.dpart[o3 + e];
