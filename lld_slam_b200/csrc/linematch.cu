@@ -696,24 +696,26 @@ __device__ __forceinline__ void gate32_endpoint(const GateK& gk, const GateL& L,
   *tol2 = gk.c_tol2 * (det2 + E2) * dd * fmaf(L.l1sq, det2, ww);
 }
 __device__ __forceinline__ int line_gate32(const GateK& gk, const GateL& L, const float* l2, float beta) {
+  // straight-line code: every entry runs the same instructions and the verdict is assembled from predicates at the end (the
+  // selectors have already removed the entries the early tests would reject, so early exits only cost divergence here)
   float dir[3], c1[3];
   cross3f(L.l1, l2, dir);
   const float dd = dot3f(dir, dir);
-  if (!(dd > 1e-12f)) return -1;
   const float lhs = beta * beta * L.l1sq, rhs = 0.25f * dd;
-  if (lhs < rhs * (1.f - 2e-3f)) return 0;
-  if (!(lhs > rhs * (1.f + 2e-3f))) return -1;
   cross3f(dir, L.l1, c1);
-  int r = 1;
+  bool undecided = !(dd > 1e-12f) || (!(lhs < rhs * (1.f - 2e-3f)) && !(lhs > rhs * (1.f + 2e-3f)));
+  bool rejected = lhs < rhs * (1.f - 2e-3f);
 #pragma unroll
   for (int e = 0; e < 2; e++) {
     float T, tol2;
     bool cond;
     gate32_endpoint(gk, L, e, dir, c1, dd, &T, &tol2, &cond);
-    if (!cond || !(T * T > tol2)) r = r == 0 ? 0 : -1;   // undecided (a clear rejection by the other endpoint stands)
-    else if (beta * T < 0.f) r = 0;
+    const bool clear = cond && (T * T > tol2);
+    undecided |= !clear;
+    rejected |= clear && (beta * T < 0.f);     // a clear rejection by one endpoint stands whatever the other one says
   }
-  return r;
+  // (a clear |X0| rejection or endpoint rejection wins over "undecided": the FP64 formulas could only confirm it)
+  return rejected && (dd > 1e-12f) ? 0 : (undecided ? -1 : 1);
 }
 // FP64 value of T for the check statistics (same formula from the FP64 line equations)
 __device__ __forceinline__ double gate64_T(const LineMatchView& v, const float* s1, const double* l1, const double* l2, int e) {
