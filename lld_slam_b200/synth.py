@@ -584,7 +584,7 @@ def make_tri_search_batch(n_pairs, n_kp, seed, n_nodes=300, only_stereo=0, check
         return ids.astype(np.int32), np.cumsum(cnt), order.astype(np.int32)
 
     for pr in range(n_pairs):
-        N = n_kp
+        N = int(n_kp[pr]) if np.ndim(n_kp) else n_kp          # a list gives ragged pairs (0 = a pair without keypoints)
         X = np.stack([rng.uniform(-10, 10, N), rng.uniform(-3, 3, N), rng.uniform(5, 40, N)], 1)
         yaw = rng.normal(0, 0.03)
         R21 = _rot_y(np.array(yaw))                          # camera 1 -> camera 2
@@ -596,7 +596,7 @@ def make_tri_search_batch(n_pairs, n_kp, seed, n_nodes=300, only_stereo=0, check
         p1 = proj(X) + rng.normal(0, 0.4, (N, 2))
         p2 = proj(X2) + rng.normal(0, 0.4, (N, 2))
         unrel = rng.random(N) < 0.15
-        p2[unrel] = np.stack([rng.uniform(0, IMG_W, unrel.sum()), rng.uniform(0, IMG_H, unrel.sum())], 1)
+        p2[unrel] = np.stack([rng.uniform(0, IMG_W, unrel.sum()), rng.uniform(0, IMG_H, unrel.sum())], 1).reshape(-1, 2)
         perm = rng.permutation(N)                            # keyframe 2 stores its keypoints in another order
         tx = np.array([[0, -t21[2], t21[1]], [t21[2], 0, -t21[0]], [-t21[1], t21[0], 0]])
         F12 = (Ki.T @ (tx @ R21).T @ Ki)                     # x1' F12 x2 = 0
@@ -604,7 +604,8 @@ def make_tri_search_batch(n_pairs, n_kp, seed, n_nodes=300, only_stereo=0, check
         C2 = t21                                             # camera centre of keyframe 1 in camera 2
         epis.append([g["fx"] * C2[0] / C2[2] + g["cx"], g["fy"] * C2[1] / C2[2] + g["cy"]])
         d1 = rng.integers(0, 256, (N, 32), dtype=np.uint8)
-        d2 = np.where(unrel[:, None], rng.integers(0, 256, (N, 32), dtype=np.uint8), _flip_bits(d1[None], 0.06, rng)[0]).astype(np.uint8)
+        d2 = (np.where(unrel[:, None], rng.integers(0, 256, (N, 32), dtype=np.uint8), _flip_bits(d1[None], 0.06, rng)[0]).astype(np.uint8)
+              if N else d1.copy())
         node1 = rng.integers(0, n_nodes, N)
         node2 = np.where(rng.random(N) < 0.9, node1, rng.integers(0, n_nodes, N))
         ang1 = rng.uniform(0, 360, N); ang2 = (ang1 + rng.normal(3, 4, N) + np.where(rng.random(N) < 0.1, rng.uniform(0, 360, N), 0)) % 360

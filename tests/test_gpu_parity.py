@@ -639,6 +639,18 @@ def test_bow_search(gpu_ctx, strict):
         assert int(o["n_matches"].sum()) > 64 * 300
 
 
+def test_feature_vector_searches_ragged_pairs(gpu_ctx):
+    """SearchForTriangulation and SearchByBoW on a batch of pairs of different sizes, one of them without keypoints and one with
+    a single keypoint"""
+    sizes = [300, 0, 1200, 1, 37]
+    p = synth.make_tri_search_batch(len(sizes), sizes, 801)
+    g = api.tri_search(p, impl="gpu", ctx=gpu_ctx); o = api.tri_search(p, impl="oracle")
+    assert np.array_equal(g["match12"], o["match12"]) and np.array_equal(g["n_matches"], o["n_matches"]) and o["n_matches"][2] > 200
+    b = synth.make_bow_search_batch(len(sizes), sizes, 802, n_nodes=40)
+    g = api.bow_search(b, impl="gpu", ctx=gpu_ctx); o = api.bow_search(b, impl="oracle")
+    assert np.array_equal(g["match12"], o["match12"]) and np.array_equal(g["n_matches"], o["n_matches"]) and o["n_matches"][2] > 200
+
+
 def test_temporal_line_association(gpu_ctx):
     """SURVEY §8(f) row 3, Tracking::AddLinesFrom: reprojection gates in both images, descriptor argmin with first-wins ties,
     sequential claims; index-exact against the oracle, ragged frames, more candidates than lanes"""
