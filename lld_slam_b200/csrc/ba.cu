@@ -146,6 +146,7 @@ struct BaHost {
   std::vector<BaDenseJob> jobs;
   pvec<int> ch_g, ch_begin, ch_end, ch_seg0, seg_begin, seg_end, g_chp0, g_chl0;
   pvec<long long> ch_S_off;
+  pvec<int> pl_tab, ll_tab;   // sparse-mode position tables (hundreds of MB in global BA: kept page-locked across calls)
   // persistent worker threads for the per-window loops
   std::vector<std::thread> workers;
   std::mutex mu;
@@ -485,7 +486,8 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         }
       }
     } else {  // FNV-1a over the sorted block list; segments are verified exactly below, the key only orders
-      std::vector<int> gs;
+      static thread_local std::vector<int> gs;   // (one allocation per worker thread, not one per landmark)
+      gs.clear();
       for (int e = off[i]; e < off[i + 1]; e++)
         if (kf_g[ekf[e]] >= 0) gs.push_back(kf_g[ekf[e]]);
       std::sort(gs.begin(), gs.end());
@@ -524,8 +526,28 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
         }
         for (int i = b; i < e; i++) order[i] = b + (int)(src[i - b] & 0xffffffffu);
       } else {
-        for (int i = b; i < e; i++) order[i] = i;
-        std::stable_sort(order.begin() + b, order.begin() + e, [&](int x, int y) { return key[x] < key[y]; });
+        // 64-bit keys (hash of the block list): stable LSD radix sort of (key, index) pairs, 11 bits per pass -- the same
+        // order as a stable sort by key, several times faster on the 300 k landmarks of a global problem
+        const int m = e - b;
+        static thread_local std::vector<uint64_t> kk, kt;
+        static thread_local std::vector<int> ii, it;
+        if ((int)kk.size() < m) { kk.resize((size_t)m); kt.resize((size_t)m); ii.resize((size_t)m); it.resize((size_t)m); }
+        for (int i = 0; i < m; i++) { kk[i] = key[b + i]; ii[i] = b + i; }
+        uint64_t* ks = kk.data(); uint64_t* kd = kt.data();
+        int* is = ii.data(); int* id = it.data();
+        const int RB = 11;
+        for (int sh = 0; sh < 64; sh += RB) {
+          std::vector<int> cnt((1 << RB) + 1, 0);
+          for (int i = 0; i < m; i++) cnt[((ks[i] >> sh) & ((1u << RB) - 1)) + 1]++;
+          if (cnt[1] == m) continue;   // every key has a zero digit here
+          for (int q = 0; q < (1 << RB); q++) cnt[q + 1] += cnt[q];
+          for (int i = 0; i < m; i++) {
+            const int pos = cnt[(ks[i] >> sh) & ((1u << RB) - 1)]++;
+            kd[pos] = ks[i]; id[pos] = is[i];
+          }
+          std::swap(ks, kd); std::swap(is, id);
+        }
+        for (int i = 0; i < m; i++) order[b + i] = is[i];
       }
     };
     sort_by_key(p->pt_off, p->pt_obs_off, pe_kf, pt_key, pt_order);
@@ -584,12 +606,41 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     }
     keys_ready = true;
   }
-  par_for(nw, [&](int w) {
-    if (!keys_ready && !ids_window(w)) return;   // malformed window: rejected below, nothing else may index with its ids
-    sort_window(w);
-    count_window(w, p->pt_off, p->pt_obs_off, pe_kf, pl_off);
-    count_window(w, p->ln_off, p->ln_obs_off, lc_kf, ll_off);
-  });
+  // single large window: the two signature sorts run side by side, and the keyframe lists are a parallel counting sort over
+  // ranges of the signature order (per-range counters, prefix over the ranges, private cursors: the same lists as the serial fill)
+  const bool big_single = keys_ready;
+  const int LP = 64;   // ranges
+  std::vector<int> cnt_pt, cnt_ln;
+  auto count_ranges = [&](int n_lm, const int* off, const pvec<int>& ekf, const pvec<int>& order, std::vector<int>& cntp) {
+    const int g0 = w_g0[0], nf = w_g0[1] - g0;
+    cntp.assign((size_t)LP * nf, 0);
+    par_for(LP, [&](int part) {
+      int* cn = cntp.data() + (size_t)part * nf;
+      for (int oi = (int)((long long)n_lm * part / LP); oi < (int)((long long)n_lm * (part + 1) / LP); oi++) {
+        const int i = order[oi];
+        for (int e = off[i]; e < off[i + 1]; e++)
+          if (kf_g[ekf[e]] >= 0) cn[kf_g[ekf[e]] - g0]++;
+      }
+    });
+  };
+  if (big_single) {
+    sort_window(0);
+    count_ranges(n_pt, p->pt_obs_off, pe_kf, pt_order, cnt_pt);
+    count_ranges(n_ln, p->ln_obs_off, lc_kf, ln_order, cnt_ln);
+    const int g0 = w_g0[0], nf = w_g0[1] - g0;
+    for (int j = 0; j < nf; j++) {
+      int sp = 0, sl = 0;
+      for (int part = 0; part < LP; part++) { sp += cnt_pt[(size_t)part * nf + j]; sl += cnt_ln[(size_t)part * nf + j]; }
+      pl_off[g0 + j + 1] = sp; ll_off[g0 + j + 1] = sl;
+    }
+  } else {
+    par_for(nw, [&](int w) {
+      if (!keys_ready && !ids_window(w)) return;   // malformed window: rejected below, nothing else may index with its ids
+      sort_window(w);
+      count_window(w, p->pt_off, p->pt_obs_off, pe_kf, pl_off);
+      count_window(w, p->ln_off, p->ln_obs_off, lc_kf, ll_off);
+    });
+  }
   if (bad_arg.load()) {
     snprintf(c->err, sizeof(c->err), "malformed problem: an observation names a keyframe outside the window, or a landmark has more than 254 observations (include/lldba.h, capacity limits)");
     return LLD_ERR_ARG;
@@ -608,10 +659,35 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   for (int g = 0; g < nG; g++) { pl_off[g + 1] += pl_off[g]; ll_off[g + 1] += ll_off[g]; }
   pl_edge.resize(std::max(pl_off[nG], 1)); ll_cell.resize(std::max(ll_off[nG], 1));
   pe_pos.resize(std::max(n_pe, 1)); lc_pos.resize(std::max(n_lc, 1));
-  par_for(nw, [&](int w) {
-    fill_window(w, p->pt_off, p->pt_obs_off, pe_kf, pt_order, pl_off, pl_edge, pe_pos);
-    fill_window(w, p->ln_off, p->ln_obs_off, lc_kf, ln_order, ll_off, ll_cell, lc_pos);
-  });
+  auto fill_ranges = [&](int n_lm, const int* off, const pvec<int>& ekf, const pvec<int>& order, std::vector<int>& cntp,
+                         const pvec<int>& l_off, pvec<int>& l_ref, pvec<int>& e_pos) {
+    const int g0 = w_g0[0], nf = w_g0[1] - g0;
+    for (int j = 0; j < nf; j++) {   // counters -> first list position of every (range, keyframe)
+      int run = l_off[g0 + j];
+      for (int part = 0; part < LP; part++) { const int c2 = cntp[(size_t)part * nf + j]; cntp[(size_t)part * nf + j] = run; run += c2; }
+    }
+    par_for(LP, [&](int part) {
+      int* cur = cntp.data() + (size_t)part * nf;
+      for (int oi = (int)((long long)n_lm * part / LP); oi < (int)((long long)n_lm * (part + 1) / LP); oi++) {
+        const int i = order[oi];
+        for (int e = off[i]; e < off[i + 1]; e++) {
+          const int g = kf_g[ekf[e]];
+          if (g < 0) { e_pos[e] = -1; continue; }
+          e_pos[e] = cur[g - g0];
+          l_ref[cur[g - g0]++] = e;
+        }
+      }
+    });
+  };
+  if (big_single) {
+    fill_ranges(n_pt, p->pt_obs_off, pe_kf, pt_order, cnt_pt, pl_off, pl_edge, pe_pos);
+    fill_ranges(n_ln, p->ln_obs_off, lc_kf, ln_order, cnt_ln, ll_off, ll_cell, lc_pos);
+  } else {
+    par_for(nw, [&](int w) {
+      fill_window(w, p->pt_off, p->pt_obs_off, pe_kf, pt_order, pl_off, pl_edge, pe_pos);
+      fill_window(w, p->ln_off, p->ln_obs_off, lc_kf, ln_order, ll_off, ll_cell, lc_pos);
+    });
+  }
   const int n_plist = pl_off[nG], n_llist = ll_off[nG];
   UP(tmp_i, pl_off.data(), nG + 1); v.pl_off = tmp_i;
   UP(tmp_i, pl_edge.data(), n_plist); v.pl_edge = tmp_i;
@@ -673,19 +749,27 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     snprintf(c->err, sizeof(c->err), "a keyframe is covisible with %d free keyframes; this implementation supports at most 170 (include/lldba.h, capacity limits)", S->max_nnb);
     return LLD_ERR_UNSUPPORTED;
   }
+  stage("neighbours");
   // position tables: per list entry and neighbour, the list position of the co-edge (or -1)
+  // The tables themselves (hundreds of MB in global BA) are filled on the DEVICE from arrays it has anyway (k_build_tab):
+  // the host only lays them out.  LLD_TAB_CHECK=1 also builds them here and compares after the device pass.
+  static const bool tab_check = getenv("LLD_TAB_CHECK") != nullptr;
   auto build_tab = [&](const pvec<int>& l_off, const pvec<int>& l_ref, const int* off, const pvec<int>& e_lm,
-                       const pvec<int>& ekf, const pvec<int>& e_pos, std::vector<long long>& t_off, std::vector<int>& tab) {
+                       const pvec<int>& ekf, const pvec<int>& e_pos, std::vector<long long>& t_off, pvec<int>& tab, long long* tot_out) {
     t_off.assign(std::max(nG, 1), 0);
     long long tot = 0;
     for (int g = 0; g < nG; g++) {
       t_off[g] = tot;
       tot += (long long)(l_off[g + 1] - l_off[g]) * (nb_off[g + 1] - nb_off[g]);
     }
-    tab.assign((size_t)std::max(tot, 1LL), -1);
+    *tot_out = tot;
+    if (!tab_check) return;
+    tab.resize((size_t)std::max(tot, 1LL));   // (no fill here: every worker initialises the rows it owns)
+    if (tot == 0) tab[0] = -1;
     par_for(nG, [&](int g) {
       const int nnb = nb_off[g + 1] - nb_off[g];
       const int* nbl = nb_g.data() + nb_off[g];
+      std::fill(tab.data() + t_off[g], tab.data() + t_off[g] + (long long)(l_off[g + 1] - l_off[g]) * nnb, -1);
       for (int i = l_off[g]; i < l_off[g + 1]; i++) {
         int* row = tab.data() + t_off[g] + (long long)(i - l_off[g]) * nnb;
         const int lm = e_lm[l_ref[i]];
@@ -699,7 +783,9 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     });
   };
   std::vector<long long> pl_tab_off(std::max(nG, 1), 0), ll_tab_off(std::max(nG, 1), 0);
-  std::vector<int> pl_tab(1, -1), ll_tab(1, -1);
+  auto& pl_tab = H.pl_tab; auto& ll_tab = H.ll_tab;
+  long long pl_tab_total = 0, ll_tab_total = 0;
+  if (dense) { pl_tab.resize(1); ll_tab.resize(1); pl_tab[0] = -1; ll_tab[0] = -1; }
   if (!dense) {
     // edge -> landmark owners: only these sparse-mode tables read them on the host (the device derives its own copy)
     par_for(nw, [&](int w) {
@@ -708,10 +794,10 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
       for (int i = p->ln_off[w]; i < p->ln_off[w + 1]; i++)
         for (int e = p->ln_obs_off[i]; e < p->ln_obs_off[i + 1]; e++) lc_ln[e] = i;
     });
-    build_tab(pl_off, pl_edge, p->pt_obs_off, pe_pt, pe_kf, pe_pos, pl_tab_off, pl_tab);
-    build_tab(ll_off, ll_cell, p->ln_obs_off, lc_ln, lc_kf, lc_pos, ll_tab_off, ll_tab);
+    build_tab(pl_off, pl_edge, p->pt_obs_off, pe_pt, pe_kf, pe_pos, pl_tab_off, pl_tab, &pl_tab_total);
+    build_tab(ll_off, ll_cell, p->ln_obs_off, lc_ln, lc_kf, lc_pos, ll_tab_off, ll_tab, &ll_tab_total);
   }
-  stage("neighbours + tabs");
+  stage("position tables");
   // dense-mode structures
   auto& pt_spos = H.pt_spos; auto& ln_spos = H.ln_spos; auto& pts_w0 = H.pts_w0; auto& lns_w0 = H.lns_w0;
   auto& pts_mask = H.pts_mask; auto& lns_mask = H.lns_mask;
@@ -952,34 +1038,68 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   auto& seg_begin = H.seg_begin; auto& seg_end = H.seg_end; auto& g_chp0 = H.g_chp0; auto& g_chl0 = H.g_chl0;
   ch_g.clear(); ch_begin.clear(); ch_end.clear(); ch_seg0.clear(); seg_begin.clear(); seg_end.clear();
   g_chp0.assign(nG + 1, 0); g_chl0.assign(nG + 1, 0);
-  auto build_chunks = [&](const pvec<int>& l_off, const std::vector<long long>& t_off, const std::vector<int>& tab,
-                          pvec<int>& g_c0) {
+  auto build_chunks = [&](const pvec<int>& l_off, const pvec<int>& l_ref, const int* off, const pvec<int>& e_lm,
+                          const pvec<int>& ekf, pvec<int>& g_c0) {
+    // A segment is a run of list entries whose table rows have the same -1 pattern, i.e. whose landmarks are seen by the same
+    // set of free blocks b >= g.  The sets are compared directly (a handful of ints per landmark), by the worker pool; the
+    // lists below are then appended in keyframe order.
+    std::vector<std::vector<int>> cuts;   // per keyframe: list positions i where a new segment starts
+    if (!dense) {
+      cuts.resize((size_t)nG);
+      par_for(nG, [&](int g) {
+        auto& cg = cuts[(size_t)g];
+        int sa[256], sb[256];
+        int na = 0;
+        auto collect = [&](int i, int* out) {
+          const int lm = e_lm[l_ref[i]];
+          int n = 0;
+          for (int e = off[lm]; e < off[lm + 1]; e++) {
+            const int b = kf_g[ekf[e]];
+            if (b >= g) out[n++] = b;
+          }
+          std::sort(out, out + n);
+          return n;
+        };
+        int* pa = sa;
+        int* pb = sb;
+        bool have_a = false;
+        for (int i = l_off[g] + 1; i < l_off[g + 1]; i++) {
+          // entries are in signature order: most neighbours observe the same keyframes in the same order -- then the sets
+          // are equal and nothing needs to be collected
+          const int la = e_lm[l_ref[i - 1]], lb = e_lm[l_ref[i]];
+          const int ea = off[la], eb = off[lb], n_e = off[la + 1] - ea;
+          if (n_e == off[lb + 1] - eb && std::equal(ekf.data() + ea, ekf.data() + ea + n_e, ekf.data() + eb)) continue;   // pa stays valid for la's set == lb's set
+          if (!have_a) na = collect(i - 1, pa);
+          const int nb2 = collect(i, pb);
+          if (nb2 != na || !std::equal(pa, pa + na, pb)) cg.push_back(i);
+          std::swap(pa, pb);
+          na = nb2;
+          have_a = true;
+        }
+      });
+    }
     for (int g = 0; g < nG; g++) {
       g_c0[g] = (int)ch_g.size();
-      const int nnb = nb_off[g + 1] - nb_off[g];
-      auto same = [&](int a, int b) {
-        const int* ra = tab.data() + t_off[g] + (long long)(a - l_off[g]) * nnb;
-        const int* rb = tab.data() + t_off[g] + (long long)(b - l_off[g]) * nnb;
-        for (int j = 0; j < nnb; j++)
-          if ((ra[j] < 0) != (rb[j] < 0)) return false;
-        return true;
-      };
+      size_t ci = 0;
       for (int b = l_off[g]; b < l_off[g + 1]; b += CH) {
         const int e = std::min(b + CH, l_off[g + 1]);
         ch_g.push_back(g); ch_begin.push_back(b); ch_end.push_back(e);
         ch_seg0.push_back((int)seg_begin.size());
         int s0 = b;
         if (dense) { seg_begin.push_back(b); seg_end.push_back(e); }
-        else
-          for (int i = b + 1; i <= e; i++)
-            if (i == e || !same(i - 1, i)) { seg_begin.push_back(s0); seg_end.push_back(i); s0 = i; }
+        else {
+          const auto& cg = cuts[(size_t)g];
+          while (ci < cg.size() && cg[ci] <= b) ci++;          // a cut at the chunk start is the chunk boundary itself
+          for (; ci < cg.size() && cg[ci] < e; ci++) { seg_begin.push_back(s0); seg_end.push_back(cg[ci]); s0 = cg[ci]; }
+          seg_begin.push_back(s0); seg_end.push_back(e);
+        }
       }
     }
     g_c0[nG] = (int)ch_g.size();
   };
-  build_chunks(pl_off, pl_tab_off, pl_tab, g_chp0);
+  build_chunks(pl_off, pl_edge, p->pt_obs_off, pe_pt, pe_kf, g_chp0);
   const int n_chp = (int)ch_g.size();
-  build_chunks(ll_off, ll_tab_off, ll_tab, g_chl0);
+  build_chunks(ll_off, ll_cell, p->ln_obs_off, lc_ln, lc_kf, g_chl0);
   const int n_ch = (int)ch_g.size();
   ch_seg0.push_back((int)seg_begin.size());
   v.n_chunks = n_ch;
@@ -1079,8 +1199,9 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
   UP(tmp_i, g_chl0.data(), nG + 1); v.g_chl0 = tmp_i;
   UP(tmp_i, nb_off.data(), nG + 1); v.nb_off = tmp_i;
   UP(tmp_i, nb_g.data(), nb_g.size()); v.nb_g = tmp_i;
-  UP(tmp_i, pl_tab.data(), pl_tab.size()); v.pl_tab = tmp_i;
-  UP(tmp_i, ll_tab.data(), ll_tab.size()); v.ll_tab = tmp_i;
+  int *d_pl_tab = nullptr, *d_ll_tab = nullptr;
+  DEV(d_pl_tab, int, std::max(pl_tab_total, 1LL)); v.pl_tab = d_pl_tab;
+  DEV(d_ll_tab, int, std::max(ll_tab_total, 1LL)); v.ll_tab = d_ll_tab;
   long long* tmp_l;
   UP(tmp_l, pl_tab_off.data(), nG); v.pl_tab_off = tmp_l;
   UP(tmp_l, ll_tab_off.data(), nG); v.ll_tab_off = tmp_l;
@@ -1212,6 +1333,27 @@ static int ba_upload(LldCtx* c, const lld_ba_problem* p, bool global_mode, int l
     if (n_ln) LLD_LAUNCH(c, k_expand_owner, grid(n_ln), 256, 0, n_ln, nw, v.ln_off, d_ln_win);
     if (n_pe) LLD_LAUNCH(c, k_expand_owner, grid(n_pe), 256, 0, n_pe, n_pt, v.pt_obs_off, d_pe_pt);
     if (n_lc) LLD_LAUNCH(c, k_expand_owner, grid(n_lc), 256, 0, n_lc, n_ln, v.ln_obs_off, d_lc_ln);
+    if (!v.dense_mode) {   // sparse-mode position tables (k_build_tab)
+      LLD_CUDA(c, cudaMemsetAsync(d_pl_tab, 0xFF, sizeof(int) * (size_t)std::max(pl_tab_total, 1LL), c->stream));
+      LLD_CUDA(c, cudaMemsetAsync(d_ll_tab, 0xFF, sizeof(int) * (size_t)std::max(ll_tab_total, 1LL), c->stream));
+      if (n_plist) LLD_LAUNCH(c, k_build_tab, grid(n_plist), 256, 0, n_plist, nG, v.pl_off, v.pl_edge, v.pt_obs_off, v.pe_pt, v.pe_kf, v.kf_g,
+                              v.pe_pos, v.nb_off, v.nb_g, v.pl_tab_off, d_pl_tab);
+      if (n_llist) LLD_LAUNCH(c, k_build_tab, grid(n_llist), 256, 0, n_llist, nG, v.ll_off, v.ll_cell, v.ln_obs_off, v.lc_ln, v.lc_kf, v.kf_g,
+                              v.lc_pos, v.nb_off, v.nb_g, v.ll_tab_off, d_ll_tab);
+      if (tab_check) {
+        std::vector<int> back((size_t)std::max(std::max(pl_tab_total, ll_tab_total), 1LL));
+        for (int which = 0; which < 2; which++) {
+          const long long tot = which ? ll_tab_total : pl_tab_total;
+          LLD_CUDA(c, cudaMemcpyAsync(back.data(), which ? d_ll_tab : d_pl_tab, sizeof(int) * (size_t)tot, cudaMemcpyDeviceToHost, c->stream));
+          LLD_CUDA(c, cudaStreamSynchronize(c->stream));
+          const pvec<int>& ref = which ? ll_tab : pl_tab;
+          long long bad = 0;
+          for (long long k = 0; k < tot; k++) bad += back[(size_t)k] != ref[(size_t)k];
+          fprintf(stderr, "[lld_ba_upload] LLD_TAB_CHECK %s table: %lld entries, %lld differ from the host build\n", which ? "line" : "point", tot, bad);
+          if (bad) { snprintf(c->err, sizeof(c->err), "device-built position table differs from the host build"); return LLD_ERR_CUDA; }
+        }
+      }
+    }
     if (v.dense_mode) {
       if (n_pe) LLD_LAUNCH(c, k_dense_wpos, grid(n_pe), 256, 0, n_pe, v.pe_pt, v.pe_kf, v.kf_g, v.pt_win, v.w_g0, v.pt_spos, v.pts_mask, v.pts_w0, d_pe_wpos);
       if (n_lc) LLD_LAUNCH(c, k_dense_wpos, grid(n_lc), 256, 0, n_lc, v.lc_ln, v.lc_kf, v.kf_g, v.ln_win, v.w_g0, v.ln_spos, v.lns_mask, v.lns_w0, d_lc_wpos);

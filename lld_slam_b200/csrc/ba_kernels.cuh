@@ -121,6 +121,38 @@ __global__ void k_expand_owner(int n_out, int n, const int* __restrict__ off, in
   out[e] = lo;
 }
 
+// Sparse-mode position tables: per list entry i of free block g (a point edge / line cell observed by g) and per neighbour block
+// nb_g[nb_off[g] + j] >= g, the list position of the same landmark's edge on that neighbour, or -1 (the table is pre-set to -1).
+// One thread per list entry: its block row by bisection in the list offsets, then the landmark's other edges.
+__global__ void k_build_tab(int n_list, int nG, const int* __restrict__ l_off, const int* __restrict__ l_ref, const int* __restrict__ off,
+                            const int* __restrict__ e_lm, const int* __restrict__ ekf, const int* __restrict__ kf_g,
+                            const int* __restrict__ e_pos, const int* __restrict__ nb_off, const int* __restrict__ nb_g,
+                            const long long* __restrict__ t_off, int* __restrict__ tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_list) return;
+  int lo = 0, hi = nG;   // largest g with l_off[g] <= i
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (l_off[mid] <= i) lo = mid;
+    else hi = mid;
+  }
+  const int g = lo, nnb = nb_off[g + 1] - nb_off[g];
+  const int* nbl = nb_g + nb_off[g];
+  int* row = tab + t_off[g] + (long long)(i - l_off[g]) * nnb;
+  const int lm = e_lm[l_ref[i]];
+  for (int e2 = off[lm]; e2 < off[lm + 1]; e2++) {
+    const int b = kf_g[ekf[e2]];
+    if (b < g) continue;
+    int a = 0, z = nnb;   // lower_bound of b in the neighbour list
+    while (a < z) {
+      const int mid = (a + z) >> 1;
+      if (nbl[mid] < b) a = mid + 1;
+      else z = mid;
+    }
+    row[a] = e_pos[e2];
+  }
+}
+
 // dense mode: the W blocks of a landmark are contiguous (first slot w0[sorted position]) and sorted by keyframe, so the
 // slot of an edge is w0 + the rank of its keyframe's block among the set bits of the landmark's mask; -1 = fixed keyframe
 __global__ void k_dense_wpos(int n_e, const int* __restrict__ e_lm, const int* __restrict__ e_kf, const int* __restrict__ kf_g,
