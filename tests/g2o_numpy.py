@@ -750,6 +750,33 @@ def local_bundle_adjustment(p, its1=5, its2=15):
     return out
 
 
+def bundle_adjustment(p, n_iter=10):
+    """Optimizer::BundleAdjustment src/Optimizer.cc:321-559 (GlobalBundleAdjustemnt :312-319): one optimize(nIterations) over every
+    keyframe, point and line; point edges robust only with bRobust (:411-416), line edges always (AddLineMinimalGlobal :217-219),
+    line endpoints K^-1-normalised (:234-235), no outlier gates, nothing removed."""
+    nw = int(p["n_win"])
+    st = n_iter + 2
+    out = dict(kf_Tcw=np.zeros((int(p["kf_off"][-1]), 12)), pt_xyz=np.zeros((int(p["pt_off"][-1]), 3)),
+               ln_x0_dir=np.zeros((int(p["ln_off"][-1]), 6)), pt_obs_bad=np.zeros(int(p["pt_obs_off"][-1]), np.uint8),
+               ln_obs_bad=np.zeros((int(p["ln_obs_off"][-1]), 2), np.uint8), ln_removed=np.zeros(int(p["ln_off"][-1]), np.uint8),
+               chi2_log=np.zeros((nw, st)), lambda_log=np.zeros((nw, st)), trials_log=np.zeros((nw, st), np.int32),
+               n_iter_done=np.zeros((nw, 2), np.int32))
+    for w in range(nw):
+        G = LocalBAGraph(p, w)
+        it = G.optimize(n_iter) if G.initialize_optimization(0) else 0
+        for k in range(G.nk):
+            out["kf_Tcw"][G.k0 + k] = G.kf[k].to_Rt12()
+        out["pt_xyz"][G.p0:G.p0 + G.np_] = G.pts
+        if G.nl:
+            R = line_R(G.ln_q)
+            out["ln_x0_dir"][G.l0:G.l0 + G.nl] = np.concatenate([G.ln_alpha[:, None] * R[:, :, 1], R[:, :, 0]], axis=1)
+        out["chi2_log"][w, :min(len(G.chi2_log), st)] = G.chi2_log[:st]
+        out["lambda_log"][w, :len(G.lambda_log)] = G.lambda_log
+        out["trials_log"][w, :len(G.trials_log)] = G.trials_log
+        out["n_iter_done"][w] = (it, 0)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Optimizer::PoseOptimization  src/Optimizer.cc:653-932 (+ AddLineMinOnlyPose :562-650)
 # ------------------------------------------------------------------------------------------------------------------

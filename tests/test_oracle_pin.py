@@ -1,6 +1,7 @@
 """Pins the CPU oracle (oracle/liblld_oracle.so) against tests/g2o_numpy.py, an independent numpy transcription of the
 reference's LocalBundleAdjustment (src/Optimizer.cc:936-1388, LineOptimizer.cc, block_solver.hpp:354-486,
-optimization_algorithm_levenberg.cpp:61-189) and PoseOptimization (src/Optimizer.cc:653-932).  The reference holds no test
+optimization_algorithm_levenberg.cpp:61-189), BundleAdjustment (src/Optimizer.cc:321-559) and PoseOptimization
+(src/Optimizer.cc:653-932).  The reference holds no test
 vectors and cannot be built here (no Eigen / OpenCV headers), so two separately written restatements that share no code,
 no data layout and no summation order are the strongest pin available.
 
@@ -73,6 +74,19 @@ def test_local_ba_stereo_path(seed, shape):
 def test_local_ba_batch_of_windows_and_flat_schedule():
     p = _mono(synth.make_local_ba_batch(3, 4, 80, 20, 17))
     _compare_ba(G.local_bundle_adjustment(p, 10, 0), api.ba_local(p, 10, 0, impl="oracle"), 1e-9, 1e-9)
+
+
+@pytest.mark.parametrize("seed,shape,robust", [(31, (10, 250, 50), False), (32, (14, 300, 60), True), (33, (8, 200, 25), False)])
+def test_global_bundle_adjustment_agrees(seed, shape, robust):
+    """Optimizer::BundleAdjustment: one 10-iteration optimise over all keyframes / points / lines, K^-1-normalised line endpoints,
+    Huber on the points only with bRobust: mono variant to 1e-9 (FP64 path), stereo variant to the 1e-6 of the float invz.
+    (Every case keeps some lines: their second camera fixes the scale that an all-monocular point problem leaves free.)"""
+    p = synth.make_global_ba(*shape, seed, robust_points=robust)
+    for q, chi_tol, pose_tol in ((_mono(p), 1e-9, 1e-9), (p, 1e-6, 1e-5)):
+        n = G.bundle_adjustment(q, 10)
+        o = api.ba_global(q, 10, impl="oracle")
+        _compare_ba(n, o, chi_tol, pose_tol)
+        assert n["n_iter_done"][0, 0] >= 3
 
 
 @pytest.mark.parametrize("seed,shape", [(21, (6, 200, 40)), (22, (4, 60, 0)), (23, (5, 5, 30)), (24, (3, 400, 80))])
