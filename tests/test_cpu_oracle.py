@@ -837,3 +837,286 @@ def test_oracle_bow_search_against_python(built, strict):
     assert int(o["n_matches"].sum()) > 150
     m = o["match12"][o["match12"] >= 0]           # a side-2 keypoint is matched at most once per pair
     assert len(np.unique(m + 100000 * np.repeat(np.arange(2), 500)[o["match12"] >= 0])) == len(m)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the two Frame-level SearchByProjection variants, pinned by plain-Python transcriptions
+# ------------------------------------------------------------------------------------------------------------------
+class _PyGrid:
+    """Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea (src/Frame.cc:294-309, 391-456) in float32, dictionary of cells"""
+
+    def __init__(self, g, xy):
+        f = np.float32
+        self.minx, self.miny = f(g["min_x"]), f(g["min_y"])
+        self.winv = f(64) / (f(g["max_x"]) - self.minx)
+        self.hinv = f(48) / (f(g["max_y"]) - self.miny)
+        self.xy = xy
+        self.cells = {}
+        for i in range(len(xy)):
+            px = int(np.round((xy[i, 0] - self.minx) * self.winv)); py = int(np.round((xy[i, 1] - self.miny) * self.hinv))
+            if 0 <= px < 64 and 0 <= py < 48:
+                self.cells.setdefault((px, py), []).append(i)
+
+    def area(self, x, y, r, min_level, max_level, octv):
+        x0 = max(0, int(np.floor((x - self.minx - r) * self.winv)))
+        x1 = min(63, int(np.ceil((x - self.minx + r) * self.winv)))
+        y0 = max(0, int(np.floor((y - self.miny - r) * self.hinv)))
+        y1 = min(47, int(np.ceil((y - self.miny + r) * self.hinv)))
+        if x0 >= 64 or x1 < 0 or y0 >= 48 or y1 < 0:
+            return []
+        check = min_level > 0 or max_level >= 0
+        out = []
+        for ix in range(x0, x1 + 1):
+            for iy in range(y0, y1 + 1):
+                for idx in self.cells.get((ix, iy), ()):
+                    if check:
+                        if int(octv[idx]) < min_level:
+                            continue
+                        if max_level >= 0 and int(octv[idx]) > max_level:
+                            continue
+                    if abs(self.xy[idx, 0] - x) < r and abs(self.xy[idx, 1] - y) < r:
+                        out.append(idx)
+        return out
+
+
+def _three_maxima(sizes):
+    m1 = m2 = m3 = 0; i1 = i2 = i3 = -1
+    for i, s_ in enumerate(sizes):
+        if s_ > m1:
+            m3, m2, m1 = m2, m1, s_; i3, i2, i1 = i2, i1, i
+        elif s_ > m2:
+            m3, m2 = m2, s_; i3, i2 = i2, i
+        elif s_ > m3:
+            m3, i3 = s_, i
+    if m2 < 0.1 * m1:
+        i2 = i3 = -1
+    elif m3 < 0.1 * m1:
+        i3 = -1
+    return i1, i2, i3
+
+
+def _ham(a, b):
+    return int(np.unpackbits(np.bitwise_xor(a, b)).sum())
+
+
+def _sbp_frame_python(p):
+    """ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) src/ORBmatcher.cc:1328-1470: cv::Mat float products as
+    double-accumulating gemms rounded once, everything else float32 in source order"""
+    f, f64 = np.float32, np.float64
+    g = p["geom"]
+    fx, fy, cx, cy, bf, b = (f(g[k]) for k in ("fx", "fy", "cx", "cy", "bf", "b"))
+    sf = np.asarray(g["scale_factors"], f)
+    nq = int(p["last_off"][-1])
+    best_idx = np.full(nq, -1, np.int32); best_dist = np.full(nq, 256, np.int32)
+    match = np.full(int(p["cur_off"][-1]), -1, np.int32); nm = np.zeros(p["n_pairs"], np.int32)
+    for pr in range(p["n_pairs"]):
+        c0, c1 = int(p["cur_off"][pr]), int(p["cur_off"][pr + 1]); l0, l1 = int(p["last_off"][pr]), int(p["last_off"][pr + 1])
+        xy = p["cur_xy"][c0:c1]; octv = p["cur_octave"][c0:c1]
+        G = _PyGrid(g, xy)
+        Tc = p["cur_Tcw"][pr]; Tl = p["last_Tcw"][pr]
+        Rcw = Tc[:9].reshape(3, 3).astype(f64); tcw = Tc[9:].astype(f64)
+        Rlw = Tl[:9].reshape(3, 3).astype(f64); tlw = Tl[9:].astype(f64)
+        twc = (-(Rcw.T @ tcw)).astype(f)
+        tlc = (Rlw @ twc.astype(f64) + tlw).astype(f)
+        fwd = bool(tlc[2] > b) and not p["mono"]
+        bwd = bool(-tlc[2] > b) and not p["mono"]
+        claimed = p["cur_claimed"][c0:c1].astype(bool).copy()
+        m = np.full(c1 - c0, -1, np.int32)
+        hist = [[] for _ in range(30)]
+        n = 0
+        for i in range(l1 - l0):
+            q = l0 + i
+            if not p["last_valid"][q]:
+                continue
+            pc = (Rcw @ p["last_xw"][q].astype(f64) + tcw).astype(f)
+            invz = f(f64(1.0) / f64(pc[2]))
+            if invz < 0 and not p.get("allow_negative_depth", 0):
+                continue
+            u = f(f(fx * pc[0]) * invz) + cx; v = f(f(fy * pc[1]) * invz) + cy
+            if u < f(g["min_x"]) or u > f(g["max_x"]) or v < f(g["min_y"]) or v > f(g["max_y"]):
+                continue
+            lo = int(p["last_octave"][q])
+            r = f(p["th"]) * sf[lo]
+            if fwd:
+                cand = G.area(u, v, r, lo, -1, octv)
+            elif bwd:
+                cand = G.area(u, v, r, 0, lo, octv)
+            else:
+                cand = G.area(u, v, r, lo - 1, lo + 1, octv)
+            bd, bi = 256, -1
+            for i2 in cand:
+                if claimed[i2]:
+                    continue
+                if p["cur_uright"][c0 + i2] > 0:
+                    ur = u - f(bf * invz)
+                    if abs(ur - p["cur_uright"][c0 + i2]) > r:
+                        continue
+                d = _ham(p["last_desc"][q], p["cur_desc"][c0 + i2])
+                if d < bd:
+                    bd, bi = d, i2
+            th_high = p.get("th_high", 0) or 100
+            if bd <= th_high:
+                m[bi] = i
+                if p["last_has_obs"][q]:
+                    claimed[bi] = True
+                n += 1
+                best_idx[q] = bi; best_dist[q] = bd
+                if p["check_orientation"]:
+                    rot = p["last_angle"][q] - p["cur_angle"][c0 + bi]
+                    if rot < 0:
+                        rot = f(rot + f(360))
+                    b_ = int(np.floor(float(f(rot * f(1.0 / 30))) + 0.5))
+                    hist[0 if b_ == 30 else b_].append(bi)
+        if p["check_orientation"]:
+            keep = _three_maxima([len(h) for h in hist])
+            for i in range(30):
+                if i not in keep:
+                    for j in hist[i]:
+                        m[j] = -1; n -= 1
+        match[c0:c1] = m; nm[pr] = n
+    return dict(match=match, n_matches=nm, best_idx=best_idx, best_dist=best_dist)
+
+
+def _sbp_mappoints_python(p):
+    """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) src/ORBmatcher.cc:45-129"""
+    f = np.float32
+    g = p["geom"]
+    sf = np.asarray(g["scale_factors"], f)
+    nq = int(p["mp_off"][-1])
+    best_idx = np.full(nq, -1, np.int32); best_dist = np.full(nq, 256, np.int32)
+    match = np.full(int(p["cur_off"][-1]), -1, np.int32); nm = np.zeros(p["n_pairs"], np.int32)
+    for pr in range(p["n_pairs"]):
+        c0, c1 = int(p["cur_off"][pr]), int(p["cur_off"][pr + 1])
+        xy = p["cur_xy"][c0:c1]; octv = p["cur_octave"][c0:c1]
+        G = _PyGrid(g, xy)
+        claimed = p["cur_claimed"][c0:c1].astype(bool).copy()
+        m = np.full(c1 - c0, -1, np.int32)
+        n = 0
+        for q in range(int(p["mp_off"][pr]), int(p["mp_off"][pr + 1])):
+            if not p["mp_valid"][q]:
+                continue
+            lvl = int(p["mp_level"][q])
+            r = f(2.5) if float(p["mp_viewcos"][q]) > 0.998 else f(4.0)
+            if p["th"] != 1.0:
+                r = f(r * f(p["th"]))
+            u, v, ur = (f(x) for x in p["mp_proj"][q])
+            rs = f(r * sf[lvl])
+            cand = G.area(u, v, rs, lvl - 1, lvl, octv)
+            bd = bd2 = 256; bl = bl2 = -1; bi = -1
+            for idx in cand:
+                if claimed[idx]:
+                    continue
+                if p["cur_uright"][c0 + idx] > 0:
+                    if abs(ur - p["cur_uright"][c0 + idx]) > f(r * sf[lvl]):
+                        continue
+                d = _ham(p["mp_desc"][q], p["cur_desc"][c0 + idx])
+                if d < bd:
+                    bd2, bd = bd, d; bl2, bl = bl, int(octv[idx]); bi = idx
+                elif d < bd2:
+                    bl2 = int(octv[idx]); bd2 = d
+            if bd <= 100:
+                if bl == bl2 and bd > f(p["nn_ratio"]) * f(bd2):
+                    continue
+                m[bi] = q - int(p["mp_off"][pr])
+                if p["mp_has_obs"][q]:
+                    claimed[bi] = True
+                n += 1
+                best_idx[q] = bi; best_dist[q] = bd
+        match[c0:c1] = m; nm[pr] = n
+    return dict(match=match, n_matches=nm, best_idx=best_idx, best_dist=best_dist)
+
+
+def test_oracle_sbp_frame_against_python(built):
+    from lld_slam_b200 import api, synth
+    p = synth.make_sbp_frame_batch(5, 400, 51)          # forward / backward / static pairs
+    o = api.sbp_frame(p, impl="oracle"); r = _sbp_frame_python(p)
+    for k in ("match", "n_matches", "best_idx", "best_dist"):
+        assert np.array_equal(o[k], r[k]), k
+    assert int(o["n_matches"].sum()) > 400
+    q = dict(p); q["mono"] = 1; q["th_high"] = 30; q["allow_negative_depth"] = 1     # the relocalisation variant (:1472-1599)
+    q["cur_uright"] = np.full_like(p["cur_uright"], -1.0); q["last_has_obs"] = np.ones_like(p["last_has_obs"])
+    o = api.sbp_frame(q, impl="oracle"); r = _sbp_frame_python(q)
+    for k in ("match", "n_matches", "best_idx", "best_dist"):
+        assert np.array_equal(o[k], r[k]), k
+
+
+def test_oracle_sbp_mappoints_against_python(built):
+    from lld_slam_b200 import api, synth
+    p = synth.make_sbp_mp_batch(4, 500, 400, 53)
+    o = api.sbp_mappoints(p, impl="oracle"); r = _sbp_mappoints_python(p)
+    for k in ("match", "n_matches", "best_idx", "best_dist"):
+        assert np.array_equal(o[k], r[k]), k
+    assert int(o["n_matches"].sum()) > 300
+
+
+def _line_match_numpy(p):
+    """TwoFrameLineMatcher::MatchLines / CheckLinePair (src/TwoFrameLineMatcher.cc:26-124) with vgl::TriangulateLine (src/vgl.cc:78-108),
+    ReprojectKeyLineTo3D (src/LineMatching.cc:277-291), vgl::ReprojectLinePointTo3D (src/vgl.cc:336-346) and NormalizedLineEquation
+    (:578-585), written with numpy's own solvers (np.linalg.solve for the 3x3 system, np.linalg.lstsq for the 3x2 one) where the
+    reference uses colPivHouseholderQr -- the oracle uses closed forms, so the two only share the formulas.  T = I, T_right = T with
+    t + R (b, 0, 0) (GetTForRight, src/LineMatching.cc:228-237); descriptor distance = L2 norm of the float rows (the oracle's definition
+    of the un-vendored LBDMOD function)."""
+    K = np.asarray(p["K"], np.float64).reshape(3, 3)
+    b = float(p["baseline"]); tau = float(p["tau"]); min_len = float(p["min_line_length"])
+    n_left = int(p["left_off"][-1])
+    match = np.full(n_left, -1, np.int32); dist = np.full(n_left, np.inf, np.float32)
+
+    def leq(seg):
+        l = K.T @ np.cross(np.array([seg[0], seg[1], 1.0]), np.array([seg[2], seg[3], 1.0]))
+        return l / np.linalg.norm(l[:2])
+
+    def length(seg):
+        return float(np.hypot(float(seg[0]) - float(seg[2]), float(seg[1]) - float(seg[3])))
+
+    t2 = np.array([b, 0.0, 0.0])
+    for pr in range(int(p["n_pairs"])):
+        a0, a1 = int(p["left_off"][pr]), int(p["left_off"][pr + 1]); b0, b1 = int(p["right_off"][pr]), int(p["right_off"][pr + 1])
+        L = [leq(p["left_seg"][i].astype(np.float64)) for i in range(a0, a1)]
+        R = [leq(p["right_seg"][i].astype(np.float64)) for i in range(b0, b1)]
+        taken = np.zeros(b1 - b0, bool)
+        for j in range(a1 - a0):
+            s1 = p["left_seg"][a0 + j].astype(np.float64)
+            min_d, min_j = np.finfo(np.float64).max, -1
+            for oi in range(b1 - b0):
+                if taken[oi]:
+                    continue
+                if int(p["left_octave"][a0 + j]) != int(p["right_octave"][b0 + oi]):
+                    continue
+                if length(s1) < min_len or length(p["right_seg"][b0 + oi]) < min_len:
+                    continue
+                n1, n2 = L[j], R[oi]
+                if abs(n1 @ n2) / np.linalg.norm(n1) / np.linalg.norm(n2) > 0.975:
+                    continue
+                d = np.cross(n1, n2); d = d / np.linalg.norm(d)
+                M = np.stack([n1, n2, d]); rhs = np.array([0.0, n2 @ t2, 0.0])
+                if np.linalg.matrix_rank(M) < 3:
+                    continue
+                X0 = np.linalg.solve(M, rhs)
+                if np.linalg.norm(X0) < 0.5:
+                    continue
+                ok = True
+                for px, py in ((s1[0], s1[1]), (s1[2], s1[3])):
+                    A = np.stack([np.array([px, py, 1.0]), -(K @ d)], 1)
+                    sol = np.linalg.lstsq(A, K @ X0, rcond=None)[0]
+                    if (X0 + sol[1] * d)[2] < 0:
+                        ok = False
+                if not ok:
+                    continue
+                df = p["left_desc"][a0 + j].astype(np.float64) - p["right_desc"][b0 + oi].astype(np.float64)
+                dd = float(np.sqrt(df @ df))
+                if dd < min_d and dd < tau:
+                    min_d, min_j = dd, oi
+            if min_j >= 0:
+                taken[min_j] = True
+                dist[a0 + j] = np.float32(min_d)
+            match[a0 + j] = min_j
+    return dict(match=match, dist=dist)
+
+
+def test_oracle_line_match_against_numpy(built):
+    from lld_slam_b200 import api, synth
+    p = synth.make_line_match_batch(2, 120, 32, 61)
+    o = api.line_match(p, impl="oracle"); r = _line_match_numpy(p)
+    assert np.array_equal(o["match"], r["match"]) and (o["match"] >= 0).sum() > 40
+    fin = np.isfinite(r["dist"])
+    assert np.array_equal(np.isfinite(o["dist"]), fin) and np.abs(o["dist"][fin] - r["dist"][fin]).max() <= 1e-6
