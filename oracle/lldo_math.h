@@ -2,10 +2,13 @@
 // and bench.py's cpu_baseline / --impl reference legs may build, load or call anything under oracle/.
 //
 // CPU restatement of the LLD-SLAM point+line BA / matching arithmetic (dependency-free C++17).
-// PARITY UNPINNED by reference tests: the reference ships no tests or golden vectors and
-// cannot be compiled here (Eigen / OpenCV / LBDMOD absent).  The oracle is pinned only by the in-tree
-// source it follows (cited per function, paths relative to the reference root) and by its own
-// self-checks in tests/ (numeric Jacobians, numpy dense solves, cv2 Hamming).
+// PARITY UNPINNED by reference tests or reference outputs: the reference ships no tests or golden vectors
+//  and cannot be compiled here (Eigen / OpenCV / LBDMOD absent).  What pins the oracle instead:
+// the in-tree source it follows (cited per function, paths relative to the reference root) and, for every
+// entry point, an independent second transcription of the same reference code in numpy / plain Python that it
+// must reproduce (tests/g2o_numpy.py + tests/test_oracle_pin.py for LocalBundleAdjustment, BundleAdjustment and
+// PoseOptimization; tests/test_cpu_oracle.py for the matchers, ComputeStereoMatches, AddLinesFrom and the medoid
+// rule), plus numeric Jacobians, numpy dense solves and cv2 Hamming.  DESIGN.md §2.
 //
 // Small fixed-size linear algebra restating the Eigen 3.x conventions the reference relies on
 // (Eigen itself is not vendored in the reference).

@@ -2,9 +2,9 @@
 //
 // CPU restatement of Frame::ComputeStereoMatches (src/Frame.cc:530-704), SURVEY.md §8(f) row 1: row-banded Hamming
 // stereo matching of ORB keypoints + 11x11 SAD sliding refinement + parabola fit + median distance gate.
-// It is here AHEAD of the product kernel (planned for the next round) so that the kernel is written against a pinned
-// checker: tests/test_cpu_oracle.py compares it with an independent numpy / cv2 transcription (cv2.norm NORM_L1 for the
-// patch distance, cv2.NORM_HAMMING for the descriptor distance).
+// It checks lld_slam_b200/csrc/stereo.cu (bit-exact mvuRight / mvDepth) and is itself pinned: tests/test_cpu_oracle.py compares
+// it with an independent numpy / cv2 transcription (cv2.norm NORM_L1 for the patch distance, cv2.NORM_HAMMING for the
+// descriptor distance).
 //
 // Reference undefined behaviour that the oracle resolves (each is a `continue`, i.e. "no stereo match for this point"):
 //  * vRowIndices[yi] is indexed without a range check (src/Frame.cc:555): rows outside the image are skipped here;
